@@ -1,0 +1,257 @@
+"""hifir_b200 -- B200 (sm_100a) device backend for HIFIR's preconditioner-application hot path.
+
+The product is the C-ABI shared library ``hifir_b200/_lib/libhifir_b200.so``
+(``include/hifir_b200.h``), built from the hand-written CUDA in ``hifir_b200/csrc``.
+This module is only the ctypes harness the Python tests / bench use to reach that
+C-ABI; it contains no numerical code and NO fallback: if the library is missing
+every entry point raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+__version__ = "0.1.0"
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_lib", "libhifir_b200.so")
+
+LHF_SUCCESS, LHF_NULL_OBJ, LHF_MISMATCHED_SIZES, LHF_BAD_PREC, LHF_HIFIR_ERROR = range(5)
+LHF_S, LHF_SH, LHF_M, LHF_MH = range(4)
+LHF_DEFAULT_RANK = -2
+FULL_RANK = (1 << 64) - 1  # size_t(-1)
+
+STAT_NAMES = ("levels", "n", "nnz", "dense_n", "dense_rank", "bytes_factors", "bytes_vec_per_rhs",
+              "bytes_dense", "device_bytes", "kernels_per_apply", "depth_total", "launch_count")
+
+
+class LhfdGpuCcs(C.Structure):
+    _fields_ = [("nrows", C.c_size_t), ("ncols", C.c_size_t), ("col_start", C.c_void_p),
+                ("row_ind", C.c_void_p), ("vals", C.c_void_p)]
+
+
+class LhfdGpuLevel(C.Structure):
+    _fields_ = [("m", C.c_size_t), ("n", C.c_size_t), ("L_B", LhfdGpuCcs), ("d_B", C.c_void_p),
+                ("U_B", LhfdGpuCcs), ("E", LhfdGpuCcs), ("F", LhfdGpuCcs), ("s", C.c_void_p),
+                ("t", C.c_void_p), ("p", C.c_void_p), ("p_inv", C.c_void_p), ("q", C.c_void_p),
+                ("q_inv", C.c_void_p), ("dense_n", C.c_size_t), ("dense_rank", C.c_size_t),
+                ("qr_mat", C.c_void_p), ("qr_tau", C.c_void_p), ("qr_jpvt", C.c_void_p),
+                ("has_symm_dense", C.c_int)]
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None and a.size else None
+
+
+def make_level_structs(levels):
+    """Describe per-level factors (list of dicts, the layout produced by the factor producer:
+    CCS blocks 'L','U','E','F' = (nrows, ncols, col_start[int64], row_ind[int32], vals[f64]),
+    'd','s','t','p','p_inv','q','q_inv', optional 'qr_mat','qr_tau','qr_jpvt','dense_n',
+    'dense_rank') as a ctypes LhfdGpuLevel array.  Returns (array, keepalive)."""
+    arr = (LhfdGpuLevel * len(levels))()
+    keep = []
+
+    def ccs(block):
+        nr, nc, cs, ri, va = block
+        cs = np.ascontiguousarray(cs, dtype=np.int64)
+        ri = np.ascontiguousarray(ri, dtype=np.int32)
+        va = np.ascontiguousarray(va, dtype=np.float64)
+        keep.extend((cs, ri, va))
+        return LhfdGpuCcs(nr, nc, _ptr(cs), _ptr(ri), _ptr(va))
+
+    def vec(a, dt):
+        a = np.ascontiguousarray(a, dtype=dt)
+        keep.append(a)
+        return _ptr(a)
+
+    for k, L in enumerate(levels):
+        s = arr[k]
+        s.m, s.n = L["m"], L["n"]
+        s.L_B, s.U_B, s.E, s.F = ccs(L["L"]), ccs(L["U"]), ccs(L["E"]), ccs(L["F"])
+        s.d_B = vec(L["d"], np.float64)
+        s.s, s.t = vec(L["s"], np.float64), vec(L["t"], np.float64)
+        for nm in ("p", "p_inv", "q", "q_inv"):
+            setattr(s, nm, vec(L[nm], np.int32) if L.get(nm) is not None else None)
+        s.dense_n = int(L.get("dense_n", 0))
+        s.dense_rank = int(L.get("dense_rank", 0))
+        if s.dense_n:
+            s.qr_mat = vec(L["qr_mat"], np.float64)
+            s.qr_tau = vec(L["qr_tau"], np.float64)
+            s.qr_jpvt = vec(L["qr_jpvt"], np.int32)
+        s.has_symm_dense = int(L.get("has_symm_dense", 0))
+    return arr, keep
+
+
+_lib = None
+
+
+def lib():
+    """The C-ABI library.  Raises if it has not been built -- there is no fallback."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(f"{LIB_PATH} not built: run `python -c 'import __graft_entry__ as g; g.build()'`"
+                               " (the product has no CPU fallback)")
+        L = C.CDLL(LIB_PATH)
+        vp, sz, i, d = C.c_void_p, C.c_size_t, C.c_int, C.c_double
+        sig = {
+            "lhfdGpuAttachLevels": [i, sz, vp, vp],
+            "lhfdGpuDestroy": [vp],
+            "lhfdGpuSetMatrix": [vp, i, sz, vp, vp, vp],
+            "lhfdGpuSetNspConst": [vp, sz, sz],
+            "lhfdGpuClearNsp": [vp],
+            "lhfdGpuSetStream": [vp, vp],
+            "lhfdGpuSynchronize": [vp],
+            "lhfdGpuSolve": [vp, vp, vp],
+            "lhfdGpuApply": [vp, i, vp, i, vp, i, vp, vp],
+            "lhfdGpuSolveMrhs": [vp, sz, vp, vp],
+            "lhfdGpuFgmres": [vp, vp, i, d, i, i, vp, vp, vp, vp],
+            "lhfdGpuGmres": [vp, vp, i, d, i, vp, vp, vp],
+            "lhfdGpuSolveDev": [vp, vp, vp, sz],
+            "lhfdGpuSolveMrhsDev": [vp, sz, vp, vp, sz],
+            "lhfdGpuHifirDev": [vp, vp, sz, vp, sz],
+            "lhfdGpuSpmvDev": [vp, vp, vp],
+            "lhfdGpuGetStats": [vp, vp],
+            "lhfdGpuGetDepths": [vp, sz, vp],
+        }
+        for name, argt in sig.items():
+            f = getattr(L, name)
+            f.argtypes = argt
+            f.restype = C.c_int
+        L.lhfGpuGetErrorMsg.restype = C.c_char_p
+        L.lhfGpuVersion.restype = C.c_char_p
+        _lib = L
+    return _lib
+
+
+EXPORTED_SYMBOLS = (
+    "lhfdGpuAttachLevels", "lhfdGpuDestroy", "lhfdGpuSetMatrix", "lhfdGpuSetNspConst", "lhfdGpuClearNsp",
+    "lhfdGpuSetStream", "lhfdGpuSynchronize", "lhfdGpuSolve", "lhfdGpuApply", "lhfdGpuSolveMrhs",
+    "lhfdGpuFgmres", "lhfdGpuGmres", "lhfdGpuSolveDev", "lhfdGpuSolveMrhsDev", "lhfdGpuHifirDev",
+    "lhfdGpuSpmvDev", "lhfdGpuGetStats", "lhfdGpuGetDepths", "lhfGpuGetErrorMsg", "lhfGpuVersion")
+
+
+class LhfError(RuntimeError):
+    def __init__(self, status, msg):
+        super().__init__(f"LhfStatus {status}: {msg}")
+        self.status = status
+
+
+def _chk(st):
+    if st != LHF_SUCCESS:
+        raise LhfError(st, (lib().lhfGpuGetErrorMsg() or b"").decode())
+
+
+class GpuHif:
+    """Thin handle wrapper: one attached preconditioner on one device.
+
+    Mirrors the libhifir calling pattern (lhfdCreate/Setup -> lhfdSolve/lhfdApply ->
+    lhfdDestroy); every method is one C-ABI call."""
+
+    def __init__(self, levels=None, device=0, raw_handle=None):
+        self._h = None
+        if raw_handle is not None:
+            self._h = C.c_void_p(raw_handle)
+        else:
+            arr, keep = make_level_structs(levels)
+            h = C.c_void_p()
+            _chk(lib().lhfdGpuAttachLevels(device, len(levels), C.cast(arr, C.c_void_p), C.byref(h)))
+            self._h = h
+        self.n = self.stats()["n"]
+
+    def close(self):
+        if self._h is not None and _lib is not None:
+            _lib.lhfdGpuDestroy(self._h)
+        self._h = None
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def stats(self):
+        s = np.zeros(len(STAT_NAMES), dtype=np.uint64)
+        _chk(lib().lhfdGpuGetStats(self._h, _ptr(s)))
+        return {k: int(v) for k, v in zip(STAT_NAMES, s)}
+
+    def depths(self):
+        nl = self.stats()["levels"]
+        d = np.zeros(2 * nl, dtype=np.uint64)
+        _chk(lib().lhfdGpuGetDepths(self._h, nl, _ptr(d)))
+        return d.reshape(nl, 2).astype(np.int64)
+
+    def set_matrix(self, A, rowmajor=True):
+        n, indptr, indices, vals = A
+        ip = np.ascontiguousarray(indptr, dtype=np.int64)
+        ix = np.ascontiguousarray(indices, dtype=np.int32)
+        va = np.ascontiguousarray(vals, dtype=np.float64)
+        _chk(lib().lhfdGpuSetMatrix(self._h, int(bool(rowmajor)), n, _ptr(ip), _ptr(ix), _ptr(va)))
+
+    def set_nsp_const(self, start=0, end=FULL_RANK):
+        _chk(lib().lhfdGpuSetNspConst(self._h, start, end))
+
+    def clear_nsp(self):
+        _chk(lib().lhfdGpuClearNsp(self._h))
+
+    def set_stream(self, stream_ptr):
+        _chk(lib().lhfdGpuSetStream(self._h, C.c_void_p(stream_ptr)))
+
+    def synchronize(self):
+        _chk(lib().lhfdGpuSynchronize(self._h))
+
+    # ---- host-buffer entry points (numpy in, numpy out) ----
+    def solve(self, b, out=None):
+        b = np.ascontiguousarray(b, dtype=np.float64)
+        x = np.empty_like(b) if out is None else out
+        _chk(lib().lhfdGpuSolve(self._h, _ptr(b), _ptr(x)))
+        return x
+
+    def apply(self, b, op=LHF_S, nirs=1, betas=None, rank=LHF_DEFAULT_RANK):
+        b = np.ascontiguousarray(b, dtype=np.float64)
+        x = np.empty_like(b)
+        bt = None if betas is None else np.asarray(betas, dtype=np.float64)
+        irs = np.zeros(2, dtype=np.int32)
+        _chk(lib().lhfdGpuApply(self._h, op, _ptr(b), nirs, _ptr(bt) if bt is not None else None, rank,
+                                _ptr(x), _ptr(irs)))
+        return x, (int(irs[0]), int(irs[1]))
+
+    def solve_mrhs(self, B):
+        B = np.ascontiguousarray(B, dtype=np.float64)
+        assert B.ndim == 2 and B.shape[0] == self.n
+        X = np.empty_like(B)
+        _chk(lib().lhfdGpuSolveMrhs(self._h, B.shape[1], _ptr(B), _ptr(X)))
+        return X
+
+    def fgmres(self, b, restart=30, rtol=1e-6, maxit=500, full_rank=False):
+        b = np.ascontiguousarray(b, dtype=np.float64)
+        x = np.empty_like(b)
+        flag, iters, nmv = C.c_int(), C.c_int(), C.c_int()
+        _chk(lib().lhfdGpuFgmres(self._h, _ptr(b), restart, rtol, maxit, int(full_rank), _ptr(x),
+                                 C.byref(flag), C.byref(iters), C.byref(nmv)))
+        return x, flag.value, iters.value, nmv.value
+
+    def gmres(self, b, restart=30, rtol=1e-6, maxit=500):
+        b = np.ascontiguousarray(b, dtype=np.float64)
+        x = np.empty_like(b)
+        flag, iters = C.c_int(), C.c_int()
+        _chk(lib().lhfdGpuGmres(self._h, _ptr(b), restart, rtol, maxit, _ptr(x), C.byref(flag),
+                                C.byref(iters)))
+        return x, flag.value, iters.value
+
+    # ---- device-pointer entry points (ints = raw device addresses, e.g. tensor.data_ptr()) ----
+    def solve_dev(self, d_b, d_x, rank=0):
+        _chk(lib().lhfdGpuSolveDev(self._h, C.c_void_p(d_b), C.c_void_p(d_x), rank))
+
+    def solve_mrhs_dev(self, nrhs, d_B, d_X, rank=0):
+        _chk(lib().lhfdGpuSolveMrhsDev(self._h, nrhs, C.c_void_p(d_B), C.c_void_p(d_X), rank))
+
+    def hifir_dev(self, d_b, nirs, d_x, rank=FULL_RANK):
+        _chk(lib().lhfdGpuHifirDev(self._h, C.c_void_p(d_b), nirs, C.c_void_p(d_x), rank))
+
+    def spmv_dev(self, d_x, d_y):
+        _chk(lib().lhfdGpuSpmvDev(self._h, C.c_void_p(d_x), C.c_void_p(d_y)))

@@ -1,0 +1,219 @@
+"""ctypes front-end of oracle/_ref/libhifir_ref.so (the UNMODIFIED reference compiled
+by oracle/Makefile).  TEST INFRASTRUCTURE: imported only by tests/, bench.py (factor
+producer + cpu_baseline leg + reference arm) and __graft_entry__.smoke().  The product
+package hifir_b200/ never imports this module.
+
+What it gives:
+  * RefHif(A, params).factorize  -> hif::HIF<double,int>::factorize (builder.hpp:263-366)
+  * .levels()                    -> per-level factors verbatim from hif::Prec (Prec.hpp:309-323)
+  * .solve/.hifir/.krylov        -> the reference's CPU path, the parity oracle proper
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_ref", "libhifir_ref.so")
+
+_lib = None
+
+
+def available():
+    return os.path.exists(LIB_PATH)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not available():
+            raise RuntimeError(
+                f"{LIB_PATH} missing: run `make -C oracle` where /root/reference exists")
+        L = C.CDLL(LIB_PATH)
+        L.hifref_last_error.restype = C.c_char_p
+        L.hifref_version.restype = C.c_char_p
+        L.hifref_create.restype = C.c_void_p
+        L.hifref_create.argtypes = [C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        L.hifref_destroy.argtypes = [C.c_void_p]
+        L.hifref_num_precs.argtypes = [C.c_void_p]
+        L.hifref_levels.restype = C.c_size_t
+        L.hifref_levels.argtypes = [C.c_void_p]
+        L.hifref_nnz.restype = C.c_size_t
+        L.hifref_nnz.argtypes = [C.c_void_p]
+        L.hifref_level_sizes.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.hifref_export_ccs.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.hifref_block_shape.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        L.hifref_export_vectors.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 7
+        L.hifref_export_dense.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.hifref_set_nsp_const.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t]
+        L.hifref_clear_nsp.argtypes = [C.c_void_p]
+        L.hifref_solve.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
+        L.hifref_mmultiply.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
+        L.hifref_hifir.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]
+        L.hifref_hifir_betas.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p,
+                                         C.c_size_t, C.c_void_p]
+        L.hifref_spmv.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.hifref_krylov.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_double, C.c_int,
+                                    C.c_void_p, C.c_void_p]
+        L.hifref_norm2.restype = C.c_double
+        L.hifref_norm2.argtypes = [C.c_void_p, C.c_size_t]
+        L.hifref_gpu_attach.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        _lib = L
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+FULL_RANK = (1 << 64) - 1  # size_t(-1)
+
+
+class RefHif:
+    """A factorized hif::HIF<double,int> living in the reference library."""
+
+    def __init__(self, A, params=None, dense_thres=0, threads=0, verbose=0):
+        n, indptr, indices, vals = A
+        self.n = int(n)
+        self._A = (np.ascontiguousarray(indptr, dtype=np.int64),
+                   np.ascontiguousarray(indices, dtype=np.int32),
+                   np.ascontiguousarray(vals, dtype=np.float64))
+        pr = np.full(8, -1.0)
+        if params:
+            for k, name in enumerate(("tau_L", "tau_U", "kappa_d", "kappa", "alpha_L", "alpha_U")):
+                if name in params:
+                    pr[k] = params[name]
+        pr[6] = dense_thres
+        pr[7] = threads
+        self._h = lib().hifref_create(self.n, _p(self._A[0]), _p(self._A[1]), _p(self._A[2]), _p(pr),
+                                      int(verbose))
+        if not self._h:
+            raise RuntimeError("reference factorize failed: " + lib().hifref_last_error().decode())
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().hifref_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def _chk(self, rc):
+        if rc != 0:
+            raise RuntimeError("reference error: " + lib().hifref_last_error().decode())
+
+    @property
+    def num_precs(self):
+        return lib().hifref_num_precs(self._h)
+
+    @property
+    def num_levels(self):
+        return lib().hifref_levels(self._h)
+
+    @property
+    def nnz(self):
+        return lib().hifref_nnz(self._h)
+
+    def level_sizes(self, lvl):
+        s = np.zeros(10, dtype=np.uint64)
+        self._chk(lib().hifref_level_sizes(self._h, lvl, _p(s)))
+        keys = ("m", "n", "nnz_L", "nnz_U", "nnz_E", "nnz_F", "dense_n", "dense_rank", "has_symm_dense",
+                "is_last")
+        return {k: int(v) for k, v in zip(keys, s)}
+
+    def levels(self):
+        """Per-level factors, copied verbatim: list of dicts with CCS blocks
+        ('L','U','E','F' -> (nrows, ncols, col_start[int64], row_ind[int32], vals)), 'd','s','t',
+        'p','p_inv','q','q_inv', and on the last level 'qr_mat' (column-major, flattened),
+        'qr_tau','qr_jpvt' (1-based), 'dense_n','dense_rank'."""
+        out = []
+        for lvl in range(self.num_precs):
+            sz = self.level_sizes(lvl)
+            m, n = sz["m"], sz["n"]
+            L = dict(m=m, n=n, has_symm_dense=sz["has_symm_dense"])
+            for which, (name, nnzk) in enumerate((("L", "nnz_L"), ("U", "nnz_U"), ("E", "nnz_E"), ("F", "nnz_F"))):
+                dims = np.zeros(2, dtype=np.uint64)
+                self._chk(lib().hifref_block_shape(self._h, lvl, which, _p(dims)))
+                nr, nc = int(dims[0]), int(dims[1])
+                cs = np.zeros(nc + 1, dtype=np.int64)
+                ri = np.zeros(sz[nnzk], dtype=np.int32)
+                va = np.zeros(sz[nnzk], dtype=np.float64)
+                self._chk(lib().hifref_export_ccs(self._h, lvl, which, _p(cs), _p(ri), _p(va)))
+                L[name] = (nr, nc, cs, ri, va)
+            d = np.zeros(m); s = np.zeros(n); t = np.zeros(n)
+            p, p_inv, q, q_inv = (np.zeros(n, dtype=np.int32) for _ in range(4))
+            self._chk(lib().hifref_export_vectors(self._h, lvl, _p(d), _p(s), _p(t), _p(p), _p(p_inv), _p(q),
+                                                  _p(q_inv)))
+            L.update(d=d, s=s, t=t, p=p, p_inv=p_inv, q=q, q_inv=q_inv)
+            nm = sz["dense_n"]
+            L["dense_n"], L["dense_rank"] = nm, sz["dense_rank"]
+            if nm:
+                mat = np.zeros(nm * nm); tau = np.zeros(nm); jp = np.zeros(nm, dtype=np.int32)
+                self._chk(lib().hifref_export_dense(self._h, lvl, _p(mat), _p(tau), _p(jp)))
+                L.update(qr_mat=mat, qr_tau=tau, qr_jpvt=jp)
+            out.append(L)
+        return out
+
+    def set_nsp_const(self, start=0, end=FULL_RANK):
+        self._chk(lib().hifref_set_nsp_const(self._h, start, end))
+
+    def clear_nsp(self):
+        lib().hifref_clear_nsp(self._h)
+
+    def solve(self, b, rank=0):
+        b = np.ascontiguousarray(b, dtype=np.float64)
+        x = np.empty_like(b)
+        self._chk(lib().hifref_solve(self._h, _p(b), _p(x), rank))
+        return x
+
+    def mmultiply(self, x, rank=0):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        y = np.empty_like(x)
+        self._chk(lib().hifref_mmultiply(self._h, _p(x), _p(y), rank))
+        return y
+
+    def hifir(self, b, nirs, rank=FULL_RANK):
+        b = np.ascontiguousarray(b, dtype=np.float64)
+        x = np.empty_like(b)
+        self._chk(lib().hifref_hifir(self._h, _p(b), nirs, _p(x), rank))
+        return x
+
+    def hifir_betas(self, b, nirs, betas, rank=FULL_RANK):
+        b = np.ascontiguousarray(b, dtype=np.float64)
+        x = np.empty_like(b)
+        bt = np.asarray(betas, dtype=np.float64)
+        out = np.zeros(2, dtype=np.int64)
+        self._chk(lib().hifref_hifir_betas(self._h, _p(b), nirs, _p(bt), _p(x), rank, _p(out)))
+        return x, int(out[0]), int(out[1])
+
+    def spmv(self, x):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        y = np.empty_like(x)
+        self._chk(lib().hifref_spmv(self._h, _p(x), _p(y)))
+        return y
+
+    def krylov(self, b, which="fgmres", restart=30, rtol=1e-6, maxit=500):
+        """gmres_hif / fgmres_hifir of examples/advanced/gmres.hpp, unmodified.
+        Returns x, flag, iters, num_mv."""
+        b = np.ascontiguousarray(b, dtype=np.float64)
+        x = np.empty_like(b)
+        out = np.zeros(3, dtype=np.int32)
+        self._chk(lib().hifref_krylov(self._h, 1 if which == "fgmres" else 0, _p(b), restart, rtol, maxit,
+                                      _p(x), _p(out)))
+        return x, int(out[0]), int(out[1]), int(out[2])
+
+    def gpu_attach(self, attach_levels_fnptr, device=0):
+        """Attach the device backend through the C++ adapter include/hifir_b200.hpp,
+        i.e. the way a hif::HIF user would.  Returns the raw LhfdGpuHdl (int)."""
+        api = (C.c_void_p * 1)(C.cast(attach_levels_fnptr, C.c_void_p))
+        out = C.c_void_p()
+        rc = lib().hifref_gpu_attach(self._h, api, device, C.byref(out))
+        if rc != 0:
+            raise RuntimeError(f"gpu attach failed ({rc}): " + lib().hifref_last_error().decode())
+        return out.value
+
+
+def norm2(v):
+    v = np.ascontiguousarray(v, dtype=np.float64)
+    return lib().hifref_norm2(_p(v), v.size)
