@@ -1,0 +1,362 @@
+#!/usr/bin/env python
+"""bench.py -- M^-1 applies/s of the multilevel HIF preconditioner on B200 (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference]
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+
+Workload (configs[1]): synthetic 3D Poisson 7-point 128^3 (n = 2 097 152), HIF factorized on the
+host by the unmodified reference with its PDE parameter set, nrhs = 1.  One "step" = one M^-1
+apply (hif::HIF::solve) of a seeded right-hand side.
+
+  value : applies/s with b and x resident in HBM (lhfdGpuSolveDev), whole job over all ranks
+  e2e   : applies/s through lhfdGpuSolve with pinned HOST b/x (H2D + apply + D2H per step)
+  roofline : algorithmic bytes per apply / measured time vs measured HBM copy peak
+  cpu_baseline : the reference's own hif::HIF::solve on this box's host, 1 core (it is serial)
+
+Multi-GPU: the apply does not shard (sequential levels); every rank holds a factor replica and
+applies to its own right-hand sides -> weak scaling, no collective on the hot path; results are
+gathered with one NCCL all_gather after the timed region.
+
+The factorization (host, reference code) is the factor PRODUCER the device backend attaches to;
+it runs before the timed region and is never part of a reported number.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+CACHE_DIR = os.environ.get("HIFIR_B200_CACHE", "/tmp/hifir_b200_cache")
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+# ----------------------------------------------------------------------------- workloads
+def make_problem(workload, size):
+    from hifir_b200 import problems as P
+    gen = {"poisson": P.poisson3d, "neumann": P.neumann3d, "convdiff": P.convdiff3d, "stokes": P.stokes2d_mac}[workload]
+    return gen(size)
+
+
+def workload_name(workload, size, nrhs):
+    shape = f"{size}^3" if workload != "stokes" else f"MAC {size}x{size}"
+    return f"{workload} {shape} nrhs={nrhs}"
+
+
+def factorize(A, threads, nsp=False):
+    """Host factorization by the unmodified reference (factor producer + CPU oracle)."""
+    from hifir_b200 import problems as P
+    from oracle import refhost as R
+    t0 = time.time()
+    M = R.RefHif(A, P.PDE_PARAMS, threads=threads)
+    if nsp:
+        M.set_nsp_const()
+    log(f"[bench] reference factorize: {time.time() - t0:.1f} s, levels {M.num_levels}, nnz {M.nnz}")
+    return M
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device, self.rows, self.proc = device, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.device), "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+                for nm, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                pass
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ----------------------------------------------------------------------------- reference arm
+def cpu_apply_rate(M, n, applies, warm=1):
+    from hifir_b200 import problems as P
+    bs = [P.seeded_rhs(n, j) for j in range(2)]
+    for _ in range(warm):
+        M.solve(bs[0])
+    t0 = time.perf_counter()
+    for k in range(applies):
+        M.solve(bs[k % 2])
+    dt = time.perf_counter() - t0
+    return applies / dt, dt
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    A = make_problem(args.workload, args.size)
+    n = A[0]
+    M = factorize(A, threads=os.cpu_count() or 1)
+    steps = min(args.steps, args.ref_max_steps)
+    cpu_apply_rate(M, n, max(1, min(args.warmup, 3)), warm=0)
+    rate, dt = cpu_apply_rate(M, n, steps, warm=0)
+    sample = (f"{steps} of the {args.steps} requested hif::HIF::solve applies (serial reference code, "
+              f"prec_solve.hpp:332-412 has no threading), each a full apply of the workload")
+    line = {
+        "impl": "reference", "metric": "M^-1 applies/sec", "value": rate, "unit": "applies/s", "n_gpus": args.gpus,
+        "steps": steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(args.workload, args.size, 1), "n": n,
+                   "params": "tau=1e-2 alpha=3 kappa=5 (reference PDE set)"},
+        "cpu_baseline": {"value": rate, "unit": "applies/s", "cores": 1, "kind": "reference", "sample": sample},
+        "e2e": {"value": rate, "unit": "applies/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------- our arm
+def sweep_bytes(levels):
+    """Algorithmic bytes of each triangular sweep launch (factor stream + rhs read + x write)."""
+    out = {}
+    for l, L in enumerate(levels):
+        m = L["m"]
+        for nm_, key in (("L", "L"), ("U", "U")):
+            nnz = len(L[key][3])
+            out[f"lv{l}.{nm_}"] = nnz * 12 + (m + 1) * 4 + (8 * m if nm_ == "U" else 0) + 16 * m
+    return out
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+
+    import hifir_b200 as hb
+    from hifir_b200 import build, problems as P
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback exists)"
+    torch.cuda.set_device(local_rank)
+    build.build()
+    A = make_problem(args.workload, args.size)
+    n = A[0]
+    nsp = args.workload == "neumann"
+    threads = max(1, (os.cpu_count() or 1) // world)
+    M = factorize(A, threads=threads, nsp=nsp)
+    levels = M.levels()
+    t0 = time.time()
+    G = hb.GpuHif(levels, device=local_rank)
+    G.set_matrix(A)
+    if nsp:
+        G.set_nsp_const()
+    st = G.stats()
+    log(f"[bench] rank {rank}: attach {time.time() - t0:.1f} s, device bytes {st['device_bytes'] / 1e9:.2f} GB, "
+        f"depths {G.depths().tolist()}")
+    stream = torch.cuda.current_stream()
+    G.set_stream(stream.cuda_stream)
+
+    nb = 4
+    b_host = [torch.from_numpy(P.seeded_rhs(n, rank * nb + j)).pin_memory() for j in range(nb)]
+    b_dev = [b.cuda() for b in b_host]
+    x_dev = torch.empty(n, dtype=torch.float64, device="cuda")
+    x_host = torch.empty(n, dtype=torch.float64).pin_memory()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- parity spot check before timing (against the reference's own apply, same object)
+    G.solve_dev(b_dev[0].data_ptr(), x_dev.data_ptr(), 0)
+    G.synchronize()
+    xr = M.solve(b_host[0].numpy())
+    parity = float(np.linalg.norm(x_dev.cpu().numpy() - xr) / np.linalg.norm(xr))
+    log(f"[bench] rank {rank}: parity vs reference apply = {parity:.2e}")
+    assert parity <= 1e-12, f"parity gate failed: {parity}"
+
+    # ---- device-resident timing
+    for k in range(args.warmup):
+        G.solve_dev(b_dev[k % nb].data_ptr(), x_dev.data_ptr(), 0)
+    launches0 = G.stats()["launch_count"]
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for k in range(args.steps):
+        G.solve_dev(b_dev[k % nb].data_ptr(), x_dev.data_ptr(), 0)
+    e1.record(stream)
+    barrier()
+    clocks = sampler.stop()
+    G.synchronize()  # also surfaces a tripped spin limit
+    ms_total = e0.elapsed_time(e1)
+    launches = G.stats()["launch_count"] - launches0
+
+    # ---- end to end through the host-buffer C-ABI call (pinned host memory)
+    for k in range(min(3, args.warmup)):
+        G.solve(b_host[k % nb].numpy(), out=x_host.numpy())
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        G.solve(b_host[k % nb].numpy(), out=x_host.numpy())
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    barrier()
+
+    t = torch.tensor([ms_total, e2e_s * 1e3], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        # result gather, off the timed path (the only NCCL traffic of this benchmark)
+        out = [torch.empty_like(x_dev) for _ in range(world)]
+        dist.all_gather(out, x_dev)
+    ms_total, e2e_ms = float(t[0]), float(t[1])
+    ms_step = ms_total / args.steps
+    if rank != 0:
+        return
+
+    bytes_apply = st["bytes_factors"] + st["bytes_dense"] + st["bytes_vec_per_rhs"]
+    peak, peak_src = hbm_peak()
+    achieved = bytes_apply / (ms_step * 1e-3) / 1e9
+    # dominant kernel, timed live with events inside an instrumented apply
+    prof = {}
+    for rep in range(5):
+        for name, ms in G.profile_solve_dev(b_dev[0].data_ptr(), x_dev.data_ptr(), 0):
+            prof.setdefault(name, []).append(ms)
+    prof = {k: statistics.median(v) for k, v in prof.items()}
+    top = max(prof, key=prof.get)
+    sb = sweep_bytes(levels)
+    top_key = None
+    if ".down." in top or ".up." in top:
+        top_key = top.split(".")[0] + "." + top.split(".")[-1]
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "scope": f"whole apply = {st['kernels_per_apply']} kernels",
+                "algorithmic_bytes_per_apply": bytes_apply, "peak_source": peak_src,
+                "latency_floor": {"dependent_steps_per_apply": st["depth_total"],
+                                  "ns_per_step_achieved": ms_step * 1e6 / max(1, st["depth_total"])},
+                "kernels_ms": {k: round(v, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1])[:8]}}
+    if top_key in sb:
+        roofline["top_kernel"] = {"name": top, "ms": prof[top], "algorithmic_bytes": sb[top_key],
+                                  "achieved": sb[top_key] / (prof[top] * 1e-3) / 1e9,
+                                  "frac": sb[top_key] / (prof[top] * 1e-3) / 1e9 / peak,
+                                  "share_of_apply": prof[top] / sum(prof.values())}
+
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        applies = args.cpu_applies
+        rate, dt = cpu_apply_rate(M, n, applies)
+        cpu = {"value": rate, "unit": "applies/s", "cores": 1, "kind": "reference",
+               "sample": f"{applies} hif::HIF::solve applies of the same workload on the same factorized object "
+                         f"({dt:.1f} s; the reference apply is serial)"}
+    extra = {}
+    if world == 1 and not args.no_fgmres:
+        bk = P.csr_matvec(A, np.ones(n)) if not nsp else P.csr_matvec(A, np.sin(0.37 * np.arange(n)))
+        G.fgmres(bk)  # warm-up (allocates the Krylov basis)
+        t0 = time.perf_counter()
+        xg, flag, iters, nmv = G.fgmres(bk)
+        tg = time.perf_counter() - t0
+        extra["fgmres"] = {"gpu_time_s": tg, "iters": iters, "num_mv": nmv, "flag": flag,
+                           "relres": float(np.linalg.norm(bk - P.csr_matvec(A, xg)) / np.linalg.norm(bk))}
+        if not args.no_cpu:
+            t0 = time.perf_counter()
+            xr, rflag, riters, rnmv = M.krylov(bk, "fgmres")
+            extra["fgmres"].update(cpu_time_s=time.perf_counter() - t0, cpu_iters=riters, cpu_num_mv=rnmv,
+                                   cpu_threads=threads)
+
+    line = {
+        "metric": "M^-1 applies/sec", "value": world * args.steps / (ms_total * 1e-3), "unit": "applies/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(args.workload, args.size, 1), "n": n, "levels": st["levels"],
+                   "nnz_factors": st["nnz"], "params": "tau=1e-2 alpha=3 kappa=5 (reference PDE set)",
+                   "l2_policy": f"inputs larger than L2: {bytes_apply / 1e9:.2f} GB streamed per apply vs 126 MB L2",
+                   "parallelism": "replicas, independent right-hand sides per GPU" if world > 1 else "1 GPU"},
+        "roofline": roofline, "cpu_baseline": cpu,
+        "e2e": {"value": world * args.steps / (e2e_ms * 1e-3), "unit": "applies/s", "h2d_bytes_per_step": 8 * n,
+                "d2h_bytes_per_step": 8 * n, "api": "lhfdGpuSolve (pinned host buffers)"},
+        "gpu_launches": launches, "clocks": clocks, "parity_vs_reference": parity,
+    }
+    line.update(extra)
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="poisson", choices=["poisson", "neumann", "convdiff", "stokes"])
+    ap.add_argument("--size", type=int, default=128)
+    ap.add_argument("--cpu-applies", type=int, default=40)
+    ap.add_argument("--ref-max-steps", type=int, default=300)
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-fgmres", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(3, args.warmup)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    try:
+        run_ours(args, rank, world, local_rank)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -113,6 +113,7 @@ def lib():
             "lhfdGpuSolveMrhsDev": [vp, sz, vp, vp, sz],
             "lhfdGpuHifirDev": [vp, vp, sz, vp, sz],
             "lhfdGpuSpmvDev": [vp, vp, vp],
+            "lhfdGpuProfileSolveDev": [vp, vp, vp, sz, sz, vp, vp, vp, sz],
             "lhfdGpuGetStats": [vp, vp],
             "lhfdGpuGetDepths": [vp, sz, vp],
         }
@@ -130,7 +131,7 @@ EXPORTED_SYMBOLS = (
     "lhfdGpuAttachLevels", "lhfdGpuDestroy", "lhfdGpuSetMatrix", "lhfdGpuSetNspConst", "lhfdGpuClearNsp",
     "lhfdGpuSetStream", "lhfdGpuSynchronize", "lhfdGpuSolve", "lhfdGpuApply", "lhfdGpuSolveMrhs",
     "lhfdGpuFgmres", "lhfdGpuGmres", "lhfdGpuSolveDev", "lhfdGpuSolveMrhsDev", "lhfdGpuHifirDev",
-    "lhfdGpuSpmvDev", "lhfdGpuGetStats", "lhfdGpuGetDepths", "lhfGpuGetErrorMsg", "lhfGpuVersion")
+    "lhfdGpuSpmvDev", "lhfdGpuProfileSolveDev", "lhfdGpuGetStats", "lhfdGpuGetDepths", "lhfGpuGetErrorMsg", "lhfGpuVersion")
 
 
 class LhfError(RuntimeError):
@@ -252,6 +253,16 @@ class GpuHif:
 
     def hifir_dev(self, d_b, nirs, d_x, rank=FULL_RANK):
         _chk(lib().lhfdGpuHifirDev(self._h, C.c_void_p(d_b), nirs, C.c_void_p(d_x), rank))
+
+    def profile_solve_dev(self, d_b, d_x, rank=0):
+        """Instrumented apply: [(label, milliseconds)] for every kernel of the schedule."""
+        ms = np.zeros(256, dtype=np.float32)
+        cnt = C.c_size_t()
+        names = C.create_string_buffer(8192)
+        _chk(lib().lhfdGpuProfileSolveDev(self._h, C.c_void_p(d_b), C.c_void_p(d_x), rank, 256, _ptr(ms),
+                                          C.byref(cnt), names, 8192))
+        labels = names.value.decode().split("\n")
+        return [(labels[k], float(ms[k])) for k in range(cnt.value)]
 
     def spmv_dev(self, d_x, d_y):
         _chk(lib().lhfdGpuSpmvDev(self._h, C.c_void_p(d_x), C.c_void_p(d_y)))

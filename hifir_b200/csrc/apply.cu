@@ -1,0 +1,397 @@
+// apply.cu -- the multilevel M^{-1} apply (reference alg/prec_solve.hpp:332-412) as a
+// static schedule of hand-written sm_100a kernels.
+//
+// The reference's recursion over levels unrolls into a down-sweep, the dense solve and
+// an up-sweep.  Per level l (m, n, nm = n-m):
+//   down:  bhat = s[p] .* b[p]                                  (gather_scale_kernel)
+//          xL   = L^{-1} bhat[0:m]                              (sptrsv_block_kernel<LOWER>)
+//          xU   = U^{-1} (xL ./ d)                              (sptrsv_block_kernel<UPPER>)
+//          r    = bhat[m:n] - E xU         -> b of level l+1    (spmv_resid_kernel)
+//   last:  ychild = P R^{-1} Q^T r                              (dense_qt_kernel, dense_trsv_kernel)
+//   up:    g    = bhat[0:m] - F ychild                          (spmv_resid_kernel)
+//          xL'  = L^{-1} g ; xU' = U^{-1} (xL' ./ d)
+//          y[i] = t[i] * [xU'; ychild][q_inv[i]]                (scatter_scale_kernel)
+// `bhat` is evaluated once per level (the reference evaluates s[p]*b[p] up to 3 times,
+// prec_solve.hpp:359/368/399).
+#include "hifgpu.h"
+
+namespace hifgpu {
+
+// ============================================================================
+// Block sync-free sparse triangular solve
+// ============================================================================
+// One CTA owns kRows consecutive rows in sweep order (forward for L, backward for U)
+// and takes its block index from a ticket counter, so that every block a CTA waits on
+// is already resident or finished (no deadlock, no per-level-set kernel launches).
+// One thread per row.  A dependency on a row of the same block is read from shared
+// memory (the reference's factors come out of AMD + Crout with strong index locality:
+// ~60% of all dependencies and nearly the whole critical path stay inside a
+// 1024-row block), a dependency on an earlier block is polled from global
+// memory (L2).  Values carry their own ready bit (common.cuh), so one 8-byte load
+// delivers data and readiness, and there are no fences on the critical path.
+//
+// Summation order per row = the reference's: CCS::solve_as_strict_lower sweeps the
+// columns j ascending, CCS::solve_as_strict_upper descending
+// (ds/CompressedStorage.hpp:2267-2279, 2356-2369), so y[i] receives its updates in
+// exactly this order; only FMA contraction differs.
+constexpr int kRows = 1024;
+
+template <bool UPPER>
+__global__ void __launch_bounds__(kRows, 1)
+    sptrsv_block_kernel(const unsigned m, const unsigned *__restrict__ ptr, const int *__restrict__ col,
+                        const double *__restrict__ val, const double *__restrict__ rhs_plain,
+                        const unsigned long long *rhs_tagged, const double *__restrict__ diag,
+                        unsigned long long *x, const unsigned parity, int *ticket, int *error_flag) {
+  __shared__ unsigned                    s_blk;
+  __shared__ volatile unsigned long long xs[kRows];
+  const unsigned                         tid = threadIdx.x;
+  if (tid == 0) s_blk = static_cast<unsigned>(atomicAdd(ticket, 1));
+  xs[tid] = parity ^ 1u;  // "not ready" pattern
+  __syncthreads();
+  const unsigned s0 = s_blk * kRows;
+  const unsigned s  = s0 + tid;
+  if (s >= m) return;
+  const unsigned i = UPPER ? m - 1u - s : s;
+
+  double acc;
+  if (UPPER) {
+    // y = D^{-1} L^{-1} b is formed on the fly (prec_solve.hpp:219): true division
+    acc = tag_value(rhs_tagged[i]) / diag[i];
+  } else {
+    acc = rhs_plain[i];
+  }
+  const unsigned begin = ptr[i], n = ptr[i + 1] - begin;
+  unsigned       k = 0, spins = 0;
+  bool           done = false;
+  // The publish step sits INSIDE the loop: a finished lane must store its value before
+  // the warp reconverges, because a sibling lane may be waiting for exactly that value.
+  while (!done) {
+    if (k < n) {
+      const unsigned idx = UPPER ? begin + n - 1u - k : begin + k;
+      const int      j   = ldg_stream(col + idx);
+      const double   a   = ldg_stream(val + idx);
+      const unsigned sj  = UPPER ? m - 1u - static_cast<unsigned>(j) : static_cast<unsigned>(j);
+      const unsigned long long bits = (sj >= s0) ? xs[sj - s0] : ld_poll(x + j);
+      if (tag_ready(bits, parity)) {
+        acc = fma(-a, tag_value(bits), acc);
+        ++k;
+        spins = 0;
+      } else if (++spins > kSpinLimit) {
+        *error_flag = 1;
+        k           = n;  // give up: publish garbage so that dependants terminate too
+      }
+    }
+    if (k >= n) {
+      const unsigned long long bits = tag_set(acc, parity);
+      xs[tid]                       = bits;
+      st_publish(x + i, bits);
+      done = true;
+    }
+  }
+}
+
+// ============================================================================
+// glue kernels
+// ============================================================================
+
+// bhat[i] = s[p[i]] * b[p[i]]   (prec_solve.hpp:359, 368, 399)
+__global__ void gather_scale_kernel(const unsigned n, const int *__restrict__ p, const double *__restrict__ s,
+                                    const double *__restrict__ b, double *__restrict__ bhat) {
+  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    const int pi = p[i];
+    bhat[i]      = s[pi] * b[pi];
+  }
+}
+
+// out[i] = base[i] - sum_j A(i,j) x[j]  with x either tagged (result of a sweep) or plain
+// E step: prec_solve.hpp:366-368 ; F step: :395-399 ; accumulation in ascending j like
+// CCS::multiply_nt_low (CompressedStorage.hpp:2078-2096).  kLanes lanes cooperate on a row.
+template <int kLanes, bool TAGGED>
+__global__ void spmv_resid_kernel(const unsigned nrows, const unsigned *__restrict__ ptr,
+                                  const int *__restrict__ col, const double *__restrict__ val,
+                                  const void *__restrict__ xin, const double *__restrict__ base,
+                                  double *__restrict__ out) {
+  const unsigned gid  = blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned row  = gid / kLanes;
+  const unsigned lane = gid % kLanes;
+  double         acc  = 0.0;
+  if (row < nrows) {
+    const unsigned e = ptr[row + 1];
+    for (unsigned k = ptr[row] + lane; k < e; k += kLanes) {
+      const int j = col[k];
+      double    xj;
+      if (TAGGED)
+        xj = tag_value(static_cast<const unsigned long long *>(xin)[j]);
+      else
+        xj = static_cast<const double *>(xin)[j];
+      acc = fma(val[k], xj, acc);
+    }
+  }
+#pragma unroll
+  for (int o = kLanes / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (row < nrows && lane == 0) out[row] = base[row] - acc;
+}
+
+// y[i] = t[i] * [xU; ychild][q_inv[i]]   (prec_solve.hpp:392, 411)
+__global__ void scatter_scale_kernel(const unsigned n, const unsigned m, const int *__restrict__ q_inv,
+                                     const double *__restrict__ t, const unsigned long long *__restrict__ xU,
+                                     const double *__restrict__ ychild, double *__restrict__ y) {
+  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    const unsigned j = static_cast<unsigned>(q_inv[i]);
+    const double   w = j < m ? tag_value(xU[j]) : ychild[j - m];
+    y[i]             = t[i] * w;
+  }
+}
+
+// ============================================================================
+// dense last level: x <- P [R11^{-1} (Q^T x)(1:rk) ; 0]   (small_scale/QRCP.hpp:370-411)
+// ============================================================================
+
+// c[k] = Q(:,k)^T x, k < rk : one warp per column of the explicit Q (coalesced)
+__global__ void dense_qt_kernel(const unsigned nm, const unsigned rk, const double *__restrict__ Q,
+                                const double *__restrict__ x, double *__restrict__ c) {
+  const unsigned warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31u;
+  if (warp >= rk) return;
+  const double *q   = Q + static_cast<std::size_t>(warp) * nm;
+  double        acc = 0.0;
+  for (unsigned i = lane; i < nm; i += 32) acc = fma(q[i], x[i], acc);
+  acc = warp_sum(acc);
+  if (lane == 0) c[warp] = acc;
+}
+
+// Back substitution on R(0:rk,0:rk) (column oriented like reference dtrsv 'U','N','N'),
+// blocked by 32: warp 0 solves the diagonal block with shuffles, the whole CTA applies
+// the block's columns to the rows above; then out[jpvt[i]-1] = x_i, zero for i >= rk.
+constexpr int kTrsvThreads = 1024;
+__global__ void __launch_bounds__(kTrsvThreads, 1)
+    dense_trsv_kernel(const unsigned nm, const unsigned rk, const double *__restrict__ R,
+                      const double *__restrict__ c, const int *__restrict__ jpvt, double *__restrict__ out) {
+  extern __shared__ double xs[];  // rk values
+  const unsigned           tid = threadIdx.x;
+  for (unsigned i = tid; i < rk; i += kTrsvThreads) xs[i] = c[i];
+  __syncthreads();
+  for (unsigned j1 = rk; j1 > 0;) {
+    const unsigned j0 = j1 >= 32u ? j1 - 32u : 0u;  // block [j0, j1)
+    const unsigned w  = j1 - j0;
+    if (tid < 32) {
+      double xv = tid < w ? xs[j0 + tid] : 0.0;
+      for (unsigned jj = w; jj-- > 0;) {
+        const unsigned col = j0 + jj;
+        double         xj  = 0.0;
+        if (tid == jj) {
+          // reference dtrsv skips the column when x(j) == 0
+          if (xv != 0.0) xv /= R[col + static_cast<std::size_t>(col) * nm];
+          xj = xv;
+        }
+        xj = __shfl_sync(0xffffffffu, xj, jj);
+        if (tid < jj && xj != 0.0) xv = fma(-xj, R[j0 + tid + static_cast<std::size_t>(col) * nm], xv);
+      }
+      if (tid < w) xs[j0 + tid] = xv;
+    }
+    __syncthreads();
+    // rows above the block: x[i] -= sum_{col in block, descending} R(i,col) * x[col]
+    for (unsigned i = tid; i < j0; i += kTrsvThreads) {
+      double xv = xs[i];
+      for (unsigned jj = w; jj-- > 0;) {
+        const unsigned col = j0 + jj;
+        const double   xj  = xs[col];
+        if (xj != 0.0) xv = fma(-xj, R[i + static_cast<std::size_t>(col) * nm], xv);
+      }
+      xs[i] = xv;
+    }
+    __syncthreads();
+    j1 = j0;
+  }
+  for (unsigned i = tid; i < nm; i += kTrsvThreads) out[jpvt[i] - 1] = i < rk ? xs[i] : 0.0;
+}
+
+// ============================================================================
+// null-space filter, constant mode: x[start:end] -= mean   (NspFilter.hpp:161-175)
+// ============================================================================
+constexpr int kRedBlocks = 2 * kNumSMs, kRedThreads = 512;
+
+__global__ void __launch_bounds__(kRedThreads) sum_partial_kernel(const double *__restrict__ x, const unsigned n,
+                                                                  double *__restrict__ part) {
+  __shared__ double sm[kRedThreads / 32];
+  double            acc = 0.0;
+  for (unsigned i = blockIdx.x * kRedThreads + threadIdx.x; i < n; i += gridDim.x * kRedThreads) acc += x[i];
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    acc = threadIdx.x < kRedThreads / 32 ? sm[threadIdx.x] : 0.0;
+    acc = warp_sum(acc);
+    if (threadIdx.x == 0) part[blockIdx.x] = acc;
+  }
+}
+
+__global__ void __launch_bounds__(kRedThreads) shift_kernel(double *__restrict__ x, const unsigned n,
+                                                            const double *__restrict__ part, const unsigned nparts) {
+  // every block re-reduces the (few) partials in the same fixed order -> deterministic
+  __shared__ double sm[kRedThreads / 32];
+  __shared__ double shift;
+  double            acc = 0.0;
+  for (unsigned i = threadIdx.x; i < nparts; i += kRedThreads) acc += part[i];
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    acc = threadIdx.x < kRedThreads / 32 ? sm[threadIdx.x] : 0.0;
+    acc = warp_sum(acc);
+    if (threadIdx.x == 0) shift = acc / static_cast<double>(n);
+  }
+  __syncthreads();
+  const double sh = shift;
+  for (unsigned i = blockIdx.x * kRedThreads + threadIdx.x; i < n; i += gridDim.x * kRedThreads) x[i] -= sh;
+}
+
+// ============================================================================
+// host-side schedule
+// ============================================================================
+namespace {
+
+inline unsigned cdiv(std::size_t a, std::size_t b) { return static_cast<unsigned>((a + b - 1) / b); }
+
+// profiling mode only: an event after each kernel of the schedule
+void mark(Handle *h, const std::string &name) {
+  if (!h->profiling) return;
+  cudaEvent_t e;
+  HIF_CUDA(cudaEventCreate(&e));
+  HIF_CUDA(cudaEventRecord(e, h->stream));
+  h->prof_marks.emplace_back(name, e);
+}
+
+void launch_sweeps(Handle *h, DevLevel &D, const double *rhs, unsigned long long *xL, unsigned long long *xU,
+                   unsigned parity, int *tickets, const std::string &tag) {
+  if (!D.m) return;
+  const unsigned m = static_cast<unsigned>(D.m), nb = cdiv(D.m, kRows);
+  sptrsv_block_kernel<false><<<nb, kRows, 0, h->stream>>>(m, D.L.ptr.p, D.L.col.p, D.L.val.p, rhs, nullptr, nullptr,
+                                                           xL, parity, tickets, h->error_flag.p);
+  HIF_KERNEL_CHECK();
+  mark(h, tag + "L");
+  sptrsv_block_kernel<true><<<nb, kRows, 0, h->stream>>>(m, D.U.ptr.p, D.U.col.p, D.U.val.p, nullptr, xL, D.d.p, xU,
+                                                          parity, tickets + 1, h->error_flag.p);
+  HIF_KERNEL_CHECK();
+  mark(h, tag + "U");
+  h->launch_count += 2;
+}
+
+template <bool TAGGED>
+void launch_spmv_resid(Handle *h, const DevCsr &A, const void *x, const double *base, double *out,
+                       const std::string &tag) {
+  if (!A.nrows) return;
+  const double avg = A.nrows ? static_cast<double>(A.nnz) / static_cast<double>(A.nrows) : 0.0;
+  constexpr int T  = 256;
+  if (avg > 12.0) {
+    spmv_resid_kernel<8, TAGGED><<<cdiv(A.nrows * 8, T), T, 0, h->stream>>>(
+        static_cast<unsigned>(A.nrows), A.ptr.p, A.col.p, A.val.p, x, base, out);
+  } else if (avg > 3.0) {
+    spmv_resid_kernel<4, TAGGED><<<cdiv(A.nrows * 4, T), T, 0, h->stream>>>(
+        static_cast<unsigned>(A.nrows), A.ptr.p, A.col.p, A.val.p, x, base, out);
+  } else {
+    spmv_resid_kernel<1, TAGGED><<<cdiv(A.nrows, T), T, 0, h->stream>>>(static_cast<unsigned>(A.nrows), A.ptr.p,
+                                                                        A.col.p, A.val.p, x, base, out);
+  }
+  HIF_KERNEL_CHECK();
+  mark(h, tag);
+  ++h->launch_count;
+}
+
+}  // namespace
+
+void apply_dev(Handle *h, const double *d_b, double *d_x, std::size_t rank) {
+  HIF_CUDA(cudaSetDevice(h->device));
+  const std::size_t nl = h->levels.size();
+  const std::size_t launches0 = h->launch_count;
+  ++h->epoch;
+  const unsigned parity = h->epoch & 1u;
+  HIF_CUDA(cudaMemsetAsync(h->tickets.p, 0, h->tickets.n * sizeof(int), h->stream));
+  constexpr int T = 256;
+  mark(h, "begin");
+
+  // ---- down-sweep
+  const double *b = d_b;
+  for (std::size_t l = 0; l < nl; ++l) {
+    DevLevel &D = h->levels[l];
+    if (D.n) {
+      gather_scale_kernel<<<cdiv(D.n, T), T, 0, h->stream>>>(static_cast<unsigned>(D.n), D.p.p, D.s.p, b, D.bhat.p);
+      HIF_KERNEL_CHECK();
+      mark(h, "lv" + std::to_string(l) + ".gather");
+      ++h->launch_count;
+    }
+    if (D.nm) {
+      launch_sweeps(h, D, D.bhat.p, D.xL_dn.p, D.xU_dn.p, parity, h->tickets.p + 4 * l,
+                    "lv" + std::to_string(l) + ".down.");
+      launch_spmv_resid<true>(h, D.E, D.xU_dn.p, D.bhat.p + D.m, D.r.p, "lv" + std::to_string(l) + ".E");
+      b = D.r.p;
+    }
+  }
+  // ---- dense last level (QRCP.hpp:370-411); rank: 0 -> numerical, > nm -> nm
+  DevLevel &last = h->levels[nl - 1];
+  if (last.nm) {
+    DevDense &      Q  = h->dense;
+    const unsigned  nm = static_cast<unsigned>(Q.nm);
+    const unsigned  rk = static_cast<unsigned>(rank == 0 ? Q.rank : (rank > Q.nm ? Q.nm : rank));
+    if (rk) {
+      dense_qt_kernel<<<cdiv(static_cast<std::size_t>(rk) * 32, T), T, 0, h->stream>>>(nm, rk, Q.Q.p, last.r.p, Q.c.p);
+      HIF_KERNEL_CHECK();
+      ++h->launch_count;
+    }
+    dense_trsv_kernel<<<1, kTrsvThreads, (rk ? rk : 1) * sizeof(double), h->stream>>>(nm, rk, Q.R.p, Q.c.p, Q.jpvt.p,
+                                                                                      last.ychild.p);
+    HIF_KERNEL_CHECK();
+    mark(h, "dense");
+    ++h->launch_count;
+  }
+  // ---- up-sweep
+  for (std::size_t l = nl; l-- > 0;) {
+    DevLevel &    D      = h->levels[l];
+    double *      y      = l == 0 ? d_x : h->levels[l - 1].ychild.p;
+    const double *rhs    = D.bhat.p;
+    if (D.nm && D.F.nnz) {
+      launch_spmv_resid<false>(h, D.F, D.ychild.p, D.bhat.p, D.g.p, "lv" + std::to_string(l) + ".F");
+      rhs = D.g.p;
+    }
+    launch_sweeps(h, D, rhs, D.xL_up.p, D.xU_up.p, parity, h->tickets.p + 4 * l + 2,
+                  "lv" + std::to_string(l) + ".up.");
+    if (D.n) {
+      scatter_scale_kernel<<<cdiv(D.n, T), T, 0, h->stream>>>(static_cast<unsigned>(D.n), static_cast<unsigned>(D.m),
+                                                             D.q_inv.p, D.t.p, D.xU_up.p, D.ychild.p, y);
+      HIF_KERNEL_CHECK();
+      mark(h, "lv" + std::to_string(l) + ".scatter");
+      ++h->launch_count;
+    }
+  }
+  // ---- null-space filter (builder.hpp:419-420)
+  if (h->nsp_on) {
+    const std::size_t n     = h->n0();
+    std::size_t       start = h->nsp_start, end = h->nsp_end;
+    if (end == static_cast<std::size_t>(-1) || end < start) end = n;
+    if (end > n) throw std::out_of_range("null-space filter range exceeds the system size");
+    if (end > start) {
+      if (h->kr_part.n < static_cast<std::size_t>(kRedBlocks)) h->kr_part.alloc(kRedBlocks, &h->device_bytes);
+      const unsigned len = static_cast<unsigned>(end - start);
+      const unsigned nb  = std::min<unsigned>(kRedBlocks, cdiv(len, kRedThreads));
+      sum_partial_kernel<<<nb, kRedThreads, 0, h->stream>>>(d_x + start, len, h->kr_part.p);
+      HIF_KERNEL_CHECK();
+      shift_kernel<<<nb, kRedThreads, 0, h->stream>>>(d_x + start, len, h->kr_part.p, nb);
+      HIF_KERNEL_CHECK();
+      mark(h, "nsp");
+      h->launch_count += 2;
+    }
+  }
+  h->kernels_per_apply = h->launch_count - launches0;
+}
+
+void check_sweep_error(Handle *h) {
+  HIF_CUDA(cudaMemcpyAsync(h->h_error, h->error_flag.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  HIF_CUDA(cudaStreamSynchronize(h->stream));
+  if (*h->h_error) {
+    HIF_CUDA(cudaMemsetAsync(h->error_flag.p, 0, sizeof(int), h->stream));
+    throw std::runtime_error("a triangular sweep exceeded its spin limit (dependency never became ready)");
+  }
+}
+
+}  // namespace hifgpu

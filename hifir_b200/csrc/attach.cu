@@ -1,0 +1,259 @@
+// attach.cu -- host side of the device backend: take the plain description of an
+// already factorized hif::HIF (LhfdGpuLevel, one per hif::Prec, reference
+// alg/Prec.hpp:309-323), convert each CCS block to the row-gather CSR form the kernels
+// consume, analyse the triangular dependency structure, upload everything once.
+#include <algorithm>
+#include <cstring>
+#include <memory>
+
+#include "hifgpu.h"
+
+namespace hifgpu {
+
+// CCS -> CSR, ascending column index inside each row.  Same result as the reference's
+// own converting constructor hif::CRS(const CCS&) (ds/CompressedStorage.hpp:861-890);
+// integers are moved verbatim (bit-exact index handling).
+HostCsr ccs_to_csr(const LhfdGpuCcs &c, const char *name) {
+  HostCsr r;
+  r.nrows = c.nrows;
+  r.ncols = c.ncols;
+  r.ptr.assign(c.nrows + 1, 0u);
+  if (!c.col_start || !c.ncols) return r;
+  const LhfIndPtr nnz = c.col_start[c.ncols];
+  if (nnz < 0 || static_cast<unsigned long long>(nnz) > 0x7fffffffull)
+    throw std::invalid_argument(std::string(name) + ": more than 2^31-1 nonzeros in one block");
+  if (nnz && (!c.row_ind || !c.vals)) throw std::invalid_argument(std::string(name) + ": null index/value array");
+  for (LhfIndPtr k = 0; k < nnz; ++k) {
+    const LhfInt i = c.row_ind[k];
+    if (i < 0 || static_cast<std::size_t>(i) >= c.nrows)
+      throw std::invalid_argument(std::string(name) + ": row index out of range");
+    ++r.ptr[i + 1];
+  }
+  for (std::size_t i = 0; i < c.nrows; ++i) r.ptr[i + 1] += r.ptr[i];
+  r.col.resize(nnz);
+  r.val.resize(nnz);
+  std::vector<unsigned> next(r.ptr.begin(), r.ptr.end() - 1);
+  for (std::size_t j = 0; j < c.ncols; ++j) {
+    if (c.col_start[j + 1] < c.col_start[j]) throw std::invalid_argument(std::string(name) + ": col_start not monotone");
+    for (LhfIndPtr k = c.col_start[j]; k < c.col_start[j + 1]; ++k) {
+      const unsigned pos = next[c.row_ind[k]]++;
+      r.col[pos]         = static_cast<int>(j);
+      r.val[pos]         = c.vals[k];
+    }
+  }
+  return r;
+}
+
+namespace {
+
+void upload_csr(const HostCsr &h, DevCsr &d, std::size_t *tally) {
+  d.nrows = h.nrows;
+  d.ncols = h.ncols;
+  d.nnz   = h.col.size();
+  d.ptr.upload(h.ptr, tally);
+  d.col.upload(h.col, tally);
+  d.val.upload(h.val, tally);
+}
+
+// number of level sets of a strictly triangular CSR (row i depends on its columns)
+std::size_t dag_depth(const HostCsr &T, bool upper) {
+  const std::size_t m = T.nrows;
+  if (!m) return 0;
+  std::vector<int> lev(m, 0);
+  int              mx = 0;
+  auto             row = [&](std::size_t i) {
+    int l = 0;
+    for (unsigned k = T.ptr[i]; k < T.ptr[i + 1]; ++k) l = std::max(l, lev[T.col[k]] + 1);
+    lev[i] = l;
+    mx     = std::max(mx, l);
+  };
+  if (!upper)
+    for (std::size_t i = 0; i < m; ++i) row(i);
+  else
+    for (std::size_t i = m; i-- > 0;) row(i);
+  return static_cast<std::size_t>(mx) + 1;
+}
+
+void check_triangular(const HostCsr &T, bool upper, const char *name) {
+  for (std::size_t i = 0; i < T.nrows; ++i)
+    for (unsigned k = T.ptr[i]; k < T.ptr[i + 1]; ++k) {
+      const std::size_t j = static_cast<std::size_t>(T.col[k]);
+      if (upper ? j <= i : j >= i)
+        throw std::invalid_argument(std::string(name) + ": block is not strictly triangular");
+    }
+}
+
+// explicit Q = H_1 H_2 ... H_nm from the Householder vectors stored below the diagonal
+// of the QRCP factor and tau (backward accumulation; LAPACK dorg2r's published scheme).
+// Column k of Q is row k of Q^T: the device computes (Q^T b)_k as a dot product.
+std::vector<double> form_q(std::size_t nm, const double *mat, const double *tau) {
+  std::vector<double> Q(nm * nm, 0.0);
+  for (std::size_t i = 0; i < nm; ++i) Q[i + i * nm] = 1.0;
+  std::vector<double> w(nm);
+  for (std::size_t kk = nm; kk-- > 0;) {
+    const double  tk = tau[kk];
+    if (tk == 0.0) continue;
+    const double *v = mat + kk * nm;  // v = [1; mat(kk+1:nm, kk)] on rows kk..nm-1
+    // Q(kk:, kk:) -= tk * v * (v^T Q(kk:, kk:))
+    for (std::size_t c = kk; c < nm; ++c) {
+      double *qc  = Q.data() + c * nm;
+      double  dot = qc[kk];
+      for (std::size_t i = kk + 1; i < nm; ++i) dot += v[i] * qc[i];
+      w[c] = tk * dot;
+    }
+    for (std::size_t c = kk; c < nm; ++c) {
+      double *     qc = Q.data() + c * nm;
+      const double wc = w[c];
+      qc[kk] -= wc;
+      for (std::size_t i = kk + 1; i < nm; ++i) qc[i] -= wc * v[i];
+    }
+  }
+  return Q;
+}
+
+}  // namespace
+
+Handle *attach_levels(int device, std::size_t nlevels, const LhfdGpuLevel *lv) {
+  if (!nlevels || !lv) throw std::invalid_argument("empty preconditioner (no levels)");
+  int ndev = 0;
+  HIF_CUDA(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) throw std::invalid_argument("invalid CUDA device ordinal");
+  HIF_CUDA(cudaSetDevice(device));
+
+  std::unique_ptr<Handle> h(new Handle());
+  h->device = device;
+  HIF_CUDA(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+  h->stream = h->own_stream;
+  h->levels.resize(nlevels);
+  std::size_t *tally = &h->device_bytes;
+  constexpr std::size_t sv = sizeof(double);
+
+  for (std::size_t l = 0; l < nlevels; ++l) {
+    const LhfdGpuLevel &P = lv[l];
+    DevLevel &          D = h->levels[l];
+    const std::string   tag = "level " + std::to_string(l);
+    if (P.has_symm_dense)
+      throw std::invalid_argument(tag + ": symmetric dense factor (SYEIG) is not supported by the device backend");
+    if (P.m > P.n) throw std::invalid_argument(tag + ": m > n");
+    if (l + 1 < nlevels && P.dense_n) throw std::invalid_argument(tag + ": dense factor on a non-final level");
+    if (l + 1 < nlevels && lv[l + 1].n != P.n - P.m)
+      throw std::invalid_argument(tag + ": next level size does not match n-m");
+    if (P.n > 0x7fffffffull) throw std::invalid_argument(tag + ": n exceeds int32");
+    D.m  = P.m;
+    D.n  = P.n;
+    D.nm = P.n - P.m;
+    if (l + 1 == nlevels && D.nm && P.dense_n != D.nm)
+      throw std::invalid_argument(tag + ": last level has a Schur block but no dense QRCP factor of that order");
+    if (!P.s || !P.t || !P.p || !P.q_inv || (P.m && !P.d_B))
+      throw std::invalid_argument(tag + ": missing scaling/permutation/diagonal array");
+    for (std::size_t i = 0; i < P.n; ++i)
+      if (P.p[i] < 0 || static_cast<std::size_t>(P.p[i]) >= P.n || P.q_inv[i] < 0 ||
+          static_cast<std::size_t>(P.q_inv[i]) >= P.n)
+        throw std::invalid_argument(tag + ": permutation entry out of range");
+
+    HostCsr Lr = ccs_to_csr(P.L_B, "L_B"), Ur = ccs_to_csr(P.U_B, "U_B");
+    HostCsr Er = ccs_to_csr(P.E, "E"), Fr = ccs_to_csr(P.F, "F");
+    // hif leaves default-constructed (0 x 0) blocks when a part is empty
+    Lr.nrows = Lr.ncols = Ur.nrows = Ur.ncols = P.m;
+    Lr.ptr.resize(P.m + 1, Lr.ptr.empty() ? 0u : Lr.ptr.back());
+    Ur.ptr.resize(P.m + 1, Ur.ptr.empty() ? 0u : Ur.ptr.back());
+    Er.ptr.resize(D.nm + 1, Er.ptr.empty() ? 0u : Er.ptr.back());
+    Er.nrows = D.nm, Er.ncols = P.m;
+    Fr.ptr.resize(P.m + 1, Fr.ptr.empty() ? 0u : Fr.ptr.back());
+    Fr.nrows = P.m, Fr.ncols = D.nm;
+    check_triangular(Lr, false, "L_B");
+    check_triangular(Ur, true, "U_B");
+    for (int c : Er.col)
+      if (static_cast<std::size_t>(c) >= P.m) throw std::invalid_argument(tag + ": E column out of range");
+    for (int c : Fr.col)
+      if (static_cast<std::size_t>(c) >= D.nm) throw std::invalid_argument(tag + ": F column out of range");
+    D.depthL = dag_depth(Lr, false);
+    D.depthU = dag_depth(Ur, true);
+
+    upload_csr(Lr, D.L, tally);
+    upload_csr(Ur, D.U, tally);
+    upload_csr(Er, D.E, tally);
+    upload_csr(Fr, D.F, tally);
+    D.d.upload(P.d_B, P.m, tally);
+    D.s.upload(P.s, P.n, tally);
+    D.t.upload(P.t, P.n, tally);
+    D.p.upload(reinterpret_cast<const int *>(P.p), P.n, tally);
+    D.q_inv.upload(reinterpret_cast<const int *>(P.q_inv), P.n, tally);
+
+    D.bhat.alloc(P.n, tally);
+    D.xL_dn.alloc(P.m, tally);
+    D.xU_dn.alloc(P.m, tally);
+    D.xL_up.alloc(P.m, tally);
+    D.xU_up.alloc(P.m, tally);
+    D.g.alloc(P.m, tally);
+    D.r.alloc(D.nm, tally);
+    D.ychild.alloc(D.nm, tally);
+
+    // algorithmic bytes per apply, SURVEY.md section 8(d)
+    const std::size_t k   = D.nm ? 2 : 1;
+    const std::size_t nLU = D.L.nnz + D.U.nnz, nEF = D.E.nnz + D.F.nnz;
+    h->bytes_factors += k * (nLU * (sv + 4) + 2 * (P.m + 1) * 4 + P.m * sv) + nEF * (sv + 4) + (P.n + 2) * 4 +
+                        P.n * (2 * sv + 2 * 4);
+    h->bytes_vec += sv * (D.nm ? (7 * P.n + 8 * P.m) : 8 * P.n);
+    h->nnz_total += nLU + nEF + P.m;
+  }
+
+  const LhfdGpuLevel &last = lv[nlevels - 1];
+  if (last.dense_n) {
+    const std::size_t nm = last.dense_n;
+    if (!last.qr_mat || !last.qr_tau || !last.qr_jpvt) throw std::invalid_argument("dense level: null QRCP arrays");
+    if (last.dense_rank > nm) throw std::invalid_argument("dense level: rank exceeds order");
+    std::vector<char> seen(nm, 0);
+    for (std::size_t i = 0; i < nm; ++i) {
+      const LhfInt j = last.qr_jpvt[i];
+      if (j < 1 || static_cast<std::size_t>(j) > nm || seen[j - 1])
+        throw std::invalid_argument("dense level: jpvt is not a 1-based permutation");
+      seen[j - 1] = 1;
+    }
+    h->dense.nm   = nm;
+    h->dense.rank = last.dense_rank;
+    h->dense.Q.upload(form_q(nm, last.qr_mat, last.qr_tau), tally);
+    h->dense.R.upload(last.qr_mat, nm * nm, tally);
+    h->dense.jpvt.upload(reinterpret_cast<const int *>(last.qr_jpvt), nm, tally);
+    h->dense.c.alloc(nm, tally);
+    h->bytes_dense = nm * nm * sv + nm * (sv + 4);
+    h->nnz_total += nm * nm;
+  }
+
+  h->tickets.alloc(4 * nlevels + 4, tally);
+  h->error_flag.alloc(1, tally);
+  HIF_CUDA(cudaMallocHost(&h->h_error, sizeof(int)));
+  *h->h_error = 0;
+  HIF_CUDA(cudaMallocHost(&h->h_scal, 256 * sizeof(double)));
+  HIF_CUDA(cudaDeviceSynchronize());
+  return h.release();
+}
+
+void set_matrix(Handle *h, bool rowmajor, std::size_t n, const LhfIndPtr *indptr, const LhfInt *indices,
+                const double *vals) {
+  if (n != h->n0()) throw std::length_error("matrix size does not match the preconditioner");
+  if (!indptr) throw std::invalid_argument("null indptr");
+  HIF_CUDA(cudaSetDevice(h->device));
+  HostCsr A;
+  if (rowmajor) {
+    const LhfIndPtr nnz = indptr[n];
+    if (nnz < 0 || static_cast<unsigned long long>(nnz) > 0x7fffffffull)
+      throw std::invalid_argument("A: more than 2^31-1 nonzeros");
+    A.nrows = A.ncols = n;
+    A.ptr.resize(n + 1);
+    for (std::size_t i = 0; i <= n; ++i) A.ptr[i] = static_cast<unsigned>(indptr[i]);
+    A.col.assign(indices, indices + nnz);
+    A.val.assign(vals, vals + nnz);
+    for (int c : A.col)
+      if (c < 0 || static_cast<std::size_t>(c) >= n) throw std::invalid_argument("A: column index out of range");
+  } else {
+    LhfdGpuCcs c{n, n, indptr, indices, vals};
+    A = ccs_to_csr(c, "A");
+  }
+  h->A.n   = n;
+  h->A.nnz = A.col.size();
+  upload_csr(A, h->A.A, &h->device_bytes);
+  h->has_A = true;
+}
+
+}  // namespace hifgpu

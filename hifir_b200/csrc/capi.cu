@@ -1,0 +1,384 @@
+// capi.cu -- the C-ABI of include/hifir_b200.h.  Exceptions never cross this boundary:
+// they become LhfStatus + a thread-local message (cf. libhifir.cpp:45-53, 224-229).
+#include <cstring>
+#include <new>
+
+#include "hifgpu.h"
+
+using namespace hifgpu;
+
+namespace {
+
+thread_local std::string g_msg;
+
+template <class F>
+LhfStatus guarded(F &&f) {
+  try {
+    f();
+    return LHF_SUCCESS;
+  } catch (const std::length_error &e) {
+    g_msg = e.what();
+    return LHF_MISMATCHED_SIZES;
+  } catch (const std::invalid_argument &e) {
+    g_msg = e.what();
+    return LHF_BAD_PREC;
+  } catch (const std::logic_error &e) {
+    g_msg = e.what();
+    return LHF_BAD_PREC;
+  } catch (const std::exception &e) {
+    g_msg = e.what();
+    return LHF_HIFIR_ERROR;
+  } catch (...) {
+    g_msg = "unknown error";
+    return LHF_HIFIR_ERROR;
+  }
+}
+
+Handle *H(LhfdGpuHdl hdl) { return reinterpret_cast<Handle *>(hdl); }
+
+#define REQUIRE_HANDLE(hdl)                 \
+  if (!(hdl)) {                             \
+    g_msg = "NULL device-backend handle";   \
+    return LHF_NULL_OBJ;                    \
+  }
+#define REQUIRE_PTR(p, what)                \
+  if (!(p)) {                               \
+    g_msg = "NULL pointer: " what;          \
+    return LHF_NULL_OBJ;                    \
+  }
+
+void ensure_io(Handle *h, std::size_t cols) {
+  const std::size_t need = h->n0() * cols;
+  if (h->io_b.n < need) {
+    h->io_b.alloc(need, &h->device_bytes);
+    h->io_x.alloc(need, &h->device_bytes);
+  }
+}
+
+// host <-> device copies of the hot path: asynchronous on the handle's stream; pinned
+// caller memory is transferred by DMA directly, pageable memory is staged by the driver
+void h2d(Handle *h, double *dst, const double *src, std::size_t count) {
+  HIF_CUDA(cudaMemcpyAsync(dst, src, count * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+}
+void d2h(Handle *h, double *dst, const double *src, std::size_t count) {
+  HIF_CUDA(cudaMemcpyAsync(dst, src, count * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+}
+
+}  // namespace
+
+// ---- multi-rhs, v1: row-interleaved block <-> contiguous columns ------------------
+namespace hifgpu {
+
+__global__ void col_extract_kernel(const unsigned n, const unsigned nrhs, const unsigned k,
+                                   const double *__restrict__ B, double *__restrict__ out) {
+  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = B[static_cast<std::size_t>(i) * nrhs + k];
+}
+__global__ void col_insert_kernel(const unsigned n, const unsigned nrhs, const unsigned k,
+                                  const double *__restrict__ in, double *__restrict__ X) {
+  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) X[static_cast<std::size_t>(i) * nrhs + k] = in[i];
+}
+
+void apply_mrhs_dev(Handle *h, std::size_t nrhs, const double *d_B, double *d_X, std::size_t rank) {
+  const std::size_t n = h->n0();
+  if (nrhs == 1) {
+    apply_dev(h, d_B, d_X, rank);
+    return;
+  }
+  if (h->mr_b.n < n) {
+    h->mr_b.alloc(n, &h->device_bytes);
+    h->mr_x.alloc(n, &h->device_bytes);
+  }
+  const unsigned T = 256, nb = static_cast<unsigned>((n + T - 1) / T);
+  for (std::size_t k = 0; k < nrhs; ++k) {
+    col_extract_kernel<<<nb, T, 0, h->stream>>>(static_cast<unsigned>(n), static_cast<unsigned>(nrhs),
+                                                static_cast<unsigned>(k), d_B, h->mr_b.p);
+    HIF_KERNEL_CHECK();
+    apply_dev(h, h->mr_b.p, h->mr_x.p, rank);
+    col_insert_kernel<<<nb, T, 0, h->stream>>>(static_cast<unsigned>(n), static_cast<unsigned>(nrhs),
+                                               static_cast<unsigned>(k), h->mr_x.p, d_X);
+    HIF_KERNEL_CHECK();
+    h->launch_count += 2;
+  }
+}
+
+}  // namespace hifgpu
+
+extern "C" {
+
+const char *lhfGpuGetErrorMsg(void) { return g_msg.c_str(); }
+const char *lhfGpuVersion(void) { return "hifir_b200 0.1.0 (sm_100a)"; }
+
+LhfStatus lhfdGpuAttachLevels(int device, size_t nlevels, const LhfdGpuLevel *levels, LhfdGpuHdl *out) {
+  REQUIRE_PTR(out, "out");
+  *out = nullptr;
+  REQUIRE_PTR(levels, "levels");
+  return guarded([&] { *out = reinterpret_cast<LhfdGpuHdl>(attach_levels(device, nlevels, levels)); });
+}
+
+LhfStatus lhfdGpuDestroy(LhfdGpuHdl hdl) {
+  REQUIRE_HANDLE(hdl);
+  return guarded([&] {
+    Handle *h = H(hdl);
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    if (h->h_error) cudaFreeHost(h->h_error);
+    if (h->h_scal) cudaFreeHost(h->h_scal);
+    cudaStream_t s = h->own_stream;
+    delete h;
+    if (s) cudaStreamDestroy(s);
+  });
+}
+
+LhfStatus lhfdGpuSetMatrix(LhfdGpuHdl hdl, int is_rowmajor, size_t n, const LhfIndPtr *indptr,
+                           const LhfInt *indices, const double *vals) {
+  REQUIRE_HANDLE(hdl);
+  REQUIRE_PTR(indptr, "indptr");
+  return guarded([&] { set_matrix(H(hdl), is_rowmajor != 0, n, indptr, indices, vals); });
+}
+
+LhfStatus lhfdGpuSetNspConst(LhfdGpuHdl hdl, size_t start, size_t end) {
+  REQUIRE_HANDLE(hdl);
+  return guarded([&] {
+    Handle *          h = H(hdl);
+    const std::size_t n = h->n0();
+    const std::size_t e = (end == static_cast<std::size_t>(-1) || end < start) ? n : end;
+    if (e < start || e > n) throw std::invalid_argument("null-space filter: wrong range (start,end,n)");
+    h->nsp_on    = true;
+    h->nsp_start = start;
+    h->nsp_end   = end;
+  });
+}
+
+LhfStatus lhfdGpuClearNsp(LhfdGpuHdl hdl) {
+  REQUIRE_HANDLE(hdl);
+  H(hdl)->nsp_on = false;
+  return LHF_SUCCESS;
+}
+
+LhfStatus lhfdGpuSetStream(LhfdGpuHdl hdl, void *cuda_stream) {
+  REQUIRE_HANDLE(hdl);
+  return guarded([&] {
+    Handle *h = H(hdl);
+    HIF_CUDA(cudaSetDevice(h->device));
+    HIF_CUDA(cudaStreamSynchronize(h->stream));
+    h->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : h->own_stream;
+  });
+}
+
+LhfStatus lhfdGpuSynchronize(LhfdGpuHdl hdl) {
+  REQUIRE_HANDLE(hdl);
+  return guarded([&] {
+    HIF_CUDA(cudaSetDevice(H(hdl)->device));
+    check_sweep_error(H(hdl));
+  });
+}
+
+LhfStatus lhfdGpuSolveDev(LhfdGpuHdl hdl, const double *d_b, double *d_x, size_t rank) {
+  REQUIRE_HANDLE(hdl);
+  REQUIRE_PTR(d_b, "b");
+  REQUIRE_PTR(d_x, "x");
+  return guarded([&] { apply_dev(H(hdl), d_b, d_x, rank); });
+}
+
+LhfStatus lhfdGpuSolveMrhsDev(LhfdGpuHdl hdl, size_t nrhs, const double *d_B, double *d_X, size_t rank) {
+  REQUIRE_HANDLE(hdl);
+  REQUIRE_PTR(d_B, "B");
+  REQUIRE_PTR(d_X, "X");
+  if (!nrhs) return LHF_SUCCESS;
+  return guarded([&] {
+    if (H(hdl)->nsp_on) throw std::logic_error("multiple RHS does not support null space filter.");  // builder.hpp:440
+    apply_mrhs_dev(H(hdl), nrhs, d_B, d_X, rank);
+  });
+}
+
+LhfStatus lhfdGpuHifirDev(LhfdGpuHdl hdl, const double *d_b, size_t nirs, double *d_x, size_t rank) {
+  REQUIRE_HANDLE(hdl);
+  REQUIRE_PTR(d_b, "b");
+  REQUIRE_PTR(d_x, "x");
+  return guarded([&] { hifir_dev(H(hdl), d_b, nirs, d_x, rank); });
+}
+
+LhfStatus lhfdGpuSpmvDev(LhfdGpuHdl hdl, const double *d_x, double *d_y) {
+  REQUIRE_HANDLE(hdl);
+  REQUIRE_PTR(d_x, "x");
+  REQUIRE_PTR(d_y, "y");
+  return guarded([&] { spmv_dev(H(hdl), d_x, d_y); });
+}
+
+LhfStatus lhfdGpuSolve(LhfdGpuHdl hdl, const double *b, double *x) {
+  REQUIRE_HANDLE(hdl);
+  REQUIRE_PTR(b, "b");
+  REQUIRE_PTR(x, "x");
+  return guarded([&] {
+    Handle *h = H(hdl);
+    HIF_CUDA(cudaSetDevice(h->device));
+    ensure_io(h, 1);
+    h2d(h, h->io_b.p, b, h->n0());
+    apply_dev(h, h->io_b.p, h->io_x.p, 0);  // lhfdSolve: M->solve(b, x), rank defaults to 0
+    d2h(h, x, h->io_x.p, h->n0());
+    check_sweep_error(h);
+  });
+}
+
+LhfStatus lhfdGpuSolveMrhs(LhfdGpuHdl hdl, size_t nrhs, const double *B, double *X) {
+  REQUIRE_HANDLE(hdl);
+  REQUIRE_PTR(B, "B");
+  REQUIRE_PTR(X, "X");
+  if (!nrhs) return LHF_SUCCESS;
+  return guarded([&] {
+    Handle *h = H(hdl);
+    if (h->nsp_on) throw std::logic_error("multiple RHS does not support null space filter.");  // builder.hpp:440
+    HIF_CUDA(cudaSetDevice(h->device));
+    ensure_io(h, nrhs);
+    h2d(h, h->io_b.p, B, h->n0() * nrhs);
+    apply_mrhs_dev(h, nrhs, h->io_b.p, h->io_x.p, 0);
+    d2h(h, X, h->io_x.p, h->n0() * nrhs);
+    check_sweep_error(h);
+  });
+}
+
+// libhifir.cpp:447-472
+LhfStatus lhfdGpuApply(LhfdGpuHdl hdl, LhfOperationType op, const double *b, int nirs, const double *betas,
+                       int rank, double *x, int *ir_status) {
+  REQUIRE_HANDLE(hdl);
+  REQUIRE_PTR(b, "b");
+  REQUIRE_PTR(x, "x");
+  if (op != LHF_S) {
+    g_msg = "LHF_SH / LHF_M / LHF_MH are not served by the device backend yet (transpose solve and multilevel "
+            "product stay on the host object)";
+    return LHF_BAD_PREC;
+  }
+  return guarded([&] {
+    Handle *h = H(hdl);
+    HIF_CUDA(cudaSetDevice(h->device));
+    // rank defaulting rule, libhifir.cpp:451-455
+    const std::size_t rnk = rank == LHF_DEFAULT_RANK ? (nirs > 1 ? static_cast<std::size_t>(-1) : 0)
+                                                     : static_cast<std::size_t>(static_cast<long long>(rank));
+    ensure_io(h, 1);
+    h2d(h, h->io_b.p, b, h->n0());
+    if (nirs <= 1) {
+      apply_dev(h, h->io_b.p, h->io_x.p, 0);  // plain solve ignores `rank` (libhifir.cpp:461)
+    } else if (!betas) {
+      hifir_dev(h, h->io_b.p, static_cast<std::size_t>(nirs), h->io_x.p, rnk);
+    } else {
+      long iters = 0;
+      int  flag  = 0;
+      hifir_betas_dev(h, h->io_b.p, static_cast<std::size_t>(nirs), betas, h->io_x.p, rnk, &iters, &flag);
+      if (ir_status) {
+        ir_status[0] = static_cast<int>(iters);
+        ir_status[1] = flag;
+      }
+    }
+    d2h(h, x, h->io_x.p, h->n0());
+    check_sweep_error(h);
+  });
+}
+
+static LhfStatus krylov_host(LhfdGpuHdl hdl, bool flexible, const double *b, int restart, double rtol, int maxit,
+                             int full_rank, double *x, int *flag, int *iters, int *num_mv) {
+  REQUIRE_HANDLE(hdl);
+  REQUIRE_PTR(b, "b");
+  REQUIRE_PTR(x, "x");
+  return guarded([&] {
+    Handle *h = H(hdl);
+    HIF_CUDA(cudaSetDevice(h->device));
+    ensure_io(h, 1);
+    h2d(h, h->io_b.p, b, h->n0());
+    int f = 0, it = 0, nmv = 0;
+    krylov_dev(h, flexible, h->io_b.p, restart, rtol, maxit, full_rank != 0, h->io_x.p, &f, &it, &nmv);
+    d2h(h, x, h->io_x.p, h->n0());
+    check_sweep_error(h);
+    if (flag) *flag = f;
+    if (iters) *iters = it;
+    if (num_mv) *num_mv = nmv;
+  });
+}
+
+LhfStatus lhfdGpuFgmres(LhfdGpuHdl hdl, const double *b, int restart, double rtol, int maxit, int full_rank,
+                        double *x, int *flag, int *iters, int *num_mv) {
+  return krylov_host(hdl, true, b, restart, rtol, maxit, full_rank, x, flag, iters, num_mv);
+}
+
+LhfStatus lhfdGpuGmres(LhfdGpuHdl hdl, const double *b, int restart, double rtol, int maxit, double *x, int *flag,
+                       int *iters) {
+  return krylov_host(hdl, false, b, restart, rtol, maxit, 0, x, flag, iters, nullptr);
+}
+
+LhfStatus lhfdGpuProfileSolveDev(LhfdGpuHdl hdl, const double *d_b, double *d_x, size_t rank, size_t max_entries,
+                                 float *ms, size_t *count, char *names, size_t names_len) {
+  REQUIRE_HANDLE(hdl);
+  REQUIRE_PTR(d_b, "b");
+  REQUIRE_PTR(d_x, "x");
+  REQUIRE_PTR(ms, "ms");
+  REQUIRE_PTR(count, "count");
+  return guarded([&] {
+    Handle *h    = H(hdl);
+    h->profiling = true;
+    h->prof_marks.clear();
+    try {
+      apply_dev(h, d_b, d_x, rank);
+      check_sweep_error(h);
+    } catch (...) {
+      h->profiling = false;
+      throw;
+    }
+    h->profiling = false;
+    std::string all;
+    size_t      n = 0;
+    for (size_t k = 1; k < h->prof_marks.size(); ++k) {
+      float t = 0.f;
+      HIF_CUDA(cudaEventElapsedTime(&t, h->prof_marks[k - 1].second, h->prof_marks[k].second));
+      if (n < max_entries) {
+        ms[n++] = t;
+        all += h->prof_marks[k].first + "\n";
+      }
+    }
+    for (auto &m : h->prof_marks) cudaEventDestroy(m.second);
+    h->prof_marks.clear();
+    *count = n;
+    if (names && names_len) {
+      std::strncpy(names, all.c_str(), names_len - 1);
+      names[names_len - 1] = '\0';
+    }
+  });
+}
+
+LhfStatus lhfdGpuGetStats(LhfdGpuHdl hdl, size_t stats[]) {
+  REQUIRE_HANDLE(hdl);
+  REQUIRE_PTR(stats, "stats");
+  Handle *h                             = H(hdl);
+  stats[LHF_GPU_STAT_LEVELS]            = h->levels.size();
+  stats[LHF_GPU_STAT_N]                 = h->n0();
+  stats[LHF_GPU_STAT_NNZ]               = h->nnz_total;
+  stats[LHF_GPU_STAT_DENSE_N]           = h->dense.nm;
+  stats[LHF_GPU_STAT_DENSE_RANK]        = h->dense.rank;
+  stats[LHF_GPU_STAT_BYTES_FACTORS]     = h->bytes_factors;
+  stats[LHF_GPU_STAT_BYTES_VEC_PER_RHS] = h->bytes_vec;
+  stats[LHF_GPU_STAT_BYTES_DENSE]       = h->bytes_dense;
+  stats[LHF_GPU_STAT_DEVICE_BYTES]      = h->device_bytes;
+  stats[LHF_GPU_STAT_KERNELS_PER_APPLY] = h->kernels_per_apply;
+  std::size_t depth = 0;
+  for (const auto &D : h->levels) depth += (D.nm ? 2 : 1) * (D.depthL + D.depthU);
+  stats[LHF_GPU_STAT_DEPTH_TOTAL]  = depth;
+  stats[LHF_GPU_STAT_LAUNCH_COUNT] = h->launch_count;
+  return LHF_SUCCESS;
+}
+
+LhfStatus lhfdGpuGetDepths(LhfdGpuHdl hdl, size_t nlevels, size_t *depth) {
+  REQUIRE_HANDLE(hdl);
+  REQUIRE_PTR(depth, "depth");
+  Handle *h = H(hdl);
+  if (nlevels != h->levels.size()) {
+    g_msg = "level count mismatch";
+    return LHF_MISMATCHED_SIZES;
+  }
+  for (std::size_t l = 0; l < nlevels; ++l) {
+    depth[2 * l]     = h->levels[l].depthL;
+    depth[2 * l + 1] = h->levels[l].depthU;
+  }
+  return LHF_SUCCESS;
+}
+
+}  // extern "C"

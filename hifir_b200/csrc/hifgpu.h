@@ -1,0 +1,153 @@
+// hifgpu.h -- internal host-side structures of the device backend.
+#pragma once
+
+#include <cstddef>
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "../../include/hifir_b200.h"
+#include "common.cuh"
+
+namespace hifgpu {
+
+// device buffer with ownership
+template <class T>
+struct DevBuf {
+  T *         p = nullptr;
+  std::size_t n = 0;
+  DevBuf()      = default;
+  DevBuf(const DevBuf &) = delete;
+  DevBuf &operator=(const DevBuf &) = delete;
+  DevBuf(DevBuf &&o) noexcept : p(o.p), n(o.n) { o.p = nullptr, o.n = 0; }
+  DevBuf &operator=(DevBuf &&o) noexcept {
+    if (this != &o) {
+      release();
+      p = o.p, n = o.n;
+      o.p = nullptr, o.n = 0;
+    }
+    return *this;
+  }
+  ~DevBuf() { release(); }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr, n = 0;
+  }
+  void alloc(std::size_t count, std::size_t *tally = nullptr) {
+    release();
+    n = count;
+    if (count) {
+      HIF_CUDA(cudaMalloc(&p, count * sizeof(T)));
+      HIF_CUDA(cudaMemset(p, 0, count * sizeof(T)));
+      if (tally) *tally += count * sizeof(T);
+    }
+  }
+  void upload(const T *host, std::size_t count, std::size_t *tally = nullptr) {
+    alloc(count, tally);
+    if (count) HIF_CUDA(cudaMemcpy(p, host, count * sizeof(T), cudaMemcpyHostToDevice));
+  }
+  void upload(const std::vector<T> &v, std::size_t *tally = nullptr) { upload(v.data(), v.size(), tally); }
+};
+
+// compressed-row matrix on the device (row-gather form of a reference CCS block)
+struct DevCsr {
+  std::size_t      nrows = 0, ncols = 0, nnz = 0;
+  DevBuf<unsigned> ptr;  // nrows+1
+  DevBuf<int>      col;  // nnz, ascending within a row
+  DevBuf<double>   val;  // nnz
+};
+
+// host CSR used during attach
+struct HostCsr {
+  std::size_t           nrows = 0, ncols = 0;
+  std::vector<unsigned> ptr;
+  std::vector<int>      col;
+  std::vector<double>   val;
+};
+
+// one hif::Prec level on the device (reference alg/Prec.hpp:309-323)
+struct DevLevel {
+  std::size_t m = 0, n = 0, nm = 0;
+  DevCsr      L, U, E, F;
+  DevBuf<double> d;        // m
+  DevBuf<double> s, t;     // n
+  DevBuf<int>    p, q_inv; // n
+  // triangular-sweep schedule
+  int         rows_per_block = 1024;
+  std::size_t depthL = 0, depthU = 0;  // dependency depth (number of level sets)
+  // per-apply work vectors (nrhs = 1 path); tagged = produced by a sync-free sweep
+  DevBuf<double>             bhat;                      // n   s[p]*b[p]
+  DevBuf<unsigned long long> xL_dn, xU_dn, xL_up, xU_up;  // m   tagged
+  DevBuf<double>             g;                         // m   bhat - F*y_child
+  DevBuf<double>             r;                         // nm  Schur rhs = child's b
+  DevBuf<double>             ychild;                    // nm  child's solution
+};
+
+// dense last level: QRCP state (reference small_scale/QRCP.hpp:544-555)
+struct DevDense {
+  std::size_t    nm = 0, rank = 0;
+  DevBuf<double> Q;     // nm x nm column-major explicit Q = H_1 ... H_nm (column k = row k of Q^T)
+  DevBuf<double> R;     // nm x nm column-major, upper triangle = R
+  DevBuf<int>    jpvt;  // nm, 1-based verbatim
+  DevBuf<double> c;     // nm work (Q^T b)
+};
+
+struct DevMatrix {  // user matrix A in CRS
+  std::size_t n = 0, nnz = 0;
+  DevCsr      A;
+};
+
+struct Handle {
+  int                   device = 0;
+  std::vector<DevLevel> levels;
+  DevDense              dense;
+  DevMatrix             A;
+  bool                  has_A = false;
+  bool                  nsp_on = false;
+  std::size_t           nsp_start = 0, nsp_end = 0;
+  cudaStream_t          own_stream = nullptr, stream = nullptr;
+  unsigned              epoch = 0;        // apply counter; parity tags the sync-free buffers
+  DevBuf<int>           tickets;          // one block-ticket counter per sweep of an apply
+  DevBuf<int>           error_flag;       // set by a sweep whose spin limit tripped
+  int *                 h_error = nullptr;  // pinned mirror
+  // scratch for host-buffer entry points / IR / Krylov
+  DevBuf<double> io_b, io_x;
+  std::size_t    io_cols = 0;
+  DevBuf<double> ir_xk, ir_r, ir_t;
+  DevBuf<double> kr_v, kr_w, kr_Q, kr_Z, kr_scal, kr_part;
+  double *       h_scal = nullptr;  // pinned
+  int            kr_restart = 0;
+  // multi-rhs column staging
+  DevBuf<double> mr_b, mr_x;
+  // statistics
+  std::size_t bytes_factors = 0, bytes_vec = 0, bytes_dense = 0, device_bytes = 0, nnz_total = 0;
+  std::size_t kernels_per_apply = 0, launch_count = 0;
+  // optional per-kernel timing of one apply (lhfdGpuProfileSolveDev)
+  bool                                  profiling = false;
+  std::vector<std::pair<std::string, cudaEvent_t>> prof_marks;
+  std::size_t n0() const { return levels.empty() ? 0 : levels[0].n; }
+};
+
+// ---- attach.cu
+Handle *attach_levels(int device, std::size_t nlevels, const LhfdGpuLevel *levels);
+void    set_matrix(Handle *h, bool rowmajor, std::size_t n, const LhfIndPtr *indptr, const LhfInt *indices,
+                   const double *vals);
+HostCsr ccs_to_csr(const LhfdGpuCcs &c, const char *name);
+
+// ---- apply.cu : the multilevel M^{-1} apply on device vectors
+void apply_dev(Handle *h, const double *d_b, double *d_x, std::size_t rank);
+void check_sweep_error(Handle *h);  // synchronizes; throws if a sweep tripped its spin limit
+
+// ---- krylov.cu
+void   spmv_dev(Handle *h, const double *d_x, double *d_y);
+void   hifir_dev(Handle *h, const double *d_b, std::size_t nirs, double *d_x, std::size_t rank);
+void   hifir_betas_dev(Handle *h, const double *d_b, std::size_t nirs, const double *betas, double *d_x,
+                       std::size_t rank, long *iters, int *flag);
+void   krylov_dev(Handle *h, bool flexible, const double *d_b, int restart, double rtol, int maxit,
+                  bool full_rank, double *d_x, int *flag, int *iters, int *num_mv);
+double norm2_dev(Handle *h, const double *d_v, std::size_t n);
+
+// ---- mrhs.cu
+void apply_mrhs_dev(Handle *h, std::size_t nrhs, const double *d_B, double *d_X, std::size_t rank);
+
+}  // namespace hifgpu

@@ -186,6 +186,14 @@ enum {
 };
 LhfStatus lhfdGpuGetStats(LhfdGpuHdl hdl, size_t stats[/* LHF_GPU_NUMBER_STATS */]);
 
+/* Instrumented apply: as lhfdGpuSolveDev, but records a CUDA event after every kernel of
+ * the schedule, synchronizes, and reports each kernel's duration (milliseconds) with a
+ * label such as "lv0.down.L".  names receives the '\n'-separated labels.  For bench /
+ * roofline reporting only -- the events serialize nothing but cost launch overhead. */
+LhfStatus lhfdGpuProfileSolveDev(LhfdGpuHdl hdl, const double *d_b, double *d_x, size_t rank,
+                                 size_t max_entries, float *ms, size_t *count, char *names,
+                                 size_t names_len);
+
 /* per-level dependency depth of the L and U sweeps: depth[2*l], depth[2*l+1] */
 LhfStatus lhfdGpuGetDepths(LhfdGpuHdl hdl, size_t nlevels, size_t *depth);
 

@@ -296,6 +296,46 @@ int hifref_krylov(const void *hdl, int which, const double *b, int restart, doub
   REF_CATCH
 }
 
+// hif::QRCP<double> on a dense row-major n x n matrix: factorize (QRCP.hpp:107-179) and
+// export its state, plus the reference's own solve of b (QRCP.hpp:211-226) -- used to
+// pin the dense-level restatement on the reference's known-answer test
+// (tests/test_sss_qrcp.cpp:16-197).
+int hifref_qrcp_factor_solve(std::size_t n, const double *a_rowmajor, const double *b, double *mat,
+                             double *tau, int *jpvt, std::size_t *rank, double *x) {
+  REF_TRY
+  hif::DenseMatrix<double> D(n, n);
+  for (std::size_t i = 0; i < n; ++i)
+    for (std::size_t j = 0; j < n; ++j) D(i, j) = a_rowmajor[i * n + j];
+  hif::QRCP<double> qr;
+  qr.set_matrix(D);
+  qr.factorize(hif::get_default_options());
+  const auto &acc = static_cast<const QrAcc &>(qr);
+  std::copy_n(qr.mat().data(), n * n, mat);
+  std::copy_n(acc._tau.cbegin(), n, tau);
+  for (std::size_t i = 0; i < n; ++i) jpvt[i] = (int)acc._jpvt[i];
+  *rank = qr.rank();
+  array_t xx(n);
+  std::copy_n(b, n, xx.begin());
+  qr.solve(xx);
+  std::copy_n(xx.cbegin(), n, x);
+  REF_CATCH
+}
+
+// the reference's own CCS -> CRS conversion (hif::CRS(const CCS&)) of one factor block,
+// to check the device backend's index handling bit-exactly. which: 0=L_B 1=U_B 2=E 3=F
+int hifref_export_crs(const void *hdl, int lvl, int which, std::int64_t *row_start, int *col_ind,
+                      double *vals) {
+  REF_TRY
+  const auto &P = level_at(static_cast<const RefHandle *>(hdl), lvl);
+  const level_t::mat_type *M =
+      which == 0 ? &P.L_B : which == 1 ? &P.U_B : which == 2 ? &P.E : &P.F;
+  const level_t::crs_type R(*M);
+  for (std::size_t i = 0; i <= R.nrows(); ++i) row_start[i] = R.row_start()[i];
+  std::copy_n(R.col_ind().cbegin(), R.nnz(), col_ind);
+  std::copy_n(R.vals().cbegin(), R.nnz(), vals);
+  REF_CATCH
+}
+
 double hifref_norm2(const double *v, std::size_t n) {
   const array_t vv(n, const_cast<double *>(v), true);
   return hif::norm2(vv);

@@ -217,3 +217,28 @@ class RefHif:
 def norm2(v):
     v = np.ascontiguousarray(v, dtype=np.float64)
     return lib().hifref_norm2(_p(v), v.size)
+
+
+def qrcp_factor_solve(a_rowmajor, b):
+    """hif::QRCP<double>: factorize a dense matrix, export (mat, tau, jpvt, rank) and the
+    reference's own solution of b."""
+    a = np.ascontiguousarray(a_rowmajor, dtype=np.float64)
+    n = a.shape[0]
+    b = np.ascontiguousarray(b, dtype=np.float64)
+    mat = np.zeros(n * n); tau = np.zeros(n); jp = np.zeros(n, dtype=np.int32); x = np.zeros(n)
+    rank = C.c_size_t()
+    f = lib().hifref_qrcp_factor_solve
+    f.argtypes = [C.c_size_t] + [C.c_void_p] * 7
+    if f(n, _p(a), _p(b), _p(mat), _p(tau), _p(jp), C.byref(rank), _p(x)) != 0:
+        raise RuntimeError(lib().hifref_last_error().decode())
+    return mat, tau, jp, rank.value, x
+
+
+def export_crs(M, lvl, which, nrows, nnz):
+    """the reference's own CRS(CCS) conversion of block `which` (0=L,1=U,2=E,3=F) of level lvl"""
+    rs = np.zeros(nrows + 1, dtype=np.int64); ci = np.zeros(nnz, dtype=np.int32); va = np.zeros(nnz)
+    f = lib().hifref_export_crs
+    f.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    if f(M._h, lvl, which, _p(rs), _p(ci), _p(va)) != 0:
+        raise RuntimeError(lib().hifref_last_error().decode())
+    return rs, ci, va

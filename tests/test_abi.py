@@ -1,0 +1,81 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library builds, loads and exports every
+symbol include/hifir_b200.h declares; argument validation works without a GPU."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import hifir_b200 as hb
+from conftest import ROOT, gpu_available, load_golden
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from hifir_b200 import build
+    build.build()
+    return hb.lib()
+
+
+def _declared_symbols():
+    src = open(os.path.join(ROOT, "include", "hifir_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(lhf\w*Gpu\w*)\s*\(", src)))
+
+
+def test_header_symbols_are_exported(lib):
+    names = _declared_symbols()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/hifir_b200.h but not exported"
+    assert set(names) == set(hb.EXPORTED_SYMBOLS)
+
+
+def test_version_and_enums(lib):
+    assert b"sm_100a" in lib.lhfGpuVersion()
+    assert (hb.LHF_SUCCESS, hb.LHF_NULL_OBJ, hb.LHF_MISMATCHED_SIZES, hb.LHF_BAD_PREC, hb.LHF_HIFIR_ERROR) == (
+        0, 1, 2, 3, 4)  # libhifir.h:148-154
+    assert (hb.LHF_S, hb.LHF_SH, hb.LHF_M, hb.LHF_MH) == (0, 1, 2, 3)  # libhifir.h:160-165
+    assert hb.LHF_DEFAULT_RANK == -2  # libhifir.h:167
+
+
+def test_null_handle_is_refused(lib):
+    x = np.zeros(4)
+    p = x.ctypes.data_as(C.c_void_p)
+    assert lib.lhfdGpuSolve(None, p, p) == hb.LHF_NULL_OBJ
+    assert lib.lhfdGpuApply(None, hb.LHF_S, p, 1, None, hb.LHF_DEFAULT_RANK, p, None) == hb.LHF_NULL_OBJ
+    assert lib.lhfdGpuDestroy(None) == hb.LHF_NULL_OBJ
+    assert lib.lhfdGpuSolveMrhs(None, 2, p, p) == hb.LHF_NULL_OBJ
+    assert lib.lhfdGpuFgmres(None, p, 30, 1e-6, 500, 0, p, None, None, None) == hb.LHF_NULL_OBJ
+    assert b"NULL" in lib.lhfGpuGetErrorMsg()
+    out = C.c_void_p()
+    assert lib.lhfdGpuAttachLevels(0, 0, None, C.byref(out)) == hb.LHF_NULL_OBJ
+
+
+def test_level_struct_layout_matches_header():
+    """ctypes mirror of LhfdGpuLevel: field order/size must follow include/hifir_b200.h."""
+    assert C.sizeof(hb.LhfdGpuCcs) == 5 * 8
+    assert C.sizeof(hb.LhfdGpuLevel) == 2 * 8 + 4 * 40 + 7 * 8 + 2 * 8 + 3 * 8 + 8
+    arr, keep = hb.make_level_structs(load_golden("poisson14_ml").levels)
+    assert arr[0].m == 2544 and arr[0].n == 2744 and arr[1].dense_n == 1
+    assert arr[0].L_B.nrows == 2544 and arr[0].E.nrows == 200 and arr[0].F.ncols == 200
+
+
+@pytest.mark.skipif(gpu_available(), reason="checks the no-GPU failure mode")
+def test_attach_without_gpu_fails_loudly(lib):
+    """No CPU fallback: without a CUDA device attach must fail with a message, not emulate."""
+    with pytest.raises(hb.LhfError) as e:
+        hb.GpuHif(load_golden("poisson14_ml").levels)
+    assert e.value.status == hb.LHF_HIFIR_ERROR
+    assert "cuda" in str(e.value).lower()
+
+
+def test_product_never_imports_oracle():
+    """The package must not reach into oracle/ (only tests, bench cpu legs and smoke may)."""
+    pkg = os.path.join(ROOT, "hifir_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in txt.replace("the parity oracle", ""), f"{f} mentions oracle"

@@ -1,0 +1,211 @@
+"""GPU parity tests proper (-m gpu): the CUDA path, called through the C-ABI, against
+  * the committed golden vectors of the unmodified reference,
+  * the plain-C oracle on the same seeded inputs,
+  * the reference itself, live, on the very object the device backend was attached to
+    (through the header-only C++ adapter), when oracle/_ref travelled to this box,
+  * size-independent properties at larger sizes (linearity, M (M^-1 b) = b round trip).
+Tolerance (north_star): ||x_gpu - x_ref|| / ||x_ref|| <= 1e-12 in double; iteration counts +-1."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import hifir_b200 as hb
+from conftest import TOL_F64, have_reference, load_golden, relerr
+from hifir_b200 import problems as P
+from oracle import port as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _built():
+    from hifir_b200 import build
+    build.build()
+    assert b"sm_100a" in hb.lib().lhfGpuVersion()
+
+
+def _gpu(g):
+    G = hb.GpuHif(g.levels)
+    G.set_matrix(g.A)
+    if g.nsp:
+        G.set_nsp_const()
+    return G
+
+
+def test_solve_matches_golden_and_oracle(golden):
+    Oh = O.OracleHif(golden.levels, golden.A)
+    if golden.nsp:
+        Oh.set_nsp_const()
+    with _gpu(golden) as G:
+        st = G.stats()
+        assert st["n"] == golden.n and st["levels"] == len(golden.levels)
+        for k in range(golden["B"].shape[1]):
+            b = np.ascontiguousarray(golden["B"][:, k])
+            x = G.solve(b)
+            assert relerr(x, golden["X"][:, k]) <= TOL_F64, "vs reference golden"
+            assert relerr(x, Oh.solve(b)) <= TOL_F64, "vs C oracle"
+        # repeated applies flip the ready-bit parity: results must not depend on it
+        b = np.ascontiguousarray(golden["B"][:, 0])
+        x1, x2, x3 = G.solve(b), G.solve(b), G.solve(b)
+        assert np.array_equal(x1, x3) and relerr(x2, x1) <= 1e-15
+
+
+def test_apply_semantics_follow_libhifir(golden):
+    """lhfdApply (libhifir.cpp:447-472): op, nirs, betas, rank and ir_status."""
+    with _gpu(golden) as G:
+        b = np.ascontiguousarray(golden["B"][:, 0])
+        x, _ = G.apply(b)  # LHF_S, nirs=1 -> plain solve, rank ignored
+        assert relerr(x, golden["X"][:, 0]) <= TOL_F64
+        x, _ = G.apply(b, rank=5)  # plain solve ignores rank (libhifir.cpp:461)
+        assert relerr(x, golden["X"][:, 0]) <= TOL_F64
+        x, _ = G.apply(b, nirs=3)  # hifir, default rank -> full (libhifir.cpp:453-455)
+        assert relerr(x, golden["x_hifir3"]) <= TOL_F64
+        x, (iters, flag) = G.apply(golden["b_krylov"], nirs=16, betas=[1e-8, 1e10])
+        riters, rflag = (int(v) for v in golden["hifir_betas_status"])
+        assert flag == rflag and abs(iters - riters) <= 1
+        assert relerr(x, golden["x_hifir_betas"]) <= 1e-8
+        for op in (hb.LHF_SH, hb.LHF_M, hb.LHF_MH):
+            with pytest.raises(hb.LhfError) as e:
+                G.apply(b, op=op)
+            assert e.value.status == hb.LHF_BAD_PREC
+
+
+def test_full_rank_device_solve(golden):
+    import torch
+    with _gpu(golden) as G:
+        b = torch.from_numpy(np.ascontiguousarray(golden["B"][:, 1])).cuda()
+        x = torch.empty_like(b)
+        if golden.nsp:
+            G.clear_nsp()
+        G.solve_dev(b.data_ptr(), x.data_ptr(), hb.FULL_RANK)
+        G.synchronize()
+        if not golden.nsp:
+            assert relerr(x.cpu().numpy(), golden["X_full"][:, 1]) <= TOL_F64
+        # truncated last-level rank (QRCP.hpp:376-377) vs the C oracle
+        dn = golden.levels[-1]["dense_n"]
+        if dn > 2:
+            Oh = O.OracleHif(golden.levels)
+            G.solve_dev(b.data_ptr(), x.data_ptr(), dn - 1)
+            G.synchronize()
+            assert relerr(x.cpu().numpy(), Oh.solve(b.cpu().numpy(), dn - 1)) <= TOL_F64
+
+
+@pytest.mark.parametrize("which", ["fgmres", "gmres"])
+def test_krylov_iteration_parity(golden, which):
+    if which == "gmres" and golden.name == "stokes28_ml":
+        pytest.skip("230-iteration GMRES: covered by fgmres on this case")
+    with _gpu(golden) as G:
+        if which == "fgmres":
+            x, flag, iters, nmv = G.fgmres(golden["b_krylov"], restart=golden.restart)
+        else:
+            x, flag, iters = G.gmres(golden["b_krylov"], restart=golden.restart)
+            nmv = iters
+        rflag, riters, rnmv = (int(v) for v in golden[which + "_status"])
+        assert flag == rflag
+        assert abs(iters - riters) <= 1, (iters, riters)
+        assert abs(nmv - rnmv) <= max(1, rnmv // max(riters, 1))
+        # both satisfy ||b - A x|| <= rtol ||b||; the iterates agree far below rtol
+        r = golden["b_krylov"] - P.csr_matvec(golden.A, x)
+        assert np.linalg.norm(r) <= 2e-6 * np.linalg.norm(golden["b_krylov"])
+        assert relerr(x, golden["x_" + which]) <= 1e-5
+
+
+def test_mrhs_is_column_loop_of_solves(golden):
+    """Row-interleaved B[i*nrhs+k] (builder.hpp:433-445); semantics = nrhs HIF::solve calls."""
+    with _gpu(golden) as G:
+        if golden.nsp:
+            with pytest.raises(hb.LhfError):  # builder.hpp:440
+                G.solve_mrhs(golden["B"])
+            G.clear_nsp()
+            Oh = O.OracleHif(golden.levels)
+            ref = Oh.solve_mrhs(golden["B"])
+        else:
+            ref = golden["X"]
+        X = G.solve_mrhs(golden["B"])
+        for k in range(ref.shape[1]):
+            assert relerr(X[:, k], ref[:, k]) <= TOL_F64
+        B3 = np.ascontiguousarray(golden["B"][:, :3])  # ragged width
+        X3 = G.solve_mrhs(B3)
+        assert relerr(X3, ref[:, :3]) <= TOL_F64
+
+
+def test_spmv_and_errors(golden):
+    import torch
+    with _gpu(golden) as G:
+        x = torch.from_numpy(P.seeded_rhs(golden.n, 5)).cuda()
+        y = torch.empty_like(x)
+        G.spmv_dev(x.data_ptr(), y.data_ptr())
+        G.synchronize()
+        assert relerr(y.cpu().numpy(), P.csr_matvec(golden.A, x.cpu().numpy())) <= 1e-14
+    with hb.GpuHif(golden.levels) as G2:  # no matrix attached
+        with pytest.raises(hb.LhfError) as e:
+            G2.apply(golden["B"][:, 0].copy(), nirs=2)
+        assert e.value.status == hb.LHF_BAD_PREC
+        bad = (4, np.zeros(5, dtype=np.int64), np.zeros(0, dtype=np.int32), np.zeros(0))
+        with pytest.raises(hb.LhfError) as e:
+            G2.set_matrix(bad)
+        assert e.value.status == hb.LHF_MISMATCHED_SIZES
+
+
+def test_attach_rejects_bad_input():
+    g = load_golden("poisson14_ml")
+    lv = [dict(L) for L in g.levels]
+    lv[0]["has_symm_dense"] = 1
+    with pytest.raises(hb.LhfError) as e:
+        hb.GpuHif(lv)
+    assert e.value.status == hb.LHF_BAD_PREC
+    lv = [dict(L) for L in g.levels]
+    p = lv[0]["p"].copy()
+    p[0] = g.n + 3
+    lv[0]["p"] = p
+    with pytest.raises(hb.LhfError):
+        hb.GpuHif(lv)
+
+
+def test_linearity_and_zero_rhs():
+    """size-independent properties: M^-1 is linear; M^-1 0 = 0."""
+    g = load_golden("stokes28_ml")
+    with _gpu(g) as G:
+        b1, b2 = P.seeded_rhs(g.n, 11), P.seeded_rhs(g.n, 12)
+        x1, x2, x12 = G.solve(b1), G.solve(b2), G.solve(2.0 * b1 - 3.0 * b2)
+        assert relerr(x12, 2.0 * x1 - 3.0 * x2) <= 1e-11
+        assert np.all(G.solve(np.zeros(g.n)) == 0.0)
+
+
+# ------------------------------------------------------------------ live reference
+needs_ref = pytest.mark.skipif(not have_reference(), reason="oracle/_ref/libhifir_ref.so not on this box")
+
+
+def _attach_through_cxx_adapter(M):
+    """hifir_b200::attach(hif::HIF&) of include/hifir_b200.hpp, compiled into the reference bridge."""
+    fn = C.cast(hb.lib().lhfdGpuAttachLevels, C.c_void_p).value
+    return hb.GpuHif(raw_handle=M.gpu_attach(fn))
+
+
+@needs_ref
+@pytest.mark.parametrize("case,N", [("poisson", 40), ("convdiff", 36), ("stokes", 96), ("neumann", 32)])
+def test_against_live_reference_same_object(case, N):
+    from oracle import refhost as R
+    gen = {"poisson": P.poisson3d, "convdiff": P.convdiff3d, "stokes": P.stokes2d_mac, "neumann": P.neumann3d}[case]
+    A = gen(N)
+    M = R.RefHif(A, P.PDE_PARAMS, dense_thres=300 if case != "stokes" else 0)
+    with _attach_through_cxx_adapter(M) as G:
+        G.set_matrix(A)
+        if case == "neumann":
+            M.set_nsp_const()
+            G.set_nsp_const()
+        assert G.stats()["levels"] == M.num_precs
+        for j in range(3):
+            b = P.seeded_rhs(A[0], j)
+            assert relerr(G.solve(b), M.solve(b)) <= TOL_F64
+        b = P.seeded_rhs(A[0], 0)
+        x, _ = G.apply(b, nirs=4)
+        assert relerr(x, M.hifir(b, 4)) <= TOL_F64
+        if case != "neumann":  # libhifir/tests/test_real.c:146 round trip through the reference's M x
+            assert relerr(M.mmultiply(G.solve(b)), b) <= 1e-10
+        bk = P.csr_matvec(A, np.ones(A[0]) if case != "neumann" else np.sin(0.37 * np.arange(A[0])))
+        xr, fr, ir, nr = M.krylov(bk, "fgmres")
+        xg, fg, ig, ng = G.fgmres(bk)
+        assert fg == fr and abs(ig - ir) <= 1, (ig, ir)
+        assert relerr(xg, xr) <= 1e-5
