@@ -258,6 +258,7 @@ def run_ours(args, rank, world, local_rank):
     if rank != 0:
         return
 
+    st = G.stats()
     bytes_apply = st["bytes_factors"] + st["bytes_dense"] + st["bytes_vec_per_rhs"]
     peak, peak_src = hbm_peak()
     achieved = bytes_apply / (ms_step * 1e-3) / 1e9

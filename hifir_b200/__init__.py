@@ -102,7 +102,7 @@ def lib():
             "lhfdGpuSetMatrix": [vp, i, sz, vp, vp, vp],
             "lhfdGpuSetNspConst": [vp, sz, sz],
             "lhfdGpuClearNsp": [vp],
-            "lhfdGpuSetStream": [vp, vp],
+            "lhfdGpuSetStream": [vp, vp, i],
             "lhfdGpuSynchronize": [vp],
             "lhfdGpuSolve": [vp, vp, vp],
             "lhfdGpuApply": [vp, i, vp, i, vp, i, vp, vp],
@@ -199,8 +199,12 @@ class GpuHif:
     def clear_nsp(self):
         _chk(lib().lhfdGpuClearNsp(self._h))
 
-    def set_stream(self, stream_ptr):
-        _chk(lib().lhfdGpuSetStream(self._h, C.c_void_p(stream_ptr)))
+    def set_stream(self, stream_ptr=None):
+        """stream_ptr: raw cudaStream_t (0 = legacy default stream); None = the handle's own stream"""
+        if stream_ptr is None:
+            _chk(lib().lhfdGpuSetStream(self._h, None, 1))
+        else:
+            _chk(lib().lhfdGpuSetStream(self._h, C.c_void_p(stream_ptr), 0))
 
     def synchronize(self):
         _chk(lib().lhfdGpuSynchronize(self._h))

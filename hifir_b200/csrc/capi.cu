@@ -157,13 +157,13 @@ LhfStatus lhfdGpuClearNsp(LhfdGpuHdl hdl) {
   return LHF_SUCCESS;
 }
 
-LhfStatus lhfdGpuSetStream(LhfdGpuHdl hdl, void *cuda_stream) {
+LhfStatus lhfdGpuSetStream(LhfdGpuHdl hdl, void *cuda_stream, int use_own_stream) {
   REQUIRE_HANDLE(hdl);
   return guarded([&] {
     Handle *h = H(hdl);
     HIF_CUDA(cudaSetDevice(h->device));
     HIF_CUDA(cudaStreamSynchronize(h->stream));
-    h->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : h->own_stream;
+    h->stream = use_own_stream ? h->own_stream : static_cast<cudaStream_t>(cuda_stream);
   });
 }
 

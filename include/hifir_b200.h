@@ -117,10 +117,11 @@ LhfStatus lhfdGpuSetMatrix(LhfdGpuHdl hdl, int is_rowmajor, size_t n, const LhfI
 LhfStatus lhfdGpuSetNspConst(LhfdGpuHdl hdl, size_t start, size_t end);
 LhfStatus lhfdGpuClearNsp(LhfdGpuHdl hdl);
 
-/* Run all work of this handle on `cuda_stream` (a cudaStream_t passed as void*;
- * NULL = the handle's own stream).  Lets a host framework (e.g. torch) time the
- * kernels with events on its current stream. */
-LhfStatus lhfdGpuSetStream(LhfdGpuHdl hdl, void *cuda_stream);
+/* Run all work of this handle on `cuda_stream` (a cudaStream_t passed as void*; NULL is
+ * the legacy default stream) or, with use_own_stream != 0, on the handle's own
+ * non-blocking stream (the state after attach).  Lets a host framework (e.g. torch)
+ * time the kernels with events on its current stream. */
+LhfStatus lhfdGpuSetStream(LhfdGpuHdl hdl, void *cuda_stream, int use_own_stream);
 /* block until all work queued on the handle's stream finished */
 LhfStatus lhfdGpuSynchronize(LhfdGpuHdl hdl);
 

@@ -48,7 +48,7 @@ def test_solve_matches_golden_and_oracle(golden):
         # repeated applies flip the ready-bit parity: results must not depend on it
         b = np.ascontiguousarray(golden["B"][:, 0])
         x1, x2, x3 = G.solve(b), G.solve(b), G.solve(b)
-        assert np.array_equal(x1, x3) and relerr(x2, x1) <= 1e-15
+        assert np.array_equal(x1, x3) and relerr(x2, x1) <= 1e-14
 
 
 def test_apply_semantics_follow_libhifir(golden):
