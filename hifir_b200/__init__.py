@@ -114,6 +114,7 @@ def lib():
             "lhfdGpuHifirDev": [vp, vp, sz, vp, sz],
             "lhfdGpuSpmvDev": [vp, vp, vp],
             "lhfdGpuProfileSolveDev": [vp, vp, vp, sz, sz, vp, vp, vp, sz],
+            "lhfdGpuDebugSweepHost": [vp, i, vp, vp, vp, vp],
             "lhfdGpuGetStats": [vp, vp],
             "lhfdGpuGetDepths": [vp, sz, vp],
         }
@@ -131,7 +132,7 @@ EXPORTED_SYMBOLS = (
     "lhfdGpuAttachLevels", "lhfdGpuDestroy", "lhfdGpuSetMatrix", "lhfdGpuSetNspConst", "lhfdGpuClearNsp",
     "lhfdGpuSetStream", "lhfdGpuSynchronize", "lhfdGpuSolve", "lhfdGpuApply", "lhfdGpuSolveMrhs",
     "lhfdGpuFgmres", "lhfdGpuGmres", "lhfdGpuSolveDev", "lhfdGpuSolveMrhsDev", "lhfdGpuHifirDev",
-    "lhfdGpuSpmvDev", "lhfdGpuProfileSolveDev", "lhfdGpuGetStats", "lhfdGpuGetDepths", "lhfGpuGetErrorMsg", "lhfGpuVersion")
+    "lhfdGpuSpmvDev", "lhfdGpuProfileSolveDev", "lhfdGpuDebugSweepHost", "lhfdGpuGetStats", "lhfdGpuGetDepths", "lhfGpuGetErrorMsg", "lhfGpuVersion")
 
 
 class LhfError(RuntimeError):
@@ -143,6 +144,23 @@ class LhfError(RuntimeError):
 def _chk(st):
     if st != LHF_SUCCESS:
         raise LhfError(st, (lib().lhfGpuGetErrorMsg() or b"").decode())
+
+
+def debug_sweep_host(block, upper, rhs, diag=None):
+    """Host-only hook (lhfdGpuDebugSweepHost): pack the triangular CCS block into device slabs
+    and solve with them on the CPU.  Returns (x, stats dict)."""
+    nr, nc, cs, ri, va = block
+    cs = np.ascontiguousarray(cs, dtype=np.int64)
+    ri = np.ascontiguousarray(ri, dtype=np.int32)
+    va = np.ascontiguousarray(va, dtype=np.float64)
+    c = LhfdGpuCcs(nr, nc, _ptr(cs), _ptr(ri), _ptr(va))
+    rhs = np.ascontiguousarray(rhs, dtype=np.float64)
+    x = np.zeros_like(rhs)
+    st = np.zeros(4, dtype=np.uint64)
+    d = None if diag is None else np.ascontiguousarray(diag, dtype=np.float64)
+    _chk(lib().lhfdGpuDebugSweepHost(C.byref(c), int(upper), _ptr(rhs), _ptr(d) if d is not None else None,
+                                     _ptr(x), _ptr(st)))
+    return x, dict(zip(("blocks", "halo", "bytes", "max_smem"), (int(v) for v in st)))
 
 
 class GpuHif:

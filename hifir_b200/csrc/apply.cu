@@ -4,8 +4,8 @@
 // The reference's recursion over levels unrolls into a down-sweep, the dense solve and
 // an up-sweep.  Per level l (m, n, nm = n-m):
 //   down:  bhat = s[p] .* b[p]                                  (gather_scale_kernel)
-//          xL   = L^{-1} bhat[0:m]                              (sptrsv_block_kernel<LOWER>)
-//          xU   = U^{-1} (xL ./ d)                              (sptrsv_block_kernel<UPPER>)
+//          xL   = L^{-1} bhat[0:m]                              (sptrsv_slab_kernel<LOWER>, sptrsv.cu)
+//          xU   = U^{-1} (xL ./ d)                              (sptrsv_slab_kernel<UPPER>)
 //          r    = bhat[m:n] - E xU         -> b of level l+1    (spmv_resid_kernel)
 //   last:  ychild = P R^{-1} Q^T r                              (dense_qt_kernel, dense_trsv_kernel)
 //   up:    g    = bhat[0:m] - F ychild                          (spmv_resid_kernel)
@@ -16,79 +16,6 @@
 #include "hifgpu.h"
 
 namespace hifgpu {
-
-// ============================================================================
-// Block sync-free sparse triangular solve
-// ============================================================================
-// One CTA owns kRows consecutive rows in sweep order (forward for L, backward for U)
-// and takes its block index from a ticket counter, so that every block a CTA waits on
-// is already resident or finished (no deadlock, no per-level-set kernel launches).
-// One thread per row.  A dependency on a row of the same block is read from shared
-// memory (the reference's factors come out of AMD + Crout with strong index locality:
-// ~60% of all dependencies and nearly the whole critical path stay inside a
-// 1024-row block), a dependency on an earlier block is polled from global
-// memory (L2).  Values carry their own ready bit (common.cuh), so one 8-byte load
-// delivers data and readiness, and there are no fences on the critical path.
-//
-// Summation order per row = the reference's: CCS::solve_as_strict_lower sweeps the
-// columns j ascending, CCS::solve_as_strict_upper descending
-// (ds/CompressedStorage.hpp:2267-2279, 2356-2369), so y[i] receives its updates in
-// exactly this order; only FMA contraction differs.
-constexpr int kRows = 1024;
-
-template <bool UPPER>
-__global__ void __launch_bounds__(kRows, 1)
-    sptrsv_block_kernel(const unsigned m, const unsigned *__restrict__ ptr, const int *__restrict__ col,
-                        const double *__restrict__ val, const double *__restrict__ rhs_plain,
-                        const unsigned long long *rhs_tagged, const double *__restrict__ diag,
-                        unsigned long long *x, const unsigned parity, int *ticket, int *error_flag) {
-  __shared__ unsigned                    s_blk;
-  __shared__ volatile unsigned long long xs[kRows];
-  const unsigned                         tid = threadIdx.x;
-  if (tid == 0) s_blk = static_cast<unsigned>(atomicAdd(ticket, 1));
-  xs[tid] = parity ^ 1u;  // "not ready" pattern
-  __syncthreads();
-  const unsigned s0 = s_blk * kRows;
-  const unsigned s  = s0 + tid;
-  if (s >= m) return;
-  const unsigned i = UPPER ? m - 1u - s : s;
-
-  double acc;
-  if (UPPER) {
-    // y = D^{-1} L^{-1} b is formed on the fly (prec_solve.hpp:219): true division
-    acc = tag_value(rhs_tagged[i]) / diag[i];
-  } else {
-    acc = rhs_plain[i];
-  }
-  const unsigned begin = ptr[i], n = ptr[i + 1] - begin;
-  unsigned       k = 0, spins = 0;
-  bool           done = false;
-  // The publish step sits INSIDE the loop: a finished lane must store its value before
-  // the warp reconverges, because a sibling lane may be waiting for exactly that value.
-  while (!done) {
-    if (k < n) {
-      const unsigned idx = UPPER ? begin + n - 1u - k : begin + k;
-      const int      j   = ldg_stream(col + idx);
-      const double   a   = ldg_stream(val + idx);
-      const unsigned sj  = UPPER ? m - 1u - static_cast<unsigned>(j) : static_cast<unsigned>(j);
-      const unsigned long long bits = (sj >= s0) ? xs[sj - s0] : ld_poll(x + j);
-      if (tag_ready(bits, parity)) {
-        acc = fma(-a, tag_value(bits), acc);
-        ++k;
-        spins = 0;
-      } else if (++spins > kSpinLimit) {
-        *error_flag = 1;
-        k           = n;  // give up: publish garbage so that dependants terminate too
-      }
-    }
-    if (k >= n) {
-      const unsigned long long bits = tag_set(acc, parity);
-      xs[tid]                       = bits;
-      st_publish(x + i, bits);
-      done = true;
-    }
-  }
-}
 
 // ============================================================================
 // glue kernels
@@ -266,16 +193,10 @@ void mark(Handle *h, const std::string &name) {
 void launch_sweeps(Handle *h, DevLevel &D, const double *rhs, unsigned long long *xL, unsigned long long *xU,
                    unsigned parity, int *tickets, const std::string &tag) {
   if (!D.m) return;
-  const unsigned m = static_cast<unsigned>(D.m), nb = cdiv(D.m, kRows);
-  sptrsv_block_kernel<false><<<nb, kRows, 0, h->stream>>>(m, D.L.ptr.p, D.L.col.p, D.L.val.p, rhs, nullptr, nullptr,
-                                                           xL, parity, tickets, h->error_flag.p);
-  HIF_KERNEL_CHECK();
+  launch_sweep(h, D.L, rhs, nullptr, nullptr, xL, parity, tickets);
   mark(h, tag + "L");
-  sptrsv_block_kernel<true><<<nb, kRows, 0, h->stream>>>(m, D.U.ptr.p, D.U.col.p, D.U.val.p, nullptr, xL, D.d.p, xU,
-                                                          parity, tickets + 1, h->error_flag.p);
-  HIF_KERNEL_CHECK();
+  launch_sweep(h, D.U, nullptr, xL, D.d.p, xU, parity, tickets + 1);
   mark(h, tag + "U");
-  h->launch_count += 2;
 }
 
 template <bool TAGGED>

@@ -170,8 +170,10 @@ Handle *attach_levels(int device, std::size_t nlevels, const LhfdGpuLevel *lv) {
     D.depthL = dag_depth(Lr, false);
     D.depthU = dag_depth(Ur, true);
 
-    upload_csr(Lr, D.L, tally);
-    upload_csr(Ur, D.U, tally);
+    build_sweep_plan(Lr, false, D.L, tally);
+    build_sweep_plan(Ur, true, D.U, tally);
+    D.L.nnz = Lr.col.size();
+    D.U.nnz = Ur.col.size();
     upload_csr(Er, D.E, tally);
     upload_csr(Fr, D.F, tally);
     D.d.upload(P.d_B, P.m, tally);

@@ -345,6 +345,21 @@ LhfStatus lhfdGpuProfileSolveDev(LhfdGpuHdl hdl, const double *d_b, double *d_x,
   });
 }
 
+LhfStatus lhfdGpuDebugSweepHost(const LhfdGpuCcs *T, int upper, const double *rhs, const double *diag, double *x,
+                                size_t stats[4]) {
+  REQUIRE_PTR(T, "T");
+  REQUIRE_PTR(rhs, "rhs");
+  REQUIRE_PTR(x, "x");
+  REQUIRE_PTR(stats, "stats");
+  return guarded([&] {
+    if (upper && !diag) throw std::invalid_argument("upper sweep needs the diagonal");
+    HostCsr R = ccs_to_csr(*T, "T");
+    R.nrows = R.ncols = T->ncols;
+    R.ptr.resize(T->ncols + 1, R.ptr.empty() ? 0u : R.ptr.back());
+    sweep_host_emulate(R, upper != 0, rhs, diag, x, stats);
+  });
+}
+
 LhfStatus lhfdGpuGetStats(LhfdGpuHdl hdl, size_t stats[]) {
   REQUIRE_HANDLE(hdl);
   REQUIRE_PTR(stats, "stats");

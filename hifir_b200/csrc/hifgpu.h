@@ -65,10 +65,20 @@ struct HostCsr {
   std::vector<double>   val;
 };
 
+// a strictly triangular factor cut into shared-memory sized slabs (sptrsv.cu)
+struct SweepPlan {
+  unsigned               m = 0, nblocks = 0, smem_bytes = 0;
+  bool                   upper = false;
+  std::size_t            slab_bytes = 0, halo_total = 0, nnz = 0;
+  DevBuf<unsigned char>  slabs;  // packed slabs
+  DevBuf<unsigned char>  info;   // SlabInfo[nblocks]
+};
+
 // one hif::Prec level on the device (reference alg/Prec.hpp:309-323)
 struct DevLevel {
   std::size_t m = 0, n = 0, nm = 0;
-  DevCsr      L, U, E, F;
+  SweepPlan   L, U;  // L_B, U_B as slabs
+  DevCsr      E, F;
   DevBuf<double> d;        // m
   DevBuf<double> s, t;     // n
   DevBuf<int>    p, q_inv; // n
@@ -133,6 +143,13 @@ Handle *attach_levels(int device, std::size_t nlevels, const LhfdGpuLevel *level
 void    set_matrix(Handle *h, bool rowmajor, std::size_t n, const LhfIndPtr *indptr, const LhfInt *indices,
                    const double *vals);
 HostCsr ccs_to_csr(const LhfdGpuCcs &c, const char *name);
+
+// ---- sptrsv.cu : block sync-free triangular sweeps
+void build_sweep_plan(const HostCsr &T, bool upper, SweepPlan &plan, std::size_t *tally);
+void sweep_host_emulate(const HostCsr &T, bool upper, const double *rhs, const double *diag, double *x,
+                        std::size_t stats[4]);
+void launch_sweep(Handle *h, const SweepPlan &plan, const double *rhs_plain, const unsigned long long *rhs_tagged,
+                  const double *diag, unsigned long long *x, unsigned parity, int *ticket);
 
 // ---- apply.cu : the multilevel M^{-1} apply on device vectors
 void apply_dev(Handle *h, const double *d_b, double *d_x, std::size_t rank);

@@ -1,0 +1,371 @@
+// sptrsv.cu -- block sync-free sparse triangular solve with TMA-staged factor slabs.
+//
+// Replaces CCS::solve_as_strict_lower / solve_as_strict_upper of the reference
+// (ds/CompressedStorage.hpp:2267-2279, 2356-2369) inside prec_solve_ldu
+// (alg/prec_solve.hpp:204-223).
+//
+// Design (DESIGN.md "triangular sweeps"):
+//  * The rows of a factor are cut, in sweep order (forward for L, backward for U), into
+//    blocks of <= kRowsMax consecutive rows whose packed "slab" fits the shared-memory
+//    budget.  The factors of the reference come out of AMD + Crout with strong index
+//    locality: with ~900-row blocks, ~60% of all dependencies and almost the whole
+//    critical path are block-local.
+//  * At attach time each block's data is packed into one contiguous, 16-byte aligned
+//    slab: row pointers, the list of EXTERNAL solution entries the block needs (its
+//    halo, global indices), 16-bit block-local column indices and the values.  10 bytes
+//    per nonzero instead of CSR's 12.
+//  * One CTA per block, block order taken from a ticket counter (everything a CTA can
+//    wait for is resident or finished -> no deadlock, no per-level-set launches).  One
+//    elected thread pulls the whole slab into shared memory with a single TMA bulk copy
+//    (cp.async.bulk + mbarrier); nothing in the dependent loop touches global memory.
+//  * Roles: thread t < rows solves row t; the last kPollWarps warps are pollers that
+//    fetch the halo entries from global memory (L2) into shared-memory slots as they
+//    become ready.  Row threads only ever poll shared memory (~30 cycles), so a chain of
+//    dependent rows inside a block advances at shared-memory latency, not L2 latency.
+//  * Values carry their own ready bit (common.cuh): one 8-byte load = data + readiness.
+//  * Per row the updates are applied in the reference's order (ascending column for L,
+//    descending for U); only FMA contraction differs from the CPU code.
+#include <algorithm>
+#include <cstring>
+
+#include "hifgpu.h"
+
+namespace hifgpu {
+
+constexpr unsigned kThreads   = 1024;
+constexpr unsigned kPollWarps = 4;
+constexpr unsigned kRowsMax   = kThreads - 32 * kPollWarps;  // 896 row threads
+constexpr unsigned kPollLanes = 32 * kPollWarps;
+constexpr unsigned kSmemBudget = 112 * 1024;  // per CTA -> two CTAs per SM (227 KB)
+constexpr unsigned kPollChunk  = 4;          // independent polling loads in flight per lane
+
+// block descriptor (32 bytes)
+struct alignas(16) SlabInfo {
+  unsigned long long off;   // byte offset of the slab in the packed buffer
+  unsigned           bytes; // slab bytes (multiple of 16)
+  unsigned           rows, nnz, nhalo, s0;
+  unsigned           pad;
+};
+
+__host__ __device__ inline unsigned pad16(unsigned x) { return (x + 15u) & ~15u; }
+// slab layout: [ptr u32[rows+1]] [halo u32[nhalo]] [idx u16[nnz]] [val f64[nnz]], 16B-aligned segments
+__host__ __device__ inline unsigned slab_off_halo(unsigned rows) { return pad16(4u * (rows + 1u)); }
+__host__ __device__ inline unsigned slab_off_idx(unsigned rows, unsigned nhalo) {
+  return slab_off_halo(rows) + pad16(4u * nhalo);
+}
+__host__ __device__ inline unsigned slab_off_val(unsigned rows, unsigned nhalo, unsigned nnz) {
+  return slab_off_idx(rows, nhalo) + pad16(2u * nnz);
+}
+__host__ __device__ inline unsigned slab_bytes(unsigned rows, unsigned nhalo, unsigned nnz) {
+  return slab_off_val(rows, nhalo, nnz) + pad16(8u * nnz);
+}
+
+// ---- PTX wrappers: mbarrier + TMA bulk copy (SASS: SYNCS.*, UBLKCP) ---------------
+__device__ __forceinline__ unsigned smem_addr(const void *p) {
+  return static_cast<unsigned>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_addr(dst)),
+               "l"(src), "r"(bytes), "r"(smem_addr(bar))
+               : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned long long *bar, unsigned phase) {
+  unsigned ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_addr(bar)), "r"(phase)
+      : "memory");
+  return ok != 0;
+}
+
+template <bool UPPER>
+__global__ void __launch_bounds__(kThreads, 2)
+    sptrsv_slab_kernel(const unsigned m, const unsigned char *__restrict__ slabs, const SlabInfo *__restrict__ info,
+                       const double *__restrict__ rhs_plain,
+                       const unsigned long long *rhs_tagged, const double *__restrict__ diag,
+                       unsigned long long *x, const unsigned parity, int *ticket, int *error_flag) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  __shared__ unsigned                        s_blk;
+  __shared__ __align__(8) unsigned long long s_bar;
+  const unsigned                             tid = threadIdx.x;
+  if (tid == 0) {
+    s_blk = static_cast<unsigned>(atomicAdd(ticket, 1));
+    mbar_init(&s_bar, 1);
+  }
+  __syncthreads();
+  const SlabInfo bi = info[s_blk];
+  if (tid == 0) {
+    mbar_expect_tx(&s_bar, bi.bytes);
+    tma_bulk_g2s(smem, slabs + bi.off, bi.bytes, &s_bar);
+  }
+  const unsigned rows = bi.rows, nhalo = bi.nhalo, nnz = bi.nnz;
+  volatile unsigned long long *xs = reinterpret_cast<volatile unsigned long long *>(smem + bi.bytes);
+  const unsigned long long     not_ready = parity ^ 1u;
+  for (unsigned i = tid; i < rows + nhalo; i += kThreads) xs[i] = not_ready;
+
+  // right-hand side of this thread's row, fetched while the slab is in flight
+  double   acc = 0.0;
+  unsigned gi  = 0;
+  if (tid < rows) {
+    const unsigned s = bi.s0 + tid;
+    gi               = UPPER ? m - 1u - s : s;
+    // U sweep: y = D^{-1} L^{-1} b formed on the fly with a true division (prec_solve.hpp:219)
+    acc = UPPER ? tag_value(rhs_tagged[gi]) / diag[gi] : rhs_plain[gi];
+  }
+  __syncthreads();  // xs initialised
+  while (!mbar_try_wait(&s_bar, 0)) {
+  }
+
+  const unsigned *      ptr  = reinterpret_cast<const unsigned *>(smem);
+  const unsigned *      halo = reinterpret_cast<const unsigned *>(smem + slab_off_halo(rows));
+  const unsigned short *idx  = reinterpret_cast<const unsigned short *>(smem + slab_off_idx(rows, nhalo));
+  const double *        val  = reinterpret_cast<const double *>(smem + slab_off_val(rows, nhalo, nnz));
+
+  if (tid < rows) {
+    // ---------------- row thread
+    unsigned       k = ptr[tid];
+    const unsigned e = ptr[tid + 1];
+    unsigned       c = 0, cn = 0;
+    double         a = 0.0, an = 0.0;
+    if (k < e) c = idx[k], a = val[k];
+    if (k + 1 < e) cn = idx[k + 1], an = val[k + 1];
+    unsigned spins = 0;
+    bool     done  = false;
+    // The publish step sits INSIDE the loop: a finished lane must store its value before
+    // the warp reconverges, because a sibling lane may be waiting for exactly that value.
+    while (!done) {
+      if (k < e) {
+        const unsigned long long bits = xs[c];
+        if (tag_ready(bits, parity)) {
+          acc = fma(-a, tag_value(bits), acc);
+          ++k;
+          c = cn, a = an;
+          if (k + 1 < e) cn = idx[k + 1], an = val[k + 1];
+          spins = 0;
+        } else if (++spins > kSpinLimit) {
+          *error_flag = 1;
+          k           = e;  // give up; publish so that dependants terminate too
+        }
+      }
+      if (k >= e) {
+        const unsigned long long bits = tag_set(acc, parity);
+        xs[tid]                       = bits;
+        st_publish(x + gi, bits);
+        done = true;
+      }
+    }
+  } else if (tid >= kRowsMax) {
+    // ---------------- poller: halo entries global (L2) -> shared slots
+    const unsigned lane = tid - kRowsMax;
+    const unsigned ne   = nhalo > lane ? (nhalo - lane + kPollLanes - 1) / kPollLanes : 0;  // my entries
+    unsigned       left = ne, passes = 0;
+    while (left) {
+      for (unsigned base = 0; base < ne; base += kPollChunk) {
+        unsigned long long v[kPollChunk];
+        bool               need[kPollChunk];
+#pragma unroll
+        for (unsigned u = 0; u < kPollChunk; ++u) {
+          const unsigned h = lane + kPollLanes * (base + u);
+          need[u]          = base + u < ne && !tag_ready(xs[rows + h], parity);
+          if (need[u]) v[u] = ld_poll(x + halo[h]);
+        }
+#pragma unroll
+        for (unsigned u = 0; u < kPollChunk; ++u) {
+          if (need[u] && tag_ready(v[u], parity)) {
+            xs[rows + lane + kPollLanes * (base + u)] = v[u];
+            --left;
+          }
+        }
+      }
+      if (left && ++passes > (kSpinLimit >> 6)) {
+        *error_flag = 1;
+        for (unsigned q = 0; q < ne; ++q) {  // release the row threads with garbage
+          const unsigned h = lane + kPollLanes * q;
+          if (!tag_ready(xs[rows + h], parity)) xs[rows + h] = parity;
+        }
+        left = 0;
+      }
+    }
+  }
+}
+
+// ============================================================================
+// host: pack a strictly triangular CSR factor into slabs
+// ============================================================================
+namespace {
+struct PackedSweep {
+  std::vector<SlabInfo>      infos;
+  std::vector<unsigned char> buf;
+  unsigned                   max_smem = 0;
+  std::size_t                halo_total = 0;
+};
+}  // namespace
+
+static void pack_sweep(const HostCsr &T, bool upper, PackedSweep &out) {
+  const unsigned m = static_cast<unsigned>(T.nrows);
+  if (!m) return;
+  std::vector<SlabInfo> &     infos = out.infos;
+  std::vector<unsigned char> &buf   = out.buf;
+  std::vector<unsigned>       stamp(m, 0u), slot(m, 0u);
+  std::vector<unsigned>      ptr, halo;
+  std::vector<unsigned short> idx;
+  std::vector<double>         val;
+  unsigned                    max_smem = 0;
+  auto nat = [&](unsigned s) { return upper ? m - 1u - s : s; };
+
+  unsigned s0 = 0, bid = 0;
+  while (s0 < m) {
+    ++bid;
+    // ---- choose the block's rows: as many as fit the thread and shared-memory budget
+    unsigned rows = 0, nnz = 0, nh = 0;
+    while (s0 + rows < m && rows < kRowsMax) {
+      const unsigned i = nat(s0 + rows);
+      unsigned       add_h = 0;
+      for (unsigned k = T.ptr[i]; k < T.ptr[i + 1]; ++k) {
+        const unsigned j  = static_cast<unsigned>(T.col[k]);
+        const unsigned sj = upper ? m - 1u - j : j;
+        if (sj < s0 && stamp[j] != bid) {
+          stamp[j] = bid;
+          slot[j]  = nh + add_h;
+          ++add_h;
+        }
+      }
+      const unsigned rn   = T.ptr[i + 1] - T.ptr[i];
+      const unsigned need = slab_bytes(rows + 1, nh + add_h, nnz + rn) + 8u * (rows + 1 + nh + add_h);
+      if (need > kSmemBudget) {
+        if (!rows)
+          throw std::invalid_argument("triangular factor has a row too long for one shared-memory slab (" +
+                                      std::to_string(rn) + " nonzeros)");
+        // undo the stamps of the rejected row
+        for (unsigned k = T.ptr[i]; k < T.ptr[i + 1]; ++k) {
+          const unsigned j = static_cast<unsigned>(T.col[k]);
+          if (stamp[j] == bid && slot[j] >= nh) stamp[j] = 0;
+        }
+        break;
+      }
+      ++rows;
+      nnz += rn;
+      nh += add_h;
+    }
+    if (rows + nh > 65536u) throw std::invalid_argument("block-local index space exceeds 16 bits");
+    // ---- pack
+    ptr.assign(rows + 1, 0u);
+    halo.assign(nh, 0u);
+    idx.clear();
+    val.clear();
+    for (unsigned r = 0; r < rows; ++r) {
+      const unsigned i = nat(s0 + r);
+      ptr[r]           = static_cast<unsigned>(idx.size());
+      const unsigned b = T.ptr[i], e = T.ptr[i + 1];
+      for (unsigned q = 0; q < e - b; ++q) {
+        const unsigned k  = upper ? e - 1u - q : b + q;  // U: descending column = sweep order
+        const unsigned j  = static_cast<unsigned>(T.col[k]);
+        const unsigned sj = upper ? m - 1u - j : j;
+        unsigned       loc;
+        if (sj >= s0) {
+          loc = sj - s0;  // a row of this block
+        } else {
+          loc            = rows + slot[j];
+          halo[slot[j]] = j;  // global (natural) index of the external entry
+        }
+        idx.push_back(static_cast<unsigned short>(loc));
+        val.push_back(T.val[k]);
+      }
+    }
+    ptr[rows] = static_cast<unsigned>(idx.size());
+    SlabInfo bi;
+    bi.off   = buf.size();
+    bi.bytes = slab_bytes(rows, nh, nnz);
+    bi.rows = rows, bi.nnz = nnz, bi.nhalo = nh, bi.s0 = s0, bi.pad = 0;
+    buf.resize(buf.size() + bi.bytes, 0);
+    unsigned char *base = buf.data() + bi.off;
+    std::memcpy(base, ptr.data(), 4u * (rows + 1));
+    if (nh) std::memcpy(base + slab_off_halo(rows), halo.data(), 4u * nh);
+    if (nnz) {
+      std::memcpy(base + slab_off_idx(rows, nh), idx.data(), 2u * nnz);
+      std::memcpy(base + slab_off_val(rows, nh, nnz), val.data(), 8u * nnz);
+    }
+    infos.push_back(bi);
+    max_smem = std::max(max_smem, bi.bytes + 8u * (rows + nh));
+    out.halo_total += nh;
+    s0 += rows;
+  }
+  out.max_smem = max_smem;
+}
+
+// CPU emulation of the slab sweep (same packed data, same per-row update order, blocks in
+// ticket order) -- lets the host-side packing be tested without a GPU (tests/test_abi.py).
+void sweep_host_emulate(const HostCsr &T, bool upper, const double *rhs, const double *diag, double *x,
+                        std::size_t stats[4]) {
+  PackedSweep P;
+  pack_sweep(T, upper, P);
+  const unsigned      m = static_cast<unsigned>(T.nrows);
+  std::vector<double> xs;
+  for (const SlabInfo &bi : P.infos) {
+    const unsigned char * base = P.buf.data() + bi.off;
+    const unsigned *      ptr  = reinterpret_cast<const unsigned *>(base);
+    const unsigned *      halo = reinterpret_cast<const unsigned *>(base + slab_off_halo(bi.rows));
+    const unsigned short *idx  = reinterpret_cast<const unsigned short *>(base + slab_off_idx(bi.rows, bi.nhalo));
+    const double *        val  = reinterpret_cast<const double *>(base + slab_off_val(bi.rows, bi.nhalo, bi.nnz));
+    xs.assign(bi.rows + bi.nhalo, 0.0);
+    for (unsigned h = 0; h < bi.nhalo; ++h) xs[bi.rows + h] = x[halo[h]];
+    for (unsigned r = 0; r < bi.rows; ++r) {
+      const unsigned s  = bi.s0 + r;
+      const unsigned gi = upper ? m - 1u - s : s;
+      double         acc = upper ? rhs[gi] / diag[gi] : rhs[gi];
+      for (unsigned k = ptr[r]; k < ptr[r + 1]; ++k) acc -= val[k] * xs[idx[k]];
+      xs[r] = acc;
+      x[gi] = acc;
+    }
+  }
+  stats[0] = P.infos.size();
+  stats[1] = P.halo_total;
+  stats[2] = P.buf.size();
+  stats[3] = P.max_smem;
+}
+
+void build_sweep_plan(const HostCsr &T, bool upper, SweepPlan &plan, std::size_t *tally) {
+  plan.m       = static_cast<unsigned>(T.nrows);
+  plan.upper   = upper;
+  plan.nblocks = 0;
+  if (!plan.m) return;
+  PackedSweep P;
+  pack_sweep(T, upper, P);
+  plan.nblocks    = static_cast<unsigned>(P.infos.size());
+  plan.smem_bytes = P.max_smem;
+  plan.slab_bytes = P.buf.size();
+  plan.halo_total = P.halo_total;
+  plan.slabs.upload(P.buf.data(), P.buf.size(), tally);
+  plan.info.upload(reinterpret_cast<const unsigned char *>(P.infos.data()), P.infos.size() * sizeof(SlabInfo), tally);
+  if (upper)
+    HIF_CUDA(cudaFuncSetAttribute(sptrsv_slab_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  static_cast<int>(kSmemBudget)));
+  else
+    HIF_CUDA(cudaFuncSetAttribute(sptrsv_slab_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  static_cast<int>(kSmemBudget)));
+}
+
+void launch_sweep(Handle *h, const SweepPlan &plan, const double *rhs_plain, const unsigned long long *rhs_tagged,
+                  const double *diag, unsigned long long *x, unsigned parity, int *ticket) {
+  if (!plan.nblocks) return;
+  const SlabInfo *info = reinterpret_cast<const SlabInfo *>(plan.info.p);
+  if (plan.upper)
+    sptrsv_slab_kernel<true><<<plan.nblocks, kThreads, plan.smem_bytes, h->stream>>>(
+        plan.m, plan.slabs.p, info, rhs_plain, rhs_tagged, diag, x, parity, ticket, h->error_flag.p);
+  else
+    sptrsv_slab_kernel<false><<<plan.nblocks, kThreads, plan.smem_bytes, h->stream>>>(
+        plan.m, plan.slabs.p, info, rhs_plain, rhs_tagged, diag, x, parity, ticket, h->error_flag.p);
+  HIF_KERNEL_CHECK();
+  ++h->launch_count;
+}
+
+}  // namespace hifgpu

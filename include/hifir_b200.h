@@ -195,6 +195,14 @@ LhfStatus lhfdGpuProfileSolveDev(LhfdGpuHdl hdl, const double *d_b, double *d_x,
                                  size_t max_entries, float *ms, size_t *count, char *names,
                                  size_t names_len);
 
+/* Host-only test hook (no GPU needed): packs the strictly triangular CCS block T into the
+ * shared-memory slabs the device sweeps consume and solves with them on the CPU, block by
+ * block in the device's order: x = T^{-1} rhs (lower, diag ignored) or x = T^{-1}(rhs./diag)
+ * (upper).  stats = {blocks, halo entries, packed bytes, max shared bytes per block}.
+ * Lets the host-side packing logic be checked bit-for-bit in the CPU test suite. */
+LhfStatus lhfdGpuDebugSweepHost(const LhfdGpuCcs *T, int upper, const double *rhs, const double *diag,
+                                double *x, size_t stats[4]);
+
 /* per-level dependency depth of the L and U sweeps: depth[2*l], depth[2*l+1] */
 LhfStatus lhfdGpuGetDepths(LhfdGpuHdl hdl, size_t nlevels, size_t *depth);
 

@@ -71,6 +71,39 @@ def test_attach_without_gpu_fails_loudly(lib):
     assert "cuda" in str(e.value).lower()
 
 
+@pytest.mark.parametrize("case", ["demo_A", "poisson14_ml", "stokes28_ml"])
+def test_slab_packing_host_emulation(lib, case):
+    """Host logic of the triangular sweeps: pack each L_B / U_B of the fixtures into device
+    slabs and solve with them on the CPU -- must equal plain substitution bit for bit up to
+    reassociation-free arithmetic (same update order => identical without FMA)."""
+    import scipy.sparse as sp
+    g = load_golden(case)
+    rng = np.random.default_rng(1)
+    for L in g.levels:
+        m = L["m"]
+        if not m:
+            continue
+        rhs = rng.uniform(-1, 1, m)
+        for name, upper in (("L", False), ("U", True)):
+            nr, nc, cs, ri, va = L[name]
+            x, st = hb.debug_sweep_host(L[name], upper, rhs, L["d"] if upper else None)
+            T = sp.csc_matrix((va, ri, cs), shape=(m, m)).tocsr()
+            T.sort_indices()
+            ref = np.array(rhs / L["d"] if upper else rhs)
+            order = range(m - 1, -1, -1) if upper else range(m)
+            for i in order:  # same per-row update order as the reference's column sweeps
+                cols = T.indices[T.indptr[i]:T.indptr[i + 1]]
+                vals = T.data[T.indptr[i]:T.indptr[i + 1]]
+                seq = zip(cols[::-1], vals[::-1]) if upper else zip(cols, vals)
+                acc = ref[i]
+                for j, v in seq:
+                    acc -= v * ref[j]
+                ref[i] = acc
+            assert np.array_equal(x, ref), (case, name)
+            assert st["blocks"] >= 1 and st["max_smem"] <= 112 * 1024
+            assert st["bytes"] >= 10 * len(va)
+
+
 def test_product_never_imports_oracle():
     """The package must not reach into oracle/ (only tests, bench cpu legs and smoke may)."""
     pkg = os.path.join(ROOT, "hifir_b200")
