@@ -66,6 +66,22 @@ def factorize(A, threads, nsp=False):
     return M
 
 
+def cached_levels(workload, size, threads=None):
+    """Per-level factors for developer tools: reference factorization, cached on local disk
+    (uncompressed npz) so that several processes on one box factorize once."""
+    from hifir_b200.levels_io import arrays_to_levels, levels_to_arrays
+    path = os.path.join(CACHE_DIR, f"{workload}{size}.npz")
+    A = make_problem(workload, size)
+    if os.path.exists(path):
+        with np.load(path) as z:
+            return A, arrays_to_levels({k: z[k] for k in z.files})
+    M = factorize(A, threads=threads or os.cpu_count() or 1)
+    levels = M.levels()
+    os.makedirs(CACHE_DIR, exist_ok=True)
+    np.savez(path, **levels_to_arrays(levels))
+    return A, levels
+
+
 # ----------------------------------------------------------------------------- clocks
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""

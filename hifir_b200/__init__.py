@@ -115,6 +115,7 @@ def lib():
             "lhfdGpuSpmvDev": [vp, vp, vp],
             "lhfdGpuProfileSolveDev": [vp, vp, vp, sz, sz, vp, vp, vp, sz],
             "lhfdGpuDebugSweepHost": [vp, i, vp, vp, vp, vp],
+            "lhfdGpuDebugTraceSweep": [vp, vp, vp, i, i, vp, sz, vp],
             "lhfdGpuGetStats": [vp, vp],
             "lhfdGpuGetDepths": [vp, sz, vp],
         }
@@ -132,7 +133,7 @@ EXPORTED_SYMBOLS = (
     "lhfdGpuAttachLevels", "lhfdGpuDestroy", "lhfdGpuSetMatrix", "lhfdGpuSetNspConst", "lhfdGpuClearNsp",
     "lhfdGpuSetStream", "lhfdGpuSynchronize", "lhfdGpuSolve", "lhfdGpuApply", "lhfdGpuSolveMrhs",
     "lhfdGpuFgmres", "lhfdGpuGmres", "lhfdGpuSolveDev", "lhfdGpuSolveMrhsDev", "lhfdGpuHifirDev",
-    "lhfdGpuSpmvDev", "lhfdGpuProfileSolveDev", "lhfdGpuDebugSweepHost", "lhfdGpuGetStats", "lhfdGpuGetDepths", "lhfGpuGetErrorMsg", "lhfGpuVersion")
+    "lhfdGpuSpmvDev", "lhfdGpuProfileSolveDev", "lhfdGpuDebugSweepHost", "lhfdGpuDebugTraceSweep", "lhfdGpuGetStats", "lhfdGpuGetDepths", "lhfGpuGetErrorMsg", "lhfGpuVersion")
 
 
 class LhfError(RuntimeError):
@@ -285,6 +286,14 @@ class GpuHif:
                                           C.byref(cnt), names, 8192))
         labels = names.value.decode().split("\n")
         return [(labels[k], float(ms[k])) for k in range(cnt.value)]
+
+    def trace_sweep(self, d_b, d_x, level, which, max_blocks=1 << 16):
+        """per-block trace of one sweep: array [nblocks, 8] (see lhfdGpuDebugTraceSweep)"""
+        out = np.zeros(max_blocks * 8, dtype=np.uint64)
+        nb = C.c_size_t()
+        _chk(lib().lhfdGpuDebugTraceSweep(self._h, C.c_void_p(d_b), C.c_void_p(d_x), level, which, _ptr(out),
+                                          max_blocks, C.byref(nb)))
+        return out[: nb.value * 8].reshape(-1, 8)
 
     def spmv_dev(self, d_x, d_y):
         _chk(lib().lhfdGpuSpmvDev(self._h, C.c_void_p(d_x), C.c_void_p(d_y)))

@@ -191,11 +191,14 @@ void mark(Handle *h, const std::string &name) {
 }
 
 void launch_sweeps(Handle *h, DevLevel &D, const double *rhs, unsigned long long *xL, unsigned long long *xU,
-                   unsigned parity, int *tickets, const std::string &tag) {
+                   unsigned parity, int *tickets, const std::string &tag, int trace_base) {
   if (!D.m) return;
-  launch_sweep(h, D.L, rhs, nullptr, nullptr, xL, parity, tickets);
+  const bool tl = h->trace_level >= 0 && &h->levels[h->trace_level] == &D;
+  launch_sweep(h, D.L, rhs, nullptr, nullptr, xL, parity, tickets,
+               tl && h->trace_which == trace_base ? h->trace_buf.p : nullptr);
   mark(h, tag + "L");
-  launch_sweep(h, D.U, nullptr, xL, D.d.p, xU, parity, tickets + 1);
+  launch_sweep(h, D.U, nullptr, xL, D.d.p, xU, parity, tickets + 1,
+               tl && h->trace_which == trace_base + 1 ? h->trace_buf.p : nullptr);
   mark(h, tag + "U");
 }
 
@@ -244,7 +247,7 @@ void apply_dev(Handle *h, const double *d_b, double *d_x, std::size_t rank) {
     }
     if (D.nm) {
       launch_sweeps(h, D, D.bhat.p, D.xL_dn.p, D.xU_dn.p, parity, h->tickets.p + 4 * l,
-                    "lv" + std::to_string(l) + ".down.");
+                    "lv" + std::to_string(l) + ".down.", 0);
       launch_spmv_resid<true>(h, D.E, D.xU_dn.p, D.bhat.p + D.m, D.r.p, "lv" + std::to_string(l) + ".E");
       b = D.r.p;
     }
@@ -276,7 +279,7 @@ void apply_dev(Handle *h, const double *d_b, double *d_x, std::size_t rank) {
       rhs = D.g.p;
     }
     launch_sweeps(h, D, rhs, D.xL_up.p, D.xU_up.p, parity, h->tickets.p + 4 * l + 2,
-                  "lv" + std::to_string(l) + ".up.");
+                  "lv" + std::to_string(l) + ".up.", 2);
     if (D.n) {
       scatter_scale_kernel<<<cdiv(D.n, T), T, 0, h->stream>>>(static_cast<unsigned>(D.n), static_cast<unsigned>(D.m),
                                                              D.q_inv.p, D.t.p, D.xU_up.p, D.ychild.p, y);

@@ -360,6 +360,34 @@ LhfStatus lhfdGpuDebugSweepHost(const LhfdGpuCcs *T, int upper, const double *rh
   });
 }
 
+LhfStatus lhfdGpuDebugTraceSweep(LhfdGpuHdl hdl, const double *d_b, double *d_x, int level, int which,
+                                 unsigned long long *out, size_t max_blocks, size_t *nblocks) {
+  REQUIRE_HANDLE(hdl);
+  REQUIRE_PTR(out, "out");
+  REQUIRE_PTR(nblocks, "nblocks");
+  return guarded([&] {
+    Handle *h = H(hdl);
+    if (level < 0 || static_cast<size_t>(level) >= h->levels.size() || which < 0 || which > 3)
+      throw std::invalid_argument("bad level / sweep selector");
+    const SweepPlan &plan = (which & 1) ? h->levels[level].U : h->levels[level].L;
+    if (h->trace_buf.n < 8ull * plan.nblocks) h->trace_buf.alloc(8ull * plan.nblocks);
+    HIF_CUDA(cudaMemsetAsync(h->trace_buf.p, 0, h->trace_buf.n * 8, h->stream));
+    h->trace_level = level;
+    h->trace_which = which;
+    try {
+      apply_dev(h, d_b, d_x, 0);
+      check_sweep_error(h);
+    } catch (...) {
+      h->trace_level = h->trace_which = -1;
+      throw;
+    }
+    h->trace_level = h->trace_which = -1;
+    const size_t nb = std::min<size_t>(plan.nblocks, max_blocks);
+    HIF_CUDA(cudaMemcpy(out, h->trace_buf.p, nb * 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    *nblocks = nb;
+  });
+}
+
 LhfStatus lhfdGpuGetStats(LhfdGpuHdl hdl, size_t stats[]) {
   REQUIRE_HANDLE(hdl);
   REQUIRE_PTR(stats, "stats");

@@ -133,6 +133,8 @@ struct Handle {
   std::size_t bytes_factors = 0, bytes_vec = 0, bytes_dense = 0, device_bytes = 0, nnz_total = 0;
   std::size_t kernels_per_apply = 0, launch_count = 0;
   // optional per-kernel timing of one apply (lhfdGpuProfileSolveDev)
+  int                                   trace_level = -1, trace_which = -1;  // debug: which sweep to trace
+  DevBuf<unsigned long long>            trace_buf;
   bool                                  profiling = false;
   std::vector<std::pair<std::string, cudaEvent_t>> prof_marks;
   std::size_t n0() const { return levels.empty() ? 0 : levels[0].n; }
@@ -149,7 +151,8 @@ void build_sweep_plan(const HostCsr &T, bool upper, SweepPlan &plan, std::size_t
 void sweep_host_emulate(const HostCsr &T, bool upper, const double *rhs, const double *diag, double *x,
                         std::size_t stats[4]);
 void launch_sweep(Handle *h, const SweepPlan &plan, const double *rhs_plain, const unsigned long long *rhs_tagged,
-                  const double *diag, unsigned long long *x, unsigned parity, int *ticket);
+                  const double *diag, unsigned long long *x, unsigned parity, int *ticket,
+                  unsigned long long *trace = nullptr);
 
 // ---- apply.cu : the multilevel M^{-1} apply on device vectors
 void apply_dev(Handle *h, const double *d_b, double *d_x, std::size_t rank);

@@ -26,18 +26,18 @@
 //  * Per row the updates are applied in the reference's order (ascending column for L,
 //    descending for U); only FMA contraction differs from the CPU code.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 #include "hifgpu.h"
 
 namespace hifgpu {
 
-constexpr unsigned kThreads   = 1024;
-constexpr unsigned kPollWarps = 4;
-constexpr unsigned kRowsMax   = kThreads - 32 * kPollWarps;  // 896 row threads
+constexpr unsigned kPollWarps = 2;
 constexpr unsigned kPollLanes = 32 * kPollWarps;
+constexpr unsigned kRowsMax   = 1024;  // rows per block (the shared-memory budget usually binds first)
 constexpr unsigned kSmemBudget = 112 * 1024;  // per CTA -> two CTAs per SM (227 KB)
-constexpr unsigned kPollChunk  = 4;          // independent polling loads in flight per lane
+constexpr unsigned kPollChunk  = 8;          // independent polling loads in flight per lane
 
 // block descriptor (32 bytes)
 struct alignas(16) SlabInfo {
@@ -77,6 +77,11 @@ __device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, unsigne
                "l"(src), "r"(bytes), "r"(smem_addr(bar))
                : "memory");
 }
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 __device__ __forceinline__ bool mbar_try_wait(unsigned long long *bar, unsigned phase) {
   unsigned ok;
   asm volatile(
@@ -87,22 +92,30 @@ __device__ __forceinline__ bool mbar_try_wait(unsigned long long *bar, unsigned 
   return ok != 0;
 }
 
-template <bool UPPER>
-__global__ void __launch_bounds__(kThreads, 2)
+template <bool UPPER, unsigned T>
+__global__ void __launch_bounds__(T + kPollLanes, 2)
     sptrsv_slab_kernel(const unsigned m, const unsigned char *__restrict__ slabs, const SlabInfo *__restrict__ info,
-                       const double *__restrict__ rhs_plain,
-                       const unsigned long long *rhs_tagged, const double *__restrict__ diag,
-                       unsigned long long *x, const unsigned parity, int *ticket, int *error_flag) {
+                       const double *__restrict__ rhs_plain, const unsigned long long *rhs_tagged,
+                       const double *__restrict__ diag, unsigned long long *x, const unsigned parity, int *ticket,
+                       int *error_flag, unsigned long long *trace) {
+  constexpr unsigned kThreads = T + kPollLanes;
   extern __shared__ __align__(16) unsigned char smem[];
-  __shared__ unsigned                        s_blk;
+  __shared__ unsigned                        s_blk, s_done;
   __shared__ __align__(8) unsigned long long s_bar;
   const unsigned                             tid = threadIdx.x;
   if (tid == 0) {
-    s_blk = static_cast<unsigned>(atomicAdd(ticket, 1));
+    s_blk  = static_cast<unsigned>(atomicAdd(ticket, 1));
+    s_done = 0;
     mbar_init(&s_bar, 1);
   }
   __syncthreads();
   const SlabInfo bi = info[s_blk];
+  if (trace && tid == 0) {
+    unsigned smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    trace[8 * s_blk + 0] = globaltimer_ns();
+    trace[8 * s_blk + 3] = smid;
+  }
   if (tid == 0) {
     mbar_expect_tx(&s_bar, bi.bytes);
     tma_bulk_g2s(smem, slabs + bi.off, bi.bytes, &s_bar);
@@ -112,39 +125,43 @@ __global__ void __launch_bounds__(kThreads, 2)
   const unsigned long long     not_ready = parity ^ 1u;
   for (unsigned i = tid; i < rows + nhalo; i += kThreads) xs[i] = not_ready;
 
-  // right-hand side of this thread's row, fetched while the slab is in flight
-  double   acc = 0.0;
-  unsigned gi  = 0;
-  if (tid < rows) {
-    const unsigned s = bi.s0 + tid;
+  // right-hand side of a row: b_i (L sweep) or (L^{-1}b)_i / d_i with a true division
+  // (prec_solve.hpp:219) for the U sweep; fetched one row ahead of its use
+  auto load_rhs = [&](unsigned r, unsigned &gi) -> double {
+    const unsigned s = bi.s0 + r;
     gi               = UPPER ? m - 1u - s : s;
-    // U sweep: y = D^{-1} L^{-1} b formed on the fly with a true division (prec_solve.hpp:219)
-    acc = UPPER ? tag_value(rhs_tagged[gi]) / diag[gi] : rhs_plain[gi];
-  }
+    return UPPER ? tag_value(rhs_tagged[gi]) / diag[gi] : rhs_plain[gi];
+  };
+  unsigned r = tid, gi = 0, gi_next = 0;
+  double   acc = 0.0, acc_next = 0.0;
+  if (tid < T && r < rows) acc = load_rhs(r, gi);
+  if (tid < T && r + T < rows) acc_next = load_rhs(r + T, gi_next);
   __syncthreads();  // xs initialised
   while (!mbar_try_wait(&s_bar, 0)) {
   }
+  if (trace && tid == 0) trace[8 * s_blk + 1] = globaltimer_ns();
 
   const unsigned *      ptr  = reinterpret_cast<const unsigned *>(smem);
   const unsigned *      halo = reinterpret_cast<const unsigned *>(smem + slab_off_halo(rows));
   const unsigned short *idx  = reinterpret_cast<const unsigned short *>(smem + slab_off_idx(rows, nhalo));
   const double *        val  = reinterpret_cast<const double *>(smem + slab_off_val(rows, nhalo, nnz));
 
-  if (tid < rows) {
-    // ---------------- row thread
-    unsigned       k = ptr[tid];
-    const unsigned e = ptr[tid + 1];
-    unsigned       c = 0, cn = 0;
-    double         a = 0.0, an = 0.0;
-    if (k < e) c = idx[k], a = val[k];
-    if (k + 1 < e) cn = idx[k + 1], an = val[k + 1];
-    unsigned spins = 0;
-    bool     done  = false;
-    // The publish step sits INSIDE the loop: a finished lane must store its value before
-    // the warp reconverges, because a sibling lane may be waiting for exactly that value.
-    while (!done) {
+  if (tid < T) {
+    // ---------------- row thread: rows tid, tid+T, tid+2T, ... one after the other
+    unsigned k = 0, e = 0, c = 0, cn = 0, spins = 0, polls = 0;
+    double   a = 0.0, an = 0.0;
+    if (r < rows) {
+      k = ptr[r], e = ptr[r + 1];
+      if (k < e) c = idx[k], a = val[k];
+      if (k + 1 < e) cn = idx[k + 1], an = val[k + 1];
+    }
+    // One non-blocking state machine per lane.  The publish step sits INSIDE the loop: a
+    // finished lane must store its value before the warp reconverges, because a sibling
+    // lane may be waiting for exactly that value.
+    while (r < rows) {
       if (k < e) {
         const unsigned long long bits = xs[c];
+        ++polls;
         if (tag_ready(bits, parity)) {
           acc = fma(-a, tag_value(bits), acc);
           ++k;
@@ -158,14 +175,28 @@ __global__ void __launch_bounds__(kThreads, 2)
       }
       if (k >= e) {
         const unsigned long long bits = tag_set(acc, parity);
-        xs[tid]                       = bits;
+        xs[r]                         = bits;
         st_publish(x + gi, bits);
-        done = true;
+        if (trace) {
+          if (atomicAdd(&s_done, 1u) + 1u == rows) {  // the row that finishes last
+            trace[8 * s_blk + 2] = globaltimer_ns();
+            trace[8 * s_blk + 4] = polls;
+            trace[8 * s_blk + 5] = r;
+          }
+        }
+        r += T;
+        if (r < rows) {
+          acc = acc_next, gi = gi_next;
+          if (r + T < rows) acc_next = load_rhs(r + T, gi_next);
+          k = ptr[r], e = ptr[r + 1];
+          if (k < e) c = idx[k], a = val[k];
+          if (k + 1 < e) cn = idx[k + 1], an = val[k + 1];
+        }
       }
     }
-  } else if (tid >= kRowsMax) {
+  } else {
     // ---------------- poller: halo entries global (L2) -> shared slots
-    const unsigned lane = tid - kRowsMax;
+    const unsigned lane = tid - T;
     const unsigned ne   = nhalo > lane ? (nhalo - lane + kPollLanes - 1) / kPollLanes : 0;  // my entries
     unsigned       left = ne, passes = 0;
     while (left) {
@@ -186,7 +217,7 @@ __global__ void __launch_bounds__(kThreads, 2)
           }
         }
       }
-      if (left && ++passes > (kSpinLimit >> 6)) {
+      if (left && passes > (kSpinLimit >> 6)) {
         *error_flag = 1;
         for (unsigned q = 0; q < ne; ++q) {  // release the row threads with garbage
           const unsigned h = lane + kPollLanes * q;
@@ -194,7 +225,9 @@ __global__ void __launch_bounds__(kThreads, 2)
         }
         left = 0;
       }
+      ++passes;
     }
+    if (trace && lane == 0) trace[8 * s_blk + 6] = passes;
   }
 }
 
@@ -346,24 +379,46 @@ void build_sweep_plan(const HostCsr &T, bool upper, SweepPlan &plan, std::size_t
   plan.halo_total = P.halo_total;
   plan.slabs.upload(P.buf.data(), P.buf.size(), tally);
   plan.info.upload(reinterpret_cast<const unsigned char *>(P.infos.data()), P.infos.size() * sizeof(SlabInfo), tally);
-  if (upper)
-    HIF_CUDA(cudaFuncSetAttribute(sptrsv_slab_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  static_cast<int>(kSmemBudget)));
-  else
-    HIF_CUDA(cudaFuncSetAttribute(sptrsv_slab_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  static_cast<int>(kSmemBudget)));
 }
 
+namespace {
+template <bool UPPER, unsigned T>
+void launch_T(Handle *h, const SweepPlan &plan, const double *rhs_plain, const unsigned long long *rhs_tagged,
+              const double *diag, unsigned long long *x, unsigned parity, int *ticket, unsigned long long *trace) {
+  static bool configured = false;
+  if (!configured) {
+    HIF_CUDA(cudaFuncSetAttribute(sptrsv_slab_kernel<UPPER, T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  static_cast<int>(kSmemBudget)));
+    configured = true;
+  }
+  sptrsv_slab_kernel<UPPER, T><<<plan.nblocks, T + kPollLanes, plan.smem_bytes, h->stream>>>(
+      plan.m, plan.slabs.p, reinterpret_cast<const SlabInfo *>(plan.info.p), rhs_plain, rhs_tagged, diag, x, parity,
+      ticket, h->error_flag.p, trace);
+}
+template <bool UPPER>
+void launch_U(Handle *h, const SweepPlan &plan, const double *rhs_plain, const unsigned long long *rhs_tagged,
+              const double *diag, unsigned long long *x, unsigned parity, int *ticket, unsigned long long *trace) {
+  static int T = 0;
+  if (!T) {
+    const char *e = std::getenv("HIFIR_B200_ROW_THREADS");
+    T             = e ? std::atoi(e) : 192;
+  }
+  switch (T) {
+    case 96: launch_T<UPPER, 96>(h, plan, rhs_plain, rhs_tagged, diag, x, parity, ticket, trace); break;
+    case 448: launch_T<UPPER, 448>(h, plan, rhs_plain, rhs_tagged, diag, x, parity, ticket, trace); break;
+    case 960: launch_T<UPPER, 960>(h, plan, rhs_plain, rhs_tagged, diag, x, parity, ticket, trace); break;
+    default: launch_T<UPPER, 192>(h, plan, rhs_plain, rhs_tagged, diag, x, parity, ticket, trace); break;
+  }
+}
+}  // namespace
+
 void launch_sweep(Handle *h, const SweepPlan &plan, const double *rhs_plain, const unsigned long long *rhs_tagged,
-                  const double *diag, unsigned long long *x, unsigned parity, int *ticket) {
+                  const double *diag, unsigned long long *x, unsigned parity, int *ticket, unsigned long long *trace) {
   if (!plan.nblocks) return;
-  const SlabInfo *info = reinterpret_cast<const SlabInfo *>(plan.info.p);
   if (plan.upper)
-    sptrsv_slab_kernel<true><<<plan.nblocks, kThreads, plan.smem_bytes, h->stream>>>(
-        plan.m, plan.slabs.p, info, rhs_plain, rhs_tagged, diag, x, parity, ticket, h->error_flag.p);
+    launch_U<true>(h, plan, rhs_plain, rhs_tagged, diag, x, parity, ticket, trace);
   else
-    sptrsv_slab_kernel<false><<<plan.nblocks, kThreads, plan.smem_bytes, h->stream>>>(
-        plan.m, plan.slabs.p, info, rhs_plain, rhs_tagged, diag, x, parity, ticket, h->error_flag.p);
+    launch_U<false>(h, plan, rhs_plain, rhs_tagged, diag, x, parity, ticket, trace);
   HIF_KERNEL_CHECK();
   ++h->launch_count;
 }

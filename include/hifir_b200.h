@@ -203,6 +203,13 @@ LhfStatus lhfdGpuProfileSolveDev(LhfdGpuHdl hdl, const double *d_b, double *d_x,
 LhfStatus lhfdGpuDebugSweepHost(const LhfdGpuCcs *T, int upper, const double *rhs, const double *diag,
                                 double *x, size_t stats[4]);
 
+/* Debug: run one apply with per-block tracing of one triangular sweep switched on
+ * (level, which: 0 = down L, 1 = down U, 2 = up L, 3 = up U).  out[8*b + ...] for ticket b:
+ * 0 start ns, 1 slab-in-shared ns, 2 last-row-done ns (globaltimer), 3 SM id, 4 polls of the
+ * last row, 5 its thread, 6 poller passes, 7 unused. */
+LhfStatus lhfdGpuDebugTraceSweep(LhfdGpuHdl hdl, const double *d_b, double *d_x, int level, int which,
+                                 unsigned long long *out, size_t max_blocks, size_t *nblocks);
+
 /* per-level dependency depth of the L and U sweeps: depth[2*l], depth[2*l+1] */
 LhfStatus lhfdGpuGetDepths(LhfdGpuHdl hdl, size_t nlevels, size_t *depth);
 
