@@ -48,10 +48,14 @@ struct alignas(16) SlabInfo {
 };
 
 __host__ __device__ inline unsigned pad16(unsigned x) { return (x + 15u) & ~15u; }
-// slab layout: [ptr u32[rows+1]] [halo u32[nhalo]] [idx u16[nnz]] [val f64[nnz]], 16B-aligned segments
+// slab layout: [ptr u32[rows+1]] [halo u32[nhalo]] [order u16[rows]] [idx u16[nnz]] [val f64[nnz]],
+// 16B-aligned segments.  order = the block's rows sorted by dependency depth (see kernel).
 __host__ __device__ inline unsigned slab_off_halo(unsigned rows) { return pad16(4u * (rows + 1u)); }
-__host__ __device__ inline unsigned slab_off_idx(unsigned rows, unsigned nhalo) {
+__host__ __device__ inline unsigned slab_off_order(unsigned rows, unsigned nhalo) {
   return slab_off_halo(rows) + pad16(4u * nhalo);
+}
+__host__ __device__ inline unsigned slab_off_idx(unsigned rows, unsigned nhalo) {
+  return slab_off_order(rows, nhalo) + pad16(2u * rows);
 }
 __host__ __device__ inline unsigned slab_off_val(unsigned rows, unsigned nhalo, unsigned nnz) {
   return slab_off_idx(rows, nhalo) + pad16(2u * nnz);
@@ -132,25 +136,31 @@ __global__ void __launch_bounds__(T + kPollLanes, 2)
     gi               = UPPER ? m - 1u - s : s;
     return UPPER ? tag_value(rhs_tagged[gi]) / diag[gi] : rhs_plain[gi];
   };
-  unsigned r = tid, gi = 0, gi_next = 0;
-  double   acc = 0.0, acc_next = 0.0;
-  if (tid < T && r < rows) acc = load_rhs(r, gi);
-  if (tid < T && r + T < rows) acc_next = load_rhs(r + T, gi_next);
   __syncthreads();  // xs initialised
   while (!mbar_try_wait(&s_bar, 0)) {
   }
   if (trace && tid == 0) trace[8 * s_blk + 1] = globaltimer_ns();
 
-  const unsigned *      ptr  = reinterpret_cast<const unsigned *>(smem);
-  const unsigned *      halo = reinterpret_cast<const unsigned *>(smem + slab_off_halo(rows));
+  const unsigned *      ptr   = reinterpret_cast<const unsigned *>(smem);
+  const unsigned *      halo  = reinterpret_cast<const unsigned *>(smem + slab_off_halo(rows));
+  const unsigned short *order = reinterpret_cast<const unsigned short *>(smem + slab_off_order(rows, nhalo));
   const unsigned short *idx  = reinterpret_cast<const unsigned short *>(smem + slab_off_idx(rows, nhalo));
   const double *        val  = reinterpret_cast<const double *>(smem + slab_off_val(rows, nhalo, nnz));
 
   if (tid < T) {
-    // ---------------- row thread: rows tid, tid+T, tid+2T, ... one after the other
+    // ---------------- row thread.  The block's rows are sorted by dependency depth
+    // (order[]); thread t solves order[t], order[t+T], ... one after the other, so a
+    // thread's next row is never expected to be ready before its current one and only
+    // T threads (not one per row) spin on the shared-memory pipe at any time.
+    unsigned q = tid;  // position in order[]
+    unsigned r = 0, gi = 0, gi_next = 0;
+    double   acc = 0.0, acc_next = 0.0;
     unsigned k = 0, e = 0, c = 0, cn = 0, spins = 0, polls = 0;
     double   a = 0.0, an = 0.0;
-    if (r < rows) {
+    if (q < rows) {
+      r   = order[q];
+      acc = load_rhs(r, gi);
+      if (q + T < rows) acc_next = load_rhs(order[q + T], gi_next);
       k = ptr[r], e = ptr[r + 1];
       if (k < e) c = idx[k], a = val[k];
       if (k + 1 < e) cn = idx[k + 1], an = val[k + 1];
@@ -158,7 +168,7 @@ __global__ void __launch_bounds__(T + kPollLanes, 2)
     // One non-blocking state machine per lane.  The publish step sits INSIDE the loop: a
     // finished lane must store its value before the warp reconverges, because a sibling
     // lane may be waiting for exactly that value.
-    while (r < rows) {
+    while (q < rows) {
       if (k < e) {
         const unsigned long long bits = xs[c];
         ++polls;
@@ -184,10 +194,11 @@ __global__ void __launch_bounds__(T + kPollLanes, 2)
             trace[8 * s_blk + 5] = r;
           }
         }
-        r += T;
-        if (r < rows) {
+        q += T;
+        if (q < rows) {
+          r   = order[q];
           acc = acc_next, gi = gi_next;
-          if (r + T < rows) acc_next = load_rhs(r + T, gi_next);
+          if (q + T < rows) acc_next = load_rhs(order[q + T], gi_next);
           k = ptr[r], e = ptr[r + 1];
           if (k < e) c = idx[k], a = val[k];
           if (k + 1 < e) cn = idx[k + 1], an = val[k + 1];
@@ -249,6 +260,15 @@ static void pack_sweep(const HostCsr &T, bool upper, PackedSweep &out) {
   std::vector<SlabInfo> &     infos = out.infos;
   std::vector<unsigned char> &buf   = out.buf;
   std::vector<unsigned>       stamp(m, 0u), slot(m, 0u);
+  // dependency depth of every row (level set index), in sweep order
+  std::vector<unsigned> lev(m, 0u);
+  for (unsigned s = 0; s < m; ++s) {
+    const unsigned i = upper ? m - 1u - s : s;
+    unsigned       l = 0;
+    for (unsigned k = T.ptr[i]; k < T.ptr[i + 1]; ++k) l = std::max(l, lev[T.col[k]] + 1u);
+    lev[i] = l;
+  }
+  std::vector<unsigned short> order;
   std::vector<unsigned>      ptr, halo;
   std::vector<unsigned short> idx;
   std::vector<double>         val;
@@ -315,6 +335,10 @@ static void pack_sweep(const HostCsr &T, bool upper, PackedSweep &out) {
       }
     }
     ptr[rows] = static_cast<unsigned>(idx.size());
+    order.resize(rows);
+    for (unsigned r = 0; r < rows; ++r) order[r] = static_cast<unsigned short>(r);
+    std::stable_sort(order.begin(), order.end(),
+                     [&](unsigned short x, unsigned short y) { return lev[nat(s0 + x)] < lev[nat(s0 + y)]; });
     SlabInfo bi;
     bi.off   = buf.size();
     bi.bytes = slab_bytes(rows, nh, nnz);
@@ -323,6 +347,7 @@ static void pack_sweep(const HostCsr &T, bool upper, PackedSweep &out) {
     unsigned char *base = buf.data() + bi.off;
     std::memcpy(base, ptr.data(), 4u * (rows + 1));
     if (nh) std::memcpy(base + slab_off_halo(rows), halo.data(), 4u * nh);
+    std::memcpy(base + slab_off_order(rows, nh), order.data(), 2u * rows);
     if (nnz) {
       std::memcpy(base + slab_off_idx(rows, nh), idx.data(), 2u * nnz);
       std::memcpy(base + slab_off_val(rows, nh, nnz), val.data(), 8u * nnz);
