@@ -155,35 +155,22 @@ __global__ void __launch_bounds__(T + kPollLanes, 2)
     unsigned q = tid;  // position in order[]
     unsigned r = 0, gi = 0, gi_next = 0;
     double   acc = 0.0, acc_next = 0.0;
-    unsigned k = 0, e = 0, c = 0, cn = 0, spins = 0, polls = 0;
-    double   a = 0.0, an = 0.0;
-    if (q < rows) {
+    unsigned k = 0, e = 0, polls = 0;
+    double   a = 0.0;
+    const volatile unsigned long long *pa = xs;  // slot of the dependency this lane waits for
+    bool active = q < rows;
+    if (active) {
       r   = order[q];
       acc = load_rhs(r, gi);
       if (q + T < rows) acc_next = load_rhs(order[q + T], gi_next);
       k = ptr[r], e = ptr[r + 1];
-      if (k < e) c = idx[k], a = val[k];
-      if (k + 1 < e) cn = idx[k + 1], an = val[k + 1];
+      if (k < e) pa = xs + idx[k], a = val[k];
     }
-    // One non-blocking state machine per lane.  The publish step sits INSIDE the loop: a
-    // finished lane must store its value before the warp reconverges, because a sibling
-    // lane may be waiting for exactly that value.
-    while (q < rows) {
-      if (k < e) {
-        const unsigned long long bits = xs[c];
-        ++polls;
-        if (tag_ready(bits, parity)) {
-          acc = fma(-a, tag_value(bits), acc);
-          ++k;
-          c = cn, a = an;
-          if (k + 1 < e) cn = idx[k + 1], an = val[k + 1];
-          spins = 0;
-        } else if (++spins > kSpinLimit) {
-          *error_flag = 1;
-          k           = e;  // give up; publish so that dependants terminate too
-        }
-      }
-      if (k >= e) {
+    // publish finished rows (also rows without any dependency) and step to this thread's
+    // next row; a published value is visible to the block through xs and to later blocks
+    // through x (global, polled by their halo warps)
+    auto finish_rows = [&]() {
+      while (active && k == e) {
         const unsigned long long bits = tag_set(acc, parity);
         xs[r]                         = bits;
         st_publish(x + gi, bits);
@@ -195,14 +182,40 @@ __global__ void __launch_bounds__(T + kPollLanes, 2)
           }
         }
         q += T;
-        if (q < rows) {
-          r   = order[q];
-          acc = acc_next, gi = gi_next;
-          if (q + T < rows) acc_next = load_rhs(order[q + T], gi_next);
-          k = ptr[r], e = ptr[r + 1];
-          if (k < e) c = idx[k], a = val[k];
-          if (k + 1 < e) cn = idx[k + 1], an = val[k + 1];
+        if (q >= rows) {
+          active = false;
+          break;
         }
+        r   = order[q];
+        acc = acc_next, gi = gi_next;
+        if (q + T < rows) acc_next = load_rhs(order[q + T], gi_next);
+        k = ptr[r], e = ptr[r + 1];
+        if (k < e) pa = xs + idx[k], a = val[k];
+      }
+    };
+    finish_rows();
+    // Warp-uniform structure: a SHORT spin (one shared load + vote per iteration) while no
+    // lane of the warp can advance, then a divergent step for the lanes whose dependency
+    // arrived.  No lane ever blocks a sibling: finished values are published inside the
+    // step, before the warp spins again.
+    while (__any_sync(0xffffffffu, active)) {
+      unsigned long long bits = 0;
+      bool               rdy  = false;
+      unsigned           spins = 0;
+      do {
+        if (active) bits = *pa;
+        rdy = active && tag_ready(bits, parity);
+        if (++spins > kSpinLimit) {  // hang guard: flag the error and drain with garbage
+          *error_flag = 1;
+          rdy         = active;
+        }
+      } while (!__any_sync(0xffffffffu, rdy));
+      polls += spins;
+      if (rdy) {
+        acc = fma(-a, tag_value(bits), acc);
+        ++k;
+        if (k < e) pa = xs + idx[k], a = val[k];
+        finish_rows();
       }
     }
   } else {
