@@ -88,13 +88,17 @@ __global__ void dense_qt_kernel(const unsigned nm, const unsigned rk, const doub
   if (lane == 0) c[warp] = acc;
 }
 
-// Back substitution on R(0:rk,0:rk) (column oriented like reference dtrsv 'U','N','N'),
-// blocked by 32: warp 0 solves the diagonal block with shuffles, the whole CTA applies
-// the block's columns to the rows above; then out[jpvt[i]-1] = x_i, zero for i >= rk.
-constexpr int kTrsvThreads = 1024;
+// Back substitution on R(0:rk,0:rk), column oriented like reference dtrsv 'U','N','N'
+// (updates applied in descending column order), blocked by 32: warp 0 keeps the 32x32
+// diagonal tile in registers and solves it with shuffles (one FMA + one shuffle per
+// dependent step), then the whole CTA applies the block's 32 columns to the rows above.
+// The diagonal is applied as a multiplication with 1/R(j,j) precomputed at attach
+// (1 ulp from the reference's division).  Finally out[jpvt[i]-1] = x_i, zero for i >= rk.
+constexpr int kTrsvThreads = 512;
 __global__ void __launch_bounds__(kTrsvThreads, 1)
     dense_trsv_kernel(const unsigned nm, const unsigned rk, const double *__restrict__ R,
-                      const double *__restrict__ c, const int *__restrict__ jpvt, double *__restrict__ out) {
+                      const double *__restrict__ rinv, const double *__restrict__ c,
+                      const int *__restrict__ jpvt, double *__restrict__ out) {
   extern __shared__ double xs[];  // rk values
   const unsigned           tid = threadIdx.x;
   for (unsigned i = tid; i < rk; i += kTrsvThreads) xs[i] = c[i];
@@ -103,29 +107,31 @@ __global__ void __launch_bounds__(kTrsvThreads, 1)
     const unsigned j0 = j1 >= 32u ? j1 - 32u : 0u;  // block [j0, j1)
     const unsigned w  = j1 - j0;
     if (tid < 32) {
-      double xv = tid < w ? xs[j0 + tid] : 0.0;
-      for (unsigned jj = w; jj-- > 0;) {
-        const unsigned col = j0 + jj;
-        double         xj  = 0.0;
-        if (tid == jj) {
-          // reference dtrsv skips the column when x(j) == 0
-          if (xv != 0.0) xv /= R[col + static_cast<std::size_t>(col) * nm];
-          xj = xv;
+      double t[32];  // row `tid` of the diagonal tile
+#pragma unroll
+      for (int jj = 0; jj < 32; ++jj)
+        t[jj] = (static_cast<unsigned>(jj) < w && tid < w) ? R[j0 + tid + static_cast<std::size_t>(j0 + jj) * nm] : 0.0;
+      const double ri = tid < w ? rinv[j0 + tid] : 0.0;
+      double       xv = tid < w ? xs[j0 + tid] : 0.0;
+#pragma unroll
+      for (int jj = 31; jj >= 0; --jj) {
+        if (static_cast<unsigned>(jj) < w) {
+          const double xj = __shfl_sync(0xffffffffu, xv * ri, jj);
+          if (tid == static_cast<unsigned>(jj))
+            xv = xj;
+          else if (tid < static_cast<unsigned>(jj))
+            xv = fma(-xj, t[jj], xv);
         }
-        xj = __shfl_sync(0xffffffffu, xj, jj);
-        if (tid < jj && xj != 0.0) xv = fma(-xj, R[j0 + tid + static_cast<std::size_t>(col) * nm], xv);
       }
       if (tid < w) xs[j0 + tid] = xv;
     }
     __syncthreads();
     // rows above the block: x[i] -= sum_{col in block, descending} R(i,col) * x[col]
     for (unsigned i = tid; i < j0; i += kTrsvThreads) {
-      double xv = xs[i];
-      for (unsigned jj = w; jj-- > 0;) {
-        const unsigned col = j0 + jj;
-        const double   xj  = xs[col];
-        if (xj != 0.0) xv = fma(-xj, R[i + static_cast<std::size_t>(col) * nm], xv);
-      }
+      double        xv = xs[i];
+      const double *Ri = R + i + static_cast<std::size_t>(j0) * nm;
+#pragma unroll 8
+      for (int jj = static_cast<int>(w) - 1; jj >= 0; --jj) xv = fma(-xs[j0 + jj], Ri[static_cast<std::size_t>(jj) * nm], xv);
       xs[i] = xv;
     }
     __syncthreads();
@@ -263,7 +269,7 @@ void apply_dev(Handle *h, const double *d_b, double *d_x, std::size_t rank) {
       HIF_KERNEL_CHECK();
       ++h->launch_count;
     }
-    dense_trsv_kernel<<<1, kTrsvThreads, (rk ? rk : 1) * sizeof(double), h->stream>>>(nm, rk, Q.R.p, Q.c.p, Q.jpvt.p,
+    dense_trsv_kernel<<<1, kTrsvThreads, (rk ? rk : 1) * sizeof(double), h->stream>>>(nm, rk, Q.R.p, Q.rinv.p, Q.c.p, Q.jpvt.p,
                                                                                       last.ychild.p);
     HIF_KERNEL_CHECK();
     mark(h, "dense");

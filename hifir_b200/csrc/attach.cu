@@ -216,6 +216,11 @@ Handle *attach_levels(int device, std::size_t nlevels, const LhfdGpuLevel *lv) {
     h->dense.rank = last.dense_rank;
     h->dense.Q.upload(form_q(nm, last.qr_mat, last.qr_tau), tally);
     h->dense.R.upload(last.qr_mat, nm * nm, tally);
+    {
+      std::vector<double> rinv(nm);
+      for (std::size_t j = 0; j < nm; ++j) rinv[j] = 1.0 / last.qr_mat[j + j * nm];
+      h->dense.rinv.upload(rinv, tally);
+    }
     h->dense.jpvt.upload(reinterpret_cast<const int *>(last.qr_jpvt), nm, tally);
     h->dense.c.alloc(nm, tally);
     h->bytes_dense = nm * nm * sv + nm * (sv + 4);

@@ -98,6 +98,7 @@ struct DevDense {
   std::size_t    nm = 0, rank = 0;
   DevBuf<double> Q;     // nm x nm column-major explicit Q = H_1 ... H_nm (column k = row k of Q^T)
   DevBuf<double> R;     // nm x nm column-major, upper triangle = R
+  DevBuf<double> rinv;  // nm, 1 / R(j,j)
   DevBuf<int>    jpvt;  // nm, 1-based verbatim
   DevBuf<double> c;     // nm work (Q^T b)
 };

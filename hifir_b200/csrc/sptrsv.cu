@@ -33,7 +33,7 @@
 
 namespace hifgpu {
 
-constexpr unsigned kPollWarps = 2;
+constexpr unsigned kPollWarps = 4;
 constexpr unsigned kPollLanes = 32 * kPollWarps;
 constexpr unsigned kRowsMax   = 1024;  // rows per block (the shared-memory budget usually binds first)
 constexpr unsigned kSmemBudget = 112 * 1024;  // per CTA -> two CTAs per SM (227 KB)
@@ -105,11 +105,13 @@ __global__ void __launch_bounds__(T + kPollLanes, 2)
   constexpr unsigned kThreads = T + kPollLanes;
   extern __shared__ __align__(16) unsigned char smem[];
   __shared__ unsigned                        s_blk, s_done;
+  __shared__ unsigned long long              s_pollend;
   __shared__ __align__(8) unsigned long long s_bar;
   const unsigned                             tid = threadIdx.x;
   if (tid == 0) {
     s_blk  = static_cast<unsigned>(atomicAdd(ticket, 1));
     s_done = 0;
+    s_pollend = 0;
     mbar_init(&s_bar, 1);
   }
   __syncthreads();
@@ -179,6 +181,7 @@ __global__ void __launch_bounds__(T + kPollLanes, 2)
             trace[8 * s_blk + 2] = globaltimer_ns();
             trace[8 * s_blk + 4] = polls;
             trace[8 * s_blk + 5] = r;
+            trace[8 * s_blk + 7] = s_pollend;
           }
         }
         q += T;
@@ -222,36 +225,46 @@ __global__ void __launch_bounds__(T + kPollLanes, 2)
     // ---------------- poller: halo entries global (L2) -> shared slots
     const unsigned lane = tid - T;
     const unsigned ne   = nhalo > lane ? (nhalo - lane + kPollLanes - 1) / kPollLanes : 0;  // my entries
-    unsigned       left = ne, passes = 0;
-    while (left) {
-      for (unsigned base = 0; base < ne; base += kPollChunk) {
+    // pending entries of this lane as a bit mask (ne <= 64 by construction).  Every pass
+    // re-polls ONLY the pending ones, up to kPollChunk loads in flight, so that once the
+    // bulk of the halo (long-finished blocks) is in, a pass costs one L2 round trip.
+    unsigned long long pend   = ne >= 64 ? ~0ull : ((1ull << ne) - 1ull);
+    unsigned           passes = 0;
+    while (pend) {
+      unsigned long long scan = pend;
+      while (scan) {
         unsigned long long v[kPollChunk];
-        bool               need[kPollChunk];
+        unsigned           ev[kPollChunk];
 #pragma unroll
         for (unsigned u = 0; u < kPollChunk; ++u) {
-          const unsigned h = lane + kPollLanes * (base + u);
-          need[u]          = base + u < ne && !tag_ready(xs[rows + h], parity);
-          if (need[u]) v[u] = ld_poll(x + halo[h]);
+          ev[u] = 64;
+          if (scan) {
+            ev[u] = static_cast<unsigned>(__ffsll(static_cast<long long>(scan))) - 1u;
+            scan &= scan - 1ull;
+            v[u] = ld_poll(x + halo[lane + kPollLanes * ev[u]]);
+          }
         }
 #pragma unroll
         for (unsigned u = 0; u < kPollChunk; ++u) {
-          if (need[u] && tag_ready(v[u], parity)) {
-            xs[rows + lane + kPollLanes * (base + u)] = v[u];
-            --left;
+          if (ev[u] < 64 && tag_ready(v[u], parity)) {
+            xs[rows + lane + kPollLanes * ev[u]] = v[u];
+            pend &= ~(1ull << ev[u]);
           }
         }
       }
-      if (left && passes > (kSpinLimit >> 6)) {
+      if (pend && ++passes > (kSpinLimit >> 4)) {  // hang guard
         *error_flag = 1;
-        for (unsigned q = 0; q < ne; ++q) {  // release the row threads with garbage
-          const unsigned h = lane + kPollLanes * q;
-          if (!tag_ready(xs[rows + h], parity)) xs[rows + h] = parity;
+        while (pend) {  // release the row threads with garbage
+          const unsigned q = static_cast<unsigned>(__ffsll(static_cast<long long>(pend))) - 1u;
+          pend &= pend - 1ull;
+          xs[rows + lane + kPollLanes * q] = parity;
         }
-        left = 0;
       }
-      ++passes;
     }
-    if (trace && lane == 0) trace[8 * s_blk + 6] = passes;
+    if (trace) {
+      atomicMax(&s_pollend, globaltimer_ns());
+      if (lane == 0) trace[8 * s_blk + 6] = passes;
+    }
   }
 }
 
@@ -307,7 +320,7 @@ static void pack_sweep(const HostCsr &T, bool upper, PackedSweep &out) {
       }
       const unsigned rn   = T.ptr[i + 1] - T.ptr[i];
       const unsigned need = slab_bytes(rows + 1, nh + add_h, nnz + rn) + 8u * (rows + 1 + nh + add_h);
-      if (need > kSmemBudget) {
+      if (need > kSmemBudget || nh + add_h > 64u * kPollLanes) {
         if (!rows)
           throw std::invalid_argument("triangular factor has a row too long for one shared-memory slab (" +
                                       std::to_string(rn) + " nonzeros)");
@@ -439,13 +452,13 @@ void launch_U(Handle *h, const SweepPlan &plan, const double *rhs_plain, const u
   static int T = 0;
   if (!T) {
     const char *e = std::getenv("HIFIR_B200_ROW_THREADS");
-    T             = e ? std::atoi(e) : 192;
+    T             = e ? std::atoi(e) : 448;
   }
   switch (T) {
     case 96: launch_T<UPPER, 96>(h, plan, rhs_plain, rhs_tagged, diag, x, parity, ticket, trace); break;
-    case 448: launch_T<UPPER, 448>(h, plan, rhs_plain, rhs_tagged, diag, x, parity, ticket, trace); break;
-    case 960: launch_T<UPPER, 960>(h, plan, rhs_plain, rhs_tagged, diag, x, parity, ticket, trace); break;
-    default: launch_T<UPPER, 192>(h, plan, rhs_plain, rhs_tagged, diag, x, parity, ticket, trace); break;
+    case 896: launch_T<UPPER, 896>(h, plan, rhs_plain, rhs_tagged, diag, x, parity, ticket, trace); break;
+    case 192: launch_T<UPPER, 192>(h, plan, rhs_plain, rhs_tagged, diag, x, parity, ticket, trace); break;
+    default: launch_T<UPPER, 448>(h, plan, rhs_plain, rhs_tagged, diag, x, parity, ticket, trace); break;
   }
 }
 }  // namespace

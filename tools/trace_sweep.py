@@ -62,6 +62,10 @@ def main():
             dur = (t[:, 2].max() - t0) / 1e3
             life = (t[:, 2] - t[:, 0]) / 1e3
             load = (t[:, 1].astype(np.int64) - t[:, 0].astype(np.int64)) / 1e3
+            halo_wait = (t[:, 7].astype(np.int64) - t[:, 1].astype(np.int64)).clip(min=0) / 1e3
+            tail = (t[:, 2].astype(np.int64) - np.maximum(t[:, 7], t[:, 1]).astype(np.int64)) / 1e3
+            print(f"   halo wait after load mean {halo_wait.mean():.1f} us; in-block tail after halo mean {tail.mean():.1f} "
+                  f"max {tail.max():.1f} us")
             print(f"lv{lvl} {names[which]}: blocks {len(t)} sweep {dur:.1f} us; block life mean {life.mean():.1f} "
                   f"max {life.max():.1f} us; load mean {load.mean():.2f} us; poller passes mean {t[:, 6].mean():.0f} "
                   f"max {t[:, 6].max()}; last-row polls mean {t[:, 4].mean():.0f} max {t[:, 4].max()}; "
