@@ -215,8 +215,18 @@ __global__ void __launch_bounds__(T + kPollLanes, 2)
       } while (!__any_sync(0xffffffffu, rdy));
       polls += spins;
       if (rdy) {
+        // consume the dependency that arrived and, in a burst, the following ones that are
+        // already there (bounded, so that sibling lanes are re-polled soon)
         acc = fma(-a, tag_value(bits), acc);
         ++k;
+#pragma unroll 1
+        for (int burst = 0; burst < 6 && k < e; ++burst) {
+          pa = xs + idx[k], a = val[k];
+          const unsigned long long b2 = *pa;
+          if (!tag_ready(b2, parity)) break;
+          acc = fma(-a, tag_value(b2), acc);
+          ++k;
+        }
         if (k < e) pa = xs + idx[k], a = val[k];
         finish_rows();
       }
@@ -277,6 +287,7 @@ struct PackedSweep {
   std::vector<unsigned char> buf;
   unsigned                   max_smem = 0;
   std::size_t                halo_total = 0;
+  unsigned                   block_depth = 0;
 };
 }  // namespace
 
@@ -384,6 +395,30 @@ static void pack_sweep(const HostCsr &T, bool upper, PackedSweep &out) {
     s0 += rows;
   }
   out.max_smem = max_smem;
+  // ---- ticket order: blocks sorted by their depth in the block dependency graph (block b
+  // needs the blocks its halo entries live in), ties in sweep order.  CTAs take tickets in
+  // this order, so the resident blocks are the least dependent ones that are still
+  // unfinished instead of a long chain of blocks that all wait for each other.
+  const std::size_t     nb = infos.size();
+  std::vector<unsigned> blk_of(m), blev(nb, 0u);
+  for (std::size_t b = 0; b < nb; ++b)
+    for (unsigned r = 0; r < infos[b].rows; ++r) blk_of[infos[b].s0 + r] = static_cast<unsigned>(b);
+  for (std::size_t b = 0; b < nb; ++b) {
+    const unsigned *hl = reinterpret_cast<const unsigned *>(buf.data() + infos[b].off + slab_off_halo(infos[b].rows));
+    unsigned        l  = 0;
+    for (unsigned h = 0; h < infos[b].nhalo; ++h) {
+      const unsigned j = hl[h], sj = upper ? m - 1u - j : j;
+      l = std::max(l, blev[blk_of[sj]] + 1u);
+    }
+    blev[b] = l;
+  }
+  std::vector<unsigned> tick(nb);
+  for (std::size_t b = 0; b < nb; ++b) tick[b] = static_cast<unsigned>(b);
+  std::stable_sort(tick.begin(), tick.end(), [&](unsigned x, unsigned y) { return blev[x] < blev[y]; });
+  std::vector<SlabInfo> sorted(nb);
+  for (std::size_t t = 0; t < nb; ++t) sorted[t] = infos[tick[t]];
+  infos.swap(sorted);
+  out.block_depth = nb ? *std::max_element(blev.begin(), blev.end()) + 1u : 0u;
 }
 
 // CPU emulation of the slab sweep (same packed data, same per-row update order, blocks in
@@ -455,9 +490,9 @@ void launch_U(Handle *h, const SweepPlan &plan, const double *rhs_plain, const u
     T             = e ? std::atoi(e) : 448;
   }
   switch (T) {
-    case 96: launch_T<UPPER, 96>(h, plan, rhs_plain, rhs_tagged, diag, x, parity, ticket, trace); break;
-    case 896: launch_T<UPPER, 896>(h, plan, rhs_plain, rhs_tagged, diag, x, parity, ticket, trace); break;
-    case 192: launch_T<UPPER, 192>(h, plan, rhs_plain, rhs_tagged, diag, x, parity, ticket, trace); break;
+    case 64: launch_T<UPPER, 64>(h, plan, rhs_plain, rhs_tagged, diag, x, parity, ticket, trace); break;
+    case 128: launch_T<UPPER, 128>(h, plan, rhs_plain, rhs_tagged, diag, x, parity, ticket, trace); break;
+    case 256: launch_T<UPPER, 256>(h, plan, rhs_plain, rhs_tagged, diag, x, parity, ticket, trace); break;
     default: launch_T<UPPER, 448>(h, plan, rhs_plain, rhs_tagged, diag, x, parity, ticket, trace); break;
   }
 }
