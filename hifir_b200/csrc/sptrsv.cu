@@ -35,8 +35,9 @@ namespace hifgpu {
 
 constexpr unsigned kPollWarps = 4;
 constexpr unsigned kPollLanes = 32 * kPollWarps;
-constexpr unsigned kRowsMax   = 1024;  // rows per block (the shared-memory budget usually binds first)
+constexpr unsigned kRowsMax   = 896;   // rows per block (the shared-memory budget usually binds first)
 constexpr unsigned kSmemBudget = 112 * 1024;  // per CTA -> two CTAs per SM (227 KB)
+constexpr unsigned kBackoffAfter = 48;  // failed polls before a waiting warp starts to sleep
 constexpr unsigned kPollChunk  = 8;          // independent polling loads in flight per lane
 
 // block descriptor (32 bytes)
@@ -101,7 +102,7 @@ __global__ void __launch_bounds__(T + kPollLanes, 2)
     sptrsv_slab_kernel(const unsigned m, const unsigned char *__restrict__ slabs, const SlabInfo *__restrict__ info,
                        const double *__restrict__ rhs_plain, const unsigned long long *rhs_tagged,
                        const double *__restrict__ diag, unsigned long long *x, const unsigned parity, int *ticket,
-                       int *error_flag, unsigned long long *trace) {
+                       int *error_flag, unsigned long long *trace, const int backoff) {
   constexpr unsigned kThreads = T + kPollLanes;
   extern __shared__ __align__(16) unsigned char smem[];
   __shared__ unsigned                        s_blk, s_done;
@@ -208,9 +209,15 @@ __global__ void __launch_bounds__(T + kPollLanes, 2)
       do {
         if (active) bits = *pa;
         rdy = active && tag_ready(bits, parity);
-        if (++spins > kSpinLimit) {  // hang guard: flag the error and drain with garbage
-          *error_flag = 1;
-          rdy         = active;
+        if (++spins > kBackoffAfter) {
+          // nothing arrived for a while: this warp is waiting for something far away.
+          // Sleep between polls so that it stops competing for issue slots with the warps
+          // that carry the critical chain (cost: <= 1 us wake-up latency, once per wait).
+          if (backoff) __nanosleep(spins > 8 * kBackoffAfter ? 1000u : 200u);
+          if (spins > kSpinLimit) {  // hang guard: flag the error and drain with garbage
+            *error_flag = 1;
+            rdy         = active;
+          }
         }
       } while (!__any_sync(0xffffffffu, rdy));
       polls += spins;
@@ -414,7 +421,8 @@ static void pack_sweep(const HostCsr &T, bool upper, PackedSweep &out) {
   }
   std::vector<unsigned> tick(nb);
   for (std::size_t b = 0; b < nb; ++b) tick[b] = static_cast<unsigned>(b);
-  std::stable_sort(tick.begin(), tick.end(), [&](unsigned x, unsigned y) { return blev[x] < blev[y]; });
+  if (std::getenv("HIFIR_B200_BLOCK_ORDER") && std::string(std::getenv("HIFIR_B200_BLOCK_ORDER")) == "level")
+    std::stable_sort(tick.begin(), tick.end(), [&](unsigned x, unsigned y) { return blev[x] < blev[y]; });
   std::vector<SlabInfo> sorted(nb);
   for (std::size_t t = 0; t < nb; ++t) sorted[t] = infos[tick[t]];
   infos.swap(sorted);
@@ -468,6 +476,10 @@ void build_sweep_plan(const HostCsr &T, bool upper, SweepPlan &plan, std::size_t
 }
 
 namespace {
+int env_int(const char *name, int dflt) {
+  const char *e = std::getenv(name);
+  return e ? std::atoi(e) : dflt;
+}
 template <bool UPPER, unsigned T>
 void launch_T(Handle *h, const SweepPlan &plan, const double *rhs_plain, const unsigned long long *rhs_tagged,
               const double *diag, unsigned long long *x, unsigned parity, int *ticket, unsigned long long *trace) {
@@ -479,7 +491,7 @@ void launch_T(Handle *h, const SweepPlan &plan, const double *rhs_plain, const u
   }
   sptrsv_slab_kernel<UPPER, T><<<plan.nblocks, T + kPollLanes, plan.smem_bytes, h->stream>>>(
       plan.m, plan.slabs.p, reinterpret_cast<const SlabInfo *>(plan.info.p), rhs_plain, rhs_tagged, diag, x, parity,
-      ticket, h->error_flag.p, trace);
+      ticket, h->error_flag.p, trace, env_int("HIFIR_B200_BACKOFF", 1));
 }
 template <bool UPPER>
 void launch_U(Handle *h, const SweepPlan &plan, const double *rhs_plain, const unsigned long long *rhs_tagged,
@@ -490,9 +502,8 @@ void launch_U(Handle *h, const SweepPlan &plan, const double *rhs_plain, const u
     T             = e ? std::atoi(e) : 448;
   }
   switch (T) {
-    case 64: launch_T<UPPER, 64>(h, plan, rhs_plain, rhs_tagged, diag, x, parity, ticket, trace); break;
-    case 128: launch_T<UPPER, 128>(h, plan, rhs_plain, rhs_tagged, diag, x, parity, ticket, trace); break;
     case 256: launch_T<UPPER, 256>(h, plan, rhs_plain, rhs_tagged, diag, x, parity, ticket, trace); break;
+    case 896: launch_T<UPPER, 896>(h, plan, rhs_plain, rhs_tagged, diag, x, parity, ticket, trace); break;
     default: launch_T<UPPER, 448>(h, plan, rhs_plain, rhs_tagged, diag, x, parity, ticket, trace); break;
   }
 }
