@@ -116,6 +116,7 @@ def lib():
             "lhfdGpuProfileSolveDev": [vp, vp, vp, sz, sz, vp, vp, vp, sz],
             "lhfdGpuDebugSweepHost": [vp, i, vp, vp, vp, vp],
             "lhfdGpuDebugTraceSweep": [vp, vp, vp, i, i, vp, sz, vp],
+            "lhfdGpuDebugSimulateSweep": [vp, i, vp, vp],
             "lhfdGpuGetStats": [vp, vp],
             "lhfdGpuGetDepths": [vp, sz, vp],
         }
@@ -133,7 +134,8 @@ EXPORTED_SYMBOLS = (
     "lhfdGpuAttachLevels", "lhfdGpuDestroy", "lhfdGpuSetMatrix", "lhfdGpuSetNspConst", "lhfdGpuClearNsp",
     "lhfdGpuSetStream", "lhfdGpuSynchronize", "lhfdGpuSolve", "lhfdGpuApply", "lhfdGpuSolveMrhs",
     "lhfdGpuFgmres", "lhfdGpuGmres", "lhfdGpuSolveDev", "lhfdGpuSolveMrhsDev", "lhfdGpuHifirDev",
-    "lhfdGpuSpmvDev", "lhfdGpuProfileSolveDev", "lhfdGpuDebugSweepHost", "lhfdGpuDebugTraceSweep", "lhfdGpuGetStats", "lhfdGpuGetDepths", "lhfGpuGetErrorMsg", "lhfGpuVersion")
+    "lhfdGpuSpmvDev", "lhfdGpuProfileSolveDev", "lhfdGpuDebugSweepHost", "lhfdGpuDebugTraceSweep", "lhfdGpuDebugSimulateSweep",
+    "lhfdGpuGetStats", "lhfdGpuGetDepths", "lhfGpuGetErrorMsg", "lhfGpuVersion")
 
 
 class LhfError(RuntimeError):
@@ -162,6 +164,20 @@ def debug_sweep_host(block, upper, rhs, diag=None):
     _chk(lib().lhfdGpuDebugSweepHost(C.byref(c), int(upper), _ptr(rhs), _ptr(d) if d is not None else None,
                                      _ptr(x), _ptr(st)))
     return x, dict(zip(("blocks", "halo", "bytes", "max_smem"), (int(v) for v in st)))
+
+
+def debug_simulate_sweep(block, upper, slots=296, threads=448, t_load=1.7, c_s=0.15, c_g=1.0, t_dep=0.08,
+                         t_pub=0.05):
+    """Host-only timing model of one sweep (lhfdGpuDebugSimulateSweep); microseconds."""
+    nr, nc, cs, ri, va = block
+    cs = np.ascontiguousarray(cs, dtype=np.int64)
+    ri = np.ascontiguousarray(ri, dtype=np.int32)
+    va = np.ascontiguousarray(va, dtype=np.float64)
+    c = LhfdGpuCcs(nr, nc, _ptr(cs), _ptr(ri), _ptr(va))
+    prm = np.array([slots, threads, t_load, c_s, c_g, t_dep, t_pub], dtype=np.float64)
+    out = np.zeros(8)
+    _chk(lib().lhfdGpuDebugSimulateSweep(C.byref(c), int(upper), _ptr(prm), _ptr(out)))
+    return dict(zip(("total", "life_sum", "life_max", "halo_wait", "tail", "blocks"), out[:6]))
 
 
 class GpuHif:

@@ -388,6 +388,18 @@ LhfStatus lhfdGpuDebugTraceSweep(LhfdGpuHdl hdl, const double *d_b, double *d_x,
   });
 }
 
+LhfStatus lhfdGpuDebugSimulateSweep(const LhfdGpuCcs *T, int upper, const double *prm, double *out) {
+  REQUIRE_PTR(T, "T");
+  REQUIRE_PTR(prm, "prm");
+  REQUIRE_PTR(out, "out");
+  return guarded([&] {
+    HostCsr R = ccs_to_csr(*T, "T");
+    R.nrows = R.ncols = T->ncols;
+    R.ptr.resize(T->ncols + 1, R.ptr.empty() ? 0u : R.ptr.back());
+    sweep_simulate(R, upper != 0, prm, out);
+  });
+}
+
 LhfStatus lhfdGpuGetStats(LhfdGpuHdl hdl, size_t stats[]) {
   REQUIRE_HANDLE(hdl);
   REQUIRE_PTR(stats, "stats");

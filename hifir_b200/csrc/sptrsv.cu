@@ -35,7 +35,7 @@ namespace hifgpu {
 
 constexpr unsigned kPollWarps = 4;
 constexpr unsigned kPollLanes = 32 * kPollWarps;
-constexpr unsigned kRowsMax   = 896;   // rows per block (the shared-memory budget usually binds first)
+constexpr unsigned kRowsMax   = 1024;  // rows per block (the shared-memory budget usually binds first)
 constexpr unsigned kSmemBudget = 112 * 1024;  // per CTA -> two CTAs per SM (227 KB)
 constexpr unsigned kBackoffAfter = 48;  // failed polls before a waiting warp starts to sleep
 constexpr unsigned kPollChunk  = 8;          // independent polling loads in flight per lane
@@ -222,18 +222,8 @@ __global__ void __launch_bounds__(T + kPollLanes, 2)
       } while (!__any_sync(0xffffffffu, rdy));
       polls += spins;
       if (rdy) {
-        // consume the dependency that arrived and, in a burst, the following ones that are
-        // already there (bounded, so that sibling lanes are re-polled soon)
         acc = fma(-a, tag_value(bits), acc);
         ++k;
-#pragma unroll 1
-        for (int burst = 0; burst < 6 && k < e; ++burst) {
-          pa = xs + idx[k], a = val[k];
-          const unsigned long long b2 = *pa;
-          if (!tag_ready(b2, parity)) break;
-          acc = fma(-a, tag_value(b2), acc);
-          ++k;
-        }
         if (k < e) pa = xs + idx[k], a = val[k];
         finish_rows();
       }
@@ -313,6 +303,9 @@ static void pack_sweep(const HostCsr &T, bool upper, PackedSweep &out) {
     lev[i] = l;
   }
   std::vector<unsigned short> order;
+  std::vector<unsigned>       ent;
+  const bool sort_by_depth = !(std::getenv("HIFIR_B200_ENTRY_ORDER") &&
+                               std::string(std::getenv("HIFIR_B200_ENTRY_ORDER")) == "natural");
   std::vector<unsigned>      ptr, halo;
   std::vector<unsigned short> idx;
   std::vector<double>         val;
@@ -363,8 +356,16 @@ static void pack_sweep(const HostCsr &T, bool upper, PackedSweep &out) {
       const unsigned i = nat(s0 + r);
       ptr[r]           = static_cast<unsigned>(idx.size());
       const unsigned b = T.ptr[i], e = T.ptr[i + 1];
+      // entries in the order the dependencies become available: by dependency depth of
+      // the producing row (ties: the reference's sweep order).  A row thread consumes its
+      // entries in this order, so the dependency it really waits for comes last and no
+      // finished work queues behind it.
+      ent.resize(e - b);
+      for (unsigned q = 0; q < e - b; ++q) ent[q] = upper ? e - 1u - q : b + q;
+      if (sort_by_depth)
+        std::stable_sort(ent.begin(), ent.end(), [&](unsigned x, unsigned y) { return lev[T.col[x]] < lev[T.col[y]]; });
       for (unsigned q = 0; q < e - b; ++q) {
-        const unsigned k  = upper ? e - 1u - q : b + q;  // U: descending column = sweep order
+        const unsigned k  = ent[q];
         const unsigned j  = static_cast<unsigned>(T.col[k]);
         const unsigned sj = upper ? m - 1u - j : j;
         unsigned       loc;
@@ -460,6 +461,65 @@ void sweep_host_emulate(const HostCsr &T, bool upper, const double *rhs, const d
   stats[3] = P.max_smem;
 }
 
+// Timing model of one sweep on the packed slabs (developer tool, host only): blocks take
+// tickets in order and occupy one of `slots` CTA slots; a row starts when its thread is
+// free, consumes its dependencies in order (each available c_s after its producer finished
+// inside the block, c_g after it finished in another block), t_dep per dependency.
+// prm = {slots, T, t_load, c_s, c_g, t_dep, t_pub}; out = {total, sum of block lives, max
+// block life, mean halo wait, mean in-block tail, blocks}.  Times in microseconds.
+void sweep_simulate(const HostCsr &T, bool upper, const double *prm, double *out) {
+  PackedSweep P;
+  pack_sweep(T, upper, P);
+  const unsigned      m     = static_cast<unsigned>(T.nrows);
+  const unsigned      slots = static_cast<unsigned>(prm[0]), NT = static_cast<unsigned>(prm[1]);
+  const double        t_load = prm[2], c_s = prm[3], c_g = prm[4], t_dep = prm[5], t_pub = prm[6];
+  std::vector<double> F(m, 0.0), fin, arrive, thr;
+  std::vector<double> slot_free(slots, 0.0);
+  double              prev_start = 0.0, total = 0.0, life_sum = 0.0, life_max = 0.0, wait_sum = 0.0, tail_sum = 0.0;
+  for (const SlabInfo &bi : P.infos) {
+    const unsigned char * base  = P.buf.data() + bi.off;
+    const unsigned *      ptr   = reinterpret_cast<const unsigned *>(base);
+    const unsigned *      halo  = reinterpret_cast<const unsigned *>(base + slab_off_halo(bi.rows));
+    const unsigned short *order = reinterpret_cast<const unsigned short *>(base + slab_off_order(bi.rows, bi.nhalo));
+    const unsigned short *idx   = reinterpret_cast<const unsigned short *>(base + slab_off_idx(bi.rows, bi.nhalo));
+    auto                  it    = std::min_element(slot_free.begin(), slot_free.end());
+    const double          start = std::max(prev_start, *it);
+    prev_start                  = start;
+    const double ready = start + t_load;
+    arrive.assign(bi.nhalo, 0.0);
+    double last_halo = ready;
+    for (unsigned h = 0; h < bi.nhalo; ++h) {
+      arrive[h] = std::max(ready, F[halo[h]] + c_g);
+      last_halo = std::max(last_halo, arrive[h]);
+    }
+    fin.assign(bi.rows, 0.0);
+    thr.assign(NT, ready);
+    double done = ready;
+    for (unsigned q = 0; q < bi.rows; ++q) {
+      const unsigned r = order[q];
+      double         t = thr[q % NT];
+      for (unsigned k = ptr[r]; k < ptr[r + 1]; ++k) {
+        const unsigned c  = idx[k];
+        const double   av = c < bi.rows ? fin[c] + c_s : arrive[c - bi.rows];
+        t                 = std::max(t, av) + t_dep;
+      }
+      fin[r]            = t + t_pub;
+      const unsigned s  = bi.s0 + r;
+      F[upper ? m - 1u - s : s] = fin[r];
+      thr[q % NT]       = fin[r];
+      done              = std::max(done, fin[r]);
+    }
+    *it = done;
+    total = std::max(total, done);
+    life_sum += done - start;
+    life_max = std::max(life_max, done - start);
+    wait_sum += last_halo - ready;
+    tail_sum += done - last_halo;
+  }
+  const double nb = static_cast<double>(P.infos.size());
+  out[0] = total, out[1] = life_sum, out[2] = life_max, out[3] = wait_sum / nb, out[4] = tail_sum / nb, out[5] = nb;
+}
+
 void build_sweep_plan(const HostCsr &T, bool upper, SweepPlan &plan, std::size_t *tally) {
   plan.m       = static_cast<unsigned>(T.nrows);
   plan.upper   = upper;
@@ -503,7 +563,7 @@ void launch_U(Handle *h, const SweepPlan &plan, const double *rhs_plain, const u
   }
   switch (T) {
     case 256: launch_T<UPPER, 256>(h, plan, rhs_plain, rhs_tagged, diag, x, parity, ticket, trace); break;
-    case 896: launch_T<UPPER, 896>(h, plan, rhs_plain, rhs_tagged, diag, x, parity, ticket, trace); break;
+    case 640: launch_T<UPPER, 640>(h, plan, rhs_plain, rhs_tagged, diag, x, parity, ticket, trace); break;
     default: launch_T<UPPER, 448>(h, plan, rhs_plain, rhs_tagged, diag, x, parity, ticket, trace); break;
   }
 }

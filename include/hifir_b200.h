@@ -210,6 +210,11 @@ LhfStatus lhfdGpuDebugSweepHost(const LhfdGpuCcs *T, int upper, const double *rh
 LhfStatus lhfdGpuDebugTraceSweep(LhfdGpuHdl hdl, const double *d_b, double *d_x, int level, int which,
                                  unsigned long long *out, size_t max_blocks, size_t *nblocks);
 
+/* Host-only developer tool: timing model of one sweep over the packed slabs.
+ * prm = {CTA slots, row threads, t_load, c_s, c_g, t_dep, t_pub} (microseconds);
+ * out = {total, sum of block lives, max block life, mean halo wait, mean tail, blocks}. */
+LhfStatus lhfdGpuDebugSimulateSweep(const LhfdGpuCcs *T, int upper, const double *prm, double *out);
+
 /* per-level dependency depth of the L and U sweeps: depth[2*l], depth[2*l+1] */
 LhfStatus lhfdGpuGetDepths(LhfdGpuHdl hdl, size_t nlevels, size_t *depth);
 
