@@ -37,7 +37,7 @@ constexpr unsigned kPollWarps = 4;
 constexpr unsigned kPollLanes = 32 * kPollWarps;
 constexpr unsigned kRowsMax   = 1024;  // rows per block (the shared-memory budget usually binds first)
 constexpr unsigned kSmemBudget = 112 * 1024;  // per CTA -> two CTAs per SM (227 KB)
-constexpr unsigned kBackoffAfter = 48;  // failed polls before a waiting warp starts to sleep
+constexpr unsigned kSpinBurst = 2048;  // polls between two hang-guard / back-off checks
 constexpr unsigned kPollChunk  = 8;          // independent polling loads in flight per lane
 
 // block descriptor (32 bytes)
@@ -130,7 +130,7 @@ __global__ void __launch_bounds__(T + kPollLanes, 2)
   const unsigned rows = bi.rows, nhalo = bi.nhalo, nnz = bi.nnz;
   volatile unsigned long long *xs = reinterpret_cast<volatile unsigned long long *>(smem + bi.bytes);
   const unsigned long long     not_ready = parity ^ 1u;
-  for (unsigned i = tid; i < rows + nhalo; i += kThreads) xs[i] = not_ready;
+  for (unsigned i = tid; i < rows + nhalo + 1u; i += kThreads) xs[i] = not_ready;  // +1: dummy slot
 
   // right-hand side of a row: b_i (L sweep) or (L^{-1}b)_i / d_i with a true division
   // (prec_solve.hpp:219) for the U sweep; fetched one row ahead of its use
@@ -155,7 +155,12 @@ __global__ void __launch_bounds__(T + kPollLanes, 2)
     // (order[]); thread t solves order[t], order[t+T], ... one after the other, so a
     // thread's next row is never expected to be ready before its current one and only
     // T threads (not one per row) spin on the shared-memory pipe at any time.
-    unsigned q = tid;  // position in order[]
+    // Position q of order[] belongs to warp q % nwarps: rows that follow each other in
+    // depth order (a dependent chain) sit in DIFFERENT warps, so the warp that just
+    // published (and is busy setting up its next row) never delays the lane that waits
+    // for that value.
+    constexpr unsigned kRowWarps = T / 32;
+    unsigned           q         = (tid & 31u) * kRowWarps + (tid >> 5);  // position in order[]
     unsigned r = 0, gi = 0, gi_next = 0;
     double   acc = 0.0, acc_next = 0.0;
     unsigned k = 0, e = 0, polls = 0;
@@ -202,30 +207,41 @@ __global__ void __launch_bounds__(T + kPollLanes, 2)
     // lane of the warp can advance, then a divergent step for the lanes whose dependency
     // arrived.  No lane ever blocks a sibling: finished values are published inside the
     // step, before the warp spins again.
+    volatile unsigned long long *const dummy = xs + rows + nhalo;  // never becomes ready
+    if (!active) pa = dummy;
     while (__any_sync(0xffffffffu, active)) {
-      unsigned long long bits = 0;
-      bool               rdy  = false;
-      unsigned           spins = 0;
-      do {
-        if (active) bits = *pa;
-        rdy = active && tag_ready(bits, parity);
-        if (++spins > kBackoffAfter) {
-          // nothing arrived for a while: this warp is waiting for something far away.
-          // Sleep between polls so that it stops competing for issue slots with the warps
-          // that carry the critical chain (cost: <= 1 us wake-up latency, once per wait).
-          if (backoff) __nanosleep(spins > 8 * kBackoffAfter ? 1000u : 200u);
-          if (spins > kSpinLimit) {  // hang guard: flag the error and drain with garbage
-            *error_flag = 1;
-            rdy         = active;
-          }
+      unsigned long long bits;
+      bool               rdy;
+      unsigned           rounds = 0;
+      // tight spin: one shared load, one test, one vote per iteration (finished lanes poll
+      // the dummy slot, so the loop needs no per-lane predicate)
+      for (;;) {
+        bool any = false;
+#pragma unroll 1
+        for (unsigned it = 0; it < kSpinBurst; ++it) {
+          bits = *pa;
+          rdy  = (static_cast<unsigned>(bits) & 1u) == parity;
+          any  = __any_sync(0xffffffffu, rdy);
+          if (any) break;
         }
-      } while (!__any_sync(0xffffffffu, rdy));
-      polls += spins;
+        if (any) break;
+        // nothing arrived during a whole burst (~100 us): this warp waits for something
+        // far away -- sleep between bursts so that it stops competing for issue slots
+        ++rounds;
+        if (backoff) __nanosleep(1000u);
+        if (rounds > kSpinLimit / kSpinBurst) {  // hang guard: flag the error, drain with garbage
+          *error_flag = 1;
+          rdy         = active;
+          break;
+        }
+      }
+      if (trace) polls += rounds;
       if (rdy) {
         acc = fma(-a, tag_value(bits), acc);
         ++k;
         if (k < e) pa = xs + idx[k], a = val[k];
         finish_rows();
+        if (!active) pa = dummy;
       }
     }
   } else {
@@ -330,7 +346,7 @@ static void pack_sweep(const HostCsr &T, bool upper, PackedSweep &out) {
         }
       }
       const unsigned rn   = T.ptr[i + 1] - T.ptr[i];
-      const unsigned need = slab_bytes(rows + 1, nh + add_h, nnz + rn) + 8u * (rows + 1 + nh + add_h);
+      const unsigned need = slab_bytes(rows + 1, nh + add_h, nnz + rn) + 8u * (rows + 2 + nh + add_h);
       if (need > kSmemBudget || nh + add_h > 64u * kPollLanes) {
         if (!rows)
           throw std::invalid_argument("triangular factor has a row too long for one shared-memory slab (" +
@@ -398,7 +414,7 @@ static void pack_sweep(const HostCsr &T, bool upper, PackedSweep &out) {
       std::memcpy(base + slab_off_val(rows, nh, nnz), val.data(), 8u * nnz);
     }
     infos.push_back(bi);
-    max_smem = std::max(max_smem, bi.bytes + 8u * (rows + nh));
+    max_smem = std::max(max_smem, bi.bytes + 8u * (rows + nh + 1u));
     out.halo_total += nh;
     s0 += rows;
   }
