@@ -117,6 +117,7 @@ def lib():
             "lhfdGpuDebugSweepHost": [vp, i, vp, vp, vp, vp],
             "lhfdGpuDebugTraceSweep": [vp, vp, vp, i, i, vp, sz, vp],
             "lhfdGpuDebugSimulateSweep": [vp, i, vp, vp],
+            "lhfdGpuDebugBlockGraph": [vp, i, sz, sz, vp, vp, vp, vp],
             "lhfdGpuGetStats": [vp, vp],
             "lhfdGpuGetDepths": [vp, sz, vp],
         }
@@ -134,7 +135,7 @@ EXPORTED_SYMBOLS = (
     "lhfdGpuAttachLevels", "lhfdGpuDestroy", "lhfdGpuSetMatrix", "lhfdGpuSetNspConst", "lhfdGpuClearNsp",
     "lhfdGpuSetStream", "lhfdGpuSynchronize", "lhfdGpuSolve", "lhfdGpuApply", "lhfdGpuSolveMrhs",
     "lhfdGpuFgmres", "lhfdGpuGmres", "lhfdGpuSolveDev", "lhfdGpuSolveMrhsDev", "lhfdGpuHifirDev",
-    "lhfdGpuSpmvDev", "lhfdGpuProfileSolveDev", "lhfdGpuDebugSweepHost", "lhfdGpuDebugTraceSweep", "lhfdGpuDebugSimulateSweep",
+    "lhfdGpuSpmvDev", "lhfdGpuProfileSolveDev", "lhfdGpuDebugSweepHost", "lhfdGpuDebugTraceSweep", "lhfdGpuDebugSimulateSweep", "lhfdGpuDebugBlockGraph",
     "lhfdGpuGetStats", "lhfdGpuGetDepths", "lhfGpuGetErrorMsg", "lhfGpuVersion")
 
 
@@ -178,6 +179,23 @@ def debug_simulate_sweep(block, upper, slots=296, threads=448, t_load=1.7, c_s=0
     out = np.zeros(8)
     _chk(lib().lhfdGpuDebugSimulateSweep(C.byref(c), int(upper), _ptr(prm), _ptr(out)))
     return dict(zip(("total", "life_sum", "life_max", "halo_wait", "tail", "blocks"), out[:6]))
+
+
+def debug_block_graph(block, upper, max_blocks=1 << 16, max_edges=1 << 24):
+    """Host-only: (info[nb,4] = s0, rows, nhalo, nnz ; src_ptr ; src_idx) of the packed sweep."""
+    nr, nc, cs, ri, va = block
+    cs = np.ascontiguousarray(cs, dtype=np.int64)
+    ri = np.ascontiguousarray(ri, dtype=np.int32)
+    va = np.ascontiguousarray(va, dtype=np.float64)
+    c = LhfdGpuCcs(nr, nc, _ptr(cs), _ptr(ri), _ptr(va))
+    info = np.zeros(max_blocks * 4, dtype=np.uint32)
+    sp = np.zeros(max_blocks + 1, dtype=np.uint32)
+    sx = np.zeros(max_edges, dtype=np.uint32)
+    nb = C.c_size_t()
+    _chk(lib().lhfdGpuDebugBlockGraph(C.byref(c), int(upper), max_blocks, max_edges, _ptr(info), _ptr(sp), _ptr(sx),
+                                      C.byref(nb)))
+    n = nb.value
+    return info[: 4 * n].reshape(n, 4), sp[: n + 1], sx[: sp[n]]
 
 
 class GpuHif:

@@ -400,6 +400,25 @@ LhfStatus lhfdGpuDebugSimulateSweep(const LhfdGpuCcs *T, int upper, const double
   });
 }
 
+LhfStatus lhfdGpuDebugBlockGraph(const LhfdGpuCcs *T, int upper, size_t max_blocks, size_t max_edges,
+                                 unsigned *info, unsigned *src_ptr, unsigned *src_idx, size_t *nblocks) {
+  REQUIRE_PTR(T, "T");
+  REQUIRE_PTR(nblocks, "nblocks");
+  return guarded([&] {
+    HostCsr R = ccs_to_csr(*T, "T");
+    R.nrows = R.ncols = T->ncols;
+    R.ptr.resize(T->ncols + 1, R.ptr.empty() ? 0u : R.ptr.back());
+    std::vector<unsigned> vi, vp, vx;
+    sweep_block_graph(R, upper != 0, vi, vp, vx);
+    const size_t nb = vp.size() - 1;
+    if (nb > max_blocks || vx.size() > max_edges) throw std::length_error("block graph exceeds the output buffers");
+    std::copy(vi.begin(), vi.end(), info);
+    std::copy(vp.begin(), vp.end(), src_ptr);
+    std::copy(vx.begin(), vx.end(), src_idx);
+    *nblocks = nb;
+  });
+}
+
 LhfStatus lhfdGpuGetStats(LhfdGpuHdl hdl, size_t stats[]) {
   REQUIRE_HANDLE(hdl);
   REQUIRE_PTR(stats, "stats");

@@ -151,6 +151,8 @@ HostCsr ccs_to_csr(const LhfdGpuCcs &c, const char *name);
 void build_sweep_plan(const HostCsr &T, bool upper, SweepPlan &plan, std::size_t *tally);
 void sweep_host_emulate(const HostCsr &T, bool upper, const double *rhs, const double *diag, double *x,
                         std::size_t stats[4]);
+void sweep_block_graph(const HostCsr &T, bool upper, std::vector<unsigned> &info, std::vector<unsigned> &src_ptr,
+                       std::vector<unsigned> &src_idx);
 void sweep_simulate(const HostCsr &T, bool upper, const double *prm, double *out);
 void launch_sweep(Handle *h, const SweepPlan &plan, const double *rhs_plain, const unsigned long long *rhs_tagged,
                   const double *diag, unsigned long long *x, unsigned parity, int *ticket,

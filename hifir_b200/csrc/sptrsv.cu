@@ -36,7 +36,12 @@ namespace hifgpu {
 constexpr unsigned kPollWarps = 4;
 constexpr unsigned kPollLanes = 32 * kPollWarps;
 constexpr unsigned kRowsMax   = 1024;  // rows per block (the shared-memory budget usually binds first)
-constexpr unsigned kSmemBudget = 112 * 1024;  // per CTA -> two CTAs per SM (227 KB)
+constexpr unsigned kSmemBudgetMax = 112 * 1024;  // per CTA -> two CTAs per SM (227 KB)
+static unsigned smem_budget() {
+  const char *e = std::getenv("HIFIR_B200_SMEM_KB");
+  const unsigned kb = e ? static_cast<unsigned>(std::atoi(e)) : 112u;
+  return std::min(kSmemBudgetMax, std::max(16u, kb) * 1024u);
+}
 constexpr unsigned kSpinBurst = 2048;  // polls between two hang-guard / back-off checks
 constexpr unsigned kPollChunk  = 8;          // independent polling loads in flight per lane
 
@@ -98,11 +103,11 @@ __device__ __forceinline__ bool mbar_try_wait(unsigned long long *bar, unsigned 
 }
 
 template <bool UPPER, unsigned T>
-__global__ void __launch_bounds__(T + kPollLanes, 2)
+__global__ void __launch_bounds__(T + kPollLanes, (T <= 256 ? 4 : 2))
     sptrsv_slab_kernel(const unsigned m, const unsigned char *__restrict__ slabs, const SlabInfo *__restrict__ info,
                        const double *__restrict__ rhs_plain, const unsigned long long *rhs_tagged,
                        const double *__restrict__ diag, unsigned long long *x, const unsigned parity, int *ticket,
-                       int *error_flag, unsigned long long *trace, const int backoff) {
+                       int *error_flag, unsigned long long *trace, const int backoff, const unsigned poll_sleep) {
   constexpr unsigned kThreads = T + kPollLanes;
   extern __shared__ __align__(16) unsigned char smem[];
   __shared__ unsigned                        s_blk, s_done;
@@ -275,6 +280,10 @@ __global__ void __launch_bounds__(T + kPollLanes, 2)
           }
         }
       }
+      // Pending entries belong to rows that are still being computed.  In a fan-out sweep
+      // hundreds of CTAs wait for the same few producer rows; polling them back to back
+      // would queue thousands of loads in front of the producer's store at one L2 slice.
+      if (pend && poll_sleep) __nanosleep(poll_sleep);
       if (pend && ++passes > (kSpinLimit >> 4)) {  // hang guard
         *error_flag = 1;
         while (pend) {  // release the row threads with garbage
@@ -328,6 +337,7 @@ static void pack_sweep(const HostCsr &T, bool upper, PackedSweep &out) {
   unsigned                    max_smem = 0;
   auto nat = [&](unsigned s) { return upper ? m - 1u - s : s; };
 
+  const unsigned budget = smem_budget();
   unsigned s0 = 0, bid = 0;
   while (s0 < m) {
     ++bid;
@@ -347,7 +357,7 @@ static void pack_sweep(const HostCsr &T, bool upper, PackedSweep &out) {
       }
       const unsigned rn   = T.ptr[i + 1] - T.ptr[i];
       const unsigned need = slab_bytes(rows + 1, nh + add_h, nnz + rn) + 8u * (rows + 2 + nh + add_h);
-      if (need > kSmemBudget || nh + add_h > 64u * kPollLanes) {
+      if (need > budget || nh + add_h > 64u * kPollLanes) {
         if (!rows)
           throw std::invalid_argument("triangular factor has a row too long for one shared-memory slab (" +
                                       std::to_string(rn) + " nonzeros)");
@@ -536,6 +546,32 @@ void sweep_simulate(const HostCsr &T, bool upper, const double *prm, double *out
   out[0] = total, out[1] = life_sum, out[2] = life_max, out[3] = wait_sum / nb, out[4] = tail_sum / nb, out[5] = nb;
 }
 
+// developer tool: the block dependency graph of a packed sweep, in ticket order
+void sweep_block_graph(const HostCsr &T, bool upper, std::vector<unsigned> &info, std::vector<unsigned> &src_ptr,
+                       std::vector<unsigned> &src_idx) {
+  PackedSweep P;
+  pack_sweep(T, upper, P);
+  const unsigned        m = static_cast<unsigned>(T.nrows);
+  std::vector<unsigned> blk_of(m);
+  for (std::size_t b = 0; b < P.infos.size(); ++b)
+    for (unsigned r = 0; r < P.infos[b].rows; ++r) blk_of[P.infos[b].s0 + r] = static_cast<unsigned>(b);
+  src_ptr.assign(1, 0u);
+  std::vector<unsigned> seen(P.infos.size(), 0xffffffffu);
+  for (std::size_t b = 0; b < P.infos.size(); ++b) {
+    const SlabInfo &bi = P.infos[b];
+    info.insert(info.end(), {bi.s0, bi.rows, bi.nhalo, bi.nnz});
+    const unsigned *hl = reinterpret_cast<const unsigned *>(P.buf.data() + bi.off + slab_off_halo(bi.rows));
+    for (unsigned h = 0; h < bi.nhalo; ++h) {
+      const unsigned j = hl[h], sb = blk_of[upper ? m - 1u - j : j];
+      if (seen[sb] != b) {
+        seen[sb] = static_cast<unsigned>(b);
+        src_idx.push_back(sb);
+      }
+    }
+    src_ptr.push_back(static_cast<unsigned>(src_idx.size()));
+  }
+}
+
 void build_sweep_plan(const HostCsr &T, bool upper, SweepPlan &plan, std::size_t *tally) {
   plan.m       = static_cast<unsigned>(T.nrows);
   plan.upper   = upper;
@@ -562,12 +598,13 @@ void launch_T(Handle *h, const SweepPlan &plan, const double *rhs_plain, const u
   static bool configured = false;
   if (!configured) {
     HIF_CUDA(cudaFuncSetAttribute(sptrsv_slab_kernel<UPPER, T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  static_cast<int>(kSmemBudget)));
+                                  static_cast<int>(kSmemBudgetMax)));
     configured = true;
   }
   sptrsv_slab_kernel<UPPER, T><<<plan.nblocks, T + kPollLanes, plan.smem_bytes, h->stream>>>(
       plan.m, plan.slabs.p, reinterpret_cast<const SlabInfo *>(plan.info.p), rhs_plain, rhs_tagged, diag, x, parity,
-      ticket, h->error_flag.p, trace, env_int("HIFIR_B200_BACKOFF", 1));
+      ticket, h->error_flag.p, trace, env_int("HIFIR_B200_BACKOFF", 1),
+      static_cast<unsigned>(env_int("HIFIR_B200_POLL_SLEEP", 100)));
 }
 template <bool UPPER>
 void launch_U(Handle *h, const SweepPlan &plan, const double *rhs_plain, const unsigned long long *rhs_tagged,

@@ -215,6 +215,12 @@ LhfStatus lhfdGpuDebugTraceSweep(LhfdGpuHdl hdl, const double *d_b, double *d_x,
  * out = {total, sum of block lives, max block life, mean halo wait, mean tail, blocks}. */
 LhfStatus lhfdGpuDebugSimulateSweep(const LhfdGpuCcs *T, int upper, const double *prm, double *out);
 
+/* Host-only developer tool: block dependency graph of a packed sweep in ticket order.
+ * info[4*b] = {first sweep row, rows, halo entries, nnz}; block b needs blocks
+ * src_idx[src_ptr[b] .. src_ptr[b+1]). */
+LhfStatus lhfdGpuDebugBlockGraph(const LhfdGpuCcs *T, int upper, size_t max_blocks, size_t max_edges,
+                                 unsigned *info, unsigned *src_ptr, unsigned *src_idx, size_t *nblocks);
+
 /* per-level dependency depth of the L and U sweeps: depth[2*l], depth[2*l+1] */
 LhfStatus lhfdGpuGetDepths(LhfdGpuHdl hdl, size_t nlevels, size_t *depth);
 
