@@ -74,8 +74,8 @@ def test_attach_without_gpu_fails_loudly(lib):
 @pytest.mark.parametrize("case", ["demo_A", "poisson14_ml", "stokes28_ml"])
 def test_slab_packing_host_emulation(lib, case):
     """Host logic of the triangular sweeps: pack each L_B / U_B of the fixtures into device
-    slabs and solve with them on the CPU -- must equal plain substitution bit for bit up to
-    reassociation-free arithmetic (same update order => identical without FMA)."""
+    slabs and solve with them on the CPU -- must equal plain substitution up to the
+    reassociation of each row's updates (the slabs list a row's entries by dependency depth)."""
     import scipy.sparse as sp
     g = load_golden(case)
     rng = np.random.default_rng(1)
@@ -99,7 +99,7 @@ def test_slab_packing_host_emulation(lib, case):
                 for j, v in seq:
                     acc -= v * ref[j]
                 ref[i] = acc
-            assert np.array_equal(x, ref), (case, name)
+            assert np.linalg.norm(x - ref) <= 1e-14 * np.linalg.norm(ref), (case, name)
             assert st["blocks"] >= 1 and st["max_smem"] <= 112 * 1024
             assert st["bytes"] >= 10 * len(va)
 
