@@ -54,20 +54,14 @@ struct alignas(16) SlabInfo {
 };
 
 __host__ __device__ inline unsigned pad16(unsigned x) { return (x + 15u) & ~15u; }
-// slab layout: [ptr u32[rows+1]] [halo u32[nhalo]] [order u16[rows]] [rowinfo u64[rows]] [idx u16[nnz]]
-// [val f64[nnz]],
+// slab layout: [ptr u32[rows+1]] [halo u32[nhalo]] [order u16[rows]] [idx u16[nnz]] [val f64[nnz]],
 // 16B-aligned segments.  order = the block's rows sorted by dependency depth (see kernel).
 __host__ __device__ inline unsigned slab_off_halo(unsigned rows) { return pad16(4u * (rows + 1u)); }
 __host__ __device__ inline unsigned slab_off_order(unsigned rows, unsigned nhalo) {
   return slab_off_halo(rows) + pad16(4u * nhalo);
 }
-// rowinfo[q] = {first entry u32 | entries u16 | local row u16} of the q-th row in depth order:
-// everything a row thread needs to switch rows comes with one 8-byte shared load
-__host__ __device__ inline unsigned slab_off_rowinfo(unsigned rows, unsigned nhalo) {
-  return slab_off_order(rows, nhalo) + pad16(2u * rows);
-}
 __host__ __device__ inline unsigned slab_off_idx(unsigned rows, unsigned nhalo) {
-  return slab_off_rowinfo(rows, nhalo) + pad16(8u * rows);
+  return slab_off_order(rows, nhalo) + pad16(2u * rows);
 }
 __host__ __device__ inline unsigned slab_off_val(unsigned rows, unsigned nhalo, unsigned nnz) {
   return slab_off_idx(rows, nhalo) + pad16(2u * nnz);
@@ -113,8 +107,7 @@ __global__ void __launch_bounds__(T + kPollLanes, (T <= 256 ? 4 : 2))
     sptrsv_slab_kernel(const unsigned m, const unsigned char *__restrict__ slabs, const SlabInfo *__restrict__ info,
                        const double *__restrict__ rhs_plain, const unsigned long long *rhs_tagged,
                        const double *__restrict__ diag, unsigned long long *x, const unsigned parity, int *ticket,
-                       int *error_flag, unsigned long long *trace, const int backoff, const unsigned poll_sleep,
-                       const unsigned spin_burst) {
+                       int *error_flag, unsigned long long *trace, const int backoff, const unsigned poll_sleep) {
   constexpr unsigned kThreads = T + kPollLanes;
   extern __shared__ __align__(16) unsigned char smem[];
   __shared__ unsigned                        s_blk, s_done;
@@ -141,116 +134,107 @@ __global__ void __launch_bounds__(T + kPollLanes, (T <= 256 ? 4 : 2))
   }
   const unsigned rows = bi.rows, nhalo = bi.nhalo, nnz = bi.nnz;
   volatile unsigned long long *xs = reinterpret_cast<volatile unsigned long long *>(smem + bi.bytes);
-  // xs[r] starts as the row's right-hand side carrying the NOT-ready tag: b_i (L sweep) or
-  // (L^{-1}b)_i / d_i with a true division (prec_solve.hpp:219) for the U sweep.  All
-  // threads fetch these coalesced while the slab is in flight; the row thread later picks
-  // its accumulator up from xs[r] and overwrites it with the tagged solution.
-  const unsigned not_ready = parity ^ 1u;
-  for (unsigned i = tid; i < rows; i += kThreads) {
-    const unsigned s  = bi.s0 + i;
-    const unsigned gi = UPPER ? m - 1u - s : s;
-    const double   v  = UPPER ? tag_value(rhs_tagged[gi]) / diag[gi] : rhs_plain[gi];
-    xs[i]             = tag_set(v, not_ready);
-  }
-  for (unsigned i = rows + tid; i < rows + nhalo + 1u; i += kThreads) xs[i] = not_ready;  // +1: dummy slot
+  const unsigned long long     not_ready = parity ^ 1u;
+  for (unsigned i = tid; i < rows + nhalo + 1u; i += kThreads) xs[i] = not_ready;  // +1: dummy slot
+
+  // right-hand side of a row: b_i (L sweep) or (L^{-1}b)_i / d_i with a true division
+  // (prec_solve.hpp:219) for the U sweep; fetched one row ahead of its use
+  auto load_rhs = [&](unsigned r, unsigned &gi) -> double {
+    const unsigned s = bi.s0 + r;
+    gi               = UPPER ? m - 1u - s : s;
+    return UPPER ? tag_value(rhs_tagged[gi]) / diag[gi] : rhs_plain[gi];
+  };
   __syncthreads();  // xs initialised
   while (!mbar_try_wait(&s_bar, 0)) {
   }
   if (trace && tid == 0) trace[8 * s_blk + 1] = globaltimer_ns();
 
-  const unsigned *          halo    = reinterpret_cast<const unsigned *>(smem + slab_off_halo(rows));
-  const unsigned long long *rowinfo = reinterpret_cast<const unsigned long long *>(smem + slab_off_rowinfo(rows, nhalo));
-  const unsigned short *    idx     = reinterpret_cast<const unsigned short *>(smem + slab_off_idx(rows, nhalo));
-  const double *            val     = reinterpret_cast<const double *>(smem + slab_off_val(rows, nhalo, nnz));
+  const unsigned *      ptr   = reinterpret_cast<const unsigned *>(smem);
+  const unsigned *      halo  = reinterpret_cast<const unsigned *>(smem + slab_off_halo(rows));
+  const unsigned short *order = reinterpret_cast<const unsigned short *>(smem + slab_off_order(rows, nhalo));
+  const unsigned short *idx  = reinterpret_cast<const unsigned short *>(smem + slab_off_idx(rows, nhalo));
+  const double *        val  = reinterpret_cast<const double *>(smem + slab_off_val(rows, nhalo, nnz));
 
   if (tid < T) {
-    // ---------------- row thread.  The block's rows are sorted by dependency depth;
-    // thread t solves the rows at positions q0, q0+T, ... of that order one after the
-    // other, so a thread's next row is never expected to be ready before its current one
-    // and only T threads (not one per row) spin at any time.  Position q belongs to warp
-    // q % nwarps: rows that follow each other in depth order (a dependent chain) sit in
-    // DIFFERENT warps, so the warp that just published never delays the lane that waits
-    // for that value.  Row switches and the next dependency are prefetched into registers,
-    // which keeps the code between "value arrived" and "result published" minimal.
+    // ---------------- row thread.  The block's rows are sorted by dependency depth
+    // (order[]); thread t solves order[t], order[t+T], ... one after the other, so a
+    // thread's next row is never expected to be ready before its current one and only
+    // T threads (not one per row) spin on the shared-memory pipe at any time.
+    // Position q of order[] belongs to warp q % nwarps: rows that follow each other in
+    // depth order (a dependent chain) sit in DIFFERENT warps, so the warp that just
+    // published (and is busy setting up its next row) never delays the lane that waits
+    // for that value.
     constexpr unsigned kRowWarps = T / 32;
-    unsigned           q         = (tid & 31u) * kRowWarps + (tid >> 5);
-    volatile unsigned long long *const dummy = xs + rows + nhalo;  // never becomes ready
-    const volatile unsigned long long *pa    = dummy;               // slot this lane waits for
-    unsigned           k = 0, e = 0, r = 0, polls = 0;
-    unsigned           idx_n = 0;   // prefetched next entry
-    double             a = 0.0, a_n = 0.0, acc = 0.0, acc_n = 0.0;
-    unsigned long long d1 = 0, d2 = 0;  // descriptors of this thread's next two rows
-    bool               active = q < rows;
-    auto start_row = [&](unsigned long long d, double rhs) {
-      k   = static_cast<unsigned>(d);
-      e   = k + (static_cast<unsigned>(d >> 32) & 0xffffu);
-      r   = static_cast<unsigned>(d >> 48);
-      acc = rhs;
+    unsigned           q         = (tid & 31u) * kRowWarps + (tid >> 5);  // position in order[]
+    unsigned r = 0, gi = 0, gi_next = 0;
+    double   acc = 0.0, acc_next = 0.0;
+    unsigned k = 0, e = 0, polls = 0;
+    double   a = 0.0;
+    const volatile unsigned long long *pa = xs;  // slot of the dependency this lane waits for
+    bool active = q < rows;
+    if (active) {
+      r   = order[q];
+      acc = load_rhs(r, gi);
+      if (q + T < rows) acc_next = load_rhs(order[q + T], gi_next);
+      k = ptr[r], e = ptr[r + 1];
       if (k < e) pa = xs + idx[k], a = val[k];
-      if (k + 1 < e) idx_n = idx[k + 1], a_n = val[k + 1];
-    };
-    auto publish = [&]() {
-      const unsigned long long bits = tag_set(acc, parity);
-      xs[r]                         = bits;
-      const unsigned s              = bi.s0 + r;
-      st_publish(x + (UPPER ? m - 1u - s : s), bits);
-      if (trace) {
-        if (atomicAdd(&s_done, 1u) + 1u == rows) {  // the row that finishes last
-          trace[8 * s_blk + 2] = globaltimer_ns();
-          trace[8 * s_blk + 4] = polls;
-          trace[8 * s_blk + 5] = r;
-          trace[8 * s_blk + 7] = s_pollend;
-        }
-      }
-    };
-    // publish finished rows (also rows without any dependency) and step to the next row
+    }
+    // publish finished rows (also rows without any dependency) and step to this thread's
+    // next row; a published value is visible to the block through xs and to later blocks
+    // through x (global, polled by their halo warps)
     auto finish_rows = [&]() {
       while (active && k == e) {
-        publish();
+        const unsigned long long bits = tag_set(acc, parity);
+        xs[r]                         = bits;
+        st_publish(x + gi, bits);
+        if (trace) {
+          if (atomicAdd(&s_done, 1u) + 1u == rows) {  // the row that finishes last
+            trace[8 * s_blk + 2] = globaltimer_ns();
+            trace[8 * s_blk + 4] = polls;
+            trace[8 * s_blk + 5] = r;
+            trace[8 * s_blk + 7] = s_pollend;
+          }
+        }
         q += T;
         if (q >= rows) {
           active = false;
-          pa     = dummy;
           break;
         }
-        start_row(d1, acc_n);
-        d1 = d2;
-        if (q + T < rows) acc_n = tag_value(xs[static_cast<unsigned>(d1 >> 48)]);
-        if (q + 2 * T < rows) d2 = rowinfo[q + 2 * T];
+        r   = order[q];
+        acc = acc_next, gi = gi_next;
+        if (q + T < rows) acc_next = load_rhs(order[q + T], gi_next);
+        k = ptr[r], e = ptr[r + 1];
+        if (k < e) pa = xs + idx[k], a = val[k];
       }
     };
-    if (active) {
-      const unsigned long long d0 = rowinfo[q];
-      if (q + T < rows) d1 = rowinfo[q + T];
-      if (q + 2 * T < rows) d2 = rowinfo[q + 2 * T];
-      start_row(d0, tag_value(xs[static_cast<unsigned>(d0 >> 48)]));
-      if (q + T < rows) acc_n = tag_value(xs[static_cast<unsigned>(d1 >> 48)]);
-    }
     finish_rows();
     // Warp-uniform structure: a SHORT spin (one shared load + vote per iteration) while no
     // lane of the warp can advance, then a divergent step for the lanes whose dependency
     // arrived.  No lane ever blocks a sibling: finished values are published inside the
     // step, before the warp spins again.
+    volatile unsigned long long *const dummy = xs + rows + nhalo;  // never becomes ready
+    if (!active) pa = dummy;
     while (__any_sync(0xffffffffu, active)) {
       unsigned long long bits;
       bool               rdy;
       unsigned           rounds = 0;
-      // tight spin (finished lanes poll the dummy slot, so no per-lane predicate is needed)
+      // tight spin: one shared load, one test, one vote per iteration (finished lanes poll
+      // the dummy slot, so the loop needs no per-lane predicate)
       for (;;) {
         bool any = false;
 #pragma unroll 1
-        for (unsigned it = 0; it < spin_burst; ++it) {
+        for (unsigned it = 0; it < kSpinBurst; ++it) {
           bits = *pa;
           rdy  = (static_cast<unsigned>(bits) & 1u) == parity;
           any  = __any_sync(0xffffffffu, rdy);
           if (any) break;
         }
         if (any) break;
-        // nothing arrived during a whole burst: this warp waits for something far away --
-        // sleep between bursts so that it stops competing for issue slots
+        // nothing arrived during a whole burst (~100 us): this warp waits for something
+        // far away -- sleep between bursts so that it stops competing for issue slots
         ++rounds;
-        if (backoff) __nanosleep(static_cast<unsigned>(backoff));
-        if (rounds > kSpinLimit / 64u) {  // hang guard: flag the error, drain with garbage
+        if (backoff) __nanosleep(1000u);
+        if (rounds > kSpinLimit / kSpinBurst) {  // hang guard: flag the error, drain with garbage
           *error_flag = 1;
           rdy         = active;
           break;
@@ -260,12 +244,9 @@ __global__ void __launch_bounds__(T + kPollLanes, (T <= 256 ? 4 : 2))
       if (rdy) {
         acc = fma(-a, tag_value(bits), acc);
         ++k;
-        if (k < e) {
-          pa = xs + idx_n, a = a_n;
-          if (k + 1 < e) idx_n = idx[k + 1], a_n = val[k + 1];
-        } else {
-          finish_rows();
-        }
+        if (k < e) pa = xs + idx[k], a = val[k];
+        finish_rows();
+        if (!active) pa = dummy;
       }
     }
   } else {
@@ -438,15 +419,6 @@ static void pack_sweep(const HostCsr &T, bool upper, PackedSweep &out) {
     std::memcpy(base, ptr.data(), 4u * (rows + 1));
     if (nh) std::memcpy(base + slab_off_halo(rows), halo.data(), 4u * nh);
     std::memcpy(base + slab_off_order(rows, nh), order.data(), 2u * rows);
-    {
-      unsigned long long *ri = reinterpret_cast<unsigned long long *>(base + slab_off_rowinfo(rows, nh));
-      for (unsigned q = 0; q < rows; ++q) {
-        const unsigned r = order[q], cnt = ptr[r + 1] - ptr[r];
-        if (cnt > 0xffffu) throw std::invalid_argument("row with more than 65535 entries");
-        ri[q] = static_cast<unsigned long long>(ptr[r]) | (static_cast<unsigned long long>(cnt) << 32) |
-                (static_cast<unsigned long long>(r) << 48);
-      }
-    }
     if (nnz) {
       std::memcpy(base + slab_off_idx(rows, nh), idx.data(), 2u * nnz);
       std::memcpy(base + slab_off_val(rows, nh, nnz), val.data(), 8u * nnz);
@@ -564,9 +536,6 @@ void sweep_simulate(const HostCsr &T, bool upper, const double *prm, double *out
       done              = std::max(done, fin[r]);
     }
     *it = done;
-    if (std::getenv("HIFIR_B200_SIM_VERBOSE") && (&bi - P.infos.data()) < 16)
-      std::fprintf(stderr, "  sim blk %ld rows %u halo %u start %.1f ready %.1f last_halo %.1f done %.1f\n",
-                   static_cast<long>(&bi - P.infos.data()), bi.rows, bi.nhalo, start, ready, last_halo, done);
     total = std::max(total, done);
     life_sum += done - start;
     life_max = std::max(life_max, done - start);
@@ -634,9 +603,8 @@ void launch_T(Handle *h, const SweepPlan &plan, const double *rhs_plain, const u
   }
   sptrsv_slab_kernel<UPPER, T><<<plan.nblocks, T + kPollLanes, plan.smem_bytes, h->stream>>>(
       plan.m, plan.slabs.p, reinterpret_cast<const SlabInfo *>(plan.info.p), rhs_plain, rhs_tagged, diag, x, parity,
-      ticket, h->error_flag.p, trace, env_int("HIFIR_B200_BACKOFF", 1000),
-      static_cast<unsigned>(env_int("HIFIR_B200_POLL_SLEEP", 100)),
-      static_cast<unsigned>(env_int("HIFIR_B200_SPIN_BURST", 2048)));
+      ticket, h->error_flag.p, trace, env_int("HIFIR_B200_BACKOFF", 1),
+      static_cast<unsigned>(env_int("HIFIR_B200_POLL_SLEEP", 100)));
 }
 template <bool UPPER>
 void launch_U(Handle *h, const SweepPlan &plan, const double *rhs_plain, const unsigned long long *rhs_tagged,
