@@ -98,10 +98,11 @@ constexpr int kTrsvThreads = 512;
 __global__ void __launch_bounds__(kTrsvThreads, 1)
     dense_trsv_kernel(const unsigned nm, const unsigned rk, const double *__restrict__ R,
                       const double *__restrict__ rinv, const double *__restrict__ c,
-                      const int *__restrict__ jpvt, double *__restrict__ out) {
+                      const int *__restrict__ jpvt, double *__restrict__ out, const unsigned stride) {
+  // one CTA per right-hand side column (blockIdx.x) of a row-interleaved block of `stride` columns
   extern __shared__ double xs[];  // rk values
-  const unsigned           tid = threadIdx.x;
-  for (unsigned i = tid; i < rk; i += kTrsvThreads) xs[i] = c[i];
+  const unsigned           tid = threadIdx.x, colr = blockIdx.x;
+  for (unsigned i = tid; i < rk; i += kTrsvThreads) xs[i] = c[static_cast<std::size_t>(i) * stride + colr];
   __syncthreads();
   for (unsigned j1 = rk; j1 > 0;) {
     const unsigned j0 = j1 >= 32u ? j1 - 32u : 0u;  // block [j0, j1)
@@ -137,7 +138,8 @@ __global__ void __launch_bounds__(kTrsvThreads, 1)
     __syncthreads();
     j1 = j0;
   }
-  for (unsigned i = tid; i < nm; i += kTrsvThreads) out[jpvt[i] - 1] = i < rk ? xs[i] : 0.0;
+  for (unsigned i = tid; i < nm; i += kTrsvThreads)
+    out[static_cast<std::size_t>(jpvt[i] - 1) * stride + colr] = i < rk ? xs[i] : 0.0;
 }
 
 // ============================================================================
@@ -270,7 +272,7 @@ void apply_dev(Handle *h, const double *d_b, double *d_x, std::size_t rank) {
       ++h->launch_count;
     }
     dense_trsv_kernel<<<1, kTrsvThreads, (rk ? rk : 1) * sizeof(double), h->stream>>>(nm, rk, Q.R.p, Q.rinv.p, Q.c.p, Q.jpvt.p,
-                                                                                      last.ychild.p);
+                                                                                      last.ychild.p, 1u);
     HIF_KERNEL_CHECK();
     mark(h, "dense");
     ++h->launch_count;
@@ -313,6 +315,14 @@ void apply_dev(Handle *h, const double *d_b, double *d_x, std::size_t rank) {
     }
   }
   h->kernels_per_apply = h->launch_count - launches0;
+}
+
+void launch_dense_trsv_cols(Handle *h, unsigned nm, unsigned rk, const double *c, double *out, unsigned ncols) {
+  DevDense &Q = h->dense;
+  dense_trsv_kernel<<<ncols, kTrsvThreads, (rk ? rk : 1) * sizeof(double), h->stream>>>(nm, rk, Q.R.p, Q.rinv.p, c,
+                                                                                       Q.jpvt.p, out, ncols);
+  HIF_KERNEL_CHECK();
+  ++h->launch_count;
 }
 
 void check_sweep_error(Handle *h) {

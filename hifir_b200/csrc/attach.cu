@@ -174,6 +174,8 @@ Handle *attach_levels(int device, std::size_t nlevels, const LhfdGpuLevel *lv) {
     build_sweep_plan(Ur, true, D.U, tally);
     D.L.nnz = Lr.col.size();
     D.U.nnz = Ur.col.size();
+    D.hostL = std::move(Lr);
+    D.hostU = std::move(Ur);
     upload_csr(Er, D.E, tally);
     upload_csr(Fr, D.F, tally);
     D.d.upload(P.d_B, P.m, tally);

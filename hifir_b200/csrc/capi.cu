@@ -66,45 +66,6 @@ void d2h(Handle *h, double *dst, const double *src, std::size_t count) {
 
 }  // namespace
 
-// ---- multi-rhs, v1: row-interleaved block <-> contiguous columns ------------------
-namespace hifgpu {
-
-__global__ void col_extract_kernel(const unsigned n, const unsigned nrhs, const unsigned k,
-                                   const double *__restrict__ B, double *__restrict__ out) {
-  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) out[i] = B[static_cast<std::size_t>(i) * nrhs + k];
-}
-__global__ void col_insert_kernel(const unsigned n, const unsigned nrhs, const unsigned k,
-                                  const double *__restrict__ in, double *__restrict__ X) {
-  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) X[static_cast<std::size_t>(i) * nrhs + k] = in[i];
-}
-
-void apply_mrhs_dev(Handle *h, std::size_t nrhs, const double *d_B, double *d_X, std::size_t rank) {
-  const std::size_t n = h->n0();
-  if (nrhs == 1) {
-    apply_dev(h, d_B, d_X, rank);
-    return;
-  }
-  if (h->mr_b.n < n) {
-    h->mr_b.alloc(n, &h->device_bytes);
-    h->mr_x.alloc(n, &h->device_bytes);
-  }
-  const unsigned T = 256, nb = static_cast<unsigned>((n + T - 1) / T);
-  for (std::size_t k = 0; k < nrhs; ++k) {
-    col_extract_kernel<<<nb, T, 0, h->stream>>>(static_cast<unsigned>(n), static_cast<unsigned>(nrhs),
-                                                static_cast<unsigned>(k), d_B, h->mr_b.p);
-    HIF_KERNEL_CHECK();
-    apply_dev(h, h->mr_b.p, h->mr_x.p, rank);
-    col_insert_kernel<<<nb, T, 0, h->stream>>>(static_cast<unsigned>(n), static_cast<unsigned>(nrhs),
-                                               static_cast<unsigned>(k), h->mr_x.p, d_X);
-    HIF_KERNEL_CHECK();
-    h->launch_count += 2;
-  }
-}
-
-}  // namespace hifgpu
-
 extern "C" {
 
 const char *lhfGpuGetErrorMsg(void) { return g_msg.c_str(); }

@@ -67,7 +67,7 @@ struct HostCsr {
 
 // a strictly triangular factor cut into shared-memory sized slabs (sptrsv.cu)
 struct SweepPlan {
-  unsigned               m = 0, nblocks = 0, smem_bytes = 0;
+  unsigned               m = 0, nblocks = 0, smem_bytes = 0, nr = 1;  // nr: right-hand sides per slot
   bool                   upper = false;
   std::size_t            slab_bytes = 0, halo_total = 0, nnz = 0;
   DevBuf<unsigned char>  slabs;  // packed slabs
@@ -91,6 +91,11 @@ struct DevLevel {
   DevBuf<double>             g;                         // m   bhat - F*y_child
   DevBuf<double>             r;                         // nm  Schur rhs = child's b
   DevBuf<double>             ychild;                    // nm  child's solution
+  // multi-rhs (kMrhsWidth columns, row-interleaved): plans + work vectors, built on first use
+  HostCsr                    hostL, hostU;  // kept for the lazily built multi-rhs plans
+  SweepPlan                  Lm, Um;
+  DevBuf<double>             m_bhat, m_g, m_r, m_ychild;
+  DevBuf<unsigned long long> m_xL_dn, m_xU_dn, m_xL_up, m_xU_up;
 };
 
 // dense last level: QRCP state (reference small_scale/QRCP.hpp:544-555)
@@ -129,7 +134,8 @@ struct Handle {
   double *       h_scal = nullptr;  // pinned
   int            kr_restart = 0;
   // multi-rhs column staging
-  DevBuf<double> mr_b, mr_x;
+  DevBuf<double> mr_b, mr_x, mr_c;
+  bool           mrhs_ready = false;
   // statistics
   std::size_t bytes_factors = 0, bytes_vec = 0, bytes_dense = 0, device_bytes = 0, nnz_total = 0;
   std::size_t kernels_per_apply = 0, launch_count = 0;
@@ -148,7 +154,8 @@ void    set_matrix(Handle *h, bool rowmajor, std::size_t n, const LhfIndPtr *ind
 HostCsr ccs_to_csr(const LhfdGpuCcs &c, const char *name);
 
 // ---- sptrsv.cu : block sync-free triangular sweeps
-void build_sweep_plan(const HostCsr &T, bool upper, SweepPlan &plan, std::size_t *tally);
+void build_sweep_plan(const HostCsr &T, bool upper, SweepPlan &plan, std::size_t *tally, unsigned nr = 1);
+constexpr unsigned kMrhsWidth = 8;  // columns processed together by the multi-rhs kernels
 void sweep_host_emulate(const HostCsr &T, bool upper, const double *rhs, const double *diag, double *x,
                         std::size_t stats[4]);
 void sweep_block_graph(const HostCsr &T, bool upper, std::vector<unsigned> &info, std::vector<unsigned> &src_ptr,

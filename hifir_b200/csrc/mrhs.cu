@@ -1,0 +1,217 @@
+// mrhs.cu -- batched multi-rhs apply: X = M^{-1} B for row-interleaved blocks B[i*nrhs + k]
+// (the Array<std::array<T,Nrhs>> layout of hif::HIF::solve_mrhs, reference builder.hpp:433-445).
+//
+// Semantics = nrhs independent hif::HIF::solve calls (the reference's own multilevel mrhs
+// driver prec_solve_mrhs is defective, prec_solve.hpp:489-497 / SURVEY.md App. B-1; its leaf
+// kernels -- CompressedStorage.hpp:2117-2137, 2286-2301, 2376-2393, QRCP.hpp:229-242 -- fix the
+// per-column arithmetic that is reproduced here).
+//
+// Columns are processed kMrhsWidth (= 8) at a time: every work vector holds 8 values per
+// row (64 B: one coalesced, vectorised transaction per dependency) and every factor is
+// streamed ONCE for the 8 columns.  The schedule is the single-rhs one (apply.cu).
+#include "hifgpu.h"
+
+namespace hifgpu {
+
+constexpr unsigned NR = kMrhsWidth;
+
+namespace {
+
+inline unsigned cdiv(std::size_t a, std::size_t b) { return static_cast<unsigned>((a + b - 1) / b); }
+
+// chunk of user columns [k0, k0+NR) <-> internal [n][NR] block (zero padded)
+__global__ void chunk_extract_kernel(const unsigned n, const unsigned nrhs, const unsigned k0,
+                                     const double *__restrict__ B, double *__restrict__ out) {
+  const std::size_t g = static_cast<std::size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (g >= static_cast<std::size_t>(n) * NR) return;
+  const std::size_t i = g / NR;
+  const unsigned    c = static_cast<unsigned>(g % NR);
+  out[g]              = k0 + c < nrhs ? B[i * nrhs + k0 + c] : 0.0;
+}
+__global__ void chunk_insert_kernel(const unsigned n, const unsigned nrhs, const unsigned k0,
+                                    const double *__restrict__ in, double *__restrict__ X) {
+  const std::size_t g = static_cast<std::size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (g >= static_cast<std::size_t>(n) * NR) return;
+  const std::size_t i = g / NR;
+  const unsigned    c = static_cast<unsigned>(g % NR);
+  if (k0 + c < nrhs) X[i * nrhs + k0 + c] = in[g];
+}
+
+// bhat[i][c] = s[p[i]] * b[p[i]][c]     (prec_solve.hpp:359, 368, 399)
+__global__ void gather_scale_m_kernel(const unsigned n, const int *__restrict__ p, const double *__restrict__ s,
+                                      const double *__restrict__ b, double *__restrict__ bhat) {
+  const std::size_t g = static_cast<std::size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (g >= static_cast<std::size_t>(n) * NR) return;
+  const std::size_t i = g / NR, c = g % NR;
+  const int         pi = p[i];
+  bhat[g]              = s[pi] * b[static_cast<std::size_t>(pi) * NR + c];
+}
+
+// out[i][c] = base[i][c] - sum_j A(i,j) x[j][c]; NR consecutive threads = the NR columns of one row
+template <bool TAGGED>
+__global__ void spmv_resid_m_kernel(const unsigned nrows, const unsigned *__restrict__ ptr,
+                                    const int *__restrict__ col, const double *__restrict__ val,
+                                    const void *__restrict__ xin, const double *__restrict__ base,
+                                    double *__restrict__ out) {
+  const std::size_t g = static_cast<std::size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (g >= static_cast<std::size_t>(nrows) * NR) return;
+  const std::size_t row = g / NR, c = g % NR;
+  double            acc = 0.0;
+  const unsigned    e   = ptr[row + 1];
+  for (unsigned k = ptr[row]; k < e; ++k) {
+    const std::size_t j = static_cast<std::size_t>(col[k]) * NR + c;
+    const double      xj =
+        TAGGED ? tag_value(static_cast<const unsigned long long *>(xin)[j]) : static_cast<const double *>(xin)[j];
+    acc = fma(val[k], xj, acc);
+  }
+  out[g] = base[g] - acc;
+}
+
+// y[i][c] = t[i] * [xU; ychild][q_inv[i]][c]   (prec_solve.hpp:392, 411)
+__global__ void scatter_scale_m_kernel(const unsigned n, const unsigned m, const int *__restrict__ q_inv,
+                                       const double *__restrict__ t, const unsigned long long *__restrict__ xU,
+                                       const double *__restrict__ ychild, double *__restrict__ y) {
+  const std::size_t g = static_cast<std::size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (g >= static_cast<std::size_t>(n) * NR) return;
+  const std::size_t i = g / NR, c = g % NR;
+  const unsigned    j = static_cast<unsigned>(q_inv[i]);
+  const double      w = j < m ? tag_value(xU[static_cast<std::size_t>(j) * NR + c])
+                              : ychild[static_cast<std::size_t>(j - m) * NR + c];
+  y[g]                = t[i] * w;
+}
+
+// dense level: cq[k][c] = Q(:,k)^T x[:, c] : one warp per column k of Q, NR accumulators
+__global__ void dense_qt_m_kernel(const unsigned nm, const unsigned rk, const double *__restrict__ Q,
+                                  const double *__restrict__ x, double *__restrict__ cq) {
+  const unsigned warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31u;
+  if (warp >= rk) return;
+  const double *q = Q + static_cast<std::size_t>(warp) * nm;
+  double        acc[NR];
+#pragma unroll
+  for (unsigned c = 0; c < NR; ++c) acc[c] = 0.0;
+  for (unsigned i = lane; i < nm; i += 32) {
+    const double qi = q[i];
+#pragma unroll
+    for (unsigned c = 0; c < NR; ++c) acc[c] = fma(qi, x[static_cast<std::size_t>(i) * NR + c], acc[c]);
+  }
+#pragma unroll
+  for (unsigned c = 0; c < NR; ++c) {
+    const double v = warp_sum(acc[c]);
+    if (lane == 0) cq[static_cast<std::size_t>(warp) * NR + c] = v;
+  }
+}
+
+void ensure_mrhs(Handle *h) {
+  if (h->mrhs_ready) return;
+  std::size_t *tally = &h->device_bytes;
+  for (DevLevel &D : h->levels) {
+    build_sweep_plan(D.hostL, false, D.Lm, tally, NR);
+    build_sweep_plan(D.hostU, true, D.Um, tally, NR);
+    D.m_bhat.alloc(D.n * NR, tally);
+    D.m_g.alloc(D.m * NR, tally);
+    D.m_r.alloc(D.nm * NR, tally);
+    D.m_ychild.alloc(D.nm * NR, tally);
+    D.m_xL_dn.alloc(D.m * NR, tally);
+    D.m_xU_dn.alloc(D.m * NR, tally);
+    D.m_xL_up.alloc(D.m * NR, tally);
+    D.m_xU_up.alloc(D.m * NR, tally);
+  }
+  const std::size_t n = h->n0();
+  h->mr_b.alloc(n * NR, tally);
+  h->mr_x.alloc(n * NR, tally);
+  h->mr_c.alloc(h->dense.nm * NR + 1, tally);
+  h->mrhs_ready = true;
+}
+
+}  // namespace
+
+// dense_trsv_kernel of apply.cu, one CTA per column of the chunk
+void launch_dense_trsv_cols(Handle *h, unsigned nm, unsigned rk, const double *c, double *out, unsigned ncols);
+
+// one chunk of NR columns: in/out are [n][NR] device blocks
+static void apply_chunk(Handle *h, const double *d_in, double *d_out, std::size_t rank) {
+  const std::size_t nl = h->levels.size();
+  ++h->epoch;
+  const unsigned parity = h->epoch & 1u;
+  HIF_CUDA(cudaMemsetAsync(h->tickets.p, 0, h->tickets.n * sizeof(int), h->stream));
+  constexpr int T = 256;
+  const double *b = d_in;
+  for (std::size_t l = 0; l < nl; ++l) {
+    DevLevel &D = h->levels[l];
+    if (D.n) {
+      gather_scale_m_kernel<<<cdiv(D.n * NR, T), T, 0, h->stream>>>(static_cast<unsigned>(D.n), D.p.p, D.s.p, b,
+                                                                     D.m_bhat.p);
+      HIF_KERNEL_CHECK();
+      ++h->launch_count;
+    }
+    if (D.nm) {
+      if (D.m) {
+        launch_sweep(h, D.Lm, D.m_bhat.p, nullptr, nullptr, D.m_xL_dn.p, parity, h->tickets.p + 4 * l);
+        launch_sweep(h, D.Um, nullptr, D.m_xL_dn.p, D.d.p, D.m_xU_dn.p, parity, h->tickets.p + 4 * l + 1);
+      }
+      spmv_resid_m_kernel<true><<<cdiv(D.nm * NR, T), T, 0, h->stream>>>(
+          static_cast<unsigned>(D.nm), D.E.ptr.p, D.E.col.p, D.E.val.p, D.m_xU_dn.p, D.m_bhat.p + D.m * NR, D.m_r.p);
+      HIF_KERNEL_CHECK();
+      ++h->launch_count;
+      b = D.m_r.p;
+    }
+  }
+  DevLevel &last = h->levels[nl - 1];
+  if (last.nm) {
+    DevDense &     Q  = h->dense;
+    const unsigned nm = static_cast<unsigned>(Q.nm);
+    const unsigned rk = static_cast<unsigned>(rank == 0 ? Q.rank : (rank > Q.nm ? Q.nm : rank));
+    if (rk) {
+      dense_qt_m_kernel<<<cdiv(static_cast<std::size_t>(rk) * 32, T), T, 0, h->stream>>>(nm, rk, Q.Q.p, last.m_r.p,
+                                                                                        h->mr_c.p);
+      HIF_KERNEL_CHECK();
+      ++h->launch_count;
+    }
+    launch_dense_trsv_cols(h, nm, rk, h->mr_c.p, last.m_ychild.p, NR);
+  }
+  for (std::size_t l = nl; l-- > 0;) {
+    DevLevel &    D   = h->levels[l];
+    double *      y   = l == 0 ? d_out : h->levels[l - 1].m_ychild.p;
+    const double *rhs = D.m_bhat.p;
+    if (D.nm && D.F.nnz && D.m) {
+      spmv_resid_m_kernel<false><<<cdiv(D.m * NR, T), T, 0, h->stream>>>(
+          static_cast<unsigned>(D.m), D.F.ptr.p, D.F.col.p, D.F.val.p, D.m_ychild.p, D.m_bhat.p, D.m_g.p);
+      HIF_KERNEL_CHECK();
+      ++h->launch_count;
+      rhs = D.m_g.p;
+    }
+    if (D.m) {
+      launch_sweep(h, D.Lm, rhs, nullptr, nullptr, D.m_xL_up.p, parity, h->tickets.p + 4 * l + 2);
+      launch_sweep(h, D.Um, nullptr, D.m_xL_up.p, D.d.p, D.m_xU_up.p, parity, h->tickets.p + 4 * l + 3);
+    }
+    if (D.n) {
+      scatter_scale_m_kernel<<<cdiv(D.n * NR, T), T, 0, h->stream>>>(
+          static_cast<unsigned>(D.n), static_cast<unsigned>(D.m), D.q_inv.p, D.t.p, D.m_xU_up.p, D.m_ychild.p, y);
+      HIF_KERNEL_CHECK();
+      ++h->launch_count;
+    }
+  }
+}
+
+void apply_mrhs_dev(Handle *h, std::size_t nrhs, const double *d_B, double *d_X, std::size_t rank) {
+  HIF_CUDA(cudaSetDevice(h->device));
+  if (nrhs == 1) {
+    apply_dev(h, d_B, d_X, rank);
+    return;
+  }
+  ensure_mrhs(h);
+  const std::size_t n = h->n0();
+  constexpr int     T = 256;
+  for (std::size_t k0 = 0; k0 < nrhs; k0 += NR) {
+    chunk_extract_kernel<<<cdiv(n * NR, T), T, 0, h->stream>>>(static_cast<unsigned>(n), static_cast<unsigned>(nrhs),
+                                                              static_cast<unsigned>(k0), d_B, h->mr_b.p);
+    HIF_KERNEL_CHECK();
+    apply_chunk(h, h->mr_b.p, h->mr_x.p, rank);
+    chunk_insert_kernel<<<cdiv(n * NR, T), T, 0, h->stream>>>(static_cast<unsigned>(n), static_cast<unsigned>(nrhs),
+                                                             static_cast<unsigned>(k0), h->mr_x.p, d_X);
+    HIF_KERNEL_CHECK();
+    h->launch_count += 2;
+  }
+}
+
+}  // namespace hifgpu

@@ -36,6 +36,7 @@ namespace hifgpu {
 constexpr unsigned kPollWarps = 4;
 constexpr unsigned kPollLanes = 32 * kPollWarps;
 constexpr unsigned kRowsMax   = 1024;  // rows per block (the shared-memory budget usually binds first)
+constexpr unsigned kSmemBudgetMrhs = 224 * 1024;  // multi-rhs sweeps: one CTA per SM
 constexpr unsigned kSmemBudgetMax = 112 * 1024;  // per CTA -> two CTAs per SM (227 KB)
 static unsigned smem_budget() {
   const char *e = std::getenv("HIFIR_B200_SMEM_KB");
@@ -301,6 +302,174 @@ __global__ void __launch_bounds__(T + kPollLanes, (T <= 256 ? 4 : 2))
 }
 
 // ============================================================================
+// multi-rhs sweep: NR right-hand sides per row, row-interleaved (X[i*NR + c], the
+// Array<std::array<T,Nrhs>> layout of hif::HIF::solve_mrhs, builder.hpp:433-445;
+// per-column arithmetic = CCS::solve_as_strict_lower/upper_mrhs,
+// CompressedStorage.hpp:2286-2301, 2376-2393).  Same design as the single-rhs kernel:
+// a solution slot holds NR tagged values (64 B for NR = 8: one coalesced, vectorised
+// transaction per dependency), the factor slab is read ONCE for all NR columns.
+// ============================================================================
+__device__ __forceinline__ void lds_v2(const unsigned long long *p, unsigned long long &a, unsigned long long &b) {
+  asm volatile("ld.volatile.shared.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "r"(smem_addr(p)) : "memory");
+}
+__device__ __forceinline__ void ldg_poll_v2(const unsigned long long *p, unsigned long long &a,
+                                            unsigned long long &b) {
+  asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
+}
+
+template <bool UPPER, unsigned T, unsigned NR>
+__global__ void __launch_bounds__(T + kPollLanes, 1)
+    sptrsv_slab_mrhs_kernel(const unsigned m, const unsigned char *__restrict__ slabs,
+                            const SlabInfo *__restrict__ info, const double *__restrict__ rhs_plain,
+                            const unsigned long long *rhs_tagged, const double *__restrict__ diag,
+                            unsigned long long *x, const unsigned parity, int *ticket, int *error_flag) {
+  static_assert(NR % 2 == 0, "NR must be even (128-bit shared/global transactions)");
+  constexpr unsigned kThreads = T + kPollLanes;
+  extern __shared__ __align__(16) unsigned char smem[];
+  __shared__ unsigned                        s_blk;
+  __shared__ __align__(8) unsigned long long s_bar;
+  const unsigned                             tid = threadIdx.x;
+  if (tid == 0) {
+    s_blk = static_cast<unsigned>(atomicAdd(ticket, 1));
+    mbar_init(&s_bar, 1);
+  }
+  __syncthreads();
+  const SlabInfo bi = info[s_blk];
+  if (tid == 0) {
+    mbar_expect_tx(&s_bar, bi.bytes);
+    tma_bulk_g2s(smem, slabs + bi.off, bi.bytes, &s_bar);
+  }
+  const unsigned      rows = bi.rows, nhalo = bi.nhalo, nnz = bi.nnz;
+  unsigned long long *xs       = reinterpret_cast<unsigned long long *>(smem + bi.bytes);  // [slot][NR]
+  const unsigned long long not_ready = parity ^ 1u;
+  for (unsigned i = tid; i < (rows + nhalo + 1u) * NR; i += kThreads) xs[i] = not_ready;
+  __syncthreads();
+  while (!mbar_try_wait(&s_bar, 0)) {
+  }
+  const unsigned *      ptr   = reinterpret_cast<const unsigned *>(smem);
+  const unsigned *      halo  = reinterpret_cast<const unsigned *>(smem + slab_off_halo(rows));
+  const unsigned short *order = reinterpret_cast<const unsigned short *>(smem + slab_off_order(rows, nhalo));
+  const unsigned short *idx   = reinterpret_cast<const unsigned short *>(smem + slab_off_idx(rows, nhalo));
+  const double *        val   = reinterpret_cast<const double *>(smem + slab_off_val(rows, nhalo, nnz));
+
+  if (tid < T) {
+    constexpr unsigned kRowWarps = T / 32;
+    unsigned           q         = (tid & 31u) * kRowWarps + (tid >> 5);
+    unsigned           r = 0, k = 0, e = 0;
+    std::size_t        gi = 0;
+    double             acc[NR], a = 0.0;
+    const unsigned long long *const dummy = xs + static_cast<std::size_t>(rows + nhalo) * NR;
+    const unsigned long long *      pa    = dummy;
+    bool                            active = q < rows;
+    auto start_row = [&]() {
+      r                = order[q];
+      const unsigned s = bi.s0 + r;
+      gi               = static_cast<std::size_t>(UPPER ? m - 1u - s : s);
+      if (UPPER) {
+        const double d = diag[gi];
+#pragma unroll
+        for (unsigned c = 0; c < NR; ++c) acc[c] = tag_value(rhs_tagged[gi * NR + c]) / d;  // prec_solve.hpp:256-259
+      } else {
+#pragma unroll
+        for (unsigned c = 0; c < NR; ++c) acc[c] = rhs_plain[gi * NR + c];
+      }
+      k = ptr[r], e = ptr[r + 1];
+      if (k < e) pa = xs + static_cast<std::size_t>(idx[k]) * NR, a = val[k];
+    };
+    auto finish_rows = [&]() {
+      while (active && k == e) {
+#pragma unroll
+        for (unsigned c = 0; c < NR; ++c) {
+          const unsigned long long bits = tag_set(acc[c], parity);
+          xs[static_cast<std::size_t>(r) * NR + c] = bits;
+          st_publish(x + gi * NR + c, bits);
+        }
+        q += T;
+        if (q >= rows) {
+          active = false;
+          pa     = dummy;
+          break;
+        }
+        start_row();
+      }
+    };
+    if (active) start_row();
+    finish_rows();
+    while (__any_sync(0xffffffffu, active)) {
+      unsigned long long v[NR];
+      bool               rdy    = false;
+      unsigned           rounds = 0;
+      for (;;) {
+        bool any = false;
+#pragma unroll 1
+        for (unsigned it = 0; it < 1024u; ++it) {
+          unsigned ok = 1u;
+#pragma unroll
+          for (unsigned c = 0; c < NR; c += 2) {
+            lds_v2(pa + c, v[c], v[c + 1]);
+            ok &= static_cast<unsigned>((static_cast<unsigned>(v[c]) & 1u) == parity) &
+                  static_cast<unsigned>((static_cast<unsigned>(v[c + 1]) & 1u) == parity);
+          }
+          rdy = ok != 0u;
+          any = __any_sync(0xffffffffu, rdy);
+          if (any) break;
+        }
+        if (any) break;
+        __nanosleep(500u);
+        if (++rounds > kSpinLimit / 64u) {
+          *error_flag = 1;
+          rdy         = active;
+          break;
+        }
+      }
+      if (rdy) {
+#pragma unroll
+        for (unsigned c = 0; c < NR; ++c) acc[c] = fma(-a, tag_value(v[c]), acc[c]);
+        ++k;
+        if (k < e) pa = xs + static_cast<std::size_t>(idx[k]) * NR, a = val[k];
+        finish_rows();
+      }
+    }
+  } else {
+    // pollers: a halo entry is NR consecutive tagged values in global memory
+    const unsigned     lane = tid - T;
+    const unsigned     ne   = nhalo > lane ? (nhalo - lane + kPollLanes - 1) / kPollLanes : 0;
+    unsigned long long pend = ne >= 64 ? ~0ull : ((1ull << ne) - 1ull);
+    unsigned           passes = 0;
+    while (pend) {
+      unsigned long long scan = pend;
+      while (scan) {
+        const unsigned ev = static_cast<unsigned>(__ffsll(static_cast<long long>(scan))) - 1u;
+        scan &= scan - 1ull;
+        const unsigned            h   = lane + kPollLanes * ev;
+        const unsigned long long *src = x + static_cast<std::size_t>(halo[h]) * NR;
+        unsigned long long        v[NR];
+        unsigned                  ok = 1u;
+#pragma unroll
+        for (unsigned c = 0; c < NR; c += 2) ldg_poll_v2(src + c, v[c], v[c + 1]);
+#pragma unroll
+        for (unsigned c = 0; c < NR; ++c) ok &= static_cast<unsigned>((static_cast<unsigned>(v[c]) & 1u) == parity);
+        if (ok) {
+#pragma unroll
+          for (unsigned c = 0; c < NR; ++c) xs[static_cast<std::size_t>(rows + h) * NR + c] = v[c];
+          pend &= ~(1ull << ev);
+        }
+      }
+      if (pend) __nanosleep(100u);
+      if (pend && ++passes > (kSpinLimit >> 4)) {
+        *error_flag = 1;
+        while (pend) {
+          const unsigned qq = static_cast<unsigned>(__ffsll(static_cast<long long>(pend))) - 1u;
+          pend &= pend - 1ull;
+#pragma unroll
+          for (unsigned c = 0; c < NR; ++c) xs[static_cast<std::size_t>(rows + lane + kPollLanes * qq) * NR + c] = parity;
+        }
+      }
+    }
+  }
+}
+
+// ============================================================================
 // host: pack a strictly triangular CSR factor into slabs
 // ============================================================================
 namespace {
@@ -313,7 +482,8 @@ struct PackedSweep {
 };
 }  // namespace
 
-static void pack_sweep(const HostCsr &T, bool upper, PackedSweep &out) {
+static void pack_sweep(const HostCsr &T, bool upper, PackedSweep &out, unsigned slot_bytes = 8u,
+                       unsigned budget_override = 0u) {
   const unsigned m = static_cast<unsigned>(T.nrows);
   if (!m) return;
   std::vector<SlabInfo> &     infos = out.infos;
@@ -337,7 +507,7 @@ static void pack_sweep(const HostCsr &T, bool upper, PackedSweep &out) {
   unsigned                    max_smem = 0;
   auto nat = [&](unsigned s) { return upper ? m - 1u - s : s; };
 
-  const unsigned budget = smem_budget();
+  const unsigned budget = budget_override ? budget_override : smem_budget();
   unsigned s0 = 0, bid = 0;
   while (s0 < m) {
     ++bid;
@@ -356,7 +526,7 @@ static void pack_sweep(const HostCsr &T, bool upper, PackedSweep &out) {
         }
       }
       const unsigned rn   = T.ptr[i + 1] - T.ptr[i];
-      const unsigned need = slab_bytes(rows + 1, nh + add_h, nnz + rn) + 8u * (rows + 2 + nh + add_h);
+      const unsigned need = slab_bytes(rows + 1, nh + add_h, nnz + rn) + slot_bytes * (rows + 2 + nh + add_h);
       if (need > budget || nh + add_h > 64u * kPollLanes) {
         if (!rows)
           throw std::invalid_argument("triangular factor has a row too long for one shared-memory slab (" +
@@ -424,7 +594,7 @@ static void pack_sweep(const HostCsr &T, bool upper, PackedSweep &out) {
       std::memcpy(base + slab_off_val(rows, nh, nnz), val.data(), 8u * nnz);
     }
     infos.push_back(bi);
-    max_smem = std::max(max_smem, bi.bytes + 8u * (rows + nh + 1u));
+    max_smem = std::max(max_smem, bi.bytes + slot_bytes * (rows + nh + 1u));
     out.halo_total += nh;
     s0 += rows;
   }
@@ -572,13 +742,18 @@ void sweep_block_graph(const HostCsr &T, bool upper, std::vector<unsigned> &info
   }
 }
 
-void build_sweep_plan(const HostCsr &T, bool upper, SweepPlan &plan, std::size_t *tally) {
+void build_sweep_plan(const HostCsr &T, bool upper, SweepPlan &plan, std::size_t *tally, unsigned nr) {
   plan.m       = static_cast<unsigned>(T.nrows);
   plan.upper   = upper;
   plan.nblocks = 0;
+  plan.nr      = nr;
   if (!plan.m) return;
   PackedSweep P;
-  pack_sweep(T, upper, P);
+  // multi-rhs plans: one CTA per SM with the whole 227 KB, a solution slot holds nr values
+  if (nr > 1)
+    pack_sweep(T, upper, P, 8u * nr, kSmemBudgetMrhs);
+  else
+    pack_sweep(T, upper, P);
   plan.nblocks    = static_cast<unsigned>(P.infos.size());
   plan.smem_bytes = P.max_smem;
   plan.slab_bytes = P.buf.size();
@@ -622,9 +797,36 @@ void launch_U(Handle *h, const SweepPlan &plan, const double *rhs_plain, const u
 }
 }  // namespace
 
+namespace {
+template <bool UPPER>
+void launch_mrhs(Handle *h, const SweepPlan &plan, const double *rhs_plain, const unsigned long long *rhs_tagged,
+                 const double *diag, unsigned long long *x, unsigned parity, int *ticket) {
+  constexpr unsigned T = 448;
+  static bool        configured = false;
+  if (!configured) {
+    HIF_CUDA(cudaFuncSetAttribute(sptrsv_slab_mrhs_kernel<UPPER, T, kMrhsWidth>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemBudgetMrhs)));
+    configured = true;
+  }
+  sptrsv_slab_mrhs_kernel<UPPER, T, kMrhsWidth><<<plan.nblocks, T + kPollLanes, plan.smem_bytes, h->stream>>>(
+      plan.m, plan.slabs.p, reinterpret_cast<const SlabInfo *>(plan.info.p), rhs_plain, rhs_tagged, diag, x, parity,
+      ticket, h->error_flag.p);
+}
+}  // namespace
+
 void launch_sweep(Handle *h, const SweepPlan &plan, const double *rhs_plain, const unsigned long long *rhs_tagged,
                   const double *diag, unsigned long long *x, unsigned parity, int *ticket, unsigned long long *trace) {
   if (!plan.nblocks) return;
+  if (plan.nr > 1) {
+    if (plan.nr != kMrhsWidth) throw std::logic_error("unsupported multi-rhs plan width");
+    if (plan.upper)
+      launch_mrhs<true>(h, plan, rhs_plain, rhs_tagged, diag, x, parity, ticket);
+    else
+      launch_mrhs<false>(h, plan, rhs_plain, rhs_tagged, diag, x, parity, ticket);
+    HIF_KERNEL_CHECK();
+    ++h->launch_count;
+    return;
+  }
   if (plan.upper)
     launch_U<true>(h, plan, rhs_plain, rhs_tagged, diag, x, parity, ticket, trace);
   else
