@@ -123,6 +123,7 @@ struct Handle {
   std::size_t           nsp_start = 0, nsp_end = 0;
   cudaStream_t          own_stream = nullptr, stream = nullptr;
   unsigned              epoch = 0;        // apply counter; parity tags the sync-free buffers
+  unsigned              epoch_m = 0;      // same for the multi-rhs work vectors
   DevBuf<int>           tickets;          // one block-ticket counter per sweep of an apply
   DevBuf<int>           error_flag;       // set by a sweep whose spin limit tripped
   int *                 h_error = nullptr;  // pinned mirror

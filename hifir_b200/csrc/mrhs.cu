@@ -131,8 +131,10 @@ void launch_dense_trsv_cols(Handle *h, unsigned nm, unsigned rk, const double *c
 // one chunk of NR columns: in/out are [n][NR] device blocks
 static void apply_chunk(Handle *h, const double *d_in, double *d_out, std::size_t rank) {
   const std::size_t nl = h->levels.size();
-  ++h->epoch;
-  const unsigned parity = h->epoch & 1u;
+  // the multi-rhs work vectors have their own epoch: a tagged buffer must be rewritten on
+  // EVERY increment of the epoch whose parity it is checked against
+  ++h->epoch_m;
+  const unsigned parity = h->epoch_m & 1u;
   HIF_CUDA(cudaMemsetAsync(h->tickets.p, 0, h->tickets.n * sizeof(int), h->stream));
   constexpr int T = 256;
   const double *b = d_in;
