@@ -188,6 +188,108 @@ def sweep_bytes(levels):
     return out
 
 
+def run_mrhs(args, rank, world, local_rank):
+    """Config 4 style run: one row-interleaved block B[n, nrhs], columns sharded over the ranks
+    (every rank holds a factor replica), X gathered with one NCCL all_gather after the timed region."""
+    import torch
+    import torch.distributed as dist
+
+    import hifir_b200 as hb
+    from hifir_b200 import build, problems as P
+    from hifir_b200.sharding import gather_columns, local_columns, shard_range
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback exists)"
+    torch.cuda.set_device(local_rank)
+    build.build()
+    A = make_problem(args.workload, args.size)
+    n, nrhs = A[0], args.nrhs
+    M = factorize(A, threads=max(1, (os.cpu_count() or 1) // world))
+    levels = M.levels()
+    G = hb.GpuHif(levels, device=local_rank)
+    st = G.stats()
+    stream = torch.cuda.current_stream()
+    G.set_stream(stream.cuda_stream)
+    B = P.seeded_rhs(n, 0, nrhs=nrhs)
+    Bl = local_columns(B, world, rank)
+    nloc = Bl.shape[1]
+    Bh = torch.from_numpy(Bl).pin_memory()
+    Bd = Bh.cuda()
+    Xd = torch.empty_like(Bd)
+    Xh = torch.empty_like(Bh).pin_memory()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    if nloc:
+        G.solve_mrhs_dev(nloc, Bd.data_ptr(), Xd.data_ptr(), 0)
+        G.synchronize()
+        b0, _ = shard_range(nrhs, world, rank)
+        xr = M.solve(np.ascontiguousarray(B[:, b0]))
+        parity = float(np.linalg.norm(Xd[:, 0].cpu().numpy() - xr) / np.linalg.norm(xr))
+        assert parity <= 1e-12, f"parity gate failed: {parity}"
+    else:
+        parity = 0.0
+    for _ in range(args.warmup):
+        if nloc:
+            G.solve_mrhs_dev(nloc, Bd.data_ptr(), Xd.data_ptr(), 0)
+    launches0 = G.stats()["launch_count"]
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        if nloc:
+            G.solve_mrhs_dev(nloc, Bd.data_ptr(), Xd.data_ptr(), 0)
+    e1.record(stream)
+    barrier()
+    clocks = sampler.stop()
+    G.synchronize()
+    ms_total = e0.elapsed_time(e1)
+    launches = G.stats()["launch_count"] - launches0
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        if nloc:
+            hb._chk(hb.lib().lhfdGpuSolveMrhs(G._h, nloc, Bh.data_ptr(), Xh.data_ptr()))
+    torch.cuda.synchronize()
+    e2e_ms = (time.perf_counter() - t0) * 1e3
+    barrier()
+    t = torch.tensor([ms_total, e2e_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    X = gather_columns(Xd, nrhs, world, rank, dist=dist if world > 1 else None, device="cuda")  # off the timed path
+    ms_total, e2e_ms = float(t[0]), float(t[1])
+    if rank != 0:
+        return
+    ms_step = ms_total / args.steps
+    peak, peak_src = hbm_peak()
+    chunks = -(-max(1, shard_range(nrhs, world, 0)[1]) // 8)
+    bytes_step = world * (st["bytes_factors"] + st["bytes_dense"]) + nrhs * st["bytes_vec_per_rhs"]
+    line = {
+        "metric": "M^-1 applies/sec", "value": nrhs * args.steps / (ms_total * 1e-3), "unit": "applies/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(args.workload, args.size, nrhs), "n": n, "levels": st["levels"],
+                   "nnz_factors": st["nnz"], "params": "tau=1e-2 alpha=3 kappa=5 (reference PDE set)",
+                   "l2_policy": "inputs larger than L2",
+                   "parallelism": f"replicas, {nrhs} columns sharded over {world} GPU(s), 8 columns per pass"},
+        "roofline": {"bound": "hbm", "kernel": "whole batched apply", "achieved": bytes_step / (ms_step * 1e-3) / 1e9,
+                     "peak": peak * world, "unit": "GB/s", "frac": bytes_step / (ms_step * 1e-3) / 1e9 / (peak * world),
+                     "traffic": None, "algorithmic_bytes_per_step": bytes_step, "peak_source": peak_src,
+                     "passes_per_step": chunks},
+        "cpu_baseline": None,
+        "e2e": {"value": nrhs * args.steps / (e2e_ms * 1e-3), "unit": "applies/s",
+                "h2d_bytes_per_step": 8 * n * nrhs, "d2h_bytes_per_step": 8 * n * nrhs,
+                "api": "lhfdGpuSolveMrhs (pinned host buffers)"},
+        "gpu_launches": launches, "clocks": clocks, "parity_vs_reference": parity,
+        "gathered_shape": list(X.shape),
+    }
+    print(json.dumps(line), flush=True)
+
+
 def run_ours(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
@@ -357,6 +459,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="poisson", choices=["poisson", "neumann", "convdiff", "stokes"])
     ap.add_argument("--size", type=int, default=128)
+    ap.add_argument("--nrhs", type=int, default=1,
+                    help="> 1: batched multi-rhs mode (config 4), columns sharded over the ranks (strong scaling)")
     ap.add_argument("--cpu-applies", type=int, default=40)
     ap.add_argument("--ref-max-steps", type=int, default=300)
     ap.add_argument("--no-cpu", action="store_true")
@@ -377,7 +481,10 @@ def main():
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     try:
-        run_ours(args, rank, world, local_rank)
+        if args.nrhs > 1:
+            run_mrhs(args, rank, world, local_rank)
+        else:
+            run_ours(args, rank, world, local_rank)
     finally:
         if world > 1:
             import torch.distributed as dist
