@@ -55,9 +55,11 @@ struct alignas(16) SlabInfo {
 };
 
 __host__ __device__ inline unsigned pad16(unsigned x) { return (x + 15u) & ~15u; }
-// slab layout: [ptr u32[rows+1]] [halo u32[nhalo]] [order u16[rows]] [idx u16[nnz]] [val f64[nnz]],
+// slab layout: [ptr u32[rows+1]] [gidx u32[rows]] [halo u32[nhalo]] [order u16[rows]] [idx u16[nnz]] [val f64[nnz]],
 // 16B-aligned segments.  order = the block's rows sorted by dependency depth (see kernel).
-__host__ __device__ inline unsigned slab_off_halo(unsigned rows) { return pad16(4u * (rows + 1u)); }
+// gidx[r] = global (natural) index of block row r: the sweep order is a permutation (below)
+__host__ __device__ inline unsigned slab_off_gidx(unsigned rows) { return pad16(4u * (rows + 1u)); }
+__host__ __device__ inline unsigned slab_off_halo(unsigned rows) { return slab_off_gidx(rows) + pad16(4u * rows); }
 __host__ __device__ inline unsigned slab_off_order(unsigned rows, unsigned nhalo) {
   return slab_off_halo(rows) + pad16(4u * nhalo);
 }
@@ -140,9 +142,9 @@ __global__ void __launch_bounds__(T + kPollLanes, (T <= 256 ? 4 : 2))
 
   // right-hand side of a row: b_i (L sweep) or (L^{-1}b)_i / d_i with a true division
   // (prec_solve.hpp:219) for the U sweep; fetched one row ahead of its use
+  const unsigned *gidx = reinterpret_cast<const unsigned *>(smem + slab_off_gidx(bi.rows));
   auto load_rhs = [&](unsigned r, unsigned &gi) -> double {
-    const unsigned s = bi.s0 + r;
-    gi               = UPPER ? m - 1u - s : s;
+    gi = gidx[r];
     return UPPER ? tag_value(rhs_tagged[gi]) / diag[gi] : rhs_plain[gi];
   };
   __syncthreads();  // xs initialised
@@ -347,6 +349,7 @@ __global__ void __launch_bounds__(T + kPollLanes, 1)
   while (!mbar_try_wait(&s_bar, 0)) {
   }
   const unsigned *      ptr   = reinterpret_cast<const unsigned *>(smem);
+  const unsigned *      gidx  = reinterpret_cast<const unsigned *>(smem + slab_off_gidx(rows));
   const unsigned *      halo  = reinterpret_cast<const unsigned *>(smem + slab_off_halo(rows));
   const unsigned short *order = reinterpret_cast<const unsigned short *>(smem + slab_off_order(rows, nhalo));
   const unsigned short *idx   = reinterpret_cast<const unsigned short *>(smem + slab_off_idx(rows, nhalo));
@@ -362,9 +365,8 @@ __global__ void __launch_bounds__(T + kPollLanes, 1)
     const unsigned long long *      pa    = dummy;
     bool                            active = q < rows;
     auto start_row = [&]() {
-      r                = order[q];
-      const unsigned s = bi.s0 + r;
-      gi               = static_cast<std::size_t>(UPPER ? m - 1u - s : s);
+      r  = order[q];
+      gi = static_cast<std::size_t>(gidx[r]);
       if (UPPER) {
         const double d = diag[gi];
 #pragma unroll
@@ -479,6 +481,7 @@ struct PackedSweep {
   unsigned                   max_smem = 0;
   std::size_t                halo_total = 0;
   unsigned                   block_depth = 0;
+  std::vector<unsigned>      perm, pos;  // sweep position -> natural row index, and back
 };
 }  // namespace
 
@@ -497,15 +500,90 @@ static void pack_sweep(const HostCsr &T, bool upper, PackedSweep &out, unsigned 
     for (unsigned k = T.ptr[i]; k < T.ptr[i + 1]; ++k) l = std::max(l, lev[T.col[k]] + 1u);
     lev[i] = l;
   }
+  // ---- sweep order.  The reference's rows come in an elimination-tree post order: the
+  // dependency closure of row i is (nearly) the contiguous range [lo(i), i] of the natural
+  // sweep.  ~85 % of the rows of the BASELINE factors sit in closures of < 1000 rows, i.e.
+  // in small closed subtrees that need NOTHING from outside.  The sweep is therefore
+  // re-ordered by (phase, subtree, natural position): phase 0 = rows of closed subtrees that
+  // fit one block, phase k = rows whose closure is up to 4^k times larger.  Blocks of phase 0
+  // have an empty halo, blocks of phase k only need phases < k (finished long ago) plus
+  // rows of their own subtree: almost no CTA ever waits, only the top of the tree is a
+  // chain of blocks.  Any such order is a valid topological order of the dependency graph.
+  std::vector<unsigned> &perm = out.perm, &pos = out.pos;
+  std::vector<unsigned>  grp_rows, grp_nnz;
+  perm.resize(m);
+  pos.resize(m);
+  {
+    const bool natural_order = std::getenv("HIFIR_B200_SWEEP_ORDER") &&
+                               std::string(std::getenv("HIFIR_B200_SWEEP_ORDER")) == "natural";
+    auto nat0 = [&](unsigned s) { return upper ? m - 1u - s : s; };   // natural sweep position -> row
+    auto pos0 = [&](unsigned i) { return upper ? m - 1u - i : i; };   // row -> natural sweep position
+    std::vector<unsigned> lo(m), phase(m), parent(m);
+    const unsigned        S0 = 640;  // closure span of phase 0
+    for (unsigned s = 0; s < m; ++s) {
+      const unsigned i = nat0(s);
+      unsigned       l = s;
+      for (unsigned k = T.ptr[i]; k < T.ptr[i + 1]; ++k) l = std::min(l, lo[pos0(T.col[k])]);
+      lo[s] = l;
+      unsigned ph = 0;
+      for (std::size_t span = S0; s - l + 1u > span; span *= 4) ++ph;
+      phase[s]  = ph;
+      parent[s] = s;
+    }
+    auto find = [&](unsigned a) {
+      while (parent[a] != a) a = parent[a] = parent[parent[a]];
+      return a;
+    };
+    // rows of one phase that depend on each other belong to one subtree group
+    for (unsigned s = 0; s < m; ++s) {
+      const unsigned i = nat0(s);
+      for (unsigned k = T.ptr[i]; k < T.ptr[i + 1]; ++k) {
+        const unsigned sj = pos0(T.col[k]);
+        if (phase[sj] == phase[s]) {
+          const unsigned a = find(sj), b = find(s);
+          if (a != b) parent[std::max(a, b)] = std::min(a, b);  // representative = first row of the group
+        }
+      }
+    }
+    std::vector<unsigned> ord(m);
+    for (unsigned s = 0; s < m; ++s) ord[s] = s;
+    if (!natural_order) {
+      std::vector<unsigned> rep(m);
+      for (unsigned s = 0; s < m; ++s) rep[s] = find(s);
+      std::stable_sort(ord.begin(), ord.end(), [&](unsigned a, unsigned b) {
+        if (phase[a] != phase[b]) return phase[a] < phase[b];
+        return rep[a] < rep[b];
+      });
+    }
+    for (unsigned t = 0; t < m; ++t) {
+      perm[t]      = nat0(ord[t]);
+      pos[perm[t]] = t;
+    }
+    // subtree groups in the new order: size of the group that STARTS at position t (0 elsewhere)
+    grp_rows.assign(m + 1, 0u);
+    grp_nnz.assign(m + 1, 0u);
+    unsigned start = 0;
+    for (unsigned t = 0; t <= m; ++t) {
+      const bool boundary = t == m || t == 0 || natural_order || find(ord[t]) != find(ord[t - 1]) ||
+                            phase[ord[t]] != phase[ord[t - 1]];
+      if (boundary && t > 0) {
+        grp_rows[start] = t - start;
+        unsigned long long z = 0;
+        for (unsigned u = start; u < t; ++u) z += T.ptr[perm[u] + 1] - T.ptr[perm[u]];
+        grp_nnz[start] = static_cast<unsigned>(std::min<unsigned long long>(z, 0xffffffffu));
+        start          = t;
+      }
+    }
+  }
   std::vector<unsigned short> order;
-  std::vector<unsigned>       ent;
+  std::vector<unsigned>       ent, gidx;
   const bool sort_by_depth = !(std::getenv("HIFIR_B200_ENTRY_ORDER") &&
                                std::string(std::getenv("HIFIR_B200_ENTRY_ORDER")) == "natural");
   std::vector<unsigned>      ptr, halo;
   std::vector<unsigned short> idx;
   std::vector<double>         val;
   unsigned                    max_smem = 0;
-  auto nat = [&](unsigned s) { return upper ? m - 1u - s : s; };
+  auto nat = [&](unsigned s) { return perm[s]; };
 
   const unsigned budget = budget_override ? budget_override : smem_budget();
   unsigned s0 = 0, bid = 0;
@@ -514,11 +592,20 @@ static void pack_sweep(const HostCsr &T, bool upper, PackedSweep &out, unsigned 
     // ---- choose the block's rows: as many as fit the thread and shared-memory budget
     unsigned rows = 0, nnz = 0, nh = 0;
     while (s0 + rows < m && rows < kRowsMax) {
+      // keep a subtree group in one block when it fits an empty one: a group that is not
+      // split has no dependency on a sibling block
+      const unsigned gr = grp_rows[s0 + rows], gz = grp_nnz[s0 + rows];
+      if (rows && gr > 1) {
+        const bool fits_empty = gr <= kRowsMax && slab_bytes(gr, gr / 4, gz) + slot_bytes * (gr + 2 + gr / 4) <= budget;
+        const bool fits_here  = rows + gr <= kRowsMax &&
+                               slab_bytes(rows + gr, nh + gr / 4, nnz + gz) + slot_bytes * (rows + gr + 2 + nh + gr / 4) <= budget;
+        if (fits_empty && !fits_here) break;
+      }
       const unsigned i = nat(s0 + rows);
       unsigned       add_h = 0;
       for (unsigned k = T.ptr[i]; k < T.ptr[i + 1]; ++k) {
         const unsigned j  = static_cast<unsigned>(T.col[k]);
-        const unsigned sj = upper ? m - 1u - j : j;
+        const unsigned sj = pos[j];
         if (sj < s0 && stamp[j] != bid) {
           stamp[j] = bid;
           slot[j]  = nh + add_h;
@@ -563,7 +650,7 @@ static void pack_sweep(const HostCsr &T, bool upper, PackedSweep &out, unsigned 
       for (unsigned q = 0; q < e - b; ++q) {
         const unsigned k  = ent[q];
         const unsigned j  = static_cast<unsigned>(T.col[k]);
-        const unsigned sj = upper ? m - 1u - j : j;
+        const unsigned sj = pos[j];
         unsigned       loc;
         if (sj >= s0) {
           loc = sj - s0;  // a row of this block
@@ -587,6 +674,9 @@ static void pack_sweep(const HostCsr &T, bool upper, PackedSweep &out, unsigned 
     buf.resize(buf.size() + bi.bytes, 0);
     unsigned char *base = buf.data() + bi.off;
     std::memcpy(base, ptr.data(), 4u * (rows + 1));
+    gidx.resize(rows);
+    for (unsigned r = 0; r < rows; ++r) gidx[r] = nat(s0 + r);
+    std::memcpy(base + slab_off_gidx(rows), gidx.data(), 4u * rows);
     if (nh) std::memcpy(base + slab_off_halo(rows), halo.data(), 4u * nh);
     std::memcpy(base + slab_off_order(rows, nh), order.data(), 2u * rows);
     if (nnz) {
@@ -611,7 +701,7 @@ static void pack_sweep(const HostCsr &T, bool upper, PackedSweep &out, unsigned 
     const unsigned *hl = reinterpret_cast<const unsigned *>(buf.data() + infos[b].off + slab_off_halo(infos[b].rows));
     unsigned        l  = 0;
     for (unsigned h = 0; h < infos[b].nhalo; ++h) {
-      const unsigned j = hl[h], sj = upper ? m - 1u - j : j;
+      const unsigned j = hl[h], sj = pos[j];
       l = std::max(l, blev[blk_of[sj]] + 1u);
     }
     blev[b] = l;
@@ -640,11 +730,11 @@ void sweep_host_emulate(const HostCsr &T, bool upper, const double *rhs, const d
     const unsigned *      halo = reinterpret_cast<const unsigned *>(base + slab_off_halo(bi.rows));
     const unsigned short *idx  = reinterpret_cast<const unsigned short *>(base + slab_off_idx(bi.rows, bi.nhalo));
     const double *        val  = reinterpret_cast<const double *>(base + slab_off_val(bi.rows, bi.nhalo, bi.nnz));
+    const unsigned *      gix  = reinterpret_cast<const unsigned *>(base + slab_off_gidx(bi.rows));
     xs.assign(bi.rows + bi.nhalo, 0.0);
     for (unsigned h = 0; h < bi.nhalo; ++h) xs[bi.rows + h] = x[halo[h]];
     for (unsigned r = 0; r < bi.rows; ++r) {
-      const unsigned s  = bi.s0 + r;
-      const unsigned gi = upper ? m - 1u - s : s;
+      const unsigned gi  = gix[r];
       double         acc = upper ? rhs[gi] / diag[gi] : rhs[gi];
       for (unsigned k = ptr[r]; k < ptr[r + 1]; ++k) acc -= val[k] * xs[idx[k]];
       xs[r] = acc;
@@ -700,8 +790,7 @@ void sweep_simulate(const HostCsr &T, bool upper, const double *prm, double *out
         t                 = std::max(t, av) + t_dep;
       }
       fin[r]            = t + t_pub;
-      const unsigned s  = bi.s0 + r;
-      F[upper ? m - 1u - s : s] = fin[r];
+      F[P.perm[bi.s0 + r]] = fin[r];
       thr[q % NT]       = fin[r];
       done              = std::max(done, fin[r]);
     }
@@ -732,7 +821,7 @@ void sweep_block_graph(const HostCsr &T, bool upper, std::vector<unsigned> &info
     info.insert(info.end(), {bi.s0, bi.rows, bi.nhalo, bi.nnz});
     const unsigned *hl = reinterpret_cast<const unsigned *>(P.buf.data() + bi.off + slab_off_halo(bi.rows));
     for (unsigned h = 0; h < bi.nhalo; ++h) {
-      const unsigned j = hl[h], sb = blk_of[upper ? m - 1u - j : j];
+      const unsigned j = hl[h], sb = blk_of[P.pos[j]];
       if (seen[sb] != b) {
         seen[sb] = static_cast<unsigned>(b);
         src_idx.push_back(sb);
