@@ -94,8 +94,7 @@ __global__ void axpy_kernel(const unsigned n, const double a, const double *__re
     y[i] = fma(a, x[i], y[i]);
 }
 // out = x + y
-__global__ void add_kernel(const unsigned n, const double *__restrict__ x, const double *__restrict__ y,
-                           double *__restrict__ out) {
+__global__ void add_kernel(const unsigned n, const double *__restrict__ x, const double *y, double *out) {
   for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[i] = x[i] + y[i];
 }
 // out = x / (*den)   (true division like the reference: Q(i,j+1) = v[i] / v_norm)

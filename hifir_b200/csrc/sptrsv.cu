@@ -110,7 +110,8 @@ __global__ void __launch_bounds__(T + kPollLanes, (T <= 256 ? 4 : 2))
     sptrsv_slab_kernel(const unsigned m, const unsigned char *__restrict__ slabs, const SlabInfo *__restrict__ info,
                        const double *__restrict__ rhs_plain, const unsigned long long *rhs_tagged,
                        const double *__restrict__ diag, unsigned long long *x, const unsigned parity, int *ticket,
-                       int *error_flag, unsigned long long *trace, const int backoff, const unsigned poll_sleep) {
+                       int *error_flag, unsigned long long *trace, const int backoff, const unsigned poll_sleep,
+                       const unsigned spin_burst, const int interleave) {
   constexpr unsigned kThreads = T + kPollLanes;
   extern __shared__ __align__(16) unsigned char smem[];
   __shared__ unsigned                        s_blk, s_done;
@@ -161,95 +162,98 @@ __global__ void __launch_bounds__(T + kPollLanes, (T <= 256 ? 4 : 2))
   if (tid < T) {
     // ---------------- row thread.  The block's rows are sorted by dependency depth
     // (order[]); thread t solves order[t], order[t+T], ... one after the other, so a
-    // thread's next row is never expected to be ready before its current one and only
-    // T threads (not one per row) spin on the shared-memory pipe at any time.
-    // Position q of order[] belongs to warp q % nwarps: rows that follow each other in
-    // depth order (a dependent chain) sit in DIFFERENT warps, so the warp that just
-    // published (and is busy setting up its next row) never delays the lane that waits
-    // for that value.
-    constexpr unsigned kRowWarps = T / 32;
-    unsigned           q         = (tid & 31u) * kRowWarps + (tid >> 5);  // position in order[]
+    // thread's next row is never expected to be ready before its current one and only T
+    // threads (not one per row) spin at any time.  Rows that follow each other in depth
+    // order -- a dependent chain -- sit in neighbouring lanes of ONE warp: the value a lane
+    // publishes is seen by its neighbour's very next poll.  To keep that hop short the warp
+    // does nothing but poll / consume / publish while any lane can advance; stepping a lane
+    // to its next row (dependent shared loads, the right-hand side) is deferred to
+    // iterations in which no lane of the warp had anything to consume.
+    unsigned q = interleave ? (tid & 31u) * (T / 32) + (tid >> 5) : tid;  // position in order[]
     unsigned r = 0, gi = 0, gi_next = 0;
     double   acc = 0.0, acc_next = 0.0;
     unsigned k = 0, e = 0, polls = 0;
     double   a = 0.0;
-    const volatile unsigned long long *pa = xs;  // slot of the dependency this lane waits for
-    bool active = q < rows;
-    if (active) {
-      r   = order[q];
-      acc = load_rhs(r, gi);
-      if (q + T < rows) acc_next = load_rhs(order[q + T], gi_next);
-      k = ptr[r], e = ptr[r + 1];
-      if (k < e) pa = xs + idx[k], a = val[k];
-    }
-    // publish finished rows (also rows without any dependency) and step to this thread's
-    // next row; a published value is visible to the block through xs and to later blocks
-    // through x (global, polled by their halo warps)
-    auto finish_rows = [&]() {
-      while (active && k == e) {
-        const unsigned long long bits = tag_set(acc, parity);
-        xs[r]                         = bits;
-        st_publish(x + gi, bits);
-        if (trace) {
-          if (atomicAdd(&s_done, 1u) + 1u == rows) {  // the row that finishes last
-            trace[8 * s_blk + 2] = globaltimer_ns();
-            trace[8 * s_blk + 4] = polls;
-            trace[8 * s_blk + 5] = r;
-            trace[8 * s_blk + 7] = s_pollend;
-          }
+    volatile unsigned long long *const dummy = xs + rows + nhalo;  // never becomes ready
+    const volatile unsigned long long *pa    = dummy;               // slot this lane waits for
+    bool active = q < rows, need = false;
+    auto publish = [&]() {
+      const unsigned long long bits = tag_set(acc, parity);
+      xs[r]                         = bits;
+      st_publish(x + gi, bits);
+      if (trace) {
+        if (atomicAdd(&s_done, 1u) + 1u == rows) {  // the row that finishes last
+          trace[8 * s_blk + 2] = globaltimer_ns();
+          trace[8 * s_blk + 4] = polls;
+          trace[8 * s_blk + 5] = r;
+          trace[8 * s_blk + 7] = s_pollend;
         }
-        q += T;
-        if (q >= rows) {
-          active = false;
-          break;
-        }
-        r   = order[q];
-        acc = acc_next, gi = gi_next;
-        if (q + T < rows) acc_next = load_rhs(order[q + T], gi_next);
-        k = ptr[r], e = ptr[r + 1];
-        if (k < e) pa = xs + idx[k], a = val[k];
       }
     };
-    finish_rows();
-    // Warp-uniform structure: a SHORT spin (one shared load + vote per iteration) while no
-    // lane of the warp can advance, then a divergent step for the lanes whose dependency
-    // arrived.  No lane ever blocks a sibling: finished values are published inside the
-    // step, before the warp spins again.
-    volatile unsigned long long *const dummy = xs + rows + nhalo;  // never becomes ready
-    if (!active) pa = dummy;
-    while (__any_sync(0xffffffffu, active)) {
-      unsigned long long bits;
-      bool               rdy;
-      unsigned           rounds = 0;
-      // tight spin: one shared load, one test, one vote per iteration (finished lanes poll
-      // the dummy slot, so the loop needs no per-lane predicate)
-      for (;;) {
-        bool any = false;
-#pragma unroll 1
-        for (unsigned it = 0; it < kSpinBurst; ++it) {
-          bits = *pa;
-          rdy  = (static_cast<unsigned>(bits) & 1u) == parity;
-          any  = __any_sync(0xffffffffu, rdy);
-          if (any) break;
-        }
-        if (any) break;
-        // nothing arrived during a whole burst (~100 us): this warp waits for something
-        // far away -- sleep between bursts so that it stops competing for issue slots
-        ++rounds;
-        if (backoff) __nanosleep(1000u);
-        if (rounds > kSpinLimit / kSpinBurst) {  // hang guard: flag the error, drain with garbage
-          *error_flag = 1;
-          rdy         = active;
-          break;
-        }
+    // row at position q: returns true when it has no dependency left (published at once)
+    auto setup = [&]() -> bool {
+      r   = order[q];
+      k = ptr[r], e = ptr[r + 1];
+      if (k < e) {
+        pa = xs + idx[k], a = val[k];
+        return false;
       }
-      if (trace) polls += rounds;
-      if (rdy) {
-        acc = fma(-a, tag_value(bits), acc);
-        ++k;
-        if (k < e) pa = xs + idx[k], a = val[k];
-        finish_rows();
-        if (!active) pa = dummy;
+      publish();
+      return true;
+    };
+    if (active) {
+      acc = load_rhs(order[q], gi);
+      if (q + T < rows) acc_next = load_rhs(order[q + T], gi_next);
+      need = setup();
+      if (need) pa = dummy;
+    }
+    unsigned rounds = 0;
+    for (;;) {
+      const unsigned long long bits = *pa;
+      const bool               rdy  = (static_cast<unsigned>(bits) & 1u) == parity;
+      if (__any_sync(0xffffffffu, rdy)) {
+        if (rdy) {
+          acc = fma(-a, tag_value(bits), acc);
+          ++k;
+          if (k < e) {
+            pa = xs + idx[k], a = val[k];
+          } else {
+            publish();
+            need = true;
+            pa   = dummy;
+          }
+        }
+        rounds = 0;
+        continue;
+      }
+      if (__any_sync(0xffffffffu, need)) {
+        if (need) {
+          q += T;
+          if (q < rows) {
+            acc = acc_next, gi = gi_next;
+            if (q + T < rows) acc_next = load_rhs(order[q + T], gi_next);
+            need = setup();
+          } else {
+            active = false;
+            need   = false;
+          }
+        }
+        continue;
+      }
+      if (!__any_sync(0xffffffffu, active)) break;
+      // nothing to do: this warp waits for values that are still being computed
+      if (++rounds > spin_burst) {
+        if (trace) ++polls;
+        if (backoff) __nanosleep(static_cast<unsigned>(backoff));
+        if (rounds > kSpinLimit) {  // hang guard: flag the error, drain with garbage
+          *error_flag = 1;
+          if (active && !need) {
+            publish();
+            need = true;
+            pa   = dummy;
+          }
+          rounds = 0;
+        }
       }
     }
   } else {
@@ -867,8 +871,9 @@ void launch_T(Handle *h, const SweepPlan &plan, const double *rhs_plain, const u
   }
   sptrsv_slab_kernel<UPPER, T><<<plan.nblocks, T + kPollLanes, plan.smem_bytes, h->stream>>>(
       plan.m, plan.slabs.p, reinterpret_cast<const SlabInfo *>(plan.info.p), rhs_plain, rhs_tagged, diag, x, parity,
-      ticket, h->error_flag.p, trace, env_int("HIFIR_B200_BACKOFF", 1),
-      static_cast<unsigned>(env_int("HIFIR_B200_POLL_SLEEP", 100)));
+      ticket, h->error_flag.p, trace, env_int("HIFIR_B200_BACKOFF", 1000),
+      static_cast<unsigned>(env_int("HIFIR_B200_POLL_SLEEP", 100)),
+      static_cast<unsigned>(env_int("HIFIR_B200_SPIN_BURST", 4096)), env_int("HIFIR_B200_INTERLEAVE", 0));
 }
 template <bool UPPER>
 void launch_U(Handle *h, const SweepPlan &plan, const double *rhs_plain, const unsigned long long *rhs_tagged,
