@@ -39,6 +39,9 @@ struct DevBuf {
     if (count) {
       HIF_CUDA(cudaMalloc(&p, count * sizeof(T)));
       HIF_CUDA(cudaMemset(p, 0, count * sizeof(T)));
+      // the handle's stream is non-blocking: make sure the (legacy-stream) memset has landed
+      // before any kernel of the handle can touch the buffer (tagged buffers rely on it)
+      HIF_CUDA(cudaDeviceSynchronize());
       if (tally) *tally += count * sizeof(T);
     }
   }
