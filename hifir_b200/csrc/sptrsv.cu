@@ -524,16 +524,38 @@ static void pack_sweep(const HostCsr &T, bool upper, PackedSweep &out, unsigned 
     auto pos0 = [&](unsigned i) { return upper ? m - 1u - i : i; };   // row -> natural sweep position
     std::vector<unsigned> lo(m), phase(m), parent(m);
     const unsigned        S0 = 640;  // closure span of phase 0
+    if (!upper) {
+      // fan-in (L): closure of a row = the rows it depends on = [lo, s]
+      for (unsigned s = 0; s < m; ++s) {
+        const unsigned i = nat0(s);
+        unsigned       l = s;
+        for (unsigned k = T.ptr[i]; k < T.ptr[i + 1]; ++k) l = std::min(l, lo[pos0(T.col[k])]);
+        lo[s] = l;
+      }
+    } else {
+      // fan-out (U): what matters is the set of rows that depend ON a row (its subtree),
+      // [s, hi]; rows with a large subtree (the top of the tree) go first, the many small
+      // closed subtrees last -- then everything they need (their ancestors) is long finished
+      for (unsigned s = 0; s < m; ++s) lo[s] = s;  // lo holds hi here
+      for (unsigned s = m; s-- > 0;) {
+        const unsigned i = nat0(s);
+        for (unsigned k = T.ptr[i]; k < T.ptr[i + 1]; ++k) {
+          const unsigned sj = pos0(T.col[k]);
+          lo[sj]            = std::max(lo[sj], lo[s]);
+        }
+      }
+    }
+    unsigned max_phase = 0;
     for (unsigned s = 0; s < m; ++s) {
-      const unsigned i = nat0(s);
-      unsigned       l = s;
-      for (unsigned k = T.ptr[i]; k < T.ptr[i + 1]; ++k) l = std::min(l, lo[pos0(T.col[k])]);
-      lo[s] = l;
-      unsigned ph = 0;
-      for (std::size_t span = S0; s - l + 1u > span; span *= 4) ++ph;
+      const std::size_t width = upper ? lo[s] - s + 1u : s - lo[s] + 1u;
+      unsigned          ph    = 0;
+      for (std::size_t span = S0; width > span; span *= 4) ++ph;
       phase[s]  = ph;
       parent[s] = s;
+      max_phase = std::max(max_phase, ph);
     }
+    if (upper)
+      for (unsigned s = 0; s < m; ++s) phase[s] = max_phase - phase[s];  // largest subtrees first
     auto find = [&](unsigned a) {
       while (parent[a] != a) a = parent[a] = parent[parent[a]];
       return a;
