@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(T + kPollLanes, (T <= 256 ? 4 : 2))
                        const double *__restrict__ rhs_plain, const unsigned long long *rhs_tagged,
                        const double *__restrict__ diag, unsigned long long *x, const unsigned parity, int *ticket,
                        int *error_flag, unsigned long long *trace, const int backoff, const unsigned poll_sleep,
-                       const unsigned spin_burst, const int interleave, const int forward) {
+                       const unsigned spin_burst, const int interleave) {
   constexpr unsigned kThreads = T + kPollLanes;
   extern __shared__ __align__(16) unsigned char smem[];
   __shared__ unsigned                        s_blk, s_done;
@@ -212,31 +212,15 @@ __global__ void __launch_bounds__(T + kPollLanes, (T <= 256 ? 4 : 2))
       const unsigned long long bits = *pa;
       const bool               rdy  = (static_cast<unsigned>(bits) & 1u) == parity;
       if (__any_sync(0xffffffffu, rdy)) {
-        bool               pub   = false;  // this lane published a row in this step
-        unsigned long long pbits = 0;
-        auto consume = [&](unsigned long long v) {
-          acc = fma(-a, tag_value(v), acc);
+        if (rdy) {
+          acc = fma(-a, tag_value(bits), acc);
           ++k;
           if (k < e) {
             pa = xs + idx[k], a = val[k];
           } else {
             publish();
-            pub = true, pbits = tag_set(acc, parity);
             need = true;
             pa   = dummy;
-          }
-        };
-        if (rdy) consume(bits);
-        // In-warp forwarding: neighbouring lanes hold rows that follow each other in depth
-        // order, so in a dependent chain lane l+1 waits for exactly the row lane l just
-        // published.  Hand the value over with shuffles instead of a shared-memory round
-        // trip; a forwarded value may complete the next row, which is forwarded again.
-        if (forward) {
-          while (__any_sync(0xffffffffu, pub)) {
-            const unsigned long long up_bits = __shfl_up_sync(0xffffffffu, pbits, 1);
-            const unsigned           up_slot = __shfl_up_sync(0xffffffffu, pub ? r : 0xffffffffu, 1);
-            pub                              = false;
-            if ((tid & 31u) != 0u && pa == xs + up_slot) consume(up_bits);
           }
         }
         rounds = 0;
@@ -911,8 +895,7 @@ void launch_T(Handle *h, const SweepPlan &plan, const double *rhs_plain, const u
       plan.m, plan.slabs.p, reinterpret_cast<const SlabInfo *>(plan.info.p), rhs_plain, rhs_tagged, diag, x, parity,
       ticket, h->error_flag.p, trace, env_int("HIFIR_B200_BACKOFF", 1000),
       static_cast<unsigned>(env_int("HIFIR_B200_POLL_SLEEP", 100)),
-      static_cast<unsigned>(env_int("HIFIR_B200_SPIN_BURST", 4096)), env_int("HIFIR_B200_INTERLEAVE", 0),
-      env_int("HIFIR_B200_FORWARD", 1));
+      static_cast<unsigned>(env_int("HIFIR_B200_SPIN_BURST", 4096)), env_int("HIFIR_B200_INTERLEAVE", 0));
 }
 template <bool UPPER>
 void launch_U(Handle *h, const SweepPlan &plan, const double *rhs_plain, const unsigned long long *rhs_tagged,
