@@ -170,7 +170,14 @@ Handle *attach_levels(int device, std::size_t nlevels, const LhfdGpuLevel *lv) {
     D.depthL = dag_depth(Lr, false);
     D.depthU = dag_depth(Ur, true);
 
-    build_sweep_plan(Lr, false, D.L, tally);
+    {
+      HostCsr               ul;
+      std::vector<unsigned> urows;
+      build_split_plans(Lr, D.L, D.L_up, ul, urows, tally);
+      upload_csr(ul, D.L_ul, tally);
+      D.L_urows.upload(urows, tally);
+      D.rhs_u.alloc(P.m, tally);
+    }
     build_sweep_plan(Ur, true, D.U, tally);
     D.L.nnz = Lr.col.size();
     D.U.nnz = Ur.col.size();
@@ -229,7 +236,7 @@ Handle *attach_levels(int device, std::size_t nlevels, const LhfdGpuLevel *lv) {
     h->nnz_total += nm * nm;
   }
 
-  h->tickets.alloc(4 * nlevels + 4, tally);
+  h->tickets.alloc(8 * nlevels + 8, tally);
   h->error_flag.alloc(1, tally);
   HIF_CUDA(cudaMallocHost(&h->h_error, sizeof(int)));
   *h->h_error = 0;

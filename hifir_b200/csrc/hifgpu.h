@@ -80,7 +80,12 @@ struct SweepPlan {
 // one hif::Prec level on the device (reference alg/Prec.hpp:309-323)
 struct DevLevel {
   std::size_t m = 0, n = 0, nm = 0;
-  SweepPlan   L, U;  // L_B, U_B as slabs
+  SweepPlan   L, U;  // L_B, U_B as slabs (L = rows of small closed subtrees when the sweep is split)
+  // split forward sweep: x_l = L_ll^{-1} b_l ; r_u = b_u - L_ul x_l ; x_u = L_uu^{-1} r_u
+  SweepPlan        L_up;     // L_uu over the upper rows (empty plan when there are none)
+  DevCsr           L_ul;     // compact rows (one per upper row) x all columns
+  DevBuf<unsigned> L_urows;  // global row index of each compact row
+  DevBuf<double>   rhs_u;    // m, right-hand side of the upper sweep
   DevCsr      E, F;
   DevBuf<double> d;        // m
   DevBuf<double> s, t;     // n
@@ -164,6 +169,8 @@ void sweep_host_emulate(const HostCsr &T, bool upper, const double *rhs, const d
                         std::size_t stats[4]);
 void sweep_block_graph(const HostCsr &T, bool upper, std::vector<unsigned> &info, std::vector<unsigned> &src_ptr,
                        std::vector<unsigned> &src_idx);
+void build_split_plans(const HostCsr &T, SweepPlan &plan_lo, SweepPlan &plan_up, HostCsr &ul,
+                       std::vector<unsigned> &urows, std::size_t *tally);
 void sweep_simulate(const HostCsr &T, bool upper, const double *prm, double *out);
 void launch_sweep(Handle *h, const SweepPlan &plan, const double *rhs_plain, const unsigned long long *rhs_tagged,
                   const double *diag, unsigned long long *x, unsigned parity, int *ticket,
