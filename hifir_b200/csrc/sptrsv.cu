@@ -492,7 +492,8 @@ struct PackedSweep {
 // `rows_mask` (optional): pack only these rows of T; every entry of an included row must
 // then reference an included row (the caller splits the matrix accordingly).
 static void pack_sweep(const HostCsr &T, bool upper, PackedSweep &out, unsigned slot_bytes = 8u,
-                       unsigned budget_override = 0u, const std::vector<char> *rows_mask = nullptr) {
+                       unsigned budget_override = 0u, const std::vector<char> *rows_mask = nullptr,
+                       unsigned rows_max = kRowsMax) {
   const unsigned m = static_cast<unsigned>(T.nrows);
   if (!m) return;
   std::vector<SlabInfo> &     infos = out.infos;
@@ -629,13 +630,13 @@ static void pack_sweep(const HostCsr &T, bool upper, PackedSweep &out, unsigned 
     ++bid;
     // ---- choose the block's rows: as many as fit the thread and shared-memory budget
     unsigned rows = 0, nnz = 0, nh = 0;
-    while (s0 + rows < mt && rows < kRowsMax) {
+    while (s0 + rows < mt && rows < rows_max) {
       // keep a subtree group in one block when it fits an empty one: a group that is not
       // split has no dependency on a sibling block
       const unsigned gr = grp_rows[s0 + rows], gz = grp_nnz[s0 + rows];
       if (rows && gr > 1) {
-        const bool fits_empty = gr <= kRowsMax && slab_bytes(gr, gr / 4, gz) + slot_bytes * (gr + 2 + gr / 4) <= budget;
-        const bool fits_here  = rows + gr <= kRowsMax &&
+        const bool fits_empty = gr <= rows_max && slab_bytes(gr, gr / 4, gz) + slot_bytes * (gr + 2 + gr / 4) <= budget;
+        const bool fits_here  = rows + gr <= rows_max &&
                                slab_bytes(rows + gr, nh + gr / 4, nnz + gz) + slot_bytes * (rows + gr + 2 + nh + gr / 4) <= budget;
         if (fits_empty && !fits_here) break;
       }
@@ -876,6 +877,12 @@ void sweep_block_graph(const HostCsr &T, bool upper, std::vector<unsigned> &info
 // (a plain SpMV on finished data) ; x_u = L_uu^{-1} r_u.  The dependent chain of blocks at the
 // top of the tree then works on L_uu only: 3-4x less data per row, small halos, 3x fewer
 // block-to-block hand-offs.
+static bool big_chain_blocks() {
+  const char *e = std::getenv("HIFIR_B200_BIG_BLOCKS");
+  return !e || std::atoi(e) != 0;
+}
+constexpr unsigned kRowsBig = 4096;
+
 void split_lower_rows(const HostCsr &T, std::vector<char> &is_lower) {
   const unsigned m = static_cast<unsigned>(T.nrows);
   is_lower.assign(m, 1);
@@ -936,7 +943,12 @@ void build_split_plans(const HostCsr &T, SweepPlan &plan_lo, SweepPlan &plan_up,
   pack_sweep(T, false, Plo, 8u, 0u, &is_lower);
   upload_plan(Plo, m, false, 1, plan_lo, tally);
   if (!urows.empty()) {
-    pack_sweep(uu, false, Pup, 8u, 0u, &is_upper);
+    // the top of the tree is a dependent chain of blocks: make them as large as one SM
+    // allows (fewer block-to-block hand-offs); occupancy is irrelevant there
+    if (big_chain_blocks())
+      pack_sweep(uu, false, Pup, 8u, kSmemBudgetMrhs, &is_upper, kRowsBig);
+    else
+      pack_sweep(uu, false, Pup, 8u, 0u, &is_upper);
     upload_plan(Pup, m, false, 1, plan_up, tally);
   }
 }
@@ -949,10 +961,18 @@ void build_sweep_plan(const HostCsr &T, bool upper, SweepPlan &plan, std::size_t
   if (!plan.m) return;
   PackedSweep P;
   // multi-rhs plans: one CTA per SM with the whole 227 KB, a solution slot holds nr values
-  if (nr > 1)
+  if (nr > 1) {
     pack_sweep(T, upper, P, 8u * nr, kSmemBudgetMrhs);
-  else
+  } else {
     pack_sweep(T, upper, P);
+    // a factor that yields only a few hundred blocks can not fill the GPU anyway and is
+    // bound by its dependent chain: prefer few large blocks (one CTA per SM)
+    if (big_chain_blocks() && P.infos.size() < 4 * kNumSMs) {
+      PackedSweep Q;
+      pack_sweep(T, upper, Q, 8u, kSmemBudgetMrhs, nullptr, kRowsBig);
+      P = std::move(Q);
+    }
+  }
   plan.nblocks    = static_cast<unsigned>(P.infos.size());
   plan.smem_bytes = P.max_smem;
   plan.slab_bytes = P.buf.size();
@@ -972,7 +992,7 @@ void launch_T(Handle *h, const SweepPlan &plan, const double *rhs_plain, const u
   static bool configured = false;
   if (!configured) {
     HIF_CUDA(cudaFuncSetAttribute(sptrsv_slab_kernel<UPPER, T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  static_cast<int>(kSmemBudgetMax)));
+                                  static_cast<int>(kSmemBudgetMrhs)));
     configured = true;
   }
   sptrsv_slab_kernel<UPPER, T><<<plan.nblocks, T + kPollLanes, plan.smem_bytes, h->stream>>>(
