@@ -360,15 +360,25 @@ __global__ void __launch_bounds__(T + kPollLanes, 1)
   const double *        val   = reinterpret_cast<const double *>(smem + slab_off_val(rows, nhalo, nnz));
 
   if (tid < T) {
-    constexpr unsigned kRowWarps = T / 32;
-    unsigned           q         = (tid & 31u) * kRowWarps + (tid >> 5);
-    unsigned           r = 0, k = 0, e = 0;
-    std::size_t        gi = 0;
-    double             acc[NR], a = 0.0;
+    // row threads: same structure as the single-rhs kernel -- chain rows in neighbouring
+    // lanes of one warp, poll / consume / publish with priority, row switches deferred to
+    // iterations in which no lane can advance
+    unsigned     q = tid;
+    unsigned     r = 0, k = 0, e = 0, rounds = 0;
+    std::size_t  gi = 0;
+    double       acc[NR], a = 0.0;
     const unsigned long long *const dummy = xs + static_cast<std::size_t>(rows + nhalo) * NR;
     const unsigned long long *      pa    = dummy;
-    bool                            active = q < rows;
-    auto start_row = [&]() {
+    bool                            active = q < rows, need = false;
+    auto publish = [&]() {
+#pragma unroll
+      for (unsigned c = 0; c < NR; ++c) {
+        const unsigned long long bits = tag_set(acc[c], parity);
+        xs[static_cast<std::size_t>(r) * NR + c] = bits;
+        st_publish(x + gi * NR + c, bits);
+      }
+    };
+    auto setup = [&]() -> bool {  // true: the row had no dependency and was published at once
       r  = order[q];
       gi = static_cast<std::size_t>(gidx[r]);
       if (UPPER) {
@@ -380,60 +390,65 @@ __global__ void __launch_bounds__(T + kPollLanes, 1)
         for (unsigned c = 0; c < NR; ++c) acc[c] = rhs_plain[gi * NR + c];
       }
       k = ptr[r], e = ptr[r + 1];
-      if (k < e) pa = xs + static_cast<std::size_t>(idx[k]) * NR, a = val[k];
-    };
-    auto finish_rows = [&]() {
-      while (active && k == e) {
-#pragma unroll
-        for (unsigned c = 0; c < NR; ++c) {
-          const unsigned long long bits = tag_set(acc[c], parity);
-          xs[static_cast<std::size_t>(r) * NR + c] = bits;
-          st_publish(x + gi * NR + c, bits);
-        }
-        q += T;
-        if (q >= rows) {
-          active = false;
-          pa     = dummy;
-          break;
-        }
-        start_row();
+      if (k < e) {
+        pa = xs + static_cast<std::size_t>(idx[k]) * NR, a = val[k];
+        return false;
       }
+      publish();
+      pa = dummy;
+      return true;
     };
-    if (active) start_row();
-    finish_rows();
-    while (__any_sync(0xffffffffu, active)) {
+    if (active) need = setup();
+    for (;;) {
       unsigned long long v[NR];
-      bool               rdy    = false;
-      unsigned           rounds = 0;
-      for (;;) {
-        bool any = false;
-#pragma unroll 1
-        for (unsigned it = 0; it < 1024u; ++it) {
-          unsigned ok = 1u;
+      unsigned           ok = 1u;
 #pragma unroll
-          for (unsigned c = 0; c < NR; c += 2) {
-            lds_v2(pa + c, v[c], v[c + 1]);
-            ok &= static_cast<unsigned>((static_cast<unsigned>(v[c]) & 1u) == parity) &
-                  static_cast<unsigned>((static_cast<unsigned>(v[c + 1]) & 1u) == parity);
-          }
-          rdy = ok != 0u;
-          any = __any_sync(0xffffffffu, rdy);
-          if (any) break;
-        }
-        if (any) break;
-        __nanosleep(500u);
-        if (++rounds > kSpinLimit / 64u) {
-          *error_flag = 1;
-          rdy         = active;
-          break;
-        }
+      for (unsigned c = 0; c < NR; c += 2) {
+        lds_v2(pa + c, v[c], v[c + 1]);
+        ok &= static_cast<unsigned>((static_cast<unsigned>(v[c]) & 1u) == parity) &
+              static_cast<unsigned>((static_cast<unsigned>(v[c + 1]) & 1u) == parity);
       }
-      if (rdy) {
+      const bool rdy = ok != 0u;
+      if (__any_sync(0xffffffffu, rdy)) {
+        if (rdy) {
 #pragma unroll
-        for (unsigned c = 0; c < NR; ++c) acc[c] = fma(-a, tag_value(v[c]), acc[c]);
-        ++k;
-        if (k < e) pa = xs + static_cast<std::size_t>(idx[k]) * NR, a = val[k];
-        finish_rows();
+          for (unsigned c = 0; c < NR; ++c) acc[c] = fma(-a, tag_value(v[c]), acc[c]);
+          ++k;
+          if (k < e) {
+            pa = xs + static_cast<std::size_t>(idx[k]) * NR, a = val[k];
+          } else {
+            publish();
+            need = true;
+            pa   = dummy;
+          }
+        }
+        rounds = 0;
+        continue;
+      }
+      if (__any_sync(0xffffffffu, need)) {
+        if (need) {
+          q += T;
+          if (q < rows) {
+            need = setup();
+          } else {
+            active = false;
+            need   = false;
+          }
+        }
+        continue;
+      }
+      if (!__any_sync(0xffffffffu, active)) break;
+      if (++rounds > 4096u) {
+        __nanosleep(500u);
+        if (rounds > kSpinLimit) {
+          *error_flag = 1;
+          if (active && !need) {
+            publish();
+            need = true;
+            pa   = dummy;
+          }
+          rounds = 0;
+        }
       }
     }
   } else {
