@@ -400,16 +400,23 @@ __global__ void __launch_bounds__(T + kPollLanes, 1)
     };
     if (active) need = setup();
     for (;;) {
-      unsigned long long v[NR];
-      unsigned           ok = 1u;
+      // cheap poll: only the tag of the LAST value of the slot (the publisher writes it
+      // last); a hit is verified on all NR tags after the full 128-bit loads, so no memory
+      // ordering between the publisher's stores is assumed
+      const unsigned long long hint = *reinterpret_cast<const volatile unsigned long long *>(pa + (NR - 1));
+      const bool               maybe = (static_cast<unsigned>(hint) & 1u) == parity;
+      if (__any_sync(0xffffffffu, maybe)) {
+        unsigned long long v[NR];
+        unsigned           ok = maybe ? 1u : 0u;
+        if (maybe) {
 #pragma unroll
-      for (unsigned c = 0; c < NR; c += 2) {
-        lds_v2(pa + c, v[c], v[c + 1]);
-        ok &= static_cast<unsigned>((static_cast<unsigned>(v[c]) & 1u) == parity) &
-              static_cast<unsigned>((static_cast<unsigned>(v[c + 1]) & 1u) == parity);
-      }
-      const bool rdy = ok != 0u;
-      if (__any_sync(0xffffffffu, rdy)) {
+          for (unsigned c = 0; c < NR; c += 2) {
+            lds_v2(pa + c, v[c], v[c + 1]);
+            ok &= static_cast<unsigned>((static_cast<unsigned>(v[c]) & 1u) == parity) &
+                  static_cast<unsigned>((static_cast<unsigned>(v[c + 1]) & 1u) == parity);
+          }
+        }
+        const bool rdy = ok != 0u;
         if (rdy) {
 #pragma unroll
           for (unsigned c = 0; c < NR; ++c) acc[c] = fma(-a, tag_value(v[c]), acc[c]);
