@@ -401,8 +401,8 @@ def run_ours(args, rank, world, local_rank):
                 "sptrsv_slab_kernel_bytes_per_launch")
         except Exception:
             traffic = None
-    roofline = {"bound": "hbm", "kernel": f"sptrsv_slab_kernel ({nl} launches per apply: L and U sweep of every "
-                                          f"level, down and up)",
+    roofline = {"bound": "hbm", "kernel": f"sptrsv_slab_kernel ({nl} triangular sweeps per apply: L and U of every "
+                                          f"level, down and up; an L sweep = subtree launch + spmv_rows + top launch)",
                 "achieved": k_ach, "peak": peak, "unit": "GB/s", "frac": k_ach / peak, "traffic": traffic,
                 "algorithmic_bytes_per_launch": sw_bytes / nl, "ms_per_launch": sw_ms / nl,
                 "share_of_step": sw_ms / sum(prof.values()), "peak_source": peak_src,
