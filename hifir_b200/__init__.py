@@ -109,6 +109,7 @@ def lib():
             "lhfdGpuSolveMrhs": [vp, sz, vp, vp],
             "lhfdGpuFgmres": [vp, vp, i, d, i, i, vp, vp, vp, vp],
             "lhfdGpuGmres": [vp, vp, i, d, i, vp, vp, vp],
+            "lhfdGpuApplyDev": [vp, i, vp, i, i, vp],
             "lhfdGpuSolveDev": [vp, vp, vp, sz],
             "lhfdGpuSolveMrhsDev": [vp, sz, vp, vp, sz],
             "lhfdGpuHifirDev": [vp, vp, sz, vp, sz],
@@ -134,7 +135,7 @@ def lib():
 EXPORTED_SYMBOLS = (
     "lhfdGpuAttachLevels", "lhfdGpuDestroy", "lhfdGpuSetMatrix", "lhfdGpuSetNspConst", "lhfdGpuClearNsp",
     "lhfdGpuSetStream", "lhfdGpuSynchronize", "lhfdGpuSolve", "lhfdGpuApply", "lhfdGpuSolveMrhs",
-    "lhfdGpuFgmres", "lhfdGpuGmres", "lhfdGpuSolveDev", "lhfdGpuSolveMrhsDev", "lhfdGpuHifirDev",
+    "lhfdGpuFgmres", "lhfdGpuGmres", "lhfdGpuApplyDev", "lhfdGpuSolveDev", "lhfdGpuSolveMrhsDev", "lhfdGpuHifirDev",
     "lhfdGpuSpmvDev", "lhfdGpuProfileSolveDev", "lhfdGpuDebugSweepHost", "lhfdGpuDebugTraceSweep", "lhfdGpuDebugSimulateSweep", "lhfdGpuDebugBlockGraph",
     "lhfdGpuGetStats", "lhfdGpuGetDepths", "lhfGpuGetErrorMsg", "lhfGpuVersion")
 
@@ -304,6 +305,9 @@ class GpuHif:
     # ---- device-pointer entry points (ints = raw device addresses, e.g. tensor.data_ptr()) ----
     def solve_dev(self, d_b, d_x, rank=0):
         _chk(lib().lhfdGpuSolveDev(self._h, C.c_void_p(d_b), C.c_void_p(d_x), rank))
+
+    def apply_dev(self, d_b, d_x, op=LHF_S, nirs=1, rank=LHF_DEFAULT_RANK):
+        _chk(lib().lhfdGpuApplyDev(self._h, op, C.c_void_p(d_b), nirs, rank, C.c_void_p(d_x)))
 
     def solve_mrhs_dev(self, nrhs, d_B, d_X, rank=0):
         _chk(lib().lhfdGpuSolveMrhsDev(self._h, nrhs, C.c_void_p(d_B), C.c_void_p(d_X), rank))

@@ -292,19 +292,8 @@ void apply_dev(Handle *h, const double *d_b, double *d_x, std::size_t rank) {
   // ---- dense last level (QRCP.hpp:370-411); rank: 0 -> numerical, > nm -> nm
   DevLevel &last = h->levels[nl - 1];
   if (last.nm) {
-    DevDense &      Q  = h->dense;
-    const unsigned  nm = static_cast<unsigned>(Q.nm);
-    const unsigned  rk = static_cast<unsigned>(rank == 0 ? Q.rank : (rank > Q.nm ? Q.nm : rank));
-    if (rk) {
-      dense_qt_kernel<<<cdiv(static_cast<std::size_t>(rk) * 32, T), T, 0, h->stream>>>(nm, rk, Q.Q.p, last.r.p, Q.c.p);
-      HIF_KERNEL_CHECK();
-      ++h->launch_count;
-    }
-    dense_trsv_kernel<<<1, kTrsvThreads, (rk ? rk : 1) * sizeof(double), h->stream>>>(nm, rk, Q.R.p, Q.rinv.p, Q.c.p, Q.jpvt.p,
-                                                                                      last.ychild.p, 1u);
-    HIF_KERNEL_CHECK();
+    dense_solve_dev(h, last.r.p, last.ychild.p, rank);
     mark(h, "dense");
-    ++h->launch_count;
   }
   // ---- up-sweep
   for (std::size_t l = nl; l-- > 0;) {
@@ -344,6 +333,123 @@ void apply_dev(Handle *h, const double *d_b, double *d_x, std::size_t rank) {
     }
   }
   h->kernels_per_apply = h->launch_count - launches0;
+}
+
+// ---- the four dense operations of QRCP (small_scale/QRCP.hpp:370-540) ------------------
+// single-CTA kernels for the transposed solve and the two products: off the BASELINE path,
+// written for clarity; arithmetic order = the reference BLAS (dtrsv / dtrmv column forms)
+constexpr int kDenseT = 512;
+
+// out = Q(:,1:rk) * R(1:rk,1:rk)^{-T} * (P^T x)(1:rk)      QRCP::_solve_t (QRCP.hpp:417-453)
+__global__ void __launch_bounds__(kDenseT, 1)
+    dense_solve_t_kernel(const unsigned nm, const unsigned rk, const double *__restrict__ R,
+                         const double *__restrict__ Q, const int *__restrict__ jpvt, const double *__restrict__ x,
+                         double *__restrict__ out) {
+  extern __shared__ double w[];
+  const unsigned           tid = threadIdx.x;
+  for (unsigned i = tid; i < rk; i += kDenseT) w[i] = x[jpvt[i] - 1];
+  __syncthreads();
+  for (unsigned j = 0; j < rk; ++j) {  // forward substitution with R^T, updates in ascending j
+    if (tid == 0) w[j] /= R[j + static_cast<std::size_t>(j) * nm];
+    __syncthreads();
+    const double wj = w[j];
+    for (unsigned i = j + 1 + tid; i < rk; i += kDenseT) w[i] -= R[j + static_cast<std::size_t>(i) * nm] * wj;
+    __syncthreads();
+  }
+  for (unsigned i = tid; i < nm; i += kDenseT) {
+    double acc = 0.0;
+    for (unsigned k = 0; k < rk; ++k) acc = fma(Q[i + static_cast<std::size_t>(k) * nm], w[k], acc);
+    out[i] = acc;
+  }
+}
+
+// out = Q(:,1:rk) * R(1:rk,1:rk) * (P^T x)(1:rk)            QRCP::_multiply_nt (QRCP.hpp:459-492)
+__global__ void __launch_bounds__(kDenseT, 1)
+    dense_mult_nt_kernel(const unsigned nm, const unsigned rk, const double *__restrict__ R,
+                         const double *__restrict__ Q, const int *__restrict__ jpvt, const double *__restrict__ x,
+                         double *__restrict__ out) {
+  extern __shared__ double w[];  // 2 * rk
+  double *                 v   = w + rk;
+  const unsigned           tid = threadIdx.x;
+  for (unsigned i = tid; i < rk; i += kDenseT) w[i] = x[jpvt[i] - 1];
+  __syncthreads();
+  for (unsigned i = tid; i < rk; i += kDenseT) {  // dtrmv 'U','N','N': diagonal term first, then ascending j
+    double acc = R[i + static_cast<std::size_t>(i) * nm] * w[i];
+    for (unsigned j = i + 1; j < rk; ++j) acc = fma(R[i + static_cast<std::size_t>(j) * nm], w[j], acc);
+    v[i] = acc;
+  }
+  __syncthreads();
+  for (unsigned i = tid; i < nm; i += kDenseT) {
+    double acc = 0.0;
+    for (unsigned k = 0; k < rk; ++k) acc = fma(Q[i + static_cast<std::size_t>(k) * nm], v[k], acc);
+    out[i] = acc;
+  }
+}
+
+// out = P [R(1:rk,1:rk)^T c ; 0] with c = Q(:,1:rk)^T x given   QRCP::_multiply_t (QRCP.hpp:494-540)
+__global__ void __launch_bounds__(kDenseT, 1)
+    dense_mult_t_kernel(const unsigned nm, const unsigned rk, const double *__restrict__ R,
+                        const double *__restrict__ c, const int *__restrict__ jpvt, double *__restrict__ out) {
+  extern __shared__ double w[];
+  const unsigned           tid = threadIdx.x;
+  for (unsigned i = tid; i < rk; i += kDenseT) w[i] = c[i];
+  __syncthreads();
+  for (unsigned j = tid; j < nm; j += kDenseT) {
+    double v = 0.0;
+    if (j < rk) {  // dtrmv 'U','C','N': diagonal term, then rows i < j in descending order
+      v = w[j] * R[j + static_cast<std::size_t>(j) * nm];
+      for (unsigned i = j; i-- > 0;) v = fma(R[i + static_cast<std::size_t>(j) * nm], w[i], v);
+    }
+    out[jpvt[j] - 1] = v;
+  }
+}
+
+static unsigned dense_rank_of(const DevDense &Q, std::size_t rank) {
+  return static_cast<unsigned>(rank == 0 ? Q.rank : (rank > Q.nm ? Q.nm : rank));
+}
+
+// QRCP::solve(x, rank, tran) with tran = the handle's orientation
+void dense_solve_dev(Handle *h, const double *d_in, double *d_out, std::size_t rank) {
+  DevDense &     Q  = h->dense;
+  const unsigned nm = static_cast<unsigned>(Q.nm), rk = dense_rank_of(Q, rank);
+  if (!Q.transposed) {
+    if (rk) {
+      dense_qt_kernel<<<cdiv(static_cast<std::size_t>(rk) * 32, 256), 256, 0, h->stream>>>(nm, rk, Q.Q.p, d_in, Q.c.p);
+      HIF_KERNEL_CHECK();
+      ++h->launch_count;
+    }
+    dense_trsv_kernel<<<1, kTrsvThreads, (rk ? rk : 1) * sizeof(double), h->stream>>>(nm, rk, Q.R.p, Q.rinv.p, Q.c.p,
+                                                                                     Q.jpvt.p, d_out, 1u);
+  } else {
+    dense_solve_t_kernel<<<1, kDenseT, (rk ? rk : 1) * sizeof(double), h->stream>>>(nm, rk, Q.R.p, Q.Q.p, Q.jpvt.p, d_in,
+                                                                                   d_out);
+  }
+  HIF_KERNEL_CHECK();
+  ++h->launch_count;
+}
+
+// QRCP::multiply(x, rank, tran)
+void dense_multiply_dev(Handle *h, const double *d_in, double *d_out, std::size_t rank) {
+  DevDense &     Q  = h->dense;
+  const unsigned nm = static_cast<unsigned>(Q.nm), rk = dense_rank_of(Q, rank);
+  if (!Q.transposed) {
+    dense_mult_nt_kernel<<<1, kDenseT, (rk ? 2 * rk : 2) * sizeof(double), h->stream>>>(nm, rk, Q.R.p, Q.Q.p, Q.jpvt.p,
+                                                                                       d_in, d_out);
+  } else {
+    if (rk) {
+      dense_qt_kernel<<<cdiv(static_cast<std::size_t>(rk) * 32, 256), 256, 0, h->stream>>>(nm, rk, Q.Q.p, d_in, Q.c.p);
+      HIF_KERNEL_CHECK();
+      ++h->launch_count;
+    }
+    dense_mult_t_kernel<<<1, kDenseT, (rk ? rk : 1) * sizeof(double), h->stream>>>(nm, rk, Q.R.p, Q.c.p, Q.jpvt.p, d_out);
+  }
+  HIF_KERNEL_CHECK();
+  ++h->launch_count;
+}
+
+void launch_ldu_solve(Handle *h, DevLevel &D, const double *rhs, unsigned long long *xL, unsigned long long *xU,
+                      unsigned parity, int *tickets) {
+  launch_sweeps(h, D, rhs, xL, xU, parity, tickets, "prod.", 100);
 }
 
 void launch_dense_trsv_cols(Handle *h, unsigned nm, unsigned rk, const double *c, double *out, unsigned ncols) {

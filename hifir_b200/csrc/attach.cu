@@ -113,7 +113,7 @@ std::vector<double> form_q(std::size_t nm, const double *mat, const double *tau)
 
 }  // namespace
 
-Handle *attach_levels(int device, std::size_t nlevels, const LhfdGpuLevel *lv) {
+Handle *attach_levels(int device, std::size_t nlevels, const LhfdGpuLevel *lv, bool dense_transposed) {
   if (!nlevels || !lv) throw std::invalid_argument("empty preconditioner (no levels)");
   int ndev = 0;
   HIF_CUDA(cudaGetDeviceCount(&ndev));
@@ -183,8 +183,23 @@ Handle *attach_levels(int device, std::size_t nlevels, const LhfdGpuLevel *lv) {
     D.U.nnz = Ur.col.size();
     D.hostL = std::move(Lr);
     D.hostU = std::move(Ur);
+    D.h_d.assign(P.d_B, P.d_B + P.m);
+    D.h_s.assign(P.s, P.s + P.n);
+    D.h_t.assign(P.t, P.t + P.n);
+    D.h_p.assign(P.p, P.p + P.n);
+    D.h_qinv.assign(P.q_inv, P.q_inv + P.n);
+    if (P.p_inv && P.q) {
+      D.h_pinv.assign(P.p_inv, P.p_inv + P.n);
+      D.h_q.assign(P.q, P.q + P.n);
+      for (std::size_t i = 0; i < P.n; ++i)
+        if (P.p_inv[i] < 0 || static_cast<std::size_t>(P.p_inv[i]) >= P.n || P.q[i] < 0 ||
+            static_cast<std::size_t>(P.q[i]) >= P.n)
+          throw std::invalid_argument(tag + ": permutation entry out of range");
+    }
     upload_csr(Er, D.E, tally);
     upload_csr(Fr, D.F, tally);
+    D.hostE = std::move(Er);
+    D.hostF = std::move(Fr);
     D.d.upload(P.d_B, P.m, tally);
     D.s.upload(P.s, P.n, tally);
     D.t.upload(P.t, P.n, tally);
@@ -223,6 +238,10 @@ Handle *attach_levels(int device, std::size_t nlevels, const LhfdGpuLevel *lv) {
     }
     h->dense.nm   = nm;
     h->dense.rank = last.dense_rank;
+    h->dense.transposed = dense_transposed;
+    h->dense.h_mat.assign(last.qr_mat, last.qr_mat + nm * nm);
+    h->dense.h_tau.assign(last.qr_tau, last.qr_tau + nm);
+    h->dense.h_jpvt.assign(last.qr_jpvt, last.qr_jpvt + nm);
     h->dense.Q.upload(form_q(nm, last.qr_mat, last.qr_tau), tally);
     h->dense.R.upload(last.qr_mat, nm * nm, tally);
     {
@@ -243,6 +262,79 @@ Handle *attach_levels(int device, std::size_t nlevels, const LhfdGpuLevel *lv) {
   HIF_CUDA(cudaMallocHost(&h->h_scal, 256 * sizeof(double)));
   HIF_CUDA(cudaDeviceSynchronize());
   return h.release();
+}
+
+// The transposed preconditioner M^T described with the same structures: with
+// P S A T Q = [B F; E C], B ~ L D U   =>   (.)^T has B^T ~ U^T D L^T, E' = F^T, F' = E^T and the
+// roles of (s, p, p_inv) and (t, q, q_inv) exchanged.  prec_solve / prec_prod on this description
+// are exactly prec_solve_tran / prec_prod_tran of the reference (prec_solve.hpp:541-612,
+// prec_prod.hpp:148-230) on the original one, so LHF_SH and LHF_MH reuse every kernel of LHF_S and
+// LHF_M.  The CCS arrays of a transposed block are the CSR arrays of the block itself.
+Handle *ensure_twin(Handle *h) {
+  if (h->twin) return h->twin;
+  if (h->is_twin) throw std::logic_error("transpose of a transposed handle requested");
+  const std::size_t nl = h->levels.size();
+  std::vector<LhfdGpuLevel>            tl(nl);
+  std::vector<std::vector<LhfIndPtr>> ptrs;
+  ptrs.reserve(4 * nl);
+  auto as_ccs = [&](const HostCsr &R, std::size_t nrows_t, std::size_t ncols_t) {
+    // R = CSR of X (rows = ncols_t of X^T ... ) -> CCS of X^T
+    ptrs.emplace_back(R.ptr.begin(), R.ptr.end());
+    if (ptrs.back().size() < ncols_t + 1) ptrs.back().resize(ncols_t + 1, ptrs.back().empty() ? 0 : ptrs.back().back());
+    LhfdGpuCcs c;
+    c.nrows     = nrows_t;
+    c.ncols     = ncols_t;
+    c.col_start = ptrs.back().data();
+    c.row_ind   = reinterpret_cast<const LhfInt *>(R.col.data());
+    c.vals      = R.val.data();
+    return c;
+  };
+  for (std::size_t l = 0; l < nl; ++l) {
+    DevLevel &D = h->levels[l];
+    if (D.h_pinv.empty() || D.h_q.empty())
+      throw std::logic_error("transpose operations need p_inv and q of every level (not given at attach)");
+    LhfdGpuLevel &T = tl[l];
+    std::memset(&T, 0, sizeof(T));
+    T.m     = D.m;
+    T.n     = D.n;
+    T.L_B   = as_ccs(D.hostU, D.m, D.m);   // (U_B)^T is strictly lower
+    T.U_B   = as_ccs(D.hostL, D.m, D.m);   // (L_B)^T is strictly upper
+    T.E     = as_ccs(D.hostF, D.nm, D.m);  // F^T : (n-m) x m
+    T.F     = as_ccs(D.hostE, D.m, D.nm);  // E^T : m x (n-m)
+    T.d_B   = D.h_d.data();
+    T.s     = D.h_t.data();
+    T.t     = D.h_s.data();
+    T.p     = reinterpret_cast<const LhfInt *>(D.h_q.data());
+    T.p_inv = reinterpret_cast<const LhfInt *>(D.h_qinv.data());
+    T.q     = reinterpret_cast<const LhfInt *>(D.h_p.data());
+    T.q_inv = reinterpret_cast<const LhfInt *>(D.h_pinv.data());
+    if (l + 1 == nl && h->dense.nm) {
+      T.dense_n    = h->dense.nm;
+      T.dense_rank = h->dense.rank;
+      T.qr_mat     = h->dense.h_mat.data();
+      T.qr_tau     = h->dense.h_tau.data();
+      T.qr_jpvt    = reinterpret_cast<const LhfInt *>(h->dense.h_jpvt.data());
+    }
+  }
+  Handle *t  = attach_levels(h->device, nl, tl.data(), true);
+  t->is_twin = true;
+  h->twin    = t;
+  h->device_bytes += t->device_bytes;
+  if (h->has_A)  // A^T: the CSR arrays of A are the CCS arrays of A^T and vice versa
+    set_matrix(t, !h->hA_rowmajor, h->n0(), h->hA_ptr.data(), h->hA_idx.data(), h->hA_val.data());
+  return t;
+}
+
+void destroy_handle(Handle *h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  if (h->twin) destroy_handle(h->twin);
+  if (h->h_error) cudaFreeHost(h->h_error);
+  if (h->h_scal) cudaFreeHost(h->h_scal);
+  cudaStream_t s = h->own_stream;
+  delete h;
+  if (s) cudaStreamDestroy(s);
 }
 
 void set_matrix(Handle *h, bool rowmajor, std::size_t n, const LhfIndPtr *indptr, const LhfInt *indices,
@@ -270,6 +362,14 @@ void set_matrix(Handle *h, bool rowmajor, std::size_t n, const LhfIndPtr *indptr
   h->A.nnz = A.col.size();
   upload_csr(A, h->A.A, &h->device_bytes);
   h->has_A = true;
+  if (!h->is_twin) {  // keep the caller's arrays for the twin's A^T
+    const std::size_t nnz = static_cast<std::size_t>(indptr[n]);
+    h->hA_ptr.assign(indptr, indptr + n + 1);
+    h->hA_idx.assign(indices, indices + nnz);
+    h->hA_val.assign(vals, vals + nnz);
+    h->hA_rowmajor = rowmajor;
+    if (h->twin) set_matrix(h->twin, !rowmajor, n, indptr, indices, vals);
+  }
 }
 
 }  // namespace hifgpu

@@ -80,16 +80,7 @@ LhfStatus lhfdGpuAttachLevels(int device, size_t nlevels, const LhfdGpuLevel *le
 
 LhfStatus lhfdGpuDestroy(LhfdGpuHdl hdl) {
   REQUIRE_HANDLE(hdl);
-  return guarded([&] {
-    Handle *h = H(hdl);
-    cudaSetDevice(h->device);
-    cudaStreamSynchronize(h->stream);
-    if (h->h_error) cudaFreeHost(h->h_error);
-    if (h->h_scal) cudaFreeHost(h->h_scal);
-    cudaStream_t s = h->own_stream;
-    delete h;
-    if (s) cudaStreamDestroy(s);
-  });
+  return guarded([&] { destroy_handle(H(hdl)); });
 }
 
 LhfStatus lhfdGpuSetMatrix(LhfdGpuHdl hdl, int is_rowmajor, size_t n, const LhfIndPtr *indptr,
@@ -206,34 +197,81 @@ LhfStatus lhfdGpuApply(LhfdGpuHdl hdl, LhfOperationType op, const double *b, int
   REQUIRE_HANDLE(hdl);
   REQUIRE_PTR(b, "b");
   REQUIRE_PTR(x, "x");
-  if (op != LHF_S) {
-    g_msg = "LHF_SH / LHF_M / LHF_MH are not served by the device backend yet (transpose solve and multilevel "
-            "product stay on the host object)";
+  if (op != LHF_S && op != LHF_SH && op != LHF_M && op != LHF_MH) {
+    g_msg = "unknown LhfOperationType";
     return LHF_BAD_PREC;
   }
   return guarded([&] {
-    Handle *h = H(hdl);
-    HIF_CUDA(cudaSetDevice(h->device));
+    Handle *h0 = H(hdl);
+    HIF_CUDA(cudaSetDevice(h0->device));
+    const bool trans = op == LHF_SH || op == LHF_MH;
+    Handle *   h     = h0;
+    if (trans) {  // the transposed twin serves S^H and M^H with the kernels of S and M
+      h         = ensure_twin(h0);
+      h->stream = h0->stream;
+    }
+    if (op == LHF_M || op == LHF_MH) {  // libhifir.cpp:458-459: mmultiply(b, x, trans), numerical rank
+      ensure_io(h0, 1);
+      h2d(h0, h0->io_b.p, b, h0->n0());
+      prod_dev(h, h0->io_b.p, h0->io_x.p, 0);
+      d2h(h0, x, h0->io_x.p, h0->n0());
+      check_sweep_error(h);
+      return;
+    }
+    if (trans && h0->nsp_on)
+      throw std::logic_error("the null-space filter of the transposed solve (nsp_tran) is not supported");
     // rank defaulting rule, libhifir.cpp:451-455
     const std::size_t rnk = rank == LHF_DEFAULT_RANK ? (nirs > 1 ? static_cast<std::size_t>(-1) : 0)
                                                      : static_cast<std::size_t>(static_cast<long long>(rank));
-    ensure_io(h, 1);
-    h2d(h, h->io_b.p, b, h->n0());
+    ensure_io(h0, 1);
+    h2d(h0, h0->io_b.p, b, h0->n0());
+    if (h != h0) {
+      if (h->io_b.n < h0->n0()) {  // the twin works on the primary handle's staging buffers
+        h->io_b.release();
+        h->io_x.release();
+      }
+    }
+    double *io_b = h0->io_b.p, *io_x = h0->io_x.p;
     if (nirs <= 1) {
-      apply_dev(h, h->io_b.p, h->io_x.p, 0);  // plain solve ignores `rank` (libhifir.cpp:461)
+      apply_dev(h, io_b, io_x, 0);  // plain solve ignores `rank` (libhifir.cpp:461)
     } else if (!betas) {
-      hifir_dev(h, h->io_b.p, static_cast<std::size_t>(nirs), h->io_x.p, rnk);
+      hifir_dev(h, io_b, static_cast<std::size_t>(nirs), io_x, rnk);
     } else {
       long iters = 0;
       int  flag  = 0;
-      hifir_betas_dev(h, h->io_b.p, static_cast<std::size_t>(nirs), betas, h->io_x.p, rnk, &iters, &flag);
+      hifir_betas_dev(h, io_b, static_cast<std::size_t>(nirs), betas, io_x, rnk, &iters, &flag);
       if (ir_status) {
         ir_status[0] = static_cast<int>(iters);
         ir_status[1] = flag;
       }
     }
-    d2h(h, x, h->io_x.p, h->n0());
+    d2h(h0, x, io_x, h0->n0());
     check_sweep_error(h);
+  });
+}
+
+// device-pointer form of lhfdGpuApply without residual bounds
+LhfStatus lhfdGpuApplyDev(LhfdGpuHdl hdl, LhfOperationType op, const double *d_b, int nirs, int rank, double *d_x) {
+  REQUIRE_HANDLE(hdl);
+  REQUIRE_PTR(d_b, "b");
+  REQUIRE_PTR(d_x, "x");
+  return guarded([&] {
+    Handle *h0 = H(hdl);
+    HIF_CUDA(cudaSetDevice(h0->device));
+    const bool trans = op == LHF_SH || op == LHF_MH;
+    Handle *   h     = h0;
+    if (trans) {
+      h         = ensure_twin(h0);
+      h->stream = h0->stream;
+    }
+    const std::size_t rnk = rank == LHF_DEFAULT_RANK ? (((op != LHF_S && op != LHF_SH) || nirs > 1) ? static_cast<std::size_t>(-1) : 0)
+                                                     : static_cast<std::size_t>(static_cast<long long>(rank));
+    if (op == LHF_M || op == LHF_MH)
+      prod_dev(h, d_b, d_x, 0);
+    else if (nirs <= 1)
+      apply_dev(h, d_b, d_x, 0);
+    else
+      hifir_dev(h, d_b, static_cast<std::size_t>(nirs), d_x, rnk);
   });
 }
 

@@ -101,6 +101,16 @@ struct DevLevel {
   DevBuf<double>             ychild;                    // nm  child's solution
   // multi-rhs (kMrhsWidth columns, row-interleaved): plans + work vectors, built on first use
   HostCsr                    hostL, hostU;  // kept for the lazily built multi-rhs plans
+  // host copies kept for the transposed twin (LHF_SH / LHF_MH) and the product (LHF_M / LHF_MH)
+  HostCsr             hostE, hostF;
+  std::vector<double> h_d, h_s, h_t;
+  std::vector<int>    h_p, h_pinv, h_q, h_qinv;  // h_pinv / h_q empty when the caller did not give them
+  // multilevel product: row-gather CSR of L_B and U_B, gather index and scalings (uploaded on first use)
+  DevCsr                     Lcsr, Ucsr;
+  DevBuf<int>                q_dev, pinv_dev;
+  DevBuf<double>             pw, pw1, pw2, pf;          // n, m, nm, m work vectors of prec_prod
+  DevBuf<unsigned long long> p_xL, p_xU;                // tagged results of the product's one LDU solve
+  DevBuf<double>             py;                        // n: product of this level (input of the level above)
   SweepPlan                  Lm, Um;
   DevBuf<double>             m_bhat, m_g, m_r, m_ychild;
   DevBuf<unsigned long long> m_xL_dn, m_xU_dn, m_xL_up, m_xU_up;
@@ -114,6 +124,9 @@ struct DevDense {
   DevBuf<double> rinv;  // nm, 1 / R(j,j)
   DevBuf<int>    jpvt;  // nm, 1-based verbatim
   DevBuf<double> c;     // nm work (Q^T b)
+  bool           transposed = false;  // twin handle: solve / multiply with (Q R P^T)^T
+  std::vector<double> h_mat, h_tau;    // host copies for the twin
+  std::vector<int>    h_jpvt;
 };
 
 struct DevMatrix {  // user matrix A in CRS
@@ -132,6 +145,14 @@ struct Handle {
   cudaStream_t          own_stream = nullptr, stream = nullptr;
   unsigned              epoch = 0;        // apply counter; parity tags the sync-free buffers
   unsigned              epoch_m = 0;      // same for the multi-rhs work vectors
+  unsigned              epoch_p = 0;      // same for the product's LDU solve
+  Handle *              twin = nullptr;   // transposed preconditioner (built on first LHF_SH / LHF_MH)
+  bool                  is_twin = false, prod_ready = false;
+  // host copy of the user matrix (for the twin's A^T)
+  std::vector<LhfIndPtr> hA_ptr;
+  std::vector<LhfInt>    hA_idx;
+  std::vector<double>    hA_val;
+  bool                   hA_rowmajor = true;
   DevBuf<int>           tickets;          // one block-ticket counter per sweep of an apply
   DevBuf<int>           error_flag;       // set by a sweep whose spin limit tripped
   int *                 h_error = nullptr;  // pinned mirror
@@ -157,7 +178,9 @@ struct Handle {
 };
 
 // ---- attach.cu
-Handle *attach_levels(int device, std::size_t nlevels, const LhfdGpuLevel *levels);
+Handle *attach_levels(int device, std::size_t nlevels, const LhfdGpuLevel *levels, bool dense_transposed = false);
+Handle *ensure_twin(Handle *h);   // transposed preconditioner sharing the stream of h
+void    destroy_handle(Handle *h);
 void    set_matrix(Handle *h, bool rowmajor, std::size_t n, const LhfIndPtr *indptr, const LhfInt *indices,
                    const double *vals);
 HostCsr ccs_to_csr(const LhfdGpuCcs &c, const char *name);
@@ -179,6 +202,14 @@ void launch_sweep(Handle *h, const SweepPlan &plan, const double *rhs_plain, con
 // ---- apply.cu : the multilevel M^{-1} apply on device vectors
 void apply_dev(Handle *h, const double *d_b, double *d_x, std::size_t rank);
 void check_sweep_error(Handle *h);  // synchronizes; throws if a sweep tripped its spin limit
+
+void dense_solve_dev(Handle *h, const double *d_in, double *d_out, std::size_t rank);     // QRCP::solve
+void dense_multiply_dev(Handle *h, const double *d_in, double *d_out, std::size_t rank);  // QRCP::multiply
+void launch_ldu_solve(Handle *h, DevLevel &D, const double *rhs, unsigned long long *xL, unsigned long long *xU,
+                      unsigned parity, int *tickets);
+
+// ---- product.cu : y = M x (prec_prod.hpp:54-134)
+void prod_dev(Handle *h, const double *d_x, double *d_y, std::size_t rank);
 
 // ---- krylov.cu
 void   spmv_dev(Handle *h, const double *d_x, double *d_y);

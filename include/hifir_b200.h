@@ -134,8 +134,10 @@ LhfStatus lhfdGpuSolve(LhfdGpuHdl hdl, const double *b, double *x);
 /* Drop-in for lhfdApply (libhifir.h:685-688, libhifir.cpp:447-472): same `op`,
  * `nirs`, `betas`, `rank`, `ir_status` meaning, including the rank-defaulting
  * rule (libhifir.cpp:453-455) and the fact that the plain solve path ignores
- * `rank`.  LHF_S is served on the device; LHF_SH / LHF_M / LHF_MH return
- * LHF_BAD_PREC with a message.
+ * `rank`.  All four operations run on the device: LHF_S = prec_solve, LHF_SH =
+ * prec_solve_tran (prec_solve.hpp:541-612), LHF_M / LHF_MH = prec_prod / prec_prod_tran
+ * (prec_prod.hpp:54-230).  The transposed operations are served by a transposed twin of
+ * the preconditioner built on first use (needs p_inv and q of every level).
  * nirs > 1 needs lhfdGpuSetMatrix. */
 LhfStatus lhfdGpuApply(LhfdGpuHdl hdl, LhfOperationType op, const double *b, int nirs,
                        const double *betas, int rank, double *x, int *ir_status);
@@ -156,6 +158,10 @@ LhfStatus lhfdGpuGmres(LhfdGpuHdl hdl, const double *b, int restart, double rtol
                        double *x, int *flag, int *iters);
 
 /* ---- the hot path, DEVICE buffers (asynchronous on the handle's stream) ---- */
+
+/* lhfdGpuApply on device buffers (no residual bounds): op in {LHF_S, LHF_SH, LHF_M, LHF_MH} */
+LhfStatus lhfdGpuApplyDev(LhfdGpuHdl hdl, LhfOperationType op, const double *d_b, int nirs, int rank,
+                          double *d_x);
 
 /* as lhfdGpuSolve with an explicit last-level rank: 0 = numerical rank,
  * (size_t)-1 = full (QRCP.hpp:376-377).  b and x may not alias. */

@@ -401,3 +401,241 @@ void hif_oracle_ccs_to_crs(const LhfdGpuCcs *A, int64_t *row_start, LhfInt *col_
     }
   free(next);
 }
+
+/* ======================================================================================
+ * Transpose solve and multilevel products: LHF_SH, LHF_M, LHF_MH
+ * ====================================================================================== */
+
+/* CCS::multiply_t_low -- CompressedStorage.hpp:2161-2178 : y = A^T x, one dot product per column */
+static void ccs_multiply_t(const LhfdGpuCcs *A, const double *x, double *y) {
+  for (size_t j = 0; j < A->ncols; ++j) {
+    double tmp = 0.0;
+    if (A->col_start)
+      for (LhfIndPtr k = A->col_start[j]; k < A->col_start[j + 1]; ++k) tmp += x[A->row_ind[k]] * A->vals[k];
+    y[j] = tmp;
+  }
+}
+
+/* CCS::solve_as_strict_upper_tran -- CompressedStorage.hpp:2399-2413 (forward, dot form) */
+static void ccs_solve_strict_upper_tran(const LhfdGpuCcs *U, double *y) {
+  if (!U->col_start) return;
+  for (size_t j = 1; j < U->ncols; ++j) {
+    double tmp = 0.0;
+    for (LhfIndPtr k = U->col_start[j]; k < U->col_start[j + 1]; ++k) tmp += U->vals[k] * y[U->row_ind[k]];
+    y[j] -= tmp;
+  }
+}
+
+/* CCS::solve_as_strict_lower_tran -- CompressedStorage.hpp:2307-2322 (backward, dot form) */
+static void ccs_solve_strict_lower_tran(const LhfdGpuCcs *L, double *y) {
+  if (!L->col_start || !L->ncols) return;
+  for (size_t j = L->ncols - 1; j != 0; --j) {
+    const size_t j1 = j - 1;
+    double       tmp = 0.0;
+    for (LhfIndPtr k = L->col_start[j1]; k < L->col_start[j1 + 1]; ++k) tmp += L->vals[k] * y[L->row_ind[k]];
+    y[j1] -= tmp;
+  }
+}
+
+/* internal::prec_solve_utdlt -- prec_solve.hpp:284-303 */
+static void solve_utdlt(const LhfdGpuLevel *P, double *y) {
+  if (!P->m) return;
+  ccs_solve_strict_upper_tran(&P->U_B, y);
+  for (size_t i = 0; i < P->m; ++i) y[i] /= P->d_B[i];
+  ccs_solve_strict_lower_tran(&P->L_B, y);
+}
+
+static size_t qr_rank(size_t nm, size_t num_rank, size_t rank) {
+  return rank == 0 ? num_rank : (rank > nm ? nm : rank);
+}
+
+/* x <- Q(:,1:rk) x(1:rk): dormqr('L','N') with rk reflectors = H_1 ... H_rk x (apply H_rk first) */
+static void qr_apply_q(size_t nm, size_t rk, const double *mat, const double *tau, double *x) {
+  for (size_t kk = rk; kk > 0; --kk) {
+    const size_t  k = kk - 1;
+    const double *v = mat + k * nm;
+    double        dot = x[k];
+    for (size_t i = k + 1; i < nm; ++i) dot += v[i] * x[i];
+    const double sigma = tau[k] * dot;
+    x[k] -= sigma;
+    for (size_t i = k + 1; i < nm; ++i) x[i] -= sigma * v[i];
+  }
+}
+static void qr_apply_qt(size_t nm, size_t rk, const double *mat, const double *tau, double *x) {
+  for (size_t k = 0; k < rk; ++k) {
+    const double *v = mat + k * nm;
+    double        dot = x[k];
+    for (size_t i = k + 1; i < nm; ++i) dot += v[i] * x[i];
+    const double sigma = tau[k] * dot;
+    x[k] -= sigma;
+    for (size_t i = k + 1; i < nm; ++i) x[i] -= sigma * v[i];
+  }
+}
+
+/* QRCP::_solve_t<1> -- QRCP.hpp:417-453 */
+void hif_oracle_qrcp_solve_t(size_t nm, size_t num_rank, const double *mat, const double *tau,
+                             const LhfInt *jpvt, size_t rank, double *x) {
+  const size_t rk = qr_rank(nm, num_rank, rank);
+  double *     w  = (double *)calloc(nm ? nm : 1, sizeof(double));
+  for (size_t i = 0; i < rk; ++i) w[i] = x[jpvt[i] - 1];
+  /* dtrsv('U','C','N'): forward substitution with R^T, dot form (reference BLAS) */
+  for (size_t j = 0; j < rk; ++j) {
+    double temp = w[j];
+    for (size_t i = 0; i < j; ++i) temp -= mat[i + j * nm] * w[i];
+    w[j] = temp / mat[j + j * nm];
+  }
+  qr_apply_q(nm, rk, mat, tau, w);
+  memcpy(x, w, sizeof(double) * nm);
+  free(w);
+}
+
+/* QRCP::_multiply_nt<1> -- QRCP.hpp:459-492 : x <- Q R(1:rk,1:rk) (P^T x)(1:rk) */
+void hif_oracle_qrcp_multiply(size_t nm, size_t num_rank, const double *mat, const double *tau,
+                              const LhfInt *jpvt, size_t rank, double *x) {
+  const size_t rk = qr_rank(nm, num_rank, rank);
+  double *     w  = (double *)calloc(nm ? nm : 1, sizeof(double));
+  for (size_t i = 0; i < rk; ++i) w[i] = x[jpvt[i] - 1];
+  /* dtrmv('U','N','N'), reference BLAS column form */
+  for (size_t j = 0; j < rk; ++j) {
+    if (w[j] != 0.0) {
+      const double temp = w[j];
+      for (size_t i = 0; i < j; ++i) w[i] += temp * mat[i + j * nm];
+      w[j] *= mat[j + j * nm];
+    }
+  }
+  qr_apply_q(nm, rk, mat, tau, w);
+  memcpy(x, w, sizeof(double) * nm);
+  free(w);
+}
+
+/* QRCP::_multiply_t<1> -- QRCP.hpp:494-540 : x <- P [R^T (Q^T x)(1:rk) ; 0] */
+void hif_oracle_qrcp_multiply_t(size_t nm, size_t num_rank, const double *mat, const double *tau,
+                                const LhfInt *jpvt, size_t rank, double *x) {
+  const size_t rk = qr_rank(nm, num_rank, rank);
+  qr_apply_qt(nm, rk, mat, tau, x);
+  /* dtrmv('U','C','N'), reference BLAS: j descending, dot with rows i < j (descending) */
+  for (size_t jj = rk; jj > 0; --jj) {
+    const size_t j = jj - 1;
+    double       temp = x[j] * mat[j + j * nm];
+    for (size_t ii = j; ii > 0; --ii) temp += mat[(ii - 1) + j * nm] * x[ii - 1];
+    x[j] = temp;
+  }
+  double *w = (double *)calloc(nm ? nm : 1, sizeof(double));
+  for (size_t i = 0; i < rk; ++i) w[jpvt[i] - 1] = x[i];
+  memcpy(x, w, sizeof(double) * nm);
+  free(w);
+}
+
+/* prec_solve_tran -- prec_solve.hpp:541-612 */
+static void prec_solve_tran(size_t nlevels, const LhfdGpuLevel *lv, size_t l, const double *b, size_t rank,
+                            double *y, double *work) {
+  const LhfdGpuLevel *P = lv + l;
+  const size_t        m = P->m, n = P->n, nm = n - m;
+  const int last = (P->dense_n != 0) || (m == n) || (l + 1 == nlevels);
+  for (size_t i = 0; i < m; ++i) work[i] = P->t[P->q[i]] * b[P->q[i]];
+  if (P->F.ncols) {
+    solve_utdlt(P, work);
+    ccs_multiply_t(&P->F, work, y + m);
+    for (size_t i = m; i < n; ++i) y[i] = P->t[P->q[i]] * b[P->q[i]] - y[i];
+  } else if (nm)
+    for (size_t i = m; i < n; ++i) y[i] = P->t[P->q[i]] * b[P->q[i]];
+  if (last) {
+    if (nm) hif_oracle_qrcp_solve_t(P->dense_n, P->dense_rank, P->qr_mat, P->qr_tau, P->qr_jpvt, rank, y + m);
+  } else {
+    memcpy(work + m, y + m, sizeof(double) * nm);
+    prec_solve_tran(nlevels, lv, l + 1, work + m, rank, y + m, work + n);
+  }
+  memcpy(work + m, y + m, sizeof(double) * nm);
+  if (nm) {
+    ccs_multiply_t(&P->E, y + m, work);
+    for (size_t i = 0; i < m; ++i) work[i] = P->t[P->q[i]] * b[P->q[i]] - work[i];
+  } else
+    for (size_t i = 0; i < m; ++i) work[i] = P->t[P->q[i]] * b[P->q[i]];
+  solve_utdlt(P, work);
+  for (size_t i = 0; i < n; ++i) y[i] = P->s[i] * work[P->p_inv[i]];
+}
+
+/* prec_prod -- prec_prod.hpp:54-134 */
+static void prec_prod(size_t nlevels, const LhfdGpuLevel *lv, size_t l, const double *b, size_t rank, double *y,
+                      double *work) {
+  const LhfdGpuLevel *P = lv + l;
+  const size_t        m = P->m, n = P->n, nm = n - m;
+  const int last = (P->dense_n != 0) || (m == n) || (l + 1 == nlevels);
+  for (size_t i = m; i < n; ++i) work[i] = b[P->q[i]] / P->t[P->q[i]];
+  if (last) {
+    if (nm) {
+      memcpy(y + m, work + m, sizeof(double) * nm);
+      hif_oracle_qrcp_multiply(P->dense_n, P->dense_rank, P->qr_mat, P->qr_tau, P->qr_jpvt, rank, y + m);
+    }
+  } else
+    prec_prod(nlevels, lv, l + 1, work + m, rank, y + m, work + n);
+  for (size_t i = 0; i < m; ++i) work[i] = b[P->q[i]] / P->t[P->q[i]];
+  ccs_multiply(&P->U_B, work, y);
+  for (size_t i = 0; i < m; ++i) y[i] = (y[i] + work[i]) * P->d_B[i];
+  ccs_multiply(&P->L_B, y, work);
+  for (size_t i = 0; i < m; ++i) work[i] += y[i];
+  if (P->F.ncols) {
+    ccs_multiply(&P->F, work + m, y);
+    for (size_t i = 0; i < m; ++i) work[i] += y[i];
+  }
+  if (nm) {
+    solve_ldu(P, y);
+    for (size_t i = 0; i < m; ++i) y[i] += b[P->q[i]] / P->t[P->q[i]];
+    ccs_multiply(&P->E, y, work + m);
+    for (size_t i = m; i < n; ++i) work[i] += y[i];
+  }
+  for (size_t i = 0; i < n; ++i) y[i] = work[P->p_inv[i]] / P->s[i];
+}
+
+/* prec_prod_tran -- prec_prod.hpp:148-230 */
+static void prec_prod_tran(size_t nlevels, const LhfdGpuLevel *lv, size_t l, const double *b, size_t rank,
+                           double *y, double *work) {
+  const LhfdGpuLevel *P = lv + l;
+  const size_t        m = P->m, n = P->n, nm = n - m;
+  const int last = (P->dense_n != 0) || (m == n) || (l + 1 == nlevels);
+  for (size_t i = m; i < n; ++i) work[i] = b[P->p[i]] / P->s[P->p[i]];
+  if (last) {
+    if (nm) {
+      memcpy(y + m, work + m, sizeof(double) * nm);
+      hif_oracle_qrcp_multiply_t(P->dense_n, P->dense_rank, P->qr_mat, P->qr_tau, P->qr_jpvt, rank, y + m);
+    }
+  } else
+    prec_prod_tran(nlevels, lv, l + 1, work + m, rank, y + m, work + n);
+  for (size_t i = 0; i < m; ++i) work[i] = b[P->p[i]] / P->s[P->p[i]];
+  ccs_multiply_t(&P->L_B, work, y);
+  for (size_t i = 0; i < m; ++i) y[i] = (y[i] + work[i]) * P->d_B[i];
+  ccs_multiply_t(&P->U_B, y, work);
+  for (size_t i = 0; i < m; ++i) work[i] += y[i];
+  if (nm) {
+    ccs_multiply_t(&P->E, work + m, y);
+    for (size_t i = 0; i < m; ++i) work[i] += y[i];
+  }
+  if (nm) {
+    solve_utdlt(P, y);
+    for (size_t i = 0; i < m; ++i) y[i] += b[P->p[i]] / P->s[P->p[i]];
+    ccs_multiply_t(&P->F, y, work + m);
+    for (size_t i = m; i < n; ++i) work[i] += y[i];
+  }
+  for (size_t i = 0; i < n; ++i) y[i] = work[P->q_inv[i]] / P->t[i];
+}
+
+/* HIF::solve(trans=true) / HIF::mmultiply -- builder.hpp:409-423, 502-512
+ * op: 1 = S^H, 2 = M, 3 = M^H (LhfOperationType values) */
+int hif_oracle_apply_op(size_t nlevels, const LhfdGpuLevel *lv, int op, const double *b, size_t rank,
+                        double *x) {
+  if (!nlevels) return -1;
+  double *work = (double *)malloc(sizeof(double) * (hif_oracle_work_size(nlevels, lv) + 1));
+  if (!work) return -2;
+  if (op == 1)
+    prec_solve_tran(nlevels, lv, 0, b, rank, x, work);
+  else if (op == 2)
+    prec_prod(nlevels, lv, 0, b, rank, x, work);
+  else if (op == 3)
+    prec_prod_tran(nlevels, lv, 0, b, rank, x, work);
+  else {
+    free(work);
+    return -3;
+  }
+  free(work);
+  return 0;
+}

@@ -79,6 +79,14 @@ class OracleHif:
         assert rc == 0
         return x
 
+    def apply_op(self, op, b, rank=0):
+        """op 1 = S^H, 2 = M, 3 = M^H (prec_solve_tran / prec_prod / prec_prod_tran)"""
+        b = np.ascontiguousarray(b, dtype=np.float64)
+        x = np.empty_like(b)
+        rc = lib().hif_oracle_apply_op(C.c_size_t(self.nl), self._arr, C.c_int(op), _p(b), C.c_size_t(rank), _p(x))
+        assert rc == 0
+        return x
+
     def solve_mrhs(self, B, rank=0):
         """multi-RHS semantics = a loop of single solves"""
         return np.stack([self.solve(np.ascontiguousarray(B[:, k]), rank) for k in range(B.shape[1])], axis=1)

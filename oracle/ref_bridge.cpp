@@ -234,6 +234,24 @@ int hifref_mmultiply(const void *hdl, const double *x, double *y, std::size_t ra
   REF_CATCH
 }
 
+// the remaining lhf?Apply operations (libhifir.cpp:447-472): op 1 = S^H (solve, trans),
+// 2 = M (mmultiply), 3 = M^H (mmultiply, trans)   -- builder.hpp:409-423, 502-512
+int hifref_apply_op(const void *hdl, int op, const double *b, double *x, std::size_t rank) {
+  REF_TRY
+  const auto *h = static_cast<const RefHandle *>(hdl);
+  const array_t bb(h->n, const_cast<double *>(b), true);
+  array_t       xx(h->n, x, true);
+  if (op == 1)
+    h->M.solve(bb, xx, true, rank);
+  else if (op == 2)
+    h->M.mmultiply(bb, xx, false, rank);
+  else if (op == 3)
+    h->M.mmultiply(bb, xx, true, rank);
+  else
+    throw std::invalid_argument("bad op");
+  REF_CATCH
+}
+
 // HIF::hifir fixed-count variant (builder.hpp:458-465), A = the matrix given at create
 int hifref_hifir(const void *hdl, const double *b, std::size_t N, double *x,
                  std::size_t rank) {

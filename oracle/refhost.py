@@ -173,6 +173,15 @@ class RefHif:
         self._chk(lib().hifref_mmultiply(self._h, _p(x), _p(y), rank))
         return y
 
+    def apply_op(self, op, b, rank=0):
+        """op 1 = S^H (solve trans), 2 = M (mmultiply), 3 = M^H -- LhfOperationType values"""
+        b = np.ascontiguousarray(b, dtype=np.float64)
+        x = np.empty_like(b)
+        f = lib().hifref_apply_op
+        f.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t]
+        self._chk(f(self._h, op, _p(b), _p(x), rank))
+        return x
+
     def hifir(self, b, nirs, rank=FULL_RANK):
         b = np.ascontiguousarray(b, dtype=np.float64)
         x = np.empty_like(b)

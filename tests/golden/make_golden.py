@@ -41,6 +41,10 @@ def make_case(name, A, params, dense_thres=0, nsp=False, b_krylov=None, restart=
     out["X"] = np.stack([M.solve(B[:, k].copy()) for k in range(4)], axis=1)
     out["X_full"] = np.stack([M.solve(B[:, k].copy(), R.FULL_RANK) for k in range(4)], axis=1)
     b = B[:, 0].copy()
+    if not nsp:  # the other lhf?Apply operations: S^H, M, M^H (numerical and full rank)
+        for op, key in ((1, "x_SH"), (2, "x_M"), (3, "x_MH")):
+            out[key] = M.apply_op(op, b)
+            out[key + "_full"] = M.apply_op(op, b, R.FULL_RANK)
     out["x_hifir3"] = M.hifir(b, 3)
     if b_krylov is None:
         b_krylov = P.csr_matvec(A, np.ones(n))

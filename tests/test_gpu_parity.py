@@ -65,10 +65,34 @@ def test_apply_semantics_follow_libhifir(golden):
         riters, rflag = (int(v) for v in golden["hifir_betas_status"])
         assert flag == rflag and abs(iters - riters) <= 1
         assert relerr(x, golden["x_hifir_betas"]) <= 1e-8
-        for op in (hb.LHF_SH, hb.LHF_M, hb.LHF_MH):
-            with pytest.raises(hb.LhfError) as e:
-                G.apply(b, op=op)
-            assert e.value.status == hb.LHF_BAD_PREC
+        with pytest.raises(hb.LhfError) as e:
+            G.apply(b, op=7)
+        assert e.value.status == hb.LHF_BAD_PREC
+
+
+def test_other_operations_match_golden_and_oracle(golden):
+    """LHF_SH / LHF_M / LHF_MH on the device (prec_solve.hpp:541-612, prec_prod.hpp:54-230) against the
+    reference's golden vectors and the C oracle; then the on-device round trips M (M^-1 b) = b and
+    M^H (M^-H b) = b (libhifir/tests/test_real.c:146)."""
+    import torch
+    if golden.nsp:
+        pytest.skip("fixture made with the null-space filter")
+    Oh = O.OracleHif(golden.levels, golden.A)
+    with _gpu(golden) as G:
+        b = np.ascontiguousarray(golden["B"][:, 0])
+        for op, key in ((hb.LHF_SH, "x_SH"), (hb.LHF_M, "x_M"), (hb.LHF_MH, "x_MH")):
+            x, _ = G.apply(b, op=op)
+            assert relerr(x, golden[key]) <= TOL_F64, key
+            assert relerr(x, Oh.apply_op(int(op), b)) <= TOL_F64, key
+        x, _ = G.apply(b)  # the primary orientation still works after the twin was built
+        assert relerr(x, golden["X"][:, 0]) <= TOL_F64
+        db = torch.from_numpy(b).cuda()
+        dx, dy = torch.empty_like(db), torch.empty_like(db)
+        for s_op, m_op in ((hb.LHF_S, hb.LHF_M), (hb.LHF_SH, hb.LHF_MH)):
+            G.apply_dev(db.data_ptr(), dx.data_ptr(), op=s_op)
+            G.apply_dev(dx.data_ptr(), dy.data_ptr(), op=m_op)
+            G.synchronize()
+            assert relerr(dy.cpu().numpy(), b) <= 1e-10
 
 
 def test_full_rank_device_solve(golden):

@@ -36,6 +36,18 @@ def test_port_hifir_matches_golden(golden):
     assert relerr(x, golden["x_hifir_betas"]) <= 1e-10
 
 
+def test_port_other_operations_match_golden(golden):
+    """lhf?Apply's other operations (libhifir.cpp:447-472): S^H = prec_solve_tran (prec_solve.hpp:541-612),
+    M / M^H = prec_prod / prec_prod_tran (prec_prod.hpp:54-230), numerical and full last-level rank."""
+    if golden.nsp:
+        pytest.skip("fixture made with the null-space filter; the reference has no transposed filter set")
+    Oh = _oracle(golden)
+    b = np.ascontiguousarray(golden["B"][:, 0])
+    for op, key in ((1, "x_SH"), (2, "x_M"), (3, "x_MH")):
+        assert relerr(Oh.apply_op(op, b), golden[key]) <= PORT_TOL
+        assert relerr(Oh.apply_op(op, b, O.FULL_RANK), golden[key + "_full"]) <= PORT_TOL
+
+
 @pytest.mark.parametrize("which", ["fgmres", "gmres"])
 def test_port_krylov_matches_golden(golden, which):
     if which == "gmres" and golden.name == "stokes28_ml":
