@@ -179,7 +179,8 @@ def debug_simulate_sweep(block, upper, slots=296, threads=448, t_load=1.7, c_s=0
     prm = np.array([slots, threads, t_load, c_s, c_g, t_dep, t_pub], dtype=np.float64)
     out = np.zeros(8)
     _chk(lib().lhfdGpuDebugSimulateSweep(C.byref(c), int(upper), _ptr(prm), _ptr(out)))
-    return dict(zip(("total", "life_sum", "life_max", "halo_wait", "tail", "blocks"), out[:6]))
+    return dict(zip(("total", "life_sum", "life_max", "halo_wait", "tail", "blocks", "merged_depth", "slab_bytes"),
+                    out[:8]))
 
 
 def debug_block_graph(block, upper, max_blocks=1 << 16, max_edges=1 << 24):

@@ -62,10 +62,10 @@ __global__ void spmv_resid_kernel(const unsigned nrows, const unsigned *__restri
 
 // out[rowmap[u]] = base[rowmap[u]] - sum_j A(u,j) x[j] for the compact rows u of the split
 // forward sweep (x = tagged results of the lower blocks, all finished); 8 lanes per row
-__global__ void spmv_rows_kernel(const unsigned nu, const unsigned *__restrict__ ptr, const int *__restrict__ col,
-                                 const double *__restrict__ val, const unsigned long long *__restrict__ x,
-                                 const unsigned *__restrict__ rowmap, const double *__restrict__ base,
-                                 double *__restrict__ out) {
+__global__ void spmv_rows_kernel(const unsigned nu, const unsigned m, const unsigned *__restrict__ ptr,
+                                 const int *__restrict__ col, const double *__restrict__ val,
+                                 const unsigned long long *__restrict__ x, const unsigned *__restrict__ rowmap,
+                                 const double *__restrict__ base, double *__restrict__ out) {
   const unsigned gid = blockIdx.x * blockDim.x + threadIdx.x, u = gid >> 3, lane = gid & 7u;
   double         acc = 0.0;
   if (u < nu) {
@@ -74,9 +74,10 @@ __global__ void spmv_rows_kernel(const unsigned nu, const unsigned *__restrict__
   }
 #pragma unroll
   for (int o = 4; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-  if (u < nu && lane == 0) {
-    const unsigned i = rowmap[u];
-    out[i]           = base[i] - acc;
+  if (u < nu && lane == 0) {  // rowmap = row codes (hifgpu.h): out is indexed by solution slot
+    const unsigned code = rowmap[u], slot = code & kCodeSlotMask;
+    const double   b    = (code & kCodeZeroRhs) ? 0.0 : base[slot >= m ? slot - m : slot];
+    out[slot]           = b - acc;
   }
 }
 
@@ -228,13 +229,13 @@ void launch_sweeps(Handle *h, DevLevel &D, const double *rhs, unsigned long long
   if (D.L_up.nblocks) {
     const unsigned nu = static_cast<unsigned>(D.L_ul.nrows);
     spmv_rows_kernel<<<cdiv(static_cast<std::size_t>(nu) * 8, 256), 256, 0, h->stream>>>(
-        nu, D.L_ul.ptr.p, D.L_ul.col.p, D.L_ul.val.p, xL, D.L_urows.p, rhs, D.rhs_u.p);
+        nu, static_cast<unsigned>(D.m), D.L_ul.ptr.p, D.L_ul.col.p, D.L_ul.val.p, xL, D.L_urows.p, rhs, D.rhs_u.p);
     HIF_KERNEL_CHECK();
-    launch_sweep(h, D.L_up, D.rhs_u.p, nullptr, nullptr, xL, parity, tickets + 4);
+    launch_sweep(h, D.L_up, D.rhs_u.p, nullptr, nullptr, xL, parity, tickets + 4 * h->tick_stride);
     h->launch_count += 1;
   }
   mark(h, tag + "L");
-  launch_sweep(h, D.U, nullptr, xL, D.d.p, xU, parity, tickets + 1,
+  launch_sweep(h, D.U, nullptr, xL, D.d.p, xU, parity, tickets + h->tick_stride,
                tl && h->trace_which == trace_base + 1 ? h->trace_buf.p : nullptr);
   mark(h, tag + "U");
 }
@@ -283,7 +284,7 @@ void apply_dev(Handle *h, const double *d_b, double *d_x, std::size_t rank) {
       ++h->launch_count;
     }
     if (D.nm) {
-      launch_sweeps(h, D, D.bhat.p, D.xL_dn.p, D.xU_dn.p, parity, h->tickets.p + 8 * l,
+      launch_sweeps(h, D, D.bhat.p, D.xL_dn.p, D.xU_dn.p, parity, h->tick(8 * l),
                     "lv" + std::to_string(l) + ".down.", 0);
       launch_spmv_resid<true>(h, D.E, D.xU_dn.p, D.bhat.p + D.m, D.r.p, "lv" + std::to_string(l) + ".E");
       b = D.r.p;
@@ -304,7 +305,7 @@ void apply_dev(Handle *h, const double *d_b, double *d_x, std::size_t rank) {
       launch_spmv_resid<false>(h, D.F, D.ychild.p, D.bhat.p, D.g.p, "lv" + std::to_string(l) + ".F");
       rhs = D.g.p;
     }
-    launch_sweeps(h, D, rhs, D.xL_up.p, D.xU_up.p, parity, h->tickets.p + 8 * l + 2,
+    launch_sweeps(h, D, rhs, D.xL_up.p, D.xU_up.p, parity, h->tick(8 * l + 2),
                   "lv" + std::to_string(l) + ".up.", 2);
     if (D.n) {
       scatter_scale_kernel<<<cdiv(D.n, T), T, 0, h->stream>>>(static_cast<unsigned>(D.n), static_cast<unsigned>(D.m),

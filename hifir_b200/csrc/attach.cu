@@ -176,7 +176,7 @@ Handle *attach_levels(int device, std::size_t nlevels, const LhfdGpuLevel *lv, b
       build_split_plans(Lr, D.L, D.L_up, ul, urows, tally);
       upload_csr(ul, D.L_ul, tally);
       D.L_urows.upload(urows, tally);
-      D.rhs_u.alloc(P.m, tally);
+      D.rhs_u.alloc(2 * P.m, tally);
     }
     build_sweep_plan(Ur, true, D.U, tally);
     D.L.nnz = Lr.col.size();
@@ -207,10 +207,11 @@ Handle *attach_levels(int device, std::size_t nlevels, const LhfdGpuLevel *lv, b
     D.q_inv.upload(reinterpret_cast<const int *>(P.q_inv), P.n, tally);
 
     D.bhat.alloc(P.n, tally);
-    D.xL_dn.alloc(P.m, tally);
-    D.xU_dn.alloc(P.m, tally);
-    D.xL_up.alloc(P.m, tally);
-    D.xU_up.alloc(P.m, tally);
+    // tagged sweep results: m solution slots + m slots for the auxiliary unknowns of merge.cu
+    D.xL_dn.alloc(2 * P.m, tally);
+    D.xU_dn.alloc(2 * P.m, tally);
+    D.xL_up.alloc(2 * P.m, tally);
+    D.xU_up.alloc(2 * P.m, tally);
     D.g.alloc(P.m, tally);
     D.r.alloc(D.nm, tally);
     D.ychild.alloc(D.nm, tally);
@@ -255,7 +256,10 @@ Handle *attach_levels(int device, std::size_t nlevels, const LhfdGpuLevel *lv, b
     h->nnz_total += nm * nm;
   }
 
-  h->tickets.alloc(8 * nlevels + 8, tally);
+  for (const DevLevel &D : h->levels)
+    h->tick_stride = std::max<std::size_t>(
+        {h->tick_stride, kSyncStride * (2 + D.L.st_depth), kSyncStride * (2 + D.U.st_depth)});
+  h->tickets.alloc((8 * nlevels + 8) * h->tick_stride, tally);
   h->error_flag.alloc(1, tally);
   HIF_CUDA(cudaMallocHost(&h->h_error, sizeof(int)));
   *h->h_error = 0;

@@ -66,12 +66,48 @@ struct HostCsr {
   std::vector<unsigned> ptr;
   std::vector<int>      col;
   std::vector<double>   val;
+  // "sweep form" of a triangular factor (merge.cu): rows in sweep order, every entry references
+  // an earlier row, and gid[r] is the ROW CODE of row r (empty = identity):
+  //   bits 0..30  slot of the row's result in the tagged solution buffer (2 * orig_rows slots:
+  //               [0, orig_rows) the solution itself, [orig_rows, 2 orig_rows) auxiliary unknowns)
+  //   bit 31      the row's right-hand side is zero
+  // right-hand side index of a row = slot < orig_rows ? slot : slot - orig_rows
+  std::vector<unsigned> gid;
+  std::size_t           orig_rows = 0;
 };
+constexpr unsigned kSyncStride = 32;  // ints between two level counters of a streaming sweep (stream.cu)
+constexpr unsigned kCodeZeroRhs = 0x80000000u, kCodeSlotMask = 0x7fffffffu;
+
+// algebraic level merging (merge.cu)
+struct MergeParams {
+  bool     enabled   = true;
+  double   gain      = 100000.0;  // fill (in nonzeros) one saved dependent step may cost
+  unsigned row_cap   = 128;       // longest row of an inverted diagonal block
+  unsigned bmax      = 64;        // most level sets merged into one super level
+  double   row_cost  = 2.0;       // cost of one auxiliary row, in nonzeros
+  static MergeParams from_env();
+};
+struct MergeStats {
+  std::size_t rows = 0, ext_rows = 0, nnz = 0, ext_nnz = 0, depth = 0, ext_depth = 0, super_levels = 0;
+};
+HostCsr to_sweep_form(const HostCsr &T, bool upper);
+HostCsr merge_levels(const HostCsr &S, const MergeParams &prm, MergeStats *st);
 
 // a strictly triangular factor cut into shared-memory sized slabs (sptrsv.cu)
 struct SweepPlan {
   unsigned               m = 0, nblocks = 0, smem_bytes = 0, nr = 1;  // nr: right-hand sides per slot
   bool                   upper = false;
+  bool                   rhs_by_slot = false;  // right-hand side indexed by the row's slot (split sweep, top rows)
+  MergeStats             merge;
+  // level-major streaming layout (stream.cu); nblocks = number of 32-row slices
+  bool                        stream = false;
+  std::size_t                 st_depth = 0, st_padded = 0;
+  unsigned                    st_chunks = 0;  // 8 slices each, all of one level set
+  DevBuf<unsigned>            st_need;   // chunks per level set
+  DevBuf<unsigned>            st_sdesc;  // uint4 per slice: offset (units of 32 entries), entries per lane, log2 lanes per row, level
+  DevBuf<unsigned>            st_codes;  // 32 row codes per slice
+  DevBuf<unsigned>            st_cols;   // solution slot of every entry, slice-interleaved
+  DevBuf<double>              st_vals;
   std::size_t            slab_bytes = 0, halo_total = 0, nnz = 0;
   DevBuf<unsigned char>  slabs;  // packed slabs
   DevBuf<unsigned char>  info;   // SlabInfo[nblocks]
@@ -153,7 +189,11 @@ struct Handle {
   std::vector<LhfInt>    hA_idx;
   std::vector<double>    hA_val;
   bool                   hA_rowmajor = true;
-  DevBuf<int>           tickets;          // one block-ticket counter per sweep of an apply
+  // per sweep of an apply: a ticket counter + the level-completion counters of stream.cu
+  // (tick_stride ints per sweep, zeroed once per apply)
+  DevBuf<int>           tickets;
+  std::size_t           tick_stride = 1;
+  int *                 tick(std::size_t sweep) const { return tickets.p + sweep * tick_stride; }
   DevBuf<int>           error_flag;       // set by a sweep whose spin limit tripped
   int *                 h_error = nullptr;  // pinned mirror
   // scratch for host-buffer entry points / IR / Krylov
@@ -195,6 +235,13 @@ void sweep_block_graph(const HostCsr &T, bool upper, std::vector<unsigned> &info
 void build_split_plans(const HostCsr &T, SweepPlan &plan_lo, SweepPlan &plan_up, HostCsr &ul,
                        std::vector<unsigned> &urows, std::size_t *tally);
 void sweep_simulate(const HostCsr &T, bool upper, const double *prm, double *out);
+bool stream_sweeps();  // HIFIR_B200_SWEEP=stream (default) | slab
+void build_stream_plan(const HostCsr &S, bool upper, SweepPlan &plan, std::size_t *tally);
+void stream_host_emulate(const HostCsr &S, bool upper, const double *rhs, const double *diag, double *x,
+                         std::size_t stats[4]);
+void launch_stream_sweep(Handle *h, const SweepPlan &plan, const double *rhs_plain,
+                         const unsigned long long *rhs_tagged, const double *diag, unsigned long long *x,
+                         unsigned parity, int *ticket, unsigned long long *trace = nullptr);
 void launch_sweep(Handle *h, const SweepPlan &plan, const double *rhs_plain, const unsigned long long *rhs_tagged,
                   const double *diag, unsigned long long *x, unsigned parity, int *ticket,
                   unsigned long long *trace = nullptr);

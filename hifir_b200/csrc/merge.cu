@@ -1,0 +1,240 @@
+// merge.cu -- algebraic level merging of a triangular factor (attach time, host only).
+//
+// The factors of the reference have dependency depth 700-2500 while a
+// sweep moves only ~200 MB: executed row by row, CCS::solve_as_strict_lower / _upper
+// (ds/CompressedStorage.hpp:2267-2279, 2356-2369) are bound by the LATENCY of that chain on
+// any parallel machine.  The chain is shortened here by an exact reformulation:
+//
+//   * level sets are grouped into SUPER LEVELS [l0, l1].  Split T = I + N + X with N = the
+//     entries that connect two rows of the same super level, X = the rest (they reference
+//     earlier super levels).  W = I + N is block diagonal over the super levels and
+//       T x = b   <=>   t = b - X x ,  x = W^{-1} t .
+//   * W^{-1} = sum_k (-N)^k is formed explicitly, row by row (N is nilpotent of order
+//     <= levels per super level).  Its rows stay short because a super level is closed as soon
+//     as the fill of the next level set would cost more than the dependent step it saves.
+//   * The result is again a unit lower triangular system ("sweep form") in the unknowns
+//     [.., t_i, x_i, ..]: a row with in-level dependencies becomes two rows (t_i: the
+//     cross-level part, x_i: -t_i - sum_j Winv_ij t_j with zero right-hand side), any other
+//     row is unchanged.  The sweep kernels of sptrsv.cu run it as they run the original; its
+//     depth is <= 2 per super level instead of one per level set.
+//
+// Nothing is approximated: the difference to the reference's substitution is rounding only
+// (the inverse-based dropping of HIF bounds ||L^{-1}||, ||U^{-1}|| by kappa, so the diagonal
+// blocks W are well conditioned).
+#include <algorithm>
+#include <cstdlib>
+#include <stdexcept>
+
+#include "hifgpu.h"
+
+namespace hifgpu {
+
+MergeParams MergeParams::from_env() {
+  MergeParams p;
+  if (const char *e = std::getenv("HIFIR_B200_MERGE")) p.enabled = std::atoi(e) != 0;
+  if (const char *e = std::getenv("HIFIR_B200_MERGE_GAIN")) p.gain = std::atof(e);
+  if (const char *e = std::getenv("HIFIR_B200_MERGE_ROWCAP")) p.row_cap = static_cast<unsigned>(std::atoi(e));
+  if (const char *e = std::getenv("HIFIR_B200_MERGE_BMAX")) p.bmax = static_cast<unsigned>(std::atoi(e));
+  if (const char *e = std::getenv("HIFIR_B200_MERGE_ROWCOST")) p.row_cost = std::atof(e);
+  return p;
+}
+
+// Rows in sweep order (forward for L, backward for U), every entry references an EARLIER row,
+// entries of a row in the order the reference's column sweep applies them.
+HostCsr to_sweep_form(const HostCsr &T, bool upper) {
+  const unsigned m = static_cast<unsigned>(T.nrows);
+  HostCsr        S;
+  S.nrows = S.ncols = m;
+  S.orig_rows       = m;
+  S.gid.resize(m);
+  if (!upper) {
+    S.ptr = T.ptr;
+    S.col = T.col;
+    S.val = T.val;
+    S.ptr.resize(m + 1, S.ptr.empty() ? 0u : S.ptr.back());
+    for (unsigned i = 0; i < m; ++i) S.gid[i] = i;
+    return S;
+  }
+  S.ptr.assign(m + 1, 0u);
+  S.col.resize(T.col.size());
+  S.val.resize(T.val.size());
+  unsigned w = 0;
+  for (unsigned s = 0; s < m; ++s) {
+    const unsigned i = m - 1u - s;
+    S.ptr[s]         = w;
+    for (unsigned k = T.ptr[i + 1]; k-- > T.ptr[i];) {
+      S.col[w] = static_cast<int>(m - 1u - static_cast<unsigned>(T.col[k]));
+      S.val[w] = T.val[k];
+      ++w;
+    }
+    S.gid[s] = i;
+  }
+  S.ptr[m] = w;
+  return S;
+}
+
+static unsigned depth_of(const HostCsr &S, std::vector<unsigned> &lev) {
+  const unsigned m = static_cast<unsigned>(S.nrows);
+  lev.assign(m, 0u);
+  unsigned depth = 0;
+  for (unsigned i = 0; i < m; ++i) {
+    unsigned l = 0;
+    for (unsigned k = S.ptr[i]; k < S.ptr[i + 1]; ++k) l = std::max(l, lev[S.col[k]] + 1u);
+    lev[i] = l;
+    depth  = std::max(depth, l + 1u);
+  }
+  return depth;
+}
+
+HostCsr merge_levels(const HostCsr &S, const MergeParams &prm, MergeStats *st) {
+  const unsigned m = static_cast<unsigned>(S.nrows);
+  if (S.gid.size() != m || S.orig_rows != m) throw std::logic_error("merge_levels: input is not in sweep form");
+  std::vector<unsigned> lev;
+  const unsigned        depth = depth_of(S, lev);
+  if (st) {
+    st->rows  = m;
+    st->nnz   = S.col.size();
+    st->depth = depth;
+  }
+  // rows bucketed by level set
+  std::vector<unsigned> lptr(depth + 1u, 0u), lrows(m);
+  for (unsigned i = 0; i < m; ++i) ++lptr[lev[i] + 1u];
+  for (unsigned l = 0; l < depth; ++l) lptr[l + 1] += lptr[l];
+  {
+    std::vector<unsigned> next(lptr.begin(), lptr.end() - 1);
+    for (unsigned i = 0; i < m; ++i) lrows[next[lev[i]]++] = i;
+  }
+  // ---- greedy super levels; rows of W^{-1} - I (strictly lower part) per row
+  std::vector<unsigned>    sl0(m, 0u);  // first level set of the row's super level
+  std::vector<std::size_t> wbeg(m, 0);
+  std::vector<unsigned>    wlen(m, 0u);
+  std::vector<unsigned>    wcol;
+  std::vector<double>      wval;
+  wcol.reserve(S.col.size());
+  wval.reserve(S.col.size());
+  std::vector<double>   acc(m, 0.0);
+  std::vector<unsigned> stamp(m, 0u), touched, tcol, tlen;
+  std::vector<double>   tval;
+  unsigned              cur = 0, l0 = 0;
+  auto close_super = [&](unsigned lend) {  // super level [l0, lend) ends
+    // two merged level sets save nothing (t and x steps instead of two x steps): undo
+    if (lend - l0 == 2u)
+      for (unsigned q = lptr[l0 + 1]; q < lptr[l0 + 2]; ++q) {
+        const unsigned i = lrows[q];
+        wlen[i]          = 0;
+        sl0[i]           = l0 + 1u;
+      }
+  };
+  for (unsigned l = 0; l < depth; ++l) {
+    const unsigned rb = lptr[l], re = lptr[l + 1];
+    bool           accept = false;
+    if (prm.enabled && l > l0 && l - l0 < prm.bmax) {
+      tcol.clear();
+      tval.clear();
+      tlen.assign(re - rb, 0u);
+      double   cost = 0.0;
+      unsigned maxlen = 0;
+      for (unsigned q = rb; q < re && maxlen <= prm.row_cap; ++q) {
+        const unsigned i = lrows[q];
+        ++cur;
+        touched.clear();
+        unsigned nwithin = 0;
+        auto     add = [&](unsigned j, double v) {
+          if (stamp[j] != cur) {
+            stamp[j] = cur;
+            acc[j]   = 0.0;
+            touched.push_back(j);
+          }
+          acc[j] += v;
+        };
+        for (unsigned k = S.ptr[i]; k < S.ptr[i + 1]; ++k) {
+          const unsigned j = static_cast<unsigned>(S.col[k]);
+          if (lev[j] < l0) continue;
+          ++nwithin;
+          const double v = -S.val[k];  // row i of -N times (I + (W^{-1} - I))
+          add(j, v);
+          for (std::size_t w = wbeg[j], we = wbeg[j] + wlen[j]; w < we; ++w) add(wcol[w], v * wval[w]);
+        }
+        std::sort(touched.begin(), touched.end());
+        for (unsigned j : touched) {
+          tcol.push_back(j);
+          tval.push_back(acc[j]);
+        }
+        tlen[q - rb] = static_cast<unsigned>(touched.size());
+        if (nwithin) cost += static_cast<double>(touched.size()) - nwithin + 1.0 + prm.row_cost;
+        maxlen = std::max<unsigned>(maxlen, static_cast<unsigned>(touched.size()) + 1u);
+      }
+      accept = maxlen <= prm.row_cap && cost <= prm.gain;
+    }
+    if (accept) {
+      std::size_t tp = 0;
+      for (unsigned q = rb; q < re; ++q) {
+        const unsigned i = lrows[q];
+        wbeg[i]          = wcol.size();
+        wlen[i]          = tlen[q - rb];
+        wcol.insert(wcol.end(), tcol.begin() + tp, tcol.begin() + tp + wlen[i]);
+        wval.insert(wval.end(), tval.begin() + tp, tval.begin() + tp + wlen[i]);
+        tp += wlen[i];
+        sl0[i] = l0;
+      }
+    } else {
+      if (l > 0) close_super(l);
+      l0 = l;
+      for (unsigned q = rb; q < re; ++q) sl0[lrows[q]] = l0;
+    }
+  }
+  if (depth) close_super(depth);
+  // ---- the merged system, rows interleaved [.., t_i, x_i, ..] in the original sweep order
+  HostCsr E;
+  E.orig_rows = m;
+  E.ptr.push_back(0u);
+  std::vector<unsigned> xpos(m), tpos(m);
+  for (unsigned i = 0; i < m; ++i) {
+    if (!wlen[i]) {
+      for (unsigned k = S.ptr[i]; k < S.ptr[i + 1]; ++k) {
+        const unsigned j = static_cast<unsigned>(S.col[k]);
+        if (lev[j] >= sl0[i]) throw std::logic_error("merge_levels: in-level entry on an unsplit row");
+        E.col.push_back(static_cast<int>(xpos[j]));
+        E.val.push_back(S.val[k]);
+      }
+      xpos[i] = tpos[i] = static_cast<unsigned>(E.gid.size());
+      E.gid.push_back(S.gid[i]);
+      E.ptr.push_back(static_cast<unsigned>(E.col.size()));
+      continue;
+    }
+    // t_i = b_i - sum_{j in earlier super levels} T_ij x_j
+    for (unsigned k = S.ptr[i]; k < S.ptr[i + 1]; ++k) {
+      const unsigned j = static_cast<unsigned>(S.col[k]);
+      if (lev[j] >= sl0[i]) continue;
+      E.col.push_back(static_cast<int>(xpos[j]));
+      E.val.push_back(S.val[k]);
+    }
+    tpos[i] = static_cast<unsigned>(E.gid.size());
+    E.gid.push_back(m + S.gid[i]);
+    E.ptr.push_back(static_cast<unsigned>(E.col.size()));
+    // x_i = t_i + sum_j Winv_ij t_j   (a sweep row computes rhs - sum val * x)
+    for (std::size_t w = wbeg[i], we = wbeg[i] + wlen[i]; w < we; ++w) {
+      E.col.push_back(static_cast<int>(tpos[wcol[w]]));
+      E.val.push_back(-wval[w]);
+    }
+    E.col.push_back(static_cast<int>(tpos[i]));
+    E.val.push_back(-1.0);
+    xpos[i] = static_cast<unsigned>(E.gid.size());
+    E.gid.push_back(S.gid[i] | kCodeZeroRhs);
+    E.ptr.push_back(static_cast<unsigned>(E.col.size()));
+  }
+  E.nrows = E.ncols = E.gid.size();
+  if (E.nrows > 0x7fffffffull || E.col.size() > 0xfffffff0ull) throw std::length_error("merged factor too large");
+  if (st) {
+    std::vector<unsigned> elev;
+    st->ext_rows     = E.nrows;
+    st->ext_nnz      = E.col.size();
+    st->ext_depth    = depth_of(E, elev);
+    std::vector<char> seen(depth + 1u, 0);
+    for (unsigned i = 0; i < m; ++i) seen[sl0[i]] = 1;
+    st->super_levels = static_cast<std::size_t>(std::count(seen.begin(), seen.end(), 1));
+  }
+  return E;
+}
+
+}  // namespace hifgpu

@@ -148,8 +148,8 @@ static void apply_chunk(Handle *h, const double *d_in, double *d_out, std::size_
     }
     if (D.nm) {
       if (D.m) {
-        launch_sweep(h, D.Lm, D.m_bhat.p, nullptr, nullptr, D.m_xL_dn.p, parity, h->tickets.p + 4 * l);
-        launch_sweep(h, D.Um, nullptr, D.m_xL_dn.p, D.d.p, D.m_xU_dn.p, parity, h->tickets.p + 4 * l + 1);
+        launch_sweep(h, D.Lm, D.m_bhat.p, nullptr, nullptr, D.m_xL_dn.p, parity, h->tick(4 * l));
+        launch_sweep(h, D.Um, nullptr, D.m_xL_dn.p, D.d.p, D.m_xU_dn.p, parity, h->tick(4 * l + 1));
       }
       spmv_resid_m_kernel<true><<<cdiv(D.nm * NR, T), T, 0, h->stream>>>(
           static_cast<unsigned>(D.nm), D.E.ptr.p, D.E.col.p, D.E.val.p, D.m_xU_dn.p, D.m_bhat.p + D.m * NR, D.m_r.p);
@@ -183,8 +183,8 @@ static void apply_chunk(Handle *h, const double *d_in, double *d_out, std::size_
       rhs = D.m_g.p;
     }
     if (D.m) {
-      launch_sweep(h, D.Lm, rhs, nullptr, nullptr, D.m_xL_up.p, parity, h->tickets.p + 4 * l + 2);
-      launch_sweep(h, D.Um, nullptr, D.m_xL_up.p, D.d.p, D.m_xU_up.p, parity, h->tickets.p + 4 * l + 3);
+      launch_sweep(h, D.Lm, rhs, nullptr, nullptr, D.m_xL_up.p, parity, h->tick(4 * l + 2));
+      launch_sweep(h, D.Um, nullptr, D.m_xL_up.p, D.d.p, D.m_xU_up.p, parity, h->tick(4 * l + 3));
     }
     if (D.n) {
       scatter_scale_m_kernel<<<cdiv(D.n * NR, T), T, 0, h->stream>>>(

@@ -100,8 +100,8 @@ void ensure_prod(Handle *h) {
     D.pw2.alloc(D.nm, tally);
     D.pf.alloc(D.m, tally);
     D.py.alloc(D.n, tally);
-    D.p_xL.alloc(D.m, tally);
-    D.p_xU.alloc(D.m, tally);
+    D.p_xL.alloc(2 * D.m, tally);
+    D.p_xU.alloc(2 * D.m, tally);
   }
   h->prod_ready = true;
 }
@@ -143,7 +143,7 @@ void prod_level(Handle *h, std::size_t l, const double *x, double *y, std::size_
       HIF_KERNEL_CHECK();
       ++h->launch_count;
       // z = (LDU)^{-1} f + w1                       (:120-124); z lives in pf
-      launch_ldu_solve(h, D, D.pf.p, D.p_xL.p, D.p_xU.p, parity, h->tickets.p + 8 * l);
+      launch_ldu_solve(h, D, D.pf.p, D.p_xL.p, D.p_xU.p, parity, h->tick(8 * l));
       add_tagged_kernel<<<cdiv(m, T), T, 0, h->stream>>>(m, D.p_xU.p, w1, D.pf.p);
       HIF_KERNEL_CHECK();
       ++h->launch_count;

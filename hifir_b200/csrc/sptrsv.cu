@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(T + kPollLanes, (T <= 256 ? 4 : 2))
                        const double *__restrict__ rhs_plain, const unsigned long long *rhs_tagged,
                        const double *__restrict__ diag, unsigned long long *x, const unsigned parity, int *ticket,
                        int *error_flag, unsigned long long *trace, const int backoff, const unsigned poll_sleep,
-                       const unsigned spin_burst, const int interleave) {
+                       const unsigned spin_burst, const int rhs_by_slot) {
   constexpr unsigned kThreads = T + kPollLanes;
   extern __shared__ __align__(16) unsigned char smem[];
   __shared__ unsigned                        s_blk, s_done;
@@ -144,9 +144,15 @@ __global__ void __launch_bounds__(T + kPollLanes, (T <= 256 ? 4 : 2))
   // right-hand side of a row: b_i (L sweep) or (L^{-1}b)_i / d_i with a true division
   // (prec_solve.hpp:219) for the U sweep; fetched one row ahead of its use
   const unsigned *gidx = reinterpret_cast<const unsigned *>(smem + slab_off_gidx(bi.rows));
+  // gidx[r] = row code (hifgpu.h): solution slot, zero-rhs flag; slots >= m are the auxiliary
+  // unknowns of the merged system (merge.cu), their right-hand side is that of row slot - m
   auto load_rhs = [&](unsigned r, unsigned &gi) -> double {
-    gi = gidx[r];
-    return UPPER ? tag_value(rhs_tagged[gi]) / diag[gi] : rhs_plain[gi];
+    const unsigned code = gidx[r];
+    gi                  = code & kCodeSlotMask;
+    if (rhs_by_slot) return rhs_plain[gi];
+    if (code & kCodeZeroRhs) return 0.0;
+    const unsigned ri = gi >= m ? gi - m : gi;
+    return UPPER ? tag_value(rhs_tagged[ri]) / diag[ri] : rhs_plain[ri];
   };
   __syncthreads();  // xs initialised
   while (!mbar_try_wait(&s_bar, 0)) {
@@ -169,7 +175,7 @@ __global__ void __launch_bounds__(T + kPollLanes, (T <= 256 ? 4 : 2))
     // does nothing but poll / consume / publish while any lane can advance; stepping a lane
     // to its next row (dependent shared loads, the right-hand side) is deferred to
     // iterations in which no lane of the warp had anything to consume.
-    unsigned q = interleave ? (tid & 31u) * (T / 32) + (tid >> 5) : tid;  // position in order[]
+    unsigned q = tid;  // position in order[]
     unsigned r = 0, gi = 0, gi_next = 0;
     double   acc = 0.0, acc_next = 0.0;
     unsigned k = 0, e = 0, polls = 0;
@@ -507,10 +513,13 @@ struct PackedSweep {
   unsigned                   max_smem = 0;
   std::size_t                halo_total = 0;
   unsigned                   block_depth = 0;
-  std::vector<unsigned>      perm, pos;  // sweep position -> natural row index, and back
+  std::vector<unsigned>      perm, pos;  // sweep position -> row of the sweep-form matrix, and back
+  std::vector<unsigned>      row_of_slot;  // solution slot -> row of the sweep-form matrix
 };
 }  // namespace
 
+// T is in SWEEP FORM (merge.cu: rows in sweep order, every entry references an earlier row,
+// T.gid = row codes).  `upper` only selects the ordering heuristic (fan-out instead of fan-in).
 // `rows_mask` (optional): pack only these rows of T; every entry of an included row must
 // then reference an included row (the caller splits the matrix accordingly).
 static void pack_sweep(const HostCsr &T, bool upper, PackedSweep &out, unsigned slot_bytes = 8u,
@@ -518,14 +527,15 @@ static void pack_sweep(const HostCsr &T, bool upper, PackedSweep &out, unsigned 
                        unsigned rows_max = kRowsMax) {
   const unsigned m = static_cast<unsigned>(T.nrows);
   if (!m) return;
+  if (T.gid.size() != m) throw std::logic_error("pack_sweep: factor is not in sweep form");
+  auto slot_of = [&](unsigned i) { return T.gid[i] & kCodeSlotMask; };
   std::vector<SlabInfo> &     infos = out.infos;
   std::vector<unsigned char> &buf   = out.buf;
   std::vector<unsigned>       stamp(m, 0u), slot(m, 0u);
   // dependency depth of every row (level set index), in sweep order
   std::vector<unsigned> lev(m, 0u);
-  for (unsigned s = 0; s < m; ++s) {
-    const unsigned i = upper ? m - 1u - s : s;
-    unsigned       l = 0;
+  for (unsigned i = 0; i < m; ++i) {
+    unsigned l = 0;
     for (unsigned k = T.ptr[i]; k < T.ptr[i + 1]; ++k) l = std::max(l, lev[T.col[k]] + 1u);
     lev[i] = l;
   }
@@ -546,8 +556,8 @@ static void pack_sweep(const HostCsr &T, bool upper, PackedSweep &out, unsigned 
   {
     const bool natural_order = std::getenv("HIFIR_B200_SWEEP_ORDER") &&
                                std::string(std::getenv("HIFIR_B200_SWEEP_ORDER")) == "natural";
-    auto nat0 = [&](unsigned s) { return upper ? m - 1u - s : s; };   // natural sweep position -> row
-    auto pos0 = [&](unsigned i) { return upper ? m - 1u - i : i; };   // row -> natural sweep position
+    auto nat0 = [&](unsigned s) { return s; };  // sweep form: natural sweep position = row
+    auto pos0 = [&](unsigned i) { return i; };
     std::vector<unsigned> lo(m), phase(m), parent(m);
     const unsigned        S0 = 640;  // closure span of phase 0
     if (!upper) {
@@ -705,7 +715,7 @@ static void pack_sweep(const HostCsr &T, bool upper, PackedSweep &out, unsigned 
       // entries in this order, so the dependency it really waits for comes last and no
       // finished work queues behind it.
       ent.resize(e - b);
-      for (unsigned q = 0; q < e - b; ++q) ent[q] = upper ? e - 1u - q : b + q;
+      for (unsigned q = 0; q < e - b; ++q) ent[q] = b + q;
       if (sort_by_depth)
         std::stable_sort(ent.begin(), ent.end(), [&](unsigned x, unsigned y) { return lev[T.col[x]] < lev[T.col[y]]; });
       for (unsigned q = 0; q < e - b; ++q) {
@@ -717,7 +727,7 @@ static void pack_sweep(const HostCsr &T, bool upper, PackedSweep &out, unsigned 
           loc = sj - s0;  // a row of this block
         } else {
           loc            = rows + slot[j];
-          halo[slot[j]] = j;  // global (natural) index of the external entry
+          halo[slot[j]] = slot_of(j);  // solution slot of the external entry
         }
         idx.push_back(static_cast<unsigned short>(loc));
         val.push_back(T.val[k]);
@@ -736,7 +746,7 @@ static void pack_sweep(const HostCsr &T, bool upper, PackedSweep &out, unsigned 
     unsigned char *base = buf.data() + bi.off;
     std::memcpy(base, ptr.data(), 4u * (rows + 1));
     gidx.resize(rows);
-    for (unsigned r = 0; r < rows; ++r) gidx[r] = nat(s0 + r);
+    for (unsigned r = 0; r < rows; ++r) gidx[r] = T.gid[nat(s0 + r)];  // row code
     std::memcpy(base + slab_off_gidx(rows), gidx.data(), 4u * rows);
     if (nh) std::memcpy(base + slab_off_halo(rows), halo.data(), 4u * nh);
     std::memcpy(base + slab_off_order(rows, nh), order.data(), 2u * rows);
@@ -756,13 +766,16 @@ static void pack_sweep(const HostCsr &T, bool upper, PackedSweep &out, unsigned 
   // unfinished instead of a long chain of blocks that all wait for each other.
   const std::size_t     nb = infos.size();
   std::vector<unsigned> blk_of(m), blev(nb, 0u);
+  std::vector<unsigned> &row_of_slot = out.row_of_slot;
+  row_of_slot.assign(2 * T.orig_rows, 0u);
+  for (unsigned i = 0; i < m; ++i) row_of_slot[slot_of(i)] = i;
   for (std::size_t b = 0; b < nb; ++b)
     for (unsigned r = 0; r < infos[b].rows; ++r) blk_of[infos[b].s0 + r] = static_cast<unsigned>(b);
   for (std::size_t b = 0; b < nb; ++b) {
     const unsigned *hl = reinterpret_cast<const unsigned *>(buf.data() + infos[b].off + slab_off_halo(infos[b].rows));
     unsigned        l  = 0;
     for (unsigned h = 0; h < infos[b].nhalo; ++h) {
-      const unsigned j = hl[h], sj = pos[j];
+      const unsigned j = row_of_slot[hl[h]], sj = pos[j];
       l = std::max(l, blev[blk_of[sj]] + 1u);
     }
     blev[b] = l;
@@ -781,10 +794,19 @@ static void pack_sweep(const HostCsr &T, bool upper, PackedSweep &out, unsigned 
 // ticket order) -- lets the host-side packing be tested without a GPU (tests/test_abi.py).
 void sweep_host_emulate(const HostCsr &T, bool upper, const double *rhs, const double *diag, double *x,
                         std::size_t stats[4]) {
-  PackedSweep P;
-  pack_sweep(T, upper, P);
+  PackedSweep       P;
+  HostCsr           S  = to_sweep_form(T, upper);
+  const MergeParams mp = MergeParams::from_env();
+  MergeStats        ms;
+  if (mp.enabled) S = merge_levels(S, mp, &ms);
   const unsigned      m = static_cast<unsigned>(T.nrows);
-  std::vector<double> xs;
+  std::vector<double> xs, xg(2 * static_cast<std::size_t>(m), 0.0);
+  if (stream_sweeps()) {
+    stream_host_emulate(S, upper, rhs, diag, xg.data(), stats);
+    std::copy(xg.begin(), xg.begin() + m, x);
+    return;
+  }
+  pack_sweep(S, upper, P);
   for (const SlabInfo &bi : P.infos) {
     const unsigned char * base = P.buf.data() + bi.off;
     const unsigned *      ptr  = reinterpret_cast<const unsigned *>(base);
@@ -793,15 +815,16 @@ void sweep_host_emulate(const HostCsr &T, bool upper, const double *rhs, const d
     const double *        val  = reinterpret_cast<const double *>(base + slab_off_val(bi.rows, bi.nhalo, bi.nnz));
     const unsigned *      gix  = reinterpret_cast<const unsigned *>(base + slab_off_gidx(bi.rows));
     xs.assign(bi.rows + bi.nhalo, 0.0);
-    for (unsigned h = 0; h < bi.nhalo; ++h) xs[bi.rows + h] = x[halo[h]];
+    for (unsigned h = 0; h < bi.nhalo; ++h) xs[bi.rows + h] = xg[halo[h]];
     for (unsigned r = 0; r < bi.rows; ++r) {
-      const unsigned gi  = gix[r];
-      double         acc = upper ? rhs[gi] / diag[gi] : rhs[gi];
+      const unsigned code = gix[r], gi = code & kCodeSlotMask, ri = gi >= m ? gi - m : gi;
+      double         acc  = (code & kCodeZeroRhs) ? 0.0 : (upper ? rhs[ri] / diag[ri] : rhs[ri]);
       for (unsigned k = ptr[r]; k < ptr[r + 1]; ++k) acc -= val[k] * xs[idx[k]];
-      xs[r] = acc;
-      x[gi] = acc;
+      xs[r]  = acc;
+      xg[gi] = acc;
     }
   }
+  std::copy(xg.begin(), xg.begin() + m, x);
   stats[0] = P.infos.size();
   stats[1] = P.halo_total;
   stats[2] = P.buf.size();
@@ -815,9 +838,13 @@ void sweep_host_emulate(const HostCsr &T, bool upper, const double *rhs, const d
 // prm = {slots, T, t_load, c_s, c_g, t_dep, t_pub}; out = {total, sum of block lives, max
 // block life, mean halo wait, mean in-block tail, blocks}.  Times in microseconds.
 void sweep_simulate(const HostCsr &T, bool upper, const double *prm, double *out) {
-  PackedSweep P;
-  pack_sweep(T, upper, P);
-  const unsigned      m     = static_cast<unsigned>(T.nrows);
+  PackedSweep       P;
+  HostCsr           S  = to_sweep_form(T, upper);
+  const MergeParams mp = MergeParams::from_env();
+  MergeStats        ms;
+  if (mp.enabled) S = merge_levels(S, mp, &ms);
+  pack_sweep(S, upper, P);
+  const unsigned      m     = 2u * static_cast<unsigned>(T.nrows);  // solution slots
   const unsigned      slots = static_cast<unsigned>(prm[0]), NT = static_cast<unsigned>(prm[1]);
   const double        t_load = prm[2], c_s = prm[3], c_g = prm[4], t_dep = prm[5], t_pub = prm[6];
   std::vector<double> F(m, 0.0), fin, arrive, thr;
@@ -829,6 +856,7 @@ void sweep_simulate(const HostCsr &T, bool upper, const double *prm, double *out
     const unsigned *      halo  = reinterpret_cast<const unsigned *>(base + slab_off_halo(bi.rows));
     const unsigned short *order = reinterpret_cast<const unsigned short *>(base + slab_off_order(bi.rows, bi.nhalo));
     const unsigned short *idx   = reinterpret_cast<const unsigned short *>(base + slab_off_idx(bi.rows, bi.nhalo));
+    const unsigned *      gix   = reinterpret_cast<const unsigned *>(base + slab_off_gidx(bi.rows));
     auto                  it    = std::min_element(slot_free.begin(), slot_free.end());
     const double          start = std::max(prev_start, *it);
     prev_start                  = start;
@@ -851,7 +879,7 @@ void sweep_simulate(const HostCsr &T, bool upper, const double *prm, double *out
         t                 = std::max(t, av) + t_dep;
       }
       fin[r]            = t + t_pub;
-      F[P.perm[bi.s0 + r]] = fin[r];
+      F[gix[r] & kCodeSlotMask] = fin[r];
       thr[q % NT]       = fin[r];
       done              = std::max(done, fin[r]);
     }
@@ -864,14 +892,18 @@ void sweep_simulate(const HostCsr &T, bool upper, const double *prm, double *out
   }
   const double nb = static_cast<double>(P.infos.size());
   out[0] = total, out[1] = life_sum, out[2] = life_max, out[3] = wait_sum / nb, out[4] = tail_sum / nb, out[5] = nb;
+  out[6] = static_cast<double>(ms.ext_depth), out[7] = static_cast<double>(P.buf.size());
 }
 
 // developer tool: the block dependency graph of a packed sweep, in ticket order
 void sweep_block_graph(const HostCsr &T, bool upper, std::vector<unsigned> &info, std::vector<unsigned> &src_ptr,
                        std::vector<unsigned> &src_idx) {
-  PackedSweep P;
-  pack_sweep(T, upper, P);
-  const unsigned        m = static_cast<unsigned>(T.nrows);
+  PackedSweep       P;
+  HostCsr           S  = to_sweep_form(T, upper);
+  const MergeParams mp = MergeParams::from_env();
+  if (mp.enabled) S = merge_levels(S, mp, nullptr);
+  pack_sweep(S, upper, P);
+  const unsigned        m = static_cast<unsigned>(S.nrows);
   std::vector<unsigned> blk_of(m);
   for (std::size_t b = 0; b < P.infos.size(); ++b)
     for (unsigned r = 0; r < P.infos[b].rows; ++r) blk_of[P.infos[b].s0 + r] = static_cast<unsigned>(b);
@@ -882,7 +914,7 @@ void sweep_block_graph(const HostCsr &T, bool upper, std::vector<unsigned> &info
     info.insert(info.end(), {bi.s0, bi.rows, bi.nhalo, bi.nnz});
     const unsigned *hl = reinterpret_cast<const unsigned *>(P.buf.data() + bi.off + slab_off_halo(bi.rows));
     for (unsigned h = 0; h < bi.nhalo; ++h) {
-      const unsigned j = hl[h], sb = blk_of[P.pos[j]];
+      const unsigned j = P.row_of_slot[hl[h]], sb = blk_of[P.pos[j]];
       if (seen[sb] != b) {
         seen[sb] = static_cast<unsigned>(b);
         src_idx.push_back(sb);
@@ -930,18 +962,39 @@ static void upload_plan(const PackedSweep &P, unsigned m, bool upper, unsigned n
   plan.info.upload(reinterpret_cast<const unsigned char *>(P.infos.data()), P.infos.size() * sizeof(SlabInfo), tally);
 }
 
-void build_split_plans(const HostCsr &T, SweepPlan &plan_lo, SweepPlan &plan_up, HostCsr &ul,
+bool stream_sweeps() {
+  const char *e = std::getenv("HIFIR_B200_SWEEP");
+  return !e || std::string(e) != "slab";
+}
+
+void build_split_plans(const HostCsr &Tnat, SweepPlan &plan_lo, SweepPlan &plan_up, HostCsr &ul,
                        std::vector<unsigned> &urows, std::size_t *tally) {
+  const unsigned    mo = static_cast<unsigned>(Tnat.nrows);
+  HostCsr           T  = to_sweep_form(Tnat, false);
+  const MergeParams mp = MergeParams::from_env();
+  MergeStats        ms;
+  if (mp.enabled) T = merge_levels(T, mp, &ms);
+  if (stream_sweeps()) {  // one level-major sweep, nothing to split
+    build_stream_plan(T, false, plan_lo, tally);
+    plan_lo.merge = ms;
+    ul.nrows = 0, ul.ncols = 2 * static_cast<std::size_t>(mo);
+    ul.ptr.assign(1, 0u);
+    urows.clear();
+    return;
+  }
   const unsigned    m = static_cast<unsigned>(T.nrows);
   std::vector<char> is_lower, is_upper(m);
   split_lower_rows(T, is_lower);
   for (unsigned i = 0; i < m; ++i) is_upper[i] = !is_lower[i];
-  // L_uu (full-size index space, upper rows keep their upper entries) and L_ul (compact rows)
+  // L_uu (full-size index space, upper rows keep their upper entries) and L_ul (compact rows;
+  // columns = solution slots of the finished lower rows, row map = row codes)
   HostCsr uu;
   uu.nrows = uu.ncols = m;
+  uu.gid              = T.gid;
+  uu.orig_rows        = T.orig_rows;
   uu.ptr.assign(m + 1, 0u);
   ul.nrows = 0;
-  ul.ncols = m;
+  ul.ncols = 2 * static_cast<std::size_t>(mo);
   ul.ptr.assign(1, 0u);
   urows.clear();
   for (unsigned i = 0; i < m; ++i) {
@@ -951,11 +1004,11 @@ void build_split_plans(const HostCsr &T, SweepPlan &plan_lo, SweepPlan &plan_up,
           uu.col.push_back(T.col[k]);
           uu.val.push_back(T.val[k]);
         } else {
-          ul.col.push_back(T.col[k]);
+          ul.col.push_back(static_cast<int>(T.gid[T.col[k]] & kCodeSlotMask));
           ul.val.push_back(T.val[k]);
         }
       }
-      urows.push_back(i);
+      urows.push_back(T.gid[i]);
       ul.ptr.push_back(static_cast<unsigned>(ul.col.size()));
     }
     uu.ptr[i + 1] = static_cast<unsigned>(uu.col.size());
@@ -963,7 +1016,8 @@ void build_split_plans(const HostCsr &T, SweepPlan &plan_lo, SweepPlan &plan_up,
   ul.nrows = urows.size();
   PackedSweep Plo, Pup;
   pack_sweep(T, false, Plo, 8u, 0u, &is_lower);
-  upload_plan(Plo, m, false, 1, plan_lo, tally);
+  upload_plan(Plo, mo, false, 1, plan_lo, tally);
+  plan_lo.merge = ms;
   if (!urows.empty()) {
     // the top of the tree is a dependent chain of blocks: make them as large as one SM
     // allows (fewer block-to-block hand-offs); occupancy is irrelevant there
@@ -971,21 +1025,29 @@ void build_split_plans(const HostCsr &T, SweepPlan &plan_lo, SweepPlan &plan_up,
       pack_sweep(uu, false, Pup, 8u, kSmemBudgetMrhs, &is_upper, kRowsBig);
     else
       pack_sweep(uu, false, Pup, 8u, 0u, &is_upper);
-    upload_plan(Pup, m, false, 1, plan_up, tally);
+    upload_plan(Pup, mo, false, 1, plan_up, tally);
+    plan_up.rhs_by_slot = true;  // its right-hand side is r_u, stored by solution slot
   }
 }
 
-void build_sweep_plan(const HostCsr &T, bool upper, SweepPlan &plan, std::size_t *tally, unsigned nr) {
-  plan.m       = static_cast<unsigned>(T.nrows);
+void build_sweep_plan(const HostCsr &Tnat, bool upper, SweepPlan &plan, std::size_t *tally, unsigned nr) {
+  plan.m       = static_cast<unsigned>(Tnat.nrows);
   plan.upper   = upper;
   plan.nblocks = 0;
   plan.nr      = nr;
   if (!plan.m) return;
+  HostCsr     T = to_sweep_form(Tnat, upper);
   PackedSweep P;
   // multi-rhs plans: one CTA per SM with the whole 227 KB, a solution slot holds nr values
   if (nr > 1) {
     pack_sweep(T, upper, P, 8u * nr, kSmemBudgetMrhs);
   } else {
+    const MergeParams mp = MergeParams::from_env();
+    if (mp.enabled) T = merge_levels(T, mp, &plan.merge);
+    if (stream_sweeps()) {
+      build_stream_plan(T, upper, plan, tally);
+      return;
+    }
     pack_sweep(T, upper, P);
     // a factor that yields only a few hundred blocks can not fill the GPU anyway and is
     // bound by its dependent chain: prefer few large blocks (one CTA per SM)
@@ -1021,7 +1083,7 @@ void launch_T(Handle *h, const SweepPlan &plan, const double *rhs_plain, const u
       plan.m, plan.slabs.p, reinterpret_cast<const SlabInfo *>(plan.info.p), rhs_plain, rhs_tagged, diag, x, parity,
       ticket, h->error_flag.p, trace, env_int("HIFIR_B200_BACKOFF", 1000),
       static_cast<unsigned>(env_int("HIFIR_B200_POLL_SLEEP", 100)),
-      static_cast<unsigned>(env_int("HIFIR_B200_SPIN_BURST", 4096)), env_int("HIFIR_B200_INTERLEAVE", 0));
+      static_cast<unsigned>(env_int("HIFIR_B200_SPIN_BURST", 4096)), plan.rhs_by_slot ? 1 : 0);
 }
 template <bool UPPER>
 void launch_U(Handle *h, const SweepPlan &plan, const double *rhs_plain, const unsigned long long *rhs_tagged,
@@ -1059,6 +1121,10 @@ void launch_mrhs(Handle *h, const SweepPlan &plan, const double *rhs_plain, cons
 void launch_sweep(Handle *h, const SweepPlan &plan, const double *rhs_plain, const unsigned long long *rhs_tagged,
                   const double *diag, unsigned long long *x, unsigned parity, int *ticket, unsigned long long *trace) {
   if (!plan.nblocks) return;
+  if (plan.stream) {
+    launch_stream_sweep(h, plan, rhs_plain, rhs_tagged, diag, x, parity, ticket, trace);
+    return;
+  }
   if (plan.nr > 1) {
     if (plan.nr != kMrhsWidth) throw std::logic_error("unsupported multi-rhs plan width");
     if (plan.upper)
