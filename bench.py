@@ -398,18 +398,28 @@ def run_ours(args, rank, world, local_rank):
     if os.path.exists(tpath):
         try:
             traffic = json.load(open(tpath)).get(workload_name(args.workload, args.size, 1), {}).get(
-                "sptrsv_slab_kernel_bytes_per_launch")
+                "sweep_stream_kernel_bytes_per_launch")
         except Exception:
             traffic = None
-    roofline = {"bound": "hbm", "kernel": f"sptrsv_slab_kernel ({nl} triangular sweeps per apply: L and U of every "
-                                          f"level, down and up; an L sweep = subtree launch + spmv_rows + top launch)",
+    # second ceiling of the streaming sweep: every factor entry gathers one solution value from L2 and an
+    # SM serves one L2 request per clock (measured: 289 G gathers/s on B200, tools/lat_bench.cu)
+    gather_peak = 289e9
+    roofline = {"bound": "hbm", "kernel": f"sweep_stream_kernel ({nl} triangular sweeps per apply: L and U of every "
+                                          f"level, down and up)",
                 "achieved": k_ach, "peak": peak, "unit": "GB/s", "frac": k_ach / peak, "traffic": traffic,
                 "algorithmic_bytes_per_launch": sw_bytes / nl, "ms_per_launch": sw_ms / nl,
                 "share_of_step": sw_ms / sum(prof.values()), "peak_source": peak_src,
+                "streamed_bytes_per_launch": st["sweep_bytes"] / nl,
+                "streamed_gbs": st["sweep_bytes"] / (sw_ms * 1e-3) / 1e9,
+                "l2_gather": {"gathers_per_launch": st["sweep_entries"] / nl,
+                              "achieved_g_per_s": st["sweep_entries"] / (sw_ms * 1e-3) / 1e9,
+                              "peak_g_per_s": gather_peak / 1e9,
+                              "frac": st["sweep_entries"] / (sw_ms * 1e-3) / gather_peak},
                 "apply": {"kernels": st["kernels_per_apply"], "algorithmic_bytes": bytes_apply, "achieved": achieved,
                           "frac": achieved / peak},
-                "latency_floor": {"dependent_steps_per_apply": st["depth_total"],
-                                  "ns_per_step_achieved": ms_step * 1e6 / max(1, st["depth_total"])},
+                "latency_floor": {"dependent_steps_per_apply_reference": st["depth_total"],
+                                  "dependent_steps_per_apply_merged": st["depth_merged"],
+                                  "us_per_merged_step_achieved": sw_ms * 1e3 / max(1, st["depth_merged"])},
                 "kernels_ms": {k: round(v, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1])[:10]}}
 
     cpu = None

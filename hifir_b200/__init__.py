@@ -24,7 +24,8 @@ LHF_DEFAULT_RANK = -2
 FULL_RANK = (1 << 64) - 1  # size_t(-1)
 
 STAT_NAMES = ("levels", "n", "nnz", "dense_n", "dense_rank", "bytes_factors", "bytes_vec_per_rhs",
-              "bytes_dense", "device_bytes", "kernels_per_apply", "depth_total", "launch_count")
+              "bytes_dense", "device_bytes", "kernels_per_apply", "depth_total", "launch_count", "depth_merged",
+              "sweep_bytes", "sweep_entries")
 
 
 class LhfdGpuCcs(C.Structure):

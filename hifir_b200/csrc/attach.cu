@@ -179,6 +179,15 @@ Handle *attach_levels(int device, std::size_t nlevels, const LhfdGpuLevel *lv, b
       D.rhs_u.alloc(2 * P.m, tally);
     }
     build_sweep_plan(Ur, true, D.U, tally);
+    if (std::getenv("HIFIR_B200_VERBOSE")) {
+      for (const SweepPlan *pl : {&D.L, &D.U})
+        std::fprintf(stderr,
+                     "[hifir_b200] level %zu %s: rows %zu nnz %zu depth %zu -> merged rows %zu nnz %zu depth %zu "
+                     "(super levels %zu); stream: slices %u chunks %u padded %zu bytes %.1f MB\n",
+                     l, pl->upper ? "U" : "L", pl->merge.rows, pl->merge.nnz, pl->merge.depth, pl->merge.ext_rows,
+                     pl->merge.ext_nnz, pl->merge.ext_depth, pl->merge.super_levels, pl->nblocks, pl->st_chunks,
+                     pl->st_padded, pl->slab_bytes / 1e6);
+    }
     D.L.nnz = Lr.col.size();
     D.U.nnz = Ur.col.size();
     D.hostL = std::move(Lr);

@@ -435,6 +435,18 @@ LhfStatus lhfdGpuGetStats(LhfdGpuHdl hdl, size_t stats[]) {
   std::size_t depth = 0;
   for (const auto &D : h->levels) depth += (D.nm ? 2 : 1) * (D.depthL + D.depthU);
   stats[LHF_GPU_STAT_DEPTH_TOTAL]  = depth;
+  std::size_t dm = 0, sb = 0, se = 0;
+  for (const auto &D : h->levels) {
+    const std::size_t k = D.nm ? 2 : 1;
+    for (const SweepPlan *p : {&D.L, &D.L_up, &D.U}) {
+      dm += k * (p->stream ? p->st_depth : 0);
+      sb += k * p->slab_bytes;
+    }
+    se += k * ((D.L.merge.ext_nnz ? D.L.merge.ext_nnz : D.L.nnz) + (D.U.merge.ext_nnz ? D.U.merge.ext_nnz : D.U.nnz));
+  }
+  stats[LHF_GPU_STAT_DEPTH_MERGED]  = dm ? dm : depth;
+  stats[LHF_GPU_STAT_SWEEP_BYTES]   = sb;
+  stats[LHF_GPU_STAT_SWEEP_ENTRIES] = se;
   stats[LHF_GPU_STAT_LAUNCH_COUNT] = h->launch_count;
   return LHF_SUCCESS;
 }

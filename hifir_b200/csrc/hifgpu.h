@@ -81,10 +81,12 @@ constexpr unsigned kCodeZeroRhs = 0x80000000u, kCodeSlotMask = 0x7fffffffu;
 // algebraic level merging (merge.cu)
 struct MergeParams {
   bool     enabled   = true;
-  double   gain      = 100000.0;  // fill (in nonzeros) one saved dependent step may cost
-  unsigned row_cap   = 128;       // longest row of an inverted diagonal block
+  double   gain      = 1000000.0;  // fill (in nonzeros) one saved dependent step may cost
+  unsigned row_cap   = 256;       // longest row of an inverted diagonal block
   unsigned bmax      = 64;        // most level sets merged into one super level
   double   row_cost  = 2.0;       // cost of one auxiliary row, in nonzeros
+  double   sl_cap    = 500000.0;  // a super level stops growing at this many entries: beyond, its two
+                                  // steps are throughput bound and more fill only costs (measured optimum 4e5-8e5)
   static MergeParams from_env();
 };
 struct MergeStats {
@@ -103,6 +105,7 @@ struct SweepPlan {
   bool                        stream = false;
   std::size_t                 st_depth = 0, st_padded = 0;
   unsigned                    st_chunks = 0;  // 8 slices each, all of one level set
+  unsigned                    st_u = 8;       // entries per lane held in registers (kernel variant)
   DevBuf<unsigned>            st_need;   // chunks per level set
   DevBuf<unsigned>            st_sdesc;  // uint4 per slice: offset (units of 32 entries), entries per lane, log2 lanes per row, level
   DevBuf<unsigned>            st_codes;  // 32 row codes per slice

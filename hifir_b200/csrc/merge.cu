@@ -36,6 +36,7 @@ MergeParams MergeParams::from_env() {
   if (const char *e = std::getenv("HIFIR_B200_MERGE_ROWCAP")) p.row_cap = static_cast<unsigned>(std::atoi(e));
   if (const char *e = std::getenv("HIFIR_B200_MERGE_BMAX")) p.bmax = static_cast<unsigned>(std::atoi(e));
   if (const char *e = std::getenv("HIFIR_B200_MERGE_ROWCOST")) p.row_cost = std::atof(e);
+  if (const char *e = std::getenv("HIFIR_B200_MERGE_SLCAP")) p.sl_cap = std::atof(e);
   return p;
 }
 
@@ -116,6 +117,7 @@ HostCsr merge_levels(const HostCsr &S, const MergeParams &prm, MergeStats *st) {
   std::vector<unsigned> stamp(m, 0u), touched, tcol, tlen;
   std::vector<double>   tval;
   unsigned              cur = 0, l0 = 0;
+  double                sl_entries = 0.0;  // entries of the current super level (both of its phases)
   auto close_super = [&](unsigned lend) {  // super level [l0, lend) ends
     // two merged level sets save nothing (t and x steps instead of two x steps): undo
     if (lend - l0 == 2u)
@@ -132,7 +134,7 @@ HostCsr merge_levels(const HostCsr &S, const MergeParams &prm, MergeStats *st) {
       tcol.clear();
       tval.clear();
       tlen.assign(re - rb, 0u);
-      double   cost = 0.0;
+      double   cost = 0.0, entries = 0.0;
       unsigned maxlen = 0;
       for (unsigned q = rb; q < re && maxlen <= prm.row_cap; ++q) {
         const unsigned i = lrows[q];
@@ -162,9 +164,13 @@ HostCsr merge_levels(const HostCsr &S, const MergeParams &prm, MergeStats *st) {
         }
         tlen[q - rb] = static_cast<unsigned>(touched.size());
         if (nwithin) cost += static_cast<double>(touched.size()) - nwithin + 1.0 + prm.row_cost;
+        entries += static_cast<double>(S.ptr[i + 1] - S.ptr[i] - nwithin + touched.size()) + (nwithin ? 1.0 : 0.0);
         maxlen = std::max<unsigned>(maxlen, static_cast<unsigned>(touched.size()) + 1u);
       }
-      accept = maxlen <= prm.row_cap && cost <= prm.gain;
+      // a super level whose phases already saturate the machine gains nothing from growing:
+      // merging only pays while its steps are bound by the latency of a dependent hop
+      accept = maxlen <= prm.row_cap && cost <= prm.gain && sl_entries + entries <= prm.sl_cap;
+      if (accept) sl_entries += entries;
     }
     if (accept) {
       std::size_t tp = 0;
@@ -179,8 +185,12 @@ HostCsr merge_levels(const HostCsr &S, const MergeParams &prm, MergeStats *st) {
       }
     } else {
       if (l > 0) close_super(l);
-      l0 = l;
-      for (unsigned q = rb; q < re; ++q) sl0[lrows[q]] = l0;
+      l0         = l;
+      sl_entries = 0.0;
+      for (unsigned q = rb; q < re; ++q) {
+        sl0[lrows[q]] = l0;
+        sl_entries += static_cast<double>(S.ptr[lrows[q] + 1] - S.ptr[lrows[q]]);
+      }
     }
   }
   if (depth) close_super(depth);

@@ -1045,7 +1045,9 @@ void build_sweep_plan(const HostCsr &Tnat, bool upper, SweepPlan &plan, std::siz
     const MergeParams mp = MergeParams::from_env();
     if (mp.enabled) T = merge_levels(T, mp, &plan.merge);
     if (stream_sweeps()) {
+      const MergeStats ms = plan.merge;
       build_stream_plan(T, upper, plan, tally);
+      plan.merge = ms;
       return;
     }
     pack_sweep(T, upper, P);

@@ -33,6 +33,7 @@ constexpr unsigned kStreamThreads = 256;                 // 8 warps = 8 slices p
 constexpr unsigned kStreamWarps   = kStreamThreads / 32;
 constexpr unsigned kPadCol        = 0xffffffffu;
 constexpr unsigned kPadCode       = 0xffffffffu;
+constexpr unsigned kEmptySlice    = 0xffffffffu;  // sdesc.z of a padding slice (its warp idles)
 
 __device__ __forceinline__ unsigned ld_stream_u32(const unsigned *p) {
   unsigned v;
@@ -57,24 +58,35 @@ __device__ __forceinline__ double ld_stream_f64(const double *p) {
 // several lanes and reduced with shuffles: the serial chain of a row is <= kU dependent-free
 // loads whatever its length); entry k of lane j at cols/vals[(sd.x + k) * 32 + j].
 // Chunk c (one CTA round) = slices [8c, 8c + 8), all of one level set (sd.w).
-constexpr int kU = 8;
 // sync layout (ints): [0] ticket, [16] frontier hint, [kSyncStride * (1 + l)] chunk counter of level l
 // (one 128-byte line per counter: the pollers of different levels hit different L2 slices)
+// first try of a gather through L1: a hit needs no L2 request (one per clock and SM is all the
+// hardware serves).  A stale line can only show an old parity -> the entry is re-polled from L2.
+__device__ __forceinline__ unsigned long long ld_l1(const unsigned long long *p) {
+  unsigned long long v;
+  asm volatile("ld.global.ca.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ int ld_poll_i32(const int *p) {
+  int v;
+  asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
 __device__ __forceinline__ unsigned long long stream_timer_ns() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
 
-template <bool UPPER>
-__global__ void __launch_bounds__(kStreamThreads)
+template <bool UPPER, int kU>
+__global__ void __launch_bounds__(kStreamThreads, kU == 4 ? 5 : 3)
     sweep_stream_kernel(const unsigned nchunks, const uint4 *__restrict__ sdesc, const unsigned *__restrict__ lvl_need,
                         const unsigned *__restrict__ codes, const unsigned *__restrict__ cols,
                         const double *__restrict__ vals, const unsigned m, const double *__restrict__ rhs_plain,
                         const unsigned long long *rhs_tagged, const double *__restrict__ diag, unsigned long long *x,
                         const unsigned parity, int *sync, int *error_flag, const unsigned window,
                         const unsigned adm_sleep, const unsigned near_sleep, const unsigned poll_sleep,
-                        unsigned long long *trace) {
+                        const int use_l1, unsigned long long *trace) {
   __shared__ unsigned s_c;
   __shared__ int      s_last;
   const unsigned      warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
@@ -82,10 +94,7 @@ __global__ void __launch_bounds__(kStreamThreads)
   for (;;) {
     __syncthreads();  // every warp of the previous chunk has published
     if (threadIdx.x == 0) {
-      if (s_last >= 0) {  // the chunk that completes a level set advances the frontier hint
-        const unsigned done = static_cast<unsigned>(atomicAdd(sync + kSyncStride * (1 + s_last), 1)) + 1u;
-        if (done == lvl_need[s_last]) atomicMax(sync + 16, s_last + 1);
-      }
+      if (s_last >= 0) atomicAdd(sync + kSyncStride * (1 + s_last), 1);  // fire and forget
       s_c = static_cast<unsigned>(atomicAdd(sync, 1));
     }
     __syncthreads();
@@ -94,8 +103,9 @@ __global__ void __launch_bounds__(kStreamThreads)
     if (trace && threadIdx.x == 0) trace[8 * c + 0] = stream_timer_ns();
     const unsigned s    = c * kStreamWarps + warp;
     const uint4    sd   = sdesc[s];  // x: offset (units of 32 entries), y: entries per lane, z: log2 lanes per row, w: level
-    const unsigned code = codes[static_cast<std::size_t>(s) * 32u + lane];
-    const unsigned lpr  = 1u << sd.z;
+    const bool     idle = sd.z == kEmptySlice;  // padding slice of a spread-out thin level set
+    const unsigned code = idle ? kPadCode : codes[static_cast<std::size_t>(s) * 32u + lane];
+    const unsigned lpr  = idle ? 1u : 1u << sd.z;
     const bool     act  = code != kPadCode && (lane & (lpr - 1u)) == 0u;  // the lane that owns the row
     const unsigned slot = code & kCodeSlotMask;
     const std::size_t base = static_cast<std::size_t>(sd.x) * 32u + lane;
@@ -139,13 +149,19 @@ __global__ void __launch_bounds__(kStreamThreads)
         const int *    ctr   = sync + kSyncStride * (1 + t);
         unsigned       spins = 0;
         for (;;) {
-          const unsigned f = static_cast<unsigned>(*reinterpret_cast<const volatile int *>(sync + 16));  // levels [0, f) done
+          const unsigned f = static_cast<unsigned>(ld_poll_i32(sync + 16));  // levels [0, f) are known to be done
           if (t < f + 2u) {
-            if (static_cast<unsigned>(*reinterpret_cast<const volatile int *>(ctr)) >= need) break;
-            if (near_sleep) __nanosleep(near_sleep);
-          } else {
-            __nanosleep(min((t - f) * adm_sleep, 20000u));
+            while (static_cast<unsigned>(ld_poll_i32(ctr)) < need) {
+              if (near_sleep) __nanosleep(near_sleep);
+              if (++spins > (kSpinLimit >> 4)) {
+                *error_flag = 1;
+                break;
+              }
+            }
+            if (t + 1u > f) atomicMax(sync + 16, static_cast<int>(t + 1u));  // advance the hint
+            break;
           }
+          __nanosleep(min((t - f) * adm_sleep, 20000u));
           if (++spins > (kSpinLimit >> 4)) {
             *error_flag = 1;
             break;
@@ -160,7 +176,7 @@ __global__ void __launch_bounds__(kStreamThreads)
       unsigned long long g[kU];
 #pragma unroll
       for (int u = 0; u < kU; ++u)
-        if (cc[u] != kPadCol) g[u] = ld_poll(x + cc[u]);
+        if (cc[u] != kPadCol) g[u] = use_l1 ? ld_l1(x + cc[u]) : ld_poll(x + cc[u]);
       if (trace && threadIdx.x == 0 && k == 0) {  // warp 0: first gather round trip
         unsigned long long any = 0;
 #pragma unroll
@@ -168,24 +184,23 @@ __global__ void __launch_bounds__(kStreamThreads)
           if (cc[u] != kPadCol) any |= g[u];
         trace[8 * c + 6] = stream_timer_ns() + (any == 0x7ff8dead00000001ull ? 1u : 0u);
       }
-      // fast path: everything was ready on the first try (padding entries count as ready)
-      bool all_ready = true;
+      // entries that were not ready on the first try (padding counts as ready) are re-polled
+      // TOGETHER, round by round: one L2 round trip per round whatever their number
+      unsigned pend = 0;
 #pragma unroll
-      for (int u = 0; u < kU; ++u) all_ready &= cc[u] == kPadCol || tag_ready(g[u], parity);
-      if (!__all_sync(0xffffffffu, all_ready)) {
+      for (int u = 0; u < kU; ++u)
+        if (cc[u] != kPadCol && !tag_ready(g[u], parity)) pend |= 1u << u;
+      for (unsigned rounds = 0; __any_sync(0xffffffffu, pend != 0u);) {
+        if (poll_sleep) __nanosleep(poll_sleep);
 #pragma unroll
-        for (int u = 0; u < kU; ++u) {
-          if (cc[u] != kPadCol) {
-            unsigned spins = 0;
-            while (!tag_ready(g[u], parity)) {
-              if (poll_sleep) __nanosleep(poll_sleep);
-              g[u] = ld_poll(x + cc[u]);
-              if (++spins > kSpinLimit) {  // hang guard: flag the error, go on with garbage
-                *error_flag = 1;
-                break;
-              }
-            }
-          }
+        for (int u = 0; u < kU; ++u)
+          if (pend & (1u << u)) g[u] = ld_poll(x + cc[u]);
+#pragma unroll
+        for (int u = 0; u < kU; ++u)
+          if ((pend & (1u << u)) && tag_ready(g[u], parity)) pend &= ~(1u << u);
+        if (++rounds > (kSpinLimit >> 3)) {  // hang guard: flag the error, go on with garbage
+          *error_flag = 1;
+          break;
         }
       }
 #pragma unroll
@@ -220,13 +235,17 @@ struct StreamHost {
   unsigned              depth = 0;
 };
 
-unsigned lanes_log2_for(unsigned len) {  // lanes per row so that a lane holds <= kU entries (max 32 lanes)
+unsigned lanes_log2_for(unsigned len, unsigned U) {  // lanes per row so that a lane holds <= U entries (max 32 lanes)
   unsigned z = 0;
-  while (z < 5u && ((len + (1u << z) - 1u) >> z) > static_cast<unsigned>(kU)) ++z;
+  while (z < 5u && ((len + (1u << z) - 1u) >> z) > U) ++z;
   return z;
 }
+unsigned stream_unroll() {
+  const char *e = std::getenv("HIFIR_B200_STREAM_U");
+  return e && std::atoi(e) == 8 ? 8u : 4u;
+}
 
-void pack_stream(const HostCsr &S, StreamHost &H) {
+void pack_stream(const HostCsr &S, StreamHost &H, unsigned U) {
   const unsigned m = static_cast<unsigned>(S.nrows);
   if (!m) return;
   if (S.gid.size() != m) throw std::logic_error("build_stream_plan: factor is not in sweep form");
@@ -255,9 +274,9 @@ void pack_stream(const HostCsr &S, StreamHost &H) {
   std::size_t padded = 0;
   for (unsigned p = 0; p < m;) {
     // one slice: rows of one level set with the same lanes-per-row class
-    const unsigned l = lev[ord[p]], z = lanes_log2_for(rowlen(ord[p])), lpr = 1u << z, cap = 32u >> z;
+    const unsigned l = lev[ord[p]], z = lanes_log2_for(rowlen(ord[p]), U), lpr = 1u << z, cap = 32u >> z;
     unsigned       cnt = 1;
-    while (cnt < cap && p + cnt < m && lev[ord[p + cnt]] == l && lanes_log2_for(rowlen(ord[p + cnt])) == z) ++cnt;
+    while (cnt < cap && p + cnt < m && lev[ord[p + cnt]] == l && lanes_log2_for(rowlen(ord[p + cnt]), U) == z) ++cnt;
     const unsigned width = (rowlen(ord[p]) + lpr - 1u) >> z;  // rows are sorted by length: the first is the longest
     sdesc.push_back(make_uint4(static_cast<unsigned>(cols.size() / 32u), width, z, l));
     const std::size_t c0 = cols.size();
@@ -283,18 +302,43 @@ void pack_stream(const HostCsr &S, StreamHost &H) {
       padded += static_cast<std::size_t>(width) * lpr - (e - b);
     }
     p += cnt;
-    // a chunk (8 slices) never straddles two level sets: pad with empty slices
-    if (p == m || lev[ord[p]] != l) {
-      while (sdesc.size() % kStreamWarps) {
-        sdesc.push_back(make_uint4(static_cast<unsigned>(cols.size() / 32u), 0u, 0u, l));
-        for (unsigned j = 0; j < 32u; ++j) codes.push_back(kPadCode);
-      }
-    }
-    if (sdesc.size() % kStreamWarps == 0 && (p == m || lev[ord[p]] != l || true)) {
-      // count the chunk that was just completed
-    }
   }
-  for (std::size_t c = 0; c < sdesc.size() / kStreamWarps; ++c) ++H.lvl_need[sdesc[c * kStreamWarps].w];
+  // ---- chunks: 8 slice descriptors each (one per warp of a CTA), all of one level set.  A
+  // thin level set is spread over as many CTAs (SMs) as possible -- an SM serves one L2 request
+  // per clock, so the gathers of a full chunk alone take ~1 us -- a wide one uses full chunks.
+  {
+    const char *          es          = std::getenv("HIFIR_B200_STREAM_SPREAD");
+    const bool            spread_thin = !es || std::atoi(es) != 0;
+    std::vector<uint4>    sd2;
+    std::vector<unsigned> cd2;
+    const std::size_t     ns = sdesc.size();
+    sd2.reserve(ns + ns / 4);
+    cd2.reserve(codes.size() + codes.size() / 4);
+    for (std::size_t s0 = 0; s0 < ns;) {
+      const unsigned l  = sdesc[s0].w;
+      std::size_t    s1 = s0;
+      while (s1 < ns && sdesc[s1].w == l) ++s1;
+      const std::size_t S = s1 - s0;
+      // up to 4 SMs' worth of slices: one chunk per SM, beyond: full chunks (throughput matters)
+      const unsigned spc = (S > 4u * kNumSMs || !spread_thin) ? kStreamWarps
+                                            : static_cast<unsigned>(std::max<std::size_t>(1, (S + kNumSMs - 1) / kNumSMs));
+      for (std::size_t s = s0; s < s1; s += spc) {
+        for (unsigned w = 0; w < kStreamWarps; ++w) {
+          if (w < spc && s + w < s1) {
+            sd2.push_back(sdesc[s + w]);
+            cd2.insert(cd2.end(), codes.begin() + (s + w) * 32u, codes.begin() + (s + w + 1) * 32u);
+          } else {
+            sd2.push_back(make_uint4(0u, 0u, kEmptySlice, l));
+            cd2.insert(cd2.end(), 32u, kPadCode);
+          }
+        }
+        ++H.lvl_need[l];
+      }
+      s0 = s1;
+    }
+    sdesc.swap(sd2);
+    codes.swap(cd2);
+  }
   if (cols.size() / 32u > 0xffffffffull) throw std::length_error("stream plan too large");
   H.padded = padded;
   H.depth  = depth;
@@ -309,7 +353,8 @@ void build_stream_plan(const HostCsr &S, bool upper, SweepPlan &plan, std::size_
   plan.nblocks = 0;
   if (!S.nrows) return;
   StreamHost H;
-  pack_stream(S, H);
+  plan.st_u = stream_unroll();
+  pack_stream(S, H, plan.st_u);
   plan.nblocks    = static_cast<unsigned>(H.sdesc.size());  // slices
   plan.slab_bytes = H.cols.size() * 12u + H.codes.size() * 4u + H.sdesc.size() * 16u;
   plan.st_depth   = H.depth;
@@ -328,10 +373,11 @@ void build_stream_plan(const HostCsr &S, bool upper, SweepPlan &plan, std::size_
 void stream_host_emulate(const HostCsr &S, bool upper, const double *rhs, const double *diag, double *x,
                          std::size_t stats[4]) {
   StreamHost H;
-  pack_stream(S, H);
+  pack_stream(S, H, stream_unroll());
   const unsigned m = static_cast<unsigned>(S.orig_rows);
   for (std::size_t s = 0; s < H.sdesc.size(); ++s) {
-    const uint4       sd   = H.sdesc[s];
+    const uint4 sd = H.sdesc[s];
+    if (sd.z == kEmptySlice) continue;
     const std::size_t base = static_cast<std::size_t>(sd.x) * 32u;
     const unsigned    lpr  = 1u << sd.z;
     for (unsigned lane = 0; lane < 32u; lane += lpr) {
@@ -363,24 +409,32 @@ int stream_env(const char *name, int dflt) {
   const char *e = std::getenv(name);
   return e ? std::atoi(e) : dflt;
 }
-template <bool UPPER>
+template <bool UPPER, int kU>
 void launch_stream_T(Handle *h, const SweepPlan &plan, const double *rhs_plain, const unsigned long long *rhs_tagged,
                      const double *diag, unsigned long long *x, unsigned parity, int *sync, unsigned long long *trace) {
   static int ctas_per_sm = 0;
   if (!ctas_per_sm) {
-    HIF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, sweep_stream_kernel<UPPER>,
+    HIF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, sweep_stream_kernel<UPPER, kU>,
                                                            static_cast<int>(kStreamThreads), 0));
     if (ctas_per_sm < 1) ctas_per_sm = 1;
   }
-  const unsigned window = static_cast<unsigned>(std::max(1, stream_env("HIFIR_B200_STREAM_WINDOW", 3)));
+  const unsigned window = static_cast<unsigned>(std::max(1, stream_env("HIFIR_B200_STREAM_WINDOW", 2)));
   const unsigned sleep  = static_cast<unsigned>(std::max(20, stream_env("HIFIR_B200_STREAM_SLEEP", 300)));
   const unsigned near_sleep = static_cast<unsigned>(std::max(0, stream_env("HIFIR_B200_STREAM_NEAR_SLEEP", 0)));
   const unsigned poll_sleep = static_cast<unsigned>(std::max(0, stream_env("HIFIR_B200_STREAM_POLL_SLEEP", 0)));
   const unsigned grid   = std::min<unsigned>(plan.st_chunks + 1u, static_cast<unsigned>(kNumSMs * ctas_per_sm));
-  sweep_stream_kernel<UPPER><<<grid, kStreamThreads, 0, h->stream>>>(
+  sweep_stream_kernel<UPPER, kU><<<grid, kStreamThreads, 0, h->stream>>>(
       plan.st_chunks, reinterpret_cast<const uint4 *>(plan.st_sdesc.p), plan.st_need.p, plan.st_codes.p,
       plan.st_cols.p, plan.st_vals.p, plan.m, rhs_plain, rhs_tagged, diag, x, parity, sync, h->error_flag.p, window,
-      sleep, near_sleep, poll_sleep, trace);
+      sleep, near_sleep, poll_sleep, stream_env("HIFIR_B200_STREAM_L1", 0), trace);
+}
+template <bool UPPER>
+void launch_stream_U(Handle *h, const SweepPlan &plan, const double *rhs_plain, const unsigned long long *rhs_tagged,
+                     const double *diag, unsigned long long *x, unsigned parity, int *sync, unsigned long long *trace) {
+  if (plan.st_u == 4)
+    launch_stream_T<UPPER, 4>(h, plan, rhs_plain, rhs_tagged, diag, x, parity, sync, trace);
+  else
+    launch_stream_T<UPPER, 8>(h, plan, rhs_plain, rhs_tagged, diag, x, parity, sync, trace);
 }
 }  // namespace
 
@@ -394,9 +448,9 @@ void launch_stream_sweep(Handle *h, const SweepPlan &plan, const double *rhs_pla
   if (stream_env("HIFIR_B200_STREAM_PRESET", 1))
     HIF_CUDA(cudaMemsetAsync(x, parity ? 0x00 : 0xff, 2ull * plan.m * sizeof(unsigned long long), h->stream));
   if (plan.upper)
-    launch_stream_T<true>(h, plan, rhs_plain, rhs_tagged, diag, x, parity, ticket, trace);
+    launch_stream_U<true>(h, plan, rhs_plain, rhs_tagged, diag, x, parity, ticket, trace);
   else
-    launch_stream_T<false>(h, plan, rhs_plain, rhs_tagged, diag, x, parity, ticket, trace);
+    launch_stream_U<false>(h, plan, rhs_plain, rhs_tagged, diag, x, parity, ticket, trace);
   HIF_KERNEL_CHECK();
   ++h->launch_count;
 }

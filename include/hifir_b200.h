@@ -189,6 +189,9 @@ enum {
   LHF_GPU_STAT_KERNELS_PER_APPLY, /* kernels launched by one nrhs=1 apply */
   LHF_GPU_STAT_DEPTH_TOTAL,     /* sum of dependency depths of all triangular sweeps in one apply */
   LHF_GPU_STAT_LAUNCH_COUNT,    /* kernels launched by this handle since attach */
+  LHF_GPU_STAT_DEPTH_MERGED,    /* the same sum after the algebraic level merging done at attach */
+  LHF_GPU_STAT_SWEEP_BYTES,     /* bytes of the merged, packed factors streamed by the sweeps of one apply */
+  LHF_GPU_STAT_SWEEP_ENTRIES,   /* entries (= gathers of one solution value) of those sweeps per apply */
   LHF_GPU_NUMBER_STATS
 };
 LhfStatus lhfdGpuGetStats(LhfdGpuHdl hdl, size_t stats[/* LHF_GPU_NUMBER_STATS */]);

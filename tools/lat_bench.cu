@@ -133,6 +133,25 @@ __global__ void gather8(const unsigned long long *x, const unsigned *idx, int ro
   if (threadIdx.x == 0) out[0] = clock64() - t0;
 }
 
+// throughput of random 8-byte gathers from an L2-resident buffer, whole GPU
+template <int MODE>
+__global__ void gather_rate(const unsigned long long *x, unsigned n, int iters, unsigned long long *sink) {
+  unsigned           s   = (blockIdx.x * blockDim.x + threadIdx.x) * 2654435761u + 12345u;
+  unsigned long long acc = 0;
+  for (int it = 0; it < iters; ++it) {
+    unsigned long long g[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      s ^= s << 13, s ^= s >> 17, s ^= s << 5;
+      const unsigned i = s % n;
+      g[u] = MODE == 0 ? ld_relaxed(x + i) : (MODE == 1 ? ld_cg(x + i) : x[i]);
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) acc += g[u];
+  }
+  if (acc == 42) sink[0] = acc;
+}
+
 int main() {
   int clk = 0;
   cudaDeviceGetAttribute(&clk, cudaDevAttrClockRate, 0);
@@ -215,6 +234,34 @@ int main() {
       cudaDeviceSynchronize();
       printf("gather8 (32 lanes x 8 ld.relaxed.gpu, data written by other SMs): %.0f cyc (%.0f ns) per round\n",
              (double)out[0] / rounds, out[0] * ns / rounds);
+    }
+  }
+  {  // gather throughput
+    const unsigned      n = 4u << 20;  // 32 MB
+    unsigned long long *x;
+    cudaMalloc(&x, (size_t)n * 8);
+    cudaMemset(x, 1, (size_t)n * 8);
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0), cudaEventCreate(&e1);
+    for (int threads : {256}) {
+      for (int ctas : {148 * 2, 148 * 4, 148 * 8}) {
+        const int iters = 200;
+        float     ms[3];
+        for (int mode = 0; mode < 3; ++mode) {
+          for (int rep = 0; rep < 2; ++rep) {
+            cudaEventRecord(e0);
+            if (mode == 0) gather_rate<0><<<ctas, threads>>>(x, n, iters, (unsigned long long *)out);
+            if (mode == 1) gather_rate<1><<<ctas, threads>>>(x, n, iters, (unsigned long long *)out);
+            if (mode == 2) gather_rate<2><<<ctas, threads>>>(x, n, iters, (unsigned long long *)out);
+            cudaEventRecord(e1);
+            cudaEventSynchronize(e1);
+            cudaEventElapsedTime(&ms[mode], e0, e1);
+          }
+        }
+        const double g = (double)ctas * threads * iters * 8;
+        printf("gather rate, %d CTAs x %d thr: ld.relaxed.gpu %.0f G/s  ld.cg %.0f G/s  ld %.0f G/s\n", ctas, threads,
+               g / ms[0] / 1e6, g / ms[1] / 1e6, g / ms[2] / 1e6);
+      }
     }
   }
   return 0;
