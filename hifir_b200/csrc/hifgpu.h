@@ -75,6 +75,7 @@ struct HostCsr {
   std::vector<unsigned> gid;
   std::size_t           orig_rows = 0;
 };
+constexpr unsigned kMrhsWidth = 8;  // columns processed together by the multi-rhs kernels
 constexpr unsigned kSyncStride = 32;  // ints between two level counters of a streaming sweep (stream.cu)
 constexpr unsigned kCodeZeroRhs = 0x80000000u, kCodeSlotMask = 0x7fffffffu;
 
@@ -230,7 +231,6 @@ HostCsr ccs_to_csr(const LhfdGpuCcs &c, const char *name);
 
 // ---- sptrsv.cu : block sync-free triangular sweeps
 void build_sweep_plan(const HostCsr &T, bool upper, SweepPlan &plan, std::size_t *tally, unsigned nr = 1);
-constexpr unsigned kMrhsWidth = 8;  // columns processed together by the multi-rhs kernels
 void sweep_host_emulate(const HostCsr &T, bool upper, const double *rhs, const double *diag, double *x,
                         std::size_t stats[4]);
 void sweep_block_graph(const HostCsr &T, bool upper, std::vector<unsigned> &info, std::vector<unsigned> &src_ptr,
@@ -244,10 +244,10 @@ void stream_host_emulate(const HostCsr &S, bool upper, const double *rhs, const 
                          std::size_t stats[4]);
 void launch_stream_sweep(Handle *h, const SweepPlan &plan, const double *rhs_plain,
                          const unsigned long long *rhs_tagged, const double *diag, unsigned long long *x,
-                         unsigned parity, int *ticket, unsigned long long *trace = nullptr);
+                         unsigned parity, int *ticket, unsigned long long *trace = nullptr, unsigned nr = 1);
 void launch_sweep(Handle *h, const SweepPlan &plan, const double *rhs_plain, const unsigned long long *rhs_tagged,
                   const double *diag, unsigned long long *x, unsigned parity, int *ticket,
-                  unsigned long long *trace = nullptr);
+                  unsigned long long *trace = nullptr, unsigned nr = 0);  // nr = 0: the plan's own width
 
 // ---- apply.cu : the multilevel M^{-1} apply on device vectors
 void apply_dev(Handle *h, const double *d_b, double *d_x, std::size_t rank);

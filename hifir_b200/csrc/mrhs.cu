@@ -9,6 +9,8 @@
 // Columns are processed kMrhsWidth (= 8) at a time: every work vector holds 8 values per
 // row (64 B: one coalesced, vectorised transaction per dependency) and every factor is
 // streamed ONCE for the 8 columns.  The schedule is the single-rhs one (apply.cu).
+#include <algorithm>
+
 #include "hifgpu.h"
 
 namespace hifgpu {
@@ -105,16 +107,21 @@ void ensure_mrhs(Handle *h) {
   if (h->mrhs_ready) return;
   std::size_t *tally = &h->device_bytes;
   for (DevLevel &D : h->levels) {
-    build_sweep_plan(D.hostL, false, D.Lm, tally, NR);
-    build_sweep_plan(D.hostU, true, D.Um, tally, NR);
+    // the streaming plans (stream.cu) serve any width; the slab kernels need their own packing
+    if (!D.L.stream) {
+      build_sweep_plan(D.hostL, false, D.Lm, tally, NR);
+      build_sweep_plan(D.hostU, true, D.Um, tally, NR);
+    }
     D.m_bhat.alloc(D.n * NR, tally);
     D.m_g.alloc(D.m * NR, tally);
     D.m_r.alloc(D.nm * NR, tally);
     D.m_ychild.alloc(D.nm * NR, tally);
-    D.m_xL_dn.alloc(D.m * NR, tally);
-    D.m_xU_dn.alloc(D.m * NR, tally);
-    D.m_xL_up.alloc(D.m * NR, tally);
-    D.m_xU_up.alloc(D.m * NR, tally);
+    // m solution slots + m slots for the auxiliary unknowns of merge.cu, NR values each
+    D.m_xL_dn.alloc(2 * D.m * NR, tally);
+    D.m_xU_dn.alloc(2 * D.m * NR, tally);
+    D.m_xL_up.alloc(2 * D.m * NR, tally);
+    D.m_xU_up.alloc(2 * D.m * NR, tally);
+
   }
   const std::size_t n = h->n0();
   h->mr_b.alloc(n * NR, tally);
@@ -148,8 +155,10 @@ static void apply_chunk(Handle *h, const double *d_in, double *d_out, std::size_
     }
     if (D.nm) {
       if (D.m) {
-        launch_sweep(h, D.Lm, D.m_bhat.p, nullptr, nullptr, D.m_xL_dn.p, parity, h->tick(4 * l));
-        launch_sweep(h, D.Um, nullptr, D.m_xL_dn.p, D.d.p, D.m_xU_dn.p, parity, h->tick(4 * l + 1));
+        launch_sweep(h, D.L.stream ? D.L : D.Lm, D.m_bhat.p, nullptr, nullptr, D.m_xL_dn.p, parity, h->tick(4 * l),
+                     nullptr, NR);
+        launch_sweep(h, D.U.stream ? D.U : D.Um, nullptr, D.m_xL_dn.p, D.d.p, D.m_xU_dn.p, parity,
+                     h->tick(4 * l + 1), nullptr, NR);
       }
       spmv_resid_m_kernel<true><<<cdiv(D.nm * NR, T), T, 0, h->stream>>>(
           static_cast<unsigned>(D.nm), D.E.ptr.p, D.E.col.p, D.E.val.p, D.m_xU_dn.p, D.m_bhat.p + D.m * NR, D.m_r.p);
@@ -183,8 +192,10 @@ static void apply_chunk(Handle *h, const double *d_in, double *d_out, std::size_
       rhs = D.m_g.p;
     }
     if (D.m) {
-      launch_sweep(h, D.Lm, rhs, nullptr, nullptr, D.m_xL_up.p, parity, h->tick(4 * l + 2));
-      launch_sweep(h, D.Um, nullptr, D.m_xL_up.p, D.d.p, D.m_xU_up.p, parity, h->tick(4 * l + 3));
+      launch_sweep(h, D.L.stream ? D.L : D.Lm, rhs, nullptr, nullptr, D.m_xL_up.p, parity, h->tick(4 * l + 2),
+                   nullptr, NR);
+      launch_sweep(h, D.U.stream ? D.U : D.Um, nullptr, D.m_xL_up.p, D.d.p, D.m_xU_up.p, parity,
+                   h->tick(4 * l + 3), nullptr, NR);
     }
     if (D.n) {
       scatter_scale_m_kernel<<<cdiv(D.n * NR, T), T, 0, h->stream>>>(

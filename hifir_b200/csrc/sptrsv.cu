@@ -1121,10 +1121,11 @@ void launch_mrhs(Handle *h, const SweepPlan &plan, const double *rhs_plain, cons
 }  // namespace
 
 void launch_sweep(Handle *h, const SweepPlan &plan, const double *rhs_plain, const unsigned long long *rhs_tagged,
-                  const double *diag, unsigned long long *x, unsigned parity, int *ticket, unsigned long long *trace) {
+                  const double *diag, unsigned long long *x, unsigned parity, int *ticket, unsigned long long *trace,
+                  unsigned nr) {
   if (!plan.nblocks) return;
   if (plan.stream) {
-    launch_stream_sweep(h, plan, rhs_plain, rhs_tagged, diag, x, parity, ticket, trace);
+    launch_stream_sweep(h, plan, rhs_plain, rhs_tagged, diag, x, parity, ticket, trace, nr ? nr : plan.nr);
     return;
   }
   if (plan.nr > 1) {

@@ -78,8 +78,20 @@ __device__ __forceinline__ unsigned long long stream_timer_ns() {
   return t;
 }
 
-template <bool UPPER, int kU>
-__global__ void __launch_bounds__(kStreamThreads, kU == 4 ? 5 : 3)
+__device__ __forceinline__ void ld_poll_v2(const unsigned long long *p, unsigned long long &a, unsigned long long &b) {
+  asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
+}
+__device__ __forceinline__ void st_publish_v2(unsigned long long *p, unsigned long long a, unsigned long long b) {
+  asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(a), "l"(b) : "memory");
+}
+
+// NR right-hand sides per row (row-interleaved, X[i*NR + c], the Array<std::array<T,Nrhs>>
+// layout of hif::HIF::solve_mrhs, builder.hpp:433-445; per-column arithmetic =
+// CCS::solve_as_strict_lower/upper_mrhs, CompressedStorage.hpp:2286-2301, 2376-2393): a lane keeps
+// NR accumulators, a dependency is ONE 64-byte gather (NR = 8) instead of eight 8-byte ones, and
+// the factor is streamed once for all NR columns.  Same plan (sliced ELL) as for NR = 1.
+template <bool UPPER, int kU, int NR>
+__global__ void __launch_bounds__(kStreamThreads, NR > 1 ? 2 : (kU == 4 ? 5 : 3))
     sweep_stream_kernel(const unsigned nchunks, const uint4 *__restrict__ sdesc, const unsigned *__restrict__ lvl_need,
                         const unsigned *__restrict__ codes, const unsigned *__restrict__ cols,
                         const double *__restrict__ vals, const unsigned m, const double *__restrict__ rhs_plain,
@@ -87,6 +99,9 @@ __global__ void __launch_bounds__(kStreamThreads, kU == 4 ? 5 : 3)
                         const unsigned parity, int *sync, int *error_flag, const unsigned window,
                         const unsigned adm_sleep, const unsigned near_sleep, const unsigned poll_sleep,
                         const int use_l1, unsigned long long *trace) {
+  static_assert(NR == 1 || NR % 2 == 0, "NR must be 1 or even (128-bit transactions)");
+  constexpr int kG = NR == 1 ? kU : 2;  // entries whose gathers are in flight together
+  static_assert(kU % kG == 0, "kU must be a multiple of the gather group");
   __shared__ unsigned s_c;
   __shared__ int      s_last;
   const unsigned      warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
@@ -107,7 +122,7 @@ __global__ void __launch_bounds__(kStreamThreads, kU == 4 ? 5 : 3)
     const unsigned code = idle ? kPadCode : codes[static_cast<std::size_t>(s) * 32u + lane];
     const unsigned lpr  = idle ? 1u : 1u << sd.z;
     const bool     act  = code != kPadCode && (lane & (lpr - 1u)) == 0u;  // the lane that owns the row
-    const unsigned slot = code & kCodeSlotMask;
+    const std::size_t slot = static_cast<std::size_t>(code & kCodeSlotMask);
     const std::size_t base = static_cast<std::size_t>(sd.x) * 32u + lane;
     const unsigned    len  = sd.y;
     // ---- everything that does not depend on other rows: factor entries, right-hand side
@@ -121,15 +136,21 @@ __global__ void __launch_bounds__(kStreamThreads, kU == 4 ? 5 : 3)
         vv[u] = ld_stream_f64(vals + base + static_cast<std::size_t>(u) * 32u);
       }
     }
-    double acc = 0.0;
+    double acc[NR];
+#pragma unroll
+    for (int q = 0; q < NR; ++q) acc[q] = 0.0;
     if (act && !(code & kCodeZeroRhs)) {
-      // b_i (L sweep) or (L^{-1} b)_i / d_i with a true division (prec_solve.hpp:219) for the
-      // U sweep; slots >= m are the auxiliary unknowns of merge.cu
-      const unsigned ri = slot >= m ? slot - m : slot;
-      if (UPPER)
-        acc = tag_value(rhs_tagged[ri]) / diag[ri];
-      else
-        acc = rhs_plain[ri];
+      // b_i (L sweep) or (L^{-1} b)_i / d_i with a true division (prec_solve.hpp:219, :256-259)
+      // for the U sweep; slots >= m are the auxiliary unknowns of merge.cu
+      const std::size_t ri = slot >= m ? slot - m : slot;
+      if (UPPER) {
+        const double d = diag[ri];
+#pragma unroll
+        for (int q = 0; q < NR; ++q) acc[q] = tag_value(rhs_tagged[ri * NR + q]) / d;
+      } else {
+#pragma unroll
+        for (int q = 0; q < NR; ++q) acc[q] = rhs_plain[ri * NR + q];
+      }
     }
     // ---- admission: level sd.w - window complete (thread 0 polls for the CTA).  sync[16] =
     // highest completed level + 1 (a hint): far-away waiters sleep in proportion to their distance
@@ -172,40 +193,61 @@ __global__ void __launch_bounds__(kStreamThreads, kU == 4 ? 5 : 3)
     if (trace && threadIdx.x == 0) trace[8 * c + 2] = stream_timer_ns();  // admitted
     __syncthreads();
     // ---- gather the dependencies optimistically, re-poll the ones that are not ready
+    auto gather = [&](unsigned col, unsigned long long(&g)[NR], bool first) {
+      const unsigned long long *src = x + static_cast<std::size_t>(col) * NR;
+      if (NR == 1) {
+        g[0] = (first && use_l1) ? ld_l1(src) : ld_poll(src);
+      } else {
+#pragma unroll
+        for (int q = 0; q < NR; q += 2) ld_poll_v2(src + q, g[q], g[q + 1]);
+      }
+    };
+    auto ready = [&](const unsigned long long(&g)[NR]) {
+      bool ok = true;
+#pragma unroll
+      for (int q = 0; q < NR; ++q) ok &= tag_ready(g[q], parity);
+      return ok;
+    };
     for (unsigned k = 0;;) {
-      unsigned long long g[kU];
 #pragma unroll
-      for (int u = 0; u < kU; ++u)
-        if (cc[u] != kPadCol) g[u] = use_l1 ? ld_l1(x + cc[u]) : ld_poll(x + cc[u]);
-      if (trace && threadIdx.x == 0 && k == 0) {  // warp 0: first gather round trip
-        unsigned long long any = 0;
+      for (int u0 = 0; u0 < kU; u0 += kG) {
+        unsigned long long g[kG][NR];
 #pragma unroll
-        for (int u = 0; u < kU; ++u)
-          if (cc[u] != kPadCol) any |= g[u];
-        trace[8 * c + 6] = stream_timer_ns() + (any == 0x7ff8dead00000001ull ? 1u : 0u);
-      }
-      // entries that were not ready on the first try (padding counts as ready) are re-polled
-      // TOGETHER, round by round: one L2 round trip per round whatever their number
-      unsigned pend = 0;
+        for (int j = 0; j < kG; ++j)
+          if (cc[u0 + j] != kPadCol) gather(cc[u0 + j], g[j], true);
+        if (trace && threadIdx.x == 0 && k == 0 && u0 == 0) {  // warp 0: first gather round trip
+          unsigned long long any = 0;
 #pragma unroll
-      for (int u = 0; u < kU; ++u)
-        if (cc[u] != kPadCol && !tag_ready(g[u], parity)) pend |= 1u << u;
-      for (unsigned rounds = 0; __any_sync(0xffffffffu, pend != 0u);) {
-        if (poll_sleep) __nanosleep(poll_sleep);
-#pragma unroll
-        for (int u = 0; u < kU; ++u)
-          if (pend & (1u << u)) g[u] = ld_poll(x + cc[u]);
-#pragma unroll
-        for (int u = 0; u < kU; ++u)
-          if ((pend & (1u << u)) && tag_ready(g[u], parity)) pend &= ~(1u << u);
-        if (++rounds > (kSpinLimit >> 3)) {  // hang guard: flag the error, go on with garbage
-          *error_flag = 1;
-          break;
+          for (int j = 0; j < kG; ++j)
+            if (cc[j] != kPadCol) any |= g[j][0];
+          trace[8 * c + 6] = stream_timer_ns() + (any == 0x7ff8dead00000001ull ? 1u : 0u);
         }
-      }
+        // entries that were not ready on the first try (padding counts as ready) are re-polled
+        // TOGETHER, round by round: one L2 round trip per round whatever their number
+        unsigned pend = 0;
 #pragma unroll
-      for (int u = 0; u < kU; ++u)
-        if (cc[u] != kPadCol) acc = fma(-vv[u], tag_value(g[u]), acc);
+        for (int j = 0; j < kG; ++j)
+          if (cc[u0 + j] != kPadCol && !ready(g[j])) pend |= 1u << j;
+        for (unsigned rounds = 0; __any_sync(0xffffffffu, pend != 0u);) {
+          if (poll_sleep) __nanosleep(poll_sleep);
+#pragma unroll
+          for (int j = 0; j < kG; ++j)
+            if (pend & (1u << j)) gather(cc[u0 + j], g[j], false);
+#pragma unroll
+          for (int j = 0; j < kG; ++j)
+            if ((pend & (1u << j)) && ready(g[j])) pend &= ~(1u << j);
+          if (++rounds > (kSpinLimit >> 3)) {  // hang guard: flag the error, go on with garbage
+            *error_flag = 1;
+            break;
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < kG; ++j)
+          if (cc[u0 + j] != kPadCol) {
+#pragma unroll
+            for (int q = 0; q < NR; ++q) acc[q] = fma(-vv[u0 + j], tag_value(g[j][q]), acc[q]);
+          }
+      }
       k += kU;
       if (k >= len) break;
 #pragma unroll
@@ -218,8 +260,19 @@ __global__ void __launch_bounds__(kStreamThreads, kU == 4 ? 5 : 3)
       }
     }
     if (trace && threadIdx.x == 0) trace[8 * c + 7] = stream_timer_ns();  // warp 0: all dependencies consumed
-    for (unsigned o = lpr >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if (act) st_publish(x + slot, tag_set(acc, parity));
+    for (unsigned o = lpr >> 1; o > 0; o >>= 1) {
+#pragma unroll
+      for (int q = 0; q < NR; ++q) acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], o);
+    }
+    if (act) {
+      if (NR == 1) {
+        st_publish(x + slot, tag_set(acc[0], parity));
+      } else {
+#pragma unroll
+        for (int q = 0; q < NR; q += 2)
+          st_publish_v2(x + slot * NR + q, tag_set(acc[q], parity), tag_set(acc[q + 1 < NR ? q + 1 : q], parity));
+      }
+    }
     if (trace && lane == 0) atomicMax(trace + 8 * c + 3, stream_timer_ns());  // last warp published
   }
 }
@@ -235,9 +288,10 @@ struct StreamHost {
   unsigned              depth = 0;
 };
 
-unsigned lanes_log2_for(unsigned len, unsigned U) {  // lanes per row so that a lane holds <= U entries (max 32 lanes)
+// lanes per row (2^z <= R) so that a lane holds <= U entries if possible
+unsigned lanes_log2_for(unsigned len, unsigned U, unsigned R) {
   unsigned z = 0;
-  while (z < 5u && ((len + (1u << z) - 1u) >> z) > U) ++z;
+  while ((2u << z) <= R && ((len + (1u << z) - 1u) >> z) > U) ++z;
   return z;
 }
 unsigned stream_unroll() {
@@ -245,7 +299,7 @@ unsigned stream_unroll() {
   return e && std::atoi(e) == 8 ? 8u : 4u;
 }
 
-void pack_stream(const HostCsr &S, StreamHost &H, unsigned U) {
+void pack_stream(const HostCsr &S, StreamHost &H, unsigned U, unsigned R = 32u) {
   const unsigned m = static_cast<unsigned>(S.nrows);
   if (!m) return;
   if (S.gid.size() != m) throw std::logic_error("build_stream_plan: factor is not in sweep form");
@@ -274,14 +328,14 @@ void pack_stream(const HostCsr &S, StreamHost &H, unsigned U) {
   std::size_t padded = 0;
   for (unsigned p = 0; p < m;) {
     // one slice: rows of one level set with the same lanes-per-row class
-    const unsigned l = lev[ord[p]], z = lanes_log2_for(rowlen(ord[p]), U), lpr = 1u << z, cap = 32u >> z;
+    const unsigned l = lev[ord[p]], z = lanes_log2_for(rowlen(ord[p]), U, R), lpr = 1u << z, cap = R >> z;
     unsigned       cnt = 1;
-    while (cnt < cap && p + cnt < m && lev[ord[p + cnt]] == l && lanes_log2_for(rowlen(ord[p + cnt]), U) == z) ++cnt;
+    while (cnt < cap && p + cnt < m && lev[ord[p + cnt]] == l && lanes_log2_for(rowlen(ord[p + cnt]), U, R) == z) ++cnt;
     const unsigned width = (rowlen(ord[p]) + lpr - 1u) >> z;  // rows are sorted by length: the first is the longest
-    sdesc.push_back(make_uint4(static_cast<unsigned>(cols.size() / 32u), width, z, l));
+    sdesc.push_back(make_uint4(static_cast<unsigned>(cols.size() / R), width, z, l));
     const std::size_t c0 = cols.size();
-    cols.resize(c0 + static_cast<std::size_t>(width) * 32u, kPadCol);
-    vals.resize(c0 + static_cast<std::size_t>(width) * 32u, 0.0);
+    cols.resize(c0 + static_cast<std::size_t>(width) * R, kPadCol);
+    vals.resize(c0 + static_cast<std::size_t>(width) * R, 0.0);
     for (unsigned r = 0; r < cap; ++r) {
       if (r >= cnt) {
         for (unsigned j = 0; j < lpr; ++j) codes.push_back(kPadCode);
@@ -295,7 +349,7 @@ void pack_stream(const HostCsr &S, StreamHost &H, unsigned U) {
       std::iota(ent.begin(), ent.end(), b);
       std::stable_sort(ent.begin(), ent.end(), [&](unsigned x, unsigned y) { return lev[S.col[x]] < lev[S.col[y]]; });
       for (unsigned q = 0; q < e - b; ++q) {  // entry q of the row -> lane r*lpr + q%lpr, position q/lpr
-        const std::size_t at = c0 + static_cast<std::size_t>(q >> z) * 32u + r * lpr + (q & (lpr - 1u));
+        const std::size_t at = c0 + static_cast<std::size_t>(q >> z) * R + r * lpr + (q & (lpr - 1u));
         cols[at]             = S.gid[S.col[ent[q]]] & kCodeSlotMask;
         vals[at]             = S.val[ent[q]];
       }
@@ -326,10 +380,10 @@ void pack_stream(const HostCsr &S, StreamHost &H, unsigned U) {
         for (unsigned w = 0; w < kStreamWarps; ++w) {
           if (w < spc && s + w < s1) {
             sd2.push_back(sdesc[s + w]);
-            cd2.insert(cd2.end(), codes.begin() + (s + w) * 32u, codes.begin() + (s + w + 1) * 32u);
+            cd2.insert(cd2.end(), codes.begin() + (s + w) * R, codes.begin() + (s + w + 1) * R);
           } else {
             sd2.push_back(make_uint4(0u, 0u, kEmptySlice, l));
-            cd2.insert(cd2.end(), 32u, kPadCode);
+            cd2.insert(cd2.end(), R, kPadCode);
           }
         }
         ++H.lvl_need[l];
@@ -339,7 +393,7 @@ void pack_stream(const HostCsr &S, StreamHost &H, unsigned U) {
     sdesc.swap(sd2);
     codes.swap(cd2);
   }
-  if (cols.size() / 32u > 0xffffffffull) throw std::length_error("stream plan too large");
+  if (cols.size() / R > 0xffffffffull) throw std::length_error("stream plan too large");
   H.padded = padded;
   H.depth  = depth;
 }
@@ -348,7 +402,7 @@ void pack_stream(const HostCsr &S, StreamHost &H, unsigned U) {
 void build_stream_plan(const HostCsr &S, bool upper, SweepPlan &plan, std::size_t *tally) {
   plan.stream  = true;
   plan.upper   = upper;
-  plan.nr      = 1;
+  plan.nr      = 1;  // the same plan serves the multi-rhs kernel (launch_stream_sweep, nr = kMrhsWidth)
   plan.m       = static_cast<unsigned>(S.orig_rows);
   plan.nblocks = 0;
   if (!S.nrows) return;
@@ -409,12 +463,12 @@ int stream_env(const char *name, int dflt) {
   const char *e = std::getenv(name);
   return e ? std::atoi(e) : dflt;
 }
-template <bool UPPER, int kU>
+template <bool UPPER, int kU, int NR>
 void launch_stream_T(Handle *h, const SweepPlan &plan, const double *rhs_plain, const unsigned long long *rhs_tagged,
                      const double *diag, unsigned long long *x, unsigned parity, int *sync, unsigned long long *trace) {
   static int ctas_per_sm = 0;
   if (!ctas_per_sm) {
-    HIF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, sweep_stream_kernel<UPPER, kU>,
+    HIF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, sweep_stream_kernel<UPPER, kU, NR>,
                                                            static_cast<int>(kStreamThreads), 0));
     if (ctas_per_sm < 1) ctas_per_sm = 1;
   }
@@ -423,34 +477,40 @@ void launch_stream_T(Handle *h, const SweepPlan &plan, const double *rhs_plain, 
   const unsigned near_sleep = static_cast<unsigned>(std::max(0, stream_env("HIFIR_B200_STREAM_NEAR_SLEEP", 0)));
   const unsigned poll_sleep = static_cast<unsigned>(std::max(0, stream_env("HIFIR_B200_STREAM_POLL_SLEEP", 0)));
   const unsigned grid   = std::min<unsigned>(plan.st_chunks + 1u, static_cast<unsigned>(kNumSMs * ctas_per_sm));
-  sweep_stream_kernel<UPPER, kU><<<grid, kStreamThreads, 0, h->stream>>>(
+  sweep_stream_kernel<UPPER, kU, NR><<<grid, kStreamThreads, 0, h->stream>>>(
       plan.st_chunks, reinterpret_cast<const uint4 *>(plan.st_sdesc.p), plan.st_need.p, plan.st_codes.p,
       plan.st_cols.p, plan.st_vals.p, plan.m, rhs_plain, rhs_tagged, diag, x, parity, sync, h->error_flag.p, window,
       sleep, near_sleep, poll_sleep, stream_env("HIFIR_B200_STREAM_L1", 0), trace);
 }
 template <bool UPPER>
 void launch_stream_U(Handle *h, const SweepPlan &plan, const double *rhs_plain, const unsigned long long *rhs_tagged,
-                     const double *diag, unsigned long long *x, unsigned parity, int *sync, unsigned long long *trace) {
-  if (plan.st_u == 4)
-    launch_stream_T<UPPER, 4>(h, plan, rhs_plain, rhs_tagged, diag, x, parity, sync, trace);
+                     const double *diag, unsigned long long *x, unsigned parity, int *sync, unsigned long long *trace,
+                     unsigned nr) {
+  if (nr == kMrhsWidth && plan.st_u == 4)
+    launch_stream_T<UPPER, 4, static_cast<int>(kMrhsWidth)>(h, plan, rhs_plain, rhs_tagged, diag, x, parity, sync, trace);
+  else if (nr == kMrhsWidth)
+    launch_stream_T<UPPER, 8, static_cast<int>(kMrhsWidth)>(h, plan, rhs_plain, rhs_tagged, diag, x, parity, sync, trace);
+  else if (nr != 1u)
+    throw std::logic_error("unsupported multi-rhs width");
+  else if (plan.st_u == 4)
+    launch_stream_T<UPPER, 4, 1>(h, plan, rhs_plain, rhs_tagged, diag, x, parity, sync, trace);
   else
-    launch_stream_T<UPPER, 8>(h, plan, rhs_plain, rhs_tagged, diag, x, parity, sync, trace);
+    launch_stream_T<UPPER, 8, 1>(h, plan, rhs_plain, rhs_tagged, diag, x, parity, sync, trace);
 }
 }  // namespace
 
 void launch_stream_sweep(Handle *h, const SweepPlan &plan, const double *rhs_plain,
                          const unsigned long long *rhs_tagged, const double *diag, unsigned long long *x,
-                         unsigned parity, int *ticket, unsigned long long *trace) {
+                         unsigned parity, int *ticket, unsigned long long *trace, unsigned nr) {
   if (!plan.nblocks) return;
-  // Pre-set the solution buffer to "not ready" with FULL-sector writes: an 8-byte store into a
-  // sector that is not resident in L2 leaves it partially valid, and the first load of the value
-  // then waits for a fill from HBM (~1 us instead of an L2 hit)
-  if (stream_env("HIFIR_B200_STREAM_PRESET", 1))
-    HIF_CUDA(cudaMemsetAsync(x, parity ? 0x00 : 0xff, 2ull * plan.m * sizeof(unsigned long long), h->stream));
+  // experiment: pre-set the solution buffer to "not ready" with full-sector writes (in case the
+  // first load of a value stored into a non-resident sector waited for a fill) -- measured: no effect
+  if (stream_env("HIFIR_B200_STREAM_PRESET", 0))
+    HIF_CUDA(cudaMemsetAsync(x, parity ? 0x00 : 0xff, 2ull * plan.m * nr * sizeof(unsigned long long), h->stream));
   if (plan.upper)
-    launch_stream_U<true>(h, plan, rhs_plain, rhs_tagged, diag, x, parity, ticket, trace);
+    launch_stream_U<true>(h, plan, rhs_plain, rhs_tagged, diag, x, parity, ticket, trace, nr);
   else
-    launch_stream_U<false>(h, plan, rhs_plain, rhs_tagged, diag, x, parity, ticket, trace);
+    launch_stream_U<false>(h, plan, rhs_plain, rhs_tagged, diag, x, parity, ticket, trace, nr);
   HIF_KERNEL_CHECK();
   ++h->launch_count;
 }
