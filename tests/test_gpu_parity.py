@@ -51,6 +51,23 @@ def test_solve_matches_golden_and_oracle(golden):
         assert np.array_equal(x1, x3) and relerr(x2, x1) <= 1e-14
 
 
+@pytest.mark.parametrize("mode", [("stream", "0"), ("slab", "1"), ("slab", "0")], ids=lambda m: f"{m[0]}-merge{m[1]}")
+def test_solve_other_sweep_kernels(golden, mode, monkeypatch):
+    """The non-default sweep configurations (HIFIR_B200_SWEEP / HIFIR_B200_MERGE are read at attach):
+    unmerged factors on the streaming kernel, merged and unmerged factors on the shared-memory slab
+    kernel -- single and multi right-hand side."""
+    monkeypatch.setenv("HIFIR_B200_SWEEP", mode[0])
+    monkeypatch.setenv("HIFIR_B200_MERGE", mode[1])
+    with _gpu(golden) as G:
+        for k in range(2):
+            b = np.ascontiguousarray(golden["B"][:, k])
+            assert relerr(G.solve(b), golden["X"][:, k]) <= TOL_F64
+        if not golden.nsp:
+            X = G.solve_mrhs(np.ascontiguousarray(golden["B"]))
+            for k in range(golden["B"].shape[1]):
+                assert relerr(X[:, k], golden["X"][:, k]) <= TOL_F64
+
+
 def test_apply_semantics_follow_libhifir(golden):
     """lhfdApply (libhifir.cpp:447-472): op, nirs, betas, rank and ir_status."""
     with _gpu(golden) as G:
