@@ -93,8 +93,8 @@ __device__ __forceinline__ void st_publish_v2(unsigned long long *p, unsigned lo
 // CCS::solve_as_strict_lower/upper_mrhs, CompressedStorage.hpp:2286-2301, 2376-2393): a lane keeps
 // NR accumulators, a dependency is ONE 64-byte gather (NR = 8) instead of eight 8-byte ones, and
 // the factor is streamed once for all NR columns.  Same plan (sliced ELL) as for NR = 1.
-template <bool UPPER, int kU, int NR, int kW>
-__global__ void __launch_bounds__(kW * 32, (NR > 1 ? 2 : (kU == 4 ? 5 : 3)) * 8 / kW)
+template <bool UPPER, int kU, int NR, int kW, int kOcc>
+__global__ void __launch_bounds__(kW * 32, kOcc)
     sweep_stream_kernel(const unsigned nchunks, const uint4 *__restrict__ sdesc, const unsigned *__restrict__ lvl_need,
                         const unsigned *__restrict__ codes, const unsigned *__restrict__ cols,
                         const double *__restrict__ vals, const unsigned m, const double *__restrict__ rhs_plain,
@@ -105,18 +105,18 @@ __global__ void __launch_bounds__(kW * 32, (NR > 1 ? 2 : (kU == 4 ? 5 : 3)) * 8 
   static_assert(NR == 1 || NR % 2 == 0, "NR must be 1 or even (128-bit transactions)");
   constexpr int kG = NR == 1 ? kU : 2;  // entries whose gathers are in flight together
   static_assert(kU % kG == 0, "kU must be a multiple of the gather group");
-  __shared__ unsigned s_c;
+  __shared__ unsigned s_c[2];
   __shared__ int      s_last;
   const unsigned      warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
-  if (threadIdx.x == 0) s_last = -1;
-  for (;;) {
-    __syncthreads();  // every warp of the previous chunk has published
-    if (threadIdx.x == 0) {
-      if (s_last >= 0) atomicAdd(sync + kSyncStride * (1 + s_last), 1);  // fire and forget
-      s_c = static_cast<unsigned>(atomicAdd(sync, 1));
-    }
-    __syncthreads();
-    const unsigned c = s_c;
+  if (threadIdx.x == 0) {
+    s_last = -1;
+    s_c[0] = static_cast<unsigned>(atomicAdd(sync, 1));
+  }
+  unsigned f_seen = 0;  // thread 0: highest completed level + 1 it has reported
+  for (unsigned round = 0;; ++round) {
+    __syncthreads();  // every warp of the previous chunk has published; s_c[round & 1] is written
+    if (threadIdx.x == 0 && s_last >= 0) atomicAdd(sync + kSyncStride * (1 + s_last), 1);  // fire and forget
+    const unsigned c = s_c[round & 1u];
     if (c >= nchunks) break;
     if (trace && threadIdx.x == 0) trace[8 * c + 0] = stream_timer_ns();
     const unsigned s    = c * kW + warp;
@@ -172,7 +172,8 @@ __global__ void __launch_bounds__(kW * 32, (NR > 1 ? 2 : (kU == 4 ? 5 : 3)) * 8 
         const unsigned need  = lvl_need[t];
         const int *    ctr   = sync + kSyncStride * (1 + t);
         unsigned       spins = 0;
-        for (;;) {
+        // common case (wide level sets): the level is complete already -- one load
+        while (static_cast<unsigned>(ld_poll_i32(ctr)) < need) {
           const unsigned f = static_cast<unsigned>(ld_poll_i32(sync + 16));  // levels [0, f) are known to be done
           if (t < f + 2u) {
             while (static_cast<unsigned>(ld_poll_i32(ctr)) < need) {
@@ -182,7 +183,6 @@ __global__ void __launch_bounds__(kW * 32, (NR > 1 ? 2 : (kU == 4 ? 5 : 3)) * 8 
                 break;
               }
             }
-            if (t + 1u > f) atomicMax(sync + 16, static_cast<int>(t + 1u));  // advance the hint
             break;
           }
           __nanosleep(min((t - f) * adm_sleep, 20000u));
@@ -191,10 +191,18 @@ __global__ void __launch_bounds__(kW * 32, (NR > 1 ? 2 : (kU == 4 ? 5 : 3)) * 8 
             break;
           }
         }
+        if (t + 1u > f_seen) {  // advance the hint
+          f_seen = t + 1u;
+          atomicMax(sync + 16, static_cast<int>(f_seen));
+        }
       }
     }
     if (trace && threadIdx.x == 0) trace[8 * c + 2] = stream_timer_ns();  // admitted
     __syncthreads();
+    // the next ticket is fetched behind the gathers of this chunk (off the critical path); it is
+    // held for the ~1 us this chunk still needs, which delays nobody
+    unsigned next_ticket = 0;
+    const bool ticket_lane = threadIdx.x == (kW > 1 ? 32u : 0u);
     // ---- gather the dependencies optimistically, re-poll the ones that are not ready
     auto gather = [&](unsigned col, unsigned long long(&g)[NR], bool first) {
       const unsigned long long *src = x + static_cast<std::size_t>(col) * NR;
@@ -218,6 +226,7 @@ __global__ void __launch_bounds__(kW * 32, (NR > 1 ? 2 : (kU == 4 ? 5 : 3)) * 8 
 #pragma unroll
         for (int j = 0; j < kG; ++j)
           if (cc[u0 + j] != kPadCol) gather(cc[u0 + j], g[j], true);
+        if (ticket_lane && k == 0 && u0 == 0) next_ticket = static_cast<unsigned>(atomicAdd(sync, 1));
         if (trace && threadIdx.x == 0 && k == 0 && u0 == 0) {  // warp 0: first gather round trip
           unsigned long long any = 0;
 #pragma unroll
@@ -287,6 +296,7 @@ __global__ void __launch_bounds__(kW * 32, (NR > 1 ? 2 : (kU == 4 ? 5 : 3)) * 8 
       }
     }
     if (trace && lane == 0) atomicMax(trace + 8 * c + 3, stream_timer_ns());  // last warp published
+    if (ticket_lane) s_c[(round + 1u) & 1u] = next_ticket;
   }
 }
 
@@ -478,24 +488,37 @@ int stream_env(const char *name, int dflt) {
   const char *e = std::getenv(name);
   return e ? std::atoi(e) : dflt;
 }
-template <bool UPPER, int kU, int NR, int kW>
-void launch_stream_W(Handle *h, const SweepPlan &plan, const double *rhs_plain, const unsigned long long *rhs_tagged,
+template <bool UPPER, int kU, int NR, int kW, int kOcc>
+void launch_stream_O(Handle *h, const SweepPlan &plan, const double *rhs_plain, const unsigned long long *rhs_tagged,
                      const double *diag, unsigned long long *x, unsigned parity, int *sync, unsigned long long *trace) {
   static int ctas_per_sm = 0;
   if (!ctas_per_sm) {
-    HIF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, sweep_stream_kernel<UPPER, kU, NR, kW>,
+    HIF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, sweep_stream_kernel<UPPER, kU, NR, kW, kOcc>,
                                                            kW * 32, 0));
     if (ctas_per_sm < 1) ctas_per_sm = 1;
   }
-  const unsigned window = static_cast<unsigned>(std::max(1, stream_env("HIFIR_B200_STREAM_WINDOW", 2)));
+  const unsigned window = static_cast<unsigned>(std::max(1, stream_env("HIFIR_B200_STREAM_WINDOW", 3)));
   const unsigned sleep  = static_cast<unsigned>(std::max(20, stream_env("HIFIR_B200_STREAM_SLEEP", 300)));
   const unsigned near_sleep = static_cast<unsigned>(std::max(0, stream_env("HIFIR_B200_STREAM_NEAR_SLEEP", 0)));
   const unsigned poll_sleep = static_cast<unsigned>(std::max(0, stream_env("HIFIR_B200_STREAM_POLL_SLEEP", 0)));
   const unsigned grid   = std::min<unsigned>(plan.st_chunks + 1u, static_cast<unsigned>(kNumSMs * ctas_per_sm));
-  sweep_stream_kernel<UPPER, kU, NR, kW><<<grid, kW * 32, 0, h->stream>>>(
+  sweep_stream_kernel<UPPER, kU, NR, kW, kOcc><<<grid, kW * 32, 0, h->stream>>>(
       plan.st_chunks, reinterpret_cast<const uint4 *>(plan.st_sdesc.p), plan.st_need.p, plan.st_codes.p,
       plan.st_cols.p, plan.st_vals.p, plan.m, rhs_plain, rhs_tagged, diag, x, parity, sync, h->error_flag.p, window,
       sleep, near_sleep, poll_sleep, stream_env("HIFIR_B200_STREAM_L1", 0) | (stream_env("HIFIR_B200_STREAM_PUBLISH_ST", 0) ? 2 : 0), trace);
+}
+// CTAs per SM the kernel is compiled for (register budget): the sweep is bound by the number of
+// gathers in flight per SM, so occupancy is worth a few spilled registers
+template <bool UPPER, int kU, int NR, int kW>
+void launch_stream_W(Handle *h, const SweepPlan &plan, const double *rhs_plain, const unsigned long long *rhs_tagged,
+                     const double *diag, unsigned long long *x, unsigned parity, int *sync, unsigned long long *trace) {
+  constexpr int kBase = (NR > 1 ? 2 : (kU == 4 ? 5 : 3)) * 8 / kW;
+  if (NR == 1 && kU == 4 && kW == 8) {
+    const int occ = stream_env("HIFIR_B200_STREAM_OCC", 5);
+    if (occ == 6) return launch_stream_O<UPPER, kU, NR, kW, (NR == 1 && kU == 4 && kW == 8) ? 6 : kBase>(h, plan, rhs_plain, rhs_tagged, diag, x, parity, sync, trace);
+    if (occ == 8) return launch_stream_O<UPPER, kU, NR, kW, (NR == 1 && kU == 4 && kW == 8) ? 8 : kBase>(h, plan, rhs_plain, rhs_tagged, diag, x, parity, sync, trace);
+  }
+  launch_stream_O<UPPER, kU, NR, kW, kBase>(h, plan, rhs_plain, rhs_tagged, diag, x, parity, sync, trace);
 }
 template <bool UPPER, int kU, int NR>
 void launch_stream_T(Handle *h, const SweepPlan &plan, const double *rhs_plain, const unsigned long long *rhs_tagged,
