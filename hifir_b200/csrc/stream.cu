@@ -103,7 +103,7 @@ __global__ void __launch_bounds__(kW * 32, kOcc)
                         const unsigned adm_sleep, const unsigned near_sleep, const unsigned poll_sleep,
                         const int use_l1, unsigned long long *trace) {
   static_assert(NR == 1 || NR % 2 == 0, "NR must be 1 or even (128-bit transactions)");
-  constexpr int kG = NR == 1 ? kU : 2;  // entries whose gathers are in flight together
+  constexpr int kG = NR == 1 ? (kU > 4 ? 4 : kU) : 2;  // entries whose gathers are in flight together
   static_assert(kU % kG == 0, "kU must be a multiple of the gather group");
   __shared__ unsigned s_c[2];
   __shared__ int      s_last;
@@ -319,7 +319,8 @@ unsigned lanes_log2_for(unsigned len, unsigned U, unsigned R) {
 }
 unsigned stream_unroll() {
   const char *e = std::getenv("HIFIR_B200_STREAM_U");
-  return e && std::atoi(e) == 8 ? 8u : 4u;
+  const int u = e ? std::atoi(e) : 8;  // measured at 128^3: 4 -> 1.58 ms, 8 -> 1.37 ms per apply
+  return u == 4 ? 4u : (u == 16 ? 16u : 8u);
 }
 
 void pack_stream(const HostCsr &S, StreamHost &H, unsigned U, unsigned kStreamWarps, unsigned R = 32u) {
@@ -512,7 +513,7 @@ void launch_stream_O(Handle *h, const SweepPlan &plan, const double *rhs_plain, 
 template <bool UPPER, int kU, int NR, int kW>
 void launch_stream_W(Handle *h, const SweepPlan &plan, const double *rhs_plain, const unsigned long long *rhs_tagged,
                      const double *diag, unsigned long long *x, unsigned parity, int *sync, unsigned long long *trace) {
-  constexpr int kBase = (NR > 1 ? 2 : (kU == 4 ? 5 : 3)) * 8 / kW;
+  constexpr int kBase = (NR > 1 ? 2 : (kU == 4 ? 5 : (kU == 8 ? 4 : 2))) * 8 / kW;
   if (NR == 1 && kU == 4 && kW == 8) {
     const int occ = stream_env("HIFIR_B200_STREAM_OCC", 5);
     if (occ == 6) return launch_stream_O<UPPER, kU, NR, kW, (NR == 1 && kU == 4 && kW == 8) ? 6 : kBase>(h, plan, rhs_plain, rhs_tagged, diag, x, parity, sync, trace);
@@ -532,7 +533,9 @@ template <bool UPPER>
 void launch_stream_U(Handle *h, const SweepPlan &plan, const double *rhs_plain, const unsigned long long *rhs_tagged,
                      const double *diag, unsigned long long *x, unsigned parity, int *sync, unsigned long long *trace,
                      unsigned nr) {
-  if (nr == kMrhsWidth && plan.st_u == 4)
+  if (nr == kMrhsWidth && plan.st_u == 16)
+    throw std::logic_error("multi-rhs sweeps need a plan with 4 or 8 entries per lane");
+  else if (nr == kMrhsWidth && plan.st_u == 4)
     launch_stream_T<UPPER, 4, static_cast<int>(kMrhsWidth)>(h, plan, rhs_plain, rhs_tagged, diag, x, parity, sync, trace);
   else if (nr == kMrhsWidth)
     launch_stream_T<UPPER, 8, static_cast<int>(kMrhsWidth)>(h, plan, rhs_plain, rhs_tagged, diag, x, parity, sync, trace);
@@ -540,6 +543,8 @@ void launch_stream_U(Handle *h, const SweepPlan &plan, const double *rhs_plain, 
     throw std::logic_error("unsupported multi-rhs width");
   else if (plan.st_u == 4)
     launch_stream_T<UPPER, 4, 1>(h, plan, rhs_plain, rhs_tagged, diag, x, parity, sync, trace);
+  else if (plan.st_u == 16)
+    launch_stream_T<UPPER, 16, 1>(h, plan, rhs_plain, rhs_tagged, diag, x, parity, sync, trace);
   else
     launch_stream_T<UPPER, 8, 1>(h, plan, rhs_plain, rhs_tagged, diag, x, parity, sync, trace);
 }
