@@ -101,7 +101,7 @@ __global__ void __launch_bounds__(kW * 32, kOcc)
                         const unsigned long long *rhs_tagged, const double *__restrict__ diag, unsigned long long *x,
                         const unsigned parity, int *sync, int *error_flag, const unsigned window,
                         const unsigned adm_sleep, const unsigned near_sleep, const unsigned poll_sleep,
-                        const int use_l1, unsigned long long *trace) {
+                        const int use_l1, const unsigned defer, unsigned long long *trace) {
   static_assert(NR == 1 || NR % 2 == 0, "NR must be 1 or even (128-bit transactions)");
   constexpr int kG = NR == 1 ? (kU > 4 ? 4 : kU) : 2;  // entries whose gathers are in flight together
   static_assert(kU % kG == 0, "kU must be a multiple of the gather group");
@@ -202,6 +202,7 @@ __global__ void __launch_bounds__(kW * 32, kOcc)
     // the next ticket is fetched behind the gathers of this chunk (off the critical path); it is
     // held for the ~1 us this chunk still needs, which delays nobody
     unsigned next_ticket = 0;
+    bool     waited      = false;
     const bool ticket_lane = threadIdx.x == (kW > 1 ? 32u : 0u);
     // ---- gather the dependencies optimistically, re-poll the ones that are not ready
     auto gather = [&](unsigned col, unsigned long long(&g)[NR], bool first) {
@@ -240,6 +241,20 @@ __global__ void __launch_bounds__(kW * 32, kOcc)
 #pragma unroll
         for (int j = 0; j < kG; ++j)
           if (cc[u0 + j] != kPadCol && !ready(g[j])) pend |= 1u << j;
+        // deferred polling: the missing values are produced by level sets >= sd.w - defer; nothing
+        // can arrive before level sd.w - defer - 1 is complete, so wait for that counter (one word
+        // per warp) instead of re-gathering 32 x pending sectors round after round
+        if (defer && !waited && sd.w > defer && __any_sync(0xffffffffu, pend != 0u)) {
+          waited = true;
+          if (lane == 0) {
+            const unsigned t    = sd.w - defer - 1u;
+            const unsigned need = lvl_need[t];
+            const int *    ctr  = sync + kSyncStride * (1 + t);
+            for (unsigned spins = 0; static_cast<unsigned>(ld_poll_i32(ctr)) < need && spins < (kSpinLimit >> 4); ++spins)
+              __nanosleep(100);
+          }
+          __syncwarp();
+        }
         for (unsigned rounds = 0; __any_sync(0xffffffffu, pend != 0u);) {
           if (poll_sleep) __nanosleep(poll_sleep);
 #pragma unroll
@@ -506,7 +521,8 @@ void launch_stream_O(Handle *h, const SweepPlan &plan, const double *rhs_plain, 
   sweep_stream_kernel<UPPER, kU, NR, kW, kOcc><<<grid, kW * 32, 0, h->stream>>>(
       plan.st_chunks, reinterpret_cast<const uint4 *>(plan.st_sdesc.p), plan.st_need.p, plan.st_codes.p,
       plan.st_cols.p, plan.st_vals.p, plan.m, rhs_plain, rhs_tagged, diag, x, parity, sync, h->error_flag.p, window,
-      sleep, near_sleep, poll_sleep, stream_env("HIFIR_B200_STREAM_L1", 0) | (stream_env("HIFIR_B200_STREAM_PUBLISH_ST", 0) ? 2 : 0), trace);
+      sleep, near_sleep, poll_sleep, stream_env("HIFIR_B200_STREAM_L1", 0) | (stream_env("HIFIR_B200_STREAM_PUBLISH_ST", 0) ? 2 : 0),
+      static_cast<unsigned>(std::max(0, stream_env("HIFIR_B200_STREAM_DEFER", 0))), trace);
 }
 // CTAs per SM the kernel is compiled for (register budget): the sweep is bound by the number of
 // gathers in flight per SM, so occupancy is worth a few spilled registers
