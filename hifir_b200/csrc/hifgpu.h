@@ -86,6 +86,7 @@ struct MergeParams {
   unsigned row_cap   = 256;       // longest row of an inverted diagonal block
   unsigned bmax      = 64;        // most level sets merged into one super level
   double   row_cost  = 2.0;       // cost of one auxiliary row, in nonzeros
+  int      alap      = 1;         // as-late-as-possible level sets: 0 never, 1 fan-out sweeps (U: leaves last), 2 always
   double   sl_cap    = 500000.0;  // a super level stops growing at this many entries: beyond, its two
                                   // steps are throughput bound and more fill only costs (measured optimum 4e5-8e5)
   static MergeParams from_env();
@@ -94,7 +95,7 @@ struct MergeStats {
   std::size_t rows = 0, ext_rows = 0, nnz = 0, ext_nnz = 0, depth = 0, ext_depth = 0, super_levels = 0;
 };
 HostCsr to_sweep_form(const HostCsr &T, bool upper);
-HostCsr merge_levels(const HostCsr &S, const MergeParams &prm, MergeStats *st);
+HostCsr merge_levels(const HostCsr &S, const MergeParams &prm, MergeStats *st, bool fan_out = false);
 
 // a strictly triangular factor cut into shared-memory sized slabs (sptrsv.cu)
 struct SweepPlan {

@@ -37,6 +37,7 @@ MergeParams MergeParams::from_env() {
   if (const char *e = std::getenv("HIFIR_B200_MERGE_BMAX")) p.bmax = static_cast<unsigned>(std::atoi(e));
   if (const char *e = std::getenv("HIFIR_B200_MERGE_ROWCOST")) p.row_cost = std::atof(e);
   if (const char *e = std::getenv("HIFIR_B200_MERGE_SLCAP")) p.sl_cap = std::atof(e);
+  if (const char *e = std::getenv("HIFIR_B200_MERGE_ALAP")) p.alap = std::atoi(e);
   return p;
 }
 
@@ -87,11 +88,33 @@ static unsigned depth_of(const HostCsr &S, std::vector<unsigned> &lev) {
   return depth;
 }
 
-HostCsr merge_levels(const HostCsr &S, const MergeParams &prm, MergeStats *st) {
+// as-late-as-possible level sets: a row sits as many steps before the end as its longest chain
+// of dependents is long.  In a fan-out sweep (U: root first) this puts ALL leaves of the
+// elimination tree into the last level set -- the mirror image of the forward sweep, where
+// they are the first one -- instead of scattering them over every level: a leaf whose parent
+// falls into the same super level would otherwise be split into two rows.
+static unsigned depth_alap(const HostCsr &S, std::vector<unsigned> &lev) {
+  const unsigned        m = static_cast<unsigned>(S.nrows);
+  std::vector<unsigned> h(m, 0u);
+  unsigned              depth = 0;
+  for (unsigned i = m; i-- > 0;) {
+    for (unsigned k = S.ptr[i]; k < S.ptr[i + 1]; ++k) {
+      const unsigned j = static_cast<unsigned>(S.col[k]);
+      h[j]             = std::max(h[j], h[i] + 1u);
+    }
+    depth = std::max(depth, h[i] + 1u);
+  }
+  lev.resize(m);
+  for (unsigned i = 0; i < m; ++i) lev[i] = depth - 1u - h[i];
+  return depth;
+}
+
+HostCsr merge_levels(const HostCsr &S, const MergeParams &prm, MergeStats *st, bool fan_out) {
   const unsigned m = static_cast<unsigned>(S.nrows);
   if (S.gid.size() != m || S.orig_rows != m) throw std::logic_error("merge_levels: input is not in sweep form");
   std::vector<unsigned> lev;
-  const unsigned        depth = depth_of(S, lev);
+  const bool            alap  = prm.alap == 2 || (prm.alap == 1 && fan_out) || (prm.alap == 3 && !fan_out);
+  const unsigned        depth = alap ? depth_alap(S, lev) : depth_of(S, lev);
   if (st) {
     st->rows  = m;
     st->nnz   = S.col.size();

@@ -798,7 +798,7 @@ void sweep_host_emulate(const HostCsr &T, bool upper, const double *rhs, const d
   HostCsr           S  = to_sweep_form(T, upper);
   const MergeParams mp = MergeParams::from_env();
   MergeStats        ms;
-  if (mp.enabled) S = merge_levels(S, mp, &ms);
+  if (mp.enabled) S = merge_levels(S, mp, &ms, upper);
   const unsigned      m = static_cast<unsigned>(T.nrows);
   std::vector<double> xs, xg(2 * static_cast<std::size_t>(m), 0.0);
   if (stream_sweeps()) {
@@ -842,7 +842,7 @@ void sweep_simulate(const HostCsr &T, bool upper, const double *prm, double *out
   HostCsr           S  = to_sweep_form(T, upper);
   const MergeParams mp = MergeParams::from_env();
   MergeStats        ms;
-  if (mp.enabled) S = merge_levels(S, mp, &ms);
+  if (mp.enabled) S = merge_levels(S, mp, &ms, upper);
   pack_sweep(S, upper, P);
   const unsigned      m     = 2u * static_cast<unsigned>(T.nrows);  // solution slots
   const unsigned      slots = static_cast<unsigned>(prm[0]), NT = static_cast<unsigned>(prm[1]);
@@ -901,7 +901,7 @@ void sweep_block_graph(const HostCsr &T, bool upper, std::vector<unsigned> &info
   PackedSweep       P;
   HostCsr           S  = to_sweep_form(T, upper);
   const MergeParams mp = MergeParams::from_env();
-  if (mp.enabled) S = merge_levels(S, mp, nullptr);
+  if (mp.enabled) S = merge_levels(S, mp, nullptr, upper);
   pack_sweep(S, upper, P);
   const unsigned        m = static_cast<unsigned>(S.nrows);
   std::vector<unsigned> blk_of(m);
@@ -973,7 +973,7 @@ void build_split_plans(const HostCsr &Tnat, SweepPlan &plan_lo, SweepPlan &plan_
   HostCsr           T  = to_sweep_form(Tnat, false);
   const MergeParams mp = MergeParams::from_env();
   MergeStats        ms;
-  if (mp.enabled) T = merge_levels(T, mp, &ms);
+  if (mp.enabled) T = merge_levels(T, mp, &ms, false);
   if (stream_sweeps()) {  // one level-major sweep, nothing to split
     build_stream_plan(T, false, plan_lo, tally);
     plan_lo.merge = ms;
@@ -1043,7 +1043,7 @@ void build_sweep_plan(const HostCsr &Tnat, bool upper, SweepPlan &plan, std::siz
     pack_sweep(T, upper, P, 8u * nr, kSmemBudgetMrhs);
   } else {
     const MergeParams mp = MergeParams::from_env();
-    if (mp.enabled) T = merge_levels(T, mp, &plan.merge);
+    if (mp.enabled) T = merge_levels(T, mp, &plan.merge, upper);
     if (stream_sweeps()) {
       const MergeStats ms = plan.merge;
       build_stream_plan(T, upper, plan, tally);
