@@ -86,8 +86,9 @@ struct MergeParams {
   unsigned row_cap   = 256;       // longest row of an inverted diagonal block
   unsigned bmax      = 64;        // most level sets merged into one super level
   double   row_cost  = 2.0;       // cost of one auxiliary row, in nonzeros
+  bool     chain     = true;      // chain the t rows of consecutive super levels (one step per super level)
   int      alap      = 1;         // as-late-as-possible level sets: 0 never, 1 fan-out sweeps (U: leaves last), 2 always
-  double   sl_cap    = 500000.0;  // a super level stops growing at this many entries: beyond, its two
+  double   sl_cap    = 300000.0;  // a super level stops growing at this many entries: beyond, its two
                                   // steps are throughput bound and more fill only costs (measured optimum 4e5-8e5)
   static MergeParams from_env();
 };

@@ -38,6 +38,7 @@ MergeParams MergeParams::from_env() {
   if (const char *e = std::getenv("HIFIR_B200_MERGE_ROWCOST")) p.row_cost = std::atof(e);
   if (const char *e = std::getenv("HIFIR_B200_MERGE_SLCAP")) p.sl_cap = std::atof(e);
   if (const char *e = std::getenv("HIFIR_B200_MERGE_ALAP")) p.alap = std::atoi(e);
+  if (const char *e = std::getenv("HIFIR_B200_MERGE_CHAIN")) p.chain = std::atoi(e) != 0;
   return p;
 }
 
@@ -222,26 +223,77 @@ HostCsr merge_levels(const HostCsr &S, const MergeParams &prm, MergeStats *st, b
   E.orig_rows = m;
   E.ptr.push_back(0u);
   std::vector<unsigned> xpos(m), tpos(m);
-  for (unsigned i = 0; i < m; ++i) {
-    if (!wlen[i]) {
+  // ordinal of the super level of every level set
+  std::vector<unsigned> sl_ord(depth, 0u);
+  {
+    std::vector<unsigned> first(depth, 0u);
+    for (unsigned i = 0; i < m; ++i) first[lev[i]] = sl0[i];
+    unsigned ordn = 0;
+    for (unsigned l = 0; l < depth; ++l) {
+      if (l > 0 && first[l] != first[l - 1]) ++ordn;
+      sl_ord[l] = ordn;
+    }
+  }
+  // Chaining (prm.chain): an entry that references x_j of the IMMEDIATELY preceding super level is
+  // replaced by x_j = t_j + sum_l Winv_jl t_l.  The t rows of consecutive super levels then depend
+  // on each other directly -- one dependent step per super level instead of two -- and the x
+  // rows leave the critical path (they are computed beside the next super level's t rows).
+  std::vector<double>   cacc;
+  std::vector<unsigned> cstamp, ctouched;
+  unsigned              ccur = 0;
+  if (prm.chain) {
+    cacc.assign(2 * static_cast<std::size_t>(m), 0.0);
+    cstamp.assign(2 * static_cast<std::size_t>(m), 0u);
+  }
+  auto emit_cross = [&](unsigned i) {  // entries of row i that reference earlier super levels
+    if (!prm.chain) {
       for (unsigned k = S.ptr[i]; k < S.ptr[i + 1]; ++k) {
         const unsigned j = static_cast<unsigned>(S.col[k]);
-        if (lev[j] >= sl0[i]) throw std::logic_error("merge_levels: in-level entry on an unsplit row");
+        if (lev[j] >= sl0[i]) continue;
         E.col.push_back(static_cast<int>(xpos[j]));
         E.val.push_back(S.val[k]);
       }
+      return;
+    }
+    ++ccur;
+    ctouched.clear();
+    auto add = [&](unsigned pos, double v) {
+      if (cstamp[pos] != ccur) {
+        cstamp[pos] = ccur;
+        cacc[pos]   = 0.0;
+        ctouched.push_back(pos);
+      }
+      cacc[pos] += v;
+    };
+    const unsigned my = sl_ord[lev[i]];
+    for (unsigned k = S.ptr[i]; k < S.ptr[i + 1]; ++k) {
+      const unsigned j = static_cast<unsigned>(S.col[k]);
+      if (lev[j] >= sl0[i]) continue;
+      if (wlen[j] && sl_ord[lev[j]] + 1u == my) {
+        add(tpos[j], S.val[k]);
+        for (std::size_t w = wbeg[j], we = wbeg[j] + wlen[j]; w < we; ++w) add(tpos[wcol[w]], S.val[k] * wval[w]);
+      } else {
+        add(xpos[j], S.val[k]);
+      }
+    }
+    std::sort(ctouched.begin(), ctouched.end());
+    for (unsigned pos : ctouched) {
+      E.col.push_back(static_cast<int>(pos));
+      E.val.push_back(cacc[pos]);
+    }
+  };
+  for (unsigned i = 0; i < m; ++i) {
+    if (!wlen[i]) {
+      for (unsigned k = S.ptr[i]; k < S.ptr[i + 1]; ++k)
+        if (lev[S.col[k]] >= sl0[i]) throw std::logic_error("merge_levels: in-level entry on an unsplit row");
+      emit_cross(i);
       xpos[i] = tpos[i] = static_cast<unsigned>(E.gid.size());
       E.gid.push_back(S.gid[i]);
       E.ptr.push_back(static_cast<unsigned>(E.col.size()));
       continue;
     }
     // t_i = b_i - sum_{j in earlier super levels} T_ij x_j
-    for (unsigned k = S.ptr[i]; k < S.ptr[i + 1]; ++k) {
-      const unsigned j = static_cast<unsigned>(S.col[k]);
-      if (lev[j] >= sl0[i]) continue;
-      E.col.push_back(static_cast<int>(xpos[j]));
-      E.val.push_back(S.val[k]);
-    }
+    emit_cross(i);
     tpos[i] = static_cast<unsigned>(E.gid.size());
     E.gid.push_back(m + S.gid[i]);
     E.ptr.push_back(static_cast<unsigned>(E.col.size()));
