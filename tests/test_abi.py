@@ -131,7 +131,7 @@ def test_level_merging_shortens_the_dependency_chain(lib, monkeypatch):
             depth[(merge, name, "bytes")] = st["bytes"]
     for name in ("L", "U"):
         assert depth[("1", name)] * 3 <= depth[("0", name)], depth
-        assert depth[("1", name, "bytes")] <= 3 * depth[("0", name, "bytes")], depth
+        assert depth[("1", name, "bytes")] <= 5 * depth[("0", name, "bytes")], depth  # tiny factor: no cap but gain / row_cap binds
 
 
 def test_product_never_imports_oracle():
