@@ -70,6 +70,18 @@ __device__ __forceinline__ unsigned long long ld_l1(const unsigned long long *p)
   asm volatile("ld.global.ca.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
 }
+__device__ __forceinline__ void cp_async_4(void *smem_dst, const void *gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(static_cast<unsigned>(__cvta_generic_to_shared(smem_dst))),
+               "l"(gsrc)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_8(void *smem_dst, const void *gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(static_cast<unsigned>(__cvta_generic_to_shared(smem_dst))),
+               "l"(gsrc)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ int ld_poll_i32(const int *p) {
   int v;
   asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -105,6 +117,9 @@ __global__ void __launch_bounds__(kW * 32, kOcc)
   static_assert(NR == 1 || NR % 2 == 0, "NR must be 1 or even (128-bit transactions)");
   constexpr int kG = NR == 1 ? (kU > 4 ? 4 : kU) : 2;  // entries whose gathers are in flight together
   static_assert(kU % kG == 0, "kU must be a multiple of the gather group");
+  constexpr bool kStage = kOcc >= 5 && NR == 1 && kU == 8;  // the high-occupancy variant stages the factor in shared memory
+  __shared__ unsigned s_cols[kStage ? kW * kU * 32 : 1];
+  __shared__ double   s_vals[kStage ? kW * kU * 32 : 1];
   __shared__ unsigned s_c[2];
   __shared__ int      s_last;
   const unsigned      warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
@@ -128,15 +143,29 @@ __global__ void __launch_bounds__(kW * 32, kOcc)
     const std::size_t slot = static_cast<std::size_t>(code & kCodeSlotMask);
     const std::size_t base = static_cast<std::size_t>(sd.x) * 32u + lane;
     const unsigned    len  = sd.y;
-    // ---- everything that does not depend on other rows: factor entries, right-hand side
-    unsigned cc[kU];
-    double   vv[kU];
+    // ---- everything that does not depend on other rows: factor entries, right-hand side.
+    // kStage: the entries go to shared memory with cp.async (no registers held while the chunk
+    // waits for its admission: two more CTAs per SM), else into registers
+    unsigned cc[kStage ? 1 : kU];
+    double   vv[kStage ? 1 : kU];
+    unsigned *const my_cols = s_cols + (kStage ? (warp * kU) * 32u + lane : 0u);
+    double *const   my_vals = s_vals + (kStage ? (warp * kU) * 32u + lane : 0u);
+    if (kStage) {
 #pragma unroll
-    for (int u = 0; u < kU; ++u) {
-      cc[u] = kPadCol;
-      if (static_cast<unsigned>(u) < len) {
-        cc[u] = ld_stream_u32(cols + base + static_cast<std::size_t>(u) * 32u);
-        vv[u] = ld_stream_f64(vals + base + static_cast<std::size_t>(u) * 32u);
+      for (int u = 0; u < kU; ++u)
+        if (static_cast<unsigned>(u) < len) {
+          cp_async_4(my_cols + u * 32, cols + base + static_cast<std::size_t>(u) * 32u);
+          cp_async_8(my_vals + u * 32, vals + base + static_cast<std::size_t>(u) * 32u);
+        }
+      cp_async_commit();
+    } else {
+#pragma unroll
+      for (int u = 0; u < kU; ++u) {
+        cc[u] = kPadCol;
+        if (static_cast<unsigned>(u) < len) {
+          cc[u] = ld_stream_u32(cols + base + static_cast<std::size_t>(u) * 32u);
+          vv[u] = ld_stream_f64(vals + base + static_cast<std::size_t>(u) * 32u);
+        }
       }
     }
     double acc[NR];
@@ -220,19 +249,32 @@ __global__ void __launch_bounds__(kW * 32, kOcc)
       for (int q = 0; q < NR; ++q) ok &= tag_ready(g[q], parity);
       return ok;
     };
+    if (kStage) cp_async_wait_all();
     for (unsigned k = 0;;) {
 #pragma unroll
       for (int u0 = 0; u0 < kU; u0 += kG) {
+        unsigned ccg[kG];
+        double   vvg[kG];
+#pragma unroll
+        for (int j = 0; j < kG; ++j) {
+          if (kStage) {
+            ccg[j] = (k + u0 + j < len) ? my_cols[(u0 + j) * 32] : kPadCol;
+            vvg[j] = (k + u0 + j < len) ? my_vals[(u0 + j) * 32] : 0.0;
+          } else {
+            ccg[j] = cc[kStage ? 0 : u0 + j];
+            vvg[j] = vv[kStage ? 0 : u0 + j];
+          }
+        }
         unsigned long long g[kG][NR];
 #pragma unroll
         for (int j = 0; j < kG; ++j)
-          if (cc[u0 + j] != kPadCol) gather(cc[u0 + j], g[j], true);
+          if (ccg[j] != kPadCol) gather(ccg[j], g[j], true);
         if (ticket_lane && k == 0 && u0 == 0) next_ticket = static_cast<unsigned>(atomicAdd(sync, 1));
         if (trace && threadIdx.x == 0 && k == 0 && u0 == 0) {  // warp 0: first gather round trip
           unsigned long long any = 0;
 #pragma unroll
           for (int j = 0; j < kG; ++j)
-            if (cc[j] != kPadCol) any |= g[j][0];
+            if (ccg[j] != kPadCol) any |= g[j][0];
           trace[8 * c + 6] = stream_timer_ns() + (any == 0x7ff8dead00000001ull ? 1u : 0u);
         }
         // entries that were not ready on the first try (padding counts as ready) are re-polled
@@ -240,7 +282,7 @@ __global__ void __launch_bounds__(kW * 32, kOcc)
         unsigned pend = 0;
 #pragma unroll
         for (int j = 0; j < kG; ++j)
-          if (cc[u0 + j] != kPadCol && !ready(g[j])) pend |= 1u << j;
+          if (ccg[j] != kPadCol && !ready(g[j])) pend |= 1u << j;
         // deferred polling: the missing values are produced by level sets >= sd.w - defer; nothing
         // can arrive before level sd.w - defer - 1 is complete, so wait for that counter (one word
         // per warp) instead of re-gathering 32 x pending sectors round after round
@@ -259,7 +301,7 @@ __global__ void __launch_bounds__(kW * 32, kOcc)
           if (poll_sleep) __nanosleep(poll_sleep);
 #pragma unroll
           for (int j = 0; j < kG; ++j)
-            if (pend & (1u << j)) gather(cc[u0 + j], g[j], false);
+            if (pend & (1u << j)) gather(ccg[j], g[j], false);
 #pragma unroll
           for (int j = 0; j < kG; ++j)
             if ((pend & (1u << j)) && ready(g[j])) pend &= ~(1u << j);
@@ -270,19 +312,31 @@ __global__ void __launch_bounds__(kW * 32, kOcc)
         }
 #pragma unroll
         for (int j = 0; j < kG; ++j)
-          if (cc[u0 + j] != kPadCol) {
+          if (ccg[j] != kPadCol) {
 #pragma unroll
-            for (int q = 0; q < NR; ++q) acc[q] = fma(-vv[u0 + j], tag_value(g[j][q]), acc[q]);
+            for (int q = 0; q < NR; ++q) acc[q] = fma(-vvg[j], tag_value(g[j][q]), acc[q]);
           }
       }
       k += kU;
       if (k >= len) break;
+      // rows longer than kU * lpr entries (rare): the next kU entries per lane
+      if (kStage) {
 #pragma unroll
-      for (int u = 0; u < kU; ++u) {  // rows longer than kU * lpr entries (rare)
-        cc[u] = kPadCol;
-        if (k + u < len) {
-          cc[u] = ld_stream_u32(cols + base + static_cast<std::size_t>(k + u) * 32u);
-          vv[u] = ld_stream_f64(vals + base + static_cast<std::size_t>(k + u) * 32u);
+        for (int u = 0; u < kU; ++u)
+          if (k + u < len) {
+            cp_async_4(my_cols + u * 32, cols + base + static_cast<std::size_t>(k + u) * 32u);
+            cp_async_8(my_vals + u * 32, vals + base + static_cast<std::size_t>(k + u) * 32u);
+          }
+        cp_async_commit();
+        cp_async_wait_all();
+      } else {
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+          cc[kStage ? 0 : u] = kPadCol;
+          if (k + u < len) {
+            cc[kStage ? 0 : u] = ld_stream_u32(cols + base + static_cast<std::size_t>(k + u) * 32u);
+            vv[kStage ? 0 : u] = ld_stream_f64(vals + base + static_cast<std::size_t>(k + u) * 32u);
+          }
         }
       }
     }
@@ -530,10 +584,16 @@ template <bool UPPER, int kU, int NR, int kW>
 void launch_stream_W(Handle *h, const SweepPlan &plan, const double *rhs_plain, const unsigned long long *rhs_tagged,
                      const double *diag, unsigned long long *x, unsigned parity, int *sync, unsigned long long *trace) {
   constexpr int kBase = (NR > 1 ? 2 : (kU == 4 ? 5 : (kU == 8 ? 4 : 2))) * 8 / kW;
-  if (NR == 1 && kU == 4 && kW == 8) {
-    const int occ = stream_env("HIFIR_B200_STREAM_OCC", 5);
-    if (occ == 6) return launch_stream_O<UPPER, kU, NR, kW, (NR == 1 && kU == 4 && kW == 8) ? 6 : kBase>(h, plan, rhs_plain, rhs_tagged, diag, x, parity, sync, trace);
-    if (occ == 8) return launch_stream_O<UPPER, kU, NR, kW, (NR == 1 && kU == 4 && kW == 8) ? 8 : kBase>(h, plan, rhs_plain, rhs_tagged, diag, x, parity, sync, trace);
+  // HIFIR_B200_STREAM_OCC = 6 / 8: variants compiled for more CTAs per SM; they stage the factor
+  // entries in shared memory (cp.async) instead of registers
+  if (NR == 1 && kW == 8 && kU <= 8) {
+    constexpr bool ok  = NR == 1 && kW == 8 && kU <= 8;
+    const int      occ = stream_env("HIFIR_B200_STREAM_OCC", 0);
+    if (occ == 5 && kU == 8) return launch_stream_O<UPPER, kU, NR, kW, (ok && kU == 8) ? 5 : kBase>(h, plan, rhs_plain, rhs_tagged, diag, x, parity, sync, trace);
+    if (occ == 3) return launch_stream_O<UPPER, kU, NR, kW, ok ? 3 : kBase>(h, plan, rhs_plain, rhs_tagged, diag, x, parity, sync, trace);
+    if (occ == 2) return launch_stream_O<UPPER, kU, NR, kW, ok ? 2 : kBase>(h, plan, rhs_plain, rhs_tagged, diag, x, parity, sync, trace);
+    if (occ == 6) return launch_stream_O<UPPER, kU, NR, kW, ok ? 6 : kBase>(h, plan, rhs_plain, rhs_tagged, diag, x, parity, sync, trace);
+    if (occ == 8) return launch_stream_O<UPPER, kU, NR, kW, ok ? 8 : kBase>(h, plan, rhs_plain, rhs_tagged, diag, x, parity, sync, trace);
   }
   launch_stream_O<UPPER, kU, NR, kW, kBase>(h, plan, rhs_plain, rhs_tagged, diag, x, parity, sync, trace);
 }
