@@ -109,55 +109,58 @@ __global__ void dense_qt_kernel(const unsigned nm, const unsigned rk, const doub
   if (lane == 0) c[warp] = acc;
 }
 
-// Back substitution on R(0:rk,0:rk), column oriented like reference dtrsv 'U','N','N'
-// (updates applied in descending column order), blocked by 32: warp 0 keeps the 32x32
-// diagonal tile in registers and solves it with shuffles (one FMA + one shuffle per
-// dependent step), then the whole CTA applies the block's 32 columns to the rows above.
-// The diagonal is applied as a multiplication with 1/R(j,j) precomputed at attach
-// (1 ulp from the reference's division).  Finally out[jpvt[i]-1] = x_i, zero for i >= rk.
+// Back substitution on R(0:rk,0:rk) (reference: dtrsv 'U','N','N', QRCP.hpp:393), blocked by 32 from
+// row 0: the 32x32 diagonal tiles are inverted once at attach (attach.cu; the leading k x k part of
+// an upper triangular inverse is the inverse of the leading part, so a truncated rank needs no other
+// tiles), hence a tile is a 32x32 matrix-vector product without any dependent chain; then the whole
+// CTA applies the tile's 32 columns to the rows above (coalesced column reads, all 32 loads of a
+// thread in flight).  Finally out[jpvt[i]-1] = x_i, zero for i >= rk (QRCP.hpp:401-409).
 constexpr int kTrsvThreads = 512;
 __global__ void __launch_bounds__(kTrsvThreads, 1)
     dense_trsv_kernel(const unsigned nm, const unsigned rk, const double *__restrict__ R,
-                      const double *__restrict__ rinv, const double *__restrict__ c,
+                      const double *__restrict__ tinv, const double *__restrict__ c,
                       const int *__restrict__ jpvt, double *__restrict__ out, const unsigned stride) {
   // one CTA per right-hand side column (blockIdx.x) of a row-interleaved block of `stride` columns
   extern __shared__ double xs[];  // rk values
   const unsigned           tid = threadIdx.x, colr = blockIdx.x;
   for (unsigned i = tid; i < rk; i += kTrsvThreads) xs[i] = c[static_cast<std::size_t>(i) * stride + colr];
   __syncthreads();
-  for (unsigned j1 = rk; j1 > 0;) {
-    const unsigned j0 = j1 >= 32u ? j1 - 32u : 0u;  // block [j0, j1)
-    const unsigned w  = j1 - j0;
+  const unsigned ntile = (rk + 31u) / 32u;
+  for (unsigned t = ntile; t-- > 0;) {
+    const unsigned j0 = 32u * t, w = min(32u, rk - j0);  // tile [j0, j0 + w)
     if (tid < 32) {
-      double t[32];  // row `tid` of the diagonal tile
-#pragma unroll
-      for (int jj = 0; jj < 32; ++jj)
-        t[jj] = (static_cast<unsigned>(jj) < w && tid < w) ? R[j0 + tid + static_cast<std::size_t>(j0 + jj) * nm] : 0.0;
-      const double ri = tid < w ? rinv[j0 + tid] : 0.0;
-      double       xv = tid < w ? xs[j0 + tid] : 0.0;
-#pragma unroll
-      for (int jj = 31; jj >= 0; --jj) {
-        if (static_cast<unsigned>(jj) < w) {
-          const double xj = __shfl_sync(0xffffffffu, xv * ri, jj);
-          if (tid == static_cast<unsigned>(jj))
-            xv = xj;
-          else if (tid < static_cast<unsigned>(jj))
-            xv = fma(-xj, t[jj], xv);
+      // x_i = sum_{j >= i} Tinv(i, j) c_j : 4 independent partial sums
+      const double *Ti = tinv + static_cast<std::size_t>(t) * 1024u + tid;  // column-major 32x32, lane = row
+      double        a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+      if (tid < w) {
+#pragma unroll 8
+        for (unsigned j = 0; j < 32u; j += 4) {
+          a0 = fma(Ti[(j + 0u) * 32u], (j + 0u < w && j + 0u >= tid) ? xs[j0 + j + 0u] : 0.0, a0);
+          a1 = fma(Ti[(j + 1u) * 32u], (j + 1u < w && j + 1u >= tid) ? xs[j0 + j + 1u] : 0.0, a1);
+          a2 = fma(Ti[(j + 2u) * 32u], (j + 2u < w && j + 2u >= tid) ? xs[j0 + j + 2u] : 0.0, a2);
+          a3 = fma(Ti[(j + 3u) * 32u], (j + 3u < w && j + 3u >= tid) ? xs[j0 + j + 3u] : 0.0, a3);
         }
       }
+      const double xv = (a0 + a1) + (a2 + a3);
+      __syncwarp();
       if (tid < w) xs[j0 + tid] = xv;
     }
     __syncthreads();
-    // rows above the block: x[i] -= sum_{col in block, descending} R(i,col) * x[col]
+    // rows above the tile: x[i] -= sum_{col in tile} R(i,col) * x[col]
     for (unsigned i = tid; i < j0; i += kTrsvThreads) {
-      double        xv = xs[i];
       const double *Ri = R + i + static_cast<std::size_t>(j0) * nm;
-#pragma unroll 8
-      for (int jj = static_cast<int>(w) - 1; jj >= 0; --jj) xv = fma(-xs[j0 + jj], Ri[static_cast<std::size_t>(jj) * nm], xv);
-      xs[i] = xv;
+      double        r[32];
+#pragma unroll
+      for (int jj = 0; jj < 32; ++jj) r[jj] = static_cast<unsigned>(jj) < w ? Ri[static_cast<std::size_t>(jj) * nm] : 0.0;
+      double b0 = 0.0, b1 = 0.0;
+#pragma unroll
+      for (int jj = 0; jj < 32; jj += 2) {
+        b0 = fma(r[jj], static_cast<unsigned>(jj) < w ? xs[j0 + jj] : 0.0, b0);
+        b1 = fma(r[jj + 1], static_cast<unsigned>(jj + 1) < w ? xs[j0 + jj + 1] : 0.0, b1);
+      }
+      xs[i] -= b0 + b1;
     }
     __syncthreads();
-    j1 = j0;
   }
   for (unsigned i = tid; i < nm; i += kTrsvThreads)
     out[static_cast<std::size_t>(jpvt[i] - 1) * stride + colr] = i < rk ? xs[i] : 0.0;
@@ -419,7 +422,7 @@ void dense_solve_dev(Handle *h, const double *d_in, double *d_out, std::size_t r
       HIF_KERNEL_CHECK();
       ++h->launch_count;
     }
-    dense_trsv_kernel<<<1, kTrsvThreads, (rk ? rk : 1) * sizeof(double), h->stream>>>(nm, rk, Q.R.p, Q.rinv.p, Q.c.p,
+    dense_trsv_kernel<<<1, kTrsvThreads, (rk ? rk : 1) * sizeof(double), h->stream>>>(nm, rk, Q.R.p, Q.tinv.p, Q.c.p,
                                                                                      Q.jpvt.p, d_out, 1u);
   } else {
     dense_solve_t_kernel<<<1, kDenseT, (rk ? rk : 1) * sizeof(double), h->stream>>>(nm, rk, Q.R.p, Q.Q.p, Q.jpvt.p, d_in,
@@ -455,7 +458,7 @@ void launch_ldu_solve(Handle *h, DevLevel &D, const double *rhs, unsigned long l
 
 void launch_dense_trsv_cols(Handle *h, unsigned nm, unsigned rk, const double *c, double *out, unsigned ncols) {
   DevDense &Q = h->dense;
-  dense_trsv_kernel<<<ncols, kTrsvThreads, (rk ? rk : 1) * sizeof(double), h->stream>>>(nm, rk, Q.R.p, Q.rinv.p, c,
+  dense_trsv_kernel<<<ncols, kTrsvThreads, (rk ? rk : 1) * sizeof(double), h->stream>>>(nm, rk, Q.R.p, Q.tinv.p, c,
                                                                                        Q.jpvt.p, out, ncols);
   HIF_KERNEL_CHECK();
   ++h->launch_count;

@@ -255,9 +255,25 @@ Handle *attach_levels(int device, std::size_t nlevels, const LhfdGpuLevel *lv, b
     h->dense.Q.upload(form_q(nm, last.qr_mat, last.qr_tau), tally);
     h->dense.R.upload(last.qr_mat, nm * nm, tally);
     {
-      std::vector<double> rinv(nm);
-      for (std::size_t j = 0; j < nm; ++j) rinv[j] = 1.0 / last.qr_mat[j + j * nm];
-      h->dense.rinv.upload(rinv, tally);
+      // inverses of the 32x32 diagonal tiles of R (upper triangular): column j of the inverse by
+      // back substitution on e_j, in double, the tile's own columns only
+      const std::size_t   nt = (nm + 31) / 32;
+      std::vector<double> tinv(nt * 1024, 0.0);
+      for (std::size_t t = 0; t < nt; ++t) {
+        const std::size_t j0 = 32 * t, w = std::min<std::size_t>(32, nm - j0);
+        double *          T  = tinv.data() + t * 1024;
+        for (std::size_t j = 0; j < w; ++j) {
+          double col[32] = {0.0};
+          col[j]         = 1.0;
+          for (std::size_t i = j + 1; i-- > 0;) {
+            double v = col[i];
+            for (std::size_t k = i + 1; k <= j; ++k) v -= last.qr_mat[(j0 + i) + (j0 + k) * nm] * col[k];
+            col[i] = v / last.qr_mat[(j0 + i) + (j0 + i) * nm];
+          }
+          for (std::size_t i = 0; i <= j; ++i) T[i + 32 * j] = col[i];
+        }
+      }
+      h->dense.tinv.upload(tinv, tally);
     }
     h->dense.jpvt.upload(reinterpret_cast<const int *>(last.qr_jpvt), nm, tally);
     h->dense.c.alloc(nm, tally);

@@ -164,7 +164,7 @@ struct DevDense {
   std::size_t    nm = 0, rank = 0;
   DevBuf<double> Q;     // nm x nm column-major explicit Q = H_1 ... H_nm (column k = row k of Q^T)
   DevBuf<double> R;     // nm x nm column-major, upper triangle = R
-  DevBuf<double> rinv;  // nm, 1 / R(j,j)
+  DevBuf<double> tinv;  // ceil(nm/32) inverted 32x32 diagonal tiles of R, column-major, zero padded
   DevBuf<int>    jpvt;  // nm, 1-based verbatim
   DevBuf<double> c;     // nm work (Q^T b)
   bool           transposed = false;  // twin handle: solve / multiply with (Q R P^T)^T
