@@ -264,3 +264,34 @@ def test_against_live_reference_same_object(case, N):
         xg, fg, ig, ng = G.fgmres(bk)
         assert fg == fr and abs(ig - ir) <= 1, (ig, ir)
         assert relerr(xg, xr) <= 1e-5
+
+
+@needs_ref
+def test_large_size_properties_and_merged_structure():
+    """A BASELINE-scale factor (Poisson 96^3, n = 884 736, 3 levels; the 128^3 run itself is gated inside
+    bench.py): parity against the reference's own apply on the same object, the size-independent
+    properties (on-device round trip M (M^-1 b) = b, linearity, repeatability across ready-bit parities),
+    and what the attach-time merging did to the dependency chain."""
+    import torch
+    from oracle import refhost as R
+    A = P.poisson3d(96)
+    M = R.RefHif(A, P.PDE_PARAMS)
+    with _attach_through_cxx_adapter(M) as G:
+        st = G.stats()
+        assert st["levels"] == M.num_precs and st["n"] == A[0]
+        assert st["depth_merged"] * 5 <= st["depth_total"], st        # 700-900-deep chains -> well under 100
+        assert st["sweep_entries"] <= 2.5 * 2 * st["nnz"], st           # at a bounded cost in entries
+        b1, b2 = P.seeded_rhs(A[0], 1), P.seeded_rhs(A[0], 2)
+        x1 = G.solve(b1)
+        assert relerr(x1, M.solve(b1)) <= TOL_F64
+        x2, x12 = G.solve(b2), G.solve(2.0 * b1 - 3.0 * b2)
+        assert relerr(x12, 2.0 * x1 - 3.0 * x2) <= 1e-11
+        assert np.array_equal(G.solve(b1), G.solve(b1)) or relerr(G.solve(b1), x1) <= 1e-14
+        db = torch.from_numpy(b1).cuda()
+        dx, dy = torch.empty_like(db), torch.empty_like(db)
+        G.apply_dev(db.data_ptr(), dx.data_ptr(), op=hb.LHF_S)
+        G.apply_dev(dx.data_ptr(), dy.data_ptr(), op=hb.LHF_M)
+        G.synchronize()
+        assert relerr(dy.cpu().numpy(), b1) <= 1e-10
+        X = G.solve_mrhs(np.stack([b1, b2, b1 - b2], axis=1))
+        assert relerr(X[:, 2], x1 - x2) <= 1e-11
