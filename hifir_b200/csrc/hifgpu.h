@@ -107,9 +107,8 @@ struct SweepPlan {
   // level-major streaming layout (stream.cu); nblocks = number of 32-row slices
   bool                        stream = false;
   std::size_t                 st_depth = 0, st_padded = 0;
-  unsigned                    st_chunks = 0;  // st_warps slices each, all of one level set
+  unsigned                    st_chunks = 0;  // 8 slices each, all of one level set
   unsigned                    st_u = 8;       // entries per lane held in registers (kernel variant)
-  unsigned                    st_warps = 8;   // slices per chunk = warps per CTA (kernel variant)
   DevBuf<unsigned>            st_need;   // chunks per level set
   DevBuf<unsigned>            st_sdesc;  // uint4 per slice: offset (units of 32 entries), entries per lane, log2 lanes per row, level
   DevBuf<unsigned>            st_codes;  // 32 row codes per slice

@@ -43,7 +43,6 @@ static unsigned smem_budget() {
   const unsigned kb = e ? static_cast<unsigned>(std::atoi(e)) : 112u;
   return std::min(kSmemBudgetMax, std::max(16u, kb) * 1024u);
 }
-constexpr unsigned kSpinBurst = 2048;  // polls between two hang-guard / back-off checks
 constexpr unsigned kPollChunk  = 8;          // independent polling loads in flight per lane
 
 // block descriptor (32 bytes)

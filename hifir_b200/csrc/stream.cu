@@ -29,14 +29,10 @@
 
 namespace hifgpu {
 
-constexpr unsigned kStreamWarpsMax = 16;  // slices per ticket (= warps per CTA): 8 or 16, chosen at attach
-static unsigned stream_warps() {
-  const char *e = std::getenv("HIFIR_B200_STREAM_WARPS");
-  return e && std::atoi(e) == 16 ? 16u : 8u;
-}
-constexpr unsigned kPadCol        = 0xffffffffu;
-constexpr unsigned kPadCode       = 0xffffffffu;
-constexpr unsigned kEmptySlice    = 0xffffffffu;  // sdesc.z of a padding slice (its warp idles)
+constexpr unsigned kStreamWarps = 8;  // slices per ticket = warps per CTA
+constexpr unsigned kPadCol      = 0xffffffffu;
+constexpr unsigned kPadCode     = 0xffffffffu;
+constexpr unsigned kEmptySlice  = 0xffffffffu;  // sdesc.z of a padding slice (its warp idles)
 
 __device__ __forceinline__ unsigned ld_stream_u32(const unsigned *p) {
   unsigned v;
@@ -48,40 +44,6 @@ __device__ __forceinline__ double ld_stream_f64(const double *p) {
   asm volatile("ld.global.cs.f64 %0, [%1];" : "=d"(v) : "l"(p));
   return v;
 }
-
-// sync[0] = ticket counter, sync[1 + l] = finished chunks of level set l (both zeroed once per
-// apply).  The level counters only THROTTLE: the warps of a chunk of level l first pull their
-// share of the factor from HBM into registers (it depends on nothing), then wait until level
-// l - window is complete before they touch the solution buffer, so that at most `window` level
-// sets poll it at any time (thousands of run-ahead warps spinning on L2 would starve the
-// producers).  Correctness never depends on the counters -- readiness is carried by the tagged
-// values -- so they need no fences.
-//
-// Slice s (one warp): 32 / lpr rows, lpr = 2^sd.z lanes per row (long rows are spread over
-// several lanes and reduced with shuffles: the serial chain of a row is <= kU dependent-free
-// loads whatever its length); entry k of lane j at cols/vals[(sd.x + k) * 32 + j].
-// Chunk c (one CTA round) = slices [8c, 8c + 8), all of one level set (sd.w).
-// sync layout (ints): [0] ticket, [16] frontier hint, [kSyncStride * (1 + l)] chunk counter of level l
-// (one 128-byte line per counter: the pollers of different levels hit different L2 slices)
-// first try of a gather through L1: a hit needs no L2 request (one per clock and SM is all the
-// hardware serves).  A stale line can only show an old parity -> the entry is re-polled from L2.
-__device__ __forceinline__ unsigned long long ld_l1(const unsigned long long *p) {
-  unsigned long long v;
-  asm volatile("ld.global.ca.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void cp_async_4(void *smem_dst, const void *gsrc) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(static_cast<unsigned>(__cvta_generic_to_shared(smem_dst))),
-               "l"(gsrc)
-               : "memory");
-}
-__device__ __forceinline__ void cp_async_8(void *smem_dst, const void *gsrc) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(static_cast<unsigned>(__cvta_generic_to_shared(smem_dst))),
-               "l"(gsrc)
-               : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ int ld_poll_i32(const int *p) {
   int v;
   asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -92,7 +54,6 @@ __device__ __forceinline__ unsigned long long stream_timer_ns() {
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
-
 __device__ __forceinline__ void ld_poll_v2(const unsigned long long *p, unsigned long long &a, unsigned long long &b) {
   asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
 }
@@ -100,26 +61,40 @@ __device__ __forceinline__ void st_publish_v2(unsigned long long *p, unsigned lo
   asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(a), "l"(b) : "memory");
 }
 
+// sync layout (ints, zeroed once per apply): [0] ticket counter, [16] frontier hint (highest
+// completed level set + 1), [kSyncStride * (1 + l)] finished chunks of level set l (one 128-byte
+// line per counter: the pollers of different levels hit different L2 slices).  The level counters
+// only THROTTLE: the warps of a chunk of level l first pull their share of the factor from HBM
+// into registers (it depends on nothing), then wait until level l - window is complete before
+// they touch the solution buffer, so that at most `window` level sets poll it at any time
+// (thousands of run-ahead warps spinning on L2 would starve the producers).  Correctness never
+// depends on the counters -- readiness is carried by the tagged values -- so they need no fences.
+//
+// Slice s (one warp): 32 / lpr rows, lpr = 2^sd.z lanes per row (long rows are spread over
+// several lanes and reduced with shuffles); entry k of lane j at cols/vals[(sd.x + k) * 32 + j].
+// Chunk c (one CTA round) = slices [8c, 8c + 8), all of one level set (sd.w).
+//
 // NR right-hand sides per row (row-interleaved, X[i*NR + c], the Array<std::array<T,Nrhs>>
 // layout of hif::HIF::solve_mrhs, builder.hpp:433-445; per-column arithmetic =
 // CCS::solve_as_strict_lower/upper_mrhs, CompressedStorage.hpp:2286-2301, 2376-2393): a lane keeps
 // NR accumulators, a dependency is ONE 64-byte gather (NR = 8) instead of eight 8-byte ones, and
 // the factor is streamed once for all NR columns.  Same plan (sliced ELL) as for NR = 1.
-template <bool UPPER, int kU, int NR, int kW, int kOcc>
-__global__ void __launch_bounds__(kW * 32, kOcc)
+//
+// kU entries per lane are held in registers; their gathers go out kG at a time.  Measured at
+// 128^3 (ms per apply): kU = 4 / 5 CTAs per SM 1.58, kU = 8 / kG = 4 / 4 CTAs 1.37 (the optimum:
+// 2, 3, 5, 6 CTAs per SM, kU = 16 and shared-memory staging of the entries are all slower).
+template <bool UPPER, int kU, int NR>
+__global__ void __launch_bounds__(kStreamWarps * 32, NR > 1 ? 2 : (kU == 4 ? 5 : 4))
     sweep_stream_kernel(const unsigned nchunks, const uint4 *__restrict__ sdesc, const unsigned *__restrict__ lvl_need,
                         const unsigned *__restrict__ codes, const unsigned *__restrict__ cols,
                         const double *__restrict__ vals, const unsigned m, const double *__restrict__ rhs_plain,
                         const unsigned long long *rhs_tagged, const double *__restrict__ diag, unsigned long long *x,
                         const unsigned parity, int *sync, int *error_flag, const unsigned window,
                         const unsigned adm_sleep, const unsigned near_sleep, const unsigned poll_sleep,
-                        const int use_l1, const unsigned defer, unsigned long long *trace) {
+                        const int publish_st, unsigned long long *trace) {
   static_assert(NR == 1 || NR % 2 == 0, "NR must be 1 or even (128-bit transactions)");
   constexpr int kG = NR == 1 ? (kU > 4 ? 4 : kU) : 2;  // entries whose gathers are in flight together
   static_assert(kU % kG == 0, "kU must be a multiple of the gather group");
-  constexpr bool kStage = kOcc >= 5 && NR == 1 && kU == 8;  // the high-occupancy variant stages the factor in shared memory
-  __shared__ unsigned s_cols[kStage ? kW * kU * 32 : 1];
-  __shared__ double   s_vals[kStage ? kW * kU * 32 : 1];
   __shared__ unsigned s_c[2];
   __shared__ int      s_last;
   const unsigned      warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
@@ -134,7 +109,7 @@ __global__ void __launch_bounds__(kW * 32, kOcc)
     const unsigned c = s_c[round & 1u];
     if (c >= nchunks) break;
     if (trace && threadIdx.x == 0) trace[8 * c + 0] = stream_timer_ns();
-    const unsigned s    = c * kW + warp;
+    const unsigned s    = c * kStreamWarps + warp;
     const uint4    sd   = sdesc[s];  // x: offset (units of 32 entries), y: entries per lane, z: log2 lanes per row, w: level
     const bool     idle = sd.z == kEmptySlice;  // padding slice of a spread-out thin level set
     const unsigned code = idle ? kPadCode : codes[static_cast<std::size_t>(s) * 32u + lane];
@@ -143,29 +118,15 @@ __global__ void __launch_bounds__(kW * 32, kOcc)
     const std::size_t slot = static_cast<std::size_t>(code & kCodeSlotMask);
     const std::size_t base = static_cast<std::size_t>(sd.x) * 32u + lane;
     const unsigned    len  = sd.y;
-    // ---- everything that does not depend on other rows: factor entries, right-hand side.
-    // kStage: the entries go to shared memory with cp.async (no registers held while the chunk
-    // waits for its admission: two more CTAs per SM), else into registers
-    unsigned cc[kStage ? 1 : kU];
-    double   vv[kStage ? 1 : kU];
-    unsigned *const my_cols = s_cols + (kStage ? (warp * kU) * 32u + lane : 0u);
-    double *const   my_vals = s_vals + (kStage ? (warp * kU) * 32u + lane : 0u);
-    if (kStage) {
+    // ---- everything that does not depend on other rows: factor entries, right-hand side
+    unsigned cc[kU];
+    double   vv[kU];
 #pragma unroll
-      for (int u = 0; u < kU; ++u)
-        if (static_cast<unsigned>(u) < len) {
-          cp_async_4(my_cols + u * 32, cols + base + static_cast<std::size_t>(u) * 32u);
-          cp_async_8(my_vals + u * 32, vals + base + static_cast<std::size_t>(u) * 32u);
-        }
-      cp_async_commit();
-    } else {
-#pragma unroll
-      for (int u = 0; u < kU; ++u) {
-        cc[u] = kPadCol;
-        if (static_cast<unsigned>(u) < len) {
-          cc[u] = ld_stream_u32(cols + base + static_cast<std::size_t>(u) * 32u);
-          vv[u] = ld_stream_f64(vals + base + static_cast<std::size_t>(u) * 32u);
-        }
+    for (int u = 0; u < kU; ++u) {
+      cc[u] = kPadCol;
+      if (static_cast<unsigned>(u) < len) {
+        cc[u] = ld_stream_u32(cols + base + static_cast<std::size_t>(u) * 32u);
+        vv[u] = ld_stream_f64(vals + base + static_cast<std::size_t>(u) * 32u);
       }
     }
     double acc[NR];
@@ -184,15 +145,15 @@ __global__ void __launch_bounds__(kW * 32, kOcc)
         for (int q = 0; q < NR; ++q) acc[q] = rhs_plain[ri * NR + q];
       }
     }
-    // ---- admission: level sd.w - window complete (thread 0 polls for the CTA).  sync[16] =
-    // highest completed level + 1 (a hint): far-away waiters sleep in proportion to their distance
-    // from it and only look at this one word, the waiters of the next levels spin on their counter
+    // ---- admission: level sd.w - window complete (thread 0 polls for the CTA).  Far-away
+    // waiters sleep in proportion to their distance from the frontier hint and only look at
+    // that one word, the waiters of the next levels spin on their counter
     if (threadIdx.x == 0) {
       s_last = static_cast<int>(sd.w);
       if (trace) {
         unsigned smid;
         asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-        trace[8 * c + 1] = stream_timer_ns();  // factor entries in registers
+        trace[8 * c + 1] = stream_timer_ns();  // factor entries requested
         trace[8 * c + 4] = sd.w;
         trace[8 * c + 5] = smid;
       }
@@ -225,19 +186,18 @@ __global__ void __launch_bounds__(kW * 32, kOcc)
           atomicMax(sync + 16, static_cast<int>(f_seen));
         }
       }
+      if (trace) trace[8 * c + 2] = stream_timer_ns();  // admitted
     }
-    if (trace && threadIdx.x == 0) trace[8 * c + 2] = stream_timer_ns();  // admitted
     __syncthreads();
     // the next ticket is fetched behind the gathers of this chunk (off the critical path); it is
     // held for the ~1 us this chunk still needs, which delays nobody
-    unsigned next_ticket = 0;
-    bool     waited      = false;
-    const bool ticket_lane = threadIdx.x == (kW > 1 ? 32u : 0u);
+    unsigned   next_ticket = 0;
+    const bool ticket_lane = threadIdx.x == 32u;
     // ---- gather the dependencies optimistically, re-poll the ones that are not ready
-    auto gather = [&](unsigned col, unsigned long long(&g)[NR], bool first) {
+    auto gather = [&](unsigned col, unsigned long long(&g)[NR]) {
       const unsigned long long *src = x + static_cast<std::size_t>(col) * NR;
       if (NR == 1) {
-        g[0] = (first && (use_l1 & 1)) ? ld_l1(src) : ld_poll(src);
+        g[0] = ld_poll(src);
       } else {
 #pragma unroll
         for (int q = 0; q < NR; q += 2) ld_poll_v2(src + q, g[q], g[q + 1]);
@@ -249,32 +209,19 @@ __global__ void __launch_bounds__(kW * 32, kOcc)
       for (int q = 0; q < NR; ++q) ok &= tag_ready(g[q], parity);
       return ok;
     };
-    if (kStage) cp_async_wait_all();
     for (unsigned k = 0;;) {
 #pragma unroll
       for (int u0 = 0; u0 < kU; u0 += kG) {
-        unsigned ccg[kG];
-        double   vvg[kG];
-#pragma unroll
-        for (int j = 0; j < kG; ++j) {
-          if (kStage) {
-            ccg[j] = (k + u0 + j < len) ? my_cols[(u0 + j) * 32] : kPadCol;
-            vvg[j] = (k + u0 + j < len) ? my_vals[(u0 + j) * 32] : 0.0;
-          } else {
-            ccg[j] = cc[kStage ? 0 : u0 + j];
-            vvg[j] = vv[kStage ? 0 : u0 + j];
-          }
-        }
         unsigned long long g[kG][NR];
 #pragma unroll
         for (int j = 0; j < kG; ++j)
-          if (ccg[j] != kPadCol) gather(ccg[j], g[j], true);
+          if (cc[u0 + j] != kPadCol) gather(cc[u0 + j], g[j]);
         if (ticket_lane && k == 0 && u0 == 0) next_ticket = static_cast<unsigned>(atomicAdd(sync, 1));
         if (trace && threadIdx.x == 0 && k == 0 && u0 == 0) {  // warp 0: first gather round trip
           unsigned long long any = 0;
 #pragma unroll
           for (int j = 0; j < kG; ++j)
-            if (ccg[j] != kPadCol) any |= g[j][0];
+            if (cc[j] != kPadCol) any |= g[j][0];
           trace[8 * c + 6] = stream_timer_ns() + (any == 0x7ff8dead00000001ull ? 1u : 0u);
         }
         // entries that were not ready on the first try (padding counts as ready) are re-polled
@@ -282,26 +229,12 @@ __global__ void __launch_bounds__(kW * 32, kOcc)
         unsigned pend = 0;
 #pragma unroll
         for (int j = 0; j < kG; ++j)
-          if (ccg[j] != kPadCol && !ready(g[j])) pend |= 1u << j;
-        // deferred polling: the missing values are produced by level sets >= sd.w - defer; nothing
-        // can arrive before level sd.w - defer - 1 is complete, so wait for that counter (one word
-        // per warp) instead of re-gathering 32 x pending sectors round after round
-        if (defer && !waited && sd.w > defer && __any_sync(0xffffffffu, pend != 0u)) {
-          waited = true;
-          if (lane == 0) {
-            const unsigned t    = sd.w - defer - 1u;
-            const unsigned need = lvl_need[t];
-            const int *    ctr  = sync + kSyncStride * (1 + t);
-            for (unsigned spins = 0; static_cast<unsigned>(ld_poll_i32(ctr)) < need && spins < (kSpinLimit >> 4); ++spins)
-              __nanosleep(100);
-          }
-          __syncwarp();
-        }
+          if (cc[u0 + j] != kPadCol && !ready(g[j])) pend |= 1u << j;
         for (unsigned rounds = 0; __any_sync(0xffffffffu, pend != 0u);) {
           if (poll_sleep) __nanosleep(poll_sleep);
 #pragma unroll
           for (int j = 0; j < kG; ++j)
-            if (pend & (1u << j)) gather(ccg[j], g[j], false);
+            if (pend & (1u << j)) gather(cc[u0 + j], g[j]);
 #pragma unroll
           for (int j = 0; j < kG; ++j)
             if ((pend & (1u << j)) && ready(g[j])) pend &= ~(1u << j);
@@ -312,31 +245,19 @@ __global__ void __launch_bounds__(kW * 32, kOcc)
         }
 #pragma unroll
         for (int j = 0; j < kG; ++j)
-          if (ccg[j] != kPadCol) {
+          if (cc[u0 + j] != kPadCol) {
 #pragma unroll
-            for (int q = 0; q < NR; ++q) acc[q] = fma(-vvg[j], tag_value(g[j][q]), acc[q]);
+            for (int q = 0; q < NR; ++q) acc[q] = fma(-vv[u0 + j], tag_value(g[j][q]), acc[q]);
           }
       }
       k += kU;
       if (k >= len) break;
-      // rows longer than kU * lpr entries (rare): the next kU entries per lane
-      if (kStage) {
 #pragma unroll
-        for (int u = 0; u < kU; ++u)
-          if (k + u < len) {
-            cp_async_4(my_cols + u * 32, cols + base + static_cast<std::size_t>(k + u) * 32u);
-            cp_async_8(my_vals + u * 32, vals + base + static_cast<std::size_t>(k + u) * 32u);
-          }
-        cp_async_commit();
-        cp_async_wait_all();
-      } else {
-#pragma unroll
-        for (int u = 0; u < kU; ++u) {
-          cc[kStage ? 0 : u] = kPadCol;
-          if (k + u < len) {
-            cc[kStage ? 0 : u] = ld_stream_u32(cols + base + static_cast<std::size_t>(k + u) * 32u);
-            vv[kStage ? 0 : u] = ld_stream_f64(vals + base + static_cast<std::size_t>(k + u) * 32u);
-          }
+      for (int u = 0; u < kU; ++u) {  // rows longer than kU * lpr entries (rare)
+        cc[u] = kPadCol;
+        if (k + u < len) {
+          cc[u] = ld_stream_u32(cols + base + static_cast<std::size_t>(k + u) * 32u);
+          vv[u] = ld_stream_f64(vals + base + static_cast<std::size_t>(k + u) * 32u);
         }
       }
     }
@@ -347,7 +268,7 @@ __global__ void __launch_bounds__(kW * 32, kOcc)
     }
     if (act) {
       if (NR == 1) {
-        if (!(use_l1 & 2)) {
+        if (!publish_st) {
           // publish through the L2 atomic unit: an exchange is visible to the pollers ~0.2 us
           // earlier than a plain store (measured: 1.81 -> 1.64 ms per apply at 128^3)
           unsigned long long old;
@@ -388,11 +309,10 @@ unsigned lanes_log2_for(unsigned len, unsigned U, unsigned R) {
 }
 unsigned stream_unroll() {
   const char *e = std::getenv("HIFIR_B200_STREAM_U");
-  const int u = e ? std::atoi(e) : 8;  // measured at 128^3: 4 -> 1.58 ms, 8 -> 1.37 ms per apply
-  return u == 4 ? 4u : (u == 16 ? 16u : 8u);
+  return e && std::atoi(e) == 4 ? 4u : 8u;  // measured at 128^3: 4 -> 1.58 ms, 8 -> 1.37 ms per apply
 }
 
-void pack_stream(const HostCsr &S, StreamHost &H, unsigned U, unsigned kStreamWarps, unsigned R = 32u) {
+void pack_stream(const HostCsr &S, StreamHost &H, unsigned U, unsigned R = 32u) {
   const unsigned m = static_cast<unsigned>(S.nrows);
   if (!m) return;
   if (S.gid.size() != m) throw std::logic_error("build_stream_plan: factor is not in sweep form");
@@ -500,10 +420,8 @@ void build_stream_plan(const HostCsr &S, bool upper, SweepPlan &plan, std::size_
   plan.nblocks = 0;
   if (!S.nrows) return;
   StreamHost H;
-  plan.st_u     = stream_unroll();
-  plan.st_warps = stream_warps();
-  const unsigned kStreamWarps = plan.st_warps;
-  pack_stream(S, H, plan.st_u, plan.st_warps);
+  plan.st_u = stream_unroll();
+  pack_stream(S, H, plan.st_u);
   plan.nblocks    = static_cast<unsigned>(H.sdesc.size());  // slices
   plan.slab_bytes = H.cols.size() * 12u + H.codes.size() * 4u + H.sdesc.size() * 16u;
   plan.st_depth   = H.depth;
@@ -522,7 +440,7 @@ void build_stream_plan(const HostCsr &S, bool upper, SweepPlan &plan, std::size_
 void stream_host_emulate(const HostCsr &S, bool upper, const double *rhs, const double *diag, double *x,
                          std::size_t stats[4]) {
   StreamHost H;
-  pack_stream(S, H, stream_unroll(), stream_warps());
+  pack_stream(S, H, stream_unroll());
   const unsigned m = static_cast<unsigned>(S.orig_rows);
   for (std::size_t s = 0; s < H.sdesc.size(); ++s) {
     const uint4 sd = H.sdesc[s];
@@ -558,69 +476,37 @@ int stream_env(const char *name, int dflt) {
   const char *e = std::getenv(name);
   return e ? std::atoi(e) : dflt;
 }
-template <bool UPPER, int kU, int NR, int kW, int kOcc>
-void launch_stream_O(Handle *h, const SweepPlan &plan, const double *rhs_plain, const unsigned long long *rhs_tagged,
-                     const double *diag, unsigned long long *x, unsigned parity, int *sync, unsigned long long *trace) {
-  static int ctas_per_sm = 0;
-  if (!ctas_per_sm) {
-    HIF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, sweep_stream_kernel<UPPER, kU, NR, kW, kOcc>,
-                                                           kW * 32, 0));
-    if (ctas_per_sm < 1) ctas_per_sm = 1;
-  }
-  const unsigned window = static_cast<unsigned>(std::max(1, stream_env("HIFIR_B200_STREAM_WINDOW", 3)));
-  const unsigned sleep  = static_cast<unsigned>(std::max(20, stream_env("HIFIR_B200_STREAM_SLEEP", 300)));
-  const unsigned near_sleep = static_cast<unsigned>(std::max(0, stream_env("HIFIR_B200_STREAM_NEAR_SLEEP", 0)));
-  const unsigned poll_sleep = static_cast<unsigned>(std::max(0, stream_env("HIFIR_B200_STREAM_POLL_SLEEP", 0)));
-  const unsigned grid   = std::min<unsigned>(plan.st_chunks + 1u, static_cast<unsigned>(kNumSMs * ctas_per_sm));
-  sweep_stream_kernel<UPPER, kU, NR, kW, kOcc><<<grid, kW * 32, 0, h->stream>>>(
-      plan.st_chunks, reinterpret_cast<const uint4 *>(plan.st_sdesc.p), plan.st_need.p, plan.st_codes.p,
-      plan.st_cols.p, plan.st_vals.p, plan.m, rhs_plain, rhs_tagged, diag, x, parity, sync, h->error_flag.p, window,
-      sleep, near_sleep, poll_sleep, stream_env("HIFIR_B200_STREAM_L1", 0) | (stream_env("HIFIR_B200_STREAM_PUBLISH_ST", 0) ? 2 : 0),
-      static_cast<unsigned>(std::max(0, stream_env("HIFIR_B200_STREAM_DEFER", 0))), trace);
-}
-// CTAs per SM the kernel is compiled for (register budget): the sweep is bound by the number of
-// gathers in flight per SM, so occupancy is worth a few spilled registers
-template <bool UPPER, int kU, int NR, int kW>
-void launch_stream_W(Handle *h, const SweepPlan &plan, const double *rhs_plain, const unsigned long long *rhs_tagged,
-                     const double *diag, unsigned long long *x, unsigned parity, int *sync, unsigned long long *trace) {
-  constexpr int kBase = (NR > 1 ? 2 : (kU == 4 ? 5 : (kU == 8 ? 4 : 2))) * 8 / kW;
-  // HIFIR_B200_STREAM_OCC = 6 / 8: variants compiled for more CTAs per SM; they stage the factor
-  // entries in shared memory (cp.async) instead of registers
-  if (NR == 1 && kW == 8 && kU <= 8) {
-    constexpr bool ok  = NR == 1 && kW == 8 && kU <= 8;
-    const int      occ = stream_env("HIFIR_B200_STREAM_OCC", 0);
-    if (occ == 5 && kU == 8) return launch_stream_O<UPPER, kU, NR, kW, (ok && kU == 8) ? 5 : kBase>(h, plan, rhs_plain, rhs_tagged, diag, x, parity, sync, trace);
-    if (occ == 3) return launch_stream_O<UPPER, kU, NR, kW, ok ? 3 : kBase>(h, plan, rhs_plain, rhs_tagged, diag, x, parity, sync, trace);
-    if (occ == 2) return launch_stream_O<UPPER, kU, NR, kW, ok ? 2 : kBase>(h, plan, rhs_plain, rhs_tagged, diag, x, parity, sync, trace);
-    if (occ == 6) return launch_stream_O<UPPER, kU, NR, kW, ok ? 6 : kBase>(h, plan, rhs_plain, rhs_tagged, diag, x, parity, sync, trace);
-    if (occ == 8) return launch_stream_O<UPPER, kU, NR, kW, ok ? 8 : kBase>(h, plan, rhs_plain, rhs_tagged, diag, x, parity, sync, trace);
-  }
-  launch_stream_O<UPPER, kU, NR, kW, kBase>(h, plan, rhs_plain, rhs_tagged, diag, x, parity, sync, trace);
-}
 template <bool UPPER, int kU, int NR>
 void launch_stream_T(Handle *h, const SweepPlan &plan, const double *rhs_plain, const unsigned long long *rhs_tagged,
                      const double *diag, unsigned long long *x, unsigned parity, int *sync, unsigned long long *trace) {
-  if (plan.st_warps == 16)
-    launch_stream_W<UPPER, kU, NR, 16>(h, plan, rhs_plain, rhs_tagged, diag, x, parity, sync, trace);
-  else
-    launch_stream_W<UPPER, kU, NR, 8>(h, plan, rhs_plain, rhs_tagged, diag, x, parity, sync, trace);
+  static int ctas_per_sm = 0;
+  if (!ctas_per_sm) {
+    HIF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, sweep_stream_kernel<UPPER, kU, NR>,
+                                                           static_cast<int>(kStreamWarps * 32), 0));
+    if (ctas_per_sm < 1) ctas_per_sm = 1;
+  }
+  const unsigned window     = static_cast<unsigned>(std::max(1, stream_env("HIFIR_B200_STREAM_WINDOW", 3)));
+  const unsigned sleep      = static_cast<unsigned>(std::max(20, stream_env("HIFIR_B200_STREAM_SLEEP", 300)));
+  const unsigned near_sleep = static_cast<unsigned>(std::max(0, stream_env("HIFIR_B200_STREAM_NEAR_SLEEP", 0)));
+  const unsigned poll_sleep = static_cast<unsigned>(std::max(0, stream_env("HIFIR_B200_STREAM_POLL_SLEEP", 0)));
+  const unsigned grid = std::min<unsigned>(plan.st_chunks + 1u, static_cast<unsigned>(kNumSMs * ctas_per_sm));
+  sweep_stream_kernel<UPPER, kU, NR><<<grid, kStreamWarps * 32, 0, h->stream>>>(
+      plan.st_chunks, reinterpret_cast<const uint4 *>(plan.st_sdesc.p), plan.st_need.p, plan.st_codes.p,
+      plan.st_cols.p, plan.st_vals.p, plan.m, rhs_plain, rhs_tagged, diag, x, parity, sync, h->error_flag.p, window,
+      sleep, near_sleep, poll_sleep, stream_env("HIFIR_B200_STREAM_PUBLISH_ST", 0), trace);
 }
 template <bool UPPER>
 void launch_stream_U(Handle *h, const SweepPlan &plan, const double *rhs_plain, const unsigned long long *rhs_tagged,
                      const double *diag, unsigned long long *x, unsigned parity, int *sync, unsigned long long *trace,
                      unsigned nr) {
-  if (nr == kMrhsWidth && plan.st_u == 16)
-    throw std::logic_error("multi-rhs sweeps need a plan with 4 or 8 entries per lane");
-  else if (nr == kMrhsWidth && plan.st_u == 4)
-    launch_stream_T<UPPER, 4, static_cast<int>(kMrhsWidth)>(h, plan, rhs_plain, rhs_tagged, diag, x, parity, sync, trace);
+  if (nr != 1u && nr != kMrhsWidth) throw std::logic_error("unsupported multi-rhs width");
+  constexpr int W = static_cast<int>(kMrhsWidth);
+  if (nr == kMrhsWidth && plan.st_u == 4)
+    launch_stream_T<UPPER, 4, W>(h, plan, rhs_plain, rhs_tagged, diag, x, parity, sync, trace);
   else if (nr == kMrhsWidth)
-    launch_stream_T<UPPER, 8, static_cast<int>(kMrhsWidth)>(h, plan, rhs_plain, rhs_tagged, diag, x, parity, sync, trace);
-  else if (nr != 1u)
-    throw std::logic_error("unsupported multi-rhs width");
+    launch_stream_T<UPPER, 8, W>(h, plan, rhs_plain, rhs_tagged, diag, x, parity, sync, trace);
   else if (plan.st_u == 4)
     launch_stream_T<UPPER, 4, 1>(h, plan, rhs_plain, rhs_tagged, diag, x, parity, sync, trace);
-  else if (plan.st_u == 16)
-    launch_stream_T<UPPER, 16, 1>(h, plan, rhs_plain, rhs_tagged, diag, x, parity, sync, trace);
   else
     launch_stream_T<UPPER, 8, 1>(h, plan, rhs_plain, rhs_tagged, diag, x, parity, sync, trace);
 }
@@ -630,10 +516,6 @@ void launch_stream_sweep(Handle *h, const SweepPlan &plan, const double *rhs_pla
                          const unsigned long long *rhs_tagged, const double *diag, unsigned long long *x,
                          unsigned parity, int *ticket, unsigned long long *trace, unsigned nr) {
   if (!plan.nblocks) return;
-  // experiment: pre-set the solution buffer to "not ready" with full-sector writes (in case the
-  // first load of a value stored into a non-resident sector waited for a fill) -- measured: no effect
-  if (stream_env("HIFIR_B200_STREAM_PRESET", 0))
-    HIF_CUDA(cudaMemsetAsync(x, parity ? 0x00 : 0xff, 2ull * plan.m * nr * sizeof(unsigned long long), h->stream));
   if (plan.upper)
     launch_stream_U<true>(h, plan, rhs_plain, rhs_tagged, diag, x, parity, ticket, trace, nr);
   else
