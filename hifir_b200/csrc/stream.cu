@@ -83,15 +83,15 @@ __device__ __forceinline__ void st_publish_v2(unsigned long long *p, unsigned lo
 // kU entries per lane are held in registers; their gathers go out kG at a time.  Measured at
 // 128^3 (ms per apply): kU = 4 / 5 CTAs per SM 1.58, kU = 8 / kG = 4 / 4 CTAs 1.37 (the optimum:
 // 2, 3, 5, 6 CTAs per SM, kU = 16 and shared-memory staging of the entries are all slower).
-template <bool UPPER, int kU, int NR>
+template <bool UPPER, int kU, int NR, bool kTrace>
 __global__ void __launch_bounds__(kStreamWarps * 32, NR > 1 ? 2 : (kU == 4 ? 5 : 4))
     sweep_stream_kernel(const unsigned nchunks, const uint4 *__restrict__ sdesc, const unsigned *__restrict__ lvl_need,
                         const unsigned *__restrict__ codes, const unsigned *__restrict__ cols,
                         const double *__restrict__ vals, const unsigned m, const double *__restrict__ rhs_plain,
                         const unsigned long long *rhs_tagged, const double *__restrict__ diag, unsigned long long *x,
                         const unsigned parity, int *sync, int *error_flag, const unsigned window,
-                        const unsigned adm_sleep, const unsigned near_sleep, const unsigned poll_sleep,
-                        const int publish_st, unsigned long long *trace) {
+                        const unsigned adm_sleep, const int publish_st, unsigned long long *trace_buf) {
+  unsigned long long *const trace = kTrace ? trace_buf : nullptr;  // the production variant carries no tracing code
   static_assert(NR == 1 || NR % 2 == 0, "NR must be 1 or even (128-bit transactions)");
   constexpr int kG = NR == 1 ? (kU > 4 ? 4 : kU) : 2;  // entries whose gathers are in flight together
   static_assert(kU % kG == 0, "kU must be a multiple of the gather group");
@@ -167,7 +167,6 @@ __global__ void __launch_bounds__(kStreamWarps * 32, NR > 1 ? 2 : (kU == 4 ? 5 :
           const unsigned f = static_cast<unsigned>(ld_poll_i32(sync + 16));  // levels [0, f) are known to be done
           if (t < f + 2u) {
             while (static_cast<unsigned>(ld_poll_i32(ctr)) < need) {
-              if (near_sleep) __nanosleep(near_sleep);
               if (++spins > (kSpinLimit >> 4)) {
                 *error_flag = 1;
                 break;
@@ -231,7 +230,6 @@ __global__ void __launch_bounds__(kStreamWarps * 32, NR > 1 ? 2 : (kU == 4 ? 5 :
         for (int j = 0; j < kG; ++j)
           if (cc[u0 + j] != kPadCol && !ready(g[j])) pend |= 1u << j;
         for (unsigned rounds = 0; __any_sync(0xffffffffu, pend != 0u);) {
-          if (poll_sleep) __nanosleep(poll_sleep);
 #pragma unroll
           for (int j = 0; j < kG; ++j)
             if (pend & (1u << j)) gather(cc[u0 + j], g[j]);
@@ -481,19 +479,23 @@ void launch_stream_T(Handle *h, const SweepPlan &plan, const double *rhs_plain, 
                      const double *diag, unsigned long long *x, unsigned parity, int *sync, unsigned long long *trace) {
   static int ctas_per_sm = 0;
   if (!ctas_per_sm) {
-    HIF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, sweep_stream_kernel<UPPER, kU, NR>,
+    HIF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, sweep_stream_kernel<UPPER, kU, NR, false>,
                                                            static_cast<int>(kStreamWarps * 32), 0));
     if (ctas_per_sm < 1) ctas_per_sm = 1;
   }
-  const unsigned window     = static_cast<unsigned>(std::max(1, stream_env("HIFIR_B200_STREAM_WINDOW", 3)));
-  const unsigned sleep      = static_cast<unsigned>(std::max(20, stream_env("HIFIR_B200_STREAM_SLEEP", 300)));
-  const unsigned near_sleep = static_cast<unsigned>(std::max(0, stream_env("HIFIR_B200_STREAM_NEAR_SLEEP", 0)));
-  const unsigned poll_sleep = static_cast<unsigned>(std::max(0, stream_env("HIFIR_B200_STREAM_POLL_SLEEP", 0)));
-  const unsigned grid = std::min<unsigned>(plan.st_chunks + 1u, static_cast<unsigned>(kNumSMs * ctas_per_sm));
-  sweep_stream_kernel<UPPER, kU, NR><<<grid, kStreamWarps * 32, 0, h->stream>>>(
-      plan.st_chunks, reinterpret_cast<const uint4 *>(plan.st_sdesc.p), plan.st_need.p, plan.st_codes.p,
-      plan.st_cols.p, plan.st_vals.p, plan.m, rhs_plain, rhs_tagged, diag, x, parity, sync, h->error_flag.p, window,
-      sleep, near_sleep, poll_sleep, stream_env("HIFIR_B200_STREAM_PUBLISH_ST", 0), trace);
+  const unsigned window = static_cast<unsigned>(std::max(1, stream_env("HIFIR_B200_STREAM_WINDOW", 3)));
+  const unsigned sleep  = static_cast<unsigned>(std::max(20, stream_env("HIFIR_B200_STREAM_SLEEP", 300)));
+  const int      pub_st = stream_env("HIFIR_B200_STREAM_PUBLISH_ST", 0);
+  const unsigned grid   = std::min<unsigned>(plan.st_chunks + 1u, static_cast<unsigned>(kNumSMs * ctas_per_sm));
+  const uint4 *  sdesc  = reinterpret_cast<const uint4 *>(plan.st_sdesc.p);
+  if (trace)
+    sweep_stream_kernel<UPPER, kU, NR, true><<<grid, kStreamWarps * 32, 0, h->stream>>>(
+        plan.st_chunks, sdesc, plan.st_need.p, plan.st_codes.p, plan.st_cols.p, plan.st_vals.p, plan.m, rhs_plain,
+        rhs_tagged, diag, x, parity, sync, h->error_flag.p, window, sleep, pub_st, trace);
+  else
+    sweep_stream_kernel<UPPER, kU, NR, false><<<grid, kStreamWarps * 32, 0, h->stream>>>(
+        plan.st_chunks, sdesc, plan.st_need.p, plan.st_codes.p, plan.st_cols.p, plan.st_vals.p, plan.m, rhs_plain,
+        rhs_tagged, diag, x, parity, sync, h->error_flag.p, window, sleep, pub_st, nullptr);
 }
 template <bool UPPER>
 void launch_stream_U(Handle *h, const SweepPlan &plan, const double *rhs_plain, const unsigned long long *rhs_tagged,
