@@ -295,3 +295,48 @@ def test_large_size_properties_and_merged_structure():
         assert relerr(dy.cpu().numpy(), b1) <= 1e-10
         X = G.solve_mrhs(np.stack([b1, b2, b1 - b2], axis=1))
         assert relerr(X[:, 2], x1 - x2) <= 1e-11
+
+
+def _ccs(dense):
+    """dense 2-D array -> (nrows, ncols, col_start, row_ind, vals) as the level dicts hold them"""
+    import scipy.sparse as sp
+    A = sp.csc_matrix(dense)
+    A.sort_indices()
+    return (dense.shape[0], dense.shape[1], A.indptr.astype(np.int64), A.indices.astype(np.int32),
+            A.data.astype(np.float64))
+
+
+def _tiny_level(rng, n, m, dense=False):
+    import scipy.linalg as sl
+    nm = n - m
+    L = np.tril(rng.uniform(-0.5, 0.5, (m, m)) * (rng.uniform(size=(m, m)) < 0.6), -1)
+    U = np.triu(rng.uniform(-0.5, 0.5, (m, m)) * (rng.uniform(size=(m, m)) < 0.6), 1)
+    lev = dict(m=m, n=n, dense_n=0, dense_rank=0, has_symm_dense=0, L=_ccs(L), U=_ccs(U),
+               E=_ccs(rng.uniform(-1, 1, (nm, m))), F=_ccs(rng.uniform(-1, 1, (m, nm))),
+               d=rng.uniform(1, 2, m), s=rng.uniform(0.5, 2, n), t=rng.uniform(0.5, 2, n))
+    p, q = rng.permutation(n).astype(np.int32), rng.permutation(n).astype(np.int32)
+    lev.update(p=p, q=q, p_inv=np.argsort(p).astype(np.int32), q_inv=np.argsort(q).astype(np.int32))
+    if dense:
+        (qr, tau), _, piv = sl.qr(rng.uniform(-1, 1, (nm, nm)) + 3 * np.eye(nm), mode="raw", pivoting=True)
+        lev.update(dense_n=nm, dense_rank=nm, qr_mat=np.asfortranarray(qr).ravel(order="F"), qr_tau=tau,
+                   qr_jpvt=(piv + 1).astype(np.int32))
+    return lev
+
+
+@pytest.mark.parametrize("shape", [(5, 5, False), (3, 1, True), (4, 0, True), (1, 1, False), (40, 33, True)],
+                         ids=lambda s: f"n{s[0]}m{s[1]}")
+def test_degenerate_levels(shape):
+    """levels with m = 0, m = 1, n = m (no Schur block), a dense level only --
+    hand-made factors, checked against the C oracle (single and multi right-hand side)."""
+    n, m, dense = shape
+    rng = np.random.default_rng(100 * n + m)
+    levels = [_tiny_level(rng, n, m, dense)]
+    Oh = O.OracleHif(levels)
+    with hb.GpuHif(levels) as G:
+        for k in range(3):
+            b = rng.uniform(-1, 1, n)
+            assert relerr(G.solve(b), Oh.solve(b)) <= TOL_F64
+        B = rng.uniform(-1, 1, (n, 3))
+        X = G.solve_mrhs(B)
+        for k in range(3):
+            assert relerr(X[:, k], Oh.solve(np.ascontiguousarray(B[:, k]))) <= TOL_F64
