@@ -46,11 +46,17 @@ def _ptr(a):
     return a.ctypes.data_as(C.c_void_p) if a is not None and a.size else None
 
 
-def make_level_structs(levels):
+def levels_dtype(levels):
+    """float32 if the factor values of `levels` are single precision (hif::HIF<float>), else float64"""
+    return np.dtype(np.float32) if np.asarray(levels[0]["s"]).dtype == np.float32 else np.dtype(np.float64)
+
+
+def make_level_structs(levels, dtype=np.float64):
     """Describe per-level factors (list of dicts, the layout produced by the factor producer:
     CCS blocks 'L','U','E','F' = (nrows, ncols, col_start[int64], row_ind[int32], vals[f64]),
     'd','s','t','p','p_inv','q','q_inv', optional 'qr_mat','qr_tau','qr_jpvt','dense_n',
-    'dense_rank') as a ctypes LhfdGpuLevel array.  Returns (array, keepalive)."""
+    'dense_rank') as a ctypes LhfdGpuLevel array (dtype=float32: LhfsGpuLevel, same field layout
+    with float value arrays).  Returns (array, keepalive)."""
     arr = (LhfdGpuLevel * len(levels))()
     keep = []
 
@@ -58,12 +64,12 @@ def make_level_structs(levels):
         nr, nc, cs, ri, va = block
         cs = np.ascontiguousarray(cs, dtype=np.int64)
         ri = np.ascontiguousarray(ri, dtype=np.int32)
-        va = np.ascontiguousarray(va, dtype=np.float64)
+        va = np.ascontiguousarray(va, dtype=dtype)
         keep.extend((cs, ri, va))
         return LhfdGpuCcs(nr, nc, _ptr(cs), _ptr(ri), _ptr(va))
 
     def vec(a, dt):
-        a = np.ascontiguousarray(a, dtype=dt)
+        a = np.ascontiguousarray(a, dtype=dtype if dt is np.float64 else dt)
         keep.append(a)
         return _ptr(a)
 
@@ -122,11 +128,22 @@ def lib():
             "lhfdGpuDebugBlockGraph": [vp, i, sz, sz, vp, vp, vp, vp],
             "lhfdGpuGetStats": [vp, vp],
             "lhfdGpuGetDepths": [vp, sz, vp],
+            "lhfsGpuAttachLevels": [i, sz, vp, vp],
+            "lhfsGpuDestroy": [vp],
+            "lhfsGpuSetMatrix": [vp, i, sz, vp, vp, vp],
+            "lhfsdGpuUpdate": [vp, i, sz, vp, vp, vp],
+            "lhfsGpuSolve": [vp, vp, vp],
+            "lhfsGpuApply": [vp, i, vp, i, vp, i, vp, vp],
+            "lhfsdGpuSolve": [vp, vp, vp],
+            "lhfsdGpuApply": [vp, i, vp, i, vp, i, vp, vp],
+            "lhfsGpuDebugSweepHost": [vp, i, vp, vp, vp, vp],
         }
         for name, argt in sig.items():
             f = getattr(L, name)
             f.argtypes = argt
             f.restype = C.c_int
+        L.lhfsGpuAsDouble.argtypes = [vp]
+        L.lhfsGpuAsDouble.restype = vp
         L.lhfGpuGetErrorMsg.restype = C.c_char_p
         L.lhfGpuVersion.restype = C.c_char_p
         _lib = L
@@ -138,7 +155,9 @@ EXPORTED_SYMBOLS = (
     "lhfdGpuSetStream", "lhfdGpuSynchronize", "lhfdGpuSolve", "lhfdGpuApply", "lhfdGpuSolveMrhs",
     "lhfdGpuFgmres", "lhfdGpuGmres", "lhfdGpuApplyDev", "lhfdGpuSolveDev", "lhfdGpuSolveMrhsDev", "lhfdGpuHifirDev",
     "lhfdGpuSpmvDev", "lhfdGpuProfileSolveDev", "lhfdGpuDebugSweepHost", "lhfdGpuDebugTraceSweep", "lhfdGpuDebugSimulateSweep", "lhfdGpuDebugBlockGraph",
-    "lhfdGpuGetStats", "lhfdGpuGetDepths", "lhfGpuGetErrorMsg", "lhfGpuVersion")
+    "lhfdGpuGetStats", "lhfdGpuGetDepths", "lhfGpuGetErrorMsg", "lhfGpuVersion",
+    "lhfsGpuAttachLevels", "lhfsGpuDestroy", "lhfsGpuAsDouble", "lhfsGpuSetMatrix", "lhfsdGpuUpdate", "lhfsGpuSolve",
+    "lhfsGpuApply", "lhfsdGpuSolve", "lhfsdGpuApply", "lhfsGpuDebugSweepHost")
 
 
 class LhfError(RuntimeError):
@@ -156,15 +175,17 @@ def debug_sweep_host(block, upper, rhs, diag=None):
     """Host-only hook (lhfdGpuDebugSweepHost): pack the triangular CCS block into device slabs
     and solve with them on the CPU.  Returns (x, stats dict)."""
     nr, nc, cs, ri, va = block
+    single = np.asarray(va).dtype == np.float32  # float block -> lhfsGpuDebugSweepHost (values stored as float)
     cs = np.ascontiguousarray(cs, dtype=np.int64)
     ri = np.ascontiguousarray(ri, dtype=np.int32)
-    va = np.ascontiguousarray(va, dtype=np.float64)
+    va = np.ascontiguousarray(va, dtype=np.float32 if single else np.float64)
     c = LhfdGpuCcs(nr, nc, _ptr(cs), _ptr(ri), _ptr(va))
     rhs = np.ascontiguousarray(rhs, dtype=np.float64)
     x = np.zeros_like(rhs)
     st = np.zeros(4, dtype=np.uint64)
     d = None if diag is None else np.ascontiguousarray(diag, dtype=np.float64)
-    _chk(lib().lhfdGpuDebugSweepHost(C.byref(c), int(upper), _ptr(rhs), _ptr(d) if d is not None else None,
+    f = lib().lhfsGpuDebugSweepHost if single else lib().lhfdGpuDebugSweepHost
+    _chk(f(C.byref(c), int(upper), _ptr(rhs), _ptr(d) if d is not None else None,
                                      _ptr(x), _ptr(st)))
     return x, dict(zip(("blocks", "halo", "bytes", "max_smem"), (int(v) for v in st)))
 
@@ -207,20 +228,29 @@ class GpuHif:
     Mirrors the libhifir calling pattern (lhfdCreate/Setup -> lhfdSolve/lhfdApply ->
     lhfdDestroy); every method is one C-ABI call."""
 
-    def __init__(self, levels=None, device=0, raw_handle=None):
+    def __init__(self, levels=None, device=0, raw_handle=None, single=False):
+        """levels with float32 factor values (or raw_handle + single=True: an LhfsGpuHdl) attach a
+        single-precision preconditioner: solve/apply then go through lhfsdGpu* (double vectors) and
+        solve_f32/apply_f32 through lhfsGpu* (float vectors); every other method reaches the handle
+        through lhfsGpuAsDouble."""
         self._h = None
+        self.single = bool(single)
         if raw_handle is not None:
             self._h = C.c_void_p(raw_handle)
         else:
-            arr, keep = make_level_structs(levels)
+            self.single = levels_dtype(levels) == np.float32
+            arr, keep = make_level_structs(levels, np.float32 if self.single else np.float64)
             h = C.c_void_p()
-            _chk(lib().lhfdGpuAttachLevels(device, len(levels), C.cast(arr, C.c_void_p), C.byref(h)))
+            f = lib().lhfsGpuAttachLevels if self.single else lib().lhfdGpuAttachLevels
+            _chk(f(device, len(levels), C.cast(arr, C.c_void_p), C.byref(h)))
             self._h = h
+        if self.single:
+            assert lib().lhfsGpuAsDouble(self._h) == self._h.value
         self.n = self.stats()["n"]
 
     def close(self):
         if self._h is not None and _lib is not None:
-            _lib.lhfdGpuDestroy(self._h)
+            (_lib.lhfsGpuDestroy if self.single else _lib.lhfdGpuDestroy)(self._h)
         self._h = None
 
     __del__ = close
@@ -247,7 +277,17 @@ class GpuHif:
         ip = np.ascontiguousarray(indptr, dtype=np.int64)
         ix = np.ascontiguousarray(indices, dtype=np.int32)
         va = np.ascontiguousarray(vals, dtype=np.float64)
-        _chk(lib().lhfdGpuSetMatrix(self._h, int(bool(rowmajor)), n, _ptr(ip), _ptr(ix), _ptr(va)))
+        f = lib().lhfsdGpuUpdate if self.single else lib().lhfdGpuSetMatrix
+        _chk(f(self._h, int(bool(rowmajor)), n, _ptr(ip), _ptr(ix), _ptr(va)))
+
+    def set_matrix_f32(self, A, rowmajor=True):
+        """lhfsGpuSetMatrix: a single-precision user matrix (widened at upload)"""
+        assert self.single
+        n, indptr, indices, vals = A
+        ip = np.ascontiguousarray(indptr, dtype=np.int64)
+        ix = np.ascontiguousarray(indices, dtype=np.int32)
+        va = np.ascontiguousarray(vals, dtype=np.float32)
+        _chk(lib().lhfsGpuSetMatrix(self._h, int(bool(rowmajor)), n, _ptr(ip), _ptr(ix), _ptr(va)))
 
     def set_nsp_const(self, start=0, end=FULL_RANK):
         _chk(lib().lhfdGpuSetNspConst(self._h, start, end))
@@ -269,16 +309,35 @@ class GpuHif:
     def solve(self, b, out=None):
         b = np.ascontiguousarray(b, dtype=np.float64)
         x = np.empty_like(b) if out is None else out
-        _chk(lib().lhfdGpuSolve(self._h, _ptr(b), _ptr(x)))
+        _chk((lib().lhfsdGpuSolve if self.single else lib().lhfdGpuSolve)(self._h, _ptr(b), _ptr(x)))
         return x
+
+    def solve_f32(self, b):
+        """lhfsGpuSolve: float vectors (single-precision handles only)"""
+        assert self.single
+        b = np.ascontiguousarray(b, dtype=np.float32)
+        x = np.empty_like(b)
+        _chk(lib().lhfsGpuSolve(self._h, _ptr(b), _ptr(x)))
+        return x
+
+    def apply_f32(self, b, op=LHF_S, nirs=1, betas=None, rank=LHF_DEFAULT_RANK):
+        """lhfsGpuApply: float vectors (single-precision handles only)"""
+        assert self.single
+        b = np.ascontiguousarray(b, dtype=np.float32)
+        x = np.empty_like(b)
+        bt = None if betas is None else np.asarray(betas, dtype=np.float64)
+        irs = np.zeros(2, dtype=np.int32)
+        _chk(lib().lhfsGpuApply(self._h, op, _ptr(b), nirs, _ptr(bt) if bt is not None else None, rank,
+                                _ptr(x), _ptr(irs)))
+        return x, (int(irs[0]), int(irs[1]))
 
     def apply(self, b, op=LHF_S, nirs=1, betas=None, rank=LHF_DEFAULT_RANK):
         b = np.ascontiguousarray(b, dtype=np.float64)
         x = np.empty_like(b)
         bt = None if betas is None else np.asarray(betas, dtype=np.float64)
         irs = np.zeros(2, dtype=np.int32)
-        _chk(lib().lhfdGpuApply(self._h, op, _ptr(b), nirs, _ptr(bt) if bt is not None else None, rank,
-                                _ptr(x), _ptr(irs)))
+        f = lib().lhfsdGpuApply if self.single else lib().lhfdGpuApply
+        _chk(f(self._h, op, _ptr(b), nirs, _ptr(bt) if bt is not None else None, rank, _ptr(x), _ptr(irs)))
         return x, (int(irs[0]), int(irs[1]))
 
     def solve_mrhs(self, B):

@@ -113,7 +113,7 @@ std::vector<double> form_q(std::size_t nm, const double *mat, const double *tau)
 
 }  // namespace
 
-Handle *attach_levels(int device, std::size_t nlevels, const LhfdGpuLevel *lv, bool dense_transposed) {
+Handle *attach_levels(int device, std::size_t nlevels, const LhfdGpuLevel *lv, bool dense_transposed, bool f32) {
   if (!nlevels || !lv) throw std::invalid_argument("empty preconditioner (no levels)");
   int ndev = 0;
   HIF_CUDA(cudaGetDeviceCount(&ndev));
@@ -122,11 +122,15 @@ Handle *attach_levels(int device, std::size_t nlevels, const LhfdGpuLevel *lv, b
 
   std::unique_ptr<Handle> h(new Handle());
   h->device = device;
+  h->f32    = f32;
   HIF_CUDA(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
   h->stream = h->own_stream;
   h->levels.resize(nlevels);
   std::size_t *tally = &h->device_bytes;
-  constexpr std::size_t sv = sizeof(double);
+  // sv = size of a factor value as the reference holds it (4 for hif::HIF<float>);
+  // the vectors of an apply are double here whatever the factor precision
+  const std::size_t     sv = f32 ? sizeof(float) : sizeof(double);
+  constexpr std::size_t sx = sizeof(double);
 
   for (std::size_t l = 0; l < nlevels; ++l) {
     const LhfdGpuLevel &P = lv[l];
@@ -170,6 +174,7 @@ Handle *attach_levels(int device, std::size_t nlevels, const LhfdGpuLevel *lv, b
     D.depthL = dag_depth(Lr, false);
     D.depthU = dag_depth(Ur, true);
 
+    D.L.f32 = D.U.f32 = f32;  // streamed sweep values in single precision (stream.cu)
     {
       HostCsr               ul;
       std::vector<unsigned> urows;
@@ -230,7 +235,7 @@ Handle *attach_levels(int device, std::size_t nlevels, const LhfdGpuLevel *lv, b
     const std::size_t nLU = D.L.nnz + D.U.nnz, nEF = D.E.nnz + D.F.nnz;
     h->bytes_factors += k * (nLU * (sv + 4) + 2 * (P.m + 1) * 4 + P.m * sv) + nEF * (sv + 4) + (P.n + 2) * 4 +
                         P.n * (2 * sv + 2 * 4);
-    h->bytes_vec += sv * (D.nm ? (7 * P.n + 8 * P.m) : 8 * P.n);
+    h->bytes_vec += sx * (D.nm ? (7 * P.n + 8 * P.m) : 8 * P.n);
     h->nnz_total += nLU + nEF + P.m;
   }
 
@@ -345,7 +350,7 @@ Handle *ensure_twin(Handle *h) {
       T.qr_jpvt    = reinterpret_cast<const LhfInt *>(h->dense.h_jpvt.data());
     }
   }
-  Handle *t  = attach_levels(h->device, nl, tl.data(), true);
+  Handle *t  = attach_levels(h->device, nl, tl.data(), true, h->f32);
   t->is_twin = true;
   h->twin    = t;
   h->device_bytes += t->device_bytes;

@@ -64,6 +64,140 @@ void d2h(Handle *h, double *dst, const double *src, std::size_t count) {
   HIF_CUDA(cudaMemcpyAsync(dst, src, count * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
 }
 
+// single-precision caller vectors (lhfsGpuSolve / lhfsGpuApply): half the PCIe bytes, widened /
+// narrowed on the device; the apply itself works on double vectors
+__global__ void widen_kernel(const float *__restrict__ in, double *__restrict__ out, std::size_t n) {
+  for (std::size_t i = blockIdx.x * static_cast<std::size_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<std::size_t>(gridDim.x) * blockDim.x)
+    out[i] = static_cast<double>(in[i]);
+}
+__global__ void narrow_kernel(const double *__restrict__ in, float *__restrict__ out, std::size_t n) {
+  for (std::size_t i = blockIdx.x * static_cast<std::size_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<std::size_t>(gridDim.x) * blockDim.x)
+    out[i] = static_cast<float>(in[i]);
+}
+unsigned cast_grid(std::size_t n) {
+  return static_cast<unsigned>(std::min<std::size_t>((n + 255) / 256, static_cast<std::size_t>(kNumSMs) * 8u));
+}
+void h2d(Handle *h, double *dst, const float *src, std::size_t count) {
+  if (h->io_f.n < count) h->io_f.alloc(count, &h->device_bytes);
+  HIF_CUDA(cudaMemcpyAsync(h->io_f.p, src, count * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+  if (count) widen_kernel<<<cast_grid(count), 256, 0, h->stream>>>(h->io_f.p, dst, count);
+  HIF_KERNEL_CHECK();
+  ++h->launch_count;
+}
+void d2h(Handle *h, float *dst, const double *src, std::size_t count) {
+  if (h->io_f.n < count) h->io_f.alloc(count, &h->device_bytes);
+  if (count) narrow_kernel<<<cast_grid(count), 256, 0, h->stream>>>(src, h->io_f.p, count);
+  HIF_KERNEL_CHECK();
+  ++h->launch_count;
+  HIF_CUDA(cudaMemcpyAsync(dst, h->io_f.p, count * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+}
+
+Handle *H(LhfsGpuHdl hdl) { return reinterpret_cast<Handle *>(hdl); }
+
+// lhf?Solve (libhifir.cpp:151-158): IO = the caller's vector type
+template <class IO>
+void solve_host(Handle *h, const IO *b, IO *x) {
+  HIF_CUDA(cudaSetDevice(h->device));
+  ensure_io(h, 1);
+  h2d(h, h->io_b.p, b, h->n0());
+  apply_dev(h, h->io_b.p, h->io_x.p, 0);  // lhfdSolve: M->solve(b, x), rank defaults to 0
+  d2h(h, x, h->io_x.p, h->n0());
+  check_sweep_error(h);
+}
+
+// lhf?Apply (libhifir.cpp:447-472; lhfsdApply :1192-1218): IO = the caller's vector type
+template <class IO>
+void apply_host(Handle *h0, LhfOperationType op, const IO *b, int nirs, const double *betas, int rank, IO *x,
+                int *ir_status) {
+  HIF_CUDA(cudaSetDevice(h0->device));
+  const bool trans = op == LHF_SH || op == LHF_MH;
+  Handle *   h     = h0;
+  if (trans) {  // the transposed twin serves S^H and M^H with the kernels of S and M
+    h         = ensure_twin(h0);
+    h->stream = h0->stream;
+  }
+  if (op == LHF_M || op == LHF_MH) {  // libhifir.cpp:458-459: mmultiply(b, x, trans), numerical rank
+    ensure_io(h0, 1);
+    h2d(h0, h0->io_b.p, b, h0->n0());
+    prod_dev(h, h0->io_b.p, h0->io_x.p, 0);
+    d2h(h0, x, h0->io_x.p, h0->n0());
+    check_sweep_error(h);
+    return;
+  }
+  if (trans && h0->nsp_on)
+    throw std::logic_error("the null-space filter of the transposed solve (nsp_tran) is not supported");
+  // rank defaulting rule, libhifir.cpp:451-455
+  const std::size_t rnk = rank == LHF_DEFAULT_RANK ? (nirs > 1 ? static_cast<std::size_t>(-1) : 0)
+                                                   : static_cast<std::size_t>(static_cast<long long>(rank));
+  ensure_io(h0, 1);
+  h2d(h0, h0->io_b.p, b, h0->n0());
+  if (h != h0) {
+    if (h->io_b.n < h0->n0()) {  // the twin works on the primary handle's staging buffers
+      h->io_b.release();
+      h->io_x.release();
+    }
+  }
+  double *io_b = h0->io_b.p, *io_x = h0->io_x.p;
+  if (nirs <= 1) {
+    apply_dev(h, io_b, io_x, 0);  // plain solve ignores `rank` (libhifir.cpp:461)
+  } else if (!betas) {
+    hifir_dev(h, io_b, static_cast<std::size_t>(nirs), io_x, rnk);
+  } else {
+    long iters = 0;
+    int  flag  = 0;
+    hifir_betas_dev(h, io_b, static_cast<std::size_t>(nirs), betas, io_x, rnk, &iters, &flag);
+    if (ir_status) {
+      ir_status[0] = static_cast<int>(iters);
+      ir_status[1] = flag;
+    }
+  }
+  d2h(h0, x, io_x, h0->n0());
+  check_sweep_error(h);
+}
+
+// widen the description of a single-precision preconditioner (hif::HIF<float>): integers verbatim,
+// values float -> double (exact).  The widened arrays live until attach_levels returns.
+struct WidenedLevels {
+  std::vector<LhfdGpuLevel>        lv;
+  std::vector<std::vector<double>> keep;
+  const double *widen(const float *p, std::size_t n) {
+    if (!p) return nullptr;
+    keep.emplace_back(p, p + n);
+    return keep.back().data();
+  }
+  LhfdGpuCcs widen(const LhfsGpuCcs &c) {
+    LhfdGpuCcs d;
+    d.nrows     = c.nrows;
+    d.ncols     = c.ncols;
+    d.col_start = c.col_start;
+    d.row_ind   = c.row_ind;
+    const LhfIndPtr nnz = (c.col_start && c.ncols) ? c.col_start[c.ncols] : 0;
+    if (nnz < 0) throw std::invalid_argument("negative nonzero count in a factor block");
+    if (nnz && !c.vals) throw std::invalid_argument("null value array in a factor block");
+    d.vals = widen(c.vals, static_cast<std::size_t>(nnz));
+    return d;
+  }
+  WidenedLevels(std::size_t nlevels, const LhfsGpuLevel *s) : lv(nlevels) {
+    keep.reserve(12 * nlevels);
+    for (std::size_t l = 0; l < nlevels; ++l) {
+      const LhfsGpuLevel &S = s[l];
+      LhfdGpuLevel &      D = lv[l];
+      std::memset(&D, 0, sizeof(D));
+      D.m = S.m, D.n = S.n;
+      D.L_B = widen(S.L_B), D.U_B = widen(S.U_B), D.E = widen(S.E), D.F = widen(S.F);
+      D.d_B = widen(S.d_B, S.m), D.s = widen(S.s, S.n), D.t = widen(S.t, S.n);
+      D.p = S.p, D.p_inv = S.p_inv, D.q = S.q, D.q_inv = S.q_inv;
+      D.dense_n = S.dense_n, D.dense_rank = S.dense_rank;
+      D.qr_mat  = widen(S.qr_mat, S.dense_n * S.dense_n);
+      D.qr_tau  = widen(S.qr_tau, S.dense_n);
+      D.qr_jpvt = S.qr_jpvt;
+      D.has_symm_dense = S.has_symm_dense;
+    }
+  }
+};
+
 }  // namespace
 
 extern "C" {
@@ -163,15 +297,7 @@ LhfStatus lhfdGpuSolve(LhfdGpuHdl hdl, const double *b, double *x) {
   REQUIRE_HANDLE(hdl);
   REQUIRE_PTR(b, "b");
   REQUIRE_PTR(x, "x");
-  return guarded([&] {
-    Handle *h = H(hdl);
-    HIF_CUDA(cudaSetDevice(h->device));
-    ensure_io(h, 1);
-    h2d(h, h->io_b.p, b, h->n0());
-    apply_dev(h, h->io_b.p, h->io_x.p, 0);  // lhfdSolve: M->solve(b, x), rank defaults to 0
-    d2h(h, x, h->io_x.p, h->n0());
-    check_sweep_error(h);
-  });
+  return guarded([&] { solve_host(H(hdl), b, x); });
 }
 
 LhfStatus lhfdGpuSolveMrhs(LhfdGpuHdl hdl, size_t nrhs, const double *B, double *X) {
@@ -201,53 +327,85 @@ LhfStatus lhfdGpuApply(LhfdGpuHdl hdl, LhfOperationType op, const double *b, int
     g_msg = "unknown LhfOperationType";
     return LHF_BAD_PREC;
   }
+  return guarded([&] { apply_host(H(hdl), op, b, nirs, betas, rank, x, ir_status); });
+}
+
+// ---- single-precision factors (hif::HIF<float>): lhfs* and the mixed lhfsd* of libhifir ----
+
+LhfStatus lhfsGpuAttachLevels(int device, size_t nlevels, const LhfsGpuLevel *levels, LhfsGpuHdl *out) {
+  REQUIRE_PTR(out, "out");
+  *out = nullptr;
+  REQUIRE_PTR(levels, "levels");
   return guarded([&] {
-    Handle *h0 = H(hdl);
-    HIF_CUDA(cudaSetDevice(h0->device));
-    const bool trans = op == LHF_SH || op == LHF_MH;
-    Handle *   h     = h0;
-    if (trans) {  // the transposed twin serves S^H and M^H with the kernels of S and M
-      h         = ensure_twin(h0);
-      h->stream = h0->stream;
-    }
-    if (op == LHF_M || op == LHF_MH) {  // libhifir.cpp:458-459: mmultiply(b, x, trans), numerical rank
-      ensure_io(h0, 1);
-      h2d(h0, h0->io_b.p, b, h0->n0());
-      prod_dev(h, h0->io_b.p, h0->io_x.p, 0);
-      d2h(h0, x, h0->io_x.p, h0->n0());
-      check_sweep_error(h);
-      return;
-    }
-    if (trans && h0->nsp_on)
-      throw std::logic_error("the null-space filter of the transposed solve (nsp_tran) is not supported");
-    // rank defaulting rule, libhifir.cpp:451-455
-    const std::size_t rnk = rank == LHF_DEFAULT_RANK ? (nirs > 1 ? static_cast<std::size_t>(-1) : 0)
-                                                     : static_cast<std::size_t>(static_cast<long long>(rank));
-    ensure_io(h0, 1);
-    h2d(h0, h0->io_b.p, b, h0->n0());
-    if (h != h0) {
-      if (h->io_b.n < h0->n0()) {  // the twin works on the primary handle's staging buffers
-        h->io_b.release();
-        h->io_x.release();
-      }
-    }
-    double *io_b = h0->io_b.p, *io_x = h0->io_x.p;
-    if (nirs <= 1) {
-      apply_dev(h, io_b, io_x, 0);  // plain solve ignores `rank` (libhifir.cpp:461)
-    } else if (!betas) {
-      hifir_dev(h, io_b, static_cast<std::size_t>(nirs), io_x, rnk);
-    } else {
-      long iters = 0;
-      int  flag  = 0;
-      hifir_betas_dev(h, io_b, static_cast<std::size_t>(nirs), betas, io_x, rnk, &iters, &flag);
-      if (ir_status) {
-        ir_status[0] = static_cast<int>(iters);
-        ir_status[1] = flag;
-      }
-    }
-    d2h(h0, x, io_x, h0->n0());
-    check_sweep_error(h);
+    if (!nlevels) throw std::invalid_argument("empty preconditioner (no levels)");
+    WidenedLevels W(nlevels, levels);
+    *out = reinterpret_cast<LhfsGpuHdl>(attach_levels(device, nlevels, W.lv.data(), false, true));
   });
+}
+
+LhfStatus lhfsGpuDestroy(LhfsGpuHdl hdl) {
+  REQUIRE_HANDLE(hdl);
+  return guarded([&] { destroy_handle(H(hdl)); });
+}
+
+LhfdGpuHdl lhfsGpuAsDouble(LhfsGpuHdl hdl) { return reinterpret_cast<LhfdGpuHdl>(hdl); }
+
+LhfStatus lhfsGpuSetMatrix(LhfsGpuHdl hdl, int is_rowmajor, size_t n, const LhfIndPtr *indptr, const LhfInt *indices,
+                           const float *vals) {
+  REQUIRE_HANDLE(hdl);
+  REQUIRE_PTR(indptr, "indptr");
+  return guarded([&] {
+    const LhfIndPtr nnz = indptr[n];
+    if (nnz < 0) throw std::invalid_argument("A: negative nonzero count");
+    if (nnz && !vals) throw std::invalid_argument("A: null value array");
+    std::vector<double> v(vals, vals + nnz);
+    set_matrix(H(hdl), is_rowmajor != 0, n, indptr, indices, v.data());
+  });
+}
+
+LhfStatus lhfsdGpuUpdate(LhfsGpuHdl hdl, int is_rowmajor, size_t n, const LhfIndPtr *indptr, const LhfInt *indices,
+                         const double *vals) {
+  REQUIRE_HANDLE(hdl);
+  REQUIRE_PTR(indptr, "indptr");
+  return guarded([&] { set_matrix(H(hdl), is_rowmajor != 0, n, indptr, indices, vals); });
+}
+
+LhfStatus lhfsGpuSolve(LhfsGpuHdl hdl, const float *b, float *x) {
+  REQUIRE_HANDLE(hdl);
+  REQUIRE_PTR(b, "b");
+  REQUIRE_PTR(x, "x");
+  return guarded([&] { solve_host(H(hdl), b, x); });
+}
+
+LhfStatus lhfsdGpuSolve(LhfsGpuHdl hdl, const double *b, double *x) {
+  REQUIRE_HANDLE(hdl);
+  REQUIRE_PTR(b, "b");
+  REQUIRE_PTR(x, "x");
+  return guarded([&] { solve_host(H(hdl), b, x); });
+}
+
+#define REQUIRE_OP(op)                                                  \
+  if (op != LHF_S && op != LHF_SH && op != LHF_M && op != LHF_MH) {   \
+    g_msg = "unknown LhfOperationType";                                 \
+    return LHF_BAD_PREC;                                                \
+  }
+
+LhfStatus lhfsGpuApply(LhfsGpuHdl hdl, LhfOperationType op, const float *b, int nirs, const double *betas, int rank,
+                       float *x, int *ir_status) {
+  REQUIRE_HANDLE(hdl);
+  REQUIRE_PTR(b, "b");
+  REQUIRE_PTR(x, "x");
+  REQUIRE_OP(op);
+  return guarded([&] { apply_host(H(hdl), op, b, nirs, betas, rank, x, ir_status); });
+}
+
+LhfStatus lhfsdGpuApply(LhfsGpuHdl hdl, LhfOperationType op, const double *b, int nirs, const double *betas, int rank,
+                        double *x, int *ir_status) {
+  REQUIRE_HANDLE(hdl);
+  REQUIRE_PTR(b, "b");
+  REQUIRE_PTR(x, "x");
+  REQUIRE_OP(op);
+  return guarded([&] { apply_host(H(hdl), op, b, nirs, betas, rank, x, ir_status); });
 }
 
 // device-pointer form of lhfdGpuApply without residual bounds
@@ -356,6 +514,26 @@ LhfStatus lhfdGpuDebugSweepHost(const LhfdGpuCcs *T, int upper, const double *rh
     R.nrows = R.ncols = T->ncols;
     R.ptr.resize(T->ncols + 1, R.ptr.empty() ? 0u : R.ptr.back());
     sweep_host_emulate(R, upper != 0, rhs, diag, x, stats);
+  });
+}
+
+// single-precision factor block: widened, merged and packed as at attach, packed values rounded to
+// float (what the device streams), emulated on the host in double
+LhfStatus lhfsGpuDebugSweepHost(const LhfsGpuCcs *T, int upper, const double *rhs, const double *diag, double *x,
+                                size_t stats[4]) {
+  REQUIRE_PTR(T, "T");
+  REQUIRE_PTR(rhs, "rhs");
+  REQUIRE_PTR(x, "x");
+  REQUIRE_PTR(stats, "stats");
+  return guarded([&] {
+    if (upper && !diag) throw std::invalid_argument("upper sweep needs the diagonal");
+    const LhfIndPtr     nnz = (T->col_start && T->ncols) ? T->col_start[T->ncols] : 0;
+    std::vector<double> wide(T->vals, T->vals + (nnz > 0 ? nnz : 0));
+    const LhfdGpuCcs    Td{T->nrows, T->ncols, T->col_start, T->row_ind, wide.data()};
+    HostCsr             R = ccs_to_csr(Td, "T");
+    R.nrows = R.ncols = T->ncols;
+    R.ptr.resize(T->ncols + 1, R.ptr.empty() ? 0u : R.ptr.back());
+    sweep_host_emulate(R, upper != 0, rhs, diag, x, stats, true);
   });
 }
 

@@ -114,6 +114,8 @@ struct SweepPlan {
   DevBuf<unsigned>            st_codes;  // 32 row codes per slice
   DevBuf<unsigned>            st_cols;   // solution slot of every entry, slice-interleaved
   DevBuf<double>              st_vals;
+  bool                        f32 = false;  // factor values stored in single precision (st_vals32 instead of st_vals)
+  DevBuf<float>               st_vals32;
   std::size_t            slab_bytes = 0, halo_total = 0, nnz = 0;
   DevBuf<unsigned char>  slabs;  // packed slabs
   DevBuf<unsigned char>  info;   // SlabInfo[nblocks]
@@ -190,6 +192,8 @@ struct Handle {
   unsigned              epoch_p = 0;      // same for the product's LDU solve
   Handle *              twin = nullptr;   // transposed preconditioner (built on first LHF_SH / LHF_MH)
   bool                  is_twin = false, prod_ready = false;
+  bool                  f32 = false;      // attached to single-precision factors (lhfsGpuAttachLevels): the
+                                          // streamed sweep values are stored as float, arithmetic stays double
   // host copy of the user matrix (for the twin's A^T)
   std::vector<LhfIndPtr> hA_ptr;
   std::vector<LhfInt>    hA_idx;
@@ -204,6 +208,7 @@ struct Handle {
   int *                 h_error = nullptr;  // pinned mirror
   // scratch for host-buffer entry points / IR / Krylov
   DevBuf<double> io_b, io_x;
+  DevBuf<float>  io_f;  // staging of single-precision caller vectors (lhfsGpuSolve / lhfsGpuApply)
   std::size_t    io_cols = 0;
   DevBuf<double> ir_xk, ir_r, ir_t;
   DevBuf<double> kr_v, kr_w, kr_Q, kr_Z, kr_scal, kr_part;
@@ -224,7 +229,8 @@ struct Handle {
 };
 
 // ---- attach.cu
-Handle *attach_levels(int device, std::size_t nlevels, const LhfdGpuLevel *levels, bool dense_transposed = false);
+Handle *attach_levels(int device, std::size_t nlevels, const LhfdGpuLevel *levels, bool dense_transposed = false,
+                      bool f32 = false);
 Handle *ensure_twin(Handle *h);   // transposed preconditioner sharing the stream of h
 void    destroy_handle(Handle *h);
 void    set_matrix(Handle *h, bool rowmajor, std::size_t n, const LhfIndPtr *indptr, const LhfInt *indices,
@@ -234,7 +240,7 @@ HostCsr ccs_to_csr(const LhfdGpuCcs &c, const char *name);
 // ---- sptrsv.cu : block sync-free triangular sweeps
 void build_sweep_plan(const HostCsr &T, bool upper, SweepPlan &plan, std::size_t *tally, unsigned nr = 1);
 void sweep_host_emulate(const HostCsr &T, bool upper, const double *rhs, const double *diag, double *x,
-                        std::size_t stats[4]);
+                        std::size_t stats[4], bool f32 = false);
 void sweep_block_graph(const HostCsr &T, bool upper, std::vector<unsigned> &info, std::vector<unsigned> &src_ptr,
                        std::vector<unsigned> &src_idx);
 void build_split_plans(const HostCsr &T, SweepPlan &plan_lo, SweepPlan &plan_up, HostCsr &ul,
@@ -243,7 +249,7 @@ void sweep_simulate(const HostCsr &T, bool upper, const double *prm, double *out
 bool stream_sweeps();  // HIFIR_B200_SWEEP=stream (default) | slab
 void build_stream_plan(const HostCsr &S, bool upper, SweepPlan &plan, std::size_t *tally);
 void stream_host_emulate(const HostCsr &S, bool upper, const double *rhs, const double *diag, double *x,
-                         std::size_t stats[4]);
+                         std::size_t stats[4], bool f32 = false);
 void launch_stream_sweep(Handle *h, const SweepPlan &plan, const double *rhs_plain,
                          const unsigned long long *rhs_tagged, const double *diag, unsigned long long *x,
                          unsigned parity, int *ticket, unsigned long long *trace = nullptr, unsigned nr = 1);

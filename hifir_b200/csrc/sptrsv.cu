@@ -792,7 +792,7 @@ static void pack_sweep(const HostCsr &T, bool upper, PackedSweep &out, unsigned 
 // CPU emulation of the slab sweep (same packed data, same per-row update order, blocks in
 // ticket order) -- lets the host-side packing be tested without a GPU (tests/test_abi.py).
 void sweep_host_emulate(const HostCsr &T, bool upper, const double *rhs, const double *diag, double *x,
-                        std::size_t stats[4]) {
+                        std::size_t stats[4], bool f32) {
   PackedSweep       P;
   HostCsr           S  = to_sweep_form(T, upper);
   const MergeParams mp = MergeParams::from_env();
@@ -801,7 +801,7 @@ void sweep_host_emulate(const HostCsr &T, bool upper, const double *rhs, const d
   const unsigned      m = static_cast<unsigned>(T.nrows);
   std::vector<double> xs, xg(2 * static_cast<std::size_t>(m), 0.0);
   if (stream_sweeps()) {
-    stream_host_emulate(S, upper, rhs, diag, xg.data(), stats);
+    stream_host_emulate(S, upper, rhs, diag, xg.data(), stats, f32);
     std::copy(xg.begin(), xg.begin() + m, x);
     return;
   }

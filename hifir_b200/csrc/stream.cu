@@ -44,6 +44,13 @@ __device__ __forceinline__ double ld_stream_f64(const double *p) {
   asm volatile("ld.global.cs.f64 %0, [%1];" : "=d"(v) : "l"(p));
   return v;
 }
+__device__ __forceinline__ float ld_stream_f32(const float *p) {
+  float v;
+  asm volatile("ld.global.cs.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ double ld_stream_val(const double *p) { return ld_stream_f64(p); }
+__device__ __forceinline__ float  ld_stream_val(const float *p) { return ld_stream_f32(p); }
 __device__ __forceinline__ int ld_poll_i32(const int *p) {
   int v;
   asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -83,11 +90,15 @@ __device__ __forceinline__ void st_publish_v2(unsigned long long *p, unsigned lo
 // kU entries per lane are held in registers; their gathers go out kG at a time.  Measured at
 // 128^3 (ms per apply): kU = 4 / 5 CTAs per SM 1.58, kU = 8 / kG = 4 / 4 CTAs 1.37 (the optimum:
 // 2, 3, 5, 6 CTAs per SM, kU = 16 and shared-memory staging of the entries are all slower).
-template <bool UPPER, int kU, int NR, bool kTrace>
+//
+// VT = storage type of the factor values: double, or float for the factors of a single-precision
+// hif::HIF<float> (lhfsGpu* / lhfsdGpu* entry points) -- 8 instead of 12 bytes per streamed entry;
+// the arithmetic and the solution stay in double whatever VT.
+template <bool UPPER, int kU, int NR, bool kTrace, class VT>
 __global__ void __launch_bounds__(kStreamWarps * 32, NR > 1 ? 2 : (kU == 4 ? 5 : 4))
     sweep_stream_kernel(const unsigned nchunks, const uint4 *__restrict__ sdesc, const unsigned *__restrict__ lvl_need,
                         const unsigned *__restrict__ codes, const unsigned *__restrict__ cols,
-                        const double *__restrict__ vals, const unsigned m, const double *__restrict__ rhs_plain,
+                        const VT *__restrict__ vals, const unsigned m, const double *__restrict__ rhs_plain,
                         const unsigned long long *rhs_tagged, const double *__restrict__ diag, unsigned long long *x,
                         const unsigned parity, int *sync, int *error_flag, const unsigned window,
                         const unsigned adm_sleep, const int publish_st, unsigned long long *trace_buf) {
@@ -120,13 +131,13 @@ __global__ void __launch_bounds__(kStreamWarps * 32, NR > 1 ? 2 : (kU == 4 ? 5 :
     const unsigned    len  = sd.y;
     // ---- everything that does not depend on other rows: factor entries, right-hand side
     unsigned cc[kU];
-    double   vv[kU];
+    VT       vv[kU];
 #pragma unroll
     for (int u = 0; u < kU; ++u) {
       cc[u] = kPadCol;
       if (static_cast<unsigned>(u) < len) {
         cc[u] = ld_stream_u32(cols + base + static_cast<std::size_t>(u) * 32u);
-        vv[u] = ld_stream_f64(vals + base + static_cast<std::size_t>(u) * 32u);
+        vv[u] = ld_stream_val(vals + base + static_cast<std::size_t>(u) * 32u);
       }
     }
     double acc[NR];
@@ -245,7 +256,7 @@ __global__ void __launch_bounds__(kStreamWarps * 32, NR > 1 ? 2 : (kU == 4 ? 5 :
         for (int j = 0; j < kG; ++j)
           if (cc[u0 + j] != kPadCol) {
 #pragma unroll
-            for (int q = 0; q < NR; ++q) acc[q] = fma(-vv[u0 + j], tag_value(g[j][q]), acc[q]);
+            for (int q = 0; q < NR; ++q) acc[q] = fma(-static_cast<double>(vv[u0 + j]), tag_value(g[j][q]), acc[q]);
           }
       }
       k += kU;
@@ -255,7 +266,7 @@ __global__ void __launch_bounds__(kStreamWarps * 32, NR > 1 ? 2 : (kU == 4 ? 5 :
         cc[u] = kPadCol;
         if (k + u < len) {
           cc[u] = ld_stream_u32(cols + base + static_cast<std::size_t>(k + u) * 32u);
-          vv[u] = ld_stream_f64(vals + base + static_cast<std::size_t>(k + u) * 32u);
+          vv[u] = ld_stream_val(vals + base + static_cast<std::size_t>(k + u) * 32u);
         }
       }
     }
@@ -421,7 +432,7 @@ void build_stream_plan(const HostCsr &S, bool upper, SweepPlan &plan, std::size_
   plan.st_u = stream_unroll();
   pack_stream(S, H, plan.st_u);
   plan.nblocks    = static_cast<unsigned>(H.sdesc.size());  // slices
-  plan.slab_bytes = H.cols.size() * 12u + H.codes.size() * 4u + H.sdesc.size() * 16u;
+  plan.slab_bytes = H.cols.size() * (plan.f32 ? 8u : 12u) + H.codes.size() * 4u + H.sdesc.size() * 16u;
   plan.st_depth   = H.depth;
   plan.st_padded  = H.padded;
   plan.st_chunks  = static_cast<unsigned>(H.sdesc.size() / kStreamWarps);
@@ -429,16 +440,23 @@ void build_stream_plan(const HostCsr &S, bool upper, SweepPlan &plan, std::size_
   plan.st_sdesc.upload(reinterpret_cast<const unsigned *>(H.sdesc.data()), H.sdesc.size() * 4u, tally);
   plan.st_codes.upload(H.codes, tally);
   plan.st_cols.upload(H.cols, tally);
-  plan.st_vals.upload(H.vals, tally);
+  if (plan.f32) {  // single-precision factors: the merged values are rounded to float once, here
+    std::vector<float> v32(H.vals.begin(), H.vals.end());
+    plan.st_vals32.upload(v32, tally);
+  } else {
+    plan.st_vals.upload(H.vals, tally);
+  }
 }
 
 // CPU emulation of the streaming sweep on the packed data (slices in ticket order, rows of a
 // slice one after the other): lets tests check merge + packing without a GPU.  `x` has
 // 2 * orig_rows slots.  stats = {slices, padded entries, bytes, depth}
 void stream_host_emulate(const HostCsr &S, bool upper, const double *rhs, const double *diag, double *x,
-                         std::size_t stats[4]) {
+                         std::size_t stats[4], bool f32) {
   StreamHost H;
   pack_stream(S, H, stream_unroll());
+  if (f32)  // single-precision factors: the packed values are rounded to float (build_stream_plan)
+    for (double &v : H.vals) v = static_cast<double>(static_cast<float>(v));
   const unsigned m = static_cast<unsigned>(S.orig_rows);
   for (std::size_t s = 0; s < H.sdesc.size(); ++s) {
     const uint4 sd = H.sdesc[s];
@@ -474,12 +492,13 @@ int stream_env(const char *name, int dflt) {
   const char *e = std::getenv(name);
   return e ? std::atoi(e) : dflt;
 }
-template <bool UPPER, int kU, int NR>
-void launch_stream_T(Handle *h, const SweepPlan &plan, const double *rhs_plain, const unsigned long long *rhs_tagged,
-                     const double *diag, unsigned long long *x, unsigned parity, int *sync, unsigned long long *trace) {
+template <bool UPPER, int kU, int NR, class VT>
+void launch_stream_V(Handle *h, const SweepPlan &plan, const VT *vals, const double *rhs_plain,
+                     const unsigned long long *rhs_tagged, const double *diag, unsigned long long *x, unsigned parity,
+                     int *sync, unsigned long long *trace) {
   static int ctas_per_sm = 0;
   if (!ctas_per_sm) {
-    HIF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, sweep_stream_kernel<UPPER, kU, NR, false>,
+    HIF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, sweep_stream_kernel<UPPER, kU, NR, false, VT>,
                                                            static_cast<int>(kStreamWarps * 32), 0));
     if (ctas_per_sm < 1) ctas_per_sm = 1;
   }
@@ -489,13 +508,21 @@ void launch_stream_T(Handle *h, const SweepPlan &plan, const double *rhs_plain, 
   const unsigned grid   = std::min<unsigned>(plan.st_chunks + 1u, static_cast<unsigned>(kNumSMs * ctas_per_sm));
   const uint4 *  sdesc  = reinterpret_cast<const uint4 *>(plan.st_sdesc.p);
   if (trace)
-    sweep_stream_kernel<UPPER, kU, NR, true><<<grid, kStreamWarps * 32, 0, h->stream>>>(
-        plan.st_chunks, sdesc, plan.st_need.p, plan.st_codes.p, plan.st_cols.p, plan.st_vals.p, plan.m, rhs_plain,
-        rhs_tagged, diag, x, parity, sync, h->error_flag.p, window, sleep, pub_st, trace);
+    sweep_stream_kernel<UPPER, kU, NR, true, VT><<<grid, kStreamWarps * 32, 0, h->stream>>>(
+        plan.st_chunks, sdesc, plan.st_need.p, plan.st_codes.p, plan.st_cols.p, vals, plan.m, rhs_plain, rhs_tagged,
+        diag, x, parity, sync, h->error_flag.p, window, sleep, pub_st, trace);
   else
-    sweep_stream_kernel<UPPER, kU, NR, false><<<grid, kStreamWarps * 32, 0, h->stream>>>(
-        plan.st_chunks, sdesc, plan.st_need.p, plan.st_codes.p, plan.st_cols.p, plan.st_vals.p, plan.m, rhs_plain,
-        rhs_tagged, diag, x, parity, sync, h->error_flag.p, window, sleep, pub_st, nullptr);
+    sweep_stream_kernel<UPPER, kU, NR, false, VT><<<grid, kStreamWarps * 32, 0, h->stream>>>(
+        plan.st_chunks, sdesc, plan.st_need.p, plan.st_codes.p, plan.st_cols.p, vals, plan.m, rhs_plain, rhs_tagged,
+        diag, x, parity, sync, h->error_flag.p, window, sleep, pub_st, nullptr);
+}
+template <bool UPPER, int kU, int NR>
+void launch_stream_T(Handle *h, const SweepPlan &plan, const double *rhs_plain, const unsigned long long *rhs_tagged,
+                     const double *diag, unsigned long long *x, unsigned parity, int *sync, unsigned long long *trace) {
+  if (plan.f32)
+    launch_stream_V<UPPER, kU, NR, float>(h, plan, plan.st_vals32.p, rhs_plain, rhs_tagged, diag, x, parity, sync, trace);
+  else
+    launch_stream_V<UPPER, kU, NR, double>(h, plan, plan.st_vals.p, rhs_plain, rhs_tagged, diag, x, parity, sync, trace);
 }
 template <bool UPPER>
 void launch_stream_U(Handle *h, const SweepPlan &plan, const double *rhs_plain, const unsigned long long *rhs_tagged,

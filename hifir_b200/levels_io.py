@@ -22,7 +22,7 @@ def levels_to_arrays(levels, prefix=""):
             out[pre + b + "_shape"] = np.array([nr, nc], dtype=np.int64)
             out[pre + b + "_cs"] = np.asarray(cs, dtype=np.int64)
             out[pre + b + "_ri"] = np.asarray(ri, dtype=np.int32)
-            out[pre + b + "_va"] = np.asarray(va, dtype=np.float64)
+            out[pre + b + "_va"] = np.asarray(va)  # float64, or float32 for hif::HIF<float> factors
         for v in _VECS:
             out[pre + v] = np.asarray(L[v])
         if L.get("dense_n", 0):

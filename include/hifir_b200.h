@@ -157,6 +157,65 @@ LhfStatus lhfdGpuFgmres(LhfdGpuHdl hdl, const double *b, int restart, double rto
 LhfStatus lhfdGpuGmres(LhfdGpuHdl hdl, const double *b, int restart, double rtol, int maxit,
                        double *x, int *flag, int *iters);
 
+/* ---- single-precision factors: hif::HIF<float> (libhifir's lhfs* family, libhifir.h:775-872)
+ * and the mixed-precision lhfsd* family (float factors, double vectors; libhifir.h:1231-1280,
+ * libhifir.cpp:1192-1229, examples/intermediate/demo_mixedprecision.cpp) ------------------------
+ *
+ * The level description is LhfdGpuLevel with float value arrays.  On the device the values of
+ * the triangular sweeps -- the bulk of an apply's traffic -- are STORED in single precision
+ * (8 instead of 12 bytes per streamed entry); every accumulation and every vector of the apply
+ * is double, i.e. at least as accurate as the reference's float work vector (builder.hpp:125-131,
+ * prec_solve.hpp:341-342).  Parity gate against the reference's single-precision apply: relative
+ * 1e-5 (BASELINE.json north_star). */
+typedef struct LhfsGpu *LhfsGpuHdl;
+
+typedef struct LhfsGpuCcs { /* hif::CCS<float,int> */
+  size_t           nrows, ncols;
+  const LhfIndPtr *col_start;
+  const LhfInt *   row_ind;
+  const float *    vals;
+} LhfsGpuCcs;
+
+typedef struct LhfsGpuLevel { /* hif::Prec<float,int,ptrdiff_t>; fields as LhfdGpuLevel */
+  size_t        m, n;
+  LhfsGpuCcs    L_B;
+  const float * d_B;
+  LhfsGpuCcs    U_B, E, F;
+  const float * s, *t;
+  const LhfInt *p, *p_inv, *q, *q_inv;
+  size_t        dense_n, dense_rank;
+  const float * qr_mat, *qr_tau; /* hif::QRCP<float>: _mat, _tau */
+  const LhfInt *qr_jpvt;
+  int           has_symm_dense;
+} LhfsGpuLevel;
+
+LhfStatus lhfsGpuAttachLevels(int device, size_t nlevels, const LhfsGpuLevel *levels, LhfsGpuHdl *out);
+LhfStatus lhfsGpuDestroy(LhfsGpuHdl hdl); /* cf. lhfsDestroy, libhifir.h:775 */
+
+/* The same handle viewed as an LhfdGpuHdl: every lhfdGpu* entry point that takes DOUBLE vectors
+ * (SolveDev, ApplyDev, SolveMrhs, Fgmres, SetNspConst, SetStream, GetStats, ...) serves a
+ * single-precision preconditioner through it.  Destroy with either lhfsGpuDestroy or
+ * lhfdGpuDestroy, once. */
+LhfdGpuHdl lhfsGpuAsDouble(LhfsGpuHdl hdl);
+
+/* user matrix for refinement: single precision (lhfsSetup/lhfsUpdate, libhifir.h:790-800; widened at
+ * upload) or double (lhfsdUpdate, libhifir.h:1231 -- the mixed-precision refinement computes its
+ * residuals with the double matrix) */
+LhfStatus lhfsGpuSetMatrix(LhfsGpuHdl hdl, int is_rowmajor, size_t n, const LhfIndPtr *indptr,
+                           const LhfInt *indices, const float *vals);
+LhfStatus lhfsdGpuUpdate(LhfsGpuHdl hdl, int is_rowmajor, size_t n, const LhfIndPtr *indptr,
+                         const LhfInt *indices, const double *vals);
+
+/* drop-ins for lhfsSolve / lhfsApply (libhifir.h:841-854): float vectors (widened / narrowed on
+ * the device) and for lhfsdSolve / lhfsdApply (libhifir.h:1267-1280): double vectors.  Same op /
+ * nirs / betas / rank / ir_status semantics as lhfdGpuApply. */
+LhfStatus lhfsGpuSolve(LhfsGpuHdl hdl, const float *b, float *x);
+LhfStatus lhfsGpuApply(LhfsGpuHdl hdl, LhfOperationType op, const float *b, int nirs, const double *betas,
+                       int rank, float *x, int *ir_status);
+LhfStatus lhfsdGpuSolve(LhfsGpuHdl hdl, const double *b, double *x);
+LhfStatus lhfsdGpuApply(LhfsGpuHdl hdl, LhfOperationType op, const double *b, int nirs, const double *betas,
+                        int rank, double *x, int *ir_status);
+
 /* ---- the hot path, DEVICE buffers (asynchronous on the handle's stream) ---- */
 
 /* lhfdGpuApply on device buffers (no residual bounds): op in {LHF_S, LHF_SH, LHF_M, LHF_MH} */
@@ -210,6 +269,11 @@ LhfStatus lhfdGpuProfileSolveDev(LhfdGpuHdl hdl, const double *d_b, double *d_x,
  * (upper).  stats = {blocks, halo entries, packed bytes, max shared bytes per block}.
  * Lets the host-side packing logic be checked bit-for-bit in the CPU test suite. */
 LhfStatus lhfdGpuDebugSweepHost(const LhfdGpuCcs *T, int upper, const double *rhs, const double *diag,
+                                double *x, size_t stats[4]);
+
+/* The same for a single-precision factor block on the streaming layout: the packed (merged) values
+ * are rounded to float exactly as lhfsGpuAttachLevels stores them; rhs / diag / x are double. */
+LhfStatus lhfsGpuDebugSweepHost(const LhfsGpuCcs *T, int upper, const double *rhs, const double *diag,
                                 double *x, size_t stats[4]);
 
 /* Debug: run one apply with per-block tracing of one triangular sweep switched on

@@ -12,6 +12,13 @@
 // (alg/Prec.hpp:309-323) with plain pointers in LhfdGpuLevel and calls the C-ABI
 // lhfdGpuAttachLevels.  Nothing of the host object is modified or copied here.
 //
+// A single-precision preconditioner (hif::HIF<float, int>, the mixed-precision set-up of
+// examples/intermediate/demo_mixedprecision.cpp) attaches the same way:
+//
+//     hif::HIF<float, int> Ms;  Ms.factorize(A);                // A in double
+//     LhfsGpuHdl Gs;  hifir_b200::attach(Ms, 0, &Gs);
+//     lhfsdGpuSolve(Gs, b, x);                                   // = Ms.solve(b, x), b/x double
+//
 // The QRCP members _tau/_jpvt are protected with no getter (QRCP.hpp:544-555);
 // they are read through a derived accessor type, the same device the reference
 // itself uses for its own internals (utils/common.hpp:268-290).
@@ -30,6 +37,23 @@ namespace hifir_b200 {
 /// time (dlopen / ctypes) instead of linking against it
 struct AttachApi {
   LhfStatus (*attach_levels)(int, std::size_t, const LhfdGpuLevel *, LhfdGpuHdl *);
+  LhfStatus (*attach_levels_s)(int, std::size_t, const LhfsGpuLevel *, LhfsGpuHdl *);  // may be null
+};
+
+/// the C-ABI types that describe factors of value type V
+template <class V>
+struct AbiOf;
+template <>
+struct AbiOf<double> {
+  typedef LhfdGpuLevel level_type;
+  typedef LhfdGpuCcs   ccs_type;
+  typedef LhfdGpuHdl   handle_type;
+};
+template <>
+struct AbiOf<float> {
+  typedef LhfsGpuLevel level_type;
+  typedef LhfsGpuCcs   ccs_type;
+  typedef LhfsGpuHdl   handle_type;
 };
 
 namespace detail {
@@ -41,12 +65,10 @@ struct QrAccess : Qr {
 };
 
 template <class Ccs>
-inline LhfdGpuCcs describe_ccs(const Ccs &M) {
-  static_assert(std::is_same<typename Ccs::value_type, double>::value,
-                "the device backend is built for double factors");
+inline typename AbiOf<typename Ccs::value_type>::ccs_type describe_ccs(const Ccs &M) {
   static_assert(sizeof(typename Ccs::index_type) == sizeof(LhfInt), "int32 indices");
   static_assert(sizeof(typename Ccs::indptr_type) == sizeof(LhfIndPtr), "ptrdiff_t indptr");
-  LhfdGpuCcs c;
+  typename AbiOf<typename Ccs::value_type>::ccs_type c;
   c.nrows = M.nrows();
   c.ncols = M.ncols();
   // a default-constructed block has no ind_start array at all
@@ -62,15 +84,17 @@ inline LhfdGpuCcs describe_ccs(const Ccs &M) {
 /// describe every level of a factorized preconditioner; \a scratch keeps
 /// converted pivot arrays alive until the attach call returned
 template <class Hif>
-inline std::vector<LhfdGpuLevel> describe(const Hif &M, std::vector<std::vector<LhfInt>> &scratch) {
-  using prec_type = typename Hif::prec_type;
-  using qr_type   = typename prec_type::sss_solver_type;
-  std::vector<LhfdGpuLevel> lv;
+inline std::vector<typename AbiOf<typename Hif::value_type>::level_type> describe(
+    const Hif &M, std::vector<std::vector<LhfInt>> &scratch) {
+  using prec_type  = typename Hif::prec_type;
+  using qr_type    = typename prec_type::sss_solver_type;
+  using level_type = typename AbiOf<typename Hif::value_type>::level_type;
+  std::vector<level_type> lv;
   lv.reserve(M.precs().size());
   scratch.clear();
   scratch.reserve(M.precs().size());
   for (const auto &P : M.precs()) {
-    LhfdGpuLevel L;
+    level_type L;
     L.m     = P.m;
     L.n     = P.n;
     L.L_B   = detail::describe_ccs(P.L_B);
@@ -105,20 +129,38 @@ inline std::vector<LhfdGpuLevel> describe(const Hif &M, std::vector<std::vector<
   return lv;
 }
 
+namespace detail {
+inline LhfStatus call_attach(const AttachApi &api, int device, std::size_t nl, const LhfdGpuLevel *lv, void **out) {
+  return api.attach_levels(device, nl, lv, reinterpret_cast<LhfdGpuHdl *>(out));
+}
+inline LhfStatus call_attach(const AttachApi &api, int device, std::size_t nl, const LhfsGpuLevel *lv, void **out) {
+  if (!api.attach_levels_s) return LHF_NULL_OBJ;
+  return api.attach_levels_s(device, nl, lv, reinterpret_cast<LhfsGpuHdl *>(out));
+}
+}  // namespace detail
+
 /// attach through a run-time resolved entry point
 template <class Hif>
 inline LhfStatus attach(const Hif &M, const AttachApi &api, int device, void **out) {
   std::vector<std::vector<LhfInt>> scratch;
   const auto lv = describe(M, scratch);
-  return api.attach_levels(device, lv.size(), lv.data(), reinterpret_cast<LhfdGpuHdl *>(out));
+  return detail::call_attach(api, device, lv.size(), lv.data(), out);
 }
 
-/// attach when the program links against libhifir_b200.so
+/// attach when the program links against libhifir_b200.so (double factors)
 template <class Hif>
 inline LhfStatus attach(const Hif &M, int device, LhfdGpuHdl *out) {
   std::vector<std::vector<LhfInt>> scratch;
   const auto lv = describe(M, scratch);
   return lhfdGpuAttachLevels(device, lv.size(), lv.data(), out);
+}
+
+/// the same for a single-precision preconditioner, hif::HIF<float, int>
+template <class Hif>
+inline LhfStatus attach(const Hif &M, int device, LhfsGpuHdl *out) {
+  std::vector<std::vector<LhfInt>> scratch;
+  const auto lv = describe(M, scratch);
+  return lhfsGpuAttachLevels(device, lv.size(), lv.data(), out);
 }
 
 }  // namespace hifir_b200

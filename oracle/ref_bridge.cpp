@@ -34,17 +34,22 @@
 
 namespace {
 
-using prec_t  = hif::HIF<double, int>;
 using crs_t   = hif::CRS<double, int>;
 using array_t = hif::Array<double>;
-using level_t = prec_t::prec_type;
 
-struct QrAcc : hif::QRCP<double> {
-  using hif::QRCP<double>::_tau;
-  using hif::QRCP<double>::_jpvt;
+template <class V>
+struct QrAccT : hif::QRCP<V> {
+  using hif::QRCP<V>::_tau;
+  using hif::QRCP<V>::_jpvt;
 };
 
-struct RefHandle {
+// V = value type of the factors: double (hifref_*) or float (hifrefs_*: hif::HIF<float,int>, the
+// mixed-precision set-up of examples/intermediate/demo_mixedprecision.cpp -- the user matrix and
+// all vectors stay double, exactly as lhfsdApply uses it, libhifir.cpp:1192-1218)
+template <class V>
+struct RefHandleT {
+  typedef hif::HIF<V, int>             prec_t;
+  typedef typename prec_t::prec_type   level_t;
   prec_t M;
   // the user matrix (CRS), wrapped around caller-kept arrays copied here
   std::vector<std::ptrdiff_t> indptr;
@@ -53,10 +58,15 @@ struct RefHandle {
   crs_t                       A;
   std::size_t                 n;
 };
+using RefHandle = RefHandleT<double>;
+using prec_t    = RefHandle::prec_t;
+using level_t   = RefHandle::level_t;
+using QrAcc     = QrAccT<double>;
 
 thread_local std::string g_err;
 
-const level_t &level_at(const RefHandle *h, int lvl) {
+template <class V>
+const typename RefHandleT<V>::level_t &level_at(const RefHandleT<V> *h, int lvl) {
   auto it = h->M.precs().cbegin();
   std::advance(it, lvl);
   return *it;
@@ -370,6 +380,164 @@ int hifref_gpu_attach(const void *hdl, const hifir_b200::AttachApi *api, int dev
   const int   st = hifir_b200::attach(h->M, *api, device, out_gpu_handle);
   if (st != 0) {
     g_err = "lhfdGpu attach failed with status " + std::to_string(st);
+    return st;
+  }
+  REF_CATCH
+}
+
+// ---- the same bridge for a single-precision preconditioner, hif::HIF<float,int> ----------------
+// (factors float, user matrix and all vectors double: the reference's mixed-precision path)
+
+using RefHandleS = RefHandleT<float>;
+
+void *hifrefs_create(std::size_t n, const std::int64_t *indptr, const int *indices, const double *vals,
+                     const double *params, int verbose) {
+  try {
+    std::unique_ptr<RefHandleS> h(new RefHandleS());
+    h->n = n;
+    h->indptr.assign(indptr, indptr + n + 1);
+    const std::size_t nnz = (std::size_t)indptr[n];
+    h->indices.assign(indices, indices + nnz);
+    h->vals.assign(vals, vals + nnz);
+    h->A      = crs_t(n, n, h->indptr.data(), h->indices.data(), h->vals.data(), true);
+    auto opts = hif::get_default_options();
+    if (params) {
+      if (params[0] >= 0) opts.tau_L = params[0];
+      if (params[1] >= 0) opts.tau_U = params[1];
+      if (params[2] >= 0) opts.kappa_d = params[2];
+      if (params[3] >= 0) opts.kappa = params[3];
+      if (params[4] >= 0) opts.alpha_L = params[4];
+      if (params[5] >= 0) opts.alpha_U = params[5];
+      if (params[6] > 0) opts.dense_thres = (int)params[6];
+      if (params[7] > 0) opts.threads = (int)params[7];
+    }
+    opts.verbose = verbose ? hif::VERBOSE_INFO : hif::VERBOSE_NONE;
+    h->M.factorize(h->A, opts);  // double matrix -> float factors (demo_mixedprecision.cpp)
+    return h.release();
+  } catch (const std::exception &e) {
+    g_err = e.what();
+    return nullptr;
+  }
+}
+
+void        hifrefs_destroy(void *hdl) { delete static_cast<RefHandleS *>(hdl); }
+int         hifrefs_num_precs(const void *hdl) { return (int)static_cast<const RefHandleS *>(hdl)->M.precs().size(); }
+std::size_t hifrefs_levels(const void *hdl) { return static_cast<const RefHandleS *>(hdl)->M.levels(); }
+std::size_t hifrefs_nnz(const void *hdl) { return static_cast<const RefHandleS *>(hdl)->M.nnz(); }
+
+int hifrefs_level_sizes(const void *hdl, int lvl, std::size_t *sizes) {
+  REF_TRY
+  const auto &P = level_at(static_cast<const RefHandleS *>(hdl), lvl);
+  sizes[0]      = P.m;
+  sizes[1]      = P.n;
+  sizes[2]      = P.L_B.nnz();
+  sizes[3]      = P.U_B.nnz();
+  sizes[4]      = P.E.nnz();
+  sizes[5]      = P.F.nnz();
+  sizes[6]      = P.dense_solver.empty() ? 0 : P.dense_solver.mat().nrows();
+  sizes[7]      = P.dense_solver.empty() ? 0 : P.dense_solver.rank();
+  sizes[8]      = !P.symm_dense_solver.empty();
+  sizes[9]      = P.is_last_level();
+  REF_CATCH
+}
+
+int hifrefs_block_shape(const void *hdl, int lvl, int which, std::size_t *dims) {
+  REF_TRY
+  const auto &P = level_at(static_cast<const RefHandleS *>(hdl), lvl);
+  const RefHandleS::level_t::mat_type *M = which == 0 ? &P.L_B : which == 1 ? &P.U_B : which == 2 ? &P.E : &P.F;
+  dims[0] = M->nrows();
+  dims[1] = M->ncols();
+  REF_CATCH
+}
+
+int hifrefs_export_ccs(const void *hdl, int lvl, int which, std::int64_t *col_start, int *row_ind, float *vals) {
+  REF_TRY
+  const auto &P = level_at(static_cast<const RefHandleS *>(hdl), lvl);
+  const RefHandleS::level_t::mat_type *M = which == 0 ? &P.L_B : which == 1 ? &P.U_B : which == 2 ? &P.E : &P.F;
+  const std::size_t nc = M->ncols();
+  const bool        has = M->col_start().size() >= nc + 1;
+  for (std::size_t i = 0; i <= nc; ++i) col_start[i] = has ? M->col_start()[i] : 0;
+  std::copy_n(M->row_ind().cbegin(), M->nnz(), row_ind);
+  std::copy_n(M->vals().cbegin(), M->nnz(), vals);
+  REF_CATCH
+}
+
+int hifrefs_export_vectors(const void *hdl, int lvl, float *d, float *s, float *t, int *p, int *p_inv, int *q,
+                           int *q_inv) {
+  REF_TRY
+  const auto &P = level_at(static_cast<const RefHandleS *>(hdl), lvl);
+  std::copy_n(P.d_B.cbegin(), P.m, d);
+  std::copy_n(P.s.cbegin(), P.n, s);
+  std::copy_n(P.t.cbegin(), P.n, t);
+  std::copy_n(P.p.cbegin(), P.n, p);
+  std::copy_n(P.p_inv.cbegin(), P.n, p_inv);
+  std::copy_n(P.q.cbegin(), P.n, q);
+  std::copy_n(P.q_inv.cbegin(), P.n, q_inv);
+  REF_CATCH
+}
+
+int hifrefs_export_dense(const void *hdl, int lvl, float *mat, float *tau, int *jpvt) {
+  REF_TRY
+  const auto &P  = level_at(static_cast<const RefHandleS *>(hdl), lvl);
+  const auto &qr = static_cast<const QrAccT<float> &>(P.dense_solver);
+  const std::size_t nm = qr.mat().nrows();
+  std::copy_n(qr.mat().data(), nm * qr.mat().ncols(), mat);
+  std::copy_n(qr._tau.cbegin(), qr._tau.size(), tau);
+  for (std::size_t i = 0; i < qr._jpvt.size(); ++i) jpvt[i] = (int)qr._jpvt[i];
+  REF_CATCH
+}
+
+int hifrefs_set_nsp_const(void *hdl, std::size_t start, std::size_t end) {
+  REF_TRY
+  static_cast<RefHandleS *>(hdl)->M.nsp = hif::create_nsp_filter(start, end);
+  REF_CATCH
+}
+int hifrefs_clear_nsp(void *hdl) {
+  static_cast<RefHandleS *>(hdl)->M.nsp.reset();
+  return 0;
+}
+
+// lhfsdApply (libhifir.cpp:1192-1218): op 0 = S, 1 = S^H, 2 = M, 3 = M^H on double vectors
+int hifrefs_apply_op(const void *hdl, int op, const double *b, double *x, std::size_t rank) {
+  REF_TRY
+  const auto *  h = static_cast<const RefHandleS *>(hdl);
+  const array_t bb(h->n, const_cast<double *>(b), true);
+  array_t       xx(h->n, x, true);
+  if (op == 0 || op == 1)
+    h->M.solve(bb, xx, op == 1, rank);
+  else if (op == 2 || op == 3)
+    h->M.mmultiply(bb, xx, op == 3, rank);
+  else
+    throw std::invalid_argument("bad op");
+  REF_CATCH
+}
+
+// lhfsApply (libhifir.h:841-854) with op = LHF_S: float vectors
+int hifrefs_solve_f32(const void *hdl, const float *b, float *x, std::size_t rank) {
+  REF_TRY
+  const auto *            h = static_cast<const RefHandleS *>(hdl);
+  const hif::Array<float> bb(h->n, const_cast<float *>(b), true);
+  hif::Array<float>       xx(h->n, x, true);
+  h->M.solve(bb, xx, false, rank);
+  REF_CATCH
+}
+
+// mixed-precision refinement: float preconditioner, residuals with the double matrix (lhfsdUpdate + lhfsdApply)
+int hifrefs_hifir(const void *hdl, const double *b, std::size_t N, double *x, std::size_t rank) {
+  REF_TRY
+  const auto *  h = static_cast<const RefHandleS *>(hdl);
+  const array_t bb(h->n, const_cast<double *>(b), true);
+  array_t       xx(h->n, x, true);
+  h->M.hifir(h->A, bb, N, xx, false, rank);
+  REF_CATCH
+}
+
+int hifrefs_gpu_attach(const void *hdl, const hifir_b200::AttachApi *api, int device, void **out_gpu_handle) {
+  REF_TRY
+  const auto *h  = static_cast<const RefHandleS *>(hdl);
+  const int   st = hifir_b200::attach(h->M, *api, device, out_gpu_handle);
+  if (st != 0) {
+    g_err = "lhfsGpu attach failed with status " + std::to_string(st);
     return st;
   }
   REF_CATCH

@@ -60,6 +60,26 @@ def lib():
         L.hifref_norm2.restype = C.c_double
         L.hifref_norm2.argtypes = [C.c_void_p, C.c_size_t]
         L.hifref_gpu_attach.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        # single-precision preconditioner (hif::HIF<float,int>), same bridge with float factor arrays
+        L.hifrefs_create.restype = C.c_void_p
+        L.hifrefs_create.argtypes = L.hifref_create.argtypes
+        L.hifrefs_destroy.argtypes = [C.c_void_p]
+        L.hifrefs_num_precs.argtypes = [C.c_void_p]
+        L.hifrefs_levels.restype = C.c_size_t
+        L.hifrefs_levels.argtypes = [C.c_void_p]
+        L.hifrefs_nnz.restype = C.c_size_t
+        L.hifrefs_nnz.argtypes = [C.c_void_p]
+        L.hifrefs_level_sizes.argtypes = L.hifref_level_sizes.argtypes
+        L.hifrefs_export_ccs.argtypes = L.hifref_export_ccs.argtypes
+        L.hifrefs_block_shape.argtypes = L.hifref_block_shape.argtypes
+        L.hifrefs_export_vectors.argtypes = L.hifref_export_vectors.argtypes
+        L.hifrefs_export_dense.argtypes = L.hifref_export_dense.argtypes
+        L.hifrefs_set_nsp_const.argtypes = L.hifref_set_nsp_const.argtypes
+        L.hifrefs_clear_nsp.argtypes = [C.c_void_p]
+        L.hifrefs_apply_op.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t]
+        L.hifrefs_solve_f32.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
+        L.hifrefs_hifir.argtypes = L.hifref_hifir.argtypes
+        L.hifrefs_gpu_attach.argtypes = L.hifref_gpu_attach.argtypes
         _lib = L
     return _lib
 
@@ -72,10 +92,15 @@ FULL_RANK = (1 << 64) - 1  # size_t(-1)
 
 
 class RefHif:
-    """A factorized hif::HIF<double,int> living in the reference library."""
+    """A factorized hif::HIF<double,int> -- or, with dtype=np.float32, hif::HIF<float,int> (float
+    factors, double user matrix and vectors: the reference's mixed-precision path) -- living in the
+    reference library."""
 
-    def __init__(self, A, params=None, dense_thres=0, threads=0, verbose=0):
+    def __init__(self, A, params=None, dense_thres=0, threads=0, verbose=0, dtype=np.float64):
         n, indptr, indices, vals = A
+        self.dtype = np.dtype(dtype)
+        assert self.dtype in (np.dtype(np.float64), np.dtype(np.float32))
+        self._pfx = "hifref_" if self.dtype == np.float64 else "hifrefs_"
         self.n = int(n)
         self._A = (np.ascontiguousarray(indptr, dtype=np.int64),
                    np.ascontiguousarray(indices, dtype=np.int32),
@@ -87,14 +112,17 @@ class RefHif:
                     pr[k] = params[name]
         pr[6] = dense_thres
         pr[7] = threads
-        self._h = lib().hifref_create(self.n, _p(self._A[0]), _p(self._A[1]), _p(self._A[2]), _p(pr),
+        self._h = self._f("create")(self.n, _p(self._A[0]), _p(self._A[1]), _p(self._A[2]), _p(pr),
                                       int(verbose))
         if not self._h:
             raise RuntimeError("reference factorize failed: " + lib().hifref_last_error().decode())
 
+    def _f(self, name):
+        return getattr(lib(), self._pfx + name)
+
     def close(self):
         if getattr(self, "_h", None):
-            lib().hifref_destroy(self._h)
+            self._f("destroy")(self._h)
             self._h = None
 
     __del__ = close
@@ -105,19 +133,19 @@ class RefHif:
 
     @property
     def num_precs(self):
-        return lib().hifref_num_precs(self._h)
+        return self._f("num_precs")(self._h)
 
     @property
     def num_levels(self):
-        return lib().hifref_levels(self._h)
+        return self._f("levels")(self._h)
 
     @property
     def nnz(self):
-        return lib().hifref_nnz(self._h)
+        return self._f("nnz")(self._h)
 
     def level_sizes(self, lvl):
         s = np.zeros(10, dtype=np.uint64)
-        self._chk(lib().hifref_level_sizes(self._h, lvl, _p(s)))
+        self._chk(self._f("level_sizes")(self._h, lvl, _p(s)))
         keys = ("m", "n", "nnz_L", "nnz_U", "nnz_E", "nnz_F", "dense_n", "dense_rank", "has_symm_dense",
                 "is_last")
         return {k: int(v) for k, v in zip(keys, s)}
@@ -134,50 +162,65 @@ class RefHif:
             L = dict(m=m, n=n, has_symm_dense=sz["has_symm_dense"])
             for which, (name, nnzk) in enumerate((("L", "nnz_L"), ("U", "nnz_U"), ("E", "nnz_E"), ("F", "nnz_F"))):
                 dims = np.zeros(2, dtype=np.uint64)
-                self._chk(lib().hifref_block_shape(self._h, lvl, which, _p(dims)))
+                self._chk(self._f("block_shape")(self._h, lvl, which, _p(dims)))
                 nr, nc = int(dims[0]), int(dims[1])
                 cs = np.zeros(nc + 1, dtype=np.int64)
                 ri = np.zeros(sz[nnzk], dtype=np.int32)
-                va = np.zeros(sz[nnzk], dtype=np.float64)
-                self._chk(lib().hifref_export_ccs(self._h, lvl, which, _p(cs), _p(ri), _p(va)))
+                va = np.zeros(sz[nnzk], dtype=self.dtype)
+                self._chk(self._f("export_ccs")(self._h, lvl, which, _p(cs), _p(ri), _p(va)))
                 L[name] = (nr, nc, cs, ri, va)
-            d = np.zeros(m); s = np.zeros(n); t = np.zeros(n)
+            d = np.zeros(m, dtype=self.dtype); s = np.zeros(n, dtype=self.dtype); t = np.zeros(n, dtype=self.dtype)
             p, p_inv, q, q_inv = (np.zeros(n, dtype=np.int32) for _ in range(4))
-            self._chk(lib().hifref_export_vectors(self._h, lvl, _p(d), _p(s), _p(t), _p(p), _p(p_inv), _p(q),
+            self._chk(self._f("export_vectors")(self._h, lvl, _p(d), _p(s), _p(t), _p(p), _p(p_inv), _p(q),
                                                   _p(q_inv)))
             L.update(d=d, s=s, t=t, p=p, p_inv=p_inv, q=q, q_inv=q_inv)
             nm = sz["dense_n"]
             L["dense_n"], L["dense_rank"] = nm, sz["dense_rank"]
             if nm:
-                mat = np.zeros(nm * nm); tau = np.zeros(nm); jp = np.zeros(nm, dtype=np.int32)
-                self._chk(lib().hifref_export_dense(self._h, lvl, _p(mat), _p(tau), _p(jp)))
+                mat = np.zeros(nm * nm, dtype=self.dtype); tau = np.zeros(nm, dtype=self.dtype)
+                jp = np.zeros(nm, dtype=np.int32)
+                self._chk(self._f("export_dense")(self._h, lvl, _p(mat), _p(tau), _p(jp)))
                 L.update(qr_mat=mat, qr_tau=tau, qr_jpvt=jp)
             out.append(L)
         return out
 
     def set_nsp_const(self, start=0, end=FULL_RANK):
-        self._chk(lib().hifref_set_nsp_const(self._h, start, end))
+        self._chk(self._f("set_nsp_const")(self._h, start, end))
 
     def clear_nsp(self):
-        lib().hifref_clear_nsp(self._h)
+        self._f("clear_nsp")(self._h)
 
     def solve(self, b, rank=0):
         b = np.ascontiguousarray(b, dtype=np.float64)
         x = np.empty_like(b)
-        self._chk(lib().hifref_solve(self._h, _p(b), _p(x), rank))
+        if self.dtype == np.float32:
+            self._chk(lib().hifrefs_apply_op(self._h, 0, _p(b), _p(x), rank))
+        else:
+            self._chk(lib().hifref_solve(self._h, _p(b), _p(x), rank))
+        return x
+
+    def solve_f32(self, b, rank=0):
+        """lhfsSolve: float factors AND float vectors (single-precision handles only)"""
+        assert self.dtype == np.float32
+        b = np.ascontiguousarray(b, dtype=np.float32)
+        x = np.empty_like(b)
+        self._chk(lib().hifrefs_solve_f32(self._h, _p(b), _p(x), rank))
         return x
 
     def mmultiply(self, x, rank=0):
         x = np.ascontiguousarray(x, dtype=np.float64)
         y = np.empty_like(x)
-        self._chk(lib().hifref_mmultiply(self._h, _p(x), _p(y), rank))
+        if self.dtype == np.float32:
+            self._chk(lib().hifrefs_apply_op(self._h, 2, _p(x), _p(y), rank))
+        else:
+            self._chk(lib().hifref_mmultiply(self._h, _p(x), _p(y), rank))
         return y
 
     def apply_op(self, op, b, rank=0):
         """op 1 = S^H (solve trans), 2 = M (mmultiply), 3 = M^H -- LhfOperationType values"""
         b = np.ascontiguousarray(b, dtype=np.float64)
         x = np.empty_like(b)
-        f = lib().hifref_apply_op
+        f = self._f("apply_op")
         f.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t]
         self._chk(f(self._h, op, _p(b), _p(x), rank))
         return x
@@ -185,7 +228,7 @@ class RefHif:
     def hifir(self, b, nirs, rank=FULL_RANK):
         b = np.ascontiguousarray(b, dtype=np.float64)
         x = np.empty_like(b)
-        self._chk(lib().hifref_hifir(self._h, _p(b), nirs, _p(x), rank))
+        self._chk(self._f("hifir")(self._h, _p(b), nirs, _p(x), rank))
         return x
 
     def hifir_betas(self, b, nirs, betas, rank=FULL_RANK):
@@ -212,12 +255,13 @@ class RefHif:
                                       _p(x), _p(out)))
         return x, int(out[0]), int(out[1]), int(out[2])
 
-    def gpu_attach(self, attach_levels_fnptr, device=0):
+    def gpu_attach(self, attach_levels_fnptr, device=0, attach_levels_s_fnptr=None):
         """Attach the device backend through the C++ adapter include/hifir_b200.hpp,
-        i.e. the way a hif::HIF user would.  Returns the raw LhfdGpuHdl (int)."""
-        api = (C.c_void_p * 1)(C.cast(attach_levels_fnptr, C.c_void_p))
+        i.e. the way a hif::HIF user would.  Returns the raw LhfdGpuHdl / LhfsGpuHdl (int)."""
+        api = (C.c_void_p * 2)(C.cast(attach_levels_fnptr, C.c_void_p),
+                               C.cast(attach_levels_s_fnptr, C.c_void_p) if attach_levels_s_fnptr else None)
         out = C.c_void_p()
-        rc = lib().hifref_gpu_attach(self._h, api, device, C.byref(out))
+        rc = self._f("gpu_attach")(self._h, api, device, C.byref(out))
         if rc != 0:
             raise RuntimeError(f"gpu attach failed ({rc}): " + lib().hifref_last_error().decode())
         return out.value

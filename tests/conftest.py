@@ -11,7 +11,11 @@ if ROOT not in sys.path:
 GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
 GOLDEN_CASES = ("demo_A", "poisson14_ml", "convdiff14_ml", "stokes28_ml", "neumann12_nsp")
 
+# single-precision preconditioners hif::HIF<float,int> (lhfs* / mixed lhfsd* entry points)
+GOLDEN_F32_CASES = ("poisson14_ml_f32", "stokes28_ml_f32", "neumann12_nsp_f32")
+
 TOL_F64 = 1e-12  # north_star: ||x_gpu - x_ref|| / ||x_ref|| <= 1e-12 in double
+TOL_F32 = 1e-5   # north_star: <= 1e-5 in float (against the reference's single-precision apply)
 
 
 def pytest_configure(config):
@@ -53,6 +57,11 @@ def load_golden(name):
 
 @pytest.fixture(params=GOLDEN_CASES)
 def golden(request):
+    return load_golden(request.param)
+
+
+@pytest.fixture(params=GOLDEN_F32_CASES)
+def golden_f32(request):
     return load_golden(request.param)
 
 

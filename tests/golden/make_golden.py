@@ -63,6 +63,36 @@ def make_case(name, A, params, dense_thres=0, nsp=False, b_krylov=None, restart=
           f"betas={out['hifir_betas_status']} -> {os.path.getsize(path) / 1e6:.2f} MB")
 
 
+def make_case_f32(name, A, params, dense_thres=0, nsp=False):
+    """Single-precision preconditioner hif::HIF<float,int> factorized from the double matrix (the
+    mixed-precision set-up of examples/intermediate/demo_mixedprecision.cpp): float factors and the
+    reference's outputs of lhfsdApply (double vectors: S, S^H, M, M^H, refinement with the double
+    matrix) and lhfsSolve (float vectors)."""
+    n = A[0]
+    M = R.RefHif(A, params, dense_thres=dense_thres, dtype=np.float32)
+    if nsp:
+        M.set_nsp_const()
+    levels = M.levels()
+    out = levels_to_arrays(levels)
+    assert out["lv0_L_va"].dtype == np.float32 and out["lv0_s"].dtype == np.float32
+    out.update(A_n=np.array(n), A_indptr=A[1], A_indices=A[2], A_vals=A[3], nsp=np.array(int(nsp)),
+               restart=np.array(30))
+    B = P.seeded_rhs(n, 0, nrhs=4)
+    out["B"] = B
+    out["X"] = np.stack([M.solve(B[:, k].copy()) for k in range(4)], axis=1)
+    out["X_full"] = np.stack([M.solve(B[:, k].copy(), R.FULL_RANK) for k in range(4)], axis=1)
+    out["X32"] = np.stack([M.solve_f32(B[:, k].astype(np.float32)) for k in range(4)], axis=1)
+    b = B[:, 0].copy()
+    if not nsp:
+        for op, key in ((1, "x_SH"), (2, "x_M"), (3, "x_MH")):
+            out[key] = M.apply_op(op, b)
+    out["x_hifir3"] = M.hifir(b, 3)
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, **out)
+    sizes = [(L["m"], L["n"], L["dense_n"]) for L in levels]
+    print(f"{name}: n={n} levels={sizes} (float factors) -> {os.path.getsize(path) / 1e6:.2f} MB")
+
+
 def qrcp_kat():
     src = open(os.path.join(REF, "tests", "test_sss_qrcp.cpp")).read()
 
@@ -80,7 +110,17 @@ def qrcp_kat():
     print("qrcp_kat: rank", rank, "max|x-x_ref|", np.abs(x - x_ref).max())
 
 
+def f32_cases():
+    make_case_f32("poisson14_ml_f32", P.poisson3d(14), P.PDE_PARAMS, dense_thres=40)
+    make_case_f32("stokes28_ml_f32", P.stokes2d_mac(28), P.PDE_PARAMS, dense_thres=60)
+    make_case_f32("neumann12_nsp_f32", P.neumann3d(12), P.PDE_PARAMS, dense_thres=100, nsp=True)
+
+
 if __name__ == "__main__":
+    if "--f32-only" in sys.argv:  # adds the single-precision fixtures without touching the others
+        f32_cases()
+        sys.exit(0)
+    f32_cases()
     qrcp_kat()
     A = P.read_matrix_market(os.path.join(REF, "examples/demo_inputs/A.mm"))
     b = P.read_matrix_market(os.path.join(REF, "examples/demo_inputs/b.mm"))

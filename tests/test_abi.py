@@ -113,6 +113,33 @@ def test_sweep_packing_host_emulation(lib, case, mode, monkeypatch):
                 assert st["max_smem"] <= 112 * 1024
 
 
+@pytest.mark.parametrize("merge", ["1", "0"])
+def test_float_sweep_packing_host_emulation(lib, merge, monkeypatch):
+    """Single-precision factors (lhfsGpuAttachLevels): the streamed values are the merged values
+    rounded to float.  Emulated on the host, the packed sweep must agree with plain substitution on
+    the float factor to float rounding -- far inside the 1e-5 gate."""
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spl
+    monkeypatch.setenv("HIFIR_B200_SWEEP", "stream")
+    monkeypatch.setenv("HIFIR_B200_MERGE", merge)
+    g = load_golden("stokes28_ml_f32")
+    rng = np.random.default_rng(2)
+    for L in g.levels:
+        m = L["m"]
+        rhs = rng.uniform(-1, 1, m)
+        for name, upper in (("L", False), ("U", True)):
+            nr, nc, cs, ri, va = L[name]
+            assert va.dtype == np.float32
+            d = L["d"].astype(np.float64)
+            x, st = hb.debug_sweep_host(L[name], upper, rhs, d if upper else None)
+            T = sp.csc_matrix((va.astype(np.float64), ri, cs), shape=(m, m)) + sp.identity(m, format="csc")
+            ref = spl.spsolve_triangular(T.tocsr(), rhs / d if upper else rhs, lower=not upper)
+            err = np.linalg.norm(x - ref) / np.linalg.norm(ref)
+            assert err <= (2e-6 if merge == "1" else 1e-13), (name, err)
+            if merge == "1" and len(va) > 100:
+                assert err > 0.0  # the merged values really were rounded
+
+
 def test_level_merging_shortens_the_dependency_chain(lib, monkeypatch):
     """merge.cu: the merged factor (the one the streaming sweep runs) must be much shallower than
     the reference's factor, at a bounded cost in entries."""

@@ -297,6 +297,109 @@ def test_large_size_properties_and_merged_structure():
         assert relerr(X[:, 2], x1 - x2) <= 1e-11
 
 
+# ------------------------------------------------------------------ single / mixed precision
+def _widened(levels):
+    """the same factors with every value array widened to double (exact)"""
+    out = []
+    for L in levels:
+        W = dict(L)
+        for k in "LUEF":
+            nr, nc, cs, ri, va = L[k]
+            W[k] = (nr, nc, cs, ri, va.astype(np.float64))
+        for k in ("d", "s", "t", "qr_mat", "qr_tau"):
+            if k in L:
+                W[k] = L[k].astype(np.float64)
+        out.append(W)
+    return out
+
+
+def test_single_precision_preconditioner_matches_float_reference(golden_f32):
+    """hif::HIF<float,int> (lhfs* and the mixed lhfsd* family, libhifir.h:775-872, 1231-1280): the
+    device stores the sweep values as float and computes in double.  Gate (north_star): 1e-5 relative
+    against the reference's single-precision apply; against the double restatement on the same float
+    factors only the float rounding of the merged values remains."""
+    from conftest import TOL_F32
+    g = golden_f32
+    Oh = O.OracleHif(g.levels, g.A)
+    if g.nsp:
+        Oh.set_nsp_const()
+    with _gpu(g) as G:
+        assert G.single
+        for k in range(g["B"].shape[1]):
+            b = np.ascontiguousarray(g["B"][:, k])
+            x = G.solve(b)  # lhfsdGpuSolve: float factors, double vectors
+            assert x.dtype == np.float64
+            assert relerr(x, g["X"][:, k]) <= TOL_F32, "vs the reference's float apply"
+            assert relerr(x, Oh.solve(b)) <= 2e-6, "vs the double restatement on the float factors"
+            x32 = G.solve_f32(b)  # lhfsGpuSolve: float vectors
+            assert x32.dtype == np.float32
+            assert relerr(x32, g["X32"][:, k]) <= TOL_F32
+            assert relerr(x32, x) <= 5e-7  # = rounding of b and x to float
+        b = np.ascontiguousarray(g["B"][:, 0])
+        x, _ = G.apply(b, nirs=3)  # lhfsdGpuApply: refinement with the double matrix (lhfsdUpdate)
+        assert relerr(x, g["x_hifir3"]) <= TOL_F32
+        x, _ = G.apply_f32(b)
+        assert relerr(x, g["X32"][:, 0]) <= TOL_F32
+        if not g.nsp:
+            for op, key in ((hb.LHF_SH, "x_SH"), (hb.LHF_M, "x_M"), (hb.LHF_MH, "x_MH")):
+                x, _ = G.apply(b, op=op)
+                assert relerr(x, g[key]) <= TOL_F32, key
+            X = G.solve_mrhs(np.ascontiguousarray(g["B"]))  # through lhfsGpuAsDouble
+            for k in range(g["B"].shape[1]):
+                assert relerr(X[:, k], g["X"][:, k]) <= TOL_F32
+        # what single precision buys: 8 instead of 12 bytes per streamed sweep entry
+        st = G.stats()
+        with hb.GpuHif(_widened(g.levels)) as Gd:
+            std = Gd.stats()
+            if g.nsp:
+                Gd.set_nsp_const()
+            assert not Gd.single and relerr(G.solve(b), Gd.solve(b)) <= 2e-6
+        assert st["sweep_entries"] == std["sweep_entries"]
+        assert st["sweep_bytes"] < 0.8 * std["sweep_bytes"], (st["sweep_bytes"], std["sweep_bytes"])
+        assert st["bytes_factors"] < 0.8 * std["bytes_factors"]
+
+
+@pytest.mark.parametrize("mode", [("stream", "0"), ("slab", "1")], ids=lambda m: f"{m[0]}-merge{m[1]}")
+def test_single_precision_other_sweep_kernels(mode, monkeypatch):
+    """unmerged streaming (no rounding beyond the float factors themselves) and the slab kernel
+    (keeps double storage) serve a single-precision preconditioner too"""
+    from conftest import TOL_F32
+    monkeypatch.setenv("HIFIR_B200_SWEEP", mode[0])
+    monkeypatch.setenv("HIFIR_B200_MERGE", mode[1])
+    g = load_golden("stokes28_ml_f32")
+    Oh = O.OracleHif(g.levels, g.A)
+    with _gpu(g) as G:
+        b = np.ascontiguousarray(g["B"][:, 1])
+        x = G.solve(b)
+        assert relerr(x, g["X"][:, 1]) <= TOL_F32
+        assert relerr(x, Oh.solve(b)) <= (1e-12 if mode == ("stream", "0") else 2e-6)
+
+
+@needs_ref
+def test_single_precision_against_live_reference_same_object():
+    """attach through the C++ adapter to a live hif::HIF<float,int> (include/hifir_b200.hpp)"""
+    from conftest import TOL_F32
+    from oracle import refhost as R
+    A = P.convdiff3d(32)
+    M = R.RefHif(A, P.PDE_PARAMS, dense_thres=300, dtype=np.float32)
+    fd = C.cast(hb.lib().lhfdGpuAttachLevels, C.c_void_p).value
+    fs = C.cast(hb.lib().lhfsGpuAttachLevels, C.c_void_p).value
+    with hb.GpuHif(raw_handle=M.gpu_attach(fd, attach_levels_s_fnptr=fs), single=True) as G:
+        G.set_matrix(A)
+        assert G.stats()["levels"] == M.num_precs
+        for j in range(2):
+            b = P.seeded_rhs(A[0], j)
+            assert relerr(G.solve(b), M.solve(b)) <= TOL_F32
+            assert relerr(G.solve_f32(b), M.solve_f32(b)) <= TOL_F32
+        b = P.seeded_rhs(A[0], 0)
+        x, _ = G.apply(b, nirs=4)
+        assert relerr(x, M.hifir(b, 4)) <= TOL_F32
+        # mixed-precision FGMRES-HIFIR: float preconditioner inside a double Krylov loop reaches rtol
+        bk = P.csr_matvec(A, np.ones(A[0]))
+        xg, fg, ig, ng = G.fgmres(bk)
+        assert fg == 0 and relerr(P.csr_matvec(A, xg), bk) <= 1e-6
+
+
 def _ccs(dense):
     """dense 2-D array -> (nrows, ncols, col_start, row_ind, vals) as the level dicts hold them"""
     import scipy.sparse as sp

@@ -99,6 +99,30 @@ def test_ccs_to_crs_restatement(golden):
             assert np.array_equal(rs, ref.indptr) and np.array_equal(ci, ref.indices) and np.array_equal(v, ref.data)
 
 
+# ---------------------------------------------------------------- single precision
+# The oracle for hif::HIF<float,int> is the same C restatement run in double on the widened float
+# factors; it is pinned here against the reference's own single-precision outputs (float work
+# vectors, builder.hpp:125-131): they differ by the reference's float rounding only.
+F32_PORT_TOL = 2e-6
+
+
+def test_port_on_float_factors_matches_float_reference(golden_f32):
+    from conftest import TOL_F32
+    g = golden_f32
+    assert g.levels[0]["L"][4].dtype == np.float32 and g.levels[0]["s"].dtype == np.float32
+    Oh = _oracle(g)
+    for k in range(g["B"].shape[1]):
+        b = np.ascontiguousarray(g["B"][:, k])
+        assert relerr(Oh.solve(b), g["X"][:, k]) <= F32_PORT_TOL          # lhfsdSolve
+        assert relerr(Oh.solve(b, O.FULL_RANK), g["X_full"][:, k]) <= F32_PORT_TOL
+        assert relerr(Oh.solve(b), g["X32"][:, k]) <= F32_PORT_TOL        # lhfsSolve (float vectors)
+    b = np.ascontiguousarray(g["B"][:, 0])
+    assert relerr(Oh.hifir(b, 3), g["x_hifir3"]) <= TOL_F32               # refinement with the double matrix
+    if not g.nsp:
+        for op, key in ((1, "x_SH"), (2, "x_M"), (3, "x_MH")):
+            assert relerr(Oh.apply_op(op, b), g[key]) <= F32_PORT_TOL, key
+
+
 # ---------------------------------------------------------------- live reference
 needs_ref = pytest.mark.skipif(not have_reference(), reason="oracle/_ref/libhifir_ref.so not built/loadable")
 
@@ -125,6 +149,21 @@ def test_port_vs_live_reference(case):
     assert (fo, io, no) == (fr, ir, nr)
     assert relerr(xo, xr) <= 1e-8
     assert np.isclose(O.norm2(b), R.norm2(b), rtol=1e-14)
+
+
+@needs_ref
+def test_port_vs_live_float_reference():
+    """hif::HIF<float,int> factorized here from the double matrix (demo_mixedprecision.cpp)"""
+    from oracle import refhost as R
+    A = P.convdiff3d(16)
+    M = R.RefHif(A, P.PDE_PARAMS, dense_thres=100, dtype=np.float32)
+    lv = M.levels()
+    assert all(L[k][4].dtype == np.float32 for L in lv for k in "LUEF")
+    Oh = O.OracleHif(lv, A)
+    b = P.seeded_rhs(A[0], 7)
+    assert relerr(Oh.solve(b), M.solve(b)) <= F32_PORT_TOL
+    assert relerr(Oh.solve(b), M.solve_f32(b)) <= F32_PORT_TOL
+    assert relerr(Oh.hifir(b, 4), M.hifir(b, 4)) <= 1e-5
 
 
 @needs_ref
