@@ -141,16 +141,28 @@ def hbm_peak():
 
 
 # ----------------------------------------------------------------------------- reference arm
-def cpu_apply_rate(M, n, applies, warm=1):
+def cpu_apply_rate(M, n, applies, warm=1, nirs=1, A=None):
+    """nirs > 1: a step is one hif::HIF::hifir(A, b, nirs, x) (builder.hpp:458-465) = nirs applies;
+    the right-hand sides are then consistent (b = A v), as config 5 asks."""
     from hifir_b200 import problems as P
-    bs = [P.seeded_rhs(n, j) for j in range(2)]
+    bs = [step_rhs(A, n, j, nirs) for j in range(2)]
+    f = (lambda b: M.solve(b)) if nirs <= 1 else (lambda b: M.hifir(b, nirs))
     for _ in range(warm):
-        M.solve(bs[0])
+        f(bs[0])
     t0 = time.perf_counter()
     for k in range(applies):
-        M.solve(bs[k % 2])
+        f(bs[k % 2])
     dt = time.perf_counter() - t0
     return applies / dt, dt
+
+
+def step_rhs(A, n, j, nirs):
+    """right-hand side j of a step: U(-1,1) seeded (apply), or the consistent b = A v_j of the
+    refinement configs (v_j = sin(0.37 i + j))"""
+    from hifir_b200 import problems as P
+    if nirs <= 1:
+        return P.seeded_rhs(n, j)
+    return P.csr_matvec(A, np.sin(0.37 * np.arange(n) + j))
 
 
 def run_reference(args, rank, world):
@@ -159,17 +171,23 @@ def run_reference(args, rank, world):
     A = make_problem(args.workload, args.size)
     n = A[0]
     single = args.precision == "single"
-    M = factorize(A, threads=os.cpu_count() or 1, dtype=np.float32 if single else np.float64)
-    steps = min(args.steps, args.ref_max_steps)
-    cpu_apply_rate(M, n, max(1, min(args.warmup, 3)), warm=0)
-    rate, dt = cpu_apply_rate(M, n, steps, warm=0)
+    nirs = args.nirs
+    M = factorize(A, threads=os.cpu_count() or 1, nsp=args.workload == "neumann",
+                  dtype=np.float32 if single else np.float64)
+    steps = min(args.steps, max(1, args.ref_max_steps // nirs))
+    cpu_apply_rate(M, n, max(1, min(args.warmup, 3)), warm=0, nirs=nirs, A=A)
+    rate, dt = cpu_apply_rate(M, n, steps, warm=0, nirs=nirs, A=A)
+    rate *= nirs  # applies/s: a refinement step holds nirs applies
     sample = (f"{steps} of the {args.steps} requested hif::HIF::solve applies (serial reference code, "
-              f"prec_solve.hpp:332-412 has no threading), each a full apply of the workload")
+              f"prec_solve.hpp:332-412 has no threading), each a full apply of the workload") if nirs <= 1 else (
+              f"{steps} of the {args.steps} requested hif::HIF::hifir(A, b, nirs={nirs}) solves = {steps * nirs} applies "
+              f"+ {steps * (nirs - 1)} A x (OpenMP, {os.cpu_count()} threads); the apply itself is serial")
     line = {
         "impl": "reference", "metric": "M^-1 applies/sec", "value": rate, "unit": "applies/s", "n_gpus": args.gpus,
         "steps": steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32" if single else "f64", "data": "synthetic",
-        "config": {"workload": workload_name(args.workload, args.size, 1) + (" single-precision factors" if single else ""),
+        "config": {"workload": workload_name(args.workload, args.size, 1) + (" single-precision factors" if single else "")
+                   + (f" hifir nirs={nirs}" if nirs > 1 else ""),
                    "n": n, "params": "tau=1e-2 alpha=3 kappa=5 (reference PDE set)"},
         "cpu_baseline": {"value": rate, "unit": "applies/s", "cores": 1, "kind": "reference", "sample": sample},
         "e2e": {"value": rate, "unit": "applies/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -308,7 +326,9 @@ def run_ours(args, rank, world, local_rank):
     nsp = args.workload == "neumann"
     threads = max(1, (os.cpu_count() or 1) // world)
     single = args.precision == "single"
+    t0 = time.time()
     M = factorize(A, threads=threads, nsp=nsp, dtype=np.float32 if single else np.float64)
+    t_fact = time.time() - t0
     levels = M.levels()
     t0 = time.time()
     G = hb.GpuHif(levels, device=local_rank)
@@ -317,13 +337,15 @@ def run_ours(args, rank, world, local_rank):
     if nsp:
         G.set_nsp_const()
     st = G.stats()
-    log(f"[bench] rank {rank}: attach {time.time() - t0:.1f} s, device bytes {st['device_bytes'] / 1e9:.2f} GB, "
+    t_attach = time.time() - t0
+    log(f"[bench] rank {rank}: attach {t_attach:.1f} s, device bytes {st['device_bytes'] / 1e9:.2f} GB, "
         f"depths {G.depths().tolist()}")
     stream = torch.cuda.current_stream()
     G.set_stream(stream.cuda_stream)
 
     nb = 4
-    b_host = [torch.from_numpy(P.seeded_rhs(n, rank * nb + j)).pin_memory() for j in range(nb)]
+    nirs = args.nirs  # > 1: a step is one hifir(A, b, nirs, x) = nirs applies + nirs - 1 residuals (config 5)
+    b_host = [torch.from_numpy(step_rhs(A, n, rank * nb + j, nirs)).pin_memory() for j in range(nb)]
     b_dev = [b.cuda() for b in b_host]
     x_dev = torch.empty(n, dtype=torch.float64, device="cuda")
     x_host = torch.empty(n, dtype=torch.float64).pin_memory()
@@ -333,10 +355,22 @@ def run_ours(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def step_dev(k):
+        if nirs <= 1:
+            G.solve_dev(b_dev[k % nb].data_ptr(), x_dev.data_ptr(), 0)
+        else:  # hif::HIF::hifir: last_dim = size_t(-1), full-rank dense solve (builder.hpp:461)
+            G.hifir_dev(b_dev[k % nb].data_ptr(), nirs, x_dev.data_ptr())
+
+    def step_host(k):
+        if nirs <= 1:
+            G.solve(b_host[k % nb].numpy(), out=x_host.numpy())
+        else:
+            x_host.numpy()[:] = G.apply(b_host[k % nb].numpy(), nirs=nirs)[0]
+
     # ---- parity spot check before timing (against the reference's own apply, same object)
-    G.solve_dev(b_dev[0].data_ptr(), x_dev.data_ptr(), 0)
+    step_dev(0)
     G.synchronize()
-    xr = M.solve(b_host[0].numpy())
+    xr = M.solve(b_host[0].numpy()) if nirs <= 1 else M.hifir(b_host[0].numpy(), nirs)
     parity = float(np.linalg.norm(x_dev.cpu().numpy() - xr) / np.linalg.norm(xr))
     log(f"[bench] rank {rank}: parity vs reference apply = {parity:.2e}")
     gate = 1e-5 if single else 1e-12  # north_star tolerances (float / double)
@@ -344,7 +378,7 @@ def run_ours(args, rank, world, local_rank):
 
     # ---- device-resident timing
     for k in range(args.warmup):
-        G.solve_dev(b_dev[k % nb].data_ptr(), x_dev.data_ptr(), 0)
+        step_dev(k)
     launches0 = G.stats()["launch_count"]
     sampler = ClockSampler(local_rank)
     barrier()
@@ -352,7 +386,7 @@ def run_ours(args, rank, world, local_rank):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     for k in range(args.steps):
-        G.solve_dev(b_dev[k % nb].data_ptr(), x_dev.data_ptr(), 0)
+        step_dev(k)
     e1.record(stream)
     barrier()
     clocks = sampler.stop()
@@ -362,11 +396,11 @@ def run_ours(args, rank, world, local_rank):
 
     # ---- end to end through the host-buffer C-ABI call (pinned host memory)
     for k in range(min(3, args.warmup)):
-        G.solve(b_host[k % nb].numpy(), out=x_host.numpy())
+        step_host(k)
     barrier()
     t0 = time.perf_counter()
     for k in range(args.steps):
-        G.solve(b_host[k % nb].numpy(), out=x_host.numpy())
+        step_host(k)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     barrier()
@@ -378,12 +412,14 @@ def run_ours(args, rank, world, local_rank):
         out = [torch.empty_like(x_dev) for _ in range(world)]
         dist.all_gather(out, x_dev)
     ms_total, e2e_ms = float(t[0]), float(t[1])
-    ms_step = ms_total / args.steps
+    ms_step = ms_total / args.steps / nirs  # per APPLY (a refinement step holds nirs of them)
     if rank != 0:
         return
 
     st = G.stats()
     bytes_apply = st["bytes_factors"] + st["bytes_dense"] + st["bytes_vec_per_rhs"]
+    if nirs > 1:  # a refinement adds the bytes of A and 3 vectors, nirs - 1 times per solve
+        bytes_apply += (nirs - 1) * (len(A[2]) * 12 + (n + 1) * 4 + 3 * 8 * n) // nirs
     peak, peak_src = hbm_peak()
     achieved = bytes_apply / (ms_step * 1e-3) / 1e9
     # dominant kernel, timed live with events inside an instrumented apply
@@ -430,11 +466,12 @@ def run_ours(args, rank, world, local_rank):
 
     cpu = None
     if world == 1 and not args.no_cpu:
-        applies = args.cpu_applies
-        rate, dt = cpu_apply_rate(M, n, applies)
-        cpu = {"value": rate, "unit": "applies/s", "cores": 1, "kind": "reference",
-               "sample": f"{applies} hif::HIF::solve applies of the same workload on the same factorized object "
-                         f"({dt:.1f} s; the reference apply is serial)"}
+        applies = max(1, args.cpu_applies // nirs)
+        rate, dt = cpu_apply_rate(M, n, applies, nirs=nirs, A=A)
+        cpu = {"value": rate * nirs, "unit": "applies/s", "cores": 1 if nirs <= 1 else threads, "kind": "reference",
+               "sample": (f"{applies} hif::HIF::solve applies" if nirs <= 1 else
+                          f"{applies} hif::HIF::hifir(nirs={nirs}) solves (A x with {threads} OpenMP threads)") +
+                         f" of the same workload on the same factorized object ({dt:.1f} s; the reference apply is serial)"}
     extra = {}
     if world == 1 and not args.no_fgmres:
         bk = P.csr_matvec(A, np.ones(n)) if not nsp else P.csr_matvec(A, np.sin(0.37 * np.arange(n)))
@@ -451,22 +488,47 @@ def run_ours(args, rank, world, local_rank):
                                    cpu_threads=threads)
 
     line = {
-        "metric": "M^-1 applies/sec", "value": world * args.steps / (ms_total * 1e-3), "unit": "applies/s",
-        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+        "metric": "M^-1 applies/sec", "value": world * args.steps * nirs / (ms_total * 1e-3), "unit": "applies/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32 factors (hif::HIF<float>), f64 vectors and accumulation" if single else "f64",
         "data": "synthetic",
-        "config": {"workload": workload_name(args.workload, args.size, 1) + (" single-precision factors" if single else ""),
+        "config": {"workload": workload_name(args.workload, args.size, 1) + (" single-precision factors" if single else "")
+                   + (f" hifir nirs={nirs}" if nirs > 1 else ""),
                    "n": n, "levels": st["levels"],
                    "nnz_factors": st["nnz"], "params": "tau=1e-2 alpha=3 kappa=5 (reference PDE set)",
                    "l2_policy": f"inputs larger than L2: {bytes_apply / 1e9:.2f} GB streamed per apply vs 126 MB L2",
                    "parallelism": "replicas, independent right-hand sides per GPU" if world > 1 else "1 GPU"},
         "roofline": roofline, "cpu_baseline": cpu,
-        "e2e": {"value": world * args.steps / (e2e_ms * 1e-3), "unit": "applies/s", "h2d_bytes_per_step": 8 * n,
+        "e2e": {"value": world * args.steps * nirs / (e2e_ms * 1e-3), "unit": "applies/s", "h2d_bytes_per_step": 8 * n,
                 "d2h_bytes_per_step": 8 * n,
-                "api": ("lhfsdGpuSolve" if single else "lhfdGpuSolve") + " (pinned host buffers)"},
+                "api": (("lhfsdGpuSolve" if single else "lhfdGpuSolve") if nirs <= 1 else
+                        ("lhfsdGpuApply" if single else "lhfdGpuApply") + f"(LHF_S, nirs={nirs})") + " (pinned host buffers)"},
         "gpu_launches": launches, "clocks": clocks, "parity_vs_reference": parity,
     }
+    if args.arena_check and world == 1:
+        # factor arena file (csrc/arena.cu): write, attach from the file, compare with the live attach
+        path = os.path.join(CACHE_DIR, f"bench_{args.workload}{args.size}_{args.precision}.hifb")
+        os.makedirs(CACHE_DIR, exist_ok=True)
+        t0 = time.time()
+        hb.save_arena(path, levels, True)
+        t_save = time.time() - t0
+        t0 = time.time()
+        F = hb.attach_arena(path, device=local_rank)
+        t_file = time.time() - t0
+        if nsp:
+            F.set_nsp_const()
+        xa, xb = F.solve(b_host[0].numpy()), G.solve(b_host[0].numpy())
+        line["arena"] = {"file_bytes": os.path.getsize(path), "save_s": t_save, "attach_file_s": t_file,
+                         "attach_live_s": t_attach, "factorize_s_not_needed": t_fact,
+                         "bit_identical_to_live_attach": bool(np.array_equal(xa, xb))}
+        F.close()
+        os.remove(path)
+    if nirs > 1:
+        line["hifir"] = {"nirs": nirs, "solves_per_s": world * args.steps / (ms_total * 1e-3),
+                         "ms_per_solve": ms_total / args.steps,
+                         "step": f"hif::HIF::hifir(A, b, {nirs}, x): {nirs} applies + {nirs - 1} residuals b - A x, "
+                                 "independent systems per GPU"}
     line.update(extra)
     print(json.dumps(line), flush=True)
 
@@ -483,6 +545,10 @@ def main():
                     help="> 1: batched multi-rhs mode (config 4), columns sharded over the ranks (strong scaling)")
     ap.add_argument("--precision", default="double", choices=["double", "single"],
                     help="single: hif::HIF<float,int> factors (mixed precision, lhfsdGpuSolve), parity gate 1e-5")
+    ap.add_argument("--nirs", type=int, default=1,
+                    help="> 1: a step is one hifir(A, b, nirs, x) iterative-refinement solve (config 5: neumann, nirs=4)")
+    ap.add_argument("--arena-check", action="store_true",
+                    help="also write a factor arena file, attach from it and compare (csrc/arena.cu)")
     ap.add_argument("--cpu-applies", type=int, default=40)
     ap.add_argument("--ref-max-steps", type=int, default=300)
     ap.add_argument("--no-cpu", action="store_true")

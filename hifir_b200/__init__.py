@@ -137,6 +137,12 @@ def lib():
             "lhfsdGpuSolve": [vp, vp, vp],
             "lhfsdGpuApply": [vp, i, vp, i, vp, i, vp, vp],
             "lhfsGpuDebugSweepHost": [vp, i, vp, vp, vp, vp],
+            "lhfdGpuSaveLevels": [sz, vp, i, C.c_char_p],
+            "lhfsGpuSaveLevels": [sz, vp, i, C.c_char_p],
+            "lhfdGpuAttachFile": [i, C.c_char_p, vp],
+            "lhfsGpuAttachFile": [i, C.c_char_p, vp],
+            "lhfGpuFileInfo": [C.c_char_p, vp],
+            "lhfGpuDebugFileSweepHost": [C.c_char_p, sz, i, vp, vp, vp],
         }
         for name, argt in sig.items():
             f = getattr(L, name)
@@ -157,7 +163,9 @@ EXPORTED_SYMBOLS = (
     "lhfdGpuSpmvDev", "lhfdGpuProfileSolveDev", "lhfdGpuDebugSweepHost", "lhfdGpuDebugTraceSweep", "lhfdGpuDebugSimulateSweep", "lhfdGpuDebugBlockGraph",
     "lhfdGpuGetStats", "lhfdGpuGetDepths", "lhfGpuGetErrorMsg", "lhfGpuVersion",
     "lhfsGpuAttachLevels", "lhfsGpuDestroy", "lhfsGpuAsDouble", "lhfsGpuSetMatrix", "lhfsdGpuUpdate", "lhfsGpuSolve",
-    "lhfsGpuApply", "lhfsdGpuSolve", "lhfsdGpuApply", "lhfsGpuDebugSweepHost")
+    "lhfsGpuApply", "lhfsdGpuSolve", "lhfsdGpuApply", "lhfsGpuDebugSweepHost",
+    "lhfdGpuSaveLevels", "lhfsGpuSaveLevels", "lhfdGpuAttachFile", "lhfsGpuAttachFile", "lhfGpuFileInfo",
+    "lhfGpuDebugFileSweepHost")
 
 
 class LhfError(RuntimeError):
@@ -187,6 +195,43 @@ def debug_sweep_host(block, upper, rhs, diag=None):
     f = lib().lhfsGpuDebugSweepHost if single else lib().lhfdGpuDebugSweepHost
     _chk(f(C.byref(c), int(upper), _ptr(rhs), _ptr(d) if d is not None else None,
                                      _ptr(x), _ptr(st)))
+    return x, dict(zip(("blocks", "halo", "bytes", "max_smem"), (int(v) for v in st)))
+
+
+FILE_INFO_NAMES = ("version", "single", "levels", "n", "nnz", "has_plans", "plan_entries", "plan_depth")
+
+
+def save_arena(path, levels, with_plans=True):
+    """lhf?GpuSaveLevels: write the level description (and the attach-time plans) to an arena file.
+    Host only -- needs no GPU."""
+    dt = levels_dtype(levels)
+    arr, keep = make_level_structs(levels, dt)
+    f = lib().lhfsGpuSaveLevels if dt == np.float32 else lib().lhfdGpuSaveLevels
+    _chk(f(len(levels), C.cast(arr, C.c_void_p), int(bool(with_plans)), os.fsencode(path)))
+
+
+def arena_info(path):
+    """lhfGpuFileInfo: reads and verifies the whole file (host only)"""
+    info = np.zeros(8, dtype=np.uint64)
+    _chk(lib().lhfGpuFileInfo(os.fsencode(path), _ptr(info)))
+    return {k: int(v) for k, v in zip(FILE_INFO_NAMES, info)}
+
+
+def attach_arena(path, device=0):
+    """lhf?GpuAttachFile -> GpuHif (single or double precision as the file says)"""
+    single = bool(arena_info(path)["single"])
+    h = C.c_void_p()
+    f = lib().lhfsGpuAttachFile if single else lib().lhfdGpuAttachFile
+    _chk(f(device, os.fsencode(path), C.byref(h)))
+    return GpuHif(raw_handle=h.value, single=single)
+
+
+def debug_file_sweep_host(path, level, upper, rhs):
+    """lhfGpuDebugFileSweepHost: host emulation of one sweep from an arena file (its stored plan)"""
+    rhs = np.ascontiguousarray(rhs, dtype=np.float64)
+    x = np.zeros_like(rhs)
+    st = np.zeros(4, dtype=np.uint64)
+    _chk(lib().lhfGpuDebugFileSweepHost(os.fsencode(path), level, int(upper), _ptr(rhs), _ptr(x), _ptr(st)))
     return x, dict(zip(("blocks", "halo", "bytes", "max_smem"), (int(v) for v in st)))
 
 

@@ -1,6 +1,7 @@
 // capi.cu -- the C-ABI of include/hifir_b200.h.  Exceptions never cross this boundary:
 // they become LhfStatus + a thread-local message (cf. libhifir.cpp:45-53, 224-229).
 #include <cstring>
+#include <memory>
 #include <new>
 
 #include "hifgpu.h"
@@ -514,6 +515,85 @@ LhfStatus lhfdGpuDebugSweepHost(const LhfdGpuCcs *T, int upper, const double *rh
     R.nrows = R.ncols = T->ncols;
     R.ptr.resize(T->ncols + 1, R.ptr.empty() ? 0u : R.ptr.back());
     sweep_host_emulate(R, upper != 0, rhs, diag, x, stats);
+  });
+}
+
+// ---- factor arena files (arena.cu) ----
+
+LhfStatus lhfdGpuSaveLevels(size_t nlevels, const LhfdGpuLevel *levels, int with_plans, const char *path) {
+  REQUIRE_PTR(levels, "levels");
+  REQUIRE_PTR(path, "path");
+  return guarded([&] { save_levels_file(path, nlevels, levels, false, with_plans != 0); });
+}
+
+LhfStatus lhfsGpuSaveLevels(size_t nlevels, const LhfsGpuLevel *levels, int with_plans, const char *path) {
+  REQUIRE_PTR(levels, "levels");
+  REQUIRE_PTR(path, "path");
+  return guarded([&] {
+    if (!nlevels) throw std::invalid_argument("empty preconditioner (no levels)");
+    WidenedLevels W(nlevels, levels);
+    save_levels_file(path, nlevels, W.lv.data(), true, with_plans != 0);
+  });
+}
+
+LhfStatus lhfdGpuAttachFile(int device, const char *path, LhfdGpuHdl *out) {
+  REQUIRE_PTR(out, "out");
+  *out = nullptr;
+  REQUIRE_PTR(path, "path");
+  return guarded([&] {
+    std::unique_ptr<Handle, void (*)(Handle *)> h(attach_file(device, path), destroy_handle);
+    if (h->f32) throw std::invalid_argument("the arena file holds a single-precision preconditioner: use lhfsGpuAttachFile");
+    *out = reinterpret_cast<LhfdGpuHdl>(h.release());
+  });
+}
+
+LhfStatus lhfsGpuAttachFile(int device, const char *path, LhfsGpuHdl *out) {
+  REQUIRE_PTR(out, "out");
+  *out = nullptr;
+  REQUIRE_PTR(path, "path");
+  return guarded([&] {
+    std::unique_ptr<Handle, void (*)(Handle *)> h(attach_file(device, path), destroy_handle);
+    if (!h->f32) throw std::invalid_argument("the arena file holds a double-precision preconditioner: use lhfdGpuAttachFile");
+    *out = reinterpret_cast<LhfsGpuHdl>(h.release());
+  });
+}
+
+LhfStatus lhfGpuFileInfo(const char *path, size_t info[8]) {
+  REQUIRE_PTR(path, "path");
+  REQUIRE_PTR(info, "info");
+  return guarded([&] {
+    ArenaFile A;
+    A.load(path, true);  // reads everything: validates the checksum as well
+    std::size_t plan_nnz = 0, plan_depth = 0;
+    for (const MergedFactor &mf : A.plans.f) plan_nnz += mf.S.col.size(), plan_depth += mf.st.ext_depth;
+    info[0] = 1, info[1] = A.f32, info[2] = A.lv.size(), info[3] = A.lv[0].n, info[4] = A.nnz_total;
+    info[5] = A.has_plans, info[6] = plan_nnz, info[7] = plan_depth;
+  });
+}
+
+// host-only: the sweep of lhfdGpuDebugSweepHost on factor (level, upper) of an arena file, using the
+// plan stored in the file when it has one -- lets the CPU tests check that a stored plan reproduces
+// what the attach-time analysis computes
+LhfStatus lhfGpuDebugFileSweepHost(const char *path, size_t level, int upper, const double *rhs, double *x,
+                                   size_t stats[4]) {
+  REQUIRE_PTR(path, "path");
+  REQUIRE_PTR(rhs, "rhs");
+  REQUIRE_PTR(x, "x");
+  REQUIRE_PTR(stats, "stats");
+  return guarded([&] {
+    ArenaFile A;
+    A.load(path, true);
+    if (level >= A.lv.size()) throw std::invalid_argument("no such level in the arena file");
+    const LhfdGpuLevel &P = A.lv[level];
+    HostCsr             R = ccs_to_csr(upper ? P.U_B : P.L_B, "T");
+    R.nrows = R.ncols = P.m;
+    R.ptr.resize(P.m + 1, R.ptr.empty() ? 0u : R.ptr.back());
+    struct Scope {
+      explicit Scope(PlanCache *p) { tls_plan_cache = p; }
+      ~Scope() { tls_plan_cache = nullptr; }
+    } scope(A.has_plans ? &A.plans : nullptr);
+    A.plans.next = 2 * level + (upper ? 1 : 0);
+    sweep_host_emulate(R, upper != 0, rhs, P.d_B, x, stats, A.f32);
   });
 }
 

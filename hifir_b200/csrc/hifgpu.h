@@ -98,6 +98,37 @@ struct MergeStats {
 HostCsr to_sweep_form(const HostCsr &T, bool upper);
 HostCsr merge_levels(const HostCsr &S, const MergeParams &prm, MergeStats *st, bool fan_out = false);
 
+// ---- arena.cu : factor arena serialization
+struct MergedFactor {  // result of to_sweep_form + merge_levels for one L_B / U_B
+  HostCsr    S;
+  MergeStats st;
+  bool       upper = false;
+};
+struct PlanCache {  // in attach order: level 0 L, level 0 U, level 1 L, ...
+  std::vector<MergedFactor> f;
+  std::size_t               next = 0;
+};
+extern thread_local PlanCache *tls_plan_cache;  // non-null while attaching from an arena file with plans
+// to_sweep_form + merge_levels (when enabled) of one factor, or the stored plan of the arena file
+HostCsr merged_sweep_form(const HostCsr &Tnat, bool upper, const MergeParams &mp, MergeStats *ms);
+void    save_levels_file(const char *path, std::size_t nlevels, const LhfdGpuLevel *lv, bool f32, bool with_plans);
+struct ArenaFile {  // an arena file read back: the level description (+ plans) with the arrays it points into
+  std::vector<LhfdGpuLevel> lv;
+  bool                      f32 = false, has_plans = false;
+  std::size_t               nnz_total = 0;
+  PlanCache                 plans;
+  ArenaFile();
+  ~ArenaFile();
+  ArenaFile(const ArenaFile &) = delete;
+  ArenaFile &operator=(const ArenaFile &) = delete;
+  void load(const char *path, bool want_plans);
+ private:
+  struct Impl;
+  Impl *impl;
+};
+struct Handle;
+Handle *attach_file(int device, const char *path);
+
 // a strictly triangular factor cut into shared-memory sized slabs (sptrsv.cu)
 struct SweepPlan {
   unsigned               m = 0, nblocks = 0, smem_bytes = 0, nr = 1;  // nr: right-hand sides per slot

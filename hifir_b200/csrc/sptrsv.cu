@@ -794,10 +794,9 @@ static void pack_sweep(const HostCsr &T, bool upper, PackedSweep &out, unsigned 
 void sweep_host_emulate(const HostCsr &T, bool upper, const double *rhs, const double *diag, double *x,
                         std::size_t stats[4], bool f32) {
   PackedSweep       P;
-  HostCsr           S  = to_sweep_form(T, upper);
   const MergeParams mp = MergeParams::from_env();
   MergeStats        ms;
-  if (mp.enabled) S = merge_levels(S, mp, &ms, upper);
+  HostCsr           S = merged_sweep_form(T, upper, mp, &ms);
   const unsigned      m = static_cast<unsigned>(T.nrows);
   std::vector<double> xs, xg(2 * static_cast<std::size_t>(m), 0.0);
   if (stream_sweeps()) {
@@ -969,10 +968,9 @@ bool stream_sweeps() {
 void build_split_plans(const HostCsr &Tnat, SweepPlan &plan_lo, SweepPlan &plan_up, HostCsr &ul,
                        std::vector<unsigned> &urows, std::size_t *tally) {
   const unsigned    mo = static_cast<unsigned>(Tnat.nrows);
-  HostCsr           T  = to_sweep_form(Tnat, false);
   const MergeParams mp = MergeParams::from_env();
   MergeStats        ms;
-  if (mp.enabled) T = merge_levels(T, mp, &ms, false);
+  HostCsr           T = merged_sweep_form(Tnat, false, mp, &ms);  // or the stored plan of an arena file
   if (stream_sweeps()) {  // one level-major sweep, nothing to split
     build_stream_plan(T, false, plan_lo, tally);
     plan_lo.merge = ms;
@@ -1035,14 +1033,15 @@ void build_sweep_plan(const HostCsr &Tnat, bool upper, SweepPlan &plan, std::siz
   plan.nblocks = 0;
   plan.nr      = nr;
   if (!plan.m) return;
-  HostCsr     T = to_sweep_form(Tnat, upper);
+  HostCsr     T;
   PackedSweep P;
   // multi-rhs plans: one CTA per SM with the whole 227 KB, a solution slot holds nr values
   if (nr > 1) {
+    T = to_sweep_form(Tnat, upper);
     pack_sweep(T, upper, P, 8u * nr, kSmemBudgetMrhs);
   } else {
     const MergeParams mp = MergeParams::from_env();
-    if (mp.enabled) T = merge_levels(T, mp, &plan.merge, upper);
+    T = merged_sweep_form(Tnat, upper, mp, &plan.merge);  // or the stored plan of an arena file
     if (stream_sweeps()) {
       const MergeStats ms = plan.merge;
       build_stream_plan(T, upper, plan, tally);

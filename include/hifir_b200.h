@@ -216,6 +216,28 @@ LhfStatus lhfsdGpuSolve(LhfsGpuHdl hdl, const double *b, double *x);
 LhfStatus lhfsdGpuApply(LhfsGpuHdl hdl, LhfOperationType op, const double *b, int nirs, const double *betas,
                         int rank, double *x, int *ir_status);
 
+/* ---- factor arena files (the reference has matrix IO, utils/io.hpp:76-303, but no
+ * on-disk form of a factorized preconditioner) ----------------------------------------------
+ *
+ * lhf?GpuSaveLevels writes the level description -- what lhf?GpuAttachLevels consumes, integers
+ * verbatim, values in the precision of the preconditioner -- and, with with_plans != 0, the result
+ * of the attach-time analysis of every L_B / U_B (sweep form + algebraic level merging).  It is plain
+ * host code: no GPU is needed to write a file.  lhf?GpuAttachFile = lhf?GpuAttachLevels on the arrays
+ * read back (results are bit-identical to attaching the live object), skipping the analysis when the
+ * file carries plans; a later process needs neither the hif::HIF object nor its factorization.
+ * Files end in a checksum; a corrupt or foreign file is refused (LHF_BAD_PREC / LHF_HIFIR_ERROR). */
+LhfStatus lhfdGpuSaveLevels(size_t nlevels, const LhfdGpuLevel *levels, int with_plans, const char *path);
+LhfStatus lhfsGpuSaveLevels(size_t nlevels, const LhfsGpuLevel *levels, int with_plans, const char *path);
+LhfStatus lhfdGpuAttachFile(int device, const char *path, LhfdGpuHdl *out);
+LhfStatus lhfsGpuAttachFile(int device, const char *path, LhfsGpuHdl *out);
+/* info = {format version, single precision, levels, n, nnz of all blocks, has plans, entries of the
+ * stored plans, their total dependency depth}; reads and verifies the whole file (host only) */
+LhfStatus lhfGpuFileInfo(const char *path, size_t info[8]);
+/* Host-only test hook: lhfdGpuDebugSweepHost on factor (level, upper) of an arena file, with the plan
+ * stored in the file when it has one. */
+LhfStatus lhfGpuDebugFileSweepHost(const char *path, size_t level, int upper, const double *rhs, double *x,
+                                   size_t stats[4]);
+
 /* ---- the hot path, DEVICE buffers (asynchronous on the handle's stream) ---- */
 
 /* lhfdGpuApply on device buffers (no residual bounds): op in {LHF_S, LHF_SH, LHF_M, LHF_MH} */

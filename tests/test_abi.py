@@ -140,6 +140,56 @@ def test_float_sweep_packing_host_emulation(lib, merge, monkeypatch):
                 assert err > 0.0  # the merged values really were rounded
 
 
+@pytest.mark.parametrize("case", ["stokes28_ml", "neumann12_nsp", "poisson14_ml_f32"])
+def test_arena_file_roundtrip_on_host(lib, case, tmp_path):
+    """Factor arena files (csrc/arena.cu): written without a GPU from the plain level description;
+    the stored plans (sweep form + level merging of every L_B / U_B) must reproduce, bit for bit,
+    what the attach-time analysis computes from the factors read back."""
+    g = load_golden(case)
+    single = case.endswith("_f32")
+    with_plans, without = str(tmp_path / "a.hifb"), str(tmp_path / "b.hifb")
+    hb.save_arena(with_plans, g.levels, True)
+    hb.save_arena(without, g.levels, False)
+    nnz = sum(len(L[k][3]) for L in g.levels for k in "LUEF")
+    ia, ib = hb.arena_info(with_plans), hb.arena_info(without)
+    assert (ia["version"], ia["single"], ia["levels"], ia["n"], ia["nnz"]) == (1, int(single), len(g.levels), g.n, nnz)
+    assert ia["has_plans"] == 1 and ia["plan_entries"] > 0 and ib["has_plans"] == 0 and ib["nnz"] == nnz
+    assert os.path.getsize(without) < os.path.getsize(with_plans)
+    rng = np.random.default_rng(5)
+    for lvl, L in enumerate(g.levels):
+        if not L["m"]:
+            continue
+        rhs = rng.uniform(-1, 1, L["m"])
+        for name, upper in (("L", False), ("U", True)):
+            x0, s0 = hb.debug_sweep_host(L[name], upper, rhs, L["d"].astype(np.float64) if upper else None)
+            for path in (with_plans, without):
+                x1, s1 = hb.debug_file_sweep_host(path, lvl, upper, rhs)
+                assert np.array_equal(x0, x1) and s0 == s1, (case, lvl, name, path)
+
+
+def test_arena_file_corruption_is_refused(lib, tmp_path):
+    g = load_golden("poisson14_ml")
+    good = str(tmp_path / "good.hifb")
+    hb.save_arena(good, g.levels, True)
+    raw = bytearray(open(good, "rb").read())
+    bad = str(tmp_path / "bad.hifb")
+    flipped = bytearray(raw)
+    flipped[len(raw) // 2] ^= 0x40  # one bit somewhere in the middle
+    open(bad, "wb").write(flipped)
+    with pytest.raises(hb.LhfError) as e:
+        hb.arena_info(bad)
+    assert "arena file" in str(e.value)
+    open(bad, "wb").write(raw[: len(raw) // 3])  # truncated
+    with pytest.raises(hb.LhfError):
+        hb.arena_info(bad)
+    open(bad, "wb").write(b"%%MatrixMarket matrix coordinate real general\n" * 4)  # some other file
+    with pytest.raises(hb.LhfError) as e:
+        hb.arena_info(bad)
+    assert e.value.status == hb.LHF_BAD_PREC
+    with pytest.raises(hb.LhfError):
+        hb.arena_info(str(tmp_path / "does_not_exist.hifb"))
+
+
 def test_level_merging_shortens_the_dependency_chain(lib, monkeypatch):
     """merge.cu: the merged factor (the one the streaming sweep runs) must be much shallower than
     the reference's factor, at a bounded cost in entries."""

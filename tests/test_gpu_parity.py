@@ -400,6 +400,45 @@ def test_single_precision_against_live_reference_same_object():
         assert fg == 0 and relerr(P.csr_matvec(A, xg), bk) <= 1e-6
 
 
+# ------------------------------------------------------------------ factor arena files
+@pytest.mark.parametrize("case", ["demo_A", "stokes28_ml", "neumann12_nsp", "stokes28_ml_f32"])
+@pytest.mark.parametrize("with_plans", [True, False], ids=["plans", "noplans"])
+def test_attach_from_arena_file(case, with_plans, tmp_path):
+    """lhf?GpuSaveLevels -> lhf?GpuAttachFile (csrc/arena.cu): the handle attached from the file must
+    give bit-identical results to the handle attached to the live description, with or without the
+    stored plans, and must pass the same gates against the reference's golden vectors."""
+    from conftest import TOL_F32
+    g = load_golden(case)
+    single = case.endswith("_f32")
+    tol = TOL_F32 if single else TOL_F64
+    path = str(tmp_path / "arena.hifb")
+    hb.save_arena(path, g.levels, with_plans)
+    with _gpu(g) as G, hb.attach_arena(path) as F:
+        assert F.single == single
+        F.set_matrix(g.A)
+        if g.nsp:
+            F.set_nsp_const()
+        sg, sf = G.stats(), F.stats()
+        for k in ("levels", "n", "nnz", "depth_total", "depth_merged", "sweep_entries", "sweep_bytes", "bytes_factors"):
+            assert sg[k] == sf[k], k
+        for k in range(2):
+            b = np.ascontiguousarray(g["B"][:, k])
+            xf = F.solve(b)
+            assert np.array_equal(xf, G.solve(b))
+            assert relerr(xf, g["X"][:, k]) <= tol
+        b = np.ascontiguousarray(g["B"][:, 0])
+        assert np.array_equal(F.apply(b, nirs=3)[0], G.apply(b, nirs=3)[0])
+        if not g.nsp:  # the transposed twin is built later, from the handle's own copies (no stored plan)
+            for op, key in ((hb.LHF_SH, "x_SH"), (hb.LHF_M, "x_M")):
+                x, _ = F.apply(b, op=op)
+                assert relerr(x, g[key]) <= tol, key
+            assert np.array_equal(F.solve_mrhs(np.ascontiguousarray(g["B"])), G.solve_mrhs(np.ascontiguousarray(g["B"])))
+    # a file of the other precision is refused by the typed entry point
+    h = C.c_void_p()
+    wrong = hb.lib().lhfdGpuAttachFile if single else hb.lib().lhfsGpuAttachFile
+    assert wrong(0, path.encode(), C.byref(h)) == hb.LHF_BAD_PREC and not h.value
+
+
 def _ccs(dense):
     """dense 2-D array -> (nrows, ncols, col_start, row_ind, vals) as the level dicts hold them"""
     import scipy.sparse as sp
