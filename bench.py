@@ -518,10 +518,14 @@ def run_ours(args, rank, world, local_rank):
         t_file = time.time() - t0
         if nsp:
             F.set_nsp_const()
-        xa, xb = F.solve(b_host[0].numpy()), G.solve(b_host[0].numpy())
+        # a result carries the ready-bit parity of its apply in the last mantissa bit (common.cuh): compare
+        # with the applies of both parities of the file-attached handle
+        xb = G.solve(b_host[0].numpy())
+        xa = [F.solve(b_host[0].numpy()) for _ in range(2)]
         line["arena"] = {"file_bytes": os.path.getsize(path), "save_s": t_save, "attach_file_s": t_file,
                          "attach_live_s": t_attach, "factorize_s_not_needed": t_fact,
-                         "bit_identical_to_live_attach": bool(np.array_equal(xa, xb))}
+                         "bit_identical_to_live_attach": bool(any(np.array_equal(x, xb) for x in xa)),
+                         "max_rel_diff": float(max(np.linalg.norm(x - xb) for x in xa) / np.linalg.norm(xb))}
         F.close()
         os.remove(path)
     if nirs > 1:

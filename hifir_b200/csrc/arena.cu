@@ -320,9 +320,12 @@ void ArenaFile::load(const char *path, bool want_plans) {
   r.finish();
 }
 
-Handle *attach_file(int device, const char *path) {
+Handle *attach_file(int device, const char *path, bool want_f32) {
   ArenaFile A;
   A.load(path, true);
+  if (A.f32 != want_f32)
+    throw std::invalid_argument(A.f32 ? "the arena file holds a single-precision preconditioner: use lhfsGpuAttachFile"
+                                      : "the arena file holds a double-precision preconditioner: use lhfdGpuAttachFile");
   struct Scope {  // the plans are consumed by exactly this attach (not by a twin built later)
     explicit Scope(PlanCache *p) { tls_plan_cache = p; }
     ~Scope() { tls_plan_cache = nullptr; }

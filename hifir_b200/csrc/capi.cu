@@ -540,22 +540,14 @@ LhfStatus lhfdGpuAttachFile(int device, const char *path, LhfdGpuHdl *out) {
   REQUIRE_PTR(out, "out");
   *out = nullptr;
   REQUIRE_PTR(path, "path");
-  return guarded([&] {
-    std::unique_ptr<Handle, void (*)(Handle *)> h(attach_file(device, path), destroy_handle);
-    if (h->f32) throw std::invalid_argument("the arena file holds a single-precision preconditioner: use lhfsGpuAttachFile");
-    *out = reinterpret_cast<LhfdGpuHdl>(h.release());
-  });
+  return guarded([&] { *out = reinterpret_cast<LhfdGpuHdl>(attach_file(device, path, false)); });
 }
 
 LhfStatus lhfsGpuAttachFile(int device, const char *path, LhfsGpuHdl *out) {
   REQUIRE_PTR(out, "out");
   *out = nullptr;
   REQUIRE_PTR(path, "path");
-  return guarded([&] {
-    std::unique_ptr<Handle, void (*)(Handle *)> h(attach_file(device, path), destroy_handle);
-    if (!h->f32) throw std::invalid_argument("the arena file holds a double-precision preconditioner: use lhfdGpuAttachFile");
-    *out = reinterpret_cast<LhfsGpuHdl>(h.release());
-  });
+  return guarded([&] { *out = reinterpret_cast<LhfsGpuHdl>(attach_file(device, path, true)); });
 }
 
 LhfStatus lhfGpuFileInfo(const char *path, size_t info[8]) {

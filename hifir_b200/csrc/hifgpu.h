@@ -127,7 +127,7 @@ struct ArenaFile {  // an arena file read back: the level description (+ plans) 
   Impl *impl;
 };
 struct Handle;
-Handle *attach_file(int device, const char *path);
+Handle *attach_file(int device, const char *path, bool want_f32);
 
 // a strictly triangular factor cut into shared-memory sized slabs (sptrsv.cu)
 struct SweepPlan {
