@@ -437,9 +437,10 @@ def run_ours(args, rank, world, local_rank):
     k_ach = sw_bytes / (sw_ms * 1e-3) / 1e9
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
-    if os.path.exists(tpath) and not single:  # the committed ncu capture is of the double-precision run
+    if os.path.exists(tpath):
         try:
-            traffic = json.load(open(tpath)).get(workload_name(args.workload, args.size, 1), {}).get(
+            traffic = json.load(open(tpath)).get(workload_name(args.workload, args.size, 1) +
+                                                 (" single-precision factors" if single else ""), {}).get(
                 "sweep_stream_kernel_bytes_per_launch")
         except Exception:
             traffic = None

@@ -340,6 +340,10 @@ def test_single_precision_preconditioner_matches_float_reference(golden_f32):
         assert relerr(x, g["x_hifir3"]) <= TOL_F32
         x, _ = G.apply_f32(b)
         assert relerr(x, g["X32"][:, 0]) <= TOL_F32
+        G.set_matrix_f32(g.A)  # lhfsGpuSetMatrix: single-precision user matrix (lhfsSetup / lhfsUpdate)
+        x, _ = G.apply_f32(b, nirs=3)
+        assert x.dtype == np.float32 and relerr(x, g["x_hifir3"]) <= TOL_F32
+        G.set_matrix(g.A)
         if not g.nsp:
             for op, key in ((hb.LHF_SH, "x_SH"), (hb.LHF_M, "x_M"), (hb.LHF_MH, "x_MH")):
                 x, _ = G.apply(b, op=op)
