@@ -34,10 +34,12 @@ thread_local PlanCache *tls_plan_cache = nullptr;
 // that carries plans -- the stored result of exactly that computation
 HostCsr merged_sweep_form(const HostCsr &Tnat, bool upper, const MergeParams &mp, MergeStats *ms) {
   if (PlanCache *pc = tls_plan_cache) {
-    if (mp.enabled && pc->next < pc->f.size()) {
-      MergedFactor &mf = pc->f[pc->next++];
-      if (mf.S.orig_rows != Tnat.nrows || mf.upper != upper || mf.st.nnz != Tnat.col.size())
-        throw std::invalid_argument("arena file: stored plan does not belong to this factor");
+    // plans are stored in attach order; a factor that is never analysed (the U_B of a level with
+    // m = 0) leaves its entry unused, so look forward for the first entry that belongs to this factor
+    for (std::size_t k = pc->next; mp.enabled && k < pc->f.size(); ++k) {
+      MergedFactor &mf = pc->f[k];
+      if (mf.S.orig_rows != Tnat.nrows || mf.upper != upper || mf.st.nnz != Tnat.col.size()) continue;
+      pc->next = k + 1;
       if (ms) *ms = mf.st;
       return std::move(mf.S);
     }

@@ -4,7 +4,9 @@
 // consume, analyse the triangular dependency structure, upload everything once.
 #include <algorithm>
 #include <cstring>
+#include <exception>
 #include <memory>
+#include <thread>
 
 #include "hifgpu.h"
 
@@ -127,6 +129,7 @@ Handle *attach_levels(int device, std::size_t nlevels, const LhfdGpuLevel *lv, b
   h->stream = h->own_stream;
   h->levels.resize(nlevels);
   std::size_t *tally = &h->device_bytes;
+  std::vector<HostCsr> Lrs(nlevels), Urs(nlevels), Ers(nlevels), Frs(nlevels);  // row-gather forms of the blocks
   // sv = size of a factor value as the reference holds it (4 for hif::HIF<float>);
   // the vectors of an apply are double here whatever the factor precision
   const std::size_t     sv = f32 ? sizeof(float) : sizeof(double);
@@ -155,8 +158,9 @@ Handle *attach_levels(int device, std::size_t nlevels, const LhfdGpuLevel *lv, b
           static_cast<std::size_t>(P.q_inv[i]) >= P.n)
         throw std::invalid_argument(tag + ": permutation entry out of range");
 
-    HostCsr Lr = ccs_to_csr(P.L_B, "L_B"), Ur = ccs_to_csr(P.U_B, "U_B");
-    HostCsr Er = ccs_to_csr(P.E, "E"), Fr = ccs_to_csr(P.F, "F");
+    HostCsr &Lr = Lrs[l], &Ur = Urs[l], &Er = Ers[l], &Fr = Frs[l];
+    Lr = ccs_to_csr(P.L_B, "L_B"), Ur = ccs_to_csr(P.U_B, "U_B");
+    Er = ccs_to_csr(P.E, "E"), Fr = ccs_to_csr(P.F, "F");
     // hif leaves default-constructed (0 x 0) blocks when a part is empty
     Lr.nrows = Lr.ncols = Ur.nrows = Ur.ncols = P.m;
     Lr.ptr.resize(P.m + 1, Lr.ptr.empty() ? 0u : Lr.ptr.back());
@@ -173,6 +177,50 @@ Handle *attach_levels(int device, std::size_t nlevels, const LhfdGpuLevel *lv, b
       if (static_cast<std::size_t>(c) >= D.nm) throw std::invalid_argument(tag + ": F column out of range");
     D.depthL = dag_depth(Lr, false);
     D.depthU = dag_depth(Ur, true);
+  }
+
+  // ---- attach-time analysis of all triangular factors (sweep form + algebraic level merging,
+  // merge.cu: 0.5-1 s per factor at 128^3), one host thread per factor.  The level loop below
+  // consumes the results in order through the plan cache -- the mechanism an arena file with plans
+  // uses (arena.cu); with such a file the analysis is not run at all.
+  PlanCache analysed;
+  struct CacheScope {
+    bool on = false;
+    ~CacheScope() {
+      if (on) tls_plan_cache = nullptr;
+    }
+  } cache_scope;
+  {
+    const MergeParams mp = MergeParams::from_env();
+    const char *      et = std::getenv("HIFIR_B200_ATTACH_THREADS");
+    if (!tls_plan_cache && mp.enabled && nlevels && (!et || std::atoi(et) != 1)) {
+      analysed.f.resize(2 * nlevels);
+      std::vector<std::exception_ptr> errs(2 * nlevels);
+      std::vector<std::thread>        pool;
+      for (std::size_t k = 0; k < 2 * nlevels; ++k)
+        pool.emplace_back([&, k] {
+          try {
+            const bool    upper = (k & 1u) != 0;
+            MergedFactor &mf    = analysed.f[k];
+            mf.upper            = upper;
+            mf.S                = merged_sweep_form(upper ? Urs[k / 2] : Lrs[k / 2], upper, mp, &mf.st);
+          } catch (...) {
+            errs[k] = std::current_exception();
+          }
+        });
+      for (std::thread &t : pool) t.join();
+      for (const std::exception_ptr &e : errs)
+        if (e) std::rethrow_exception(e);
+      tls_plan_cache = &analysed;
+      cache_scope.on = true;
+    }
+  }
+
+  for (std::size_t l = 0; l < nlevels; ++l) {
+    const LhfdGpuLevel &P = lv[l];
+    DevLevel &          D = h->levels[l];
+    HostCsr &Lr = Lrs[l], &Ur = Urs[l], &Er = Ers[l], &Fr = Frs[l];
+    const std::string tag = "level " + std::to_string(l);
 
     D.L.f32 = D.U.f32 = f32;  // streamed sweep values in single precision (stream.cu)
     {
