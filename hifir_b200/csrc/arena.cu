@@ -22,7 +22,9 @@
 // f64 val[nnz]; u32 gid[nrows]; u64 stats[7]}; trailer u64 = FNV-1a of everything before it.
 #include <cstdio>
 #include <cstring>
+#include <exception>
 #include <memory>
+#include <thread>
 
 #include "hifgpu.h"
 
@@ -210,14 +212,24 @@ void save_levels_file(const char *path, std::size_t nlevels, const LhfdGpuLevel 
     }
   }
   if (with_plans) {
-    for (std::size_t l = 0; l < nlevels; ++l) {
-      for (int upper = 0; upper < 2; ++upper) {
-        const HostCsr T = factor_csr(upper ? lv[l].U_B : lv[l].L_B, lv[l].m, upper ? "U_B" : "L_B");
-        MergeStats    st;
-        const HostCsr S = merged_sweep_form(T, upper != 0, mp, &st);
-        write_plan(w, S, st);
-      }
-    }
+    // the analysis of every factor on its own host thread (as attach_levels does), written in attach order
+    std::vector<MergedFactor>       mf(2 * nlevels);
+    std::vector<std::exception_ptr> errs(2 * nlevels);
+    std::vector<std::thread>        pool;
+    for (std::size_t k = 0; k < 2 * nlevels; ++k)
+      pool.emplace_back([&, k] {
+        try {
+          const bool    upper = (k & 1u) != 0;
+          const HostCsr T     = factor_csr(upper ? lv[k / 2].U_B : lv[k / 2].L_B, lv[k / 2].m, upper ? "U_B" : "L_B");
+          mf[k].S             = merged_sweep_form(T, upper, mp, &mf[k].st);
+        } catch (...) {
+          errs[k] = std::current_exception();
+        }
+      });
+    for (std::thread &t : pool) t.join();
+    for (const std::exception_ptr &e : errs)
+      if (e) std::rethrow_exception(e);
+    for (const MergedFactor &f : mf) write_plan(w, f.S, f.st);
   }
   w.finish();
 }

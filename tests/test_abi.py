@@ -51,6 +51,16 @@ def test_null_handle_is_refused(lib):
     assert b"NULL" in lib.lhfGpuGetErrorMsg()
     out = C.c_void_p()
     assert lib.lhfdGpuAttachLevels(0, 0, None, C.byref(out)) == hb.LHF_NULL_OBJ
+    # the single / mixed precision family and the arena entry points follow the same rule
+    assert lib.lhfsGpuAttachLevels(0, 0, None, C.byref(out)) == hb.LHF_NULL_OBJ
+    assert lib.lhfsGpuSolve(None, p, p) == hb.LHF_NULL_OBJ
+    assert lib.lhfsdGpuSolve(None, p, p) == hb.LHF_NULL_OBJ
+    assert lib.lhfsGpuApply(None, hb.LHF_S, p, 1, None, hb.LHF_DEFAULT_RANK, p, None) == hb.LHF_NULL_OBJ
+    assert lib.lhfsdGpuApply(None, hb.LHF_S, p, 1, None, hb.LHF_DEFAULT_RANK, p, None) == hb.LHF_NULL_OBJ
+    assert lib.lhfsGpuDestroy(None) == hb.LHF_NULL_OBJ
+    assert lib.lhfsGpuAsDouble(None) is None
+    assert lib.lhfdGpuAttachFile(0, None, C.byref(out)) == hb.LHF_NULL_OBJ
+    assert lib.lhfdGpuSaveLevels(1, None, 1, b"/tmp/x.hifb") == hb.LHF_NULL_OBJ
 
 
 def test_level_struct_layout_matches_header():
