@@ -356,6 +356,7 @@ LhfStatus lhfsGpuSetMatrix(LhfsGpuHdl hdl, int is_rowmajor, size_t n, const LhfI
   REQUIRE_HANDLE(hdl);
   REQUIRE_PTR(indptr, "indptr");
   return guarded([&] {
+    if (n != H(hdl)->n0()) throw std::length_error("matrix size does not match the preconditioner");
     const LhfIndPtr nnz = indptr[n];
     if (nnz < 0) throw std::invalid_argument("A: negative nonzero count");
     if (nnz && !vals) throw std::invalid_argument("A: null value array");

@@ -221,6 +221,46 @@ def test_level_merging_shortens_the_dependency_chain(lib, monkeypatch):
         assert depth[("1", name, "bytes")] <= 5 * depth[("0", name, "bytes")], depth  # tiny factor: no cap but gain / row_cap binds
 
 
+REF_SRC = "/root/reference/src"
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(REF_SRC, "hifir.hpp")), reason="reference headers not on this box")
+def test_cxx_adapter_compiles_against_the_reference_headers(tmp_path):
+    """include/hifir_b200.hpp next to the reference's own <hifir.hpp>: the link-time attach overloads for
+    hif::HIF<double,int> and hif::HIF<float,int>, the entry-point-table form and describe() + SaveLevels
+    must compile as C++11 (the reference's language level) -- INTEGRATION.md sections 1, 1b, 1c."""
+    import subprocess
+    src = tmp_path / "adapter_check.cpp"
+    src.write_text('''
+#include <hifir.hpp>
+#include <hifir_b200.hpp>
+int use_double(const hif::HIF<double, int> &M, LhfdGpuHdl *out) { return hifir_b200::attach(M, 0, out); }
+int use_single(const hif::HIF<float, int> &M, LhfsGpuHdl *out) { return hifir_b200::attach(M, 0, out); }
+int use_table(const hif::HIF<float, int> &M, const hifir_b200::AttachApi &api, void **out) {
+  return hifir_b200::attach(M, api, 0, out);
+}
+int save(const hif::HIF<double, int> &M) {
+  std::vector<std::vector<LhfInt>> scratch;
+  auto lv = hifir_b200::describe(M, scratch);
+  return lhfdGpuSaveLevels(lv.size(), lv.data(), 1, "M.hifb");
+}
+''')
+    r = subprocess.run(["g++", "-std=c++11", "-fsyntax-only", "-w", "-I" + REF_SRC, "-I" + os.path.join(ROOT, "include"),
+                        str(src)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+
+
+def test_header_is_plain_c(tmp_path):
+    """include/hifir_b200.h is a C header (extern "C", plain pointers and sizes): it must compile as C99."""
+    import subprocess
+    src = tmp_path / "c_check.c"
+    src.write_text('#include <hifir_b200.h>\nint main(void) { LhfdGpuLevel l; LhfsGpuLevel s; (void)l; (void)s; '
+                   'return (int)LHF_GPU_NUMBER_STATS - 15; }\n')
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-fsyntax-only", "-I" + os.path.join(ROOT, "include"),
+                        str(src)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+
+
 def test_product_never_imports_oracle():
     """The package must not reach into oracle/ (only tests, bench cpu legs and smoke may)."""
     pkg = os.path.join(ROOT, "hifir_b200")
