@@ -165,9 +165,76 @@ def step_rhs(A, n, j, nirs):
     return P.csr_matvec(A, np.sin(0.37 * np.arange(n) + j))
 
 
+def _ref_batched_worker(wid, T, workload, size, nrhs, steps, threads, ready, go, out):
+    """One reference object per worker: hif::HIF is neither copyable (Prec.hpp:134) nor re-entrant
+    (mutable work buffer, builder.hpp:579), so a throughput baseline over independent columns needs T
+    factorized objects."""
+    from hifir_b200 import problems as P
+    os.environ["OMP_NUM_THREADS"] = str(threads)
+    A = make_problem(workload, size)
+    M = factorize(A, threads=threads)
+    cols = list(range(wid, nrhs, T))  # this worker's columns of the block
+    B = P.seeded_rhs(A[0], 0, nrhs=nrhs)
+    bs = [np.ascontiguousarray(B[:, k]) for k in cols]
+    if bs:
+        M.solve(bs[0])
+    ready.put(wid)
+    go.wait()
+    t0 = time.time()
+    for _ in range(steps):
+        for b in bs:
+            M.solve(b)
+    out.put((wid, len(bs) * steps, t0, time.time()))
+
+
+def run_reference_batched(args):
+    """--impl reference --nrhs K: the reference's batched apply is a column loop of hif::HIF::solve (its own
+    multi-rhs driver is defective); with all the host threads it can use that is T
+    objects applying disjoint columns concurrently."""
+    import multiprocessing as mp
+    nproc = os.cpu_count() or 1
+    T = max(1, min(nproc, 8, args.nrhs))
+    threads = max(1, nproc // T)
+    A = make_problem(args.workload, args.size)
+    n = A[0]
+    # a step = one block of nrhs columns; bounded sample of steps (~0.07 s per column at 96^3)
+    steps = max(1, min(args.steps, args.ref_max_steps // max(1, -(-args.nrhs // T)) // 4 or 1))
+    ctx = mp.get_context("spawn")
+    ready, out, go = ctx.Queue(), ctx.Queue(), ctx.Event()
+    ws = [ctx.Process(target=_ref_batched_worker,
+                      args=(w, T, args.workload, args.size, args.nrhs, steps, threads, ready, go, out)) for w in range(T)]
+    for w in ws:
+        w.start()
+    for _ in ws:
+        ready.get()
+    go.set()
+    res = [out.get() for _ in ws]
+    for w in ws:
+        w.join()
+    cols = sum(r[1] for r in res)
+    wall = max(r[3] for r in res) - min(r[2] for r in res)
+    rate = cols / wall
+    sample = (f"{steps} of the {args.steps} requested blocks of {args.nrhs} columns: {T} factorized hif::HIF objects "
+              f"(one per process, {threads} OpenMP thread(s) each for the factorization), each applying its "
+              f"{-(-args.nrhs // T)} columns of the block with hif::HIF::solve; {cols} applies in {wall:.1f} s")
+    line = {
+        "impl": "reference", "metric": "M^-1 applies/sec", "value": rate, "unit": "applies/s", "n_gpus": args.gpus,
+        "steps": steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / steps, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(args.workload, args.size, args.nrhs), "n": n,
+                   "params": "tau=1e-2 alpha=3 kappa=5 (reference PDE set)"},
+        "cpu_baseline": {"value": rate, "unit": "applies/s", "cores": T, "kind": "reference", "sample": sample},
+        "e2e": {"value": rate, "unit": "applies/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
+    if args.nrhs > 1:
+        return run_reference_batched(args)
     A = make_problem(args.workload, args.size)
     n = A[0]
     single = args.precision == "single"
