@@ -123,9 +123,8 @@ def lib():
             "lhfdGpuSpmvDev": [vp, vp, vp],
             "lhfdGpuProfileSolveDev": [vp, vp, vp, sz, sz, vp, vp, vp, sz],
             "lhfdGpuDebugSweepHost": [vp, i, vp, vp, vp, vp],
-            "lhfdGpuDebugTraceSweep": [vp, vp, vp, i, i, vp, sz, vp],
-            "lhfdGpuDebugSimulateSweep": [vp, i, vp, vp],
-            "lhfdGpuDebugBlockGraph": [vp, i, sz, sz, vp, vp, vp, vp],
+            "lhfdGpuDebugPlanLab": [vp, i, vp, vp, vp],
+            "lhfdGpuDebugExportInts": [vp, sz, i, vp, sz, vp],
             "lhfdGpuGetStats": [vp, vp],
             "lhfdGpuGetDepths": [vp, sz, vp],
             "lhfsGpuAttachLevels": [i, sz, vp, vp],
@@ -160,12 +159,14 @@ EXPORTED_SYMBOLS = (
     "lhfdGpuAttachLevels", "lhfdGpuDestroy", "lhfdGpuSetMatrix", "lhfdGpuSetNspConst", "lhfdGpuClearNsp",
     "lhfdGpuSetStream", "lhfdGpuSynchronize", "lhfdGpuSolve", "lhfdGpuApply", "lhfdGpuSolveMrhs",
     "lhfdGpuFgmres", "lhfdGpuGmres", "lhfdGpuApplyDev", "lhfdGpuSolveDev", "lhfdGpuSolveMrhsDev", "lhfdGpuHifirDev",
-    "lhfdGpuSpmvDev", "lhfdGpuProfileSolveDev", "lhfdGpuDebugSweepHost", "lhfdGpuDebugTraceSweep", "lhfdGpuDebugSimulateSweep", "lhfdGpuDebugBlockGraph",
+    "lhfdGpuSpmvDev", "lhfdGpuProfileSolveDev",
     "lhfdGpuGetStats", "lhfdGpuGetDepths", "lhfGpuGetErrorMsg", "lhfGpuVersion",
     "lhfsGpuAttachLevels", "lhfsGpuDestroy", "lhfsGpuAsDouble", "lhfsGpuSetMatrix", "lhfsdGpuUpdate", "lhfsGpuSolve",
-    "lhfsGpuApply", "lhfsdGpuSolve", "lhfsdGpuApply", "lhfsGpuDebugSweepHost",
-    "lhfdGpuSaveLevels", "lhfsGpuSaveLevels", "lhfdGpuAttachFile", "lhfsGpuAttachFile", "lhfGpuFileInfo",
-    "lhfGpuDebugFileSweepHost")
+    "lhfsGpuApply", "lhfsdGpuSolve", "lhfsdGpuApply",
+    "lhfdGpuSaveLevels", "lhfsGpuSaveLevels", "lhfdGpuAttachFile", "lhfsGpuAttachFile", "lhfGpuFileInfo")
+# developer / test hooks declared in hifir_b200/csrc/debug_api.h (not part of the drop-in boundary)
+DEBUG_SYMBOLS = ("lhfdGpuDebugSweepHost", "lhfsGpuDebugSweepHost", "lhfGpuDebugFileSweepHost", "lhfdGpuDebugPlanLab",
+                 "lhfdGpuDebugExportInts")
 
 
 class LhfError(RuntimeError):
@@ -180,8 +181,8 @@ def _chk(st):
 
 
 def debug_sweep_host(block, upper, rhs, diag=None):
-    """Host-only hook (lhfdGpuDebugSweepHost): pack the triangular CCS block into device slabs
-    and solve with them on the CPU.  Returns (x, stats dict)."""
+    """Host-only hook (lhfdGpuDebugSweepHost): merge and pack the triangular CCS block as attach
+    does and solve with the packed data on the CPU.  Returns (x, stats dict)."""
     nr, nc, cs, ri, va = block
     single = np.asarray(va).dtype == np.float32  # float block -> lhfsGpuDebugSweepHost (values stored as float)
     cs = np.ascontiguousarray(cs, dtype=np.int64)
@@ -195,7 +196,7 @@ def debug_sweep_host(block, upper, rhs, diag=None):
     f = lib().lhfsGpuDebugSweepHost if single else lib().lhfdGpuDebugSweepHost
     _chk(f(C.byref(c), int(upper), _ptr(rhs), _ptr(d) if d is not None else None,
                                      _ptr(x), _ptr(st)))
-    return x, dict(zip(("blocks", "halo", "bytes", "max_smem"), (int(v) for v in st)))
+    return x, dict(zip(("slices", "padded", "bytes", "depth"), (int(v) for v in st)))
 
 
 FILE_INFO_NAMES = ("version", "single", "levels", "n", "nnz", "has_plans", "plan_entries", "plan_depth")
@@ -232,39 +233,7 @@ def debug_file_sweep_host(path, level, upper, rhs):
     x = np.zeros_like(rhs)
     st = np.zeros(4, dtype=np.uint64)
     _chk(lib().lhfGpuDebugFileSweepHost(os.fsencode(path), level, int(upper), _ptr(rhs), _ptr(x), _ptr(st)))
-    return x, dict(zip(("blocks", "halo", "bytes", "max_smem"), (int(v) for v in st)))
-
-
-def debug_simulate_sweep(block, upper, slots=296, threads=448, t_load=1.7, c_s=0.15, c_g=1.0, t_dep=0.08,
-                         t_pub=0.05):
-    """Host-only timing model of one sweep (lhfdGpuDebugSimulateSweep); microseconds."""
-    nr, nc, cs, ri, va = block
-    cs = np.ascontiguousarray(cs, dtype=np.int64)
-    ri = np.ascontiguousarray(ri, dtype=np.int32)
-    va = np.ascontiguousarray(va, dtype=np.float64)
-    c = LhfdGpuCcs(nr, nc, _ptr(cs), _ptr(ri), _ptr(va))
-    prm = np.array([slots, threads, t_load, c_s, c_g, t_dep, t_pub], dtype=np.float64)
-    out = np.zeros(8)
-    _chk(lib().lhfdGpuDebugSimulateSweep(C.byref(c), int(upper), _ptr(prm), _ptr(out)))
-    return dict(zip(("total", "life_sum", "life_max", "halo_wait", "tail", "blocks", "merged_depth", "slab_bytes"),
-                    out[:8]))
-
-
-def debug_block_graph(block, upper, max_blocks=1 << 16, max_edges=1 << 24):
-    """Host-only: (info[nb,4] = s0, rows, nhalo, nnz ; src_ptr ; src_idx) of the packed sweep."""
-    nr, nc, cs, ri, va = block
-    cs = np.ascontiguousarray(cs, dtype=np.int64)
-    ri = np.ascontiguousarray(ri, dtype=np.int32)
-    va = np.ascontiguousarray(va, dtype=np.float64)
-    c = LhfdGpuCcs(nr, nc, _ptr(cs), _ptr(ri), _ptr(va))
-    info = np.zeros(max_blocks * 4, dtype=np.uint32)
-    sp = np.zeros(max_blocks + 1, dtype=np.uint32)
-    sx = np.zeros(max_edges, dtype=np.uint32)
-    nb = C.c_size_t()
-    _chk(lib().lhfdGpuDebugBlockGraph(C.byref(c), int(upper), max_blocks, max_edges, _ptr(info), _ptr(sp), _ptr(sx),
-                                      C.byref(nb)))
-    n = nb.value
-    return info[: 4 * n].reshape(n, 4), sp[: n + 1], sx[: sp[n]]
+    return x, dict(zip(("slices", "padded", "bytes", "depth"), (int(v) for v in st)))
 
 
 class GpuHif:
@@ -431,13 +400,16 @@ class GpuHif:
         labels = names.value.decode().split("\n")
         return [(labels[k], float(ms[k])) for k in range(cnt.value)]
 
-    def trace_sweep(self, d_b, d_x, level, which, max_blocks=1 << 16):
-        """per-block trace of one sweep: array [nblocks, 8] (see lhfdGpuDebugTraceSweep)"""
-        out = np.zeros(max_blocks * 8, dtype=np.uint64)
-        nb = C.c_size_t()
-        _chk(lib().lhfdGpuDebugTraceSweep(self._h, C.c_void_p(d_b), C.c_void_p(d_x), level, which, _ptr(out),
-                                          max_blocks, C.byref(nb)))
-        return out[: nb.value * 8].reshape(-1, 8)
+    def export_ints(self, level, which):
+        """lhfdGpuDebugExportInts: a device-resident index array of one level, copied back
+        (which: 'p', 'q_inv', 'E_ptr', 'E_col', 'F_ptr', 'F_col', 'jpvt')"""
+        sel = ("p", "q_inv", "E_ptr", "E_col", "F_ptr", "F_col", "jpvt").index(which)
+        cnt = C.c_size_t()
+        dummy = np.zeros(1, dtype=np.int32)
+        _chk(lib().lhfdGpuDebugExportInts(self._h, level, sel, _ptr(dummy), 0, C.byref(cnt)))
+        out = np.zeros(max(1, cnt.value), dtype=np.int32)
+        _chk(lib().lhfdGpuDebugExportInts(self._h, level, sel, _ptr(out), out.size, C.byref(cnt)))
+        return out[: cnt.value]
 
     def spmv_dev(self, d_x, d_y):
         _chk(lib().lhfdGpuSpmvDev(self._h, C.c_void_p(d_x), C.c_void_p(d_y)))

@@ -60,36 +60,16 @@ __global__ void spmv_resid_kernel(const unsigned nrows, const unsigned *__restri
   if (row < nrows && lane == 0) out[row] = base[row] - acc;
 }
 
-// out[rowmap[u]] = base[rowmap[u]] - sum_j A(u,j) x[j] for the compact rows u of the split
-// forward sweep (x = tagged results of the lower blocks, all finished); 8 lanes per row
-__global__ void spmv_rows_kernel(const unsigned nu, const unsigned m, const unsigned *__restrict__ ptr,
-                                 const int *__restrict__ col, const double *__restrict__ val,
-                                 const unsigned long long *__restrict__ x, const unsigned *__restrict__ rowmap,
-                                 const double *__restrict__ base, double *__restrict__ out) {
-  const unsigned gid = blockIdx.x * blockDim.x + threadIdx.x, u = gid >> 3, lane = gid & 7u;
-  double         acc = 0.0;
-  if (u < nu) {
-    const unsigned e = ptr[u + 1];
-    for (unsigned k = ptr[u] + lane; k < e; k += 8) acc = fma(val[k], tag_value(x[col[k]]), acc);
-  }
-#pragma unroll
-  for (int o = 4; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-  if (u < nu && lane == 0) {  // rowmap = row codes (hifgpu.h): out is indexed by solution slot
-    const unsigned code = rowmap[u], slot = code & kCodeSlotMask;
-    const double   b    = (code & kCodeZeroRhs) ? 0.0 : base[slot >= m ? slot - m : slot];
-    out[slot]           = b - acc;
-  }
-}
-
 // y[i] = t[i] * [xU; ychild][q_inv[i]]   (prec_solve.hpp:392, 411)
-__global__ void scatter_scale_kernel(const unsigned n, const unsigned m, const int *__restrict__ q_inv,
+// q_slot = q_inv mapped at attach: >= 0 -> solution slot of the U sweep, < 0 -> entry -q-1 of ychild
+__global__ void scatter_scale_kernel(const unsigned n, const int *__restrict__ q_slot,
                                      const double *__restrict__ t, const unsigned long long *__restrict__ xU,
                                      const double *__restrict__ ychild, double *__restrict__ y) {
   const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) {
-    const unsigned j = static_cast<unsigned>(q_inv[i]);
-    const double   w = j < m ? tag_value(xU[j]) : ychild[j - m];
-    y[i]             = t[i] * w;
+    const int    j = q_slot[i];
+    const double w = j >= 0 ? tag_value(xU[j]) : ychild[-j - 1];
+    y[i]           = t[i] * w;
   }
 }
 
@@ -223,41 +203,30 @@ void mark(Handle *h, const std::string &name) {
 }
 
 void launch_sweeps(Handle *h, DevLevel &D, const double *rhs, unsigned long long *xL, unsigned long long *xU,
-                   unsigned parity, int *tickets, const std::string &tag, int trace_base) {
+                   unsigned parity, int *tickets, const std::string &tag) {
   if (!D.m) return;
-  const bool tl = h->trace_level >= 0 && &h->levels[h->trace_level] == &D;
-  // forward sweep, split: closed subtrees, SpMV with their results, top of the tree
-  launch_sweep(h, D.L, rhs, nullptr, nullptr, xL, parity, tickets,
-               tl && h->trace_which == trace_base ? h->trace_buf.p : nullptr);
-  if (D.L_up.nblocks) {
-    const unsigned nu = static_cast<unsigned>(D.L_ul.nrows);
-    spmv_rows_kernel<<<cdiv(static_cast<std::size_t>(nu) * 8, 256), 256, 0, h->stream>>>(
-        nu, static_cast<unsigned>(D.m), D.L_ul.ptr.p, D.L_ul.col.p, D.L_ul.val.p, xL, D.L_urows.p, rhs, D.rhs_u.p);
-    HIF_KERNEL_CHECK();
-    launch_sweep(h, D.L_up, D.rhs_u.p, nullptr, nullptr, xL, parity, tickets + 4 * h->tick_stride);
-    h->launch_count += 1;
-  }
+  launch_sweep(h, D.L, rhs, nullptr, nullptr, xL, parity, tickets);
   mark(h, tag + "L");
-  launch_sweep(h, D.U, nullptr, xL, D.d.p, xU, parity, tickets + h->tick_stride,
-               tl && h->trace_which == trace_base + 1 ? h->trace_buf.p : nullptr);
+  // the U sweep reads x_L at the L sweep's slots and divides by d (permuted to those slots)
+  launch_sweep(h, D.U, nullptr, xL, D.d_ls.p, xU, parity, tickets + h->tick_stride);
   mark(h, tag + "U");
 }
 
 template <bool TAGGED>
-void launch_spmv_resid(Handle *h, const DevCsr &A, const void *x, const double *base, double *out,
+void launch_spmv_resid(Handle *h, const DevCsr &A, const int *col, const void *x, const double *base, double *out,
                        const std::string &tag) {
   if (!A.nrows) return;
   const double avg = A.nrows ? static_cast<double>(A.nnz) / static_cast<double>(A.nrows) : 0.0;
   constexpr int T  = 256;
   if (avg > 12.0) {
     spmv_resid_kernel<8, TAGGED><<<cdiv(A.nrows * 8, T), T, 0, h->stream>>>(
-        static_cast<unsigned>(A.nrows), A.ptr.p, A.col.p, A.val.p, x, base, out);
+        static_cast<unsigned>(A.nrows), A.ptr.p, col, A.val.p, x, base, out);
   } else if (avg > 3.0) {
     spmv_resid_kernel<4, TAGGED><<<cdiv(A.nrows * 4, T), T, 0, h->stream>>>(
-        static_cast<unsigned>(A.nrows), A.ptr.p, A.col.p, A.val.p, x, base, out);
+        static_cast<unsigned>(A.nrows), A.ptr.p, col, A.val.p, x, base, out);
   } else {
     spmv_resid_kernel<1, TAGGED><<<cdiv(A.nrows, T), T, 0, h->stream>>>(static_cast<unsigned>(A.nrows), A.ptr.p,
-                                                                        A.col.p, A.val.p, x, base, out);
+                                                                        col, A.val.p, x, base, out);
   }
   HIF_KERNEL_CHECK();
   mark(h, tag);
@@ -287,9 +256,8 @@ void apply_dev(Handle *h, const double *d_b, double *d_x, std::size_t rank) {
       ++h->launch_count;
     }
     if (D.nm) {
-      launch_sweeps(h, D, D.bhat.p, D.xL_dn.p, D.xU_dn.p, parity, h->tick(8 * l),
-                    "lv" + std::to_string(l) + ".down.", 0);
-      launch_spmv_resid<true>(h, D.E, D.xU_dn.p, D.bhat.p + D.m, D.r.p, "lv" + std::to_string(l) + ".E");
+      launch_sweeps(h, D, D.bhat.p, D.xL_dn.p, D.xU_dn.p, parity, h->tick(8 * l), "lv" + std::to_string(l) + ".down.");
+      launch_spmv_resid<true>(h, D.E, D.E_xcol.p, D.xU_dn.p, D.bhat.p + D.m, D.r.p, "lv" + std::to_string(l) + ".E");
       b = D.r.p;
     }
   }
@@ -305,14 +273,13 @@ void apply_dev(Handle *h, const double *d_b, double *d_x, std::size_t rank) {
     double *      y      = l == 0 ? d_x : h->levels[l - 1].ychild.p;
     const double *rhs    = D.bhat.p;
     if (D.nm && D.F.nnz) {
-      launch_spmv_resid<false>(h, D.F, D.ychild.p, D.bhat.p, D.g.p, "lv" + std::to_string(l) + ".F");
+      launch_spmv_resid<false>(h, D.F, D.F.col.p, D.ychild.p, D.bhat.p, D.g.p, "lv" + std::to_string(l) + ".F");
       rhs = D.g.p;
     }
-    launch_sweeps(h, D, rhs, D.xL_up.p, D.xU_up.p, parity, h->tick(8 * l + 2),
-                  "lv" + std::to_string(l) + ".up.", 2);
+    launch_sweeps(h, D, rhs, D.xL_up.p, D.xU_up.p, parity, h->tick(8 * l + 2), "lv" + std::to_string(l) + ".up.");
     if (D.n) {
-      scatter_scale_kernel<<<cdiv(D.n, T), T, 0, h->stream>>>(static_cast<unsigned>(D.n), static_cast<unsigned>(D.m),
-                                                             D.q_inv.p, D.t.p, D.xU_up.p, D.ychild.p, y);
+      scatter_scale_kernel<<<cdiv(D.n, T), T, 0, h->stream>>>(static_cast<unsigned>(D.n), D.q_slot.p, D.t.p,
+                                                             D.xU_up.p, D.ychild.p, y);
       HIF_KERNEL_CHECK();
       mark(h, "lv" + std::to_string(l) + ".scatter");
       ++h->launch_count;
@@ -453,7 +420,7 @@ void dense_multiply_dev(Handle *h, const double *d_in, double *d_out, std::size_
 
 void launch_ldu_solve(Handle *h, DevLevel &D, const double *rhs, unsigned long long *xL, unsigned long long *xU,
                       unsigned parity, int *tickets) {
-  launch_sweeps(h, D, rhs, xL, xU, parity, tickets, "prod.", 100);
+  launch_sweeps(h, D, rhs, xL, xU, parity, tickets, "prod.");
 }
 
 void launch_dense_trsv_cols(Handle *h, unsigned nm, unsigned rk, const double *c, double *out, unsigned ncols) {

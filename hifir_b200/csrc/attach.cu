@@ -124,6 +124,7 @@ Handle *attach_levels(int device, std::size_t nlevels, const LhfdGpuLevel *lv, b
 
   std::unique_ptr<Handle> h(new Handle());
   h->device = device;
+  HIF_CUDA(cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device));
   h->f32    = f32;
   HIF_CUDA(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
   h->stream = h->own_stream;
@@ -222,24 +223,40 @@ Handle *attach_levels(int device, std::size_t nlevels, const LhfdGpuLevel *lv, b
     HostCsr &Lr = Lrs[l], &Ur = Urs[l], &Er = Ers[l], &Fr = Frs[l];
     const std::string tag = "level " + std::to_string(l);
 
-    D.L.f32 = D.U.f32 = f32;  // streamed sweep values in single precision (stream.cu)
-    {
-      HostCsr               ul;
-      std::vector<unsigned> urows;
-      build_split_plans(Lr, D.L, D.L_up, ul, urows, tally);
-      upload_csr(ul, D.L_ul, tally);
-      D.L_urows.upload(urows, tally);
-      D.rhs_u.alloc(2 * P.m, tally);
-    }
-    build_sweep_plan(Ur, true, D.U, tally);
+    D.L.f32 = D.U.f32 = f32;  // streamed sweep values in single precision
+    // L first: the U sweep reads its right-hand side (L's tagged result) at L's solution slots
+    build_sweep_plan(Lr, false, D.L, tally, h->num_sms);
+    build_sweep_plan(Ur, true, D.U, tally, h->num_sms, D.L.slot_of.empty() ? nullptr : D.L.slot_of.data());
     if (std::getenv("HIFIR_B200_VERBOSE")) {
       for (const SweepPlan *pl : {&D.L, &D.U})
         std::fprintf(stderr,
                      "[hifir_b200] level %zu %s: rows %zu nnz %zu depth %zu -> merged rows %zu nnz %zu depth %zu "
-                     "(super levels %zu); stream: slices %u chunks %u padded %zu bytes %.1f MB\n",
+                     "(steps %zu); packed: slices %u depth %zu padded %zu bytes %.1f MB\n",
                      l, pl->upper ? "U" : "L", pl->merge.rows, pl->merge.nnz, pl->merge.depth, pl->merge.ext_rows,
-                     pl->merge.ext_nnz, pl->merge.ext_depth, pl->merge.super_levels, pl->nblocks, pl->st_chunks,
+                     pl->merge.ext_nnz, pl->merge.ext_depth, pl->merge.super_levels, pl->nblocks, pl->st_depth,
                      pl->st_padded, pl->slab_bytes / 1e6);
+    }
+    {
+      // consumers of the renumbered solution slots
+      std::vector<unsigned> ls(P.m), us(P.m);
+      for (std::size_t r = 0; r < P.m; ++r) {
+        ls[r] = D.L.slot_of.empty() ? static_cast<unsigned>(r) : D.L.slot_of[r];
+        us[r] = D.U.slot_of.empty() ? static_cast<unsigned>(r) : D.U.slot_of[r];
+      }
+      std::vector<double> dls(2 * P.m, 1.0);
+      for (std::size_t r = 0; r < P.m; ++r) dls[ls[r]] = P.d_B[r];
+      D.d_ls.upload(dls, tally);
+      std::vector<int> xc(Er.col.size());
+      for (std::size_t k = 0; k < xc.size(); ++k) xc[k] = static_cast<int>(us[Er.col[k]]);
+      D.E_xcol.upload(xc, tally);
+      std::vector<int> qs(P.n);
+      for (std::size_t i = 0; i < P.n; ++i) {
+        const std::size_t j = static_cast<std::size_t>(P.q_inv[i]);
+        qs[i] = j < P.m ? static_cast<int>(us[j]) : -static_cast<int>(j - P.m) - 1;  // < 0: entry of ychild
+      }
+      D.q_slot.upload(qs, tally);
+      D.L_slot.upload(ls, tally);
+      D.U_slot.upload(us, tally);
     }
     D.L.nnz = Lr.col.size();
     D.U.nnz = Ur.col.size();

@@ -4,6 +4,7 @@
 #include <memory>
 #include <new>
 
+#include "debug_api.h"
 #include "hifgpu.h"
 
 using namespace hifgpu;
@@ -519,6 +520,18 @@ LhfStatus lhfdGpuDebugSweepHost(const LhfdGpuCcs *T, int upper, const double *rh
   });
 }
 
+LhfStatus lhfdGpuDebugPlanLab(const LhfdGpuCcs *T, int upper, const int *key, const double *opts, double *out) {
+  REQUIRE_PTR(T, "T");
+  REQUIRE_PTR(opts, "opts");
+  REQUIRE_PTR(out, "out");
+  return guarded([&] {
+    HostCsr R = ccs_to_csr(*T, "T");
+    R.nrows = R.ncols = T->ncols;
+    R.ptr.resize(T->ncols + 1, R.ptr.empty() ? 0u : R.ptr.back());
+    plan_lab(R, upper != 0, key, opts, out);
+  });
+}
+
 // ---- factor arena files (arena.cu) ----
 
 LhfStatus lhfdGpuSaveLevels(size_t nlevels, const LhfdGpuLevel *levels, int with_plans, const char *path) {
@@ -610,62 +623,33 @@ LhfStatus lhfsGpuDebugSweepHost(const LhfsGpuCcs *T, int upper, const double *rh
   });
 }
 
-LhfStatus lhfdGpuDebugTraceSweep(LhfdGpuHdl hdl, const double *d_b, double *d_x, int level, int which,
-                                 unsigned long long *out, size_t max_blocks, size_t *nblocks) {
+LhfStatus lhfdGpuDebugExportInts(LhfdGpuHdl hdl, size_t level, int which, int *out, size_t max, size_t *count) {
   REQUIRE_HANDLE(hdl);
   REQUIRE_PTR(out, "out");
-  REQUIRE_PTR(nblocks, "nblocks");
+  REQUIRE_PTR(count, "count");
   return guarded([&] {
     Handle *h = H(hdl);
-    if (level < 0 || static_cast<size_t>(level) >= h->levels.size() || which < 0 || which > 3)
-      throw std::invalid_argument("bad level / sweep selector");
-    const SweepPlan &plan = (which & 1) ? h->levels[level].U : h->levels[level].L;
-    if (h->trace_buf.n < 8ull * plan.nblocks) h->trace_buf.alloc(8ull * plan.nblocks);
-    HIF_CUDA(cudaMemsetAsync(h->trace_buf.p, 0, h->trace_buf.n * 8, h->stream));
-    h->trace_level = level;
-    h->trace_which = which;
-    try {
-      apply_dev(h, d_b, d_x, 0);
-      check_sweep_error(h);
-    } catch (...) {
-      h->trace_level = h->trace_which = -1;
-      throw;
+    HIF_CUDA(cudaSetDevice(h->device));
+    const void *src = nullptr;
+    std::size_t n   = 0;
+    if (which == 6) {
+      src = h->dense.jpvt.p, n = h->dense.jpvt.n;
+    } else {
+      if (level >= h->levels.size()) throw std::invalid_argument("no such level");
+      const DevLevel &D = h->levels[level];
+      switch (which) {
+        case 0: src = D.p.p, n = D.p.n; break;
+        case 1: src = D.q_inv.p, n = D.q_inv.n; break;
+        case 2: src = D.E.ptr.p, n = D.E.ptr.n; break;
+        case 3: src = D.E.col.p, n = D.E.col.n; break;
+        case 4: src = D.F.ptr.p, n = D.F.ptr.n; break;
+        case 5: src = D.F.col.p, n = D.F.col.n; break;
+        default: throw std::invalid_argument("bad array selector");
+      }
     }
-    h->trace_level = h->trace_which = -1;
-    const size_t nb = std::min<size_t>(plan.nblocks, max_blocks);
-    HIF_CUDA(cudaMemcpy(out, h->trace_buf.p, nb * 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
-    *nblocks = nb;
-  });
-}
-
-LhfStatus lhfdGpuDebugSimulateSweep(const LhfdGpuCcs *T, int upper, const double *prm, double *out) {
-  REQUIRE_PTR(T, "T");
-  REQUIRE_PTR(prm, "prm");
-  REQUIRE_PTR(out, "out");
-  return guarded([&] {
-    HostCsr R = ccs_to_csr(*T, "T");
-    R.nrows = R.ncols = T->ncols;
-    R.ptr.resize(T->ncols + 1, R.ptr.empty() ? 0u : R.ptr.back());
-    sweep_simulate(R, upper != 0, prm, out);
-  });
-}
-
-LhfStatus lhfdGpuDebugBlockGraph(const LhfdGpuCcs *T, int upper, size_t max_blocks, size_t max_edges,
-                                 unsigned *info, unsigned *src_ptr, unsigned *src_idx, size_t *nblocks) {
-  REQUIRE_PTR(T, "T");
-  REQUIRE_PTR(nblocks, "nblocks");
-  return guarded([&] {
-    HostCsr R = ccs_to_csr(*T, "T");
-    R.nrows = R.ncols = T->ncols;
-    R.ptr.resize(T->ncols + 1, R.ptr.empty() ? 0u : R.ptr.back());
-    std::vector<unsigned> vi, vp, vx;
-    sweep_block_graph(R, upper != 0, vi, vp, vx);
-    const size_t nb = vp.size() - 1;
-    if (nb > max_blocks || vx.size() > max_edges) throw std::length_error("block graph exceeds the output buffers");
-    std::copy(vi.begin(), vi.end(), info);
-    std::copy(vp.begin(), vp.end(), src_ptr);
-    std::copy(vx.begin(), vx.end(), src_idx);
-    *nblocks = nb;
+    *count = n;
+    HIF_CUDA(cudaStreamSynchronize(h->stream));
+    if (n && max) HIF_CUDA(cudaMemcpy(out, src, std::min(n, max) * sizeof(int), cudaMemcpyDeviceToHost));
   });
 }
 
@@ -689,8 +673,8 @@ LhfStatus lhfdGpuGetStats(LhfdGpuHdl hdl, size_t stats[]) {
   std::size_t dm = 0, sb = 0, se = 0;
   for (const auto &D : h->levels) {
     const std::size_t k = D.nm ? 2 : 1;
-    for (const SweepPlan *p : {&D.L, &D.L_up, &D.U}) {
-      dm += k * (p->stream ? p->st_depth : 0);
+    for (const SweepPlan *p : {&D.L, &D.U}) {
+      dm += k * p->st_depth;
       sb += k * p->slab_bytes;
     }
     se += k * ((D.L.merge.ext_nnz ? D.L.merge.ext_nnz : D.L.nnz) + (D.U.merge.ext_nnz ? D.U.merge.ext_nnz : D.U.nnz));

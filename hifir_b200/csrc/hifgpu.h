@@ -90,6 +90,9 @@ struct MergeParams {
   int      alap      = 1;         // as-late-as-possible level sets: 0 never, 1 fan-out sweeps (U: leaves last), 2 always
   double   sl_cap    = 300000.0;  // a super level stops growing at this many entries: beyond, its two
                                   // steps are throughput bound and more fill only costs (measured optimum 4e5-8e5)
+  bool     slack     = false;     // slack-aware merging (merge_slack): only rows pinned to the critical core pay fill
+  unsigned steps     = 0;         // > 0: proportional scheduling into this many steps (merge_prop)
+  bool     chain_all = true;      // chain every row (not only the pinned ones) to the t rows of the previous step
   static MergeParams from_env();
 };
 struct MergeStats {
@@ -129,11 +132,10 @@ struct ArenaFile {  // an arena file read back: the level description (+ plans) 
 struct Handle;
 Handle *attach_file(int device, const char *path, bool want_f32);
 
-// a strictly triangular factor cut into shared-memory sized slabs (sptrsv.cu)
+// a strictly triangular factor prepared for the device sweeps
 struct SweepPlan {
-  unsigned               m = 0, nblocks = 0, smem_bytes = 0, nr = 1;  // nr: right-hand sides per slot
+  unsigned               m = 0, nblocks = 0, nr = 1;  // nblocks: slices; nr: right-hand sides per slot
   bool                   upper = false;
-  bool                   rhs_by_slot = false;  // right-hand side indexed by the row's slot (split sweep, top rows)
   MergeStats             merge;
   // level-major streaming layout (stream.cu); nblocks = number of 32-row slices
   bool                        stream = false;
@@ -147,22 +149,26 @@ struct SweepPlan {
   DevBuf<double>              st_vals;
   bool                        f32 = false;  // factor values stored in single precision (st_vals32 instead of st_vals)
   DevBuf<float>               st_vals32;
-  std::size_t            slab_bytes = 0, halo_total = 0, nnz = 0;
-  DevBuf<unsigned char>  slabs;  // packed slabs
-  DevBuf<unsigned char>  info;   // SlabInfo[nblocks]
+  // warp-stream layout (wsweep.cu): one private segment stream per warp of a persistent CTA per SM
+  bool                        ws = false;
+  unsigned                    ws_grid = 0, ws_warps = 0, ws_stages = 0, ws_window = 0, ws_nslots = 0;
+  DevBuf<unsigned>            ws_wdesc;   // 8 words per global warp: offset (16 B units), segments, -, -, first 4 sizes
+  DevBuf<unsigned>            ws_stream;  // segments
+  std::vector<unsigned>       slot_of;    // host: solution slot of every original row (empty: identity)
+  std::size_t            slab_bytes = 0, nnz = 0;  // slab_bytes: bytes the sweep streams
 };
 
 // one hif::Prec level on the device (reference alg/Prec.hpp:309-323)
 struct DevLevel {
   std::size_t m = 0, n = 0, nm = 0;
-  SweepPlan   L, U;  // L_B, U_B as slabs (L = rows of small closed subtrees when the sweep is split)
-  // split forward sweep: x_l = L_ll^{-1} b_l ; r_u = b_u - L_ul x_l ; x_u = L_uu^{-1} r_u
-  SweepPlan        L_up;     // L_uu over the upper rows (empty plan when there are none)
-  DevCsr           L_ul;     // compact rows (one per upper row) x all columns
-  DevBuf<unsigned> L_urows;  // global row index of each compact row
-  DevBuf<double>   rhs_u;    // m, right-hand side of the upper sweep
+  SweepPlan   L, U;  // L_B, U_B
   DevCsr      E, F;
   DevBuf<double> d;        // m
+  // consumers of the sweeps' renumbered solution slots (wsweep.cu): built once at attach
+  DevBuf<double> d_ls;     // d permuted to the slots of the L sweep (the U sweep divides its right-hand side)
+  DevBuf<int>    E_xcol;   // E.col mapped to the slots of the U sweep
+  DevBuf<int>    q_slot;   // q_inv mapped: < nslots(U) -> slot of the U sweep, else nslots + (q_inv - m)
+  DevBuf<unsigned> L_slot, U_slot;  // slot of every original row (indirection for the off-path kernels)
   DevBuf<double> s, t;     // n
   DevBuf<int>    p, q_inv; // n
   // triangular-sweep schedule
@@ -210,7 +216,7 @@ struct DevMatrix {  // user matrix A in CRS
 };
 
 struct Handle {
-  int                   device = 0;
+  int                   device = 0, num_sms = 148;
   std::vector<DevLevel> levels;
   DevDense              dense;
   DevMatrix             A;
@@ -252,8 +258,6 @@ struct Handle {
   std::size_t bytes_factors = 0, bytes_vec = 0, bytes_dense = 0, device_bytes = 0, nnz_total = 0;
   std::size_t kernels_per_apply = 0, launch_count = 0;
   // optional per-kernel timing of one apply (lhfdGpuProfileSolveDev)
-  int                                   trace_level = -1, trace_which = -1;  // debug: which sweep to trace
-  DevBuf<unsigned long long>            trace_buf;
   bool                                  profiling = false;
   std::vector<std::pair<std::string, cudaEvent_t>> prof_marks;
   std::size_t n0() const { return levels.empty() ? 0 : levels[0].n; }
@@ -268,25 +272,24 @@ void    set_matrix(Handle *h, bool rowmajor, std::size_t n, const LhfIndPtr *ind
                    const double *vals);
 HostCsr ccs_to_csr(const LhfdGpuCcs &c, const char *name);
 
-// ---- sptrsv.cu : block sync-free triangular sweeps
-void build_sweep_plan(const HostCsr &T, bool upper, SweepPlan &plan, std::size_t *tally, unsigned nr = 1);
+// ---- sweep.cu : plan construction / launch dispatch of the triangular sweeps
+// kind: 2 = warp streams (wsweep.cu), 1 = round-1 streaming kernel (stream.cu), -1 = HIFIR_B200_SWEEP
+// nsm = SMs of the device the plan is built for; rhs_index (nullable) = position of original row r in
+// the sweep's right-hand side array (the U sweep reads the L sweep's result at the L plan's slots)
+void build_sweep_plan(const HostCsr &T, bool upper, SweepPlan &plan, std::size_t *tally, unsigned nsm,
+                      const unsigned *rhs_index = nullptr, int kind = -1);
 void sweep_host_emulate(const HostCsr &T, bool upper, const double *rhs, const double *diag, double *x,
                         std::size_t stats[4], bool f32 = false);
-void sweep_block_graph(const HostCsr &T, bool upper, std::vector<unsigned> &info, std::vector<unsigned> &src_ptr,
-                       std::vector<unsigned> &src_idx);
-void build_split_plans(const HostCsr &T, SweepPlan &plan_lo, SweepPlan &plan_up, HostCsr &ul,
-                       std::vector<unsigned> &urows, std::size_t *tally);
-void sweep_simulate(const HostCsr &T, bool upper, const double *prm, double *out);
-bool stream_sweeps();  // HIFIR_B200_SWEEP=stream (default) | slab
+void launch_sweep(Handle *h, const SweepPlan &plan, const double *rhs_plain, const unsigned long long *rhs_tagged,
+                  const double *diag, unsigned long long *x, unsigned parity, int *sync,
+                  unsigned nr = 0);  // nr = 0: the plan's own width
+// ---- stream.cu
 void build_stream_plan(const HostCsr &S, bool upper, SweepPlan &plan, std::size_t *tally);
 void stream_host_emulate(const HostCsr &S, bool upper, const double *rhs, const double *diag, double *x,
                          std::size_t stats[4], bool f32 = false);
 void launch_stream_sweep(Handle *h, const SweepPlan &plan, const double *rhs_plain,
                          const unsigned long long *rhs_tagged, const double *diag, unsigned long long *x,
                          unsigned parity, int *ticket, unsigned long long *trace = nullptr, unsigned nr = 1);
-void launch_sweep(Handle *h, const SweepPlan &plan, const double *rhs_plain, const unsigned long long *rhs_tagged,
-                  const double *diag, unsigned long long *x, unsigned parity, int *ticket,
-                  unsigned long long *trace = nullptr, unsigned nr = 0);  // nr = 0: the plan's own width
 
 // ---- apply.cu : the multilevel M^{-1} apply on device vectors
 void apply_dev(Handle *h, const double *d_b, double *d_x, std::size_t rank);
@@ -308,6 +311,28 @@ void   hifir_betas_dev(Handle *h, const double *d_b, std::size_t nirs, const dou
 void   krylov_dev(Handle *h, bool flexible, const double *d_b, int restart, double rtol, int maxit,
                   bool full_rank, double *d_x, int *flag, int *iters, int *num_mv);
 double norm2_dev(Handle *h, const double *d_v, std::size_t n);
+
+// ---- wsweep.cu : statically scheduled warp-stream sweeps
+struct WsHost {  // packed plan on the host
+  unsigned                           nwarps = 0, nslots = 0, depth = 0, slices = 0;
+  std::vector<unsigned>              wdesc, stream, slot_of, order;  // order: (warp, absolute word offset) in creation order
+  std::vector<std::vector<unsigned>> seg_off;                        // per warp: word offsets of its segments (private stream)
+  std::size_t                        entries = 0, padded = 0, copy_rows = 0, max_segs = 0;
+};
+void pack_warp_streams(const HostCsr &S, WsHost &H, unsigned nwarps, unsigned window, bool f32,
+                       const unsigned *rhs_index);
+void ws_finalize_ring(WsHost &H, unsigned stages);
+void ws_host_emulate_packed(const WsHost &H, bool upper, bool f32, const double *rhs, const double *diag, double *x);
+void build_ws_plan(const HostCsr &S, bool upper, SweepPlan &plan, std::size_t *tally, unsigned nsm,
+                   const unsigned *rhs_index);
+void ws_host_emulate(const HostCsr &S, bool upper, const double *rhs, const double *diag, double *x_by_row,
+                     std::size_t stats[4], bool f32);
+void launch_ws_sweep(Handle *h, const SweepPlan &plan, const double *rhs_plain, const unsigned long long *rhs_tagged,
+                     const double *diag, unsigned long long *x, unsigned parity, int *sync);
+int  sweep_kind();  // HIFIR_B200_SWEEP = ws (default) | stream | slab  ->  2 | 1 | 0
+
+// ---- planlab.cu (developer tool, host only)
+void plan_lab(const HostCsr &Tnat, bool upper, const int *user_key, const double *opts, double *out);
 
 // ---- mrhs.cu
 void apply_mrhs_dev(Handle *h, std::size_t nrhs, const double *d_B, double *d_X, std::size_t rank);

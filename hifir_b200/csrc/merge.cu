@@ -22,6 +22,7 @@
 // (the inverse-based dropping of HIF bounds ||L^{-1}||, ||U^{-1}|| by kappa, so the diagonal
 // blocks W are well conditioned).
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 #include <stdexcept>
 
@@ -39,6 +40,9 @@ MergeParams MergeParams::from_env() {
   if (const char *e = std::getenv("HIFIR_B200_MERGE_SLCAP")) p.sl_cap = std::atof(e);
   if (const char *e = std::getenv("HIFIR_B200_MERGE_ALAP")) p.alap = std::atoi(e);
   if (const char *e = std::getenv("HIFIR_B200_MERGE_CHAIN")) p.chain = std::atoi(e) != 0;
+  if (const char *e = std::getenv("HIFIR_B200_MERGE_SLACK")) p.slack = std::atoi(e) != 0;
+  if (const char *e = std::getenv("HIFIR_B200_MERGE_CHAINALL")) p.chain_all = std::atoi(e) != 0;
+  if (const char *e = std::getenv("HIFIR_B200_MERGE_STEPS")) p.steps = static_cast<unsigned>(std::atoi(e));
   return p;
 }
 
@@ -110,9 +114,380 @@ static unsigned depth_alap(const HostCsr &S, std::vector<unsigned> &lev) {
   return depth;
 }
 
+// The merged system for a given step assignment: rows interleaved [.., t_i, x_i, ..] in the original
+// sweep order.  step[] is monotone along dependencies; a row with wlen > 0 is PINNED (it has producers
+// in its own step and carries the row wcol/wval of W^{-1} - I over the t unknowns of its step).
+static HostCsr emit_merged(const HostCsr &S, const MergeParams &prm, MergeStats *st, const std::vector<unsigned> &step,
+                           const std::vector<char> &pinned, const std::vector<std::size_t> &wbeg,
+                           const std::vector<unsigned> &wlen, const std::vector<unsigned> &wcol,
+                           const std::vector<double> &wval, unsigned nsteps) {
+  const unsigned m = static_cast<unsigned>(S.nrows);
+  // ---- the merged system, rows interleaved [.., t_i, x_i, ..] in the original sweep order
+  HostCsr E;
+  E.orig_rows = m;
+  E.ptr.push_back(0u);
+  std::vector<unsigned> xpos(m), tpos(m);
+  std::vector<double>   cacc;
+  std::vector<unsigned> cstamp, ctouched;
+  unsigned              ccur = 0;
+  if (prm.chain) {
+    cacc.assign(2 * static_cast<std::size_t>(m), 0.0);
+    cstamp.assign(2 * static_cast<std::size_t>(m), 0u);
+  }
+  auto emit_cross = [&](unsigned i) {  // entries of row i that reference earlier steps
+    if (!prm.chain) {
+      for (unsigned k = S.ptr[i]; k < S.ptr[i + 1]; ++k) {
+        const unsigned j = static_cast<unsigned>(S.col[k]);
+        if (step[j] == step[i]) continue;
+        E.col.push_back(static_cast<int>(xpos[j]));
+        E.val.push_back(S.val[k]);
+      }
+      return;
+    }
+    ++ccur;
+    ctouched.clear();
+    auto add = [&](unsigned pos, double v) {
+      if (cstamp[pos] != ccur) {
+        cstamp[pos] = ccur;
+        cacc[pos]   = 0.0;
+        ctouched.push_back(pos);
+      }
+      cacc[pos] += v;
+    };
+    for (unsigned k = S.ptr[i]; k < S.ptr[i + 1]; ++k) {
+      const unsigned j = static_cast<unsigned>(S.col[k]);
+      if (step[j] == step[i]) continue;
+      // chaining: x_j of a PINNED row of the immediately preceding step is replaced by its
+      // expansion in t, so that the critical rows of consecutive steps depend on each other's t
+      if ((prm.chain_all || pinned[i]) && wlen[j] && step[j] + 1u == step[i]) {
+        add(tpos[j], S.val[k]);
+        for (std::size_t w = wbeg[j], we = wbeg[j] + wlen[j]; w < we; ++w) add(tpos[wcol[w]], S.val[k] * wval[w]);
+      } else {
+        add(xpos[j], S.val[k]);
+      }
+    }
+    std::sort(ctouched.begin(), ctouched.end());
+    for (unsigned pos : ctouched) {
+      E.col.push_back(static_cast<int>(pos));
+      E.val.push_back(cacc[pos]);
+    }
+  };
+  for (unsigned i = 0; i < m; ++i) {
+    if (!wlen[i]) {
+      for (unsigned k = S.ptr[i]; k < S.ptr[i + 1]; ++k)
+        if (step[S.col[k]] >= step[i]) throw std::logic_error("merge_slack: in-step entry on an unsplit row");
+      emit_cross(i);
+      xpos[i] = tpos[i] = static_cast<unsigned>(E.gid.size());
+      E.gid.push_back(S.gid[i]);
+      E.ptr.push_back(static_cast<unsigned>(E.col.size()));
+      continue;
+    }
+    emit_cross(i);  // t_i = b_i - sum_{j in earlier steps} T_ij x_j
+    tpos[i] = static_cast<unsigned>(E.gid.size());
+    E.gid.push_back(m + S.gid[i]);
+    E.ptr.push_back(static_cast<unsigned>(E.col.size()));
+    for (std::size_t w = wbeg[i], we = wbeg[i] + wlen[i]; w < we; ++w) {  // x_i = t_i + sum_j Winv_ij t_j
+      E.col.push_back(static_cast<int>(tpos[wcol[w]]));
+      E.val.push_back(-wval[w]);
+    }
+    E.col.push_back(static_cast<int>(tpos[i]));
+    E.val.push_back(-1.0);
+    xpos[i] = static_cast<unsigned>(E.gid.size());
+    E.gid.push_back(S.gid[i] | kCodeZeroRhs);
+    E.ptr.push_back(static_cast<unsigned>(E.col.size()));
+  }
+  E.nrows = E.ncols = E.gid.size();
+  if (E.nrows > 0x7fffffffull || E.col.size() > 0xfffffff0ull) throw std::length_error("merged factor too large");
+  if (st) {
+    std::vector<unsigned> elev;
+    st->ext_rows     = E.nrows;
+    st->ext_nnz      = E.col.size();
+    st->ext_depth    = depth_of(E, elev);
+    st->super_levels = nsteps;
+  }
+  return E;
+}
+
+// ---- slack-aware merging ------------------------------------------------------------------
+// The dependency DAG of an incomplete factor is a thin critical core inside a mass of rows with
+// slack (Poisson 128^3, L_0: depth 715, but only 2 % of the rows -- 6 % of the entries -- lie
+// within 64 levels of the critical path).  merge_levels() above groups LEVEL
+// SETS, so every row of a merged level set pays fill, critical or not.  Here a row is handled
+// when it is DUE (its as-late-as-possible time z = depth - 1 - height) and placed into the
+// earliest STEP its producers allow:
+//     step(i) = min(current step, 1 + max_j step(j)).
+// Only a row whose producer sits in the still-open current step is PINNED: it is the only kind
+// of row that is split into (t_i, x_i) and receives a row of W^{-1}.  A row with slack lands in
+// an earlier, already closed step and keeps its original entries.  The current step is closed
+// (greedily, in due-time order) when the fill of the pinned rows due next would exceed `gain`,
+// a W^{-1} row would exceed `row_cap`, or the step holds more than `sl_cap` entries.
+// Result: the same exact reformulation T x = b <=> t = b - X x, x = W^{-1} t (W block diagonal
+// over the steps), with fill proportional to the critical core instead of to the factor.
+static unsigned height_of(const HostCsr &S, std::vector<unsigned> &h) {
+  const unsigned m = static_cast<unsigned>(S.nrows);
+  h.assign(m, 0u);
+  unsigned depth = 0;
+  for (unsigned i = m; i-- > 0;) {
+    for (unsigned k = S.ptr[i]; k < S.ptr[i + 1]; ++k) {
+      const unsigned j = static_cast<unsigned>(S.col[k]);
+      h[j]             = std::max(h[j], h[i] + 1u);
+    }
+    depth = std::max(depth, h[i] + 1u);
+  }
+  return depth;
+}
+
+HostCsr merge_slack(const HostCsr &S, const MergeParams &prm, MergeStats *st) {
+  const unsigned m = static_cast<unsigned>(S.nrows);
+  if (S.gid.size() != m || S.orig_rows != m) throw std::logic_error("merge_slack: input is not in sweep form");
+  std::vector<unsigned> h;
+  const unsigned        depth = height_of(S, h);
+  if (st) {
+    st->rows  = m;
+    st->nnz   = S.col.size();
+    st->depth = depth;
+  }
+  // rows bucketed by due time z = depth - 1 - h, index order inside a bucket (topological: a
+  // producer is due strictly earlier than its consumers)
+  std::vector<unsigned> dptr(depth + 1u, 0u), drows(m);
+  for (unsigned i = 0; i < m; ++i) ++dptr[depth - h[i]];
+  for (unsigned t = 0; t < depth; ++t) dptr[t + 1] += dptr[t];
+  {
+    std::vector<unsigned> next(dptr.begin(), dptr.end() - 1);
+    for (unsigned i = 0; i < m; ++i) drows[next[depth - 1u - h[i]]++] = i;
+  }
+  std::vector<unsigned>    step(m, 0u);
+  std::vector<std::size_t> wbeg(m, 0);
+  std::vector<unsigned>    wlen(m, 0u);
+  std::vector<char>        pinned(m, 0);
+  std::vector<unsigned>    wcol;
+  std::vector<double>      wval;
+  std::vector<double>      acc(m, 0.0);
+  std::vector<unsigned>    stamp(m, 0u), touched, tcol, tlen, trow, smax_of, cur_pinned;
+  std::vector<double>      tval;
+  unsigned                 cur = 0, t0 = 0, mark = 0;
+  double                   step_entries = 0.0;
+  std::vector<unsigned char> idepth(m, 0);  // length of the chain of pinned rows below a row, inside its step
+  unsigned                 step_idepth = 0;
+  // a step whose pinned rows only depend on unpinned rows of the step saved nothing (a t and an x
+  // phase instead of two plain steps): undo its fill, its pinned rows open a step of their own
+  auto close_step = [&] {
+    if (step_idepth == 1u) {
+      ++cur;
+      for (unsigned i : cur_pinned) {
+        wlen[i]   = 0;
+        pinned[i] = 0;
+        idepth[i] = 0;
+        step[i]   = cur;
+      }
+    }
+    cur_pinned.clear();
+    step_idepth = 0;
+  };
+  for (unsigned t = 0; t < depth; ++t) {
+    const unsigned rb = dptr[t], re = dptr[t + 1];
+    smax_of.assign(re - rb, 0u);
+    auto smax_plus1 = [&](unsigned i) {  // 1 + highest step of a producer (0: no producers)
+      unsigned s = 0;
+      for (unsigned k = S.ptr[i]; k < S.ptr[i + 1]; ++k) s = std::max(s, step[S.col[k]] + 1u);
+      return s;
+    };
+    for (unsigned q = rb; q < re; ++q) smax_of[q - rb] = smax_plus1(drows[q]);
+    // tentative W^{-1} rows of the rows that would be pinned to the current step
+    bool accept = false;
+    tcol.clear(), tval.clear(), tlen.clear(), trow.clear();
+    double   cost = 0.0, entries = 0.0;
+    unsigned maxlen = 0;
+    bool     any_pinned = false;
+    for (unsigned q = rb; q < re; ++q) {
+      const unsigned i = drows[q];
+      if (smax_of[q - rb] <= cur) {
+        if (smax_of[q - rb] == cur) entries += static_cast<double>(S.ptr[i + 1] - S.ptr[i]);
+        continue;
+      }
+      any_pinned = true;
+      if (!prm.enabled || t == t0 || t - t0 >= prm.bmax || maxlen > prm.row_cap) continue;
+      ++mark;
+      touched.clear();
+      unsigned nwithin = 0;
+      auto     add = [&](unsigned j, double v) {
+        if (stamp[j] != mark) {
+          stamp[j] = mark;
+          acc[j]   = 0.0;
+          touched.push_back(j);
+        }
+        acc[j] += v;
+      };
+      for (unsigned k = S.ptr[i]; k < S.ptr[i + 1]; ++k) {
+        const unsigned j = static_cast<unsigned>(S.col[k]);
+        if (step[j] != cur) continue;
+        ++nwithin;
+        const double v = -S.val[k];  // row i of -N times (I + (W^{-1} - I))
+        add(j, v);
+        for (std::size_t w = wbeg[j], we = wbeg[j] + wlen[j]; w < we; ++w) add(wcol[w], v * wval[w]);
+      }
+      std::sort(touched.begin(), touched.end());
+      for (unsigned j : touched) {
+        tcol.push_back(j);
+        tval.push_back(acc[j]);
+      }
+      trow.push_back(i);
+      tlen.push_back(static_cast<unsigned>(touched.size()));
+      cost += static_cast<double>(touched.size()) - nwithin + 1.0 + prm.row_cost;
+      entries += static_cast<double>(S.ptr[i + 1] - S.ptr[i] - nwithin + touched.size()) + 1.0;
+      maxlen = std::max<unsigned>(maxlen, static_cast<unsigned>(touched.size()) + 1u);
+    }
+    if (!any_pinned)
+      accept = true;  // nothing due now depends on the open step: it simply stays open
+    else
+      accept = prm.enabled && t > t0 && t - t0 < prm.bmax && maxlen <= prm.row_cap && cost <= prm.gain &&
+               step_entries + entries <= prm.sl_cap;
+    if (!accept) {
+      close_step();
+      for (unsigned q = rb; q < re; ++q) smax_of[q - rb] = smax_plus1(drows[q]);
+      ++cur;
+      t0           = t;
+      step_entries = 0.0;
+      for (unsigned q = rb; q < re; ++q) {
+        const unsigned i = drows[q];
+        step[i]          = std::min(cur, smax_of[q - rb]);
+        if (step[i] == cur) step_entries += static_cast<double>(S.ptr[i + 1] - S.ptr[i]);
+      }
+      continue;
+    }
+    step_entries += entries;
+    std::size_t tp = 0, tr = 0;
+    for (unsigned q = rb; q < re; ++q) {
+      const unsigned i = drows[q];
+      if (smax_of[q - rb] <= cur) {
+        step[i] = smax_of[q - rb];
+        continue;
+      }
+      // pinned
+      if (trow[tr] != i) throw std::logic_error("merge_slack: tentative rows out of order");
+      step[i]   = cur;
+      pinned[i] = 1;
+      {
+        unsigned d = 0;
+        for (unsigned k = S.ptr[i]; k < S.ptr[i + 1]; ++k)
+          if (step[S.col[k]] == cur) d = std::max<unsigned>(d, idepth[S.col[k]]);
+        idepth[i]   = static_cast<unsigned char>(std::min(255u, d + 1u));
+        step_idepth = std::max<unsigned>(step_idepth, idepth[i]);
+      }
+      wbeg[i]   = wcol.size();
+      wlen[i]   = tlen[tr];
+      wcol.insert(wcol.end(), tcol.begin() + tp, tcol.begin() + tp + wlen[i]);
+      wval.insert(wval.end(), tval.begin() + tp, tval.begin() + tp + wlen[i]);
+      tp += wlen[i];
+      ++tr;
+      cur_pinned.push_back(i);
+    }
+  }
+  close_step();
+  if (std::getenv("HIFIR_B200_MERGE_DEBUG")) {
+    std::vector<unsigned> rows_in(cur + 1u, 0u), pin_in(cur + 1u, 0u), tmin(cur + 1u, depth), tmax(cur + 1u, 0u);
+    std::vector<double>   fill_in(cur + 1u, 0.0);
+    for (unsigned i = 0; i < m; ++i) {
+      ++rows_in[step[i]];
+      if (pinned[i]) {
+        ++pin_in[step[i]];
+        fill_in[step[i]] += wlen[i];
+        const unsigned z = depth - 1u - h[i];
+        tmin[step[i]] = std::min(tmin[step[i]], z), tmax[step[i]] = std::max(tmax[step[i]], z);
+      }
+    }
+    for (unsigned s = 0; s <= cur; ++s)
+      std::fprintf(stderr, "  step %u: rows %u pinned %u fill %.0f due-times of pinned [%u, %u]\n", s, rows_in[s], pin_in[s],
+                   fill_in[s], tmin[s], tmax[s]);
+  }
+  return emit_merged(S, prm, st, step, pinned, wbeg, wlen, wcol, wval, cur + 1u);
+}
+
+// ---- proportional scheduling ----------------------------------------------------------------
+// Every row sits at the relative position u = a / (a + h) of the longest path through it
+// (a = as-soon-as-possible level, h = height = longest chain of dependents); u increases strictly
+// along every dependency.  K steps cut [0, 1] uniformly: a path of P rows is compressed by P / K,
+// a path with P <= K is not compressed at all (no fill) -- level-set bucketing compresses every
+// path by depth / K, whatever its length.  Rows whose W^{-1} row would exceed row_cap are moved to
+// the next step (the shift propagates to their dependents).
+HostCsr merge_prop(const HostCsr &S, const MergeParams &prm, MergeStats *st) {
+  const unsigned m = static_cast<unsigned>(S.nrows);
+  std::vector<unsigned> a, h;
+  const unsigned        depth = depth_of(S, a);
+  height_of(S, h);
+  if (st) {
+    st->rows  = m;
+    st->nnz   = S.col.size();
+    st->depth = depth;
+  }
+  const unsigned K = std::max(1u, std::min(prm.steps, depth));
+  std::vector<unsigned>    step(m, 0u);
+  std::vector<std::size_t> wbeg(m, 0);
+  std::vector<unsigned>    wlen(m, 0u);
+  std::vector<char>        pinned(m, 0);
+  std::vector<unsigned>    wcol;
+  std::vector<double>      wval;
+  std::vector<double>      acc(m, 0.0);
+  std::vector<unsigned>    stamp(m, 0u), touched;
+  unsigned                 mark = 0, nsteps = 1;
+  for (unsigned i = 0; i < m; ++i) {
+    const unsigned P  = a[i] + h[i];
+    unsigned       s0 = P ? static_cast<unsigned>((static_cast<unsigned long long>(a[i]) * K) / (P + 1u)) : 0u;
+    unsigned       smax = 0;
+    bool           any = false;
+    for (unsigned k = S.ptr[i]; k < S.ptr[i + 1]; ++k) {
+      smax = std::max(smax, step[S.col[k]]);
+      any  = true;
+    }
+    unsigned s = any ? std::max(s0, smax) : s0;
+    if (!prm.enabled && any) s = std::max(s, smax + 1u);  // no merging: one step per dependent row
+    for (;;) {
+      // row of W^{-1} - I if the row stays in step s
+      ++mark;
+      touched.clear();
+      unsigned nwithin = 0;
+      auto     add = [&](unsigned j, double v) {
+        if (stamp[j] != mark) {
+          stamp[j] = mark;
+          acc[j]   = 0.0;
+          touched.push_back(j);
+        }
+        acc[j] += v;
+      };
+      for (unsigned k = S.ptr[i]; k < S.ptr[i + 1]; ++k) {
+        const unsigned j = static_cast<unsigned>(S.col[k]);
+        if (step[j] != s) continue;
+        ++nwithin;
+        const double v = -S.val[k];
+        add(j, v);
+        for (std::size_t w = wbeg[j], we = wbeg[j] + wlen[j]; w < we; ++w) add(wcol[w], v * wval[w]);
+      }
+      if (!nwithin) break;
+      if (touched.size() + 1u > prm.row_cap) {  // too long: the row opens the next step for its paths
+        ++s;
+        continue;
+      }
+      std::sort(touched.begin(), touched.end());
+      pinned[i] = 1;
+      wbeg[i]   = wcol.size();
+      wlen[i]   = static_cast<unsigned>(touched.size());
+      for (unsigned j : touched) {
+        wcol.push_back(j);
+        wval.push_back(acc[j]);
+      }
+      break;
+    }
+    step[i] = s;
+    nsteps  = std::max(nsteps, s + 1u);
+  }
+  return emit_merged(S, prm, st, step, pinned, wbeg, wlen, wcol, wval, nsteps);
+}
+
 HostCsr merge_levels(const HostCsr &S, const MergeParams &prm, MergeStats *st, bool fan_out) {
   const unsigned m = static_cast<unsigned>(S.nrows);
   if (S.gid.size() != m || S.orig_rows != m) throw std::logic_error("merge_levels: input is not in sweep form");
+  if (prm.steps) return merge_prop(S, prm, st);
+  if (prm.slack) return merge_slack(S, prm, st);
   std::vector<unsigned> lev;
   const bool            alap  = prm.alap == 2 || (prm.alap == 1 && fan_out) || (prm.alap == 3 && !fan_out);
   const unsigned        depth = alap ? depth_alap(S, lev) : depth_of(S, lev);

@@ -107,10 +107,12 @@ void ensure_mrhs(Handle *h) {
   if (h->mrhs_ready) return;
   std::size_t *tally = &h->device_bytes;
   for (DevLevel &D : h->levels) {
-    // the streaming plans (stream.cu) serve any width; the slab kernels need their own packing
+    // the streaming plans (stream.cu) serve any width; warp-stream plans serve one column: the
+    // multi-rhs sweeps then run on streaming plans of their own (identity slots)
     if (!D.L.stream) {
-      build_sweep_plan(D.hostL, false, D.Lm, tally, NR);
-      build_sweep_plan(D.hostU, true, D.Um, tally, NR);
+      D.Lm.f32 = D.Um.f32 = h->f32;
+      build_sweep_plan(D.hostL, false, D.Lm, tally, static_cast<unsigned>(h->num_sms), nullptr, 1);
+      build_sweep_plan(D.hostU, true, D.Um, tally, static_cast<unsigned>(h->num_sms), nullptr, 1);
     }
     D.m_bhat.alloc(D.n * NR, tally);
     D.m_g.alloc(D.m * NR, tally);
@@ -155,10 +157,9 @@ static void apply_chunk(Handle *h, const double *d_in, double *d_out, std::size_
     }
     if (D.nm) {
       if (D.m) {
-        launch_sweep(h, D.L.stream ? D.L : D.Lm, D.m_bhat.p, nullptr, nullptr, D.m_xL_dn.p, parity, h->tick(4 * l),
-                     nullptr, NR);
+        launch_sweep(h, D.L.stream ? D.L : D.Lm, D.m_bhat.p, nullptr, nullptr, D.m_xL_dn.p, parity, h->tick(4 * l), NR);
         launch_sweep(h, D.U.stream ? D.U : D.Um, nullptr, D.m_xL_dn.p, D.d.p, D.m_xU_dn.p, parity,
-                     h->tick(4 * l + 1), nullptr, NR);
+                     h->tick(4 * l + 1), NR);
       }
       spmv_resid_m_kernel<true><<<cdiv(D.nm * NR, T), T, 0, h->stream>>>(
           static_cast<unsigned>(D.nm), D.E.ptr.p, D.E.col.p, D.E.val.p, D.m_xU_dn.p, D.m_bhat.p + D.m * NR, D.m_r.p);
@@ -193,9 +194,9 @@ static void apply_chunk(Handle *h, const double *d_in, double *d_out, std::size_
     }
     if (D.m) {
       launch_sweep(h, D.L.stream ? D.L : D.Lm, rhs, nullptr, nullptr, D.m_xL_up.p, parity, h->tick(4 * l + 2),
-                   nullptr, NR);
+                   NR);
       launch_sweep(h, D.U.stream ? D.U : D.Um, nullptr, D.m_xL_up.p, D.d.p, D.m_xU_up.p, parity,
-                   h->tick(4 * l + 3), nullptr, NR);
+                   h->tick(4 * l + 3), NR);
     }
     if (D.n) {
       scatter_scale_m_kernel<<<cdiv(D.n * NR, T), T, 0, h->stream>>>(

@@ -59,10 +59,12 @@ __global__ void vec_add_kernel(const unsigned n, const double *a, const double *
 }
 
 // z[i] = value(xU[i]) + w1[i]      (prec_prod.hpp:124)
+// (row i of the U sweep's result lives at slot[i])
 __global__ void add_tagged_kernel(const unsigned m, const unsigned long long *__restrict__ xU,
-                                  const double *__restrict__ w1, double *__restrict__ z) {
+                                  const unsigned *__restrict__ slot, const double *__restrict__ w1,
+                                  double *__restrict__ z) {
   const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < m) z[i] = tag_value(xU[i]) + w1[i];
+  if (i < m) z[i] = tag_value(xU[slot[i]]) + w1[i];
 }
 
 // y[i] = [v1; v2][p_inv[i]] / s[i]   (prec_prod.hpp:133)
@@ -144,7 +146,7 @@ void prod_level(Handle *h, std::size_t l, const double *x, double *y, std::size_
       ++h->launch_count;
       // z = (LDU)^{-1} f + w1                       (:120-124); z lives in pf
       launch_ldu_solve(h, D, D.pf.p, D.p_xL.p, D.p_xU.p, parity, h->tick(8 * l));
-      add_tagged_kernel<<<cdiv(m, T), T, 0, h->stream>>>(m, D.p_xU.p, w1, D.pf.p);
+      add_tagged_kernel<<<cdiv(m, T), T, 0, h->stream>>>(m, D.p_xU.p, D.U_slot.p, w1, D.pf.p);
       HIF_KERNEL_CHECK();
       ++h->launch_count;
     }

@@ -1,0 +1,664 @@
+// wsweep.cu -- statically scheduled, warp-autonomous triangular sweep ("warp streams").
+//
+// Replaces CCS::solve_as_strict_lower / solve_as_strict_upper of the reference
+// (ds/CompressedStorage.hpp:2267-2279, 2356-2369) on the merged factors of merge.cu.
+//
+// Round 1's streaming kernel handed out chunks of 8 slices through a ticket counter and ran every
+// chunk through a dependent chain ticket -> descriptor -> factor entries -> admission -> gathers
+// -> publish, two CTA barriers per chunk: 2.1-2.8 us per level set although the hardware hand-off
+// is 0.3-0.5 us.  Here nothing is dynamic:
+//   * the slices of every level set are dealt round-robin to the warps of ONE persistent CTA per SM
+//     at attach time; a warp owns a private, contiguous STREAM of segments (header, row codes,
+//     publish slots, slot indices and values of <= 8 entries per lane) in level order;
+//   * the stream is staged through shared memory by 1-D TMA bulk copies (cp.async.bulk + mbarrier)
+//     into a per-warp ring several segments ahead -- the factor data never sits on the dependent
+//     path of a level, costs no registers and is read from HBM exactly once;
+//   * warps never synchronize with each other: no tickets, no CTA barriers, no level counters.
+//     Readiness travels with the value (tagged words, common.cuh).  A warp gathers all entries of
+//     a segment at once and re-polls only what was not ready;
+//   * run-ahead warps do not hammer L2: before touching the solution a warp waits (sleeping in
+//     proportion to its distance from a frontier hint) until a SENTINEL row -- the last row of
+//     level l - window -- carries the current tag.  The sentinel only throttles; correctness
+//     rests on the tags alone;
+//   * solution slots are renumbered level-major and, inside a level set, in sweep order, rows of a
+//     level are ordered by (lanes per row, length bucket, sweep order): the 32 gathers of a warp
+//     instruction share 32-byte sectors (0.6-0.7 sector requests per entry instead of 0.7-0.8; an
+//     SM issues one L2 sector request per clock, the throughput ceiling of the wide level sets).
+//   * rows without entries (55 % of L_0: the leaves of the elimination tree) are copied 8 per
+//     lane by COPY segments.
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <numeric>
+
+#include "hifgpu.h"
+
+namespace hifgpu {
+
+namespace {
+constexpr unsigned kWsU        = 8;            // entries per lane and segment
+constexpr unsigned kWsNone     = 0xffffffffu;  // padding column / no sentinel
+constexpr unsigned kSegFirst   = 1u, kSegLast = 2u, kSegCopy = 4u;
+constexpr unsigned kWsHdrWords = 4;
+
+inline unsigned seg_words(unsigned width, bool copy, bool f32) {
+  if (copy) return kWsHdrWords + width * 32u * 2u;
+  return kWsHdrWords + 64u + width * 32u * (f32 ? 2u : 3u);
+}
+}  // namespace
+
+unsigned ws_stage_bytes(bool f32) { return seg_words(kWsU, false, f32) * 4u; }
+
+int ws_env(const char *name, int dflt) {
+  const char *e = std::getenv(name);
+  return e ? std::atoi(e) : dflt;
+}
+
+// ---- host: merged sweep form -> warp streams ------------------------------------------
+// slot_of (out): solution slot of every ORIGINAL row.  rhs_index (nullable): position of original
+// row r in the right-hand side array of this sweep (identity when null) -- the U sweep reads the L
+// sweep's tagged result, which lives at the L plan's slots.
+void pack_warp_streams(const HostCsr &S, WsHost &H, unsigned nwarps, unsigned window, bool f32,
+                       const unsigned *rhs_index) {
+  const unsigned n = static_cast<unsigned>(S.nrows), m = static_cast<unsigned>(S.orig_rows);
+  H = WsHost();
+  H.nwarps = nwarps;
+  H.wdesc.assign(static_cast<std::size_t>(nwarps) * 8u, 0u);
+  H.slot_of.assign(m, 0u);
+  H.nslots = n;
+  if (!n) return;
+  if (S.gid.size() != n) throw std::logic_error("pack_warp_streams: factor is not in sweep form");
+  std::vector<unsigned> lev(n, 0u);
+  unsigned              depth = 0;
+  for (unsigned i = 0; i < n; ++i) {
+    unsigned l = 0;
+    for (unsigned k = S.ptr[i]; k < S.ptr[i + 1]; ++k) l = std::max(l, lev[S.col[k]] + 1u);
+    lev[i] = l;
+    depth  = std::max(depth, l + 1u);
+  }
+  auto rowlen = [&](unsigned i) { return S.ptr[i + 1] - S.ptr[i]; };
+  // class: lanes per row 2^z so that a lane holds <= kWsU entries (z = 5 beyond 256 entries: the
+  // slice then takes several segments)
+  auto zof = [&](unsigned len) {
+    unsigned z = 0;
+    while (z < 5u && ((len + (1u << z) - 1u) >> z) > kWsU) ++z;
+    return z;
+  };
+  std::vector<unsigned char> cls(n), bkt(n);
+  for (unsigned i = 0; i < n; ++i) {
+    const unsigned len = rowlen(i);
+    cls[i]             = static_cast<unsigned char>(len ? zof(len) : 0u);
+    const unsigned w   = (len + (1u << cls[i]) - 1u) >> cls[i];
+    bkt[i] = static_cast<unsigned char>(len == 0 ? 0u : w <= 2 ? 1u : w <= 4 ? 2u : w <= 6 ? 3u : w <= 8 ? 4u : 5u);
+  }
+  // slots: level-major, sweep order inside a level set (rows of S are in sweep order)
+  std::vector<unsigned> slot(n);
+  {
+    std::vector<unsigned> cnt(depth + 1u, 0u);
+    for (unsigned i = 0; i < n; ++i) ++cnt[lev[i] + 1u];
+    for (unsigned l = 0; l < depth; ++l) cnt[l + 1] += cnt[l];
+    for (unsigned i = 0; i < n; ++i) slot[i] = cnt[lev[i]]++;
+  }
+  for (unsigned i = 0; i < n; ++i) {
+    const unsigned code = S.gid[i] & kCodeSlotMask;
+    if (code < m) H.slot_of[code] = slot[i];  // the solution itself (codes >= m: auxiliary unknowns)
+  }
+  // order: level, (empty rows first), class desc, bucket desc, sweep order
+  std::vector<unsigned> ord(n);
+  std::iota(ord.begin(), ord.end(), 0u);
+  std::stable_sort(ord.begin(), ord.end(), [&](unsigned a, unsigned b) {
+    if (lev[a] != lev[b]) return lev[a] < lev[b];
+    const bool ea = rowlen(a) == 0, eb = rowlen(b) == 0;
+    if (ea != eb) return ea;
+    if (cls[a] != cls[b]) return cls[a] > cls[b];
+    if (bkt[a] != bkt[b]) return bkt[a] > bkt[b];
+    return a < b;
+  });
+  // ---- slices in level order; slice q (global count) goes to warp q % nwarps
+  struct Seg {
+    unsigned warp, off;  // offset in words inside the warp's private stream
+  };
+  std::vector<std::vector<unsigned>> ws(nwarps);  // private streams
+  std::vector<std::vector<unsigned>> seg_off(nwarps);
+  std::vector<unsigned>              sentinel_of_level(depth, kWsNone);
+  unsigned                           q = 0;
+  std::vector<unsigned>              ent;
+  auto rhs_code = [&](unsigned i) {
+    const unsigned code = S.gid[i];
+    unsigned       r    = code & kCodeSlotMask;
+    if (r >= m) r -= m;
+    if (rhs_index) r = rhs_index[r];
+    return r | (code & kCodeZeroRhs);
+  };
+  auto push_seg = [&](unsigned warp, unsigned width, unsigned z, unsigned flags, unsigned level) -> unsigned * {
+    std::vector<unsigned> &st = ws[warp];
+    const unsigned         o  = static_cast<unsigned>(st.size());
+    seg_off[warp].push_back(o);
+    st.resize(o + seg_words(width, (flags & kSegCopy) != 0, f32), 0u);
+    unsigned *hd = st.data() + o;
+    hd[0]        = width | (z << 8) | (flags << 16);
+    hd[1]        = 0;  // size of the segment `stages` ahead: filled by the kernel-side ring depth at finalize
+    hd[2]        = level >= window ? sentinel_of_level[level - window] : kWsNone;
+    hd[3]        = level;
+    H.order.push_back(warp);
+    H.order.push_back(o);
+    return hd;
+  };
+  for (unsigned p = 0; p < n;) {
+    const unsigned i0 = ord[p], l = lev[i0];
+    if (rowlen(i0) == 0) {  // COPY segment: up to 8 rows per lane
+      unsigned cnt = 1;
+      while (cnt < 32u * kWsU && p + cnt < n && lev[ord[p + cnt]] == l && rowlen(ord[p + cnt]) == 0) ++cnt;
+      const unsigned width = (cnt + 31u) / 32u;
+      unsigned *     hd    = push_seg(q % nwarps, width, 0u, kSegFirst | kSegLast | kSegCopy, l);
+      unsigned *     codes = hd + kWsHdrWords, *slots = codes + width * 32u;
+      for (unsigned r = 0; r < width * 32u; ++r) {
+        // row r of the segment: lane r % 32, position r / 32 -> stored at [pos * 32 + lane] = [r]
+        codes[r] = r < cnt ? rhs_code(ord[p + r]) : kWsNone;
+        slots[r] = r < cnt ? slot[ord[p + r]] : kWsNone;
+      }
+      sentinel_of_level[l] = slot[ord[p + cnt - 1u]];
+      ++q;
+      p += cnt;
+      H.copy_rows += cnt;
+      continue;
+    }
+    const unsigned z = cls[i0], lpr = 1u << z, cap = 32u >> z;
+    unsigned       cnt = 1;
+    while (cnt < cap && p + cnt < n && lev[ord[p + cnt]] == l && rowlen(ord[p + cnt]) != 0 && cls[ord[p + cnt]] == z &&
+           bkt[ord[p + cnt]] == bkt[i0])
+      ++cnt;
+    unsigned width = 0;
+    for (unsigned r = 0; r < cnt; ++r) width = std::max(width, (rowlen(ord[p + r]) + lpr - 1u) >> z);
+    const unsigned nseg = (width + kWsU - 1u) / kWsU, warp = q % nwarps;
+    for (unsigned sg = 0; sg < nseg; ++sg) {
+      const unsigned w0 = sg * kWsU, w = std::min(kWsU, width - w0);
+      unsigned *     hd = push_seg(warp, w, z, (sg == 0 ? kSegFirst : 0u) | (sg + 1 == nseg ? kSegLast : 0u), l);
+      unsigned *     codes = hd + kWsHdrWords, *slots = codes + 32u, *cols = slots + 32u;
+      for (unsigned j = 0; j < 32u; ++j) {
+        const unsigned r = j >> z;
+        codes[j]         = r < cnt ? rhs_code(ord[p + r]) : kWsNone;
+        slots[j]         = r < cnt ? slot[ord[p + r]] : kWsNone;
+      }
+      for (unsigned k = 0; k < w * 32u; ++k) cols[k] = kWsNone;
+      unsigned char *vals = reinterpret_cast<unsigned char *>(cols + w * 32u);
+      for (unsigned r = 0; r < cnt; ++r) {
+        const unsigned i = ord[p + r], b = S.ptr[i], e = S.ptr[i + 1];
+        // entries in slot order = producer level, then sweep order: the ones that become ready last come last
+        ent.resize(e - b);
+        std::iota(ent.begin(), ent.end(), b);
+        std::stable_sort(ent.begin(), ent.end(), [&](unsigned x, unsigned y) { return slot[S.col[x]] < slot[S.col[y]]; });
+        for (unsigned qq = 0; qq < e - b; ++qq) {  // entry qq of the row -> lane r*lpr + qq % lpr, position qq / lpr
+          const unsigned pos = qq >> z;
+          if (pos < w0 || pos >= w0 + w) continue;
+          const unsigned at = (pos - w0) * 32u + r * lpr + (qq & (lpr - 1u));
+          cols[at]          = slot[S.col[ent[qq]]];
+          if (f32) {
+            const float v = static_cast<float>(S.val[ent[qq]]);
+            std::memcpy(vals + static_cast<std::size_t>(at) * 4u, &v, 4);
+          } else {
+            std::memcpy(vals + static_cast<std::size_t>(at) * 8u, &S.val[ent[qq]], 8);
+          }
+        }
+        if (sg == 0) H.padded += static_cast<std::size_t>(width) * lpr - (e - b);
+      }
+    }
+    H.entries += 0;
+    sentinel_of_level[l] = slot[ord[p + cnt - 1u]];
+    ++q;
+    p += cnt;
+  }
+  H.entries = S.col.size();
+  H.depth   = depth;
+  H.slices  = q;
+  // ---- concatenate the private streams; descriptor = {offset (words / 4), segments, 0, 0, first sizes}
+  std::size_t total = 0;
+  for (unsigned w = 0; w < nwarps; ++w) total += ws[w].size();
+  if (total / 4u > 0xffffffffull) throw std::length_error("warp streams too large");
+  H.stream.reserve(total);
+  H.max_segs = 0;
+  for (unsigned w = 0; w < nwarps; ++w) {
+    unsigned *d = H.wdesc.data() + static_cast<std::size_t>(w) * 8u;
+    d[0]        = static_cast<unsigned>(H.stream.size() / 4u);
+    d[1]        = static_cast<unsigned>(seg_off[w].size());
+    H.max_segs  = std::max<std::size_t>(H.max_segs, seg_off[w].size());
+    H.stream.insert(H.stream.end(), ws[w].begin(), ws[w].end());
+  }
+  // order entries: (warp, offset inside the private stream) -> absolute word offset
+  for (std::size_t k = 0; k < H.order.size(); k += 2) {
+    const unsigned w = H.order[k];
+    H.order[k + 1] += H.wdesc[static_cast<std::size_t>(w) * 8u] * 4u;
+  }
+  // segment sizes for the ring: wdesc[4..7] = sizes (in 16-byte units) of the first 4 segments, header
+  // word 1 of segment k = size of segment k + stages (set by finalize_ring)
+  H.seg_off = std::move(seg_off);
+}
+
+// header word 1 of segment k = size (16-byte units) of segment k + stages of the same warp; the
+// descriptor carries the sizes of the first `stages` segments
+void ws_finalize_ring(WsHost &H, unsigned stages) {
+  if (stages > 4u) throw std::logic_error("at most 4 ring stages");
+  for (unsigned w = 0; w < H.nwarps; ++w) {
+    unsigned *                   d   = H.wdesc.data() + static_cast<std::size_t>(w) * 8u;
+    const std::vector<unsigned> &so  = H.seg_off[w];
+    const std::size_t            base = static_cast<std::size_t>(d[0]) * 4u, ns = so.size();
+    const std::size_t            end  = w + 1 < H.nwarps ? static_cast<std::size_t>(H.wdesc[(w + 1) * 8u]) * 4u : H.stream.size();
+    auto size16 = [&](std::size_t k) {
+      const std::size_t e = k + 1 < ns ? base + so[k + 1] : end;
+      return static_cast<unsigned>((e - (base + so[k])) / 4u);
+    };
+    for (unsigned s = 0; s < 4u; ++s) d[4 + s] = s < ns ? size16(s) : 0u;
+    for (std::size_t k = 0; k < ns; ++k) H.stream[base + so[k] + 1u] = k + stages < ns ? size16(k + stages) : 0u;
+  }
+}
+
+// CPU emulation of the warp-stream sweep on the packed data (segments in creation order = level
+// order): lets tests check merge + packing without a GPU.  x has H.nslots entries.
+void ws_host_emulate_packed(const WsHost &H, bool upper, bool f32, const double *rhs, const double *diag, double *x) {
+  double acc[32];
+  for (std::size_t k = 0; k < H.order.size(); k += 2) {
+    const unsigned *hd    = H.stream.data() + H.order[k + 1];
+    const unsigned  width = hd[0] & 0xffu, z = (hd[0] >> 8) & 0xffu, flags = hd[0] >> 16;
+    auto rhs_of = [&](unsigned code) {
+      if (code & kCodeZeroRhs) return 0.0;
+      const unsigned r = code & kCodeSlotMask;
+      return upper ? rhs[r] / diag[r] : rhs[r];
+    };
+    if (flags & kSegCopy) {
+      const unsigned *codes = hd + kWsHdrWords, *slots = codes + width * 32u;
+      for (unsigned r = 0; r < width * 32u; ++r)
+        if (slots[r] != kWsNone) x[slots[r]] = rhs_of(codes[r]);
+      continue;
+    }
+    const unsigned *     codes = hd + kWsHdrWords, *slots = codes + 32u, *cols = slots + 32u;
+    const unsigned char *vals  = reinterpret_cast<const unsigned char *>(cols + width * 32u);
+    const unsigned       lpr   = 1u << z;
+    for (unsigned j = 0; j < 32u; ++j) {
+      if (flags & kSegFirst) acc[j] = ((j & (lpr - 1u)) == 0u && codes[j] != kWsNone) ? rhs_of(codes[j]) : 0.0;
+      for (unsigned u = 0; u < width; ++u) {
+        const unsigned c = cols[u * 32u + j];
+        if (c == kWsNone) continue;
+        double v;
+        if (f32) {
+          float f;
+          std::memcpy(&f, vals + static_cast<std::size_t>(u * 32u + j) * 4u, 4);
+          v = f;
+        } else {
+          std::memcpy(&v, vals + static_cast<std::size_t>(u * 32u + j) * 8u, 8);
+        }
+        acc[j] = std::fma(-v, x[c], acc[j]);
+      }
+    }
+    if (flags & kSegLast) {
+      for (unsigned o = lpr >> 1; o > 0; o >>= 1) {  // the butterfly of the device (shfl_xor)
+        double nw[32];
+        for (unsigned j = 0; j < 32u; ++j) nw[j] = acc[j] + acc[j ^ o];
+        std::memcpy(acc, nw, sizeof(nw));
+      }
+      for (unsigned j = 0; j < 32u; j += lpr)
+        if (slots[j] != kWsNone) x[slots[j]] = acc[j];
+    }
+  }
+}
+
+// ---- device ----------------------------------------------------------------------------
+namespace {
+__device__ __forceinline__ unsigned ws_smem_addr(const void *p) { return static_cast<unsigned>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void ws_mbar_init(unsigned bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void ws_mbar_expect_tx(unsigned bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void ws_tma_g2s(unsigned dst, const void *src, unsigned bytes, unsigned bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ bool ws_mbar_try_wait(unsigned bar, unsigned phase) {
+  unsigned ok;
+  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+               : "=r"(ok)
+               : "r"(bar), "r"(phase)
+               : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ int ws_ld_poll_i32(const int *p) {
+  int v;
+  asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void ws_publish(unsigned long long *p, unsigned long long v, int use_store) {
+  if (use_store) {
+    st_publish(p, v);
+  } else {
+    // through the L2 atomic unit: visible to pollers ~0.2 us earlier than a plain store (round 1 A/B)
+    unsigned long long old;
+    asm volatile("atom.relaxed.gpu.global.exch.b64 %0, [%1], %2;" : "=l"(old) : "l"(p), "l"(v) : "memory");
+  }
+}
+}  // namespace
+
+struct WsParams {
+  const unsigned *          wdesc;
+  const unsigned *          stream;
+  const double *            rhs_plain;
+  const unsigned long long *rhs_tagged;
+  const double *            diag;
+  unsigned long long *      x;
+  int *                     sync;  // [0] frontier hint (highest level some warp finished a slice of)
+  int *                     error_flag;
+  unsigned                  parity, window, adm_sleep, poll_sleep;
+  int                       publish_st;
+};
+
+// One persistent CTA per SM, kWarps warps; warp (blockIdx.x + gridDim.x * warp) owns stream
+// wdesc[..].  kStages ring stages of kStageBytes each per warp.
+template <bool UPPER, class VT, int kWarps, int kStages>
+__global__ void __launch_bounds__(kWarps * 32, 1) wsweep_kernel(const WsParams P) {
+  constexpr unsigned kStageBytes = (kWsHdrWords + 64u + kWsU * 32u * (sizeof(VT) == 4 ? 2u : 3u)) * 4u;
+  extern __shared__ __align__(128) unsigned char smem[];
+  const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+  const unsigned gw   = blockIdx.x + gridDim.x * warp;
+  const uint4    d0   = reinterpret_cast<const uint4 *>(P.wdesc)[2 * gw];
+  const uint4    d1   = reinterpret_cast<const uint4 *>(P.wdesc)[2 * gw + 1];
+  const unsigned nseg = d0.y;
+  if (!nseg) return;  // warps never meet at a CTA barrier
+  unsigned char *ring = smem + static_cast<std::size_t>(kWarps) * kStages * 8u + static_cast<std::size_t>(warp) * kStages * kStageBytes;
+  const unsigned bar0 = ws_smem_addr(smem) + warp * kStages * 8u;
+  const unsigned char *src = reinterpret_cast<const unsigned char *>(P.stream) + static_cast<std::size_t>(d0.x) * 16u;
+  if (lane == 0) {
+    for (int s = 0; s < kStages; ++s) ws_mbar_init(bar0 + s * 8u, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    const unsigned sz[4] = {d1.x, d1.y, d1.z, d1.w};
+    for (int s = 0; s < kStages; ++s)
+      if (sz[s]) {
+        ws_mbar_expect_tx(bar0 + s * 8u, sz[s] * 16u);
+        ws_tma_g2s(ws_smem_addr(ring + s * kStageBytes), src, sz[s] * 16u, bar0 + s * 8u);
+        src += static_cast<std::size_t>(sz[s]) * 16u;
+      }
+  }
+  __syncwarp();
+  double   acc        = 0.0;
+  unsigned my_front   = 0;
+  const unsigned parity = P.parity;
+  for (unsigned k = 0; k < nseg; ++k) {
+    const unsigned stage = k % kStages, phase = (k / kStages) & 1u;
+    {
+      unsigned spins = 0;
+      while (!ws_mbar_try_wait(bar0 + stage * 8u, phase)) {
+        if (++spins > kSpinLimit) {
+          *P.error_flag = 2;
+          break;
+        }
+      }
+    }
+    const unsigned *sg    = reinterpret_cast<const unsigned *>(ring + stage * kStageBytes);
+    const uint4     hd    = *reinterpret_cast<const uint4 *>(sg);
+    const unsigned  width = hd.x & 0xffu, z = (hd.x >> 8) & 0xffu, flags = hd.x >> 16;
+    if (flags & kSegCopy) {
+      // rows without entries: x = rhs, 8 per lane, all loads in flight together
+      unsigned code[kWsU], slot[kWsU];
+#pragma unroll
+      for (unsigned u = 0; u < kWsU; ++u) {
+        code[u] = slot[u] = kWsNone;
+        if (u < width) {
+          code[u] = sg[kWsHdrWords + u * 32u + lane];
+          slot[u] = sg[kWsHdrWords + (width + u) * 32u + lane];
+        }
+      }
+      __syncwarp();
+      if (lane == 0 && hd.y) {
+        ws_mbar_expect_tx(bar0 + stage * 8u, hd.y * 16u);
+        ws_tma_g2s(ws_smem_addr(ring + stage * kStageBytes), src, hd.y * 16u, bar0 + stage * 8u);
+        src += static_cast<std::size_t>(hd.y) * 16u;
+      }
+      double v[kWsU];
+#pragma unroll
+      for (unsigned u = 0; u < kWsU; ++u) {
+        v[u] = 0.0;
+        if (slot[u] != kWsNone && !(code[u] & kCodeZeroRhs)) {
+          const unsigned r = code[u] & kCodeSlotMask;
+          if (UPPER) {
+            unsigned long long t = ld_poll(P.rhs_tagged + r);
+            for (unsigned spins = 0; !tag_ready(t, parity); t = ld_poll(P.rhs_tagged + r))
+              if (++spins > kSpinLimit) {
+                *P.error_flag = 3;
+                break;
+              }
+            v[u] = tag_value(t) / P.diag[r];
+          } else {
+            v[u] = P.rhs_plain[r];
+          }
+        }
+      }
+#pragma unroll
+      for (unsigned u = 0; u < kWsU; ++u)
+        if (slot[u] != kWsNone) st_publish(P.x + slot[u], tag_set(v[u], parity));
+      if (lane == 0 && hd.w > my_front) {
+        my_front = hd.w;
+        atomicMax(P.sync, static_cast<int>(hd.w));
+      }
+      continue;
+    }
+    // ---- a slice segment: codes, slots, <= 8 entries per lane
+    const unsigned code = sg[kWsHdrWords + lane];
+    const unsigned slot = sg[kWsHdrWords + 32u + lane];
+    unsigned       cc[kWsU];
+    VT             vv[kWsU];
+    const VT *     sv = reinterpret_cast<const VT *>(sg + kWsHdrWords + 64u + width * 32u);
+#pragma unroll
+    for (unsigned u = 0; u < kWsU; ++u) {
+      cc[u] = kWsNone;
+      vv[u] = VT(0);
+      if (u < width) {
+        cc[u] = sg[kWsHdrWords + 64u + u * 32u + lane];
+        vv[u] = sv[u * 32u + lane];
+      }
+    }
+    __syncwarp();  // every lane has read the stage: refill it with the segment kStages ahead
+    if (lane == 0 && hd.y) {
+      ws_mbar_expect_tx(bar0 + stage * 8u, hd.y * 16u);
+      ws_tma_g2s(ws_smem_addr(ring + stage * kStageBytes), src, hd.y * 16u, bar0 + stage * 8u);
+      src += static_cast<std::size_t>(hd.y) * 16u;
+    }
+    const unsigned lpr = 1u << z;
+    const bool     own = slot != kWsNone && (lane & (lpr - 1u)) == 0u;
+    // ---- right-hand side (in flight beside the gathers)
+    double             rhs_v  = 0.0, dg = 1.0;
+    unsigned long long rhs_t  = 0;
+    const bool         want_r = (flags & kSegFirst) && own && !(code & kCodeZeroRhs);
+    if (want_r) {
+      const unsigned r = code & kCodeSlotMask;
+      if (UPPER) {
+        rhs_t = ld_poll(P.rhs_tagged + r);
+        dg    = P.diag[r];
+      } else {
+        rhs_v = P.rhs_plain[r];
+      }
+    }
+    // ---- admission: the sentinel of level (this - window) is published
+    if (hd.z != kWsNone) {
+      if (lane == 0) {
+        unsigned spins = 0;
+        while (!tag_ready(ld_poll(P.x + hd.z), parity)) {
+          const unsigned f    = static_cast<unsigned>(ws_ld_poll_i32(P.sync));
+          const unsigned need = hd.w - P.window;
+          const unsigned dist = need > f ? need - f : 0u;
+          __nanosleep(min(dist * P.adm_sleep + 32u, 20000u));
+          if (++spins > (kSpinLimit >> 4)) {
+            *P.error_flag = 1;
+            break;
+          }
+        }
+      }
+      __syncwarp();
+    }
+    // ---- gather all entries optimistically, re-poll the ones that are not ready
+    unsigned long long g[kWsU];
+    unsigned           pend = 0;
+#pragma unroll
+    for (unsigned u = 0; u < kWsU; ++u)
+      if (cc[u] != kWsNone) g[u] = ld_poll(P.x + cc[u]);
+#pragma unroll
+    for (unsigned u = 0; u < kWsU; ++u)
+      if (cc[u] != kWsNone && !tag_ready(g[u], parity)) pend |= 1u << u;
+    if (UPPER && want_r && !tag_ready(rhs_t, parity)) pend |= 1u << kWsU;
+    for (unsigned rounds = 0; __any_sync(0xffffffffu, pend != 0u);) {
+      if (P.poll_sleep) __nanosleep(P.poll_sleep);
+#pragma unroll
+      for (unsigned u = 0; u < kWsU; ++u)
+        if (pend & (1u << u)) g[u] = ld_poll(P.x + cc[u]);
+      if (UPPER && (pend & (1u << kWsU))) rhs_t = ld_poll(P.rhs_tagged + (code & kCodeSlotMask));
+#pragma unroll
+      for (unsigned u = 0; u < kWsU; ++u)
+        if ((pend & (1u << u)) && tag_ready(g[u], parity)) pend &= ~(1u << u);
+      if (UPPER && (pend & (1u << kWsU)) && tag_ready(rhs_t, parity)) pend &= ~(1u << kWsU);
+      if (++rounds > (kSpinLimit >> 3)) {  // hang guard: flag the error, go on with garbage
+        *P.error_flag = 1;
+        break;
+      }
+    }
+    if (flags & kSegFirst) {
+      acc = 0.0;
+      // b_i (L sweep) or (L^{-1} b)_i / d_i with a true division (prec_solve.hpp:219, :256-259)
+      if (want_r) acc = UPPER ? tag_value(rhs_t) / dg : rhs_v;
+    }
+#pragma unroll
+    for (unsigned u = 0; u < kWsU; ++u)
+      if (cc[u] != kWsNone) acc = fma(-static_cast<double>(vv[u]), tag_value(g[u]), acc);
+    if (flags & kSegLast) {
+      for (unsigned o = lpr >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      if (own) ws_publish(P.x + slot, tag_set(acc, parity), P.publish_st);
+      if (lane == 0 && hd.w > my_front) {
+        my_front = hd.w;
+        atomicMax(P.sync, static_cast<int>(hd.w));
+      }
+    }
+  }
+}
+
+// ---- plan construction / launch -------------------------------------------------------------
+namespace {
+struct WsConfig {
+  unsigned warps, stages;
+};
+WsConfig ws_config() {
+  WsConfig c;
+  c.warps  = static_cast<unsigned>(ws_env("HIFIR_B200_WS_WARPS", 16));
+  c.stages = static_cast<unsigned>(ws_env("HIFIR_B200_WS_STAGES", 4));
+  if (c.warps != 16u && c.warps != 32u && c.warps != 24u) c.warps = 16u;
+  if (c.stages < 2u || c.stages > 4u) c.stages = 4u;
+  return c;
+}
+}  // namespace
+
+void build_ws_plan(const HostCsr &S, bool upper, SweepPlan &plan, std::size_t *tally, unsigned nsm,
+                   const unsigned *rhs_index) {
+  const WsConfig cfg = ws_config();
+  plan.ws        = true;
+  plan.stream    = false;
+  plan.upper     = upper;
+  plan.nr        = 1;
+  plan.m         = static_cast<unsigned>(S.orig_rows);
+  plan.nblocks   = 0;
+  plan.ws_grid   = nsm;
+  plan.ws_warps  = cfg.warps;
+  plan.ws_stages = cfg.stages;
+  plan.ws_window = static_cast<unsigned>(std::max(1, ws_env("HIFIR_B200_WS_WINDOW", 2)));
+  if (!S.nrows) return;
+  WsHost H;
+  pack_warp_streams(S, H, nsm * cfg.warps, plan.ws_window, plan.f32, rhs_index);
+  ws_finalize_ring(H, cfg.stages);
+  plan.nblocks    = H.slices;
+  plan.slab_bytes = H.stream.size() * 4u;
+  plan.st_depth   = H.depth;
+  plan.st_padded  = H.padded;
+  plan.ws_nslots  = H.nslots;
+  plan.slot_of    = std::move(H.slot_of);
+  plan.ws_wdesc.upload(H.wdesc, tally);
+  plan.ws_stream.upload(H.stream, tally);
+}
+
+void ws_host_emulate(const HostCsr &S, bool upper, const double *rhs, const double *diag, double *x_by_row,
+                     std::size_t stats[4], bool f32) {
+  const WsConfig cfg = ws_config();
+  WsHost         H;
+  pack_warp_streams(S, H, 148u * cfg.warps, static_cast<unsigned>(std::max(1, ws_env("HIFIR_B200_WS_WINDOW", 2))), f32,
+                    nullptr);
+  ws_finalize_ring(H, cfg.stages);
+  std::vector<double> x(H.nslots, 0.0);
+  ws_host_emulate_packed(H, upper, f32, rhs, diag, x.data());
+  for (std::size_t r = 0; r < S.orig_rows; ++r) x_by_row[r] = x[H.slot_of[r]];
+  stats[0] = H.slices;
+  stats[1] = H.padded;
+  stats[2] = H.stream.size() * 4u;
+  stats[3] = H.depth;
+}
+
+namespace {
+template <bool UPPER, class VT, int kWarps, int kStages>
+void launch_ws_K(Handle *h, const SweepPlan &plan, const WsParams &P) {
+  constexpr unsigned kStageBytes = (kWsHdrWords + 64u + kWsU * 32u * (sizeof(VT) == 4 ? 2u : 3u)) * 4u;
+  constexpr unsigned smem        = kWarps * kStages * (8u + kStageBytes);
+  auto               kern        = wsweep_kernel<UPPER, VT, kWarps, kStages>;
+  // per device, once (cudaFuncSetAttribute is per device)
+  static bool configured[64] = {false};
+  if (h->device < 64 && !configured[h->device]) {
+    HIF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    configured[h->device] = true;
+  }
+  kern<<<plan.ws_grid, kWarps * 32, smem, h->stream>>>(P);
+}
+template <bool UPPER, class VT>
+void launch_ws_V(Handle *h, const SweepPlan &plan, const WsParams &P) {
+  const unsigned w = plan.ws_warps, s = plan.ws_stages;
+  if (w == 16 && s == 4)
+    launch_ws_K<UPPER, VT, 16, 4>(h, plan, P);
+  else if (w == 16 && s == 3)
+    launch_ws_K<UPPER, VT, 16, 3>(h, plan, P);
+  else if (w == 16 && s == 2)
+    launch_ws_K<UPPER, VT, 16, 2>(h, plan, P);
+  else if (w == 24 && s == 2)
+    launch_ws_K<UPPER, VT, 24, 2>(h, plan, P);
+  else if (w == 32 && s == 2)
+    launch_ws_K<UPPER, VT, 32, 2>(h, plan, P);
+  else
+    throw std::logic_error("unsupported warp-stream configuration (warps x stages)");
+}
+}  // namespace
+
+void launch_ws_sweep(Handle *h, const SweepPlan &plan, const double *rhs_plain, const unsigned long long *rhs_tagged,
+                     const double *diag, unsigned long long *x, unsigned parity, int *sync) {
+  if (!plan.nblocks) return;
+  WsParams P;
+  P.wdesc      = plan.ws_wdesc.p;
+  P.stream     = plan.ws_stream.p;
+  P.rhs_plain  = rhs_plain;
+  P.rhs_tagged = rhs_tagged;
+  P.diag       = diag;
+  P.x          = x;
+  P.sync       = sync;
+  P.error_flag = h->error_flag.p;
+  P.parity     = parity;
+  P.window     = plan.ws_window;
+  P.adm_sleep  = static_cast<unsigned>(std::max(0, ws_env("HIFIR_B200_WS_SLEEP", 200)));
+  P.poll_sleep = static_cast<unsigned>(std::max(0, ws_env("HIFIR_B200_WS_POLL_SLEEP", 0)));
+  P.publish_st = ws_env("HIFIR_B200_WS_PUBLISH_ST", 0);
+  if (plan.upper) {
+    if (plan.f32)
+      launch_ws_V<true, float>(h, plan, P);
+    else
+      launch_ws_V<true, double>(h, plan, P);
+  } else {
+    if (plan.f32)
+      launch_ws_V<false, float>(h, plan, P);
+    else
+      launch_ws_V<false, double>(h, plan, P);
+  }
+  HIF_KERNEL_CHECK();
+  ++h->launch_count;
+}
+
+}  // namespace hifgpu

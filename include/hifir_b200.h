@@ -233,11 +233,6 @@ LhfStatus lhfsGpuAttachFile(int device, const char *path, LhfsGpuHdl *out);
 /* info = {format version, single precision, levels, n, nnz of all blocks, has plans, entries of the
  * stored plans, their total dependency depth}; reads and verifies the whole file (host only) */
 LhfStatus lhfGpuFileInfo(const char *path, size_t info[8]);
-/* Host-only test hook: lhfdGpuDebugSweepHost on factor (level, upper) of an arena file, with the plan
- * stored in the file when it has one. */
-LhfStatus lhfGpuDebugFileSweepHost(const char *path, size_t level, int upper, const double *rhs, double *x,
-                                   size_t stats[4]);
-
 /* ---- the hot path, DEVICE buffers (asynchronous on the handle's stream) ---- */
 
 /* lhfdGpuApply on device buffers (no residual bounds): op in {LHF_S, LHF_SH, LHF_M, LHF_MH} */
@@ -284,37 +279,6 @@ LhfStatus lhfdGpuGetStats(LhfdGpuHdl hdl, size_t stats[/* LHF_GPU_NUMBER_STATS *
 LhfStatus lhfdGpuProfileSolveDev(LhfdGpuHdl hdl, const double *d_b, double *d_x, size_t rank,
                                  size_t max_entries, float *ms, size_t *count, char *names,
                                  size_t names_len);
-
-/* Host-only test hook (no GPU needed): packs the strictly triangular CCS block T into the
- * shared-memory slabs the device sweeps consume and solves with them on the CPU, block by
- * block in the device's order: x = T^{-1} rhs (lower, diag ignored) or x = T^{-1}(rhs./diag)
- * (upper).  stats = {blocks, halo entries, packed bytes, max shared bytes per block}.
- * Lets the host-side packing logic be checked bit-for-bit in the CPU test suite. */
-LhfStatus lhfdGpuDebugSweepHost(const LhfdGpuCcs *T, int upper, const double *rhs, const double *diag,
-                                double *x, size_t stats[4]);
-
-/* The same for a single-precision factor block on the streaming layout: the packed (merged) values
- * are rounded to float exactly as lhfsGpuAttachLevels stores them; rhs / diag / x are double. */
-LhfStatus lhfsGpuDebugSweepHost(const LhfsGpuCcs *T, int upper, const double *rhs, const double *diag,
-                                double *x, size_t stats[4]);
-
-/* Debug: run one apply with per-block tracing of one triangular sweep switched on
- * (level, which: 0 = down L, 1 = down U, 2 = up L, 3 = up U).  out[8*b + ...] for ticket b:
- * 0 start ns, 1 slab-in-shared ns, 2 last-row-done ns (globaltimer), 3 SM id, 4 polls of the
- * last row, 5 its thread, 6 poller passes, 7 unused. */
-LhfStatus lhfdGpuDebugTraceSweep(LhfdGpuHdl hdl, const double *d_b, double *d_x, int level, int which,
-                                 unsigned long long *out, size_t max_blocks, size_t *nblocks);
-
-/* Host-only developer tool: timing model of one sweep over the packed slabs.
- * prm = {CTA slots, row threads, t_load, c_s, c_g, t_dep, t_pub} (microseconds);
- * out = {total, sum of block lives, max block life, mean halo wait, mean tail, blocks}. */
-LhfStatus lhfdGpuDebugSimulateSweep(const LhfdGpuCcs *T, int upper, const double *prm, double *out);
-
-/* Host-only developer tool: block dependency graph of a packed sweep in ticket order.
- * info[4*b] = {first sweep row, rows, halo entries, nnz}; block b needs blocks
- * src_idx[src_ptr[b] .. src_ptr[b+1]). */
-LhfStatus lhfdGpuDebugBlockGraph(const LhfdGpuCcs *T, int upper, size_t max_blocks, size_t max_edges,
-                                 unsigned *info, unsigned *src_ptr, unsigned *src_idx, size_t *nblocks);
 
 /* per-level dependency depth of the L and U sweeps: depth[2*l], depth[2*l+1] */
 LhfStatus lhfdGpuGetDepths(LhfdGpuHdl hdl, size_t nlevels, size_t *depth);

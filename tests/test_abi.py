@@ -81,15 +81,15 @@ def test_attach_without_gpu_fails_loudly(lib):
     assert "cuda" in str(e.value).lower()
 
 
-SWEEP_MODES = [("stream", "1"), ("stream", "0"), ("slab", "1"), ("slab", "0")]
+SWEEP_MODES = [("ws", "1"), ("ws", "0"), ("stream", "1"), ("stream", "0")]
 
 
 @pytest.mark.parametrize("mode", SWEEP_MODES, ids=lambda m: f"{m[0]}-merge{m[1]}")
 @pytest.mark.parametrize("case", ["demo_A", "poisson14_ml", "stokes28_ml"])
 def test_sweep_packing_host_emulation(lib, case, mode, monkeypatch):
     """Host logic of the triangular sweeps: transform each L_B / U_B of the fixtures the way
-    attach does (algebraic level merging, merge.cu; level-major sliced-ELL packing, stream.cu;
-    or shared-memory slabs, sptrsv.cu) and solve with the packed data on the CPU -- must equal
+    attach does (algebraic level merging, merge.cu; packing into per-warp segment streams,
+    wsweep.cu; or round 1's level-major sliced ELL, stream.cu) and solve with the packed data on the CPU -- must equal
     plain substitution up to rounding (merging is an exact reformulation; the packed layouts
     list a row's entries by the dependency depth of their producers)."""
     import scipy.sparse as sp
@@ -118,9 +118,7 @@ def test_sweep_packing_host_emulation(lib, case, mode, monkeypatch):
                     acc -= v * ref[j]
                 ref[i] = acc
             assert np.linalg.norm(x - ref) <= 1e-13 * np.linalg.norm(ref), (case, name)
-            assert st["blocks"] >= 1 and st["bytes"] >= 10 * len(va)
-            if mode[0] == "slab":
-                assert st["max_smem"] <= 112 * 1024
+            assert st["slices"] >= 1 and st["bytes"] >= 10 * len(va)
 
 
 @pytest.mark.parametrize("merge", ["1", "0"])
@@ -130,7 +128,7 @@ def test_float_sweep_packing_host_emulation(lib, merge, monkeypatch):
     the float factor to float rounding -- far inside the 1e-5 gate."""
     import scipy.sparse as sp
     import scipy.sparse.linalg as spl
-    monkeypatch.setenv("HIFIR_B200_SWEEP", "stream")
+    # default sweep kernel (warp streams)
     monkeypatch.setenv("HIFIR_B200_MERGE", merge)
     g = load_golden("stokes28_ml_f32")
     rng = np.random.default_rng(2)
@@ -208,13 +206,12 @@ def test_level_merging_shortens_the_dependency_chain(lib, monkeypatch):
     L = g.levels[0]
     m = L["m"]
     rhs = np.random.default_rng(3).uniform(-1, 1, m)
-    monkeypatch.setenv("HIFIR_B200_SWEEP", "stream")
     depth = {}
     for merge in ("0", "1"):
         monkeypatch.setenv("HIFIR_B200_MERGE", merge)
         for name, upper in (("L", False), ("U", True)):
             x, st = hb.debug_sweep_host(L[name], upper, rhs, L["d"] if upper else None)
-            depth[(merge, name)] = st["max_smem"]  # stats[3] of the streaming emulation = dependency depth
+            depth[(merge, name)] = st["depth"]  # dependency depth of the packed factor
             depth[(merge, name, "bytes")] = st["bytes"]
     for name in ("L", "U"):
         assert depth[("1", name)] * 3 <= depth[("0", name)], depth

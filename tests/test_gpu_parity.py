@@ -51,10 +51,10 @@ def test_solve_matches_golden_and_oracle(golden):
         assert np.array_equal(x1, x3) and relerr(x2, x1) <= 1e-14
 
 
-@pytest.mark.parametrize("mode", [("stream", "0"), ("slab", "1"), ("slab", "0")], ids=lambda m: f"{m[0]}-merge{m[1]}")
+@pytest.mark.parametrize("mode", [("ws", "0"), ("stream", "1"), ("stream", "0")], ids=lambda m: f"{m[0]}-merge{m[1]}")
 def test_solve_other_sweep_kernels(golden, mode, monkeypatch):
     """The non-default sweep configurations (HIFIR_B200_SWEEP / HIFIR_B200_MERGE are read at attach):
-    unmerged factors on the streaming kernel, merged and unmerged factors on the shared-memory slab
+    unmerged factors on the warp-stream kernel, merged and unmerged factors on round 1's streaming
     kernel -- single and multi right-hand side."""
     monkeypatch.setenv("HIFIR_B200_SWEEP", mode[0])
     monkeypatch.setenv("HIFIR_B200_MERGE", mode[1])
@@ -363,10 +363,10 @@ def test_single_precision_preconditioner_matches_float_reference(golden_f32):
         assert st["bytes_factors"] < 0.8 * std["bytes_factors"]
 
 
-@pytest.mark.parametrize("mode", [("stream", "0"), ("slab", "1")], ids=lambda m: f"{m[0]}-merge{m[1]}")
+@pytest.mark.parametrize("mode", [("ws", "0"), ("stream", "1")], ids=lambda m: f"{m[0]}-merge{m[1]}")
 def test_single_precision_other_sweep_kernels(mode, monkeypatch):
-    """unmerged streaming (no rounding beyond the float factors themselves) and the slab kernel
-    (keeps double storage) serve a single-precision preconditioner too"""
+    """unmerged warp streams (no rounding beyond the float factors themselves) and round 1's streaming
+    kernel serve a single-precision preconditioner too"""
     from conftest import TOL_F32
     monkeypatch.setenv("HIFIR_B200_SWEEP", mode[0])
     monkeypatch.setenv("HIFIR_B200_MERGE", mode[1])
@@ -376,7 +376,7 @@ def test_single_precision_other_sweep_kernels(mode, monkeypatch):
         b = np.ascontiguousarray(g["B"][:, 1])
         x = G.solve(b)
         assert relerr(x, g["X"][:, 1]) <= TOL_F32
-        assert relerr(x, Oh.solve(b)) <= (1e-12 if mode == ("stream", "0") else 2e-6)
+        assert relerr(x, Oh.solve(b)) <= (1e-12 if mode[1] == "0" else 2e-6)
 
 
 @needs_ref
