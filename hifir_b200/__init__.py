@@ -16,7 +16,8 @@ import numpy as np
 __version__ = "0.1.0"
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_lib", "libhifir_b200.so")
+# HIFIR_B200_LIB: developer override (A/B of differently built libraries); the default is the in-tree build
+LIB_PATH = os.environ.get("HIFIR_B200_LIB") or os.path.join(_HERE, "_lib", "libhifir_b200.so")
 
 LHF_SUCCESS, LHF_NULL_OBJ, LHF_MISMATCHED_SIZES, LHF_BAD_PREC, LHF_HIFIR_ERROR = range(5)
 LHF_S, LHF_SH, LHF_M, LHF_MH = range(4)
@@ -125,6 +126,7 @@ def lib():
             "lhfdGpuDebugSweepHost": [vp, i, vp, vp, vp, vp],
             "lhfdGpuDebugPlanLab": [vp, i, vp, vp, vp],
             "lhfdGpuDebugExportInts": [vp, sz, i, vp, sz, vp],
+            "lhfdGpuDebugTraceSweep": [vp, vp, vp, i, i, vp, sz, vp],
             "lhfdGpuGetStats": [vp, vp],
             "lhfdGpuGetDepths": [vp, sz, vp],
             "lhfsGpuAttachLevels": [i, sz, vp, vp],
@@ -166,7 +168,7 @@ EXPORTED_SYMBOLS = (
     "lhfdGpuSaveLevels", "lhfsGpuSaveLevels", "lhfdGpuAttachFile", "lhfsGpuAttachFile", "lhfGpuFileInfo")
 # developer / test hooks declared in hifir_b200/csrc/debug_api.h (not part of the drop-in boundary)
 DEBUG_SYMBOLS = ("lhfdGpuDebugSweepHost", "lhfsGpuDebugSweepHost", "lhfGpuDebugFileSweepHost", "lhfdGpuDebugPlanLab",
-                 "lhfdGpuDebugExportInts")
+                 "lhfdGpuDebugExportInts", "lhfdGpuDebugTraceSweep")
 
 
 class LhfError(RuntimeError):
@@ -399,6 +401,14 @@ class GpuHif:
                                           C.byref(cnt), names, 8192))
         labels = names.value.decode().split("\n")
         return [(labels[k], float(ms[k])) for k in range(cnt.value)]
+
+    def trace_sweep(self, d_b, d_x, level, which, max_segs=1 << 20):
+        """per-segment trace of one warp-stream sweep: array [nsegs, 4] (see lhfdGpuDebugTraceSweep)"""
+        out = np.zeros(max_segs * 4, dtype=np.uint64)
+        ns = C.c_size_t()
+        _chk(lib().lhfdGpuDebugTraceSweep(self._h, C.c_void_p(d_b), C.c_void_p(d_x), level, which, _ptr(out),
+                                          max_segs, C.byref(ns)))
+        return out[: ns.value * 4].reshape(-1, 4)
 
     def export_ints(self, level, which):
         """lhfdGpuDebugExportInts: a device-resident index array of one level, copied back

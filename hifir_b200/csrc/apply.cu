@@ -203,12 +203,15 @@ void mark(Handle *h, const std::string &name) {
 }
 
 void launch_sweeps(Handle *h, DevLevel &D, const double *rhs, unsigned long long *xL, unsigned long long *xU,
-                   unsigned parity, int *tickets, const std::string &tag) {
+                   unsigned parity, int *tickets, const std::string &tag, int trace_base = -100) {
   if (!D.m) return;
-  launch_sweep(h, D.L, rhs, nullptr, nullptr, xL, parity, tickets);
+  const bool tl = h->trace_level >= 0 && &h->levels[h->trace_level] == &D;
+  launch_sweep(h, D.L, rhs, nullptr, nullptr, xL, parity, tickets, 0,
+               tl && h->trace_which == trace_base ? h->trace_buf.p : nullptr);
   mark(h, tag + "L");
   // the U sweep reads x_L at the L sweep's slots and divides by d (permuted to those slots)
-  launch_sweep(h, D.U, nullptr, xL, D.d_ls.p, xU, parity, tickets + h->tick_stride);
+  launch_sweep(h, D.U, nullptr, xL, D.d_ls.p, xU, parity, tickets + h->tick_stride, 0,
+               tl && h->trace_which == trace_base + 1 ? h->trace_buf.p : nullptr);
   mark(h, tag + "U");
 }
 
@@ -256,7 +259,7 @@ void apply_dev(Handle *h, const double *d_b, double *d_x, std::size_t rank) {
       ++h->launch_count;
     }
     if (D.nm) {
-      launch_sweeps(h, D, D.bhat.p, D.xL_dn.p, D.xU_dn.p, parity, h->tick(8 * l), "lv" + std::to_string(l) + ".down.");
+      launch_sweeps(h, D, D.bhat.p, D.xL_dn.p, D.xU_dn.p, parity, h->tick(8 * l), "lv" + std::to_string(l) + ".down.", 0);
       launch_spmv_resid<true>(h, D.E, D.E_xcol.p, D.xU_dn.p, D.bhat.p + D.m, D.r.p, "lv" + std::to_string(l) + ".E");
       b = D.r.p;
     }
@@ -276,7 +279,7 @@ void apply_dev(Handle *h, const double *d_b, double *d_x, std::size_t rank) {
       launch_spmv_resid<false>(h, D.F, D.F.col.p, D.ychild.p, D.bhat.p, D.g.p, "lv" + std::to_string(l) + ".F");
       rhs = D.g.p;
     }
-    launch_sweeps(h, D, rhs, D.xL_up.p, D.xU_up.p, parity, h->tick(8 * l + 2), "lv" + std::to_string(l) + ".up.");
+    launch_sweeps(h, D, rhs, D.xL_up.p, D.xU_up.p, parity, h->tick(8 * l + 2), "lv" + std::to_string(l) + ".up.", 2);
     if (D.n) {
       scatter_scale_kernel<<<cdiv(D.n, T), T, 0, h->stream>>>(static_cast<unsigned>(D.n), D.q_slot.p, D.t.p,
                                                              D.xU_up.p, D.ychild.p, y);
@@ -435,8 +438,17 @@ void check_sweep_error(Handle *h) {
   HIF_CUDA(cudaMemcpyAsync(h->h_error, h->error_flag.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
   HIF_CUDA(cudaStreamSynchronize(h->stream));
   if (*h->h_error) {
-    HIF_CUDA(cudaMemsetAsync(h->error_flag.p, 0, sizeof(int), h->stream));
-    throw std::runtime_error("a triangular sweep exceeded its spin limit (dependency never became ready)");
+    const int kind = *h->h_error;
+    int       info[8] = {0};
+    cudaMemcpy(info, h->error_flag.p, sizeof(info), cudaMemcpyDeviceToHost);
+    HIF_CUDA(cudaMemsetAsync(h->error_flag.p, 0, 8 * sizeof(int), h->stream));
+    std::string where;
+    if (info[1])  // the first failing wait left its coordinates (wsweep.cu, ws_fail)
+      where = " [warp " + std::to_string(info[2]) + " segment " + std::to_string(info[3]) + " level " +
+              std::to_string(info[4]) + " kind " + std::to_string(info[5]) + " detail " + std::to_string(info[6]) +
+              " parity " + std::to_string(info[7]) + "]";
+    throw std::runtime_error("a triangular sweep exceeded its spin limit (dependency never became ready; kind " +
+                             std::to_string(kind) + ")" + where);
   }
 }
 

@@ -355,7 +355,7 @@ Handle *attach_levels(int device, std::size_t nlevels, const LhfdGpuLevel *lv, b
     h->tick_stride = std::max<std::size_t>(
         {h->tick_stride, kSyncStride * (2 + D.L.st_depth), kSyncStride * (2 + D.U.st_depth)});
   h->tickets.alloc((8 * nlevels + 8) * h->tick_stride, tally);
-  h->error_flag.alloc(1, tally);
+  h->error_flag.alloc(8, tally);  // [0] flag, [1..7] coordinates of the first failing wait (wsweep.cu)
   HIF_CUDA(cudaMallocHost(&h->h_error, sizeof(int)));
   *h->h_error = 0;
   HIF_CUDA(cudaMallocHost(&h->h_scal, 256 * sizeof(double)));

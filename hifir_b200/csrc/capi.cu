@@ -623,6 +623,35 @@ LhfStatus lhfsGpuDebugSweepHost(const LhfsGpuCcs *T, int upper, const double *rh
   });
 }
 
+LhfStatus lhfdGpuDebugTraceSweep(LhfdGpuHdl hdl, const double *d_b, double *d_x, int level, int which,
+                                 unsigned long long *out, size_t max_segs, size_t *nsegs) {
+  REQUIRE_HANDLE(hdl);
+  REQUIRE_PTR(out, "out");
+  REQUIRE_PTR(nsegs, "nsegs");
+  return guarded([&] {
+    Handle *h = H(hdl);
+    if (level < 0 || static_cast<size_t>(level) >= h->levels.size() || which < 0 || which > 3)
+      throw std::invalid_argument("bad level / sweep selector");
+    const SweepPlan &plan = (which & 1) ? h->levels[level].U : h->levels[level].L;
+    if (!plan.ws) throw std::invalid_argument("tracing is implemented for the warp-stream sweeps");
+    if (h->trace_buf.n < 4ull * plan.ws_nsegs) h->trace_buf.alloc(4ull * plan.ws_nsegs);
+    HIF_CUDA(cudaMemsetAsync(h->trace_buf.p, 0, h->trace_buf.n * 8, h->stream));
+    h->trace_level = level;
+    h->trace_which = which;
+    try {
+      apply_dev(h, d_b, d_x, 0);
+      check_sweep_error(h);
+    } catch (...) {
+      h->trace_level = h->trace_which = -1;
+      throw;
+    }
+    h->trace_level = h->trace_which = -1;
+    const size_t ns = std::min<size_t>(plan.ws_nsegs, max_segs);
+    HIF_CUDA(cudaMemcpy(out, h->trace_buf.p, ns * 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    *nsegs = ns;
+  });
+}
+
 LhfStatus lhfdGpuDebugExportInts(LhfdGpuHdl hdl, size_t level, int which, int *out, size_t max, size_t *count) {
   REQUIRE_HANDLE(hdl);
   REQUIRE_PTR(out, "out");

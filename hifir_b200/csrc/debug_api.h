@@ -32,6 +32,13 @@ LhfStatus lhfGpuDebugFileSweepHost(const char *path, size_t level, int upper, co
 /* Host only: gather-locality statistics of candidate row orders / slot numberings (planlab.cu). */
 LhfStatus lhfdGpuDebugPlanLab(const LhfdGpuCcs *T, int upper, const int *key, const double *opts, double *out);
 
+/* One apply with per-segment tracing of one warp-stream sweep (level, which: 0 = down L, 1 = down U,
+ * 2 = up L, 3 = up U).  out[4*s + ...] for segment s (numbered warp by warp): 0 decoded at ns
+ * (globaltimer); relative to that: 1 admitted, 2 (first-try gathers returned) << 8 | re-poll rounds,
+ * 3 (published) << 16 | level (bit 15: copy segment). */
+LhfStatus lhfdGpuDebugTraceSweep(LhfdGpuHdl hdl, const double *d_b, double *d_x, int level, int which,
+                                 unsigned long long *out, size_t max_segs, size_t *nsegs);
+
 /* Bit-exact checks of the attach-time integer handling: copies the device-resident index arrays of
  * level `level` back to the host.  which: 0 p, 1 q_inv, 2 E row pointers, 3 E columns (original
  * numbering), 4 F row pointers, 5 F columns, 6 jpvt (level ignored).  out receives min(count, max)

@@ -151,7 +151,7 @@ struct SweepPlan {
   DevBuf<float>               st_vals32;
   // warp-stream layout (wsweep.cu): one private segment stream per warp of a persistent CTA per SM
   bool                        ws = false;
-  unsigned                    ws_grid = 0, ws_warps = 0, ws_stages = 0, ws_window = 0, ws_nslots = 0;
+  unsigned                    ws_grid = 0, ws_warps = 0, ws_stages = 0, ws_window = 0, ws_nslots = 0, ws_nsegs = 0;
   DevBuf<unsigned>            ws_wdesc;   // 8 words per global warp: offset (16 B units), segments, -, -, first 4 sizes
   DevBuf<unsigned>            ws_stream;  // segments
   std::vector<unsigned>       slot_of;    // host: solution slot of every original row (empty: identity)
@@ -257,6 +257,9 @@ struct Handle {
   // statistics
   std::size_t bytes_factors = 0, bytes_vec = 0, bytes_dense = 0, device_bytes = 0, nnz_total = 0;
   std::size_t kernels_per_apply = 0, launch_count = 0;
+  // debug: per-segment trace of one warp-stream sweep (lhfdGpuDebugTraceSweep)
+  int                        trace_level = -1, trace_which = -1;
+  DevBuf<unsigned long long> trace_buf;
   // optional per-kernel timing of one apply (lhfdGpuProfileSolveDev)
   bool                                  profiling = false;
   std::vector<std::pair<std::string, cudaEvent_t>> prof_marks;
@@ -282,7 +285,7 @@ void sweep_host_emulate(const HostCsr &T, bool upper, const double *rhs, const d
                         std::size_t stats[4], bool f32 = false);
 void launch_sweep(Handle *h, const SweepPlan &plan, const double *rhs_plain, const unsigned long long *rhs_tagged,
                   const double *diag, unsigned long long *x, unsigned parity, int *sync,
-                  unsigned nr = 0);  // nr = 0: the plan's own width
+                  unsigned nr = 0, unsigned long long *trace = nullptr);  // nr = 0: the plan's own width
 // ---- stream.cu
 void build_stream_plan(const HostCsr &S, bool upper, SweepPlan &plan, std::size_t *tally);
 void stream_host_emulate(const HostCsr &S, bool upper, const double *rhs, const double *diag, double *x,
@@ -317,7 +320,7 @@ struct WsHost {  // packed plan on the host
   unsigned                           nwarps = 0, nslots = 0, depth = 0, slices = 0;
   std::vector<unsigned>              wdesc, stream, slot_of, order;  // order: (warp, absolute word offset) in creation order
   std::vector<std::vector<unsigned>> seg_off;                        // per warp: word offsets of its segments (private stream)
-  std::size_t                        entries = 0, padded = 0, copy_rows = 0, max_segs = 0;
+  std::size_t                        entries = 0, padded = 0, copy_rows = 0, max_segs = 0, nsegs = 0;
 };
 void pack_warp_streams(const HostCsr &S, WsHost &H, unsigned nwarps, unsigned window, bool f32,
                        const unsigned *rhs_index);
@@ -328,7 +331,8 @@ void build_ws_plan(const HostCsr &S, bool upper, SweepPlan &plan, std::size_t *t
 void ws_host_emulate(const HostCsr &S, bool upper, const double *rhs, const double *diag, double *x_by_row,
                      std::size_t stats[4], bool f32);
 void launch_ws_sweep(Handle *h, const SweepPlan &plan, const double *rhs_plain, const unsigned long long *rhs_tagged,
-                     const double *diag, unsigned long long *x, unsigned parity, int *sync);
+                     const double *diag, unsigned long long *x, unsigned parity, int *sync,
+                     unsigned long long *trace = nullptr);
 int  sweep_kind();  // HIFIR_B200_SWEEP = ws (default) | stream | slab  ->  2 | 1 | 0
 
 // ---- planlab.cu (developer tool, host only)

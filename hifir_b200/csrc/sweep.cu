@@ -53,11 +53,12 @@ void sweep_host_emulate(const HostCsr &T, bool upper, const double *rhs, const d
 }
 
 void launch_sweep(Handle *h, const SweepPlan &plan, const double *rhs_plain, const unsigned long long *rhs_tagged,
-                  const double *diag, unsigned long long *x, unsigned parity, int *sync, unsigned nr) {
+                  const double *diag, unsigned long long *x, unsigned parity, int *sync, unsigned nr,
+                  unsigned long long *trace) {
   if (!plan.nblocks) return;
   if (plan.ws) {
     if (nr > 1) throw std::logic_error("the warp-stream plan serves one right-hand side");
-    launch_ws_sweep(h, plan, rhs_plain, rhs_tagged, diag, x, parity, sync);
+    launch_ws_sweep(h, plan, rhs_plain, rhs_tagged, diag, x, parity, sync, trace);
     return;
   }
   launch_stream_sweep(h, plan, rhs_plain, rhs_tagged, diag, x, parity, sync, nullptr, nr ? nr : plan.nr);

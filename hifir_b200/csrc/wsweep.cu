@@ -31,6 +31,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <numeric>
+#include <string>
 
 #include "hifgpu.h"
 
@@ -78,19 +79,35 @@ void pack_warp_streams(const HostCsr &S, WsHost &H, unsigned nwarps, unsigned wi
     depth  = std::max(depth, l + 1u);
   }
   auto rowlen = [&](unsigned i) { return S.ptr[i + 1] - S.ptr[i]; };
-  // class: lanes per row 2^z so that a lane holds <= kWsU entries (z = 5 beyond 256 entries: the
-  // slice then takes several segments)
-  auto zof = [&](unsigned len) {
+  // Entries per lane, chosen per level set: a thin level set is bound by the latency of one warp's
+  // round of scattered gathers (~1 us for 8 x 32 of them: an SM accepts one sector request per
+  // clock, a single warp one every ~5), so its rows are spread over as many lanes -- and warps --
+  // as there are: U_l = entries of the level / lanes of one warp group, clamped to [umin, 8].
+  const unsigned groups = static_cast<unsigned>(std::max(1, ws_env("HIFIR_B200_WS_GROUPS", 2)));
+  const unsigned umin   = static_cast<unsigned>(std::min(8, std::max(1, ws_env("HIFIR_B200_WS_UMIN", 1))));
+  const unsigned gwarps = std::max(1u, nwarps / groups);  // warps that serve one level set of a thin stretch
+  std::vector<unsigned> ulev(depth, kWsU);
+  {
+    std::vector<double> ent_l(depth, 0.0);
+    for (unsigned i = 0; i < n; ++i) ent_l[lev[i]] += rowlen(i);
+    for (unsigned l = 0; l < depth; ++l) {
+      const double u = std::ceil(ent_l[l] / (32.0 * gwarps));
+      ulev[l]        = static_cast<unsigned>(std::min<double>(kWsU, std::max<double>(umin, u)));
+    }
+  }
+  // class: lanes per row 2^z so that a lane holds <= U_l entries (z = 5 at most: beyond, a lane holds
+  // more, and beyond 8 per lane the slice takes several segments)
+  auto zof = [&](unsigned len, unsigned U) {
     unsigned z = 0;
-    while (z < 5u && ((len + (1u << z) - 1u) >> z) > kWsU) ++z;
+    while (z < 5u && ((len + (1u << z) - 1u) >> z) > U) ++z;
     return z;
   };
   std::vector<unsigned char> cls(n), bkt(n);
   for (unsigned i = 0; i < n; ++i) {
     const unsigned len = rowlen(i);
-    cls[i]             = static_cast<unsigned char>(len ? zof(len) : 0u);
+    cls[i]             = static_cast<unsigned char>(len ? zof(len, ulev[lev[i]]) : 0u);
     const unsigned w   = (len + (1u << cls[i]) - 1u) >> cls[i];
-    bkt[i] = static_cast<unsigned char>(len == 0 ? 0u : w <= 2 ? 1u : w <= 4 ? 2u : w <= 6 ? 3u : w <= 8 ? 4u : 5u);
+    bkt[i] = static_cast<unsigned char>(len == 0 ? 0u : w <= 1 ? 1u : w <= 2 ? 2u : w <= 4 ? 3u : w <= 6 ? 4u : w <= 8 ? 5u : 6u);
   }
   // slots: level-major, sweep order inside a level set (rows of S are in sweep order)
   std::vector<unsigned> slot(n);
@@ -122,7 +139,17 @@ void pack_warp_streams(const HostCsr &S, WsHost &H, unsigned nwarps, unsigned wi
   std::vector<std::vector<unsigned>> ws(nwarps);  // private streams
   std::vector<std::vector<unsigned>> seg_off(nwarps);
   std::vector<unsigned>              sentinel_of_level(depth, kWsNone);
-  unsigned                           q = 0;
+  // Slice q of a level set goes to warp q % nwarps -- the count restarts with every level set, so
+  // the thin level sets at the top of the elimination tree (<= one slice per SM) are all served by
+  // the same warps, which then walk from level to level without ever waiting for admission; a
+  // warp is throttled by a sentinel only when it JUMPS more than `window` level sets ahead of its
+  // previous segment.
+  // Consecutive level sets start at different warp GROUPS (level l at warp (l % groups) * nwarps /
+  // groups): while one group re-polls for the results of level l - 1, the other has its first
+  // round of gathers for level l + 1 in flight.
+  std::vector<int>                   last_level(nwarps, -1000000);
+  unsigned                           q = 0, nslices = 0, cur_level = 0;
+  const unsigned                     jump_after = std::max(window, groups);
   std::vector<unsigned>              ent;
   auto rhs_code = [&](unsigned i) {
     const unsigned code = S.gid[i];
@@ -139,14 +166,17 @@ void pack_warp_streams(const HostCsr &S, WsHost &H, unsigned nwarps, unsigned wi
     unsigned *hd = st.data() + o;
     hd[0]        = width | (z << 8) | (flags << 16);
     hd[1]        = 0;  // size of the segment `stages` ahead: filled by the kernel-side ring depth at finalize
-    hd[2]        = level >= window ? sentinel_of_level[level - window] : kWsNone;
+    const bool jump = static_cast<int>(level) - last_level[warp] > static_cast<int>(jump_after);
+    hd[2]        = (jump && level >= window) ? sentinel_of_level[level - window] : kWsNone;
     hd[3]        = level;
+    last_level[warp] = static_cast<int>(level);
     H.order.push_back(warp);
     H.order.push_back(o);
     return hd;
   };
   for (unsigned p = 0; p < n;) {
     const unsigned i0 = ord[p], l = lev[i0];
+    if (l != cur_level) cur_level = l, q = (l % groups) * gwarps;
     if (rowlen(i0) == 0) {  // COPY segment: up to 8 rows per lane
       unsigned cnt = 1;
       while (cnt < 32u * kWsU && p + cnt < n && lev[ord[p + cnt]] == l && rowlen(ord[p + cnt]) == 0) ++cnt;
@@ -159,7 +189,7 @@ void pack_warp_streams(const HostCsr &S, WsHost &H, unsigned nwarps, unsigned wi
         slots[r] = r < cnt ? slot[ord[p + r]] : kWsNone;
       }
       sentinel_of_level[l] = slot[ord[p + cnt - 1u]];
-      ++q;
+      ++q, ++nslices;
       p += cnt;
       H.copy_rows += cnt;
       continue;
@@ -204,24 +234,27 @@ void pack_warp_streams(const HostCsr &S, WsHost &H, unsigned nwarps, unsigned wi
         if (sg == 0) H.padded += static_cast<std::size_t>(width) * lpr - (e - b);
       }
     }
-    H.entries += 0;
     sentinel_of_level[l] = slot[ord[p + cnt - 1u]];
-    ++q;
+    ++q, ++nslices;
     p += cnt;
   }
   H.entries = S.col.size();
   H.depth   = depth;
-  H.slices  = q;
+  H.slices  = nslices;
+  H.nsegs   = H.order.size() / 2u;
   // ---- concatenate the private streams; descriptor = {offset (words / 4), segments, 0, 0, first sizes}
   std::size_t total = 0;
   for (unsigned w = 0; w < nwarps; ++w) total += ws[w].size();
   if (total / 4u > 0xffffffffull) throw std::length_error("warp streams too large");
   H.stream.reserve(total);
   H.max_segs = 0;
+  unsigned seg_base = 0;
   for (unsigned w = 0; w < nwarps; ++w) {
     unsigned *d = H.wdesc.data() + static_cast<std::size_t>(w) * 8u;
     d[0]        = static_cast<unsigned>(H.stream.size() / 4u);
     d[1]        = static_cast<unsigned>(seg_off[w].size());
+    d[2]        = seg_base;  // first segment of the warp in the global numbering (trace records)
+    seg_base += d[1];
     H.max_segs  = std::max<std::size_t>(H.max_segs, seg_off[w].size());
     H.stream.insert(H.stream.end(), ws[w].begin(), ws[w].end());
   }
@@ -302,6 +335,56 @@ void ws_host_emulate_packed(const WsHost &H, bool upper, bool f32, const double 
   }
 }
 
+// Dataflow check of a packed plan (host only): every warp walks its stream in order, a segment can
+// run when its sentinel and every slot it gathers are published.  Returns the number of segments
+// that can never run (0 = the static schedule is deadlock free).
+std::size_t ws_check_schedule(const WsHost &H, bool f32, std::string *why) {
+  std::vector<char>        ready(H.nslots, 0);
+  std::vector<std::size_t> pos(H.nwarps, 0);
+  std::size_t              left = 0;
+  for (unsigned w = 0; w < H.nwarps; ++w) left += H.seg_off[w].size();
+  (void)f32;
+  for (bool progress = true; progress && left;) {
+    progress = false;
+    for (unsigned w = 0; w < H.nwarps; ++w) {
+      const std::size_t base = static_cast<std::size_t>(H.wdesc[static_cast<std::size_t>(w) * 8u]) * 4u;
+      while (pos[w] < H.seg_off[w].size()) {
+        const unsigned *hd    = H.stream.data() + base + H.seg_off[w][pos[w]];
+        const unsigned  width = hd[0] & 0xffu, flags = hd[0] >> 16;
+        bool            ok    = hd[2] == kWsNone || ready[hd[2]];
+        if (ok && !(flags & kSegCopy)) {
+          const unsigned *cols = hd + kWsHdrWords + 64u;
+          for (unsigned k = 0; k < width * 32u && ok; ++k)
+            if (cols[k] != kWsNone && !ready[cols[k]]) ok = false;
+        }
+        if (!ok) break;
+        if (flags & kSegCopy) {
+          const unsigned *slots = hd + kWsHdrWords + width * 32u;
+          for (unsigned r = 0; r < width * 32u; ++r)
+            if (slots[r] != kWsNone) ready[slots[r]] = 1;
+        } else if (flags & kSegLast) {
+          const unsigned *slots = hd + kWsHdrWords + 32u;
+          for (unsigned j = 0; j < 32u; ++j)
+            if (slots[j] != kWsNone) ready[slots[j]] = 1;
+        }
+        ++pos[w];
+        --left;
+        progress = true;
+      }
+    }
+  }
+  if (left && why) {
+    for (unsigned w = 0; w < H.nwarps && why->size() < 400; ++w)
+      if (pos[w] < H.seg_off[w].size()) {
+        const std::size_t base = static_cast<std::size_t>(H.wdesc[static_cast<std::size_t>(w) * 8u]) * 4u;
+        const unsigned *  hd   = H.stream.data() + base + H.seg_off[w][pos[w]];
+        *why += " warp " + std::to_string(w) + " seg " + std::to_string(pos[w]) + " level " + std::to_string(hd[3]) +
+                " sentinel " + std::to_string(hd[2]) + ";";
+      }
+  }
+  return left;
+}
+
 // ---- device ----------------------------------------------------------------------------
 namespace {
 __device__ __forceinline__ unsigned ws_smem_addr(const void *p) { return static_cast<unsigned>(__cvta_generic_to_shared(p)); }
@@ -351,11 +434,45 @@ struct WsParams {
   int *                     error_flag;
   unsigned                  parity, window, adm_sleep, poll_sleep;
   int                       publish_st;
+  unsigned                  spin_limit;  // poll rounds after which a wait gives up (and every other wait with it)
+  unsigned long long *      trace;  // kTrace: 4 words per segment (decoded, admitted, gathered | rounds, published | level)
 };
 
 // One persistent CTA per SM, kWarps warps; warp (blockIdx.x + gridDim.x * warp) owns stream
 // wdesc[..].  kStages ring stages of kStageBytes each per warp.
-template <bool UPPER, class VT, int kWarps, int kStages>
+// first failing wait: remember where (error_flag[1..]: claimed, global warp, segment, level, kind, detail, upper)
+__device__ __noinline__ void ws_fail(const WsParams &P, unsigned gw, unsigned k, unsigned level, int kind, unsigned detail) {
+  if (atomicCAS(P.error_flag + 1, 0, 1) == 0) {
+    P.error_flag[2] = static_cast<int>(gw);
+    P.error_flag[3] = static_cast<int>(k);
+    P.error_flag[4] = static_cast<int>(level);
+    P.error_flag[5] = kind;
+    P.error_flag[6] = static_cast<int>(detail);
+    P.error_flag[7] = static_cast<int>(P.parity);
+    __threadfence();
+  }
+  atomicExch(P.error_flag, kind);
+}
+__device__ __forceinline__ bool ws_aborted(const WsParams &P) { return ws_ld_poll_i32(P.error_flag) != 0; }
+
+// The ring stage of a segment may be refilled (an ASYNC-proxy write by the TMA unit) only when every
+// lane's shared-memory reads of it have RETURNED: a warp barrier only orders their issue, and under
+// load a shared-memory read can sit in the SM's load/store queue behind thousands of cycles of
+// scattered global gathers of all the warps -- longer than a bulk copy from L2 takes to land
+// (measured: stale stages -> wrong indices -> illegal addresses / rows that never become ready).
+// A warp vote over a value derived from everything a lane has loaded can not be issued before
+// those loads have written their registers.
+__device__ __forceinline__ bool ws_reads_done(unsigned digest) {
+  return __ballot_sync(0xffffffffu, digest == 0x9e3779b9u) != 0xffffffffu;  // (practically) always true
+}
+
+__device__ __forceinline__ unsigned long long ws_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+template <bool UPPER, class VT, int kWarps, int kStages, bool kTrace>
 __global__ void __launch_bounds__(kWarps * 32, 1) wsweep_kernel(const WsParams P) {
   constexpr unsigned kStageBytes = (kWsHdrWords + 64u + kWsU * 32u * (sizeof(VT) == 4 ? 2u : 3u)) * 4u;
   extern __shared__ __align__(128) unsigned char smem[];
@@ -387,16 +504,23 @@ __global__ void __launch_bounds__(kWarps * 32, 1) wsweep_kernel(const WsParams P
     const unsigned stage = k % kStages, phase = (k / kStages) & 1u;
     {
       unsigned spins = 0;
+      bool ok = true;
       while (!ws_mbar_try_wait(bar0 + stage * 8u, phase)) {
-        if (++spins > kSpinLimit) {
-          *P.error_flag = 2;
+        if (++spins > P.spin_limit || ((spins & 255u) == 255u && ws_aborted(P))) {
+          ok = false;
           break;
         }
+      }
+      if (!ok) {  // the stage never arrived (or another warp gave up): stop, never decode garbage
+        if (lane == 0 && !ws_aborted(P)) ws_fail(P, gw, k, 0u, 2, stage);
+        return;
       }
     }
     const unsigned *sg    = reinterpret_cast<const unsigned *>(ring + stage * kStageBytes);
     const uint4     hd    = *reinterpret_cast<const uint4 *>(sg);
     const unsigned  width = hd.x & 0xffu, z = (hd.x >> 8) & 0xffu, flags = hd.x >> 16;
+    unsigned long long *tr = kTrace ? P.trace + 4ull * (d0.z + k) : nullptr;
+    if (kTrace && lane == 0) tr[0] = ws_timer_ns();
     if (flags & kSegCopy) {
       // rows without entries: x = rhs, 8 per lane, all loads in flight together
       unsigned code[kWsU], slot[kWsU];
@@ -408,11 +532,15 @@ __global__ void __launch_bounds__(kWarps * 32, 1) wsweep_kernel(const WsParams P
           slot[u] = sg[kWsHdrWords + (width + u) * 32u + lane];
         }
       }
-      __syncwarp();
-      if (lane == 0 && hd.y) {
-        ws_mbar_expect_tx(bar0 + stage * 8u, hd.y * 16u);
-        ws_tma_g2s(ws_smem_addr(ring + stage * kStageBytes), src, hd.y * 16u, bar0 + stage * 8u);
-        src += static_cast<std::size_t>(hd.y) * 16u;
+      {
+        unsigned digest = hd.x;
+#pragma unroll
+        for (unsigned u = 0; u < kWsU; ++u) digest ^= code[u] + 3u * slot[u];
+        if (ws_reads_done(digest) && lane == 0 && hd.y) {
+          ws_mbar_expect_tx(bar0 + stage * 8u, hd.y * 16u);
+          ws_tma_g2s(ws_smem_addr(ring + stage * kStageBytes), src, hd.y * 16u, bar0 + stage * 8u);
+          src += static_cast<std::size_t>(hd.y) * 16u;
+        }
       }
       double v[kWsU];
 #pragma unroll
@@ -423,8 +551,8 @@ __global__ void __launch_bounds__(kWarps * 32, 1) wsweep_kernel(const WsParams P
           if (UPPER) {
             unsigned long long t = ld_poll(P.rhs_tagged + r);
             for (unsigned spins = 0; !tag_ready(t, parity); t = ld_poll(P.rhs_tagged + r))
-              if (++spins > kSpinLimit) {
-                *P.error_flag = 3;
+              if (++spins > P.spin_limit || ((spins & 255u) == 255u && ws_aborted(P))) {
+                if (!ws_aborted(P)) ws_fail(P, gw, k, hd.w, 3, r);
                 break;
               }
             v[u] = tag_value(t) / P.diag[r];
@@ -440,9 +568,10 @@ __global__ void __launch_bounds__(kWarps * 32, 1) wsweep_kernel(const WsParams P
         my_front = hd.w;
         atomicMax(P.sync, static_cast<int>(hd.w));
       }
+      if (kTrace && lane == 0) tr[1] = tr[2] = 0, tr[3] = ((ws_timer_ns() - tr[0]) << 16) | hd.w | 0x8000u;
       continue;
     }
-    // ---- a slice segment: codes, slots, <= 8 entries per lane
+    // ---- a slice segment: codes, slots, <= 8 entries per lane -- all shared-memory reads first
     const unsigned code = sg[kWsHdrWords + lane];
     const unsigned slot = sg[kWsHdrWords + 32u + lane];
     unsigned       cc[kWsU];
@@ -457,15 +586,32 @@ __global__ void __launch_bounds__(kWarps * 32, 1) wsweep_kernel(const WsParams P
         vv[u] = sv[u * 32u + lane];
       }
     }
-    __syncwarp();  // every lane has read the stage: refill it with the segment kStages ahead
-    if (lane == 0 && hd.y) {
-      ws_mbar_expect_tx(bar0 + stage * 8u, hd.y * 16u);
-      ws_tma_g2s(ws_smem_addr(ring + stage * kStageBytes), src, hd.y * 16u, bar0 + stage * 8u);
-      src += static_cast<std::size_t>(hd.y) * 16u;
+    // ---- admission (only a warp that jumps ahead carries a sentinel): the sentinel row of level
+    // (this - window) is published
+    if (hd.z != kWsNone) {
+      if (lane == 0) {
+        unsigned       spins = 0;
+        const unsigned need  = hd.w - P.window;
+        while (!tag_ready(ld_poll(P.x + hd.z), parity)) {
+          // far from the frontier: sleep in proportion to the distance; close to it: spin on the sentinel
+          const unsigned f = static_cast<unsigned>(ws_ld_poll_i32(P.sync));
+          if (need > f + 1u) __nanosleep(min((need - f) * P.adm_sleep, 20000u));
+          if (++spins > P.spin_limit || ((spins & 63u) == 63u && ws_aborted(P))) {
+            if (!ws_aborted(P)) ws_fail(P, gw, k, hd.w, 4, hd.z);
+            break;
+          }
+        }
+      }
+      __syncwarp();
     }
+    if (kTrace && lane == 0) tr[1] = ws_timer_ns() - tr[0];
+    // ---- gather all entries optimistically (re-polled below if not ready), right-hand side beside them
+    unsigned long long g[kWsU];
+#pragma unroll
+    for (unsigned u = 0; u < kWsU; ++u)
+      if (cc[u] != kWsNone) g[u] = ld_poll(P.x + cc[u]);
     const unsigned lpr = 1u << z;
     const bool     own = slot != kWsNone && (lane & (lpr - 1u)) == 0u;
-    // ---- right-hand side (in flight beside the gathers)
     double             rhs_v  = 0.0, dg = 1.0;
     unsigned long long rhs_t  = 0;
     const bool         want_r = (flags & kSegFirst) && own && !(code & kCodeZeroRhs);
@@ -478,34 +624,36 @@ __global__ void __launch_bounds__(kWarps * 32, 1) wsweep_kernel(const WsParams P
         rhs_v = P.rhs_plain[r];
       }
     }
-    // ---- admission: the sentinel of level (this - window) is published
-    if (hd.z != kWsNone) {
-      if (lane == 0) {
-        unsigned spins = 0;
-        while (!tag_ready(ld_poll(P.x + hd.z), parity)) {
-          const unsigned f    = static_cast<unsigned>(ws_ld_poll_i32(P.sync));
-          const unsigned need = hd.w - P.window;
-          const unsigned dist = need > f ? need - f : 0u;
-          __nanosleep(min(dist * P.adm_sleep + 32u, 20000u));
-          if (++spins > (kSpinLimit >> 4)) {
-            *P.error_flag = 1;
-            break;
-          }
+    // ---- every lane's reads of the stage have returned: refill it with the segment kStages ahead
+    {
+      unsigned digest = code + 3u * slot;
+#pragma unroll
+      for (unsigned u = 0; u < kWsU; ++u) {
+        digest ^= cc[u];
+        if (sizeof(VT) == 8) {
+          const unsigned long long b = static_cast<unsigned long long>(__double_as_longlong(static_cast<double>(vv[u])));
+          digest += static_cast<unsigned>(b) ^ static_cast<unsigned>(b >> 32);
+        } else {
+          digest += __float_as_uint(static_cast<float>(vv[u]));
         }
       }
-      __syncwarp();
+      if (ws_reads_done(digest) && lane == 0 && hd.y) {
+        ws_mbar_expect_tx(bar0 + stage * 8u, hd.y * 16u);
+        ws_tma_g2s(ws_smem_addr(ring + stage * kStageBytes), src, hd.y * 16u, bar0 + stage * 8u);
+        src += static_cast<std::size_t>(hd.y) * 16u;
+      }
     }
-    // ---- gather all entries optimistically, re-poll the ones that are not ready
-    unsigned long long g[kWsU];
-    unsigned           pend = 0;
-#pragma unroll
-    for (unsigned u = 0; u < kWsU; ++u)
-      if (cc[u] != kWsNone) g[u] = ld_poll(P.x + cc[u]);
+    unsigned pend = 0, nrounds = 0;
 #pragma unroll
     for (unsigned u = 0; u < kWsU; ++u)
       if (cc[u] != kWsNone && !tag_ready(g[u], parity)) pend |= 1u << u;
     if (UPPER && want_r && !tag_ready(rhs_t, parity)) pend |= 1u << kWsU;
+    if (kTrace) {
+      const unsigned any = __ballot_sync(0xffffffffu, pend != 0u);  // depends on every first-try gather
+      if (lane == 0) tr[2] = ws_timer_ns() - tr[0] + (any == 0xdeadbeefu ? 1u : 0u);
+    }
     for (unsigned rounds = 0; __any_sync(0xffffffffu, pend != 0u);) {
+      if (kTrace) ++nrounds;
       if (P.poll_sleep) __nanosleep(P.poll_sleep);
 #pragma unroll
       for (unsigned u = 0; u < kWsU; ++u)
@@ -515,8 +663,15 @@ __global__ void __launch_bounds__(kWarps * 32, 1) wsweep_kernel(const WsParams P
       for (unsigned u = 0; u < kWsU; ++u)
         if ((pend & (1u << u)) && tag_ready(g[u], parity)) pend &= ~(1u << u);
       if (UPPER && (pend & (1u << kWsU)) && tag_ready(rhs_t, parity)) pend &= ~(1u << kWsU);
-      if (++rounds > (kSpinLimit >> 3)) {  // hang guard: flag the error, go on with garbage
-        *P.error_flag = 1;
+      if (++rounds > P.spin_limit || ((rounds & 255u) == 255u && ws_aborted(P))) {
+        // hang guard: a dependency never became ready (or another warp gave up) -- remember where, go on
+        if (pend && !ws_aborted(P)) {
+          unsigned which = kWsNone;
+#pragma unroll
+          for (unsigned u = 0; u < kWsU; ++u)
+            if (pend & (1u << u)) which = cc[u];
+          ws_fail(P, gw, k, hd.w, 1, which);
+        }
         break;
       }
     }
@@ -535,6 +690,10 @@ __global__ void __launch_bounds__(kWarps * 32, 1) wsweep_kernel(const WsParams P
         my_front = hd.w;
         atomicMax(P.sync, static_cast<int>(hd.w));
       }
+    }
+    if (kTrace && lane == 0) {
+      tr[2] = (tr[2] << 8) | min(nrounds, 255u);
+      tr[3] = ((ws_timer_ns() - tr[0]) << 16) | hd.w;
     }
   }
 }
@@ -576,6 +735,7 @@ void build_ws_plan(const HostCsr &S, bool upper, SweepPlan &plan, std::size_t *t
   plan.st_depth   = H.depth;
   plan.st_padded  = H.padded;
   plan.ws_nslots  = H.nslots;
+  plan.ws_nsegs   = static_cast<unsigned>(H.nsegs);
   plan.slot_of    = std::move(H.slot_of);
   plan.ws_wdesc.upload(H.wdesc, tally);
   plan.ws_stream.upload(H.stream, tally);
@@ -588,6 +748,11 @@ void ws_host_emulate(const HostCsr &S, bool upper, const double *rhs, const doub
   pack_warp_streams(S, H, 148u * cfg.warps, static_cast<unsigned>(std::max(1, ws_env("HIFIR_B200_WS_WINDOW", 2))), f32,
                     nullptr);
   ws_finalize_ring(H, cfg.stages);
+  {
+    std::string       why;
+    const std::size_t stuck = ws_check_schedule(H, f32, &why);
+    if (stuck) throw std::logic_error("warp-stream schedule can not complete: " + std::to_string(stuck) + " segments stuck;" + why);
+  }
   std::vector<double> x(H.nslots, 0.0);
   ws_host_emulate_packed(H, upper, f32, rhs, diag, x.data());
   for (std::size_t r = 0; r < S.orig_rows; ++r) x_by_row[r] = x[H.slot_of[r]];
@@ -602,12 +767,19 @@ template <bool UPPER, class VT, int kWarps, int kStages>
 void launch_ws_K(Handle *h, const SweepPlan &plan, const WsParams &P) {
   constexpr unsigned kStageBytes = (kWsHdrWords + 64u + kWsU * 32u * (sizeof(VT) == 4 ? 2u : 3u)) * 4u;
   constexpr unsigned smem        = kWarps * kStages * (8u + kStageBytes);
-  auto               kern        = wsweep_kernel<UPPER, VT, kWarps, kStages>;
+  auto               kern        = wsweep_kernel<UPPER, VT, kWarps, kStages, false>;
   // per device, once (cudaFuncSetAttribute is per device)
   static bool configured[64] = {false};
   if (h->device < 64 && !configured[h->device]) {
     HIF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     configured[h->device] = true;
+  }
+  if (P.trace) {
+    if (kWarps != 16 || kStages != 4 || sizeof(VT) != 8) throw std::logic_error("tracing needs the 16 x 4 double configuration");
+    auto tk = wsweep_kernel<UPPER, double, 16, 4, true>;
+    HIF_CUDA(cudaFuncSetAttribute(tk, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    tk<<<plan.ws_grid, kWarps * 32, smem, h->stream>>>(P);
+    return;
   }
   kern<<<plan.ws_grid, kWarps * 32, smem, h->stream>>>(P);
 }
@@ -630,9 +802,10 @@ void launch_ws_V(Handle *h, const SweepPlan &plan, const WsParams &P) {
 }  // namespace
 
 void launch_ws_sweep(Handle *h, const SweepPlan &plan, const double *rhs_plain, const unsigned long long *rhs_tagged,
-                     const double *diag, unsigned long long *x, unsigned parity, int *sync) {
+                     const double *diag, unsigned long long *x, unsigned parity, int *sync, unsigned long long *trace) {
   if (!plan.nblocks) return;
   WsParams P;
+  P.trace      = trace;
   P.wdesc      = plan.ws_wdesc.p;
   P.stream     = plan.ws_stream.p;
   P.rhs_plain  = rhs_plain;
@@ -646,6 +819,7 @@ void launch_ws_sweep(Handle *h, const SweepPlan &plan, const double *rhs_plain, 
   P.adm_sleep  = static_cast<unsigned>(std::max(0, ws_env("HIFIR_B200_WS_SLEEP", 200)));
   P.poll_sleep = static_cast<unsigned>(std::max(0, ws_env("HIFIR_B200_WS_POLL_SLEEP", 0)));
   P.publish_st = ws_env("HIFIR_B200_WS_PUBLISH_ST", 0);
+  P.spin_limit = static_cast<unsigned>(std::max(1000, ws_env("HIFIR_B200_WS_SPIN_LIMIT", 1 << 21)));
   if (plan.upper) {
     if (plan.f32)
       launch_ws_V<true, float>(h, plan, P);

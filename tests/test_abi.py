@@ -215,7 +215,9 @@ def test_level_merging_shortens_the_dependency_chain(lib, monkeypatch):
             depth[(merge, name, "bytes")] = st["bytes"]
     for name in ("L", "U"):
         assert depth[("1", name)] * 3 <= depth[("0", name)], depth
-        assert depth[("1", name, "bytes")] <= 5 * depth[("0", name, "bytes")], depth  # tiny factor: no cap but gain / row_cap binds
+        # tiny factor: no cap but gain / row_cap binds; a thin level set is spread over many lanes
+        # (few entries per lane), which costs segment headers
+        assert depth[("1", name, "bytes")] <= 8 * depth[("0", name, "bytes")], depth
 
 
 REF_SRC = "/root/reference/src"
