@@ -127,6 +127,7 @@ def lib():
             "lhfdGpuDebugPlanLab": [vp, i, vp, vp, vp],
             "lhfdGpuDebugExportInts": [vp, sz, i, vp, sz, vp],
             "lhfdGpuDebugTraceSweep": [vp, vp, vp, i, i, vp, sz, vp],
+            "lhfdGpuDebugSegmentGraph": [vp, i, sz, sz, vp, vp, vp],
             "lhfdGpuGetStats": [vp, vp],
             "lhfdGpuGetDepths": [vp, sz, vp],
             "lhfsGpuAttachLevels": [i, sz, vp, vp],
@@ -168,7 +169,7 @@ EXPORTED_SYMBOLS = (
     "lhfdGpuSaveLevels", "lhfsGpuSaveLevels", "lhfdGpuAttachFile", "lhfsGpuAttachFile", "lhfGpuFileInfo")
 # developer / test hooks declared in hifir_b200/csrc/debug_api.h (not part of the drop-in boundary)
 DEBUG_SYMBOLS = ("lhfdGpuDebugSweepHost", "lhfsGpuDebugSweepHost", "lhfGpuDebugFileSweepHost", "lhfdGpuDebugPlanLab",
-                 "lhfdGpuDebugExportInts", "lhfdGpuDebugTraceSweep")
+                 "lhfdGpuDebugExportInts", "lhfdGpuDebugTraceSweep", "lhfdGpuDebugSegmentGraph")
 
 
 class LhfError(RuntimeError):
@@ -199,6 +200,21 @@ def debug_sweep_host(block, upper, rhs, diag=None):
     _chk(f(C.byref(c), int(upper), _ptr(rhs), _ptr(d) if d is not None else None,
                                      _ptr(x), _ptr(st)))
     return x, dict(zip(("slices", "padded", "bytes", "depth"), (int(v) for v in st)))
+
+
+def debug_segment_graph(block, upper, max_segs=1 << 19, max_deps=1 << 26):
+    """lhfdGpuDebugSegmentGraph: (dep_ptr, dep_idx) of the packed warp streams, trace numbering"""
+    nr, nc, cs, ri, va = block
+    cs = np.ascontiguousarray(cs, dtype=np.int64)
+    ri = np.ascontiguousarray(ri, dtype=np.int32)
+    va = np.ascontiguousarray(va, dtype=np.float64)
+    c = LhfdGpuCcs(nr, nc, _ptr(cs), _ptr(ri), _ptr(va))
+    dp = np.zeros(max_segs + 1, dtype=np.uint32)
+    di = np.zeros(max_deps, dtype=np.uint32)
+    ns = C.c_size_t()
+    _chk(lib().lhfdGpuDebugSegmentGraph(C.byref(c), int(upper), max_segs, max_deps, _ptr(dp), _ptr(di), C.byref(ns)))
+    n = ns.value
+    return dp[: n + 1], di[: dp[n]]
 
 
 FILE_INFO_NAMES = ("version", "single", "levels", "n", "nnz", "has_plans", "plan_entries", "plan_depth")

@@ -623,6 +623,26 @@ LhfStatus lhfsGpuDebugSweepHost(const LhfsGpuCcs *T, int upper, const double *rh
   });
 }
 
+LhfStatus lhfdGpuDebugSegmentGraph(const LhfdGpuCcs *T, int upper, size_t max_segs, size_t max_deps, unsigned *dep_ptr,
+                                   unsigned *dep_idx, size_t *nsegs) {
+  REQUIRE_PTR(T, "T");
+  REQUIRE_PTR(nsegs, "nsegs");
+  return guarded([&] {
+    HostCsr R = ccs_to_csr(*T, "T");
+    R.nrows = R.ncols = T->ncols;
+    R.ptr.resize(T->ncols + 1, R.ptr.empty() ? 0u : R.ptr.back());
+    const MergeParams mp = MergeParams::from_env();
+    MergeStats        ms;
+    HostCsr           S = merged_sweep_form(R, upper != 0, mp, &ms);
+    std::vector<unsigned> dp, di;
+    ws_debug_graph(S, 148u, dp, di);
+    if (dp.size() - 1 > max_segs || di.size() > max_deps) throw std::length_error("segment graph exceeds the output buffers");
+    std::copy(dp.begin(), dp.end(), dep_ptr);
+    std::copy(di.begin(), di.end(), dep_idx);
+    *nsegs = dp.size() - 1;
+  });
+}
+
 LhfStatus lhfdGpuDebugTraceSweep(LhfdGpuHdl hdl, const double *d_b, double *d_x, int level, int which,
                                  unsigned long long *out, size_t max_segs, size_t *nsegs) {
   REQUIRE_HANDLE(hdl);

@@ -39,6 +39,11 @@ LhfStatus lhfdGpuDebugPlanLab(const LhfdGpuCcs *T, int upper, const int *key, co
 LhfStatus lhfdGpuDebugTraceSweep(LhfdGpuHdl hdl, const double *d_b, double *d_x, int level, int which,
                                  unsigned long long *out, size_t max_segs, size_t *nsegs);
 
+/* Host only: segment dependency graph of the packed warp streams of T, segments numbered as in the
+ * trace (warp by warp): segment s gathers results published by dep_idx[dep_ptr[s] .. dep_ptr[s+1]). */
+LhfStatus lhfdGpuDebugSegmentGraph(const LhfdGpuCcs *T, int upper, size_t max_segs, size_t max_deps, unsigned *dep_ptr,
+                                   unsigned *dep_idx, size_t *nsegs);
+
 /* Bit-exact checks of the attach-time integer handling: copies the device-resident index arrays of
  * level `level` back to the host.  which: 0 p, 1 q_inv, 2 E row pointers, 3 E columns (original
  * numbering), 4 F row pointers, 5 F columns, 6 jpvt (level ignored).  out receives min(count, max)

@@ -93,6 +93,7 @@ struct MergeParams {
   bool     slack     = false;     // slack-aware merging (merge_slack): only rows pinned to the critical core pay fill
   unsigned steps     = 0;         // > 0: proportional scheduling into this many steps (merge_prop)
   bool     chain_all = true;      // chain every row (not only the pinned ones) to the t rows of the previous step
+  bool     auto_caps = true;      // choose sl_cap / gain from the size of the factor (merge_levels)
   static MergeParams from_env();
 };
 struct MergeStats {
@@ -333,6 +334,7 @@ void ws_host_emulate(const HostCsr &S, bool upper, const double *rhs, const doub
 void launch_ws_sweep(Handle *h, const SweepPlan &plan, const double *rhs_plain, const unsigned long long *rhs_tagged,
                      const double *diag, unsigned long long *x, unsigned parity, int *sync,
                      unsigned long long *trace = nullptr);
+void ws_debug_graph(const HostCsr &S, unsigned nsm, std::vector<unsigned> &dep_ptr, std::vector<unsigned> &dep_idx);
 int  sweep_kind();  // HIFIR_B200_SWEEP = ws (default) | stream | slab  ->  2 | 1 | 0
 
 // ---- planlab.cu (developer tool, host only)

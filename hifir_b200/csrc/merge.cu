@@ -33,11 +33,11 @@ namespace hifgpu {
 MergeParams MergeParams::from_env() {
   MergeParams p;
   if (const char *e = std::getenv("HIFIR_B200_MERGE")) p.enabled = std::atoi(e) != 0;
-  if (const char *e = std::getenv("HIFIR_B200_MERGE_GAIN")) p.gain = std::atof(e);
+  if (const char *e = std::getenv("HIFIR_B200_MERGE_GAIN")) p.gain = std::atof(e), p.auto_caps = false;
   if (const char *e = std::getenv("HIFIR_B200_MERGE_ROWCAP")) p.row_cap = static_cast<unsigned>(std::atoi(e));
   if (const char *e = std::getenv("HIFIR_B200_MERGE_BMAX")) p.bmax = static_cast<unsigned>(std::atoi(e));
   if (const char *e = std::getenv("HIFIR_B200_MERGE_ROWCOST")) p.row_cost = std::atof(e);
-  if (const char *e = std::getenv("HIFIR_B200_MERGE_SLCAP")) p.sl_cap = std::atof(e);
+  if (const char *e = std::getenv("HIFIR_B200_MERGE_SLCAP")) p.sl_cap = std::atof(e), p.auto_caps = false;
   if (const char *e = std::getenv("HIFIR_B200_MERGE_ALAP")) p.alap = std::atoi(e);
   if (const char *e = std::getenv("HIFIR_B200_MERGE_CHAIN")) p.chain = std::atoi(e) != 0;
   if (const char *e = std::getenv("HIFIR_B200_MERGE_SLACK")) p.slack = std::atoi(e) != 0;
@@ -486,6 +486,17 @@ HostCsr merge_prop(const HostCsr &S, const MergeParams &prm, MergeStats *st) {
 HostCsr merge_levels(const HostCsr &S, const MergeParams &prm, MergeStats *st, bool fan_out) {
   const unsigned m = static_cast<unsigned>(S.nrows);
   if (S.gid.size() != m || S.orig_rows != m) throw std::logic_error("merge_levels: input is not in sweep form");
+  if (prm.auto_caps) {
+    // Per-factor caps (measured at Poisson 128^3 on the warp-stream sweep): a large factor keeps the
+    // machine busy between two dependent steps, so it pays for fewer, fatter steps (L_0 / U_0, 14 M
+    // entries: sl_cap 1e6 -> 133 / 156 us per sweep instead of 157 / 162); a small one is bound by the
+    // hops and more fill only costs (L_1 / U_1, 4 M entries: 3e5 -> 67 / 84 us instead of 76 / 84).
+    MergeParams q = prm;
+    q.auto_caps   = false;
+    q.sl_cap      = std::min(1.2e6, std::max(3.0e5, static_cast<double>(S.col.size()) / 14.0));
+    q.gain        = std::max(prm.gain, 3.0 * q.sl_cap);
+    return merge_levels(S, q, st, fan_out);
+  }
   if (prm.steps) return merge_prop(S, prm, st);
   if (prm.slack) return merge_slack(S, prm, st);
   std::vector<unsigned> lev;

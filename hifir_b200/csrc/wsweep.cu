@@ -139,17 +139,46 @@ void pack_warp_streams(const HostCsr &S, WsHost &H, unsigned nwarps, unsigned wi
   std::vector<std::vector<unsigned>> ws(nwarps);  // private streams
   std::vector<std::vector<unsigned>> seg_off(nwarps);
   std::vector<unsigned>              sentinel_of_level(depth, kWsNone);
-  // Slice q of a level set goes to warp q % nwarps -- the count restarts with every level set, so
-  // the thin level sets at the top of the elimination tree (<= one slice per SM) are all served by
-  // the same warps, which then walk from level to level without ever waiting for admission; a
-  // warp is throttled by a sentinel only when it JUMPS more than `window` level sets ahead of its
-  // previous segment.
-  // Consecutive level sets start at different warp GROUPS (level l at warp (l % groups) * nwarps /
-  // groups): while one group re-polls for the results of level l - 1, the other has its first
-  // round of gathers for level l + 1 in flight.
-  std::vector<int>                   last_level(nwarps, -1000000);
-  unsigned                           q = 0, nslices = 0, cur_level = 0;
-  const unsigned                     jump_after = std::max(window, groups);
+  // Warp assignment.  A warp works through its segments one after the other and a segment costs about
+  // one L2 round trip whatever its width, so the sweep lasts as long as the warp with the MOST
+  // segments (measured: a dependency-free second pass takes as long as the first).  Hence plain
+  // round-robin with counters that never restart: every warp gets the same number of segments and
+  // the slices of one level set land on distinct warps.  Thin level sets (fewer slices than a warp
+  // GROUP has warps) alternate between the groups -- level l on group l % groups -- so that one
+  // group gathers for level l + 1 while the other finishes level l; wide ones use all warps.
+  // A warp is throttled by a sentinel only when it JUMPS far ahead of its previous segment.
+  std::vector<int>      last_level(nwarps, -1000000);
+  unsigned              nslices = 0;
+  unsigned long long    q_all = 0;
+  std::vector<unsigned long long> q_grp(groups, 0ull);
+  const unsigned        jump_after = static_cast<unsigned>(std::max<int>(static_cast<int>(window), ws_env("HIFIR_B200_WS_JUMP", 8)));
+  auto slice_at = [&](unsigned p, bool &copy) {  // rows of the slice that starts at ord[p]
+    const unsigned i0 = ord[p], l = lev[i0];
+    unsigned       cnt = 1;
+    copy               = rowlen(i0) == 0;
+    if (copy) {
+      while (cnt < 32u * kWsU && p + cnt < n && lev[ord[p + cnt]] == l && rowlen(ord[p + cnt]) == 0) ++cnt;
+    } else {
+      const unsigned z = cls[i0], cap = 32u >> z;
+      while (cnt < cap && p + cnt < n && lev[ord[p + cnt]] == l && rowlen(ord[p + cnt]) != 0 && cls[ord[p + cnt]] == z &&
+             bkt[ord[p + cnt]] == bkt[i0])
+        ++cnt;
+    }
+    return cnt;
+  };
+  std::vector<unsigned> slices_of_level(depth, 0u);
+  for (unsigned p = 0; p < n;) {
+    bool copy;
+    ++slices_of_level[lev[ord[p]]];
+    p += slice_at(p, copy);
+  }
+  auto next_warp = [&](unsigned l) {
+    if (groups > 1u && slices_of_level[l] <= gwarps) {
+      const unsigned g = l % groups;
+      return g * gwarps + static_cast<unsigned>(q_grp[g]++ % gwarps);
+    }
+    return static_cast<unsigned>(q_all++ % nwarps);
+  };
   std::vector<unsigned>              ent;
   auto rhs_code = [&](unsigned i) {
     const unsigned code = S.gid[i];
@@ -176,12 +205,11 @@ void pack_warp_streams(const HostCsr &S, WsHost &H, unsigned nwarps, unsigned wi
   };
   for (unsigned p = 0; p < n;) {
     const unsigned i0 = ord[p], l = lev[i0];
-    if (l != cur_level) cur_level = l, q = (l % groups) * gwarps;
-    if (rowlen(i0) == 0) {  // COPY segment: up to 8 rows per lane
-      unsigned cnt = 1;
-      while (cnt < 32u * kWsU && p + cnt < n && lev[ord[p + cnt]] == l && rowlen(ord[p + cnt]) == 0) ++cnt;
+    bool           is_copy;
+    const unsigned cnt = slice_at(p, is_copy);
+    if (is_copy) {  // COPY segment: up to 8 rows per lane
       const unsigned width = (cnt + 31u) / 32u;
-      unsigned *     hd    = push_seg(q % nwarps, width, 0u, kSegFirst | kSegLast | kSegCopy, l);
+      unsigned *     hd    = push_seg(next_warp(l), width, 0u, kSegFirst | kSegLast | kSegCopy, l);
       unsigned *     codes = hd + kWsHdrWords, *slots = codes + width * 32u;
       for (unsigned r = 0; r < width * 32u; ++r) {
         // row r of the segment: lane r % 32, position r / 32 -> stored at [pos * 32 + lane] = [r]
@@ -189,19 +217,15 @@ void pack_warp_streams(const HostCsr &S, WsHost &H, unsigned nwarps, unsigned wi
         slots[r] = r < cnt ? slot[ord[p + r]] : kWsNone;
       }
       sentinel_of_level[l] = slot[ord[p + cnt - 1u]];
-      ++q, ++nslices;
+      ++nslices;
       p += cnt;
       H.copy_rows += cnt;
       continue;
     }
-    const unsigned z = cls[i0], lpr = 1u << z, cap = 32u >> z;
-    unsigned       cnt = 1;
-    while (cnt < cap && p + cnt < n && lev[ord[p + cnt]] == l && rowlen(ord[p + cnt]) != 0 && cls[ord[p + cnt]] == z &&
-           bkt[ord[p + cnt]] == bkt[i0])
-      ++cnt;
-    unsigned width = 0;
+    const unsigned z = cls[i0], lpr = 1u << z;
+    unsigned       width = 0;
     for (unsigned r = 0; r < cnt; ++r) width = std::max(width, (rowlen(ord[p + r]) + lpr - 1u) >> z);
-    const unsigned nseg = (width + kWsU - 1u) / kWsU, warp = q % nwarps;
+    const unsigned nseg = (width + kWsU - 1u) / kWsU, warp = next_warp(l);
     for (unsigned sg = 0; sg < nseg; ++sg) {
       const unsigned w0 = sg * kWsU, w = std::min(kWsU, width - w0);
       unsigned *     hd = push_seg(warp, w, z, (sg == 0 ? kSegFirst : 0u) | (sg + 1 == nseg ? kSegLast : 0u), l);
@@ -235,7 +259,7 @@ void pack_warp_streams(const HostCsr &S, WsHost &H, unsigned nwarps, unsigned wi
       }
     }
     sentinel_of_level[l] = slot[ord[p + cnt - 1u]];
-    ++q, ++nslices;
+    ++nslices;
     p += cnt;
   }
   H.entries = S.col.size();
@@ -385,6 +409,48 @@ std::size_t ws_check_schedule(const WsHost &H, bool f32, std::string *why) {
   return left;
 }
 
+// Developer tool (host only): the segment dependency graph of a packed plan in the trace numbering
+// (warp by warp).  dep_ptr[nsegs + 1], dep_idx = distinct producer segments of every segment.
+void ws_segment_graph(const WsHost &H, std::vector<unsigned> &dep_ptr, std::vector<unsigned> &dep_idx) {
+  std::vector<unsigned> seg_of_slot(H.nslots, kWsNone), base(H.nwarps + 1u, 0u);
+  for (unsigned w = 0; w < H.nwarps; ++w) base[w + 1] = base[w] + static_cast<unsigned>(H.seg_off[w].size());
+  auto header = [&](unsigned w, std::size_t k) {
+    return H.stream.data() + static_cast<std::size_t>(H.wdesc[static_cast<std::size_t>(w) * 8u]) * 4u + H.seg_off[w][k];
+  };
+  for (unsigned w = 0; w < H.nwarps; ++w)
+    for (std::size_t k = 0; k < H.seg_off[w].size(); ++k) {
+      const unsigned *hd = header(w, k);
+      const unsigned  width = hd[0] & 0xffu, flags = hd[0] >> 16;
+      if (flags & kSegCopy) {
+        const unsigned *slots = hd + kWsHdrWords + width * 32u;
+        for (unsigned r = 0; r < width * 32u; ++r)
+          if (slots[r] != kWsNone) seg_of_slot[slots[r]] = base[w] + static_cast<unsigned>(k);
+      } else if (flags & kSegLast) {
+        const unsigned *slots = hd + kWsHdrWords + 32u;
+        for (unsigned j = 0; j < 32u; ++j)
+          if (slots[j] != kWsNone) seg_of_slot[slots[j]] = base[w] + static_cast<unsigned>(k);
+      }
+    }
+  dep_ptr.assign(1, 0u);
+  dep_idx.clear();
+  std::vector<unsigned> tmp;
+  for (unsigned w = 0; w < H.nwarps; ++w)
+    for (std::size_t k = 0; k < H.seg_off[w].size(); ++k) {
+      const unsigned *hd = header(w, k);
+      const unsigned  width = hd[0] & 0xffu, flags = hd[0] >> 16;
+      tmp.clear();
+      if (!(flags & kSegCopy)) {
+        const unsigned *cols = hd + kWsHdrWords + 64u;
+        for (unsigned q = 0; q < width * 32u; ++q)
+          if (cols[q] != kWsNone) tmp.push_back(seg_of_slot[cols[q]]);
+        std::sort(tmp.begin(), tmp.end());
+        tmp.erase(std::unique(tmp.begin(), tmp.end()), tmp.end());
+      }
+      dep_idx.insert(dep_idx.end(), tmp.begin(), tmp.end());
+      dep_ptr.push_back(static_cast<unsigned>(dep_idx.size()));
+    }
+}
+
 // ---- device ----------------------------------------------------------------------------
 namespace {
 __device__ __forceinline__ unsigned ws_smem_addr(const void *p) { return static_cast<unsigned>(__cvta_generic_to_shared(p)); }
@@ -394,10 +460,21 @@ __device__ __forceinline__ void ws_mbar_init(unsigned bar, unsigned count) {
 __device__ __forceinline__ void ws_mbar_expect_tx(unsigned bar, unsigned bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void ws_tma_g2s(unsigned dst, const void *src, unsigned bytes, unsigned bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-               "l"(src), "r"(bytes), "r"(bar)
-               : "memory");
+// The factor stream is touched once per sweep: EVICT-FIRST in L2, so that it does not push the
+// solution buffers and right-hand sides (gathered at random, re-used ~9x) out to HBM -- with the
+// default policy the trace showed first-try gathers of 0.7 us and right-hand side loads of ~1.2 us
+// (HBM latency) on level sets whose producers had long finished.
+__device__ __forceinline__ unsigned long long ws_policy_evict_first() {
+  unsigned long long pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void ws_tma_g2s(unsigned dst, const void *src, unsigned bytes, unsigned bar,
+                                           unsigned long long policy) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst),
+      "l"(src), "r"(bytes), "r"(bar), "l"(policy)
+      : "memory");
 }
 __device__ __forceinline__ bool ws_mbar_try_wait(unsigned bar, unsigned phase) {
   unsigned ok;
@@ -432,7 +509,7 @@ struct WsParams {
   unsigned long long *      x;
   int *                     sync;  // [0] frontier hint (highest level some warp finished a slice of)
   int *                     error_flag;
-  unsigned                  parity, window, adm_sleep, poll_sleep;
+  unsigned                  parity, window, adm_sleep;
   int                       publish_st;
   unsigned                  spin_limit;  // poll rounds after which a wait gives up (and every other wait with it)
   unsigned long long *      trace;  // kTrace: 4 words per segment (decoded, admitted, gathered | rounds, published | level)
@@ -455,17 +532,6 @@ __device__ __noinline__ void ws_fail(const WsParams &P, unsigned gw, unsigned k,
 }
 __device__ __forceinline__ bool ws_aborted(const WsParams &P) { return ws_ld_poll_i32(P.error_flag) != 0; }
 
-// The ring stage of a segment may be refilled (an ASYNC-proxy write by the TMA unit) only when every
-// lane's shared-memory reads of it have RETURNED: a warp barrier only orders their issue, and under
-// load a shared-memory read can sit in the SM's load/store queue behind thousands of cycles of
-// scattered global gathers of all the warps -- longer than a bulk copy from L2 takes to land
-// (measured: stale stages -> wrong indices -> illegal addresses / rows that never become ready).
-// A warp vote over a value derived from everything a lane has loaded can not be issued before
-// those loads have written their registers.
-__device__ __forceinline__ bool ws_reads_done(unsigned digest) {
-  return __ballot_sync(0xffffffffu, digest == 0x9e3779b9u) != 0xffffffffu;  // (practically) always true
-}
-
 __device__ __forceinline__ unsigned long long ws_timer_ns() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -485,6 +551,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) wsweep_kernel(const WsParams P
   unsigned char *ring = smem + static_cast<std::size_t>(kWarps) * kStages * 8u + static_cast<std::size_t>(warp) * kStages * kStageBytes;
   const unsigned bar0 = ws_smem_addr(smem) + warp * kStages * 8u;
   const unsigned char *src = reinterpret_cast<const unsigned char *>(P.stream) + static_cast<std::size_t>(d0.x) * 16u;
+  const unsigned long long policy = ws_policy_evict_first();
   if (lane == 0) {
     for (int s = 0; s < kStages; ++s) ws_mbar_init(bar0 + s * 8u, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -492,21 +559,37 @@ __global__ void __launch_bounds__(kWarps * 32, 1) wsweep_kernel(const WsParams P
     for (int s = 0; s < kStages; ++s)
       if (sz[s]) {
         ws_mbar_expect_tx(bar0 + s * 8u, sz[s] * 16u);
-        ws_tma_g2s(ws_smem_addr(ring + s * kStageBytes), src, sz[s] * 16u, bar0 + s * 8u);
+        ws_tma_g2s(ws_smem_addr(ring + s * kStageBytes), src, sz[s] * 16u, bar0 + s * 8u, policy);
         src += static_cast<std::size_t>(sz[s]) * 16u;
       }
   }
   __syncwarp();
-  double   acc        = 0.0;
-  unsigned my_front   = 0;
-  const unsigned parity = P.parity;
+  double         acc      = 0.0;
+  unsigned       my_front = 0;
+  const unsigned parity   = P.parity;
+  // The ring stage of a segment is refilled (an ASYNC-proxy write by the TMA unit) at the END of the
+  // segment, in program order after instructions that consume every register the segment's
+  // shared-memory reads wrote: a warp issues in order and an instruction can not issue before its
+  // source registers have arrived, so by then every read of the stage has RETURNED.  (Refilling
+  // right after the reads were ISSUED is a race: under load a shared-memory read sits in the SM's
+  // load/store queue behind thousands of cycles of scattered gathers -- longer than a bulk copy from
+  // L2 takes to land.  Measured: stale stages -> wrong indices -> illegal addresses / rows that
+  // never become ready.)
+  auto refill = [&](unsigned stage, unsigned size16) {
+    __syncwarp();
+    if (lane == 0 && size16) {
+      ws_mbar_expect_tx(bar0 + stage * 8u, size16 * 16u);
+      ws_tma_g2s(ws_smem_addr(ring + stage * kStageBytes), src, size16 * 16u, bar0 + stage * 8u, policy);
+      src += static_cast<std::size_t>(size16) * 16u;
+    }
+  };
   for (unsigned k = 0; k < nseg; ++k) {
     const unsigned stage = k % kStages, phase = (k / kStages) & 1u;
     {
       unsigned spins = 0;
-      bool ok = true;
+      bool     ok    = true;
       while (!ws_mbar_try_wait(bar0 + stage * 8u, phase)) {
-        if (++spins > P.spin_limit || ((spins & 255u) == 255u && ws_aborted(P))) {
+        if (++spins > P.spin_limit || ((spins & 1023u) == 1023u && ws_aborted(P))) {
           ok = false;
           break;
         }
@@ -520,10 +603,12 @@ __global__ void __launch_bounds__(kWarps * 32, 1) wsweep_kernel(const WsParams P
     const uint4     hd    = *reinterpret_cast<const uint4 *>(sg);
     const unsigned  width = hd.x & 0xffu, z = (hd.x >> 8) & 0xffu, flags = hd.x >> 16;
     unsigned long long *tr = kTrace ? P.trace + 4ull * (d0.z + k) : nullptr;
-    if (kTrace && lane == 0) tr[0] = ws_timer_ns();
+    unsigned long long  t_dec = 0;
+    if (kTrace) t_dec = ws_timer_ns();
     if (flags & kSegCopy) {
       // rows without entries: x = rhs, 8 per lane, all loads in flight together
       unsigned code[kWsU], slot[kWsU];
+      double   v[kWsU];
 #pragma unroll
       for (unsigned u = 0; u < kWsU; ++u) {
         code[u] = slot[u] = kWsNone;
@@ -532,17 +617,6 @@ __global__ void __launch_bounds__(kWarps * 32, 1) wsweep_kernel(const WsParams P
           slot[u] = sg[kWsHdrWords + (width + u) * 32u + lane];
         }
       }
-      {
-        unsigned digest = hd.x;
-#pragma unroll
-        for (unsigned u = 0; u < kWsU; ++u) digest ^= code[u] + 3u * slot[u];
-        if (ws_reads_done(digest) && lane == 0 && hd.y) {
-          ws_mbar_expect_tx(bar0 + stage * 8u, hd.y * 16u);
-          ws_tma_g2s(ws_smem_addr(ring + stage * kStageBytes), src, hd.y * 16u, bar0 + stage * 8u);
-          src += static_cast<std::size_t>(hd.y) * 16u;
-        }
-      }
-      double v[kWsU];
 #pragma unroll
       for (unsigned u = 0; u < kWsU; ++u) {
         v[u] = 0.0;
@@ -563,28 +637,21 @@ __global__ void __launch_bounds__(kWarps * 32, 1) wsweep_kernel(const WsParams P
       }
 #pragma unroll
       for (unsigned u = 0; u < kWsU; ++u)
-        if (slot[u] != kWsNone) st_publish(P.x + slot[u], tag_set(v[u], parity));
-      if (lane == 0 && hd.w > my_front) {
+        if (slot[u] != kWsNone) st_publish(P.x + slot[u], tag_set(v[u], parity));  // consumes code and slot
+      refill(stage, hd.y);
+      if (lane == 0 && hd.w > my_front + 3u) {
         my_front = hd.w;
         atomicMax(P.sync, static_cast<int>(hd.w));
       }
-      if (kTrace && lane == 0) tr[1] = tr[2] = 0, tr[3] = ((ws_timer_ns() - tr[0]) << 16) | hd.w | 0x8000u;
+      if (kTrace && lane == 0) tr[0] = t_dec, tr[1] = tr[2] = 0, tr[3] = ((ws_timer_ns() - t_dec) << 16) | hd.w | 0x8000u;
       continue;
     }
-    // ---- a slice segment: codes, slots, <= 8 entries per lane -- all shared-memory reads first
-    const unsigned code = sg[kWsHdrWords + lane];
-    const unsigned slot = sg[kWsHdrWords + 32u + lane];
-    unsigned       cc[kWsU];
-    VT             vv[kWsU];
-    const VT *     sv = reinterpret_cast<const VT *>(sg + kWsHdrWords + 64u + width * 32u);
+    // ---- a slice segment: slot indices first, the gathers are the long pole
+    unsigned cc[kWsU];
 #pragma unroll
     for (unsigned u = 0; u < kWsU; ++u) {
       cc[u] = kWsNone;
-      vv[u] = VT(0);
-      if (u < width) {
-        cc[u] = sg[kWsHdrWords + 64u + u * 32u + lane];
-        vv[u] = sv[u * 32u + lane];
-      }
+      if (u < width) cc[u] = sg[kWsHdrWords + 64u + u * 32u + lane];
     }
     // ---- admission (only a warp that jumps ahead carries a sentinel): the sentinel row of level
     // (this - window) is published
@@ -595,7 +662,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) wsweep_kernel(const WsParams P
         while (!tag_ready(ld_poll(P.x + hd.z), parity)) {
           // far from the frontier: sleep in proportion to the distance; close to it: spin on the sentinel
           const unsigned f = static_cast<unsigned>(ws_ld_poll_i32(P.sync));
-          if (need > f + 1u) __nanosleep(min((need - f) * P.adm_sleep, 20000u));
+          if (need > f + 4u) __nanosleep(min((need - f) * P.adm_sleep, 20000u));
           if (++spins > P.spin_limit || ((spins & 63u) == 63u && ws_aborted(P))) {
             if (!ws_aborted(P)) ws_fail(P, gw, k, hd.w, 4, hd.z);
             break;
@@ -604,14 +671,17 @@ __global__ void __launch_bounds__(kWarps * 32, 1) wsweep_kernel(const WsParams P
       }
       __syncwarp();
     }
-    if (kTrace && lane == 0) tr[1] = ws_timer_ns() - tr[0];
+    unsigned long long t_adm = 0, t_gat = 0;
+    if (kTrace) t_adm = ws_timer_ns();
     // ---- gather all entries optimistically (re-polled below if not ready), right-hand side beside them
     unsigned long long g[kWsU];
 #pragma unroll
     for (unsigned u = 0; u < kWsU; ++u)
       if (cc[u] != kWsNone) g[u] = ld_poll(P.x + cc[u]);
-    const unsigned lpr = 1u << z;
-    const bool     own = slot != kWsNone && (lane & (lpr - 1u)) == 0u;
+    const unsigned code = sg[kWsHdrWords + lane];
+    const unsigned slot = sg[kWsHdrWords + 32u + lane];
+    const unsigned lpr  = 1u << z;
+    const bool     own  = slot != kWsNone && (lane & (lpr - 1u)) == 0u;
     double             rhs_v  = 0.0, dg = 1.0;
     unsigned long long rhs_t  = 0;
     const bool         want_r = (flags & kSegFirst) && own && !(code & kCodeZeroRhs);
@@ -624,37 +694,27 @@ __global__ void __launch_bounds__(kWarps * 32, 1) wsweep_kernel(const WsParams P
         rhs_v = P.rhs_plain[r];
       }
     }
-    // ---- every lane's reads of the stage have returned: refill it with the segment kStages ahead
+    // fast path: one combined test of all tags (the common case: everything was ready)
+    unsigned pend = 0, nrounds = 0;
     {
-      unsigned digest = code + 3u * slot;
+      unsigned bad = 0;
 #pragma unroll
-      for (unsigned u = 0; u < kWsU; ++u) {
-        digest ^= cc[u];
-        if (sizeof(VT) == 8) {
-          const unsigned long long b = static_cast<unsigned long long>(__double_as_longlong(static_cast<double>(vv[u])));
-          digest += static_cast<unsigned>(b) ^ static_cast<unsigned>(b >> 32);
-        } else {
-          digest += __float_as_uint(static_cast<float>(vv[u]));
-        }
-      }
-      if (ws_reads_done(digest) && lane == 0 && hd.y) {
-        ws_mbar_expect_tx(bar0 + stage * 8u, hd.y * 16u);
-        ws_tma_g2s(ws_smem_addr(ring + stage * kStageBytes), src, hd.y * 16u, bar0 + stage * 8u);
-        src += static_cast<std::size_t>(hd.y) * 16u;
+      for (unsigned u = 0; u < kWsU; ++u)
+        if (cc[u] != kWsNone) bad |= static_cast<unsigned>(g[u]) ^ parity;
+      if (UPPER && want_r) bad |= static_cast<unsigned>(rhs_t) ^ parity;
+      if (bad & 1u) {
+#pragma unroll
+        for (unsigned u = 0; u < kWsU; ++u)
+          if (cc[u] != kWsNone && !tag_ready(g[u], parity)) pend |= 1u << u;
+        if (UPPER && want_r && !tag_ready(rhs_t, parity)) pend |= 1u << kWsU;
       }
     }
-    unsigned pend = 0, nrounds = 0;
-#pragma unroll
-    for (unsigned u = 0; u < kWsU; ++u)
-      if (cc[u] != kWsNone && !tag_ready(g[u], parity)) pend |= 1u << u;
-    if (UPPER && want_r && !tag_ready(rhs_t, parity)) pend |= 1u << kWsU;
     if (kTrace) {
       const unsigned any = __ballot_sync(0xffffffffu, pend != 0u);  // depends on every first-try gather
-      if (lane == 0) tr[2] = ws_timer_ns() - tr[0] + (any == 0xdeadbeefu ? 1u : 0u);
+      t_gat              = ws_timer_ns() + (any == 0xdeadbeefu ? 1u : 0u);
     }
     for (unsigned rounds = 0; __any_sync(0xffffffffu, pend != 0u);) {
       if (kTrace) ++nrounds;
-      if (P.poll_sleep) __nanosleep(P.poll_sleep);
 #pragma unroll
       for (unsigned u = 0; u < kWsU; ++u)
         if (pend & (1u << u)) g[u] = ld_poll(P.x + cc[u]);
@@ -680,20 +740,30 @@ __global__ void __launch_bounds__(kWarps * 32, 1) wsweep_kernel(const WsParams P
       // b_i (L sweep) or (L^{-1} b)_i / d_i with a true division (prec_solve.hpp:219, :256-259)
       if (want_r) acc = UPPER ? tag_value(rhs_t) / dg : rhs_v;
     }
+    // the factor values are read from the stage only now (no registers held across the gather wait);
+    // the multiply is unconditional for every entry position of the segment, so that each of these
+    // reads is consumed before the stage is refilled (a padded position holds 0.0)
+    const VT *sv = reinterpret_cast<const VT *>(sg + kWsHdrWords + 64u + width * 32u);
 #pragma unroll
     for (unsigned u = 0; u < kWsU; ++u)
-      if (cc[u] != kWsNone) acc = fma(-static_cast<double>(vv[u]), tag_value(g[u]), acc);
+      if (u < width) {
+        const double v = static_cast<double>(sv[u * 32u + lane]);
+        acc            = fma(-v, cc[u] != kWsNone ? tag_value(g[u]) : 0.0, acc);
+      }
     if (flags & kSegLast) {
       for (unsigned o = lpr >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
       if (own) ws_publish(P.x + slot, tag_set(acc, parity), P.publish_st);
-      if (lane == 0 && hd.w > my_front) {
-        my_front = hd.w;
-        atomicMax(P.sync, static_cast<int>(hd.w));
-      }
+    }
+    refill(stage, hd.y + (acc == 1.2345e300 ? 1u : 0u));  // (the refill depends on acc: see above)
+    if (lane == 0 && hd.w > my_front + 3u) {  // frontier hint for the sleeping jumpers, every 4th level
+      my_front = hd.w;
+      atomicMax(P.sync, static_cast<int>(hd.w));
     }
     if (kTrace && lane == 0) {
-      tr[2] = (tr[2] << 8) | min(nrounds, 255u);
-      tr[3] = ((ws_timer_ns() - tr[0]) << 16) | hd.w;
+      tr[0] = t_dec;
+      tr[1] = t_adm - t_dec;
+      tr[2] = ((t_gat - t_dec) << 8) | min(nrounds, 255u);
+      tr[3] = ((ws_timer_ns() - t_dec) << 16) | hd.w;
     }
   }
 }
@@ -705,10 +775,12 @@ struct WsConfig {
 };
 WsConfig ws_config() {
   WsConfig c;
-  c.warps  = static_cast<unsigned>(ws_env("HIFIR_B200_WS_WARPS", 16));
-  c.stages = static_cast<unsigned>(ws_env("HIFIR_B200_WS_STAGES", 4));
-  if (c.warps != 16u && c.warps != 32u && c.warps != 24u) c.warps = 16u;
-  if (c.stages < 2u || c.stages > 4u) c.stages = 4u;
+  // measured at Poisson 128^3 (ms per apply): 16 x 4 1.10, 24 x 2 1.05, 32 x 2 1.24
+  c.warps  = static_cast<unsigned>(ws_env("HIFIR_B200_WS_WARPS", 24));
+  c.stages = static_cast<unsigned>(ws_env("HIFIR_B200_WS_STAGES", 2));
+  const bool ok = (c.warps == 16u && c.stages >= 2u && c.stages <= 4u) || (c.warps == 24u && c.stages == 2u) ||
+                  (c.warps == 32u && c.stages == 2u) || (c.warps == 20u && c.stages == 3u) || (c.warps == 28u && c.stages == 2u);
+  if (!ok) c.warps = 24u, c.stages = 2u;
   return c;
 }
 }  // namespace
@@ -739,6 +811,14 @@ void build_ws_plan(const HostCsr &S, bool upper, SweepPlan &plan, std::size_t *t
   plan.slot_of    = std::move(H.slot_of);
   plan.ws_wdesc.upload(H.wdesc, tally);
   plan.ws_stream.upload(H.stream, tally);
+}
+
+void ws_debug_graph(const HostCsr &S, unsigned nsm, std::vector<unsigned> &dep_ptr, std::vector<unsigned> &dep_idx) {
+  const WsConfig cfg = ws_config();
+  WsHost         H;
+  pack_warp_streams(S, H, nsm * cfg.warps, static_cast<unsigned>(std::max(1, ws_env("HIFIR_B200_WS_WINDOW", 2))), false,
+                    nullptr);
+  ws_segment_graph(H, dep_ptr, dep_idx);
 }
 
 void ws_host_emulate(const HostCsr &S, bool upper, const double *rhs, const double *diag, double *x_by_row,
@@ -775,8 +855,8 @@ void launch_ws_K(Handle *h, const SweepPlan &plan, const WsParams &P) {
     configured[h->device] = true;
   }
   if (P.trace) {
-    if (kWarps != 16 || kStages != 4 || sizeof(VT) != 8) throw std::logic_error("tracing needs the 16 x 4 double configuration");
-    auto tk = wsweep_kernel<UPPER, double, 16, 4, true>;
+    if (kWarps != 24 || kStages != 2 || sizeof(VT) != 8) throw std::logic_error("tracing needs the 24 x 2 double configuration");
+    auto tk = wsweep_kernel<UPPER, double, 24, 2, true>;
     HIF_CUDA(cudaFuncSetAttribute(tk, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     tk<<<plan.ws_grid, kWarps * 32, smem, h->stream>>>(P);
     return;
@@ -794,6 +874,10 @@ void launch_ws_V(Handle *h, const SweepPlan &plan, const WsParams &P) {
     launch_ws_K<UPPER, VT, 16, 2>(h, plan, P);
   else if (w == 24 && s == 2)
     launch_ws_K<UPPER, VT, 24, 2>(h, plan, P);
+  else if (w == 20 && s == 3)
+    launch_ws_K<UPPER, VT, 20, 3>(h, plan, P);
+  else if (w == 28 && s == 2)
+    launch_ws_K<UPPER, VT, 28, 2>(h, plan, P);
   else if (w == 32 && s == 2)
     launch_ws_K<UPPER, VT, 32, 2>(h, plan, P);
   else
@@ -817,7 +901,6 @@ void launch_ws_sweep(Handle *h, const SweepPlan &plan, const double *rhs_plain, 
   P.parity     = parity;
   P.window     = plan.ws_window;
   P.adm_sleep  = static_cast<unsigned>(std::max(0, ws_env("HIFIR_B200_WS_SLEEP", 200)));
-  P.poll_sleep = static_cast<unsigned>(std::max(0, ws_env("HIFIR_B200_WS_POLL_SLEEP", 0)));
   P.publish_st = ws_env("HIFIR_B200_WS_PUBLISH_ST", 0);
   P.spin_limit = static_cast<unsigned>(std::max(1000, ws_env("HIFIR_B200_WS_SPIN_LIMIT", 1 << 21)));
   if (plan.upper) {
@@ -833,6 +916,17 @@ void launch_ws_sweep(Handle *h, const SweepPlan &plan, const double *rhs_plain, 
   }
   HIF_KERNEL_CHECK();
   ++h->launch_count;
+  // developer experiment: launch the sweep again -- every slot already carries the current tag, so the
+  // second pass never waits: its duration is the pure throughput bound of the kernel on this factor
+  static const int repeat = ws_env("HIFIR_B200_WS_REPEAT", 0);
+  for (int r = 0; r < repeat; ++r) {
+    if (plan.upper) {
+      if (plan.f32) launch_ws_V<true, float>(h, plan, P); else launch_ws_V<true, double>(h, plan, P);
+    } else {
+      if (plan.f32) launch_ws_V<false, float>(h, plan, P); else launch_ws_V<false, double>(h, plan, P);
+    }
+    HIF_KERNEL_CHECK();
+  }
 }
 
 }  // namespace hifgpu
