@@ -13,6 +13,8 @@
 //          y[i] = t[i] * [xU'; ychild][q_inv[i]]                (scatter_scale_kernel)
 // `bhat` is evaluated once per level (the reference evaluates s[p]*b[p] up to 3 times,
 // prec_solve.hpp:359/368/399).
+#include <cstdlib>
+
 #include "hifgpu.h"
 
 namespace hifgpu {
@@ -238,12 +240,78 @@ void launch_spmv_resid(Handle *h, const DevCsr &A, const int *col, const void *x
 
 }  // namespace
 
+namespace {
+void apply_schedule(Handle *h, const double *d_b, double *d_x, std::size_t rank, unsigned parity);
+}
+
+// The schedule of one apply is static: the second apply with the same (b, x, rank, tag parity, filter)
+// captures it into a CUDA graph, every later one is a single graph launch (the kernels of an apply
+// are short -- 8 to 160 us -- and there are a dozen and a half of them).
 void apply_dev(Handle *h, const double *d_b, double *d_x, std::size_t rank) {
   HIF_CUDA(cudaSetDevice(h->device));
-  const std::size_t nl = h->levels.size();
-  const std::size_t launches0 = h->launch_count;
   ++h->epoch;
   const unsigned parity = h->epoch & 1u;
+  static const bool graphs_on = [] {
+    const char *e = std::getenv("HIFIR_B200_GRAPH");
+    return !e || std::atoi(e) != 0;
+  }();
+  if (!graphs_on || h->graphs_off || h->profiling || h->trace_level >= 0) {
+    apply_schedule(h, d_b, d_x, rank, parity);
+    return;
+  }
+  ApplyGraph *g = nullptr;
+  for (ApplyGraph &c : h->graphs)
+    if (c.b == d_b && c.x == d_x && c.rank == rank && c.parity == parity && c.nsp_on == h->nsp_on &&
+        c.nsp_start == h->nsp_start && c.nsp_end == h->nsp_end)
+      g = &c;
+  if (!g) {
+    if (h->graphs.size() >= 256) clear_apply_graphs(h);
+    h->graphs.push_back(ApplyGraph{d_b, d_x, rank, parity, h->nsp_on, h->nsp_start, h->nsp_end, 0, nullptr, 0});
+    g = &h->graphs.back();
+  }
+  if (!g->exec && g->uses++ == 0) {  // first use: run eagerly (lazy allocations, function attributes)
+    apply_schedule(h, d_b, d_x, rank, parity);
+    return;
+  }
+  if (!g->exec) {
+    const std::size_t launches0 = h->launch_count;
+    cudaGraph_t       graph = nullptr;
+    if (cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+      // e.g. the legacy default stream can not be captured: this handle launches its kernels one by one
+      cudaGetLastError();
+      h->graphs_off = true;
+      apply_schedule(h, d_b, d_x, rank, parity);
+      return;
+    }
+    try {
+      apply_schedule(h, d_b, d_x, rank, parity);
+    } catch (...) {
+      cudaStreamEndCapture(h->stream, &graph);
+      if (graph) cudaGraphDestroy(graph);
+      throw;
+    }
+    HIF_CUDA(cudaStreamEndCapture(h->stream, &graph));
+    const cudaError_t e = cudaGraphInstantiate(&g->exec, graph, 0);
+    cudaGraphDestroy(graph);
+    cuda_check(e, "cudaGraphInstantiate", __FILE__, __LINE__);
+    g->launches     = h->launch_count - launches0;
+    h->launch_count = launches0;
+  }
+  HIF_CUDA(cudaGraphLaunch(g->exec, h->stream));
+  h->launch_count += g->launches;
+  h->kernels_per_apply = g->launches;
+}
+
+void clear_apply_graphs(Handle *h) {
+  for (ApplyGraph &c : h->graphs)
+    if (c.exec) cudaGraphExecDestroy(c.exec);
+  h->graphs.clear();
+}
+
+namespace {
+void apply_schedule(Handle *h, const double *d_b, double *d_x, std::size_t rank, unsigned parity) {
+  const std::size_t nl = h->levels.size();
+  const std::size_t launches0 = h->launch_count;
   HIF_CUDA(cudaMemsetAsync(h->tickets.p, 0, h->tickets.n * sizeof(int), h->stream));
   constexpr int T = 256;
   mark(h, "begin");
@@ -308,6 +376,7 @@ void apply_dev(Handle *h, const double *d_b, double *d_x, std::size_t rank) {
   }
   h->kernels_per_apply = h->launch_count - launches0;
 }
+}  // namespace
 
 // ---- the four dense operations of QRCP (small_scale/QRCP.hpp:370-540) ------------------
 // single-CTA kernels for the transposed solve and the two products: off the BASELINE path,

@@ -428,6 +428,7 @@ void destroy_handle(Handle *h) {
   if (!h) return;
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
+  clear_apply_graphs(h);
   if (h->twin) destroy_handle(h->twin);
   if (h->h_error) cudaFreeHost(h->h_error);
   if (h->h_scal) cudaFreeHost(h->h_scal);

@@ -252,6 +252,8 @@ LhfStatus lhfdGpuSetStream(LhfdGpuHdl hdl, void *cuda_stream, int use_own_stream
     HIF_CUDA(cudaSetDevice(h->device));
     HIF_CUDA(cudaStreamSynchronize(h->stream));
     h->stream = use_own_stream ? h->own_stream : static_cast<cudaStream_t>(cuda_stream);
+    h->graphs_off = false;  // the new stream may be capturable (apply.cu)
+    if (h->twin) h->twin->stream = h->stream, h->twin->graphs_off = false;
   });
 }
 

@@ -216,8 +216,22 @@ struct DevMatrix {  // user matrix A in CRS
   DevCsr      A;
 };
 
+struct ApplyGraph {  // one captured apply (apply.cu)
+  const double *  b;
+  double *        x;
+  std::size_t     rank;
+  unsigned        parity;
+  bool            nsp_on;
+  std::size_t     nsp_start, nsp_end;
+  unsigned        uses;
+  cudaGraphExec_t exec;
+  std::size_t     launches;
+};
+
 struct Handle {
   int                   device = 0, num_sms = 148;
+  std::vector<ApplyGraph> graphs;
+  bool                    graphs_off = false;  // the handle's stream can not be captured
   std::vector<DevLevel> levels;
   DevDense              dense;
   DevMatrix             A;
@@ -297,6 +311,7 @@ void launch_stream_sweep(Handle *h, const SweepPlan &plan, const double *rhs_pla
 
 // ---- apply.cu : the multilevel M^{-1} apply on device vectors
 void apply_dev(Handle *h, const double *d_b, double *d_x, std::size_t rank);
+void clear_apply_graphs(Handle *h);
 void check_sweep_error(Handle *h);  // synchronizes; throws if a sweep tripped its spin limit
 
 void dense_solve_dev(Handle *h, const double *d_in, double *d_out, std::size_t rank);     // QRCP::solve

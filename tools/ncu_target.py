@@ -24,7 +24,9 @@ def main():
     bh = P.seeded_rhs(n, 0)
     b = torch.from_numpy(bh).cuda()
     x = torch.empty_like(b)
-    G.set_stream(torch.cuda.current_stream().cuda_stream)
+    side = torch.cuda.Stream()
+    torch.cuda.set_stream(side)
+    G.set_stream(side.cuda_stream)
     for _ in range(args.applies):
         G.solve_dev(b.data_ptr(), x.data_ptr())
     G.synchronize()

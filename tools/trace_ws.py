@@ -76,7 +76,9 @@ def main():
     n = A[0]
     b = torch.from_numpy(P.seeded_rhs(n, 0)).cuda()
     x = torch.empty_like(b)
-    G.set_stream(torch.cuda.current_stream().cuda_stream)
+    side = torch.cuda.Stream()
+    torch.cuda.set_stream(side)
+    G.set_stream(side.cuda_stream)
     for _ in range(3):
         G.solve_dev(b.data_ptr(), x.data_ptr())
     G.synchronize()

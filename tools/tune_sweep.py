@@ -52,7 +52,9 @@ def main():
                 os.environ.pop(k, None)
             continue
         t_attach = time.time() - t0
-        G.set_stream(torch.cuda.current_stream().cuda_stream)
+        side = torch.cuda.Stream()
+        torch.cuda.set_stream(side)
+        G.set_stream(side.cuda_stream)
         try:
             for _ in range(3):
                 G.solve_dev(b.data_ptr(), x.data_ptr())
