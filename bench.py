@@ -390,6 +390,132 @@ def run_mrhs(args, rank, world, local_rank):
     print(json.dumps(line), flush=True)
 
 
+def pin_to_gpu_numa(local_rank):
+    """Bind this rank to the host cores of the NUMA node its GPU hangs off (pinned-memory copies of 8
+    ranks all served by node 0 were the e2e limiter of round 1).  Best effort: returns a description."""
+    try:
+        out = subprocess.run(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i", str(local_rank)],
+                             capture_output=True, text=True, timeout=10).stdout.strip().lower()
+        bus = out[-12:] if len(out) >= 12 else out  # 0000:xx:yy.z
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read())
+        if node < 0:
+            return "numa node unknown"
+        cpus = []
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.extend(range(int(lo), int(hi or lo) + 1))
+        allowed = sorted(set(cpus) & os.sched_getaffinity(0))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return f"numa node {node}, {len(allowed)} cores"
+        return f"numa node {node} (no allowed cores there)"
+    except Exception as e:  # noqa: BLE001
+        return f"not pinned ({type(e).__name__})"
+
+
+REPEATS = 5  # timed repeats of the --steps steps; the median is reported (SURVEY.md 8d)
+
+
+def timed_repeats(step, steps, barrier, stream, repeats=REPEATS):
+    """`repeats` device-timed runs of `steps` calls of step(k) -> list of milliseconds (this rank)"""
+    import torch
+    out = []
+    for _ in range(repeats):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for k in range(steps):
+            step(k)
+        e1.record(stream)
+        barrier()
+        out.append(e0.elapsed_time(e1))
+    return out
+
+
+def max_over_ranks(values, world, dist):
+    """element-wise MAX over the ranks of a list of floats"""
+    import torch
+    t = torch.tensor(values, dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return [float(v) for v in t]
+
+
+def extra_workload(kind, args, rank, world, local_rank, barrier, stream):
+    """Sub-record of the bench line for one of the other BASELINE configs, measured on every rank
+    (no collective inside: the caller gathers).  kind: 'mrhs' (config 4: conv-diff 96^3, nrhs = 64
+    columns sharded over the ranks), 'hifir' (config 5: Neumann 128^3, hifir(nirs = 4), one system per
+    rank), 'stokes' (config 3: Stokes MAC 577^2 apply)."""
+    import torch
+
+    import hifir_b200 as hb
+    from hifir_b200 import problems as P
+    from hifir_b200.sharding import local_columns, shard_range
+    wl, size = {"mrhs": ("convdiff", 96), "hifir": ("neumann", 128), "stokes": ("stokes", 577)}[kind]
+    if args.extras_small:
+        size = {"mrhs": 24, "hifir": 24, "stokes": 48}[kind]
+    steps = max(2, min(args.steps, args.extra_steps))
+    threads = max(1, (os.cpu_count() or 1) // world)
+    A = make_problem(wl, size)
+    n = A[0]
+    nsp = wl == "neumann"
+    t0 = time.time()
+    M = factorize(A, threads=threads, nsp=nsp)
+    t_fact = time.time() - t0
+    G = hb.GpuHif(M.levels(), device=local_rank)
+    G.set_stream(stream.cuda_stream)
+    if nsp:
+        G.set_nsp_const()
+    st = G.stats()
+    rec = {"workload": workload_name(wl, size, 64 if kind == "mrhs" else 1), "n": n, "levels": st["levels"],
+           "factorize_s": round(t_fact, 1), "steps": steps, "repeats": 3}
+    try:
+        if kind == "mrhs":
+            nrhs = 64
+            B = P.seeded_rhs(n, 0, nrhs=nrhs)
+            Bl = local_columns(B, world, rank)
+            nloc = Bl.shape[1]
+            Bd = torch.from_numpy(Bl).cuda()
+            Xd = torch.empty_like(Bd)
+            G.solve_mrhs_dev(nloc, Bd.data_ptr(), Xd.data_ptr(), 0)
+            G.synchronize()
+            b0, _ = shard_range(nrhs, world, rank)
+            errs = []
+            for c in sorted({0, nloc - 1}):
+                xr = M.solve(np.ascontiguousarray(B[:, b0 + c]))
+                errs.append(float(np.linalg.norm(Xd[:, c].cpu().numpy() - xr) / np.linalg.norm(xr)))
+            ms = timed_repeats(lambda k: G.solve_mrhs_dev(nloc, Bd.data_ptr(), Xd.data_ptr(), 0), steps, barrier, stream, 3)
+            rec.update(parity_vs_reference=max(errs), local_ms=ms, nrhs=nrhs, local_columns=nloc,
+                       bytes_per_block=world * (st["bytes_factors"] + st["bytes_dense"]) + nrhs * st["bytes_vec_per_rhs"])
+        elif kind == "hifir":
+            G.set_matrix(A)
+            nirs = 4
+            bh = step_rhs(A, n, rank, nirs)  # one system per rank: its own consistent right-hand side
+            bd = torch.from_numpy(bh).cuda()
+            xd = torch.empty_like(bd)
+            G.hifir_dev(bd.data_ptr(), nirs, xd.data_ptr())
+            G.synchronize()
+            xr = M.hifir(bh, nirs)
+            err = float(np.linalg.norm(xd.cpu().numpy() - xr) / np.linalg.norm(xr))
+            ms = timed_repeats(lambda k: G.hifir_dev(bd.data_ptr(), nirs, xd.data_ptr()), steps, barrier, stream, 3)
+            rec.update(parity_vs_reference=err, local_ms=ms, nirs=nirs)
+        else:
+            bh = P.seeded_rhs(n, rank)
+            bd = torch.from_numpy(bh).cuda()
+            xd = torch.empty_like(bd)
+            G.solve_dev(bd.data_ptr(), xd.data_ptr(), 0)
+            G.synchronize()
+            xr = M.solve(bh)
+            err = float(np.linalg.norm(xd.cpu().numpy() - xr) / np.linalg.norm(xr))
+            ms = timed_repeats(lambda k: G.solve_dev(bd.data_ptr(), xd.data_ptr(), 0), steps, barrier, stream, 3)
+            rec.update(parity_vs_reference=err, local_ms=ms, depths=G.depths().tolist(),
+                       bytes_per_apply=st["bytes_factors"] + st["bytes_dense"] + st["bytes_vec_per_rhs"])
+        G.synchronize()
+    finally:
+        G.close()
+    return rec
+
+
 def run_ours(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
@@ -399,6 +525,7 @@ def run_ours(args, rank, world, local_rank):
 
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback exists)"
     torch.cuda.set_device(local_rank)
+    pinned = pin_to_gpu_numa(local_rank)
     build.build()
     A = make_problem(args.workload, args.size)
     n = A[0]
@@ -418,8 +545,9 @@ def run_ours(args, rank, world, local_rank):
     st = G.stats()
     t_attach = time.time() - t0
     log(f"[bench] rank {rank}: attach {t_attach:.1f} s, device bytes {st['device_bytes'] / 1e9:.2f} GB, "
-        f"depths {G.depths().tolist()}")
-    stream = torch.cuda.current_stream()
+        f"depths {G.depths().tolist()}, {pinned}")
+    stream = torch.cuda.Stream()  # a side stream: the apply schedule is captured into CUDA graphs
+    torch.cuda.set_stream(stream)
     G.set_stream(stream.cuda_stream)
 
     nb = 4
@@ -427,7 +555,7 @@ def run_ours(args, rank, world, local_rank):
     b_host = [torch.from_numpy(step_rhs(A, n, rank * nb + j, nirs)).pin_memory() for j in range(nb)]
     b_dev = [b.cuda() for b in b_host]
     x_dev = torch.empty(n, dtype=torch.float64, device="cuda")
-    x_host = torch.empty(n, dtype=torch.float64).pin_memory()
+    x_host = [torch.empty(n, dtype=torch.float64).pin_memory() for _ in range(2)]
 
     def barrier():
         if world > 1:
@@ -440,11 +568,15 @@ def run_ours(args, rank, world, local_rank):
         else:  # hif::HIF::hifir: last_dim = size_t(-1), full-rank dense solve (builder.hpp:461)
             G.hifir_dev(b_dev[k % nb].data_ptr(), nirs, x_dev.data_ptr())
 
+    pipelined = nirs <= 1 and not single  # lhfdGpuSolveAsync: H2D(k+1) | apply(k) | D2H(k-1)
+
     def step_host(k):
-        if nirs <= 1:
-            G.solve(b_host[k % nb].numpy(), out=x_host.numpy())
+        if pipelined:
+            G.solve_async(b_host[k % nb].numpy(), x_host[k % 2].numpy())
+        elif nirs <= 1:
+            G.solve(b_host[k % nb].numpy(), out=x_host[0].numpy())
         else:
-            x_host.numpy()[:] = G.apply(b_host[k % nb].numpy(), nirs=nirs)[0]
+            x_host[0].numpy()[:] = G.apply(b_host[k % nb].numpy(), nirs=nirs)[0]
 
     # ---- parity spot check before timing (against the reference's own apply, same object)
     step_dev(0)
@@ -455,137 +587,81 @@ def run_ours(args, rank, world, local_rank):
     gate = 1e-5 if single else 1e-12  # north_star tolerances (float / double)
     assert parity <= gate, f"parity gate failed: {parity}"
 
-    # ---- device-resident timing
-    for k in range(args.warmup):
+    # ---- device-resident timing: REPEATS x --steps steps, median
+    for k in range(max(args.warmup, 2 * nb)):
         step_dev(k)
+    G.synchronize()
     launches0 = G.stats()["launch_count"]
     sampler = ClockSampler(local_rank)
-    barrier()
     sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    for k in range(args.steps):
-        step_dev(k)
-    e1.record(stream)
-    barrier()
+    ms_rep = timed_repeats(step_dev, args.steps, barrier, stream)
     clocks = sampler.stop()
     G.synchronize()  # also surfaces a tripped spin limit
-    ms_total = e0.elapsed_time(e1)
-    launches = G.stats()["launch_count"] - launches0
+    launches = (G.stats()["launch_count"] - launches0) // REPEATS
 
-    # ---- end to end through the host-buffer C-ABI call (pinned host memory)
-    for k in range(min(3, args.warmup)):
+    # ---- end to end through the host-buffer C-ABI call (pinned host memory, copies inside the timed region)
+    for k in range(min(4, args.warmup)):
         step_host(k)
-    barrier()
-    t0 = time.perf_counter()
-    for k in range(args.steps):
-        step_host(k)
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    barrier()
+    G.synchronize()
+    e2e_rep = []
+    for _ in range(3):
+        barrier()
+        t0 = time.perf_counter()
+        for k in range(args.steps):
+            step_host(k)
+        G.synchronize()
+        e2e_rep.append((time.perf_counter() - t0) * 1e3)
+        barrier()
+    if pipelined:  # the pipelined entry returns what the synchronous one returns
+        G.solve_async(b_host[0].numpy(), x_host[0].numpy())
+        G.synchronize()
+        assert np.linalg.norm(x_host[0].numpy() - xr) <= gate * np.linalg.norm(xr), "pipelined host solve differs"
 
-    t = torch.tensor([ms_total, e2e_s * 1e3], dtype=torch.float64, device="cuda")
+    red = max_over_ranks(ms_rep + e2e_rep, world, dist)
+    ms_rep, e2e_rep = red[:REPEATS], red[REPEATS:]
+    ms_total, e2e_ms = statistics.median(ms_rep), statistics.median(e2e_rep)
     if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
         # result gather, off the timed path (the only NCCL traffic of this benchmark)
         out = [torch.empty_like(x_dev) for _ in range(world)]
         dist.all_gather(out, x_dev)
-    ms_total, e2e_ms = float(t[0]), float(t[1])
     ms_step = ms_total / args.steps / nirs  # per APPLY (a refinement step holds nirs of them)
-    if rank != 0:
-        return
 
+    # ---- FGMRES-HIFIR solve time on every rank (second half of BASELINE.json's metric)
+    extra = {}
+    if not args.no_fgmres and not single:
+        bk = P.csr_matvec(A, np.ones(n)) if not nsp else P.csr_matvec(A, np.sin(0.37 * np.arange(n)))
+        G.fgmres(bk)  # warm-up (allocates the Krylov basis)
+        barrier()
+        t0 = time.perf_counter()
+        xg, flag, iters, nmv = G.fgmres(bk)
+        tg = time.perf_counter() - t0
+        tmax = max_over_ranks([tg], world, dist)[0]
+        extra["fgmres"] = {"gpu_time_s": tmax, "gpu_time_s_rank0": tg, "iters": iters, "num_mv": nmv, "flag": flag,
+                           "restart": 30, "rtol": 1e-6, "systems": world,
+                           "relres": float(np.linalg.norm(bk - P.csr_matvec(A, xg)) / np.linalg.norm(bk))}
+        if world == 1 and not args.no_cpu:
+            t0 = time.perf_counter()
+            _, rflag, riters, rnmv = M.krylov(bk, "fgmres")
+            extra["fgmres"].update(cpu_time_s=time.perf_counter() - t0, cpu_iters=riters, cpu_num_mv=rnmv,
+                                   cpu_threads=threads)
+
+    # ---- the other BASELINE configs (3, 4, 5) as sub-records, measured on every rank
     st = G.stats()
-    bytes_apply = st["bytes_factors"] + st["bytes_dense"] + st["bytes_vec_per_rhs"]
-    if nirs > 1:  # SURVEY.md 8(d): a refinement adds the bytes of A and 3 vectors, nirs - 1 times per solve
-        bytes_apply += (nirs - 1) * (len(A[2]) * 12 + (n + 1) * 4 + 3 * 8 * n) // nirs
-    peak, peak_src = hbm_peak()
-    achieved = bytes_apply / (ms_step * 1e-3) / 1e9
-    # dominant kernel, timed live with events inside an instrumented apply
     prof = {}
-    for rep in range(5):
-        for name, ms in G.profile_solve_dev(b_dev[0].data_ptr(), x_dev.data_ptr(), 0):
-            prof.setdefault(name, []).append(ms)
-    prof = {k: statistics.median(v) for k, v in prof.items()}
-    sb = sweep_bytes(levels)
-    # dominant kernel = sptrsv_slab_kernel (all triangular sweeps of one apply are launches of it)
-    sweep_ms = {k: v for k, v in prof.items() if k.endswith((".L", ".U"))}
-    sw_bytes = sum(sb[k.split(".")[0] + "." + k.split(".")[-1]] for k in sweep_ms)
-    sw_ms = sum(sweep_ms.values())
-    nl = max(1, len(sweep_ms))
-    k_ach = sw_bytes / (sw_ms * 1e-3) / 1e9
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
-    if os.path.exists(tpath):
-        try:
-            traffic = json.load(open(tpath)).get(workload_name(args.workload, args.size, 1) +
-                                                 (" single-precision factors" if single else ""), {}).get(
-                "sweep_stream_kernel_bytes_per_launch")
-        except Exception:
-            traffic = None
-    # second ceiling of the streaming sweep: every factor entry gathers one solution value from L2 and an
-    # SM serves one L2 request per clock (measured: 289 G gathers/s on B200, tools/lat_bench.cu)
-    gather_peak = 289e9
-    roofline = {"bound": "hbm", "kernel": f"sweep_stream_kernel ({nl} triangular sweeps per apply: L and U of every "
-                                          f"level, down and up)",
-                "achieved": k_ach, "peak": peak, "unit": "GB/s", "frac": k_ach / peak, "traffic": traffic,
-                "algorithmic_bytes_per_launch": sw_bytes / nl, "ms_per_launch": sw_ms / nl,
-                "share_of_step": sw_ms / sum(prof.values()), "peak_source": peak_src,
-                "streamed_bytes_per_launch": st["sweep_bytes"] / nl,
-                "streamed_gbs": st["sweep_bytes"] / (sw_ms * 1e-3) / 1e9,
-                "l2_gather": {"gathers_per_launch": st["sweep_entries"] / nl,
-                              "achieved_g_per_s": st["sweep_entries"] / (sw_ms * 1e-3) / 1e9,
-                              "peak_g_per_s": gather_peak / 1e9,
-                              "frac": st["sweep_entries"] / (sw_ms * 1e-3) / gather_peak},
-                "apply": {"kernels": st["kernels_per_apply"], "algorithmic_bytes": bytes_apply, "achieved": achieved,
-                          "frac": achieved / peak},
-                "latency_floor": {"dependent_steps_per_apply_reference": st["depth_total"],
-                                  "dependent_steps_per_apply_merged": st["depth_merged"],
-                                  "us_per_merged_step_achieved": sw_ms * 1e3 / max(1, st["depth_merged"])},
-                "kernels_ms": {k: round(v, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1])[:10]}}
-
+    if rank == 0:  # dominant kernel, timed live with events inside an instrumented (eager) apply
+        for rep in range(5):
+            for name, ms in G.profile_solve_dev(b_dev[0].data_ptr(), x_dev.data_ptr(), 0):
+                prof.setdefault(name, []).append(ms)
+        prof = {k: statistics.median(v) for k, v in prof.items()}
     cpu = None
-    if world == 1 and not args.no_cpu:
+    if rank == 0 and world == 1 and not args.no_cpu:
         applies = max(1, args.cpu_applies // nirs)
         rate, dt = cpu_apply_rate(M, n, applies, nirs=nirs, A=A)
         cpu = {"value": rate * nirs, "unit": "applies/s", "cores": 1 if nirs <= 1 else threads, "kind": "reference",
                "sample": (f"{applies} hif::HIF::solve applies" if nirs <= 1 else
                           f"{applies} hif::HIF::hifir(nirs={nirs}) solves (A x with {threads} OpenMP threads)") +
                          f" of the same workload on the same factorized object ({dt:.1f} s; the reference apply is serial)"}
-    extra = {}
-    if world == 1 and not args.no_fgmres:
-        bk = P.csr_matvec(A, np.ones(n)) if not nsp else P.csr_matvec(A, np.sin(0.37 * np.arange(n)))
-        G.fgmres(bk)  # warm-up (allocates the Krylov basis)
-        t0 = time.perf_counter()
-        xg, flag, iters, nmv = G.fgmres(bk)
-        tg = time.perf_counter() - t0
-        extra["fgmres"] = {"gpu_time_s": tg, "iters": iters, "num_mv": nmv, "flag": flag,
-                           "relres": float(np.linalg.norm(bk - P.csr_matvec(A, xg)) / np.linalg.norm(bk))}
-        if not args.no_cpu:
-            t0 = time.perf_counter()
-            xr, rflag, riters, rnmv = M.krylov(bk, "fgmres")
-            extra["fgmres"].update(cpu_time_s=time.perf_counter() - t0, cpu_iters=riters, cpu_num_mv=rnmv,
-                                   cpu_threads=threads)
-
-    line = {
-        "metric": "M^-1 applies/sec", "value": world * args.steps * nirs / (ms_total * 1e-3), "unit": "applies/s",
-        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32 factors (hif::HIF<float>), f64 vectors and accumulation" if single else "f64",
-        "data": "synthetic",
-        "config": {"workload": workload_name(args.workload, args.size, 1) + (" single-precision factors" if single else "")
-                   + (f" hifir nirs={nirs}" if nirs > 1 else ""),
-                   "n": n, "levels": st["levels"],
-                   "nnz_factors": st["nnz"], "params": "tau=1e-2 alpha=3 kappa=5 (reference PDE set)",
-                   "l2_policy": f"inputs larger than L2: {bytes_apply / 1e9:.2f} GB streamed per apply vs 126 MB L2",
-                   "parallelism": "replicas, independent right-hand sides per GPU" if world > 1 else "1 GPU"},
-        "roofline": roofline, "cpu_baseline": cpu,
-        "e2e": {"value": world * args.steps * nirs / (e2e_ms * 1e-3), "unit": "applies/s", "h2d_bytes_per_step": 8 * n,
-                "d2h_bytes_per_step": 8 * n,
-                "api": (("lhfsdGpuSolve" if single else "lhfdGpuSolve") if nirs <= 1 else
-                        ("lhfsdGpuApply" if single else "lhfdGpuApply") + f"(LHF_S, nirs={nirs})") + " (pinned host buffers)"},
-        "gpu_launches": launches, "clocks": clocks, "parity_vs_reference": parity,
-    }
+    arena = None
     if args.arena_check and world == 1:
         # factor arena file (csrc/arena.cu): write, attach from the file, compare with the live attach
         path = os.path.join(CACHE_DIR, f"bench_{args.workload}{args.size}_{args.precision}.hifb")
@@ -602,18 +678,133 @@ def run_ours(args, rank, world, local_rank):
         # with the applies of both parities of the file-attached handle
         xb = G.solve(b_host[0].numpy())
         xa = [F.solve(b_host[0].numpy()) for _ in range(2)]
-        line["arena"] = {"file_bytes": os.path.getsize(path), "save_s": t_save, "attach_file_s": t_file,
-                         "attach_live_s": t_attach, "factorize_s_not_needed": t_fact,
-                         "bit_identical_to_live_attach": bool(any(np.array_equal(x, xb) for x in xa)),
-                         "max_rel_diff": float(max(np.linalg.norm(x - xb) for x in xa) / np.linalg.norm(xb))}
+        arena = {"file_bytes": os.path.getsize(path), "save_s": t_save, "attach_file_s": t_file,
+                 "attach_live_s": t_attach, "factorize_s_not_needed": t_fact,
+                 "bit_identical_to_live_attach": bool(any(np.array_equal(x, xb) for x in xa)),
+                 "max_rel_diff": float(max(np.linalg.norm(x - xb) for x in xa) / np.linalg.norm(xb))}
         F.close()
         os.remove(path)
+    G.close()
+    del M
+    extras = {}
+    for kind in [k for k in args.extras.split(",") if k in ("mrhs", "hifir", "stokes")]:
+        barrier()
+        try:
+            rec = extra_workload(kind, args, rank, world, local_rank, barrier, stream)
+        except Exception as e:  # noqa: BLE001 -- a failing extra must not take the headline down
+            rec = {"error": f"{type(e).__name__}: {e}"[:300]}
+        if world > 1:
+            allrec = [None] * world
+            dist.all_gather_object(allrec, rec)
+        else:
+            allrec = [rec]
+        if rank == 0:
+            errs = [r["error"] for r in allrec if "error" in r]
+            if errs:
+                extras[kind] = {"error": errs[0]}
+                continue
+            r0 = dict(allrec[0])
+            ms = statistics.median([max(r["local_ms"][i] for r in allrec) for i in range(len(r0["local_ms"]))])  # max over ranks
+            r0.pop("local_ms")
+            r0["parity_vs_reference"] = max(r["parity_vs_reference"] for r in allrec)
+            r0["ms_per_step"] = ms / r0["steps"]
+            peak = hbm_peak()[0]
+            if kind == "mrhs":
+                r0.update(metric="column applies/s, 64 columns sharded over the ranks (strong scaling)",
+                          value=r0["nrhs"] * r0["steps"] / (ms * 1e-3), scaling="strong",
+                          roofline_frac=r0["bytes_per_block"] / (r0["ms_per_step"] * 1e-3) / 1e9 / (peak * world))
+            elif kind == "hifir":
+                r0.update(metric="applies/s inside hifir(A, b, 4, x), one system per rank (weak scaling)",
+                          value=world * r0["nirs"] * r0["steps"] / (ms * 1e-3), scaling="weak",
+                          solves_per_s=world * r0["steps"] / (ms * 1e-3))
+            else:
+                r0.update(metric="applies/s, one replica per rank (weak scaling)",
+                          value=world * r0["steps"] / (ms * 1e-3), scaling="weak",
+                          roofline_frac=r0["bytes_per_apply"] / (r0["ms_per_step"] * 1e-3) / 1e9 / peak)
+            extras[kind] = r0
+    if rank != 0:
+        return
+
+    bytes_apply = st["bytes_factors"] + st["bytes_dense"] + st["bytes_vec_per_rhs"]
+    if nirs > 1:  # SURVEY.md 8(d): a refinement adds the bytes of A and 3 vectors, nirs - 1 times per solve
+        bytes_apply += (nirs - 1) * (len(A[2]) * 12 + (n + 1) * 4 + 3 * 8 * n) // nirs
+    peak, peak_src = hbm_peak()
+    achieved = bytes_apply / (ms_step * 1e-3) / 1e9
+    sb = sweep_bytes(levels)
+    # dominant kernel = wsweep_kernel (all triangular sweeps of one apply are launches of it)
+    sweep_ms = {k: v for k, v in prof.items() if k.endswith((".L", ".U"))}
+    sw_bytes = sum(sb[k.split(".")[0] + "." + k.split(".")[-1]] for k in sweep_ms)
+    sw_ms = sum(sweep_ms.values())
+    nl = max(1, len(sweep_ms))
+    k_ach = sw_bytes / (sw_ms * 1e-3) / 1e9
+    # DRAM traffic of the dominant kernel: from the ncu capture of THIS kernel on THIS workload
+    # (tools/ncu_traffic.py writes profiles/ncu_traffic.json); dropped when the packed factor differs
+    traffic, traffic_src = None, None
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tpath):
+        try:
+            t = json.load(open(tpath)).get(workload_name(args.workload, args.size, 1), {})
+            if t.get("kernel") == "wsweep_kernel" and abs(t.get("sweep_bytes", 0) - st["sweep_bytes"]) <= 0.02 * st["sweep_bytes"]:
+                traffic, traffic_src = t.get("dram_bytes_per_launch"), t.get("source")
+        except Exception:
+            traffic = None
+    # second ceiling of the sweeps: every factor entry gathers one solution value from L2 and an SM
+    # accepts one L2 sector request per clock (measured: 289 G gathers/s on B200, tools/lat_bench.cu)
+    gather_peak = 289e9
+    roofline = {"bound": "hbm", "kernel": f"wsweep_kernel ({nl} triangular sweeps per apply: L and U of every "
+                                          f"level, down and up)",
+                "achieved": k_ach, "peak": peak, "unit": "GB/s", "frac": k_ach / peak, "traffic": traffic,
+                "traffic_source": traffic_src,
+                "algorithmic_bytes_per_launch": sw_bytes / nl, "ms_per_launch": sw_ms / nl,
+                "share_of_step": sw_ms / max(1e-9, sum(prof.values())), "peak_source": peak_src,
+                "streamed_bytes_per_launch": st["sweep_bytes"] / nl,
+                "streamed_gbs": st["sweep_bytes"] / (sw_ms * 1e-3) / 1e9,
+                "l2_gather": {"gathers_per_launch": st["sweep_entries"] / nl,
+                              "achieved_g_per_s": st["sweep_entries"] / (sw_ms * 1e-3) / 1e9,
+                              "peak_g_per_s": gather_peak / 1e9,
+                              "frac": st["sweep_entries"] / (sw_ms * 1e-3) / gather_peak},
+                "apply": {"kernels": st["kernels_per_apply"], "algorithmic_bytes": bytes_apply, "achieved": achieved,
+                          "frac": achieved / peak},
+                "latency_floor": {"dependent_steps_per_apply_reference": st["depth_total"],
+                                  "dependent_steps_per_apply_merged": st["depth_merged"],
+                                  "us_per_merged_step_achieved": sw_ms * 1e3 / max(1, st["depth_merged"])},
+                "kernels_ms": {k: round(v, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1])[:12]},
+                "timing": "kernels_ms: CUDA events around every kernel of an eager apply (median of 5); the timed "
+                          "region itself launches each apply as one CUDA graph"}
+
+    line = {
+        "metric": "M^-1 applies/sec", "value": world * args.steps * nirs / (ms_total * 1e-3), "unit": "applies/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
+        "repeats": REPEATS, "ms_per_step_repeats": [round(v / args.steps, 5) for v in ms_rep],
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32 factors (hif::HIF<float>), f64 vectors and accumulation" if single else "f64",
+        "data": "synthetic",
+        "config": {"workload": workload_name(args.workload, args.size, 1) + (" single-precision factors" if single else "")
+                   + (f" hifir nirs={nirs}" if nirs > 1 else ""),
+                   "n": n, "params": "tau=1e-2 alpha=3 kappa=5 (reference PDE set)"},
+        "run": {"levels": st["levels"], "nnz_factors": st["nnz"],
+                "l2_policy": f"inputs larger than L2: {bytes_apply / 1e9:.2f} GB streamed per apply vs 126 MB L2",
+                "parallelism": "replicas, independent right-hand sides per GPU" if world > 1 else "1 GPU",
+                "host_binding": pinned, "attach_s": round(t_attach, 1), "factorize_s": round(t_fact, 1)},
+        "roofline": roofline, "cpu_baseline": cpu,
+        "e2e": {"value": world * args.steps * nirs / (e2e_ms * 1e-3), "unit": "applies/s", "h2d_bytes_per_step": 8 * n,
+                "d2h_bytes_per_step": 8 * n, "ms_per_step": e2e_ms / args.steps,
+                "copy_gb_per_s_per_rank": 16 * n * args.steps / (e2e_ms * 1e-3) / 1e9,
+                "api": ("lhfdGpuSolveAsync + lhfdGpuSynchronize (pinned host buffers; H2D, apply and D2H of consecutive "
+                        "steps overlap; every step copies its b in and its x out)") if pipelined else
+                       ((("lhfsdGpuSolve" if single else "lhfdGpuSolve") if nirs <= 1 else
+                         ("lhfsdGpuApply" if single else "lhfdGpuApply") + f"(LHF_S, nirs={nirs})") + " (pinned host buffers)")},
+        "gpu_launches": launches, "clocks": clocks, "parity_vs_reference": parity,
+    }
+    if arena:
+        line["arena"] = arena
     if nirs > 1:
         line["hifir"] = {"nirs": nirs, "solves_per_s": world * args.steps / (ms_total * 1e-3),
                          "ms_per_solve": ms_total / args.steps,
                          "step": f"hif::HIF::hifir(A, b, {nirs}, x): {nirs} applies + {nirs - 1} residuals b - A x, "
                                  "independent systems per GPU"}
     line.update(extra)
+    line.update(extras)
     print(json.dumps(line), flush=True)
 
 
@@ -637,6 +828,11 @@ def main():
     ap.add_argument("--ref-max-steps", type=int, default=300)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-fgmres", action="store_true")
+    ap.add_argument("--extras", default="mrhs,hifir,stokes",
+                    help="other BASELINE configs measured as sub-records of the line: mrhs (config 4), hifir (config 5), "
+                         "stokes (config 3); '' = none")
+    ap.add_argument("--extra-steps", type=int, default=10)
+    ap.add_argument("--extras-small", action="store_true", help="developer: small sizes for the extras")
     args = ap.parse_args()
     args.warmup = max(3, args.warmup)
 

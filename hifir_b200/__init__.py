@@ -113,6 +113,7 @@ def lib():
             "lhfdGpuSetStream": [vp, vp, i],
             "lhfdGpuSynchronize": [vp],
             "lhfdGpuSolve": [vp, vp, vp],
+            "lhfdGpuSolveAsync": [vp, vp, vp],
             "lhfdGpuApply": [vp, i, vp, i, vp, i, vp, vp],
             "lhfdGpuSolveMrhs": [vp, sz, vp, vp],
             "lhfdGpuFgmres": [vp, vp, i, d, i, i, vp, vp, vp, vp],
@@ -160,7 +161,7 @@ def lib():
 
 EXPORTED_SYMBOLS = (
     "lhfdGpuAttachLevels", "lhfdGpuDestroy", "lhfdGpuSetMatrix", "lhfdGpuSetNspConst", "lhfdGpuClearNsp",
-    "lhfdGpuSetStream", "lhfdGpuSynchronize", "lhfdGpuSolve", "lhfdGpuApply", "lhfdGpuSolveMrhs",
+    "lhfdGpuSetStream", "lhfdGpuSynchronize", "lhfdGpuSolve", "lhfdGpuSolveAsync", "lhfdGpuApply", "lhfdGpuSolveMrhs",
     "lhfdGpuFgmres", "lhfdGpuGmres", "lhfdGpuApplyDev", "lhfdGpuSolveDev", "lhfdGpuSolveMrhsDev", "lhfdGpuHifirDev",
     "lhfdGpuSpmvDev", "lhfdGpuProfileSolveDev",
     "lhfdGpuGetStats", "lhfdGpuGetDepths", "lhfGpuGetErrorMsg", "lhfGpuVersion",
@@ -343,6 +344,12 @@ class GpuHif:
         x = np.empty_like(b) if out is None else out
         _chk((lib().lhfsdGpuSolve if self.single else lib().lhfdGpuSolve)(self._h, _ptr(b), _ptr(x)))
         return x
+
+    def solve_async(self, b, out):
+        """lhfdGpuSolveAsync: enqueue x = M^-1 b for host arrays (contiguous float64, ideally pinned);
+        `out` must not be read before synchronize().  b and out must stay alive until then."""
+        assert b.dtype == np.float64 and out.dtype == np.float64 and b.flags.c_contiguous and out.flags.c_contiguous
+        _chk(lib().lhfdGpuSolveAsync(self._h, _ptr(b), _ptr(out)))
 
     def solve_f32(self, b):
         """lhfsGpuSolve: float vectors (single-precision handles only)"""

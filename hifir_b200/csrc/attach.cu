@@ -429,6 +429,17 @@ void destroy_handle(Handle *h) {
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
   clear_apply_graphs(h);
+  if (h->aio.h2d) {
+    cudaStreamSynchronize(h->aio.h2d);
+    cudaStreamSynchronize(h->aio.d2h);
+    for (int s = 0; s < 2; ++s) {
+      cudaEventDestroy(h->aio.copied_in[s]);
+      cudaEventDestroy(h->aio.applied[s]);
+      cudaEventDestroy(h->aio.copied_out[s]);
+    }
+    cudaStreamDestroy(h->aio.h2d);
+    cudaStreamDestroy(h->aio.d2h);
+  }
   if (h->twin) destroy_handle(h->twin);
   if (h->h_error) cudaFreeHost(h->h_error);
   if (h->h_scal) cudaFreeHost(h->h_scal);

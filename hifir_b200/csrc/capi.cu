@@ -98,6 +98,48 @@ void d2h(Handle *h, float *dst, const double *src, std::size_t count) {
 
 Handle *H(LhfsGpuHdl hdl) { return reinterpret_cast<Handle *>(hdl); }
 
+// lhfdGpuSolveAsync: host-buffer solves as a three-stage pipeline.  Two staging slots; the copies
+// run on their own streams, ordered against the apply by events, so that H2D(k+1), apply(k) and
+// D2H(k-1) overlap.  The apply of slot s always sees the same device pointers: its CUDA graph is
+// captured once.
+void solve_host_async(Handle *h, const double *b, double *x) {
+  HIF_CUDA(cudaSetDevice(h->device));
+  const std::size_t n = h->n0();
+  AsyncIo &         A = h->aio;
+  if (!A.h2d) {
+    HIF_CUDA(cudaStreamCreateWithFlags(&A.h2d, cudaStreamNonBlocking));
+    HIF_CUDA(cudaStreamCreateWithFlags(&A.d2h, cudaStreamNonBlocking));
+    for (int s = 0; s < 2; ++s) {
+      A.b[s].alloc(n, &h->device_bytes);
+      A.x[s].alloc(n, &h->device_bytes);
+      HIF_CUDA(cudaEventCreateWithFlags(&A.copied_in[s], cudaEventDisableTiming));
+      HIF_CUDA(cudaEventCreateWithFlags(&A.applied[s], cudaEventDisableTiming));
+      HIF_CUDA(cudaEventCreateWithFlags(&A.copied_out[s], cudaEventDisableTiming));
+    }
+  }
+  const int s = static_cast<int>(A.count++ & 1u);
+  if (A.count > 2) {
+    HIF_CUDA(cudaStreamWaitEvent(A.h2d, A.applied[s], 0));  // the previous apply of this slot has consumed b[s]
+  }
+  HIF_CUDA(cudaMemcpyAsync(A.b[s].p, b, n * sizeof(double), cudaMemcpyHostToDevice, A.h2d));
+  HIF_CUDA(cudaEventRecord(A.copied_in[s], A.h2d));
+  HIF_CUDA(cudaStreamWaitEvent(h->stream, A.copied_in[s], 0));
+  if (A.count > 2) HIF_CUDA(cudaStreamWaitEvent(h->stream, A.copied_out[s], 0));  // x[s] has left the device
+  apply_dev(h, A.b[s].p, A.x[s].p, 0);
+  HIF_CUDA(cudaEventRecord(A.applied[s], h->stream));
+  HIF_CUDA(cudaStreamWaitEvent(A.d2h, A.applied[s], 0));
+  HIF_CUDA(cudaMemcpyAsync(x, A.x[s].p, n * sizeof(double), cudaMemcpyDeviceToHost, A.d2h));
+  HIF_CUDA(cudaEventRecord(A.copied_out[s], A.d2h));
+}
+void wait_host_async(Handle *h) {
+  AsyncIo &A = h->aio;
+  if (A.h2d) {
+    HIF_CUDA(cudaStreamSynchronize(A.h2d));
+    HIF_CUDA(cudaStreamSynchronize(h->stream));
+    HIF_CUDA(cudaStreamSynchronize(A.d2h));
+  }
+}
+
 // lhf?Solve (libhifir.cpp:151-158): IO = the caller's vector type
 template <class IO>
 void solve_host(Handle *h, const IO *b, IO *x) {
@@ -261,8 +303,16 @@ LhfStatus lhfdGpuSynchronize(LhfdGpuHdl hdl) {
   REQUIRE_HANDLE(hdl);
   return guarded([&] {
     HIF_CUDA(cudaSetDevice(H(hdl)->device));
+    wait_host_async(H(hdl));
     check_sweep_error(H(hdl));
   });
+}
+
+LhfStatus lhfdGpuSolveAsync(LhfdGpuHdl hdl, const double *b, double *x) {
+  REQUIRE_HANDLE(hdl);
+  REQUIRE_PTR(b, "b");
+  REQUIRE_PTR(x, "x");
+  return guarded([&] { solve_host_async(H(hdl), b, x); });
 }
 
 LhfStatus lhfdGpuSolveDev(LhfdGpuHdl hdl, const double *d_b, double *d_x, size_t rank) {

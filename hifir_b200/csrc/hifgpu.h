@@ -216,6 +216,13 @@ struct DevMatrix {  // user matrix A in CRS
   DevCsr      A;
 };
 
+struct AsyncIo {  // pipelined host-buffer solves (lhfdGpuSolveAsync, capi.cu)
+  cudaStream_t   h2d = nullptr, d2h = nullptr;
+  DevBuf<double> b[2], x[2];
+  cudaEvent_t    copied_in[2] = {nullptr, nullptr}, applied[2] = {nullptr, nullptr}, copied_out[2] = {nullptr, nullptr};
+  std::size_t    count = 0;
+};
+
 struct ApplyGraph {  // one captured apply (apply.cu)
   const double *  b;
   double *        x;
@@ -231,6 +238,7 @@ struct ApplyGraph {  // one captured apply (apply.cu)
 struct Handle {
   int                   device = 0, num_sms = 148;
   std::vector<ApplyGraph> graphs;
+  AsyncIo                 aio;
   bool                    graphs_off = false;  // the handle's stream can not be captured
   std::vector<DevLevel> levels;
   DevDense              dense;

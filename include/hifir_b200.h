@@ -131,6 +131,14 @@ LhfStatus lhfdGpuSynchronize(LhfdGpuHdl hdl);
  * = hif::HIF::solve(b, x) (builder.hpp:409-423), last-level rank = numerical. */
 LhfStatus lhfdGpuSolve(LhfdGpuHdl hdl, const double *b, double *x);
 
+/* lhfdGpuSolve without the wait: the copy of b to the device, the apply and the copy of x back are
+ * enqueued as a three-stage pipeline over two staging slots, so that consecutive calls overlap
+ * (H2D of call k+1, apply of call k, D2H of call k-1).  b and x (pinned host memory for true
+ * overlap) must stay valid, and x must not be read, until lhfdGpuSynchronize(hdl) returns.
+ * Same arithmetic and result as lhfdGpuSolve (libhifir.cpp:151-158 semantics); errors of the
+ * enqueued work surface at lhfdGpuSynchronize. */
+LhfStatus lhfdGpuSolveAsync(LhfdGpuHdl hdl, const double *b, double *x);
+
 /* Drop-in for lhfdApply (libhifir.h:685-688, libhifir.cpp:447-472): same `op`,
  * `nirs`, `betas`, `rank`, `ir_status` meaning, including the rank-defaulting
  * rule (libhifir.cpp:453-455) and the fact that the plain solve path ignores
