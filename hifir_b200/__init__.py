@@ -109,6 +109,7 @@ def lib():
             "lhfdGpuDestroy": [vp],
             "lhfdGpuSetMatrix": [vp, i, sz, vp, vp, vp],
             "lhfdGpuSetNspConst": [vp, sz, sz],
+            "lhfdGpuSetNspTranConst": [vp, sz, sz],
             "lhfdGpuClearNsp": [vp],
             "lhfdGpuSetStream": [vp, vp, i],
             "lhfdGpuSynchronize": [vp],
@@ -129,6 +130,7 @@ def lib():
             "lhfdGpuDebugExportInts": [vp, sz, i, vp, sz, vp],
             "lhfdGpuDebugTraceSweep": [vp, vp, vp, i, i, vp, sz, vp],
             "lhfdGpuDebugSegmentGraph": [vp, i, sz, sz, vp, vp, vp],
+            "lhfdGpuDebugNorm2Dev": [vp, vp, sz, vp],
             "lhfdGpuGetStats": [vp, vp],
             "lhfdGpuGetDepths": [vp, sz, vp],
             "lhfsGpuAttachLevels": [i, sz, vp, vp],
@@ -160,7 +162,7 @@ def lib():
 
 
 EXPORTED_SYMBOLS = (
-    "lhfdGpuAttachLevels", "lhfdGpuDestroy", "lhfdGpuSetMatrix", "lhfdGpuSetNspConst", "lhfdGpuClearNsp",
+    "lhfdGpuAttachLevels", "lhfdGpuDestroy", "lhfdGpuSetMatrix", "lhfdGpuSetNspConst", "lhfdGpuSetNspTranConst", "lhfdGpuClearNsp",
     "lhfdGpuSetStream", "lhfdGpuSynchronize", "lhfdGpuSolve", "lhfdGpuSolveAsync", "lhfdGpuApply", "lhfdGpuSolveMrhs",
     "lhfdGpuFgmres", "lhfdGpuGmres", "lhfdGpuApplyDev", "lhfdGpuSolveDev", "lhfdGpuSolveMrhsDev", "lhfdGpuHifirDev",
     "lhfdGpuSpmvDev", "lhfdGpuProfileSolveDev",
@@ -170,7 +172,8 @@ EXPORTED_SYMBOLS = (
     "lhfdGpuSaveLevels", "lhfsGpuSaveLevels", "lhfdGpuAttachFile", "lhfsGpuAttachFile", "lhfGpuFileInfo")
 # developer / test hooks declared in hifir_b200/csrc/debug_api.h (not part of the drop-in boundary)
 DEBUG_SYMBOLS = ("lhfdGpuDebugSweepHost", "lhfsGpuDebugSweepHost", "lhfGpuDebugFileSweepHost", "lhfdGpuDebugPlanLab",
-                 "lhfdGpuDebugExportInts", "lhfdGpuDebugTraceSweep", "lhfdGpuDebugSegmentGraph")
+                 "lhfdGpuDebugExportInts", "lhfdGpuDebugTraceSweep", "lhfdGpuDebugSegmentGraph",
+                 "lhfdGpuDebugNorm2Dev")
 
 
 class LhfError(RuntimeError):
@@ -324,6 +327,16 @@ class GpuHif:
 
     def set_nsp_const(self, start=0, end=FULL_RANK):
         _chk(lib().lhfdGpuSetNspConst(self._h, start, end))
+
+    def set_nsp_tran_const(self, start=0, end=FULL_RANK):
+        """hif::HIF::nsp_tran: the filter of the transposed solve (LHF_SH)"""
+        _chk(lib().lhfdGpuSetNspTranConst(self._h, start, end))
+
+    def norm2_dev(self, d_v, n):
+        """lhfdGpuDebugNorm2Dev: the device 2-norm of the refinement / Krylov loops"""
+        out = C.c_double()
+        _chk(lib().lhfdGpuDebugNorm2Dev(self._h, C.c_void_p(d_v), n, C.byref(out)))
+        return out.value
 
     def clear_nsp(self):
         _chk(lib().lhfdGpuClearNsp(self._h))

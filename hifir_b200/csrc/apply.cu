@@ -117,10 +117,11 @@ __global__ void __launch_bounds__(kTrsvThreads, 1)
       if (tid < w) {
 #pragma unroll 8
         for (unsigned j = 0; j < 32u; j += 4) {
-          a0 = fma(Ti[(j + 0u) * 32u], (j + 0u < w && j + 0u >= tid) ? xs[j0 + j + 0u] : 0.0, a0);
-          a1 = fma(Ti[(j + 1u) * 32u], (j + 1u < w && j + 1u >= tid) ? xs[j0 + j + 1u] : 0.0, a1);
-          a2 = fma(Ti[(j + 2u) * 32u], (j + 2u < w && j + 2u >= tid) ? xs[j0 + j + 2u] : 0.0, a2);
-          a3 = fma(Ti[(j + 3u) * 32u], (j + 3u < w && j + 3u >= tid) ? xs[j0 + j + 3u] : 0.0, a3);
+          // masked columns (beyond the rank, below the diagonal) stay OUT of the arithmetic
+          if (j + 0u < w && j + 0u >= tid) a0 = fma(Ti[(j + 0u) * 32u], xs[j0 + j + 0u], a0);
+          if (j + 1u < w && j + 1u >= tid) a1 = fma(Ti[(j + 1u) * 32u], xs[j0 + j + 1u], a1);
+          if (j + 2u < w && j + 2u >= tid) a2 = fma(Ti[(j + 2u) * 32u], xs[j0 + j + 2u], a2);
+          if (j + 3u < w && j + 3u >= tid) a3 = fma(Ti[(j + 3u) * 32u], xs[j0 + j + 3u], a3);
         }
       }
       const double xv = (a0 + a1) + (a2 + a3);
@@ -137,8 +138,8 @@ __global__ void __launch_bounds__(kTrsvThreads, 1)
       double b0 = 0.0, b1 = 0.0;
 #pragma unroll
       for (int jj = 0; jj < 32; jj += 2) {
-        b0 = fma(r[jj], static_cast<unsigned>(jj) < w ? xs[j0 + jj] : 0.0, b0);
-        b1 = fma(r[jj + 1], static_cast<unsigned>(jj + 1) < w ? xs[j0 + jj + 1] : 0.0, b1);
+        if (static_cast<unsigned>(jj) < w) b0 = fma(r[jj], xs[j0 + jj], b0);
+        if (static_cast<unsigned>(jj + 1) < w) b1 = fma(r[jj + 1], xs[j0 + jj + 1], b1);
       }
       xs[i] -= b0 + b1;
     }
@@ -243,11 +244,22 @@ void launch_spmv_resid(Handle *h, const DevCsr &A, const int *col, const void *x
 namespace {
 void apply_schedule(Handle *h, const double *d_b, double *d_x, std::size_t rank, unsigned parity);
 }
+void apply_dev_impl(Handle *h, const double *d_b, double *d_x, std::size_t rank);
+void reset_tagged_state(Handle *h);
 
 // The schedule of one apply is static: the second apply with the same (b, x, rank, tag parity, filter)
 // captures it into a CUDA graph, every later one is a single graph launch (the kernels of an apply
 // are short -- 8 to 160 us -- and there are a dozen and a half of them).
 void apply_dev(Handle *h, const double *d_b, double *d_x, std::size_t rank) {
+  try {
+    apply_dev_impl(h, d_b, d_x, rank);
+  } catch (...) {
+    reset_tagged_state(h);
+    throw;
+  }
+}
+
+void apply_dev_impl(Handle *h, const double *d_b, double *d_x, std::size_t rank) {
   HIF_CUDA(cudaSetDevice(h->device));
   ++h->epoch;
   const unsigned parity = h->epoch & 1u;
@@ -300,6 +312,23 @@ void apply_dev(Handle *h, const double *d_b, double *d_x, std::size_t rank) {
   HIF_CUDA(cudaGraphLaunch(g->exec, h->stream));
   h->launch_count += g->launches;
   h->kernels_per_apply = g->launches;
+}
+
+// An apply that failed half way (launch error, exception) has bumped the epoch but rewritten only some
+// of the tagged buffers: two applies later their stale slots would read as ready.  Start over: zero
+// every tagged buffer, epoch 0.
+void reset_tagged_state(Handle *h) {
+  cudaStreamSynchronize(h->stream);
+  cudaGetLastError();
+  auto zero = [&](DevBuf<unsigned long long> &b) {
+    if (b.p) cudaMemset(b.p, 0, b.n * sizeof(unsigned long long));
+  };
+  for (DevLevel &D : h->levels)
+    for (DevBuf<unsigned long long> *b : {&D.xL_dn, &D.xU_dn, &D.xL_up, &D.xU_up, &D.p_xL, &D.p_xU, &D.m_xL_dn, &D.m_xU_dn,
+                                          &D.m_xL_up, &D.m_xU_up})
+      zero(*b);
+  h->epoch = h->epoch_m = h->epoch_p = 0;
+  cudaDeviceSynchronize();
 }
 
 void clear_apply_graphs(Handle *h) {
@@ -511,6 +540,7 @@ void check_sweep_error(Handle *h) {
     int       info[8] = {0};
     cudaMemcpy(info, h->error_flag.p, sizeof(info), cudaMemcpyDeviceToHost);
     HIF_CUDA(cudaMemsetAsync(h->error_flag.p, 0, 8 * sizeof(int), h->stream));
+    reset_tagged_state(h);  // the aborted sweep left slots unwritten
     std::string where;
     if (info[1])  // the first failing wait left its coordinates (wsweep.cu, ws_fail)
       where = " [warp " + std::to_string(info[2]) + " segment " + std::to_string(info[3]) + " level " +

@@ -47,6 +47,7 @@ HostCsr merged_sweep_form(const HostCsr &Tnat, bool upper, const MergeParams &mp
     }
   }
   HostCsr S = to_sweep_form(Tnat, upper);
+  validate_sweep_form(S);  // strictly triangular input: every entry references an earlier sweep row
   if (mp.enabled) S = merge_levels(S, mp, ms, upper);
   return S;
 }
@@ -325,8 +326,11 @@ void ArenaFile::load(const char *path, bool want_plans) {
         mf.st.depth = s[4], mf.st.ext_depth = s[5], mf.st.super_levels = s[6];
         if (mf.S.ptr.empty() || mf.S.ptr.back() != nnz || orig != lv[l].m)
           throw std::runtime_error("arena file: inconsistent plan");
-        for (int c : mf.S.col)
-          if (c < 0 || static_cast<std::size_t>(c) >= nrows) throw std::runtime_error("arena file: inconsistent plan");
+        try {
+          validate_sweep_form(mf.S);  // a stale or foreign file must not become an out-of-bounds device access
+        } catch (const std::exception &e) {
+          throw std::runtime_error(std::string("arena file: inconsistent plan (") + e.what() + ")");
+        }
         if (want_plans) plans.f.push_back(std::move(mf));
       }
     }

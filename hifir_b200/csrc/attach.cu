@@ -3,6 +3,7 @@
 // alg/Prec.hpp:309-323), convert each CCS block to the row-gather CSR form the kernels
 // consume, analyse the triangular dependency structure, upload everything once.
 #include <algorithm>
+#include <cmath>
 #include <cstring>
 #include <exception>
 #include <memory>
@@ -22,6 +23,7 @@ HostCsr ccs_to_csr(const LhfdGpuCcs &c, const char *name) {
   r.ptr.assign(c.nrows + 1, 0u);
   if (!c.col_start || !c.ncols) return r;
   const LhfIndPtr nnz = c.col_start[c.ncols];
+  if (c.col_start[0] != 0) throw std::invalid_argument(std::string(name) + ": col_start[0] is not 0");
   if (nnz < 0 || static_cast<unsigned long long>(nnz) > 0x7fffffffull)
     throw std::invalid_argument(std::string(name) + ": more than 2^31-1 nonzeros in one block");
   if (nnz && (!c.row_ind || !c.vals)) throw std::invalid_argument(std::string(name) + ": null index/value array");
@@ -340,7 +342,10 @@ Handle *attach_levels(int device, std::size_t nlevels, const LhfdGpuLevel *lv, b
             for (std::size_t k = i + 1; k <= j; ++k) v -= last.qr_mat[(j0 + i) + (j0 + k) * nm] * col[k];
             col[i] = v / last.qr_mat[(j0 + i) + (j0 + i) * nm];
           }
-          for (std::size_t i = 0; i <= j; ++i) T[i + 32 * j] = col[i];
+          // a zero or subnormal R(j,j) -- a column beyond the numerical rank of a singular Schur block --
+          // gives inf / NaN here; the reference's dtrsv on R(0:rk,0:rk) never touches such a column and
+          // the device kernel masks it, so it is stored as 0 (inf * 0 must not poison the tile)
+          for (std::size_t i = 0; i <= j; ++i) T[i + 32 * j] = std::isfinite(col[i]) ? col[i] : 0.0;
         }
       }
       h->dense.tinv.upload(tinv, tally);

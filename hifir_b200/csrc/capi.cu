@@ -13,8 +13,22 @@ namespace {
 
 thread_local std::string g_msg;
 
+// Every entry point selects the handle's device; the caller's current device is restored on the way
+// out (a single-process multi-GPU host -- PETSc, torch -- must not find itself on another device).
+struct DeviceGuard {
+  int  prev = -1;
+  bool ok;
+  DeviceGuard() : ok(cudaGetDevice(&prev) == cudaSuccess) {
+    if (!ok) cudaGetLastError();  // no device at all: the host-only entry points still work
+  }
+  ~DeviceGuard() {
+    if (ok) cudaSetDevice(prev);
+  }
+};
+
 template <class F>
 LhfStatus guarded(F &&f) {
+  DeviceGuard guard;
   try {
     f();
     return LHF_SUCCESS;
@@ -151,17 +165,26 @@ void solve_host(Handle *h, const IO *b, IO *x) {
   check_sweep_error(h);
 }
 
+// The handle that serves `op` (libhifir.cpp:447-472): the transposed twin for S^H / M^H, with the
+// filter hif::HIF::solve applies in that orientation -- nsp for the plain solve, nsp_tran for the
+// transposed one (builder.hpp:419-422) -- shared by the host- and the device-pointer entry points.
+Handle *handle_for_op(Handle *h0, LhfOperationType op) {
+  if (op != LHF_S && op != LHF_SH && op != LHF_M && op != LHF_MH) throw std::logic_error("unknown operation");
+  if (op == LHF_S || op == LHF_M) return h0;
+  Handle *t    = ensure_twin(h0);
+  t->stream    = h0->stream;
+  t->nsp_on    = h0->nspt_on;
+  t->nsp_start = h0->nspt_start;
+  t->nsp_end   = h0->nspt_end;
+  return t;
+}
+
 // lhf?Apply (libhifir.cpp:447-472; lhfsdApply :1192-1218): IO = the caller's vector type
 template <class IO>
 void apply_host(Handle *h0, LhfOperationType op, const IO *b, int nirs, const double *betas, int rank, IO *x,
                 int *ir_status) {
   HIF_CUDA(cudaSetDevice(h0->device));
-  const bool trans = op == LHF_SH || op == LHF_MH;
-  Handle *   h     = h0;
-  if (trans) {  // the transposed twin serves S^H and M^H with the kernels of S and M
-    h         = ensure_twin(h0);
-    h->stream = h0->stream;
-  }
+  Handle *h = handle_for_op(h0, op);  // the transposed twin serves S^H and M^H with the kernels of S and M
   if (op == LHF_M || op == LHF_MH) {  // libhifir.cpp:458-459: mmultiply(b, x, trans), numerical rank
     ensure_io(h0, 1);
     h2d(h0, h0->io_b.p, b, h0->n0());
@@ -170,8 +193,6 @@ void apply_host(Handle *h0, LhfOperationType op, const IO *b, int nirs, const do
     check_sweep_error(h);
     return;
   }
-  if (trans && h0->nsp_on)
-    throw std::logic_error("the null-space filter of the transposed solve (nsp_tran) is not supported");
   // rank defaulting rule, libhifir.cpp:451-455
   const std::size_t rnk = rank == LHF_DEFAULT_RANK ? (nirs > 1 ? static_cast<std::size_t>(-1) : 0)
                                                    : static_cast<std::size_t>(static_cast<long long>(rank));
@@ -281,9 +302,22 @@ LhfStatus lhfdGpuSetNspConst(LhfdGpuHdl hdl, size_t start, size_t end) {
   });
 }
 
+LhfStatus lhfdGpuSetNspTranConst(LhfdGpuHdl hdl, size_t start, size_t end) {
+  REQUIRE_HANDLE(hdl);
+  return guarded([&] {
+    Handle *          h = H(hdl);
+    const std::size_t n = h->n0();
+    const std::size_t e = (end == static_cast<std::size_t>(-1) || end < start) ? n : end;
+    if (e < start || e > n) throw std::invalid_argument("null-space filter: wrong range (start,end,n)");
+    h->nspt_on    = true;
+    h->nspt_start = start;
+    h->nspt_end   = end;
+  });
+}
+
 LhfStatus lhfdGpuClearNsp(LhfdGpuHdl hdl) {
   REQUIRE_HANDLE(hdl);
-  H(hdl)->nsp_on = false;
+  H(hdl)->nsp_on = H(hdl)->nspt_on = false;
   return LHF_SUCCESS;
 }
 
@@ -471,12 +505,7 @@ LhfStatus lhfdGpuApplyDev(LhfdGpuHdl hdl, LhfOperationType op, const double *d_b
   return guarded([&] {
     Handle *h0 = H(hdl);
     HIF_CUDA(cudaSetDevice(h0->device));
-    const bool trans = op == LHF_SH || op == LHF_MH;
-    Handle *   h     = h0;
-    if (trans) {
-      h         = ensure_twin(h0);
-      h->stream = h0->stream;
-    }
+    Handle *h = handle_for_op(h0, op);
     const std::size_t rnk = rank == LHF_DEFAULT_RANK ? (((op != LHF_S && op != LHF_SH) || nirs > 1) ? static_cast<std::size_t>(-1) : 0)
                                                      : static_cast<std::size_t>(static_cast<long long>(rank));
     if (op == LHF_M || op == LHF_MH)
@@ -721,6 +750,16 @@ LhfStatus lhfdGpuDebugTraceSweep(LhfdGpuHdl hdl, const double *d_b, double *d_x,
     const size_t ns = std::min<size_t>(plan.ws_nsegs, max_segs);
     HIF_CUDA(cudaMemcpy(out, h->trace_buf.p, ns * 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
     *nsegs = ns;
+  });
+}
+
+LhfStatus lhfdGpuDebugNorm2Dev(LhfdGpuHdl hdl, const double *d_v, size_t n, double *out) {
+  REQUIRE_HANDLE(hdl);
+  REQUIRE_PTR(d_v, "v");
+  REQUIRE_PTR(out, "out");
+  return guarded([&] {
+    HIF_CUDA(cudaSetDevice(H(hdl)->device));
+    *out = norm2_dev(H(hdl), d_v, n);
   });
 }
 

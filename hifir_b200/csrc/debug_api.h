@@ -44,6 +44,10 @@ LhfStatus lhfdGpuDebugTraceSweep(LhfdGpuHdl hdl, const double *d_b, double *d_x,
 LhfStatus lhfdGpuDebugSegmentGraph(const LhfdGpuCcs *T, int upper, size_t max_segs, size_t max_deps, unsigned *dep_ptr,
                                    unsigned *dep_idx, size_t *nsegs);
 
+/* The device 2-norm of the refinement / Krylov loops (max-scaled, two passes: utils/math.hpp:112-137)
+ * of a device vector -- for a direct test incl. inputs whose squares overflow. */
+LhfStatus lhfdGpuDebugNorm2Dev(LhfdGpuHdl hdl, const double *d_v, size_t n, double *out);
+
 /* Bit-exact checks of the attach-time integer handling: copies the device-resident index arrays of
  * level `level` back to the host.  which: 0 p, 1 q_inv, 2 E row pointers, 3 E columns (original
  * numbering), 4 F row pointers, 5 F columns, 6 jpvt (level ignored).  out receives min(count, max)

@@ -100,6 +100,7 @@ struct MergeStats {
   std::size_t rows = 0, ext_rows = 0, nnz = 0, ext_nnz = 0, depth = 0, ext_depth = 0, super_levels = 0;
 };
 HostCsr to_sweep_form(const HostCsr &T, bool upper);
+void    validate_sweep_form(const HostCsr &S);  // throws std::invalid_argument
 HostCsr merge_levels(const HostCsr &S, const MergeParams &prm, MergeStats *st, bool fan_out = false);
 
 // ---- arena.cu : factor arena serialization
@@ -246,6 +247,10 @@ struct Handle {
   bool                  has_A = false;
   bool                  nsp_on = false;
   std::size_t           nsp_start = 0, nsp_end = 0;
+  // filter of the TRANSPOSED solve (hif::HIF::nsp_tran, builder.hpp:421-422): lives on the primary
+  // handle, copied to the twin before every transposed solve
+  bool                  nspt_on = false;
+  std::size_t           nspt_start = 0, nspt_end = 0;
   cudaStream_t          own_stream = nullptr, stream = nullptr;
   unsigned              epoch = 0;        // apply counter; parity tags the sync-free buffers
   unsigned              epoch_m = 0;      // same for the multi-rhs work vectors

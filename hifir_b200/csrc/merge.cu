@@ -25,6 +25,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <stdexcept>
+#include <string>
 
 #include "hifgpu.h"
 
@@ -78,6 +79,27 @@ HostCsr to_sweep_form(const HostCsr &T, bool upper) {
   }
   S.ptr[m] = w;
   return S;
+}
+
+// A factor in sweep form as the packers need it: row pointers start at 0 and never decrease, every
+// entry references an EARLIER row, every row code addresses one of the 2 * orig_rows solution slots
+// and no slot is written twice.  (The device sweeps index the solution buffers with these numbers.)
+void validate_sweep_form(const HostCsr &S) {
+  const std::size_t n = S.nrows;
+  if (S.ptr.size() != n + 1 || S.gid.size() != n || S.col.size() != S.val.size())
+    throw std::invalid_argument("sweep form: array sizes do not match");
+  if (n == 0) return;
+  if (S.ptr[0] != 0u || S.ptr[n] != S.col.size()) throw std::invalid_argument("sweep form: bad row pointers");
+  std::vector<char> seen(2 * S.orig_rows, 0);
+  for (std::size_t i = 0; i < n; ++i) {
+    if (S.ptr[i + 1] < S.ptr[i]) throw std::invalid_argument("sweep form: row pointers decrease");
+    for (unsigned k = S.ptr[i]; k < S.ptr[i + 1]; ++k)
+      if (S.col[k] < 0 || static_cast<std::size_t>(S.col[k]) >= i)
+        throw std::invalid_argument("sweep form: an entry does not reference an earlier row");
+    const std::size_t slot = S.gid[i] & kCodeSlotMask;
+    if (slot >= seen.size() || seen[slot]) throw std::invalid_argument("sweep form: bad or repeated solution slot");
+    seen[slot] = 1;
+  }
 }
 
 static unsigned depth_of(const HostCsr &S, std::vector<unsigned> &lev) {

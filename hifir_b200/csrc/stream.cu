@@ -325,6 +325,7 @@ void pack_stream(const HostCsr &S, StreamHost &H, unsigned U, unsigned R = 32u) 
   const unsigned m = static_cast<unsigned>(S.nrows);
   if (!m) return;
   if (S.gid.size() != m) throw std::logic_error("build_stream_plan: factor is not in sweep form");
+  validate_sweep_form(S);
   std::vector<uint4> &   sdesc = H.sdesc;
   std::vector<unsigned> &codes = H.codes, &cols = H.cols;
   std::vector<double> &  vals = H.vals;

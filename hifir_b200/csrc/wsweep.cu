@@ -70,6 +70,7 @@ void pack_warp_streams(const HostCsr &S, WsHost &H, unsigned nwarps, unsigned wi
   H.nslots = n;
   if (!n) return;
   if (S.gid.size() != n) throw std::logic_error("pack_warp_streams: factor is not in sweep form");
+  validate_sweep_form(S);  // the device indexes the solution buffers with these numbers
   std::vector<unsigned> lev(n, 0u);
   unsigned              depth = 0;
   for (unsigned i = 0; i < n; ++i) {

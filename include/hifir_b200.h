@@ -115,6 +115,10 @@ LhfStatus lhfdGpuSetMatrix(LhfdGpuHdl hdl, int is_rowmajor, size_t n, const LhfI
 /* hif::HIF::nsp = create_nsp_filter(start, end) in constant mode
  * (reference src/hif/NspFilter.hpp:139-175, 190).  end == (size_t)-1 -> n. */
 LhfStatus lhfdGpuSetNspConst(LhfdGpuHdl hdl, size_t start, size_t end);
+/* The same for the TRANSPOSED solve (LHF_SH): hif::HIF::nsp_tran, applied by hif::HIF::solve(b, x, true)
+ * instead of nsp (builder.hpp:421-422).  Without it a transposed solve is not filtered, as in the
+ * reference. */
+LhfStatus lhfdGpuSetNspTranConst(LhfdGpuHdl hdl, size_t start, size_t end);
 LhfStatus lhfdGpuClearNsp(LhfdGpuHdl hdl);
 
 /* Run all work of this handle on `cuda_stream` (a cudaStream_t passed as void*; NULL is

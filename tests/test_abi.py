@@ -32,6 +32,34 @@ def test_header_symbols_are_exported(lib):
     assert set(names) == set(hb.EXPORTED_SYMBOLS)
 
 
+def test_debug_header_symbols_are_exported(lib):
+    """the developer / test hooks live in a private header (hifir_b200/csrc/debug_api.h), not in the
+    drop-in boundary; they must be exported too and must not leak into the public header"""
+    src = open(os.path.join(ROOT, "hifir_b200", "csrc", "debug_api.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    names = sorted(set(re.findall(r"\b(lhf\w*Gpu\w*)\s*\(", src)))
+    assert set(names) == set(hb.DEBUG_SYMBOLS)
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in debug_api.h but not exported"
+    assert not [n for n in _declared_symbols() if "Debug" in n]
+
+
+def test_plan_validation_refuses_inconsistent_sweep_forms(lib, tmp_path):
+    """a stored plan is checked before it can become an out-of-bounds device access --
+    every sweep row must reference earlier rows only (the arena loader runs the same check on the
+    plans of a file; here a CCS block that is not strictly triangular is refused by the packer's
+    front door)."""
+    import scipy.sparse as sp
+    A = sp.csc_matrix(np.array([[0.0, 0.5, 0.0], [0.3, 0.0, 0.0], [0.0, 0.2, 0.0]]))  # entry above the diagonal
+    blk = (3, 3, A.indptr.astype(np.int64), A.indices.astype(np.int32), A.data)
+    with pytest.raises(hb.LhfError) as e:
+        hb.debug_sweep_host(blk, False, np.ones(3))
+    assert e.value.status == hb.LHF_BAD_PREC
+    bad = (3, 3, np.array([1, 1, 2, 2], dtype=np.int64), np.array([1, 2], dtype=np.int32), np.array([0.3, 0.2]))
+    with pytest.raises(hb.LhfError):
+        hb.debug_sweep_host(bad, False, np.ones(3))  # col_start[0] != 0
+
+
 def test_version_and_enums(lib):
     assert b"sm_100a" in lib.lhfGpuVersion()
     assert (hb.LHF_SUCCESS, hb.LHF_NULL_OBJ, hb.LHF_MISMATCHED_SIZES, hb.LHF_BAD_PREC, hb.LHF_HIFIR_ERROR) == (
