@@ -117,11 +117,13 @@ __global__ void __launch_bounds__(kTrsvThreads, 1)
       if (tid < w) {
 #pragma unroll 8
         for (unsigned j = 0; j < 32u; j += 4) {
-          // masked columns (beyond the rank, below the diagonal) stay OUT of the arithmetic
-          if (j + 0u < w && j + 0u >= tid) a0 = fma(Ti[(j + 0u) * 32u], xs[j0 + j + 0u], a0);
-          if (j + 1u < w && j + 1u >= tid) a1 = fma(Ti[(j + 1u) * 32u], xs[j0 + j + 1u], a1);
-          if (j + 2u < w && j + 2u >= tid) a2 = fma(Ti[(j + 2u) * 32u], xs[j0 + j + 2u], a2);
-          if (j + 3u < w && j + 3u >= tid) a3 = fma(Ti[(j + 3u) * 32u], xs[j0 + j + 3u], a3);
+          // masked columns (beyond the rank, below the diagonal) enter as 0 * finite: the tile inverses
+          // hold no inf / NaN (attach.cu stores 0 where a zero pivot beyond the numerical rank gave one),
+          // and the loads stay unconditional so that all of them are in flight together
+          a0 = fma(Ti[(j + 0u) * 32u], (j + 0u < w && j + 0u >= tid) ? xs[j0 + j + 0u] : 0.0, a0);
+          a1 = fma(Ti[(j + 1u) * 32u], (j + 1u < w && j + 1u >= tid) ? xs[j0 + j + 1u] : 0.0, a1);
+          a2 = fma(Ti[(j + 2u) * 32u], (j + 2u < w && j + 2u >= tid) ? xs[j0 + j + 2u] : 0.0, a2);
+          a3 = fma(Ti[(j + 3u) * 32u], (j + 3u < w && j + 3u >= tid) ? xs[j0 + j + 3u] : 0.0, a3);
         }
       }
       const double xv = (a0 + a1) + (a2 + a3);
@@ -137,9 +139,9 @@ __global__ void __launch_bounds__(kTrsvThreads, 1)
       for (int jj = 0; jj < 32; ++jj) r[jj] = static_cast<unsigned>(jj) < w ? Ri[static_cast<std::size_t>(jj) * nm] : 0.0;
       double b0 = 0.0, b1 = 0.0;
 #pragma unroll
-      for (int jj = 0; jj < 32; jj += 2) {
-        if (static_cast<unsigned>(jj) < w) b0 = fma(r[jj], xs[j0 + jj], b0);
-        if (static_cast<unsigned>(jj + 1) < w) b1 = fma(r[jj + 1], xs[j0 + jj + 1], b1);
+      for (int jj = 0; jj < 32; jj += 2) {  // r[jj] = 0 for a masked column (loaded that way above)
+        b0 = fma(r[jj], static_cast<unsigned>(jj) < w ? xs[j0 + jj] : 0.0, b0);
+        b1 = fma(r[jj + 1], static_cast<unsigned>(jj + 1) < w ? xs[j0 + jj + 1] : 0.0, b1);
       }
       xs[i] -= b0 + b1;
     }

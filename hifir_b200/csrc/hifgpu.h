@@ -282,6 +282,8 @@ struct Handle {
   // multi-rhs column staging
   DevBuf<double> mr_b, mr_x, mr_c;
   bool           mrhs_ready = false;
+  bool           wide_plans = false;  // warp-stream plans of the multi-rhs kernel built (mrhs.cu)
+  std::size_t    wide_nc = 0;         // columns the multi-rhs work vectors hold
   // statistics
   std::size_t bytes_factors = 0, bytes_vec = 0, bytes_dense = 0, device_bytes = 0, nnz_total = 0;
   std::size_t kernels_per_apply = 0, launch_count = 0;
@@ -325,6 +327,7 @@ void launch_stream_sweep(Handle *h, const SweepPlan &plan, const double *rhs_pla
 // ---- apply.cu : the multilevel M^{-1} apply on device vectors
 void apply_dev(Handle *h, const double *d_b, double *d_x, std::size_t rank);
 void clear_apply_graphs(Handle *h);
+void reset_tagged_state(Handle *h);
 void check_sweep_error(Handle *h);  // synchronizes; throws if a sweep tripped its spin limit
 
 void dense_solve_dev(Handle *h, const double *d_in, double *d_out, std::size_t rank);     // QRCP::solve
@@ -352,17 +355,21 @@ struct WsHost {  // packed plan on the host
   std::size_t                        entries = 0, padded = 0, copy_rows = 0, max_segs = 0, nsegs = 0;
 };
 void pack_warp_streams(const HostCsr &S, WsHost &H, unsigned nwarps, unsigned window, bool f32,
-                       const unsigned *rhs_index);
+                       const unsigned *rhs_index, unsigned umin_force = 0);
 void ws_finalize_ring(WsHost &H, unsigned stages);
 void ws_host_emulate_packed(const WsHost &H, bool upper, bool f32, const double *rhs, const double *diag, double *x);
 void build_ws_plan(const HostCsr &S, bool upper, SweepPlan &plan, std::size_t *tally, unsigned nsm,
-                   const unsigned *rhs_index);
+                   const unsigned *rhs_index, unsigned warps = 0, unsigned stages = 0);  // 0: HIFIR_B200_WS_WARPS / _STAGES
+void launch_ws_sweep_mrhs(Handle *h, const SweepPlan &plan, const double *rhs_plain, const unsigned long long *rhs_tagged,
+                          const double *diag, unsigned long long *x, unsigned parity, int *sync, unsigned nc);
 void ws_host_emulate(const HostCsr &S, bool upper, const double *rhs, const double *diag, double *x_by_row,
                      std::size_t stats[4], bool f32);
 void launch_ws_sweep(Handle *h, const SweepPlan &plan, const double *rhs_plain, const unsigned long long *rhs_tagged,
                      const double *diag, unsigned long long *x, unsigned parity, int *sync,
                      unsigned long long *trace = nullptr);
 void ws_debug_graph(const HostCsr &S, unsigned nsm, std::vector<unsigned> &dep_ptr, std::vector<unsigned> &dep_idx);
+void build_ws_plan_for(const HostCsr &Tnat, bool upper, SweepPlan &plan, std::size_t *tally, unsigned nsm,
+                       const unsigned *rhs_index, unsigned warps, unsigned stages);  // merge + pack (sweep.cu)
 int  sweep_kind();  // HIFIR_B200_SWEEP = ws (default) | stream | slab  ->  2 | 1 | 0
 
 // ---- planlab.cu (developer tool, host only)

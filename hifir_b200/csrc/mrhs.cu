@@ -10,6 +10,7 @@
 // row (64 B: one coalesced, vectorised transaction per dependency) and every factor is
 // streamed ONCE for the 8 columns.  The schedule is the single-rhs one (apply.cu).
 #include <algorithm>
+#include <cstdlib>
 
 #include "hifgpu.h"
 
@@ -40,28 +41,29 @@ __global__ void chunk_insert_kernel(const unsigned n, const unsigned nrhs, const
 }
 
 // bhat[i][c] = s[p[i]] * b[p[i]][c]     (prec_solve.hpp:359, 368, 399)
-__global__ void gather_scale_m_kernel(const unsigned n, const int *__restrict__ p, const double *__restrict__ s,
-                                      const double *__restrict__ b, double *__restrict__ bhat) {
+__global__ void gather_scale_m_kernel(const unsigned n, const unsigned nc, const int *__restrict__ p,
+                                      const double *__restrict__ s, const double *__restrict__ b,
+                                      double *__restrict__ bhat) {
   const std::size_t g = static_cast<std::size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (g >= static_cast<std::size_t>(n) * NR) return;
-  const std::size_t i = g / NR, c = g % NR;
+  if (g >= static_cast<std::size_t>(n) * nc) return;
+  const std::size_t i = g / nc, c = g % nc;
   const int         pi = p[i];
-  bhat[g]              = s[pi] * b[static_cast<std::size_t>(pi) * NR + c];
+  bhat[g]              = s[pi] * b[static_cast<std::size_t>(pi) * nc + c];
 }
 
 // out[i][c] = base[i][c] - sum_j A(i,j) x[j][c]; NR consecutive threads = the NR columns of one row
 template <bool TAGGED>
-__global__ void spmv_resid_m_kernel(const unsigned nrows, const unsigned *__restrict__ ptr,
+__global__ void spmv_resid_m_kernel(const unsigned nrows, const unsigned nc, const unsigned *__restrict__ ptr,
                                     const int *__restrict__ col, const double *__restrict__ val,
                                     const void *__restrict__ xin, const double *__restrict__ base,
                                     double *__restrict__ out) {
   const std::size_t g = static_cast<std::size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (g >= static_cast<std::size_t>(nrows) * NR) return;
-  const std::size_t row = g / NR, c = g % NR;
+  if (g >= static_cast<std::size_t>(nrows) * nc) return;
+  const std::size_t row = g / nc, c = g % nc;
   double            acc = 0.0;
   const unsigned    e   = ptr[row + 1];
   for (unsigned k = ptr[row]; k < e; ++k) {
-    const std::size_t j = static_cast<std::size_t>(col[k]) * NR + c;
+    const std::size_t j = static_cast<std::size_t>(col[k]) * nc + c;
     const double      xj =
         TAGGED ? tag_value(static_cast<const unsigned long long *>(xin)[j]) : static_cast<const double *>(xin)[j];
     acc = fma(val[k], xj, acc);
@@ -70,37 +72,105 @@ __global__ void spmv_resid_m_kernel(const unsigned nrows, const unsigned *__rest
 }
 
 // y[i][c] = t[i] * [xU; ychild][q_inv[i]][c]   (prec_solve.hpp:392, 411)
-__global__ void scatter_scale_m_kernel(const unsigned n, const unsigned m, const int *__restrict__ q_inv,
-                                       const double *__restrict__ t, const unsigned long long *__restrict__ xU,
-                                       const double *__restrict__ ychild, double *__restrict__ y) {
+__global__ void scatter_scale_m_kernel(const unsigned n, const unsigned nc, const unsigned m,
+                                       const int *__restrict__ q_inv, const double *__restrict__ t,
+                                       const unsigned long long *__restrict__ xU, const double *__restrict__ ychild,
+                                       double *__restrict__ y) {
   const std::size_t g = static_cast<std::size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (g >= static_cast<std::size_t>(n) * NR) return;
-  const std::size_t i = g / NR, c = g % NR;
+  if (g >= static_cast<std::size_t>(n) * nc) return;
+  const std::size_t i = g / nc, c = g % nc;
   const unsigned    j = static_cast<unsigned>(q_inv[i]);
-  const double      w = j < m ? tag_value(xU[static_cast<std::size_t>(j) * NR + c])
-                              : ychild[static_cast<std::size_t>(j - m) * NR + c];
+  const double      w = j < m ? tag_value(xU[static_cast<std::size_t>(j) * nc + c])
+                              : ychild[static_cast<std::size_t>(j - m) * nc + c];
   y[g]                = t[i] * w;
 }
 
+// the same with q_inv mapped to the solution slots of the U sweep (attach.cu: q_slot)
+__global__ void scatter_scale_ms_kernel(const unsigned n, const unsigned nc, const int *__restrict__ q_slot,
+                                        const double *__restrict__ t, const unsigned long long *__restrict__ xU,
+                                        const double *__restrict__ ychild, double *__restrict__ y) {
+  const std::size_t g = static_cast<std::size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (g >= static_cast<std::size_t>(n) * nc) return;
+  const std::size_t i = g / nc, c = g % nc;
+  const int         j = q_slot[i];
+  const double      w = j >= 0 ? tag_value(xU[static_cast<std::size_t>(j) * nc + c])
+                               : ychild[static_cast<std::size_t>(-j - 1) * nc + c];
+  y[g]                = t[i] * w;
+}
+
+// [n][nrhs] <-> [n][nc] (nc = nrhs rounded up to a multiple of 8, zero padded)
+__global__ void pad_cols_kernel(const unsigned n, const unsigned nrhs, const unsigned nc, const double *__restrict__ B,
+                                double *__restrict__ out) {
+  const std::size_t g = static_cast<std::size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (g >= static_cast<std::size_t>(n) * nc) return;
+  const std::size_t i = g / nc, c = g % nc;
+  out[g]              = c < nrhs ? B[i * nrhs + c] : 0.0;
+}
+__global__ void unpad_cols_kernel(const unsigned n, const unsigned nrhs, const unsigned nc, const double *__restrict__ in,
+                                  double *__restrict__ X) {
+  const std::size_t g = static_cast<std::size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (g >= static_cast<std::size_t>(n) * nrhs) return;
+  const std::size_t i = g / nrhs, c = g % nrhs;
+  X[g]                = in[i * nc + c];
+}
+
 // dense level: cq[k][c] = Q(:,k)^T x[:, c] : one warp per column k of Q, NR accumulators
-__global__ void dense_qt_m_kernel(const unsigned nm, const unsigned rk, const double *__restrict__ Q,
+// (row stride nc, blockIdx.y = group of NR columns)
+__global__ void dense_qt_m_kernel(const unsigned nm, const unsigned rk, const unsigned nc, const double *__restrict__ Q,
                                   const double *__restrict__ x, double *__restrict__ cq) {
   const unsigned warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31u;
   if (warp >= rk) return;
-  const double *q = Q + static_cast<std::size_t>(warp) * nm;
-  double        acc[NR];
+  const unsigned c0 = blockIdx.y * NR;
+  const double * q  = Q + static_cast<std::size_t>(warp) * nm;
+  double         acc[NR];
 #pragma unroll
   for (unsigned c = 0; c < NR; ++c) acc[c] = 0.0;
   for (unsigned i = lane; i < nm; i += 32) {
     const double qi = q[i];
 #pragma unroll
-    for (unsigned c = 0; c < NR; ++c) acc[c] = fma(qi, x[static_cast<std::size_t>(i) * NR + c], acc[c]);
+    for (unsigned c = 0; c < NR; ++c) acc[c] = fma(qi, x[static_cast<std::size_t>(i) * nc + c0 + c], acc[c]);
   }
 #pragma unroll
   for (unsigned c = 0; c < NR; ++c) {
     const double v = warp_sum(acc[c]);
-    if (lane == 0) cq[static_cast<std::size_t>(warp) * NR + c] = v;
+    if (lane == 0) cq[static_cast<std::size_t>(warp) * nc + c0 + c] = v;
   }
+}
+
+// ---- wide blocks on warp-stream plans: all nc columns in one pass over the factors (wsweep.cu)
+void ensure_wide(Handle *h, std::size_t nc) {
+  std::size_t *tally = &h->device_bytes;
+  if (!h->wide_plans) {
+    for (DevLevel &D : h->levels) {
+      // the multi-rhs kernel runs 16 warps x 4 stages: its own streams, the same solution slots
+      D.Lm.f32 = D.Um.f32 = h->f32;
+      build_ws_plan_for(D.hostL, false, D.Lm, tally, static_cast<unsigned>(h->num_sms), nullptr, 16u, 4u);
+      build_ws_plan_for(D.hostU, true, D.Um, tally, static_cast<unsigned>(h->num_sms),
+                        D.Lm.slot_of.empty() ? nullptr : D.Lm.slot_of.data(), 16u, 4u);
+      if (D.Lm.slot_of != D.L.slot_of || D.Um.slot_of != D.U.slot_of)
+        throw std::logic_error("multi-rhs plans disagree with the single-rhs solution slots");
+    }
+    h->wide_plans = true;
+  }
+  if (h->wide_nc >= nc) return;
+  HIF_CUDA(cudaStreamSynchronize(h->stream));
+  for (DevLevel &D : h->levels) {
+    D.m_bhat.alloc(D.n * nc, tally);
+    D.m_g.alloc(D.m * nc, tally);
+    D.m_r.alloc(D.nm * nc, tally);
+    D.m_ychild.alloc(D.nm * nc, tally);
+    D.m_xL_dn.alloc(2 * D.m * nc, tally);
+    D.m_xU_dn.alloc(2 * D.m * nc, tally);
+    D.m_xL_up.alloc(2 * D.m * nc, tally);
+    D.m_xU_up.alloc(2 * D.m * nc, tally);
+  }
+  const std::size_t n = h->n0();
+  h->mr_b.alloc(n * nc, tally);
+  h->mr_x.alloc(n * nc, tally);
+  h->mr_c.alloc(h->dense.nm * nc + 1, tally);
+  h->wide_nc    = nc;
+  h->epoch_m    = 0;  // fresh (zeroed) tagged buffers
+  h->mrhs_ready = false;
 }
 
 void ensure_mrhs(Handle *h) {
@@ -150,7 +220,7 @@ static void apply_chunk(Handle *h, const double *d_in, double *d_out, std::size_
   for (std::size_t l = 0; l < nl; ++l) {
     DevLevel &D = h->levels[l];
     if (D.n) {
-      gather_scale_m_kernel<<<cdiv(D.n * NR, T), T, 0, h->stream>>>(static_cast<unsigned>(D.n), D.p.p, D.s.p, b,
+      gather_scale_m_kernel<<<cdiv(D.n * NR, T), T, 0, h->stream>>>(static_cast<unsigned>(D.n), NR, D.p.p, D.s.p, b,
                                                                      D.m_bhat.p);
       HIF_KERNEL_CHECK();
       ++h->launch_count;
@@ -162,7 +232,7 @@ static void apply_chunk(Handle *h, const double *d_in, double *d_out, std::size_
                      h->tick(4 * l + 1), NR);
       }
       spmv_resid_m_kernel<true><<<cdiv(D.nm * NR, T), T, 0, h->stream>>>(
-          static_cast<unsigned>(D.nm), D.E.ptr.p, D.E.col.p, D.E.val.p, D.m_xU_dn.p, D.m_bhat.p + D.m * NR, D.m_r.p);
+          static_cast<unsigned>(D.nm), NR, D.E.ptr.p, D.E.col.p, D.E.val.p, D.m_xU_dn.p, D.m_bhat.p + D.m * NR, D.m_r.p);
       HIF_KERNEL_CHECK();
       ++h->launch_count;
       b = D.m_r.p;
@@ -174,7 +244,7 @@ static void apply_chunk(Handle *h, const double *d_in, double *d_out, std::size_
     const unsigned nm = static_cast<unsigned>(Q.nm);
     const unsigned rk = static_cast<unsigned>(rank == 0 ? Q.rank : (rank > Q.nm ? Q.nm : rank));
     if (rk) {
-      dense_qt_m_kernel<<<cdiv(static_cast<std::size_t>(rk) * 32, T), T, 0, h->stream>>>(nm, rk, Q.Q.p, last.m_r.p,
+      dense_qt_m_kernel<<<cdiv(static_cast<std::size_t>(rk) * 32, T), T, 0, h->stream>>>(nm, rk, NR, Q.Q.p, last.m_r.p,
                                                                                         h->mr_c.p);
       HIF_KERNEL_CHECK();
       ++h->launch_count;
@@ -187,7 +257,7 @@ static void apply_chunk(Handle *h, const double *d_in, double *d_out, std::size_
     const double *rhs = D.m_bhat.p;
     if (D.nm && D.F.nnz && D.m) {
       spmv_resid_m_kernel<false><<<cdiv(D.m * NR, T), T, 0, h->stream>>>(
-          static_cast<unsigned>(D.m), D.F.ptr.p, D.F.col.p, D.F.val.p, D.m_ychild.p, D.m_bhat.p, D.m_g.p);
+          static_cast<unsigned>(D.m), NR, D.F.ptr.p, D.F.col.p, D.F.val.p, D.m_ychild.p, D.m_bhat.p, D.m_g.p);
       HIF_KERNEL_CHECK();
       ++h->launch_count;
       rhs = D.m_g.p;
@@ -200,7 +270,75 @@ static void apply_chunk(Handle *h, const double *d_in, double *d_out, std::size_
     }
     if (D.n) {
       scatter_scale_m_kernel<<<cdiv(D.n * NR, T), T, 0, h->stream>>>(
-          static_cast<unsigned>(D.n), static_cast<unsigned>(D.m), D.q_inv.p, D.t.p, D.m_xU_up.p, D.m_ychild.p, y);
+          static_cast<unsigned>(D.n), NR, static_cast<unsigned>(D.m), D.q_inv.p, D.t.p, D.m_xU_up.p, D.m_ychild.p, y);
+      HIF_KERNEL_CHECK();
+      ++h->launch_count;
+    }
+  }
+}
+
+void launch_dense_trsv_cols(Handle *h, unsigned nm, unsigned rk, const double *c, double *out, unsigned ncols);
+
+// X = M^{-1} B for a row-interleaved block of nc columns (nc a multiple of 8), every factor streamed once
+static void apply_wide(Handle *h, unsigned nc, const double *d_in, double *d_out, std::size_t rank) {
+  const std::size_t nl = h->levels.size();
+  ++h->epoch_m;
+  const unsigned parity = h->epoch_m & 1u;
+  HIF_CUDA(cudaMemsetAsync(h->tickets.p, 0, h->tickets.n * sizeof(int), h->stream));
+  constexpr int T = 256;
+  const double *b = d_in;
+  for (std::size_t l = 0; l < nl; ++l) {
+    DevLevel &D = h->levels[l];
+    if (D.n) {
+      gather_scale_m_kernel<<<cdiv(D.n * nc, T), T, 0, h->stream>>>(static_cast<unsigned>(D.n), nc, D.p.p, D.s.p, b,
+                                                                     D.m_bhat.p);
+      HIF_KERNEL_CHECK();
+      ++h->launch_count;
+    }
+    if (D.nm) {
+      if (D.m) {
+        launch_ws_sweep_mrhs(h, D.Lm, D.m_bhat.p, nullptr, nullptr, D.m_xL_dn.p, parity, h->tick(8 * l), nc);
+        launch_ws_sweep_mrhs(h, D.Um, nullptr, D.m_xL_dn.p, D.d_ls.p, D.m_xU_dn.p, parity, h->tick(8 * l + 1), nc);
+      }
+      spmv_resid_m_kernel<true><<<cdiv(D.nm * nc, T), T, 0, h->stream>>>(
+          static_cast<unsigned>(D.nm), nc, D.E.ptr.p, D.E_xcol.p, D.E.val.p, D.m_xU_dn.p,
+          D.m_bhat.p + D.m * static_cast<std::size_t>(nc), D.m_r.p);
+      HIF_KERNEL_CHECK();
+      ++h->launch_count;
+      b = D.m_r.p;
+    }
+  }
+  DevLevel &last = h->levels[nl - 1];
+  if (last.nm) {
+    DevDense &     Q  = h->dense;
+    const unsigned nm = static_cast<unsigned>(Q.nm);
+    const unsigned rk = static_cast<unsigned>(rank == 0 ? Q.rank : (rank > Q.nm ? Q.nm : rank));
+    if (rk) {
+      dense_qt_m_kernel<<<dim3(cdiv(static_cast<std::size_t>(rk) * 32, T), nc / NR), T, 0, h->stream>>>(
+          nm, rk, nc, Q.Q.p, last.m_r.p, h->mr_c.p);
+      HIF_KERNEL_CHECK();
+      ++h->launch_count;
+    }
+    launch_dense_trsv_cols(h, nm, rk, h->mr_c.p, last.m_ychild.p, nc);
+  }
+  for (std::size_t l = nl; l-- > 0;) {
+    DevLevel &    D   = h->levels[l];
+    double *      y   = l == 0 ? d_out : h->levels[l - 1].m_ychild.p;
+    const double *rhs = D.m_bhat.p;
+    if (D.nm && D.F.nnz && D.m) {
+      spmv_resid_m_kernel<false><<<cdiv(D.m * nc, T), T, 0, h->stream>>>(
+          static_cast<unsigned>(D.m), nc, D.F.ptr.p, D.F.col.p, D.F.val.p, D.m_ychild.p, D.m_bhat.p, D.m_g.p);
+      HIF_KERNEL_CHECK();
+      ++h->launch_count;
+      rhs = D.m_g.p;
+    }
+    if (D.m) {
+      launch_ws_sweep_mrhs(h, D.Lm, rhs, nullptr, nullptr, D.m_xL_up.p, parity, h->tick(8 * l + 2), nc);
+      launch_ws_sweep_mrhs(h, D.Um, nullptr, D.m_xL_up.p, D.d_ls.p, D.m_xU_up.p, parity, h->tick(8 * l + 3), nc);
+    }
+    if (D.n) {
+      scatter_scale_ms_kernel<<<cdiv(D.n * nc, T), T, 0, h->stream>>>(static_cast<unsigned>(D.n), nc, D.q_slot.p, D.t.p,
+                                                                       D.m_xU_up.p, D.m_ychild.p, y);
       HIF_KERNEL_CHECK();
       ++h->launch_count;
     }
@@ -212,6 +350,41 @@ void apply_mrhs_dev(Handle *h, std::size_t nrhs, const double *d_B, double *d_X,
   if (nrhs == 1) {
     apply_dev(h, d_B, d_X, rank);
     return;
+  }
+  static const int wide_max = [] {  // most columns per pass of the wide path (0: chunked path of 8 on stream plans)
+    const char *e = std::getenv("HIFIR_B200_MRHS_WIDE");
+    return e ? std::atoi(e) : 0;
+  }();
+  if (wide_max >= 8 && !h->levels.empty() && (h->levels[0].L.ws || !h->levels[0].m)) {
+    // warp-stream plans: the whole block in one pass (columns padded to a multiple of 8); a block whose
+    // width is a multiple of 8 is read and written in place, in the caller's row-interleaved layout
+    bool all_ws = true;
+    for (const DevLevel &D : h->levels) all_ws = all_ws && (D.L.ws || !D.m);
+    if (all_ws) {
+      const std::size_t n  = h->n0();
+      const unsigned    nc = static_cast<unsigned>((nrhs + 7u) & ~static_cast<std::size_t>(7u));
+      if (static_cast<unsigned long long>(n) * nc > 0xffffffffull * 8ull) throw std::length_error("multi-rhs block too large");
+      ensure_wide(h, nc);
+      constexpr int T = 256;
+      try {
+        if (nc == nrhs) {
+          apply_wide(h, nc, d_B, d_X, rank);
+        } else {
+          pad_cols_kernel<<<cdiv(n * nc, T), T, 0, h->stream>>>(static_cast<unsigned>(n), static_cast<unsigned>(nrhs), nc,
+                                                               d_B, h->mr_b.p);
+          HIF_KERNEL_CHECK();
+          apply_wide(h, nc, h->mr_b.p, h->mr_x.p, rank);
+          unpad_cols_kernel<<<cdiv(n * nrhs, T), T, 0, h->stream>>>(static_cast<unsigned>(n), static_cast<unsigned>(nrhs),
+                                                                   nc, h->mr_x.p, d_X);
+          HIF_KERNEL_CHECK();
+          h->launch_count += 2;
+        }
+      } catch (...) {
+        reset_tagged_state(h);
+        throw;
+      }
+      return;
+    }
   }
   ensure_mrhs(h);
   const std::size_t n = h->n0();

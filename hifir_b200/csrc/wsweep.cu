@@ -61,7 +61,7 @@ int ws_env(const char *name, int dflt) {
 // row r in the right-hand side array of this sweep (identity when null) -- the U sweep reads the L
 // sweep's tagged result, which lives at the L plan's slots.
 void pack_warp_streams(const HostCsr &S, WsHost &H, unsigned nwarps, unsigned window, bool f32,
-                       const unsigned *rhs_index) {
+                       const unsigned *rhs_index, unsigned umin_force) {
   const unsigned n = static_cast<unsigned>(S.nrows), m = static_cast<unsigned>(S.orig_rows);
   H = WsHost();
   H.nwarps = nwarps;
@@ -85,7 +85,7 @@ void pack_warp_streams(const HostCsr &S, WsHost &H, unsigned nwarps, unsigned wi
   // clock, a single warp one every ~5), so its rows are spread over as many lanes -- and warps --
   // as there are: U_l = entries of the level / lanes of one warp group, clamped to [umin, 8].
   const unsigned groups = static_cast<unsigned>(std::max(1, ws_env("HIFIR_B200_WS_GROUPS", 2)));
-  const unsigned umin   = static_cast<unsigned>(std::min(8, std::max(1, ws_env("HIFIR_B200_WS_UMIN", 1))));
+  const unsigned umin   = umin_force ? umin_force : static_cast<unsigned>(std::min(8, std::max(1, ws_env("HIFIR_B200_WS_UMIN", 1))));
   const unsigned gwarps = std::max(1u, nwarps / groups);  // warps that serve one level set of a thin stretch
   std::vector<unsigned> ulev(depth, kWsU);
   {
@@ -485,6 +485,14 @@ __device__ __forceinline__ bool ws_mbar_try_wait(unsigned bar, unsigned phase) {
                : "memory");
   return ok != 0;
 }
+// first-try gather through L1 (ld.global.ca): lanes of different gather instructions and warps of the
+// SM that hit the same 128-byte line share one L2 request; a stale line only means "not ready" (the tag
+// travels with the value) and the re-poll goes to L2
+__device__ __forceinline__ unsigned long long ws_ld_l1(const unsigned long long *p) {
+  unsigned long long v;
+  asm volatile("ld.global.ca.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
 __device__ __forceinline__ int ws_ld_poll_i32(const int *p) {
   int v;
   asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -512,6 +520,7 @@ struct WsParams {
   int *                     error_flag;
   unsigned                  parity, window, adm_sleep;
   int                       publish_st;
+  int                       l1_first;    // first-try gathers through L1
   unsigned                  spin_limit;  // poll rounds after which a wait gives up (and every other wait with it)
   unsigned long long *      trace;  // kTrace: 4 words per segment (decoded, admitted, gathered | rounds, published | level)
 };
@@ -539,7 +548,7 @@ __device__ __forceinline__ unsigned long long ws_timer_ns() {
   return t;
 }
 
-template <bool UPPER, class VT, int kWarps, int kStages, bool kTrace>
+template <bool UPPER, class VT, int kWarps, int kStages, bool kTrace, bool kPipe>
 __global__ void __launch_bounds__(kWarps * 32, 1) wsweep_kernel(const WsParams P) {
   constexpr unsigned kStageBytes = (kWsHdrWords + 64u + kWsU * 32u * (sizeof(VT) == 4 ? 2u : 3u)) * 4u;
   extern __shared__ __align__(128) unsigned char smem[];
@@ -576,6 +585,9 @@ __global__ void __launch_bounds__(kWarps * 32, 1) wsweep_kernel(const WsParams P
   // load/store queue behind thousands of cycles of scattered gathers -- longer than a bulk copy from
   // L2 takes to land.  Measured: stale stages -> wrong indices -> illegal addresses / rows that
   // never become ready.)
+  unsigned           cc[kWsU];          // slot indices / gathered words of the current segment
+  unsigned long long g[kWsU];
+  bool               have_cur = false;  // kPipe: they were requested during the previous segment
   auto refill = [&](unsigned stage, unsigned size16) {
     __syncwarp();
     if (lane == 0 && size16) {
@@ -640,6 +652,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) wsweep_kernel(const WsParams P
       for (unsigned u = 0; u < kWsU; ++u)
         if (slot[u] != kWsNone) st_publish(P.x + slot[u], tag_set(v[u], parity));  // consumes code and slot
       refill(stage, hd.y);
+      have_cur = false;
       if (lane == 0 && hd.w > my_front + 3u) {
         my_front = hd.w;
         atomicMax(P.sync, static_cast<int>(hd.w));
@@ -647,38 +660,72 @@ __global__ void __launch_bounds__(kWarps * 32, 1) wsweep_kernel(const WsParams P
       if (kTrace && lane == 0) tr[0] = t_dec, tr[1] = tr[2] = 0, tr[3] = ((ws_timer_ns() - t_dec) << 16) | hd.w | 0x8000u;
       continue;
     }
-    // ---- a slice segment: slot indices first, the gathers are the long pole
-    unsigned cc[kWsU];
+    // ---- a slice segment: slot indices first, the gathers are the long pole.  With kPipe the
+    // first-try gathers of this segment were issued while the PREVIOUS segment was being finished.
+    unsigned long long t_adm = 0, t_gat = 0;
+    if (!have_cur) {
 #pragma unroll
-    for (unsigned u = 0; u < kWsU; ++u) {
-      cc[u] = kWsNone;
-      if (u < width) cc[u] = sg[kWsHdrWords + 64u + u * 32u + lane];
-    }
-    // ---- admission (only a warp that jumps ahead carries a sentinel): the sentinel row of level
-    // (this - window) is published
-    if (hd.z != kWsNone) {
-      if (lane == 0) {
-        unsigned       spins = 0;
-        const unsigned need  = hd.w - P.window;
-        while (!tag_ready(ld_poll(P.x + hd.z), parity)) {
-          // far from the frontier: sleep in proportion to the distance; close to it: spin on the sentinel
-          const unsigned f = static_cast<unsigned>(ws_ld_poll_i32(P.sync));
-          if (need > f + 4u) __nanosleep(min((need - f) * P.adm_sleep, 20000u));
-          if (++spins > P.spin_limit || ((spins & 63u) == 63u && ws_aborted(P))) {
-            if (!ws_aborted(P)) ws_fail(P, gw, k, hd.w, 4, hd.z);
-            break;
+      for (unsigned u = 0; u < kWsU; ++u) {
+        cc[u] = kWsNone;
+        if (u < width) cc[u] = sg[kWsHdrWords + 64u + u * 32u + lane];
+      }
+      // ---- admission (only a warp that jumps ahead carries a sentinel): the sentinel row of level
+      // (this - window) is published
+      if (hd.z != kWsNone) {
+        if (lane == 0) {
+          unsigned       spins = 0;
+          const unsigned need  = hd.w - P.window;
+          while (!tag_ready(ld_poll(P.x + hd.z), parity)) {
+            // far from the frontier: sleep in proportion to the distance; close to it: spin on the sentinel
+            const unsigned f = static_cast<unsigned>(ws_ld_poll_i32(P.sync));
+            if (need > f + 4u) __nanosleep(min((need - f) * P.adm_sleep, 20000u));
+            if (++spins > P.spin_limit || ((spins & 63u) == 63u && ws_aborted(P))) {
+              if (!ws_aborted(P)) ws_fail(P, gw, k, hd.w, 4, hd.z);
+              break;
+            }
           }
         }
+        __syncwarp();
       }
-      __syncwarp();
-    }
-    unsigned long long t_adm = 0, t_gat = 0;
-    if (kTrace) t_adm = ws_timer_ns();
-    // ---- gather all entries optimistically (re-polled below if not ready), right-hand side beside them
-    unsigned long long g[kWsU];
+      if (kTrace) t_adm = ws_timer_ns();
+      // ---- gather all entries optimistically (re-polled below if not ready)
+      if (P.l1_first) {
 #pragma unroll
-    for (unsigned u = 0; u < kWsU; ++u)
-      if (cc[u] != kWsNone) g[u] = ld_poll(P.x + cc[u]);
+        for (unsigned u = 0; u < kWsU; ++u)
+          if (cc[u] != kWsNone) g[u] = ws_ld_l1(P.x + cc[u]);
+      } else {
+#pragma unroll
+        for (unsigned u = 0; u < kWsU; ++u)
+          if (cc[u] != kWsNone) g[u] = ld_poll(P.x + cc[u]);
+      }
+    } else if (kTrace) {
+      t_adm = ws_timer_ns();
+    }
+    // ---- software pipeline: the next segment's slot indices are in its stage already (the ring runs
+    // ahead); its first-try gathers go out NOW, so that they travel while this segment is finished.
+    // (A dependency-free pass of the unpipelined kernel took as long as the real sweep: a warp had
+    // gathers in flight only ~1/3 of the time.)  A segment with a sentinel is not pre-gathered.
+    bool               have_nxt = false;
+    unsigned           ccn[kWsU];
+    unsigned long long gn[kWsU];
+    if (kPipe && k + 1u < nseg) {
+      const unsigned st1 = (k + 1u) % kStages, ph1 = ((k + 1u) / kStages) & 1u;
+      if (__all_sync(0xffffffffu, ws_mbar_try_wait(bar0 + st1 * 8u, ph1))) {
+        const unsigned *sg1 = reinterpret_cast<const unsigned *>(ring + st1 * kStageBytes);
+        const unsigned  hx1 = sg1[0], hz1 = sg1[2], w1 = hx1 & 0xffu;
+        if (!((hx1 >> 16) & kSegCopy) && hz1 == kWsNone) {
+#pragma unroll
+          for (unsigned u = 0; u < kWsU; ++u) {
+            ccn[u] = kWsNone;
+            if (u < w1) ccn[u] = sg1[kWsHdrWords + 64u + u * 32u + lane];
+          }
+#pragma unroll
+          for (unsigned u = 0; u < kWsU; ++u)
+            if (ccn[u] != kWsNone) gn[u] = ld_poll(P.x + ccn[u]);
+          have_nxt = true;
+        }
+      }
+    }
     const unsigned code = sg[kWsHdrWords + lane];
     const unsigned slot = sg[kWsHdrWords + 32u + lane];
     const unsigned lpr  = 1u << z;
@@ -756,6 +803,11 @@ __global__ void __launch_bounds__(kWarps * 32, 1) wsweep_kernel(const WsParams P
       if (own) ws_publish(P.x + slot, tag_set(acc, parity), P.publish_st);
     }
     refill(stage, hd.y + (acc == 1.2345e300 ? 1u : 0u));  // (the refill depends on acc: see above)
+    have_cur = have_nxt;
+    if (have_nxt) {
+#pragma unroll
+      for (unsigned u = 0; u < kWsU; ++u) cc[u] = ccn[u], g[u] = gn[u];
+    }
     if (lane == 0 && hd.w > my_front + 3u) {  // frontier hint for the sleeping jumpers, every 4th level
       my_front = hd.w;
       atomicMax(P.sync, static_cast<int>(hd.w));
@@ -765,6 +817,237 @@ __global__ void __launch_bounds__(kWarps * 32, 1) wsweep_kernel(const WsParams P
       tr[1] = t_adm - t_dec;
       tr[2] = ((t_gat - t_dec) << 8) | min(nrounds, 255u);
       tr[3] = ((ws_timer_ns() - t_dec) << 16) | hd.w;
+    }
+  }
+}
+
+// ---- multi-rhs: the same warp streams, all right-hand sides in ONE pass over the factor -----------
+// Row-interleaved blocks X[slot * nc + c] (the Array<std::array<T,Nrhs>> layout of
+// hif::HIF::solve_mrhs, builder.hpp:433-445; per-column arithmetic = CCS::solve_as_strict_lower /
+// _upper_mrhs, CompressedStorage.hpp:2286-2301, 2376-2393).  nc is a multiple of 8; a segment sits in
+// its ring stage while the warp loops over the column GROUPS of 8: per group a dependency is one
+// 64-byte gather (two sectors for eight values), a lane keeps 8 accumulators, and the factor is read
+// from HBM once for all nc columns (round 1 re-streamed it for every 8).
+__device__ __forceinline__ void ws_ld_poll8(const unsigned long long *p, unsigned long long (&v)[8]) {
+#pragma unroll
+  for (int q = 0; q < 8; q += 2)
+    asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(v[q]), "=l"(v[q + 1]) : "l"(p + q) : "memory");
+}
+__device__ __forceinline__ bool ws_ready8(const unsigned long long (&v)[8], unsigned parity) {
+  unsigned bad = 0;
+#pragma unroll
+  for (int q = 0; q < 8; ++q) bad |= static_cast<unsigned>(v[q]) ^ parity;
+  return !(bad & 1u);
+}
+
+template <bool UPPER, class VT, int kWarps, int kStages>
+__global__ void __launch_bounds__(kWarps * 32, 1) wsweep_mrhs_kernel(const WsParams P, const unsigned nc) {
+  constexpr unsigned kStageBytes = (kWsHdrWords + 64u + kWsU * 32u * (sizeof(VT) == 4 ? 2u : 3u)) * 4u;
+  extern __shared__ __align__(128) unsigned char smem[];
+  const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+  const unsigned gw   = blockIdx.x + gridDim.x * warp;
+  const uint4    d0   = reinterpret_cast<const uint4 *>(P.wdesc)[2 * gw];
+  const uint4    d1   = reinterpret_cast<const uint4 *>(P.wdesc)[2 * gw + 1];
+  const unsigned nseg = d0.y;
+  if (!nseg) return;
+  unsigned char *ring = smem + static_cast<std::size_t>(kWarps) * kStages * 8u + static_cast<std::size_t>(warp) * kStages * kStageBytes;
+  const unsigned bar0 = ws_smem_addr(smem) + warp * kStages * 8u;
+  const unsigned char *src = reinterpret_cast<const unsigned char *>(P.stream) + static_cast<std::size_t>(d0.x) * 16u;
+  const unsigned long long policy = ws_policy_evict_first();
+  if (lane == 0) {
+    for (int s = 0; s < kStages; ++s) ws_mbar_init(bar0 + s * 8u, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    const unsigned sz[4] = {d1.x, d1.y, d1.z, d1.w};
+    for (int s = 0; s < kStages; ++s)
+      if (sz[s]) {
+        ws_mbar_expect_tx(bar0 + s * 8u, sz[s] * 16u);
+        ws_tma_g2s(ws_smem_addr(ring + s * kStageBytes), src, sz[s] * 16u, bar0 + s * 8u, policy);
+        src += static_cast<std::size_t>(sz[s]) * 16u;
+      }
+  }
+  __syncwarp();
+  const unsigned parity = P.parity, ngroups = nc >> 3;
+  unsigned       my_front = 0;
+  for (unsigned k = 0; k < nseg; ++k) {
+    const unsigned stage = k % kStages, phase = (k / kStages) & 1u;
+    {
+      unsigned spins = 0;
+      bool     ok    = true;
+      while (!ws_mbar_try_wait(bar0 + stage * 8u, phase)) {
+        if (++spins > P.spin_limit || ((spins & 1023u) == 1023u && ws_aborted(P))) {
+          ok = false;
+          break;
+        }
+      }
+      if (!ok) {
+        if (lane == 0 && !ws_aborted(P)) ws_fail(P, gw, k, 0u, 2, stage);
+        return;
+      }
+    }
+    const unsigned *sg    = reinterpret_cast<const unsigned *>(ring + stage * kStageBytes);
+    const uint4     hd    = *reinterpret_cast<const uint4 *>(sg);
+    const unsigned  width = hd.x & 0xffu, z = (hd.x >> 8) & 0xffu, flags = hd.x >> 16;
+    unsigned        keep  = 0;  // consumed before the refill: every shared-memory read of the stage has returned
+    if (flags & kSegCopy) {
+      for (unsigned u = 0; u < width; ++u) {
+        const unsigned code = sg[kWsHdrWords + u * 32u + lane], slot = sg[kWsHdrWords + (width + u) * 32u + lane];
+        keep ^= code + slot;
+        if (slot == kWsNone) continue;
+        const unsigned r = code & kCodeSlotMask;
+        for (unsigned cg = 0; cg < ngroups; ++cg) {
+          unsigned long long v[8];
+          if (code & kCodeZeroRhs) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) v[q] = tag_set(0.0, parity);
+          } else if (UPPER) {
+            const unsigned long long *rp = P.rhs_tagged + static_cast<std::size_t>(r) * nc + cg * 8u;
+            ws_ld_poll8(rp, v);
+            for (unsigned spins = 0; !ws_ready8(v, parity); ws_ld_poll8(rp, v))
+              if (++spins > P.spin_limit || ((spins & 255u) == 255u && ws_aborted(P))) {
+                if (!ws_aborted(P)) ws_fail(P, gw, k, hd.w, 3, r);
+                break;
+              }
+            const double dg = P.diag[r];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) v[q] = tag_set(tag_value(v[q]) / dg, parity);
+          } else {
+            const double *rp = P.rhs_plain + static_cast<std::size_t>(r) * nc + cg * 8u;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) v[q] = tag_set(rp[q], parity);
+          }
+          unsigned long long *xp = P.x + static_cast<std::size_t>(slot) * nc + cg * 8u;
+#pragma unroll
+          for (int q = 0; q < 8; q += 2)
+            asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"(xp + q), "l"(v[q]), "l"(v[q + 1]) : "memory");
+        }
+      }
+    } else {
+      unsigned cc[kWsU];
+#pragma unroll
+      for (unsigned u = 0; u < kWsU; ++u) {
+        cc[u] = kWsNone;
+        if (u < width) cc[u] = sg[kWsHdrWords + 64u + u * 32u + lane];
+      }
+      const unsigned code = sg[kWsHdrWords + lane], slot = sg[kWsHdrWords + 32u + lane];
+      const unsigned lpr = 1u << z;
+      const bool     own = slot != kWsNone && (lane & (lpr - 1u)) == 0u;
+      const bool     want_r = (flags & kSegFirst) && own && !(code & kCodeZeroRhs);
+      const unsigned r = code & kCodeSlotMask;
+      if (hd.z != kWsNone) {  // admission of a warp that jumps ahead (throttle only)
+        if (lane == 0) {
+          unsigned       spins = 0;
+          const unsigned need  = hd.w - P.window;
+          while (!tag_ready(ld_poll(P.x + static_cast<std::size_t>(hd.z) * nc), parity)) {
+            const unsigned f = static_cast<unsigned>(ws_ld_poll_i32(P.sync));
+            if (need > f + 4u) __nanosleep(min((need - f) * P.adm_sleep, 20000u));
+            if (++spins > P.spin_limit || ((spins & 63u) == 63u && ws_aborted(P))) {
+              if (!ws_aborted(P)) ws_fail(P, gw, k, hd.w, 4, hd.z);
+              break;
+            }
+          }
+        }
+        __syncwarp();
+      }
+      const VT *sv = reinterpret_cast<const VT *>(sg + kWsHdrWords + 64u + width * 32u);
+      for (unsigned cg = 0; cg < ngroups; ++cg) {
+        double acc[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) acc[q] = 0.0;
+        unsigned long long *xs = P.x + static_cast<std::size_t>(slot) * nc + cg * 8u;  // this row, this group
+        if (flags & kSegFirst) {
+          if (want_r) {
+            if (UPPER) {
+              const unsigned long long *rp = P.rhs_tagged + static_cast<std::size_t>(r) * nc + cg * 8u;
+              unsigned long long        t[8];
+              ws_ld_poll8(rp, t);
+              for (unsigned spins = 0; !ws_ready8(t, parity); ws_ld_poll8(rp, t))
+                if (++spins > P.spin_limit || ((spins & 255u) == 255u && ws_aborted(P))) {
+                  if (!ws_aborted(P)) ws_fail(P, gw, k, hd.w, 3, r);
+                  break;
+                }
+              const double dg = P.diag[r];
+#pragma unroll
+              for (int q = 0; q < 8; ++q) acc[q] = tag_value(t[q]) / dg;  // true division (prec_solve.hpp:219)
+            } else {
+              const double *rp = P.rhs_plain + static_cast<std::size_t>(r) * nc + cg * 8u;
+#pragma unroll
+              for (int q = 0; q < 8; ++q) acc[q] = rp[q];
+            }
+          }
+        } else if (own) {
+          // continuation of a slice of several segments (rows beyond 256 entries): the partial sums
+          // were parked in the row's own slot under the OTHER tag (nobody consumes them)
+#pragma unroll
+          for (int q = 0; q < 8; ++q) acc[q] = tag_value(ld_poll(xs + q));
+        }
+        // entries four at a time: 4 x 64-byte gathers in flight per lane
+#pragma unroll
+        for (unsigned u0 = 0; u0 < kWsU; u0 += 4) {
+          if (u0 >= width) break;
+          unsigned long long        gg[4][8];
+          const unsigned long long *pp[4];
+          bool                      has[4], pend[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            has[j] = (u0 + j < width) && cc[u0 + j] != kWsNone;
+            pp[j]  = P.x + static_cast<std::size_t>(has[j] ? cc[u0 + j] : 0u) * nc + cg * 8u;
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (has[j]) ws_ld_poll8(pp[j], gg[j]);
+          bool any = false;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            pend[j] = has[j] && !ws_ready8(gg[j], parity);
+            any |= pend[j];
+          }
+          for (unsigned rounds = 0; __any_sync(0xffffffffu, any);) {
+            any = false;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              if (pend[j]) {
+                ws_ld_poll8(pp[j], gg[j]);
+                pend[j] = !ws_ready8(gg[j], parity);
+                any |= pend[j];
+              }
+            if (++rounds > P.spin_limit || ((rounds & 255u) == 255u && ws_aborted(P))) {
+              if (any && !ws_aborted(P)) ws_fail(P, gw, k, hd.w, 1, cc[u0]);
+              break;
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (u0 + j < width) {
+              const double v = static_cast<double>(sv[(u0 + j) * 32u + lane]);
+#pragma unroll
+              for (int q = 0; q < 8; ++q) acc[q] = fma(-v, has[j] ? tag_value(gg[j][q]) : 0.0, acc[q]);
+            }
+        }
+        for (unsigned o = lpr >> 1; o > 0; o >>= 1) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], o);
+        }
+        if (own) {
+          const unsigned tag = (flags & kSegLast) ? parity : (parity ^ 1u);  // parked partial sums: the other tag
+#pragma unroll
+          for (int q = 0; q < 8; q += 2)
+            asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"(xs + q), "l"(tag_set(acc[q], tag)),
+                         "l"(tag_set(acc[q + 1], tag))
+                         : "memory");
+        }
+        keep ^= __double2hiint(acc[0]);
+      }
+      keep ^= code + slot;
+    }
+    __syncwarp();
+    if (lane == 0 && (hd.y + (keep == 0x12345678u ? 1u : 0u))) {  // refill after everything read from the stage was used
+      ws_mbar_expect_tx(bar0 + stage * 8u, hd.y * 16u);
+      ws_tma_g2s(ws_smem_addr(ring + stage * kStageBytes), src, hd.y * 16u, bar0 + stage * 8u, policy);
+      src += static_cast<std::size_t>(hd.y) * 16u;
+    }
+    if (lane == 0 && (flags & kSegLast) && hd.w > my_front + 3u) {
+      my_front = hd.w;
+      atomicMax(P.sync, static_cast<int>(hd.w));
     }
   }
 }
@@ -787,8 +1070,9 @@ WsConfig ws_config() {
 }  // namespace
 
 void build_ws_plan(const HostCsr &S, bool upper, SweepPlan &plan, std::size_t *tally, unsigned nsm,
-                   const unsigned *rhs_index) {
-  const WsConfig cfg = ws_config();
+                   const unsigned *rhs_index, unsigned warps, unsigned stages) {
+  WsConfig cfg = ws_config();
+  if (warps) cfg.warps = warps, cfg.stages = stages;
   plan.ws        = true;
   plan.stream    = false;
   plan.upper     = upper;
@@ -801,7 +1085,9 @@ void build_ws_plan(const HostCsr &S, bool upper, SweepPlan &plan, std::size_t *t
   plan.ws_window = static_cast<unsigned>(std::max(1, ws_env("HIFIR_B200_WS_WINDOW", 2)));
   if (!S.nrows) return;
   WsHost H;
-  pack_warp_streams(S, H, nsm * cfg.warps, plan.ws_window, plan.f32, rhs_index);
+  // the multi-rhs kernel (explicit configuration) amortizes a segment over all columns: full segments
+  // of 8 entries per lane, no spreading of thin level sets over many lanes (fewer reductions / publishes)
+  pack_warp_streams(S, H, nsm * cfg.warps, plan.ws_window, plan.f32, rhs_index, warps ? 8u : 0u);
   ws_finalize_ring(H, cfg.stages);
   plan.nblocks    = H.slices;
   plan.slab_bytes = H.stream.size() * 4u;
@@ -818,7 +1104,7 @@ void ws_debug_graph(const HostCsr &S, unsigned nsm, std::vector<unsigned> &dep_p
   const WsConfig cfg = ws_config();
   WsHost         H;
   pack_warp_streams(S, H, nsm * cfg.warps, static_cast<unsigned>(std::max(1, ws_env("HIFIR_B200_WS_WINDOW", 2))), false,
-                    nullptr);
+                    nullptr, 0u);
   ws_segment_graph(H, dep_ptr, dep_idx);
 }
 
@@ -827,7 +1113,7 @@ void ws_host_emulate(const HostCsr &S, bool upper, const double *rhs, const doub
   const WsConfig cfg = ws_config();
   WsHost         H;
   pack_warp_streams(S, H, 148u * cfg.warps, static_cast<unsigned>(std::max(1, ws_env("HIFIR_B200_WS_WINDOW", 2))), f32,
-                    nullptr);
+                    nullptr, 0u);
   ws_finalize_ring(H, cfg.stages);
   {
     std::string       why;
@@ -848,16 +1134,17 @@ template <bool UPPER, class VT, int kWarps, int kStages>
 void launch_ws_K(Handle *h, const SweepPlan &plan, const WsParams &P) {
   constexpr unsigned kStageBytes = (kWsHdrWords + 64u + kWsU * 32u * (sizeof(VT) == 4 ? 2u : 3u)) * 4u;
   constexpr unsigned smem        = kWarps * kStages * (8u + kStageBytes);
-  auto               kern        = wsweep_kernel<UPPER, VT, kWarps, kStages, false>;
+  const bool         pipe        = ws_env("HIFIR_B200_WS_PIPE", 0) != 0;
+  auto               kern        = pipe ? wsweep_kernel<UPPER, VT, kWarps, kStages, false, true> : wsweep_kernel<UPPER, VT, kWarps, kStages, false, false>;
   // per device, once (cudaFuncSetAttribute is per device)
-  static bool configured[64] = {false};
-  if (h->device < 64 && !configured[h->device]) {
+  static bool configured[64][2] = {{false}};
+  if (h->device < 64 && !configured[h->device][pipe ? 1 : 0]) {
     HIF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    configured[h->device] = true;
+    configured[h->device][pipe ? 1 : 0] = true;
   }
   if (P.trace) {
     if (kWarps != 24 || kStages != 2 || sizeof(VT) != 8) throw std::logic_error("tracing needs the 24 x 2 double configuration");
-    auto tk = wsweep_kernel<UPPER, double, 24, 2, true>;
+    auto tk = wsweep_kernel<UPPER, double, 24, 2, true, false>;
     HIF_CUDA(cudaFuncSetAttribute(tk, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     tk<<<plan.ws_grid, kWarps * 32, smem, h->stream>>>(P);
     return;
@@ -886,6 +1173,53 @@ void launch_ws_V(Handle *h, const SweepPlan &plan, const WsParams &P) {
 }
 }  // namespace
 
+namespace {
+template <bool UPPER, class VT>
+void launch_ws_mrhs_V(Handle *h, const SweepPlan &plan, const WsParams &P, unsigned nc) {
+  // the multi-rhs kernel keeps 8 accumulators and 2 x 8 gathered words per lane: 16 warps x 4 stages
+  constexpr int      kWarps = 16, kStages = 4;
+  constexpr unsigned kStageBytes = (kWsHdrWords + 64u + kWsU * 32u * (sizeof(VT) == 4 ? 2u : 3u)) * 4u;
+  constexpr unsigned smem        = kWarps * kStages * (8u + kStageBytes);
+  auto               kern        = wsweep_mrhs_kernel<UPPER, VT, kWarps, kStages>;
+  static bool        configured[64] = {false};
+  if (h->device < 64 && !configured[h->device]) {
+    HIF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    configured[h->device] = true;
+  }
+  kern<<<plan.ws_grid, kWarps * 32, smem, h->stream>>>(P, nc);
+}
+}  // namespace
+
+// multi-rhs sweep on a warp-stream plan built for 16 warps x 4 stages (build_ws_plan_mrhs)
+void launch_ws_sweep_mrhs(Handle *h, const SweepPlan &plan, const double *rhs_plain, const unsigned long long *rhs_tagged,
+                          const double *diag, unsigned long long *x, unsigned parity, int *sync, unsigned nc) {
+  if (!plan.nblocks) return;
+  if (plan.ws_warps != 16u || plan.ws_stages != 4u || (nc & 7u)) throw std::logic_error("multi-rhs warp-stream plan mismatch");
+  WsParams P;
+  P.trace      = nullptr;
+  P.wdesc      = plan.ws_wdesc.p;
+  P.stream     = plan.ws_stream.p;
+  P.rhs_plain  = rhs_plain;
+  P.rhs_tagged = rhs_tagged;
+  P.diag       = diag;
+  P.x          = x;
+  P.sync       = sync;
+  P.error_flag = h->error_flag.p;
+  P.parity     = parity;
+  P.window     = plan.ws_window;
+  P.adm_sleep  = static_cast<unsigned>(std::max(0, ws_env("HIFIR_B200_WS_SLEEP", 200)));
+  P.publish_st = 1;
+  P.l1_first   = 0;
+  P.spin_limit = static_cast<unsigned>(std::max(1000, ws_env("HIFIR_B200_WS_SPIN_LIMIT", 1 << 21)));
+  if (plan.upper) {
+    if (plan.f32) launch_ws_mrhs_V<true, float>(h, plan, P, nc); else launch_ws_mrhs_V<true, double>(h, plan, P, nc);
+  } else {
+    if (plan.f32) launch_ws_mrhs_V<false, float>(h, plan, P, nc); else launch_ws_mrhs_V<false, double>(h, plan, P, nc);
+  }
+  HIF_KERNEL_CHECK();
+  ++h->launch_count;
+}
+
 void launch_ws_sweep(Handle *h, const SweepPlan &plan, const double *rhs_plain, const unsigned long long *rhs_tagged,
                      const double *diag, unsigned long long *x, unsigned parity, int *sync, unsigned long long *trace) {
   if (!plan.nblocks) return;
@@ -903,6 +1237,7 @@ void launch_ws_sweep(Handle *h, const SweepPlan &plan, const double *rhs_plain, 
   P.window     = plan.ws_window;
   P.adm_sleep  = static_cast<unsigned>(std::max(0, ws_env("HIFIR_B200_WS_SLEEP", 200)));
   P.publish_st = ws_env("HIFIR_B200_WS_PUBLISH_ST", 0);
+  P.l1_first   = ws_env("HIFIR_B200_WS_L1", 0);
   P.spin_limit = static_cast<unsigned>(std::max(1000, ws_env("HIFIR_B200_WS_SPIN_LIMIT", 1 << 21)));
   if (plan.upper) {
     if (plan.f32)
