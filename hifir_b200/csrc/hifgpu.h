@@ -231,9 +231,10 @@ struct ApplyGraph {  // one captured apply (apply.cu)
   unsigned        parity;
   bool            nsp_on;
   std::size_t     nsp_start, nsp_end;
-  unsigned        uses;
+  unsigned        uses;  // uses at short intervals (capture on the third)
   cudaGraphExec_t exec;
   std::size_t     launches;
+  unsigned        last_epoch;
 };
 
 struct Handle {
@@ -277,6 +278,7 @@ struct Handle {
   std::size_t    io_cols = 0;
   DevBuf<double> ir_xk, ir_r, ir_t;
   DevBuf<double> kr_v, kr_w, kr_Q, kr_Z, kr_scal, kr_part;
+  DevBuf<unsigned> kr_count;        // arrival counter of the fused Gram-Schmidt step (krylov.cu)
   double *       h_scal = nullptr;  // pinned
   int            kr_restart = 0;
   // multi-rhs column staging

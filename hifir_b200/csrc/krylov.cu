@@ -8,6 +8,7 @@
 // device memory.  Only the O(restart) Hessenberg/Givens scalars travel to the host, once
 // per inner iteration, exactly where the reference evaluates its stopping tests.
 #include <cmath>
+#include <cstdlib>
 
 #include "hifgpu.h"
 
@@ -104,6 +105,43 @@ __global__ void div_dev_kernel(const unsigned n, const double *__restrict__ x, c
   for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[i] = x[i] / d;
 }
 
+// One modified Gram-Schmidt step in ONE pass and ONE launch (gmres.hpp:174-177):
+//   v <- v - h_k q_k   and, on the updated v,   h_next = <v, q_next>   (q_next = v itself: ||v||^2).
+// The block partials are folded by the block that arrives last, in fixed order (deterministic:
+// iteration counts must reproduce); it also re-arms the arrival counter.
+__global__ void __launch_bounds__(kRT) mgs_step_kernel(const unsigned n, const double *coef,
+                                                       const double *__restrict__ qk, const double *qnext,
+                                                       double *v, double *__restrict__ part, unsigned *counter,
+                                                       double *out) {
+  __shared__ double sm[kRT / 32];
+  __shared__ bool   last;
+  const double      a   = -*coef;
+  const bool        self = qnext == v;
+  double            acc = 0.0;
+  for (unsigned i = blockIdx.x * kRT + threadIdx.x; i < n; i += gridDim.x * kRT) {
+    const double vi = fma(a, qk[i], v[i]);
+    v[i]            = vi;
+    acc             = fma(vi, self ? vi : qnext[i], acc);
+  }
+  acc = block_sum(acc, sm);
+  if (threadIdx.x == 0) {
+    part[blockIdx.x] = acc;
+    __threadfence();
+    last = atomicAdd(counter, 1u) == gridDim.x - 1u;
+  }
+  __syncthreads();
+  if (last) {
+    __threadfence();
+    double t = 0.0;
+    for (unsigned i = threadIdx.x; i < gridDim.x; i += kRT) t += reinterpret_cast<volatile double *>(part)[i];
+    t = block_sum(t, sm);
+    if (threadIdx.x == 0) {
+      *out     = t;
+      *counter = 0u;
+    }
+  }
+}
+
 namespace {
 
 inline unsigned cdiv(std::size_t a, std::size_t b) { return static_cast<unsigned>((a + b - 1) / b); }
@@ -116,6 +154,7 @@ void ensure(Handle *h, DevBuf<double> &buf, std::size_t n) {
 void ensure_scal(Handle *h) {
   ensure(h, h->kr_scal, 256);
   ensure(h, h->kr_part, kRB);
+  if (!h->kr_count.n) h->kr_count.alloc(1, &h->device_bytes);  // zeroed: arrival counter of mgs_step_kernel
 }
 
 // out (device scalar) = <a, b>
@@ -300,15 +339,33 @@ void krylov_dev(Handle *h, bool flexible, const double *d_b, int restart, double
         num_mv += 1;
         spmv_dev(h, w, v);
       }
-      // modified Gram-Schmidt, coefficients stay on the device (gmres.hpp:174-177)
-      for (int k = 0; k <= j; ++k) {
-        const double *qk = Q + static_cast<std::size_t>(k) * n;
-        dot_to(h, n, v, qk, d_w2 + k);
-        axpy_dev_kernel<<<kEW, kRT, 0, h->stream>>>(un, d_w2 + k, -1.0, qk, v);
-        HIF_KERNEL_CHECK();
-        ++h->launch_count;
+      // modified Gram-Schmidt, coefficients stay on the device (gmres.hpp:174-177): h_0 = <v, q_0>, then
+      // one fused launch per k: v -= h_k q_k and h_{k+1} = <v, q_{k+1}> (after the last k: norm2_sq(v),
+      // math.hpp:97-105) -- the same products in the same order as dot-then-axpy, one pass instead of two
+      static const bool fused_mgs = [] {
+        const char *e = std::getenv("HIFIR_B200_MGS_FUSED");
+        return !e || std::atoi(e) != 0;
+      }();
+      if (fused_mgs) {
+        dot_to(h, n, v, Q, d_w2);
+        for (int k = 0; k <= j; ++k) {
+          const double *qk    = Q + static_cast<std::size_t>(k) * n;
+          const double *qnext = k < j ? qk + n : v;
+          mgs_step_kernel<<<nblk(n), kRT, 0, h->stream>>>(un, d_w2 + k, qk, qnext, v, h->kr_part.p, h->kr_count.p,
+                                                          k < j ? d_w2 + k + 1 : d_w2 + restart);
+          HIF_KERNEL_CHECK();
+          ++h->launch_count;
+        }
+      } else {
+        for (int k = 0; k <= j; ++k) {
+          const double *qk = Q + static_cast<std::size_t>(k) * n;
+          dot_to(h, n, v, qk, d_w2 + k);
+          axpy_dev_kernel<<<kEW, kRT, 0, h->stream>>>(un, d_w2 + k, -1.0, qk, v);
+          HIF_KERNEL_CHECK();
+          ++h->launch_count;
+        }
+        dot_to(h, n, v, v, d_w2 + restart);
       }
-      dot_to(h, n, v, v, d_w2 + restart);  // norm2_sq(v), math.hpp:97-105
       if (j + 1 < restart) {
         div_dev_kernel<<<kEW, kRT, 0, h->stream>>>(un, v, d_w2 + restart, true, Q + static_cast<std::size_t>(j + 1) * n);
         HIF_KERNEL_CHECK();
