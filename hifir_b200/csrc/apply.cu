@@ -101,11 +101,28 @@ constexpr int kTrsvThreads = 512;
 __global__ void __launch_bounds__(kTrsvThreads, 1)
     dense_trsv_kernel(const unsigned nm, const unsigned rk, const double *__restrict__ R,
                       const double *__restrict__ tinv, const double *__restrict__ c,
-                      const int *__restrict__ jpvt, double *__restrict__ out, const unsigned stride) {
+                      const int *__restrict__ jpvt, double *__restrict__ out, const unsigned stride,
+                      const double *__restrict__ Qfull) {
   // one CTA per right-hand side column (blockIdx.x) of a row-interleaved block of `stride` columns
-  extern __shared__ double xs[];  // rk values
+  extern __shared__ double xs[];  // rk values (+ nm values of the input when the Q^T product is fused)
   const unsigned           tid = threadIdx.x, colr = blockIdx.x;
-  for (unsigned i = tid; i < rk; i += kTrsvThreads) xs[i] = c[static_cast<std::size_t>(i) * stride + colr];
+  if (Qfull) {
+    // single-rhs path: c = Q(:,1:rk)^T x in the same launch -- one warp per column of the explicit Q,
+    // the input vector staged in shared memory (a second launch cost more than this product)
+    double *xin = xs + rk;
+    for (unsigned i = tid; i < nm; i += kTrsvThreads) xin[i] = c[i];
+    __syncthreads();
+    const unsigned warp = tid >> 5, lane = tid & 31u;
+    for (unsigned k = warp; k < rk; k += kTrsvThreads / 32) {
+      const double *q   = Qfull + static_cast<std::size_t>(k) * nm;
+      double        acc = 0.0;
+      for (unsigned i = lane; i < nm; i += 32) acc = fma(q[i], xin[i], acc);
+      acc = warp_sum(acc);
+      if (lane == 0) xs[k] = acc;
+    }
+  } else {
+    for (unsigned i = tid; i < rk; i += kTrsvThreads) xs[i] = c[static_cast<std::size_t>(i) * stride + colr];
+  }
   __syncthreads();
   const unsigned ntile = (rk + 31u) / 32u;
   for (unsigned t = ntile; t-- > 0;) {
@@ -210,6 +227,11 @@ void mark(Handle *h, const std::string &name) {
 void launch_sweeps(Handle *h, DevLevel &D, const double *rhs, unsigned long long *xL, unsigned long long *xU,
                    unsigned parity, int *tickets, const std::string &tag, int trace_base = -100) {
   if (!D.m) return;
+  if (D.LU.nblocks) {  // L then U in one launch (wsweep.cu, MODE 2); d permuted to the L sweep's slots
+    launch_ws_sweep(h, D.LU, rhs, nullptr, D.d_ls.p, xL, parity, tickets, nullptr, xU);
+    mark(h, tag + "LU");
+    return;
+  }
   const bool tl = h->trace_level >= 0 && &h->levels[h->trace_level] == &D;
   launch_sweep(h, D.L, rhs, nullptr, nullptr, xL, parity, tickets, 0,
                tl && h->trace_which == trace_base ? h->trace_buf.p : nullptr);
@@ -496,13 +518,21 @@ void dense_solve_dev(Handle *h, const double *d_in, double *d_out, std::size_t r
   DevDense &     Q  = h->dense;
   const unsigned nm = static_cast<unsigned>(Q.nm), rk = dense_rank_of(Q, rank);
   if (!Q.transposed) {
-    if (rk) {
+    // Q^T product and back substitution in one launch only for tiny dense levels: one SM reading the
+    // whole explicit Q is slow (measured at nm = 215: 54 us in one launch against 34 us with the
+    // multi-CTA product in front)
+    const bool one_launch = nm <= 64u;
+    if (rk && !one_launch) {
       dense_qt_kernel<<<cdiv(static_cast<std::size_t>(rk) * 32, 256), 256, 0, h->stream>>>(nm, rk, Q.Q.p, d_in, Q.c.p);
       HIF_KERNEL_CHECK();
       ++h->launch_count;
     }
-    dense_trsv_kernel<<<1, kTrsvThreads, (rk ? rk : 1) * sizeof(double), h->stream>>>(nm, rk, Q.R.p, Q.tinv.p, Q.c.p,
-                                                                                     Q.jpvt.p, d_out, 1u);
+    if (one_launch)
+      dense_trsv_kernel<<<1, kTrsvThreads, (rk + nm + 1) * sizeof(double), h->stream>>>(nm, rk, Q.R.p, Q.tinv.p, d_in,
+                                                                                       Q.jpvt.p, d_out, 1u, Q.Q.p);
+    else
+      dense_trsv_kernel<<<1, kTrsvThreads, (rk ? rk : 1) * sizeof(double), h->stream>>>(nm, rk, Q.R.p, Q.tinv.p, Q.c.p,
+                                                                                       Q.jpvt.p, d_out, 1u, nullptr);
   } else {
     dense_solve_t_kernel<<<1, kDenseT, (rk ? rk : 1) * sizeof(double), h->stream>>>(nm, rk, Q.R.p, Q.Q.p, Q.jpvt.p, d_in,
                                                                                    d_out);
@@ -538,7 +568,7 @@ void launch_ldu_solve(Handle *h, DevLevel &D, const double *rhs, unsigned long l
 void launch_dense_trsv_cols(Handle *h, unsigned nm, unsigned rk, const double *c, double *out, unsigned ncols) {
   DevDense &Q = h->dense;
   dense_trsv_kernel<<<ncols, kTrsvThreads, (rk ? rk : 1) * sizeof(double), h->stream>>>(nm, rk, Q.R.p, Q.tinv.p, c,
-                                                                                       Q.jpvt.p, out, ncols);
+                                                                                       Q.jpvt.p, out, ncols, nullptr);
   HIF_KERNEL_CHECK();
   ++h->launch_count;
 }

@@ -226,9 +226,20 @@ Handle *attach_levels(int device, std::size_t nlevels, const LhfdGpuLevel *lv, b
     const std::string tag = "level " + std::to_string(l);
 
     D.L.f32 = D.U.f32 = f32;  // streamed sweep values in single precision
-    // L first: the U sweep reads its right-hand side (L's tagged result) at L's solution slots
-    build_sweep_plan(Lr, false, D.L, tally, h->num_sms);
-    build_sweep_plan(Ur, true, D.U, tally, h->num_sms, D.L.slot_of.empty() ? nullptr : D.L.slot_of.data());
+    const char *ef   = std::getenv("HIFIR_B200_WS_FUSE");
+    const bool  fuse = sweep_kind() == 2 && P.m && (!ef || std::atoi(ef) != 0);
+    if (fuse) {
+      // one launch per U^{-1} D^{-1} L^{-1} solve: L's segments followed by U's in every warp's stream
+      const MergeParams mp = MergeParams::from_env();
+      D.LU.f32             = f32;
+      HostCsr SL = merged_sweep_form(Lr, false, mp, &D.L.merge);
+      HostCsr SU = merged_sweep_form(Ur, true, mp, &D.U.merge);
+      build_ws_ldu_plan(SL, SU, D.LU, D.L, D.U, tally, static_cast<unsigned>(h->num_sms));
+    } else {
+      // L first: the U sweep reads its right-hand side (L's tagged result) at L's solution slots
+      build_sweep_plan(Lr, false, D.L, tally, h->num_sms);
+      build_sweep_plan(Ur, true, D.U, tally, h->num_sms, D.L.slot_of.empty() ? nullptr : D.L.slot_of.data());
+    }
     if (std::getenv("HIFIR_B200_VERBOSE")) {
       for (const SweepPlan *pl : {&D.L, &D.U})
         std::fprintf(stderr,
@@ -358,7 +369,7 @@ Handle *attach_levels(int device, std::size_t nlevels, const LhfdGpuLevel *lv, b
 
   for (const DevLevel &D : h->levels)
     h->tick_stride = std::max<std::size_t>(
-        {h->tick_stride, kSyncStride * (2 + D.L.st_depth), kSyncStride * (2 + D.U.st_depth)});
+        {h->tick_stride, kSyncStride * (2 + D.L.st_depth), kSyncStride * (2 + D.U.st_depth), kSyncStride * (2 + D.LU.st_depth)});
   h->tickets.alloc((8 * nlevels + 8) * h->tick_stride, tally);
   h->error_flag.alloc(8, tally);  // [0] flag, [1..7] coordinates of the first failing wait (wsweep.cu)
   HIF_CUDA(cudaMallocHost(&h->h_error, sizeof(int)));

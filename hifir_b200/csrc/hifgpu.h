@@ -153,6 +153,7 @@ struct SweepPlan {
   DevBuf<float>               st_vals32;
   // warp-stream layout (wsweep.cu): one private segment stream per warp of a persistent CTA per SM
   bool                        ws = false;
+  bool                        fused = false;  // L segments followed by U segments: one launch per LDU solve
   unsigned                    ws_grid = 0, ws_warps = 0, ws_stages = 0, ws_window = 0, ws_nslots = 0, ws_nsegs = 0;
   DevBuf<unsigned>            ws_wdesc;   // 8 words per global warp: offset (16 B units), segments, -, -, first 4 sizes
   DevBuf<unsigned>            ws_stream;  // segments
@@ -164,6 +165,7 @@ struct SweepPlan {
 struct DevLevel {
   std::size_t m = 0, n = 0, nm = 0;
   SweepPlan   L, U;  // L_B, U_B
+  SweepPlan   LU;    // fused: L then U in one launch (wsweep.cu); L and U then only carry slot maps / statistics
   DevCsr      E, F;
   DevBuf<double> d;        // m
   // consumers of the sweeps' renumbered solution slots (wsweep.cu): built once at attach
@@ -368,7 +370,9 @@ void ws_host_emulate(const HostCsr &S, bool upper, const double *rhs, const doub
                      std::size_t stats[4], bool f32);
 void launch_ws_sweep(Handle *h, const SweepPlan &plan, const double *rhs_plain, const unsigned long long *rhs_tagged,
                      const double *diag, unsigned long long *x, unsigned parity, int *sync,
-                     unsigned long long *trace = nullptr);
+                     unsigned long long *trace = nullptr, unsigned long long *x2 = nullptr);
+void build_ws_ldu_plan(const HostCsr &SL, const HostCsr &SU, SweepPlan &plan, SweepPlan &L, SweepPlan &U, std::size_t *tally,
+                       unsigned nsm);
 void ws_debug_graph(const HostCsr &S, unsigned nsm, std::vector<unsigned> &dep_ptr, std::vector<unsigned> &dep_idx);
 void build_ws_plan_for(const HostCsr &Tnat, bool upper, SweepPlan &plan, std::size_t *tally, unsigned nsm,
                        const unsigned *rhs_index, unsigned warps, unsigned stages);  // merge + pack (sweep.cu)

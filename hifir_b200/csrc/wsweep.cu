@@ -40,7 +40,7 @@ namespace hifgpu {
 namespace {
 constexpr unsigned kWsU        = 8;            // entries per lane and segment
 constexpr unsigned kWsNone     = 0xffffffffu;  // padding column / no sentinel
-constexpr unsigned kSegFirst   = 1u, kSegLast = 2u, kSegCopy = 4u;
+constexpr unsigned kSegFirst   = 1u, kSegLast = 2u, kSegCopy = 4u, kSegUpper = 8u;
 constexpr unsigned kWsHdrWords = 4;
 
 inline unsigned seg_words(unsigned width, bool copy, bool f32) {
@@ -311,6 +311,53 @@ void ws_finalize_ring(WsHost &H, unsigned stages) {
   }
 }
 
+// Fused L-then-U plan: warp w's stream = its L segments followed by its U segments (flagged kSegUpper,
+// levels continued after the L levels).  One launch serves the whole  U^{-1} D^{-1} L^{-1}  solve: the
+// ring keeps running across the seam, and the first U rows simply poll the last L rows' tags.
+void ws_concat_ldu(const WsHost &L, const WsHost &U, WsHost &H) {
+  if (L.nwarps != U.nwarps) throw std::logic_error("ws_concat_ldu: plans of different width");
+  H          = WsHost();
+  H.nwarps   = L.nwarps;
+  H.nslots   = std::max(L.nslots, U.nslots);
+  H.depth    = L.depth + U.depth;
+  H.slices   = L.slices + U.slices;
+  H.entries  = L.entries + U.entries;
+  H.padded   = L.padded + U.padded;
+  H.nsegs    = L.nsegs + U.nsegs;
+  H.slot_of  = U.slot_of;  // the final solution is the U sweep's
+  H.wdesc.assign(static_cast<std::size_t>(H.nwarps) * 8u, 0u);
+  H.seg_off.assign(H.nwarps, {});
+  H.stream.reserve(L.stream.size() + U.stream.size());
+  unsigned seg_base = 0;
+  auto     part = [](const WsHost &P, unsigned w, const unsigned *&b, const unsigned *&e) {
+    b = P.stream.data() + static_cast<std::size_t>(P.wdesc[static_cast<std::size_t>(w) * 8u]) * 4u;
+    e = w + 1 < P.nwarps ? P.stream.data() + static_cast<std::size_t>(P.wdesc[static_cast<std::size_t>(w + 1) * 8u]) * 4u
+                         : P.stream.data() + P.stream.size();
+  };
+  for (unsigned w = 0; w < H.nwarps; ++w) {
+    unsigned *d = H.wdesc.data() + static_cast<std::size_t>(w) * 8u;
+    d[0]        = static_cast<unsigned>(H.stream.size() / 4u);
+    const unsigned *b, *e;
+    part(L, w, b, e);
+    const std::size_t lwords = static_cast<std::size_t>(e - b);
+    H.stream.insert(H.stream.end(), b, e);
+    H.seg_off[w] = L.seg_off[w];
+    part(U, w, b, e);
+    const std::size_t o0 = H.stream.size();
+    H.stream.insert(H.stream.end(), b, e);
+    for (unsigned so : U.seg_off[w]) {
+      H.seg_off[w].push_back(static_cast<unsigned>(lwords + so));
+      unsigned *hd = H.stream.data() + o0 + so;
+      hd[0] |= kSegUpper << 16;
+      hd[3] += L.depth;
+    }
+    d[1] = static_cast<unsigned>(H.seg_off[w].size());
+    d[2] = seg_base;
+    seg_base += d[1];
+    H.max_segs = std::max<std::size_t>(H.max_segs, H.seg_off[w].size());
+  }
+}
+
 // CPU emulation of the warp-stream sweep on the packed data (segments in creation order = level
 // order): lets tests check merge + packing without a GPU.  x has H.nslots entries.
 void ws_host_emulate_packed(const WsHost &H, bool upper, bool f32, const double *rhs, const double *diag, double *x) {
@@ -516,6 +563,7 @@ struct WsParams {
   const unsigned long long *rhs_tagged;
   const double *            diag;
   unsigned long long *      x;
+  unsigned long long *      x2;    // fused L-then-U sweep: solution of the U sweep (x: of the L sweep)
   int *                     sync;  // [0] frontier hint (highest level some warp finished a slice of)
   int *                     error_flag;
   unsigned                  parity, window, adm_sleep;
@@ -548,7 +596,9 @@ __device__ __forceinline__ unsigned long long ws_timer_ns() {
   return t;
 }
 
-template <bool UPPER, class VT, int kWarps, int kStages, bool kTrace, bool kPipe>
+// MODE 0: L sweep, 1: U sweep, 2: fused L-then-U sweep (a segment's header says which factor it belongs to:
+// L segments gather from / publish to x, U segments x2, and read their right-hand side from x)
+template <int MODE, class VT, int kWarps, int kStages, bool kTrace, bool kPipe>
 __global__ void __launch_bounds__(kWarps * 32, 1) wsweep_kernel(const WsParams P) {
   constexpr unsigned kStageBytes = (kWsHdrWords + 64u + kWsU * 32u * (sizeof(VT) == 4 ? 2u : 3u)) * 4u;
   extern __shared__ __align__(128) unsigned char smem[];
@@ -615,6 +665,9 @@ __global__ void __launch_bounds__(kWarps * 32, 1) wsweep_kernel(const WsParams P
     const unsigned *sg    = reinterpret_cast<const unsigned *>(ring + stage * kStageBytes);
     const uint4     hd    = *reinterpret_cast<const uint4 *>(sg);
     const unsigned  width = hd.x & 0xffu, z = (hd.x >> 8) & 0xffu, flags = hd.x >> 16;
+    const bool      UPPER = MODE == 2 ? (flags & kSegUpper) != 0u : MODE == 1;
+    unsigned long long *const       xw  = (MODE == 2 && UPPER) ? P.x2 : P.x;           // this factor's solution
+    const unsigned long long *const rht = MODE == 2 ? P.x : P.rhs_tagged;              // U: the L sweep's result
     unsigned long long *tr = kTrace ? P.trace + 4ull * (d0.z + k) : nullptr;
     unsigned long long  t_dec = 0;
     if (kTrace) t_dec = ws_timer_ns();
@@ -636,8 +689,8 @@ __global__ void __launch_bounds__(kWarps * 32, 1) wsweep_kernel(const WsParams P
         if (slot[u] != kWsNone && !(code[u] & kCodeZeroRhs)) {
           const unsigned r = code[u] & kCodeSlotMask;
           if (UPPER) {
-            unsigned long long t = ld_poll(P.rhs_tagged + r);
-            for (unsigned spins = 0; !tag_ready(t, parity); t = ld_poll(P.rhs_tagged + r))
+            unsigned long long t = ld_poll(rht + r);
+            for (unsigned spins = 0; !tag_ready(t, parity); t = ld_poll(rht + r))
               if (++spins > P.spin_limit || ((spins & 255u) == 255u && ws_aborted(P))) {
                 if (!ws_aborted(P)) ws_fail(P, gw, k, hd.w, 3, r);
                 break;
@@ -650,7 +703,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) wsweep_kernel(const WsParams P
       }
 #pragma unroll
       for (unsigned u = 0; u < kWsU; ++u)
-        if (slot[u] != kWsNone) st_publish(P.x + slot[u], tag_set(v[u], parity));  // consumes code and slot
+        if (slot[u] != kWsNone) st_publish(xw + slot[u], tag_set(v[u], parity));  // consumes code and slot
       refill(stage, hd.y);
       have_cur = false;
       if (lane == 0 && hd.w > my_front + 3u) {
@@ -675,7 +728,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) wsweep_kernel(const WsParams P
         if (lane == 0) {
           unsigned       spins = 0;
           const unsigned need  = hd.w - P.window;
-          while (!tag_ready(ld_poll(P.x + hd.z), parity)) {
+          while (!tag_ready(ld_poll(xw + hd.z), parity)) {
             // far from the frontier: sleep in proportion to the distance; close to it: spin on the sentinel
             const unsigned f = static_cast<unsigned>(ws_ld_poll_i32(P.sync));
             if (need > f + 4u) __nanosleep(min((need - f) * P.adm_sleep, 20000u));
@@ -692,11 +745,11 @@ __global__ void __launch_bounds__(kWarps * 32, 1) wsweep_kernel(const WsParams P
       if (P.l1_first) {
 #pragma unroll
         for (unsigned u = 0; u < kWsU; ++u)
-          if (cc[u] != kWsNone) g[u] = ws_ld_l1(P.x + cc[u]);
+          if (cc[u] != kWsNone) g[u] = ws_ld_l1(xw + cc[u]);
       } else {
 #pragma unroll
         for (unsigned u = 0; u < kWsU; ++u)
-          if (cc[u] != kWsNone) g[u] = ld_poll(P.x + cc[u]);
+          if (cc[u] != kWsNone) g[u] = ld_poll(xw + cc[u]);
       }
     } else if (kTrace) {
       t_adm = ws_timer_ns();
@@ -713,6 +766,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) wsweep_kernel(const WsParams P
       if (__all_sync(0xffffffffu, ws_mbar_try_wait(bar0 + st1 * 8u, ph1))) {
         const unsigned *sg1 = reinterpret_cast<const unsigned *>(ring + st1 * kStageBytes);
         const unsigned  hx1 = sg1[0], hz1 = sg1[2], w1 = hx1 & 0xffu;
+        const unsigned long long *const xn = (MODE == 2 && ((hx1 >> 16) & kSegUpper)) ? P.x2 : P.x;
         if (!((hx1 >> 16) & kSegCopy) && hz1 == kWsNone) {
 #pragma unroll
           for (unsigned u = 0; u < kWsU; ++u) {
@@ -721,7 +775,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) wsweep_kernel(const WsParams P
           }
 #pragma unroll
           for (unsigned u = 0; u < kWsU; ++u)
-            if (ccn[u] != kWsNone) gn[u] = ld_poll(P.x + ccn[u]);
+            if (ccn[u] != kWsNone) gn[u] = ld_poll(xn + ccn[u]);
           have_nxt = true;
         }
       }
@@ -736,7 +790,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) wsweep_kernel(const WsParams P
     if (want_r) {
       const unsigned r = code & kCodeSlotMask;
       if (UPPER) {
-        rhs_t = ld_poll(P.rhs_tagged + r);
+        rhs_t = ld_poll(rht + r);
         dg    = P.diag[r];
       } else {
         rhs_v = P.rhs_plain[r];
@@ -765,8 +819,8 @@ __global__ void __launch_bounds__(kWarps * 32, 1) wsweep_kernel(const WsParams P
       if (kTrace) ++nrounds;
 #pragma unroll
       for (unsigned u = 0; u < kWsU; ++u)
-        if (pend & (1u << u)) g[u] = ld_poll(P.x + cc[u]);
-      if (UPPER && (pend & (1u << kWsU))) rhs_t = ld_poll(P.rhs_tagged + (code & kCodeSlotMask));
+        if (pend & (1u << u)) g[u] = ld_poll(xw + cc[u]);
+      if (UPPER && (pend & (1u << kWsU))) rhs_t = ld_poll(rht + (code & kCodeSlotMask));
 #pragma unroll
       for (unsigned u = 0; u < kWsU; ++u)
         if ((pend & (1u << u)) && tag_ready(g[u], parity)) pend &= ~(1u << u);
@@ -800,7 +854,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) wsweep_kernel(const WsParams P
       }
     if (flags & kSegLast) {
       for (unsigned o = lpr >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-      if (own) ws_publish(P.x + slot, tag_set(acc, parity), P.publish_st);
+      if (own) ws_publish(xw + slot, tag_set(acc, parity), P.publish_st);
     }
     refill(stage, hd.y + (acc == 1.2345e300 ? 1u : 0u));  // (the refill depends on acc: see above)
     have_cur = have_nxt;
@@ -1100,6 +1154,38 @@ void build_ws_plan(const HostCsr &S, bool upper, SweepPlan &plan, std::size_t *t
   plan.ws_stream.upload(H.stream, tally);
 }
 
+// fused plan of one level: L and U merged factors -> one stream per warp (ws_concat_ldu)
+void build_ws_ldu_plan(const HostCsr &SL, const HostCsr &SU, SweepPlan &plan, SweepPlan &L, SweepPlan &U, std::size_t *tally,
+                       unsigned nsm) {
+  const WsConfig cfg = ws_config();
+  const unsigned window = static_cast<unsigned>(std::max(1, ws_env("HIFIR_B200_WS_WINDOW", 2)));
+  WsHost HL, HU, H;
+  pack_warp_streams(SL, HL, nsm * cfg.warps, window, plan.f32, nullptr, 0u);
+  pack_warp_streams(SU, HU, nsm * cfg.warps, window, plan.f32, HL.slot_of.empty() ? nullptr : HL.slot_of.data(), 0u);
+  ws_concat_ldu(HL, HU, H);
+  ws_finalize_ring(H, cfg.stages);
+  plan.ws = true, plan.stream = false, plan.upper = false, plan.fused = true, plan.nr = 1;
+  plan.m         = static_cast<unsigned>(SL.orig_rows);
+  plan.ws_grid   = nsm, plan.ws_warps = cfg.warps, plan.ws_stages = cfg.stages, plan.ws_window = window;
+  plan.nblocks   = H.slices;
+  plan.slab_bytes = H.stream.size() * 4u;
+  plan.st_depth  = H.depth;
+  plan.st_padded = H.padded;
+  plan.ws_nslots = H.nslots;
+  plan.ws_nsegs  = static_cast<unsigned>(H.nsegs);
+  plan.ws_wdesc.upload(H.wdesc, tally);
+  plan.ws_stream.upload(H.stream, tally);
+  // the unfused descriptions (slot maps, statistics) without their device streams
+  L.ws = U.ws = true, L.upper = false, U.upper = true;
+  L.m = U.m = plan.m;
+  L.slot_of = HL.slot_of, U.slot_of = HU.slot_of;
+  L.st_depth = HL.depth, U.st_depth = HU.depth;
+  L.st_padded = HL.padded, U.st_padded = HU.padded;
+  L.slab_bytes = HL.stream.size() * 4u, U.slab_bytes = HU.stream.size() * 4u;
+  L.ws_nslots = HL.nslots, U.ws_nslots = HU.nslots;
+  L.nblocks = U.nblocks = 0;  // not launchable on their own
+}
+
 void ws_debug_graph(const HostCsr &S, unsigned nsm, std::vector<unsigned> &dep_ptr, std::vector<unsigned> &dep_idx) {
   const WsConfig cfg = ws_config();
   WsHost         H;
@@ -1130,7 +1216,7 @@ void ws_host_emulate(const HostCsr &S, bool upper, const double *rhs, const doub
 }
 
 namespace {
-template <bool UPPER, class VT, int kWarps, int kStages>
+template <int UPPER, class VT, int kWarps, int kStages>
 void launch_ws_K(Handle *h, const SweepPlan &plan, const WsParams &P) {
   constexpr unsigned kStageBytes = (kWsHdrWords + 64u + kWsU * 32u * (sizeof(VT) == 4 ? 2u : 3u)) * 4u;
   constexpr unsigned smem        = kWarps * kStages * (8u + kStageBytes);
@@ -1151,7 +1237,7 @@ void launch_ws_K(Handle *h, const SweepPlan &plan, const WsParams &P) {
   }
   kern<<<plan.ws_grid, kWarps * 32, smem, h->stream>>>(P);
 }
-template <bool UPPER, class VT>
+template <int UPPER, class VT>
 void launch_ws_V(Handle *h, const SweepPlan &plan, const WsParams &P) {
   const unsigned w = plan.ws_warps, s = plan.ws_stages;
   if (w == 16 && s == 4)
@@ -1197,6 +1283,7 @@ void launch_ws_sweep_mrhs(Handle *h, const SweepPlan &plan, const double *rhs_pl
   if (plan.ws_warps != 16u || plan.ws_stages != 4u || (nc & 7u)) throw std::logic_error("multi-rhs warp-stream plan mismatch");
   WsParams P;
   P.trace      = nullptr;
+  P.x2         = nullptr;
   P.wdesc      = plan.ws_wdesc.p;
   P.stream     = plan.ws_stream.p;
   P.rhs_plain  = rhs_plain;
@@ -1221,10 +1308,12 @@ void launch_ws_sweep_mrhs(Handle *h, const SweepPlan &plan, const double *rhs_pl
 }
 
 void launch_ws_sweep(Handle *h, const SweepPlan &plan, const double *rhs_plain, const unsigned long long *rhs_tagged,
-                     const double *diag, unsigned long long *x, unsigned parity, int *sync, unsigned long long *trace) {
+                     const double *diag, unsigned long long *x, unsigned parity, int *sync, unsigned long long *trace,
+                     unsigned long long *x2) {
   if (!plan.nblocks) return;
   WsParams P;
   P.trace      = trace;
+  P.x2         = x2;
   P.wdesc      = plan.ws_wdesc.p;
   P.stream     = plan.ws_stream.p;
   P.rhs_plain  = rhs_plain;
@@ -1239,27 +1328,33 @@ void launch_ws_sweep(Handle *h, const SweepPlan &plan, const double *rhs_plain, 
   P.publish_st = ws_env("HIFIR_B200_WS_PUBLISH_ST", 0);
   P.l1_first   = ws_env("HIFIR_B200_WS_L1", 0);
   P.spin_limit = static_cast<unsigned>(std::max(1000, ws_env("HIFIR_B200_WS_SPIN_LIMIT", 1 << 21)));
-  if (plan.upper) {
+  if (plan.fused) {
+    if (!x2) throw std::logic_error("fused L-then-U sweep needs both solution buffers");
     if (plan.f32)
-      launch_ws_V<true, float>(h, plan, P);
+      launch_ws_V<2, float>(h, plan, P);
     else
-      launch_ws_V<true, double>(h, plan, P);
+      launch_ws_V<2, double>(h, plan, P);
+  } else if (plan.upper) {
+    if (plan.f32)
+      launch_ws_V<1, float>(h, plan, P);
+    else
+      launch_ws_V<1, double>(h, plan, P);
   } else {
     if (plan.f32)
-      launch_ws_V<false, float>(h, plan, P);
+      launch_ws_V<0, float>(h, plan, P);
     else
-      launch_ws_V<false, double>(h, plan, P);
+      launch_ws_V<0, double>(h, plan, P);
   }
   HIF_KERNEL_CHECK();
   ++h->launch_count;
   // developer experiment: launch the sweep again -- every slot already carries the current tag, so the
   // second pass never waits: its duration is the pure throughput bound of the kernel on this factor
   static const int repeat = ws_env("HIFIR_B200_WS_REPEAT", 0);
-  for (int r = 0; r < repeat; ++r) {
+  for (int r = 0; r < repeat && !plan.fused; ++r) {
     if (plan.upper) {
-      if (plan.f32) launch_ws_V<true, float>(h, plan, P); else launch_ws_V<true, double>(h, plan, P);
+      if (plan.f32) launch_ws_V<1, float>(h, plan, P); else launch_ws_V<1, double>(h, plan, P);
     } else {
-      if (plan.f32) launch_ws_V<false, float>(h, plan, P); else launch_ws_V<false, double>(h, plan, P);
+      if (plan.f32) launch_ws_V<0, float>(h, plan, P); else launch_ws_V<0, double>(h, plan, P);
     }
     HIF_KERNEL_CHECK();
   }

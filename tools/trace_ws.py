@@ -67,6 +67,7 @@ def main():
     ap.add_argument("--sweeps", default="0:0,0:1,1:0,1:1")
     args = ap.parse_args()
     build.build()
+    os.environ.setdefault("HIFIR_B200_WS_FUSE", "0")  # the trace numbers the segments of ONE sweep
     for kv in filter(None, args.cfg.split(",")):
         k, v = kv.split("=")
         os.environ[k] = v
