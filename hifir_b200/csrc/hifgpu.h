@@ -286,8 +286,8 @@ struct Handle {
   // multi-rhs column staging
   DevBuf<double> mr_b, mr_x, mr_c;
   bool           mrhs_ready = false;
-  bool           wide_plans = false;  // warp-stream plans of the multi-rhs kernel built (mrhs.cu)
-  std::size_t    wide_nc = 0;         // columns the multi-rhs work vectors hold
+  std::size_t    wide_nc = 0;         // row stride (columns) the multi-rhs work vectors are laid out for
+  std::size_t    wide_cap = 0;        // columns they can hold
   // statistics
   std::size_t bytes_factors = 0, bytes_vec = 0, bytes_dense = 0, device_bytes = 0, nnz_total = 0;
   std::size_t kernels_per_apply = 0, launch_count = 0;
@@ -364,8 +364,8 @@ void ws_finalize_ring(WsHost &H, unsigned stages);
 void ws_host_emulate_packed(const WsHost &H, bool upper, bool f32, const double *rhs, const double *diag, double *x);
 void build_ws_plan(const HostCsr &S, bool upper, SweepPlan &plan, std::size_t *tally, unsigned nsm,
                    const unsigned *rhs_index, unsigned warps = 0, unsigned stages = 0);  // 0: HIFIR_B200_WS_WARPS / _STAGES
-void launch_ws_sweep_mrhs(Handle *h, const SweepPlan &plan, const double *rhs_plain, const unsigned long long *rhs_tagged,
-                          const double *diag, unsigned long long *x, unsigned parity, int *sync, unsigned nc);
+void launch_ws_sweep_cols(Handle *h, const SweepPlan &plan, const double *rhs_plain, const double *diag, unsigned long long *xL,
+                          unsigned long long *xU, unsigned parity, int *sync, unsigned nc);  // fused plan, nc = 16 | 32 | 64
 void ws_host_emulate(const HostCsr &S, bool upper, const double *rhs, const double *diag, double *x_by_row,
                      std::size_t stats[4], bool f32);
 void launch_ws_sweep(Handle *h, const SweepPlan &plan, const double *rhs_plain, const unsigned long long *rhs_tagged,

@@ -6,9 +6,12 @@
 // kernels -- CompressedStorage.hpp:2117-2137, 2286-2301, 2376-2393, QRCP.hpp:229-242 -- fix the
 // per-column arithmetic that is reproduced here).
 //
-// Columns are processed kMrhsWidth (= 8) at a time: every work vector holds 8 values per
-// row (64 B: one coalesced, vectorised transaction per dependency) and every factor is
-// streamed ONCE for the 8 columns.  The schedule is the single-rhs one (apply.cu).
+// Default path (warp-stream plans): the block is processed in passes of W = 16, 32 or 64 columns
+// (HIFIR_B200_MRHS_WIDE) on the fused L-then-U plans of the single-rhs apply -- wsweep_cols_kernel
+// (wsweep.cu) puts the lanes ACROSS the columns, every dependency is one coalesced row of W values
+// and every factor is streamed once per W columns.  The glue kernels read the caller's block in
+// place (row stride nrhs, column offset of the pass).  Streaming plans (HIFIR_B200_SWEEP=stream)
+// keep round 1's passes of kMrhsWidth (= 8) columns.  The schedule is the single-rhs one (apply.cu).
 #include <algorithm>
 #include <cstdlib>
 
@@ -40,15 +43,16 @@ __global__ void chunk_insert_kernel(const unsigned n, const unsigned nrhs, const
   if (k0 + c < nrhs) X[i * nrhs + k0 + c] = in[g];
 }
 
-// bhat[i][c] = s[p[i]] * b[p[i]][c]     (prec_solve.hpp:359, 368, 399)
+// bhat[i][c] = s[p[i]] * b[p[i]][k0 + c]     (prec_solve.hpp:359, 368, 399); b has row stride ldb and
+// nvalid columns from k0 on (the rest of the pass is zero padding)
 __global__ void gather_scale_m_kernel(const unsigned n, const unsigned nc, const int *__restrict__ p,
-                                      const double *__restrict__ s, const double *__restrict__ b,
-                                      double *__restrict__ bhat) {
+                                      const double *__restrict__ s, const double *__restrict__ b, const unsigned ldb,
+                                      const unsigned k0, const unsigned nvalid, double *__restrict__ bhat) {
   const std::size_t g = static_cast<std::size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (g >= static_cast<std::size_t>(n) * nc) return;
   const std::size_t i = g / nc, c = g % nc;
   const int         pi = p[i];
-  bhat[g]              = s[pi] * b[static_cast<std::size_t>(pi) * nc + c];
+  bhat[g]              = c < nvalid ? s[pi] * b[static_cast<std::size_t>(pi) * ldb + k0 + c] : 0.0;
 }
 
 // out[i][c] = base[i][c] - sum_j A(i,j) x[j][c]; NR consecutive threads = the NR columns of one row
@@ -85,33 +89,20 @@ __global__ void scatter_scale_m_kernel(const unsigned n, const unsigned nc, cons
   y[g]                = t[i] * w;
 }
 
-// the same with q_inv mapped to the solution slots of the U sweep (attach.cu: q_slot)
+// the same with q_inv mapped to the solution slots of the U sweep (attach.cu: q_slot); y has row stride
+// ldy and receives the first nvalid columns of the pass at column k0
 __global__ void scatter_scale_ms_kernel(const unsigned n, const unsigned nc, const int *__restrict__ q_slot,
                                         const double *__restrict__ t, const unsigned long long *__restrict__ xU,
-                                        const double *__restrict__ ychild, double *__restrict__ y) {
+                                        const double *__restrict__ ychild, double *__restrict__ y, const unsigned ldy,
+                                        const unsigned k0, const unsigned nvalid) {
   const std::size_t g = static_cast<std::size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (g >= static_cast<std::size_t>(n) * nc) return;
   const std::size_t i = g / nc, c = g % nc;
-  const int         j = q_slot[i];
-  const double      w = j >= 0 ? tag_value(xU[static_cast<std::size_t>(j) * nc + c])
-                               : ychild[static_cast<std::size_t>(-j - 1) * nc + c];
-  y[g]                = t[i] * w;
-}
-
-// [n][nrhs] <-> [n][nc] (nc = nrhs rounded up to a multiple of 8, zero padded)
-__global__ void pad_cols_kernel(const unsigned n, const unsigned nrhs, const unsigned nc, const double *__restrict__ B,
-                                double *__restrict__ out) {
-  const std::size_t g = static_cast<std::size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (g >= static_cast<std::size_t>(n) * nc) return;
-  const std::size_t i = g / nc, c = g % nc;
-  out[g]              = c < nrhs ? B[i * nrhs + c] : 0.0;
-}
-__global__ void unpad_cols_kernel(const unsigned n, const unsigned nrhs, const unsigned nc, const double *__restrict__ in,
-                                  double *__restrict__ X) {
-  const std::size_t g = static_cast<std::size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (g >= static_cast<std::size_t>(n) * nrhs) return;
-  const std::size_t i = g / nrhs, c = g % nrhs;
-  X[g]                = in[i * nc + c];
+  if (c >= nvalid) return;
+  const int    j = q_slot[i];
+  const double w = j >= 0 ? tag_value(xU[static_cast<std::size_t>(j) * nc + c])
+                          : ychild[static_cast<std::size_t>(-j - 1) * nc + c];
+  y[i * ldy + k0 + c] = t[i] * w;
 }
 
 // dense level: cq[k][c] = Q(:,k)^T x[:, c] : one warp per column k of Q, NR accumulators
@@ -137,69 +128,54 @@ __global__ void dense_qt_m_kernel(const unsigned nm, const unsigned rk, const un
   }
 }
 
-// ---- wide blocks on warp-stream plans: all nc columns in one pass over the factors (wsweep.cu)
-void ensure_wide(Handle *h, std::size_t nc) {
+// work vectors of the multi-rhs paths with row stride nc.  The tagged ones are only valid for ONE stride:
+// after a change a word of an older layout could carry the tag two epochs later -> zero them, epoch 0.
+void ensure_cols(Handle *h, std::size_t nc) {
+  if (h->wide_nc == nc) return;
   std::size_t *tally = &h->device_bytes;
-  if (!h->wide_plans) {
-    for (DevLevel &D : h->levels) {
-      // the multi-rhs kernel runs 16 warps x 4 stages: its own streams, the same solution slots
-      D.Lm.f32 = D.Um.f32 = h->f32;
-      build_ws_plan_for(D.hostL, false, D.Lm, tally, static_cast<unsigned>(h->num_sms), nullptr, 16u, 4u);
-      build_ws_plan_for(D.hostU, true, D.Um, tally, static_cast<unsigned>(h->num_sms),
-                        D.Lm.slot_of.empty() ? nullptr : D.Lm.slot_of.data(), 16u, 4u);
-      if (D.Lm.slot_of != D.L.slot_of || D.Um.slot_of != D.U.slot_of)
-        throw std::logic_error("multi-rhs plans disagree with the single-rhs solution slots");
-    }
-    h->wide_plans = true;
-  }
-  if (h->wide_nc >= nc) return;
   HIF_CUDA(cudaStreamSynchronize(h->stream));
-  for (DevLevel &D : h->levels) {
-    D.m_bhat.alloc(D.n * nc, tally);
-    D.m_g.alloc(D.m * nc, tally);
-    D.m_r.alloc(D.nm * nc, tally);
-    D.m_ychild.alloc(D.nm * nc, tally);
-    D.m_xL_dn.alloc(2 * D.m * nc, tally);
-    D.m_xU_dn.alloc(2 * D.m * nc, tally);
-    D.m_xL_up.alloc(2 * D.m * nc, tally);
-    D.m_xU_up.alloc(2 * D.m * nc, tally);
+  if (h->wide_cap < nc) {
+    for (DevLevel &D : h->levels) {
+      D.m_bhat.alloc(D.n * nc, tally);
+      D.m_g.alloc(D.m * nc, tally);
+      D.m_r.alloc(D.nm * nc, tally);
+      D.m_ychild.alloc(D.nm * nc, tally);
+      // m solution slots + m slots for the auxiliary unknowns of merge.cu, nc values each
+      D.m_xL_dn.alloc(2 * D.m * nc, tally);
+      D.m_xU_dn.alloc(2 * D.m * nc, tally);
+      D.m_xL_up.alloc(2 * D.m * nc, tally);
+      D.m_xU_up.alloc(2 * D.m * nc, tally);
+    }
+    const std::size_t n = h->n0();
+    h->mr_b.alloc(n * nc, tally);
+    h->mr_x.alloc(n * nc, tally);
+    h->mr_c.alloc(h->dense.nm * nc + 1, tally);
+    h->wide_cap = nc;
+  } else {
+    for (DevLevel &D : h->levels)
+      for (DevBuf<unsigned long long> *b : {&D.m_xL_dn, &D.m_xU_dn, &D.m_xL_up, &D.m_xU_up})
+        if (b->p) HIF_CUDA(cudaMemset(b->p, 0, b->n * sizeof(unsigned long long)));
+    HIF_CUDA(cudaDeviceSynchronize());
   }
-  const std::size_t n = h->n0();
-  h->mr_b.alloc(n * nc, tally);
-  h->mr_x.alloc(n * nc, tally);
-  h->mr_c.alloc(h->dense.nm * nc + 1, tally);
-  h->wide_nc    = nc;
-  h->epoch_m    = 0;  // fresh (zeroed) tagged buffers
-  h->mrhs_ready = false;
+  h->wide_nc = nc;
+  h->epoch_m = 0;  // fresh (zeroed) tagged buffers
 }
 
 void ensure_mrhs(Handle *h) {
-  if (h->mrhs_ready) return;
-  std::size_t *tally = &h->device_bytes;
-  for (DevLevel &D : h->levels) {
-    // the streaming plans (stream.cu) serve any width; warp-stream plans serve one column: the
-    // multi-rhs sweeps then run on streaming plans of their own (identity slots)
-    if (!D.L.stream) {
-      D.Lm.f32 = D.Um.f32 = h->f32;
-      build_sweep_plan(D.hostL, false, D.Lm, tally, static_cast<unsigned>(h->num_sms), nullptr, 1);
-      build_sweep_plan(D.hostU, true, D.Um, tally, static_cast<unsigned>(h->num_sms), nullptr, 1);
+  if (!h->mrhs_ready) {
+    std::size_t *tally = &h->device_bytes;
+    for (DevLevel &D : h->levels) {
+      // the streaming plans (stream.cu) serve any width; warp-stream plans that are not fused serve one
+      // column: the multi-rhs sweeps then run on streaming plans of their own (identity slots)
+      if (!D.L.stream) {
+        D.Lm.f32 = D.Um.f32 = h->f32;
+        build_sweep_plan(D.hostL, false, D.Lm, tally, static_cast<unsigned>(h->num_sms), nullptr, 1);
+        build_sweep_plan(D.hostU, true, D.Um, tally, static_cast<unsigned>(h->num_sms), nullptr, 1);
+      }
     }
-    D.m_bhat.alloc(D.n * NR, tally);
-    D.m_g.alloc(D.m * NR, tally);
-    D.m_r.alloc(D.nm * NR, tally);
-    D.m_ychild.alloc(D.nm * NR, tally);
-    // m solution slots + m slots for the auxiliary unknowns of merge.cu, NR values each
-    D.m_xL_dn.alloc(2 * D.m * NR, tally);
-    D.m_xU_dn.alloc(2 * D.m * NR, tally);
-    D.m_xL_up.alloc(2 * D.m * NR, tally);
-    D.m_xU_up.alloc(2 * D.m * NR, tally);
-
+    h->mrhs_ready = true;
   }
-  const std::size_t n = h->n0();
-  h->mr_b.alloc(n * NR, tally);
-  h->mr_x.alloc(n * NR, tally);
-  h->mr_c.alloc(h->dense.nm * NR + 1, tally);
-  h->mrhs_ready = true;
+  ensure_cols(h, NR);
 }
 
 }  // namespace
@@ -220,8 +196,8 @@ static void apply_chunk(Handle *h, const double *d_in, double *d_out, std::size_
   for (std::size_t l = 0; l < nl; ++l) {
     DevLevel &D = h->levels[l];
     if (D.n) {
-      gather_scale_m_kernel<<<cdiv(D.n * NR, T), T, 0, h->stream>>>(static_cast<unsigned>(D.n), NR, D.p.p, D.s.p, b,
-                                                                     D.m_bhat.p);
+      gather_scale_m_kernel<<<cdiv(D.n * NR, T), T, 0, h->stream>>>(static_cast<unsigned>(D.n), NR, D.p.p, D.s.p, b, NR, 0u,
+                                                                     NR, D.m_bhat.p);
       HIF_KERNEL_CHECK();
       ++h->launch_count;
     }
@@ -279,33 +255,33 @@ static void apply_chunk(Handle *h, const double *d_in, double *d_out, std::size_
 
 void launch_dense_trsv_cols(Handle *h, unsigned nm, unsigned rk, const double *c, double *out, unsigned ncols);
 
-// X = M^{-1} B for a row-interleaved block of nc columns (nc a multiple of 8), every factor streamed once
-static void apply_wide(Handle *h, unsigned nc, const double *d_in, double *d_out, std::size_t rank) {
+// one pass of the column-parallel path: columns [k0, k0 + nvalid) of the caller's blocks (row stride nrhs),
+// nc = 16 | 32 | 64 internal columns (zero padded), every factor streamed once
+static void apply_cols(Handle *h, unsigned nc, const double *d_B, double *d_X, unsigned nrhs, unsigned k0, unsigned nvalid,
+                       std::size_t rank) {
   const std::size_t nl = h->levels.size();
   ++h->epoch_m;
   const unsigned parity = h->epoch_m & 1u;
   HIF_CUDA(cudaMemsetAsync(h->tickets.p, 0, h->tickets.n * sizeof(int), h->stream));
   constexpr int T = 256;
-  const double *b = d_in;
+  const double *b = d_B;
+  unsigned      ldb = nrhs, kb = k0, nvb = nvalid;
   for (std::size_t l = 0; l < nl; ++l) {
     DevLevel &D = h->levels[l];
     if (D.n) {
-      gather_scale_m_kernel<<<cdiv(D.n * nc, T), T, 0, h->stream>>>(static_cast<unsigned>(D.n), nc, D.p.p, D.s.p, b,
-                                                                     D.m_bhat.p);
+      gather_scale_m_kernel<<<cdiv(D.n * nc, T), T, 0, h->stream>>>(static_cast<unsigned>(D.n), nc, D.p.p, D.s.p, b, ldb, kb,
+                                                                     nvb, D.m_bhat.p);
       HIF_KERNEL_CHECK();
       ++h->launch_count;
     }
     if (D.nm) {
-      if (D.m) {
-        launch_ws_sweep_mrhs(h, D.Lm, D.m_bhat.p, nullptr, nullptr, D.m_xL_dn.p, parity, h->tick(8 * l), nc);
-        launch_ws_sweep_mrhs(h, D.Um, nullptr, D.m_xL_dn.p, D.d_ls.p, D.m_xU_dn.p, parity, h->tick(8 * l + 1), nc);
-      }
+      if (D.m) launch_ws_sweep_cols(h, D.LU, D.m_bhat.p, D.d_ls.p, D.m_xL_dn.p, D.m_xU_dn.p, parity, h->tick(8 * l), nc);
       spmv_resid_m_kernel<true><<<cdiv(D.nm * nc, T), T, 0, h->stream>>>(
           static_cast<unsigned>(D.nm), nc, D.E.ptr.p, D.E_xcol.p, D.E.val.p, D.m_xU_dn.p,
           D.m_bhat.p + D.m * static_cast<std::size_t>(nc), D.m_r.p);
       HIF_KERNEL_CHECK();
       ++h->launch_count;
-      b = D.m_r.p;
+      b = D.m_r.p, ldb = nc, kb = 0u, nvb = nc;
     }
   }
   DevLevel &last = h->levels[nl - 1];
@@ -323,7 +299,7 @@ static void apply_wide(Handle *h, unsigned nc, const double *d_in, double *d_out
   }
   for (std::size_t l = nl; l-- > 0;) {
     DevLevel &    D   = h->levels[l];
-    double *      y   = l == 0 ? d_out : h->levels[l - 1].m_ychild.p;
+    double *      y   = l == 0 ? d_X : h->levels[l - 1].m_ychild.p;
     const double *rhs = D.m_bhat.p;
     if (D.nm && D.F.nnz && D.m) {
       spmv_resid_m_kernel<false><<<cdiv(D.m * nc, T), T, 0, h->stream>>>(
@@ -332,13 +308,11 @@ static void apply_wide(Handle *h, unsigned nc, const double *d_in, double *d_out
       ++h->launch_count;
       rhs = D.m_g.p;
     }
-    if (D.m) {
-      launch_ws_sweep_mrhs(h, D.Lm, rhs, nullptr, nullptr, D.m_xL_up.p, parity, h->tick(8 * l + 2), nc);
-      launch_ws_sweep_mrhs(h, D.Um, nullptr, D.m_xL_up.p, D.d_ls.p, D.m_xU_up.p, parity, h->tick(8 * l + 3), nc);
-    }
+    if (D.m) launch_ws_sweep_cols(h, D.LU, rhs, D.d_ls.p, D.m_xL_up.p, D.m_xU_up.p, parity, h->tick(8 * l + 2), nc);
     if (D.n) {
-      scatter_scale_ms_kernel<<<cdiv(D.n * nc, T), T, 0, h->stream>>>(static_cast<unsigned>(D.n), nc, D.q_slot.p, D.t.p,
-                                                                       D.m_xU_up.p, D.m_ychild.p, y);
+      scatter_scale_ms_kernel<<<cdiv(D.n * nc, T), T, 0, h->stream>>>(
+          static_cast<unsigned>(D.n), nc, D.q_slot.p, D.t.p, D.m_xU_up.p, D.m_ychild.p, y, l == 0 ? nrhs : nc,
+          l == 0 ? k0 : 0u, l == 0 ? nvalid : nc);
       HIF_KERNEL_CHECK();
       ++h->launch_count;
     }
@@ -351,40 +325,28 @@ void apply_mrhs_dev(Handle *h, std::size_t nrhs, const double *d_B, double *d_X,
     apply_dev(h, d_B, d_X, rank);
     return;
   }
-  static const int wide_max = [] {  // most columns per pass of the wide path (0: chunked path of 8 on stream plans)
+  static const int wide_max = [] {  // most columns per pass of the column-parallel path (0: passes of 8 on streaming plans)
     const char *e = std::getenv("HIFIR_B200_MRHS_WIDE");
-    return e ? std::atoi(e) : 0;
+    const int   w = e ? std::atoi(e) : 32;
+    return w >= 64 ? 64 : w >= 32 ? 32 : w >= 16 ? 16 : 0;
   }();
-  if (wide_max >= 8 && !h->levels.empty() && (h->levels[0].L.ws || !h->levels[0].m)) {
-    // warp-stream plans: the whole block in one pass (columns padded to a multiple of 8); a block whose
-    // width is a multiple of 8 is read and written in place, in the caller's row-interleaved layout
-    bool all_ws = true;
-    for (const DevLevel &D : h->levels) all_ws = all_ws && (D.L.ws || !D.m);
-    if (all_ws) {
-      const std::size_t n  = h->n0();
-      const unsigned    nc = static_cast<unsigned>((nrhs + 7u) & ~static_cast<std::size_t>(7u));
-      if (static_cast<unsigned long long>(n) * nc > 0xffffffffull * 8ull) throw std::length_error("multi-rhs block too large");
-      ensure_wide(h, nc);
-      constexpr int T = 256;
-      try {
-        if (nc == nrhs) {
-          apply_wide(h, nc, d_B, d_X, rank);
-        } else {
-          pad_cols_kernel<<<cdiv(n * nc, T), T, 0, h->stream>>>(static_cast<unsigned>(n), static_cast<unsigned>(nrhs), nc,
-                                                               d_B, h->mr_b.p);
-          HIF_KERNEL_CHECK();
-          apply_wide(h, nc, h->mr_b.p, h->mr_x.p, rank);
-          unpad_cols_kernel<<<cdiv(n * nrhs, T), T, 0, h->stream>>>(static_cast<unsigned>(n), static_cast<unsigned>(nrhs),
-                                                                   nc, h->mr_x.p, d_X);
-          HIF_KERNEL_CHECK();
-          h->launch_count += 2;
-        }
-      } catch (...) {
-        reset_tagged_state(h);
-        throw;
-      }
-      return;
+  bool fused = wide_max > 0 && !h->levels.empty();
+  for (const DevLevel &D : h->levels) fused = fused && (!D.m || (D.LU.nblocks && D.LU.ws_warps == 24u && D.LU.ws_stages == 2u));
+  if (fused) {
+    const std::size_t n = h->n0();
+    // one internal width per call: the widest pass that the block fills (narrow blocks: 16 columns)
+    const unsigned nc = nrhs >= 64u && wide_max >= 64 ? 64u : nrhs > 16u && wide_max >= 32 ? 32u : 16u;
+    if (static_cast<unsigned long long>(n) * std::max<std::size_t>(nc, nrhs) > 0xffffffffull) throw std::length_error("multi-rhs block too large");
+    ensure_cols(h, nc);
+    try {
+      for (std::size_t k0 = 0; k0 < nrhs; k0 += nc)
+        apply_cols(h, nc, d_B, d_X, static_cast<unsigned>(nrhs), static_cast<unsigned>(k0),
+                   static_cast<unsigned>(std::min<std::size_t>(nc, nrhs - k0)), rank);
+    } catch (...) {
+      reset_tagged_state(h);
+      throw;
     }
+    return;
   }
   ensure_mrhs(h);
   const std::size_t n = h->n0();

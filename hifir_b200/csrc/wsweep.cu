@@ -32,6 +32,7 @@
 #include <cstring>
 #include <numeric>
 #include <string>
+#include <type_traits>
 
 #include "hifgpu.h"
 
@@ -856,7 +857,12 @@ __global__ void __launch_bounds__(kWarps * 32, 1) wsweep_kernel(const WsParams P
       for (unsigned o = lpr >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
       if (own) ws_publish(xw + slot, tag_set(acc, parity), P.publish_st);
     }
-    refill(stage, hd.y + (acc == 1.2345e300 ? 1u : 0u));  // (the refill depends on acc: see above)
+    {
+      // the refill must depend on acc (see above) WITHOUT changing its size: choose between the header
+      // word and a second, volatile read of the same word -- equal values the compiler can not prove equal
+      const unsigned y2 = *reinterpret_cast<const volatile unsigned *>(sg + 1);
+      refill(stage, acc == 1.2345e300 ? y2 : hd.y);
+    }
     have_cur = have_nxt;
     if (have_nxt) {
 #pragma unroll
@@ -875,27 +881,40 @@ __global__ void __launch_bounds__(kWarps * 32, 1) wsweep_kernel(const WsParams P
   }
 }
 
-// ---- multi-rhs: the same warp streams, all right-hand sides in ONE pass over the factor -----------
-// Row-interleaved blocks X[slot * nc + c] (the Array<std::array<T,Nrhs>> layout of
+// ---- multi-rhs: the same warp streams, lanes ACROSS the columns -------------------------------
+// Row-interleaved blocks X[slot * NC + c] (the Array<std::array<T,Nrhs>> layout of
 // hif::HIF::solve_mrhs, builder.hpp:433-445; per-column arithmetic = CCS::solve_as_strict_lower /
-// _upper_mrhs, CompressedStorage.hpp:2286-2301, 2376-2393).  nc is a multiple of 8; a segment sits in
-// its ring stage while the warp loops over the column GROUPS of 8: per group a dependency is one
-// 64-byte gather (two sectors for eight values), a lane keeps 8 accumulators, and the factor is read
-// from HBM once for all nc columns (round 1 re-streamed it for every 8).
-__device__ __forceinline__ void ws_ld_poll8(const unsigned long long *p, unsigned long long (&v)[8]) {
-#pragma unroll
-  for (int q = 0; q < 8; q += 2)
-    asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(v[q]), "=l"(v[q + 1]) : "l"(p + q) : "memory");
+// _upper_mrhs, CompressedStorage.hpp:2286-2301, 2376-2393).  NC = 2 G columns, G in {8, 16, 32}.
+//
+// The single-rhs kernel gives every lane its own entries: 32 scattered 8-byte gathers per instruction,
+// one L1 wavefront each -- that is its throughput bound.  With NC columns the unit of dependency is a
+// ROW of NC values: G consecutive lanes own the columns (two each, one 16-byte load), so one gather
+// instruction moves 32 / G whole rows of 16 G bytes -- full 128-byte lines, 4 wavefronts for 512 bytes
+// instead of 32 for 256.  Consequently:
+//   * lane group grp = lane / G works on one row of the segment at a time (a row's entry slots are
+//     walked serially: the sum over the entries needs no shuffle), 32 / G rows side by side, two rows
+//     per group in flight (RIF) with B entries each;
+//   * a segment with fewer rows than groups (long rows: 2^z lanes per row in the single-rhs layout)
+//     splits each row's entry slots over K groups and adds the K partial sums with shuffles;
+//   * the packed streams, the tags, the sentinel admission and the ring refill are those of
+//     wsweep_kernel MODE 2 (fused L-then-U plan): one launch per LDU solve for all NC columns, the
+//     factor is read from HBM once per NC columns.
+__device__ __forceinline__ void ws_ld_poll2(const unsigned long long *p, unsigned long long &a, unsigned long long &b) {
+  asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
 }
-__device__ __forceinline__ bool ws_ready8(const unsigned long long (&v)[8], unsigned parity) {
-  unsigned bad = 0;
-#pragma unroll
-  for (int q = 0; q < 8; ++q) bad |= static_cast<unsigned>(v[q]) ^ parity;
-  return !(bad & 1u);
+__device__ __forceinline__ void ws_st_publish2(unsigned long long *p, unsigned long long a, unsigned long long b) {
+  asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(a), "l"(b) : "memory");
+}
+__device__ __forceinline__ bool ws_ready2(unsigned long long a, unsigned long long b, unsigned parity) {
+  return !(((static_cast<unsigned>(a) ^ parity) | (static_cast<unsigned>(b) ^ parity)) & 1u);
 }
 
-template <bool UPPER, class VT, int kWarps, int kStages>
-__global__ void __launch_bounds__(kWarps * 32, 1) wsweep_mrhs_kernel(const WsParams P, const unsigned nc) {
+template <class VT, int G>
+__global__ void __launch_bounds__(24 * 32, 1) wsweep_cols_kernel(const WsParams P) {
+  constexpr int      kWarps = 24, kStages = 2;
+  constexpr unsigned NC = 2u * G, EPI = 32u / G;  // columns; rows (or row parts) per gather instruction
+  constexpr unsigned B = 4u;                      // entries of a row in flight per lane (a second row in flight
+                                                  // spills registers -- 85 per thread at 24 warps -- and measured slower)
   constexpr unsigned kStageBytes = (kWsHdrWords + 64u + kWsU * 32u * (sizeof(VT) == 4 ? 2u : 3u)) * 4u;
   extern __shared__ __align__(128) unsigned char smem[];
   const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
@@ -920,8 +939,35 @@ __global__ void __launch_bounds__(kWarps * 32, 1) wsweep_mrhs_kernel(const WsPar
       }
   }
   __syncwarp();
-  const unsigned parity = P.parity, ngroups = nc >> 3;
+  const unsigned parity = P.parity;
+  const unsigned grp = lane / G, cp = (lane % G) * 2u;  // lane group; first of this lane's two columns
   unsigned       my_front = 0;
+  // right-hand side of a row: b (L segments) or the L sweep's tagged result divided by d (U segments)
+  auto rhs_issue = [&](bool upper, unsigned r, unsigned long long &t0, unsigned long long &t1, double &dg) {
+    if (upper) {
+      ws_ld_poll2(P.x + static_cast<std::size_t>(r) * NC + cp, t0, t1);
+      dg = P.diag[r];
+    } else {
+      const double2 v = *reinterpret_cast<const double2 *>(P.rhs_plain + static_cast<std::size_t>(r) * NC + cp);
+      t0 = static_cast<unsigned long long>(__double_as_longlong(v.x));
+      t1 = static_cast<unsigned long long>(__double_as_longlong(v.y));
+    }
+  };
+  auto rhs_finish = [&](bool upper, unsigned r, unsigned long long t0, unsigned long long t1, double dg, double &a0,
+                        double &a1, unsigned k, unsigned level) {
+    if (upper) {
+      for (unsigned spins = 0; !ws_ready2(t0, t1, parity); ws_ld_poll2(P.x + static_cast<std::size_t>(r) * NC + cp, t0, t1))
+        if (++spins > P.spin_limit || ((spins & 255u) == 255u && ws_aborted(P))) {
+          if (!ws_aborted(P)) ws_fail(P, gw, k, level, 3, r);
+          break;
+        }
+      a0 = tag_value(t0) / dg;  // true division (prec_solve.hpp:219)
+      a1 = tag_value(t1) / dg;
+    } else {
+      a0 = __longlong_as_double(static_cast<long long>(t0));
+      a1 = __longlong_as_double(static_cast<long long>(t1));
+    }
+  };
   for (unsigned k = 0; k < nseg; ++k) {
     const unsigned stage = k % kStages, phase = (k / kStages) & 1u;
     {
@@ -941,57 +987,44 @@ __global__ void __launch_bounds__(kWarps * 32, 1) wsweep_mrhs_kernel(const WsPar
     const unsigned *sg    = reinterpret_cast<const unsigned *>(ring + stage * kStageBytes);
     const uint4     hd    = *reinterpret_cast<const uint4 *>(sg);
     const unsigned  width = hd.x & 0xffu, z = (hd.x >> 8) & 0xffu, flags = hd.x >> 16;
-    unsigned        keep  = 0;  // consumed before the refill: every shared-memory read of the stage has returned
+    const bool      upper = (flags & kSegUpper) != 0u;
+    unsigned long long *const xw = upper ? P.x2 : P.x;  // this factor's solution
+    unsigned keep = 0;  // digest of everything read from the stage: the refill below depends on it
     if (flags & kSegCopy) {
-      for (unsigned u = 0; u < width; ++u) {
-        const unsigned code = sg[kWsHdrWords + u * 32u + lane], slot = sg[kWsHdrWords + (width + u) * 32u + lane];
-        keep ^= code + slot;
-        if (slot == kWsNone) continue;
-        const unsigned r = code & kCodeSlotMask;
-        for (unsigned cg = 0; cg < ngroups; ++cg) {
-          unsigned long long v[8];
-          if (code & kCodeZeroRhs) {
+      // rows without entries: x = rhs; width * 32 rows, four per lane group in flight
+      const unsigned nrows = width * 32u;
+      for (unsigned r0 = 0; r0 < nrows; r0 += EPI * 4u) {
+        unsigned           code[4], slot[4];
+        unsigned long long t0[4], t1[4];
+        double             dg[4];
 #pragma unroll
-            for (int q = 0; q < 8; ++q) v[q] = tag_set(0.0, parity);
-          } else if (UPPER) {
-            const unsigned long long *rp = P.rhs_tagged + static_cast<std::size_t>(r) * nc + cg * 8u;
-            ws_ld_poll8(rp, v);
-            for (unsigned spins = 0; !ws_ready8(v, parity); ws_ld_poll8(rp, v))
-              if (++spins > P.spin_limit || ((spins & 255u) == 255u && ws_aborted(P))) {
-                if (!ws_aborted(P)) ws_fail(P, gw, k, hd.w, 3, r);
-                break;
-              }
-            const double dg = P.diag[r];
-#pragma unroll
-            for (int q = 0; q < 8; ++q) v[q] = tag_set(tag_value(v[q]) / dg, parity);
-          } else {
-            const double *rp = P.rhs_plain + static_cast<std::size_t>(r) * nc + cg * 8u;
-#pragma unroll
-            for (int q = 0; q < 8; ++q) v[q] = tag_set(rp[q], parity);
-          }
-          unsigned long long *xp = P.x + static_cast<std::size_t>(slot) * nc + cg * 8u;
-#pragma unroll
-          for (int q = 0; q < 8; q += 2)
-            asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"(xp + q), "l"(v[q]), "l"(v[q + 1]) : "memory");
+        for (unsigned j = 0; j < 4; ++j) {
+          const unsigned row = r0 + j * EPI + grp;
+          code[j]            = sg[kWsHdrWords + row];
+          slot[j]            = sg[kWsHdrWords + nrows + row];
+          keep ^= code[j] + slot[j];
+          t0[j] = t1[j] = 0ull;
+          dg[j]         = 1.0;
+          if (slot[j] != kWsNone && !(code[j] & kCodeZeroRhs)) rhs_issue(upper, code[j] & kCodeSlotMask, t0[j], t1[j], dg[j]);
         }
+#pragma unroll
+        for (unsigned j = 0; j < 4; ++j)
+          if (slot[j] != kWsNone) {
+            double a0 = 0.0, a1 = 0.0;
+            if (!(code[j] & kCodeZeroRhs)) rhs_finish(upper, code[j] & kCodeSlotMask, t0[j], t1[j], dg[j], a0, a1, k, hd.w);
+            ws_st_publish2(xw + static_cast<std::size_t>(slot[j]) * NC + cp, tag_set(a0, parity), tag_set(a1, parity));
+          }
       }
     } else {
-      unsigned cc[kWsU];
-#pragma unroll
-      for (unsigned u = 0; u < kWsU; ++u) {
-        cc[u] = kWsNone;
-        if (u < width) cc[u] = sg[kWsHdrWords + 64u + u * 32u + lane];
-      }
-      const unsigned code = sg[kWsHdrWords + lane], slot = sg[kWsHdrWords + 32u + lane];
-      const unsigned lpr = 1u << z;
-      const bool     own = slot != kWsNone && (lane & (lpr - 1u)) == 0u;
-      const bool     want_r = (flags & kSegFirst) && own && !(code & kCodeZeroRhs);
-      const unsigned r = code & kCodeSlotMask;
+      const unsigned lpr = 1u << z, R = 32u >> z;    // lanes per row of the single-rhs layout; rows
+      const unsigned Rg  = R < EPI ? R : EPI;        // rows the lane groups work on side by side
+      const unsigned K   = EPI / Rg;                 // lane groups that share one row
+      const unsigned sub = grp % Rg, part = grp / Rg;
       if (hd.z != kWsNone) {  // admission of a warp that jumps ahead (throttle only)
         if (lane == 0) {
           unsigned       spins = 0;
           const unsigned need  = hd.w - P.window;
-          while (!tag_ready(ld_poll(P.x + static_cast<std::size_t>(hd.z) * nc), parity)) {
+          while (!tag_ready(ld_poll(xw + static_cast<std::size_t>(hd.z) * NC), parity)) {
             const unsigned f = static_cast<unsigned>(ws_ld_poll_i32(P.sync));
             if (need > f + 4u) __nanosleep(min((need - f) * P.adm_sleep, 20000u));
             if (++spins > P.spin_limit || ((spins & 63u) == 63u && ws_aborted(P))) {
@@ -1002,104 +1035,132 @@ __global__ void __launch_bounds__(kWarps * 32, 1) wsweep_mrhs_kernel(const WsPar
         }
         __syncwarp();
       }
-      const VT *sv = reinterpret_cast<const VT *>(sg + kWsHdrWords + 64u + width * 32u);
-      for (unsigned cg = 0; cg < ngroups; ++cg) {
-        double acc[8];
+      const unsigned *sc    = sg + kWsHdrWords + 64u;
+      const VT *      sv    = reinterpret_cast<const VT *>(sc + width * 32u);
+      const bool      first = (flags & kSegFirst) != 0u, last = (flags & kSegLast) != 0u;
+      // The entry slots of a row are walked in batches of B = 4, addressed by a running pointer and
+      // compile-time offsets.  Four layouts (word of entry u of lane l of the row: u * 32 + first lane + l):
+      //   CLS 0  one lane per row: slots u = 0 .. width-1, 32 words apart              (batch: +128 words)
+      //   CLS 1  two lanes per row: (u, l) = (0,0) (0,1) (1,0) (1,1) ...               (batch: +64 words)
+      //   CLS 2  4+ lanes per row, one lane group per row: consecutive lanes, then the next u
+      //   CLS 3  K lane groups share the row: every K-th lane (the partial sums are added below)
+      auto run = [&](auto cls_tag) {
+        constexpr unsigned CLS = decltype(cls_tag)::value;
+        for (unsigned r0 = 0; r0 < R; r0 += Rg) {
+          const unsigned ol   = (r0 + sub) << z;  // the row's first lane in the single-rhs layout
+          const unsigned code = sg[kWsHdrWords + ol], slot = sg[kWsHdrWords + 32u + ol];
+          keep ^= code + slot;
+          const bool live = slot != kWsNone, head = live && part == 0u;
+          const bool want = head && first && !(code & kCodeZeroRhs);
+          double     a0 = 0.0, a1 = 0.0, dg = 1.0;
+          unsigned long long t0 = 0ull, t1 = 0ull;
+          if (want)
+            rhs_issue(upper, code & kCodeSlotMask, t0, t1, dg);
+          else if (head && !first)
+            // continuation of a slice of several segments (rows beyond 256 entries): the partial sums
+            // were parked in the row's own slot under the OTHER tag (nobody consumes them)
+            ws_ld_poll2(xw + static_cast<std::size_t>(slot) * NC + cp, t0, t1);
+          // gathered rows; a slot without entry keeps an older (finite) row and meets the value 0.0
+          unsigned long long g0[B] = {0ull, 0ull, 0ull, 0ull}, g1[B] = {0ull, 0ull, 0ull, 0ull};
+          bool               firstb = true;
+          auto batch = [&](const unsigned *pc, const VT *pv, unsigned rem) {  // rem: slots left (CLS 0, 1)
+            unsigned col[B];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) acc[q] = 0.0;
-        unsigned long long *xs = P.x + static_cast<std::size_t>(slot) * nc + cg * 8u;  // this row, this group
-        if (flags & kSegFirst) {
-          if (want_r) {
-            if (UPPER) {
-              const unsigned long long *rp = P.rhs_tagged + static_cast<std::size_t>(r) * nc + cg * 8u;
-              unsigned long long        t[8];
-              ws_ld_poll8(rp, t);
-              for (unsigned spins = 0; !ws_ready8(t, parity); ws_ld_poll8(rp, t))
-                if (++spins > P.spin_limit || ((spins & 255u) == 255u && ws_aborted(P))) {
-                  if (!ws_aborted(P)) ws_fail(P, gw, k, hd.w, 3, r);
+            for (unsigned j = 0; j < B; ++j) {
+              const unsigned off = CLS == 0u ? j * 32u : CLS == 1u ? (j >> 1) * 32u + (j & 1u) : CLS == 2u ? j : j * K;
+              col[j]             = kWsNone;
+              if ((CLS >= 2u || j < rem) && live) col[j] = pc[off];
+              if (col[j] != kWsNone) ws_ld_poll2(xw + static_cast<std::size_t>(col[j]) * NC + cp, g0[j], g1[j]);
+            }
+            unsigned bad = 0;
+#pragma unroll
+            for (unsigned j = 0; j < B; ++j)
+              bad |= col[j] != kWsNone ? (static_cast<unsigned>(g0[j]) ^ parity) | (static_cast<unsigned>(g1[j]) ^ parity) : 0u;
+            if (__any_sync(0xffffffffu, (bad & 1u) != 0u)) {  // rare: some row was not published yet
+              unsigned pend = 0;
+#pragma unroll
+              for (unsigned j = 0; j < B; ++j)
+                if (col[j] != kWsNone && !ws_ready2(g0[j], g1[j], parity)) pend |= 1u << j;
+              for (unsigned rounds = 0; __any_sync(0xffffffffu, pend != 0u);) {
+#pragma unroll
+                for (unsigned j = 0; j < B; ++j)
+                  if (pend & (1u << j)) {
+                    ws_ld_poll2(xw + static_cast<std::size_t>(col[j]) * NC + cp, g0[j], g1[j]);
+                    if (ws_ready2(g0[j], g1[j], parity)) pend &= ~(1u << j);
+                  }
+                if (++rounds > P.spin_limit || ((rounds & 255u) == 255u && ws_aborted(P))) {
+                  if (pend && !ws_aborted(P)) ws_fail(P, gw, k, hd.w, 1, slot);
                   break;
                 }
-              const double dg = P.diag[r];
-#pragma unroll
-              for (int q = 0; q < 8; ++q) acc[q] = tag_value(t[q]) / dg;  // true division (prec_solve.hpp:219)
-            } else {
-              const double *rp = P.rhs_plain + static_cast<std::size_t>(r) * nc + cg * 8u;
-#pragma unroll
-              for (int q = 0; q < 8; ++q) acc[q] = rp[q];
-            }
-          }
-        } else if (own) {
-          // continuation of a slice of several segments (rows beyond 256 entries): the partial sums
-          // were parked in the row's own slot under the OTHER tag (nobody consumes them)
-#pragma unroll
-          for (int q = 0; q < 8; ++q) acc[q] = tag_value(ld_poll(xs + q));
-        }
-        // entries four at a time: 4 x 64-byte gathers in flight per lane
-#pragma unroll
-        for (unsigned u0 = 0; u0 < kWsU; u0 += 4) {
-          if (u0 >= width) break;
-          unsigned long long        gg[4][8];
-          const unsigned long long *pp[4];
-          bool                      has[4], pend[4];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            has[j] = (u0 + j < width) && cc[u0 + j] != kWsNone;
-            pp[j]  = P.x + static_cast<std::size_t>(has[j] ? cc[u0 + j] : 0u) * nc + cg * 8u;
-          }
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-            if (has[j]) ws_ld_poll8(pp[j], gg[j]);
-          bool any = false;
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            pend[j] = has[j] && !ws_ready8(gg[j], parity);
-            any |= pend[j];
-          }
-          for (unsigned rounds = 0; __any_sync(0xffffffffu, any);) {
-            any = false;
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              if (pend[j]) {
-                ws_ld_poll8(pp[j], gg[j]);
-                pend[j] = !ws_ready8(gg[j], parity);
-                any |= pend[j];
               }
-            if (++rounds > P.spin_limit || ((rounds & 255u) == 255u && ws_aborted(P))) {
-              if (any && !ws_aborted(P)) ws_fail(P, gw, k, hd.w, 1, cc[u0]);
-              break;
+            }
+            if (firstb) {  // the right-hand side (parked sum) travelled with the first batch of gathers
+              firstb = false;
+              if (want) {
+                rhs_finish(upper, code & kCodeSlotMask, t0, t1, dg, a0, a1, k, hd.w);
+              } else if (head && !first) {
+                a0 = tag_value(t0);
+                a1 = tag_value(t1);
+              }
+            }
+#pragma unroll
+            for (unsigned j = 0; j < B; ++j) {
+              const unsigned off = CLS == 0u ? j * 32u : CLS == 1u ? (j >> 1) * 32u + (j & 1u) : CLS == 2u ? j : j * K;
+              double         v   = 0.0;  // (beyond the row's slots the stage holds other data: never read)
+              if (CLS >= 2u || j < rem) v = static_cast<double>(pv[off]);
+              a0 = fma(-v, tag_value(g0[j]), a0);
+              a1 = fma(-v, tag_value(g1[j]), a1);
+            }
+          };
+          if (CLS == 0u) {
+            const unsigned *pc = sc + ol;
+            const VT *      pv = sv + ol;
+            for (unsigned t = 0; t < width; t += B, pc += 4u * 32u, pv += 4u * 32u) batch(pc, pv, width - t);
+          } else if (CLS == 1u) {
+            const unsigned *pc = sc + ol;
+            const VT *      pv = sv + ol;
+            for (unsigned t = 0; t < 2u * width; t += B, pc += 2u * 32u, pv += 2u * 32u) batch(pc, pv, 2u * width - t);
+          } else {
+            const unsigned step = CLS == 2u ? B : B * K, nb = lpr / step;  // batches per entry index u
+            for (unsigned u = 0; u < width; ++u) {
+              const unsigned *pc = sc + u * 32u + ol + part;
+              const VT *      pv = sv + u * 32u + ol + part;
+              for (unsigned b = 0; b < nb; ++b, pc += step, pv += step) batch(pc, pv, B);
             }
           }
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-            if (u0 + j < width) {
-              const double v = static_cast<double>(sv[(u0 + j) * 32u + lane]);
-#pragma unroll
-              for (int q = 0; q < 8; ++q) acc[q] = fma(-v, has[j] ? tag_value(gg[j][q]) : 0.0, acc[q]);
+          if (CLS == 3u) {  // the lane groups that shared a row add their partial sums
+            for (unsigned o = Rg * G; o < 32u; o <<= 1) {
+              a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+              a1 += __shfl_xor_sync(0xffffffffu, a1, o);
             }
+          }
+          if (head) {
+            const unsigned tag = last ? parity : (parity ^ 1u);  // parked partial sums: the other tag
+            ws_st_publish2(xw + static_cast<std::size_t>(slot) * NC + cp, tag_set(a0, tag), tag_set(a1, tag));
+          }
+          keep ^= static_cast<unsigned>(__double2hiint(a0));
         }
-        for (unsigned o = lpr >> 1; o > 0; o >>= 1) {
-#pragma unroll
-          for (int q = 0; q < 8; ++q) acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], o);
-        }
-        if (own) {
-          const unsigned tag = (flags & kSegLast) ? parity : (parity ^ 1u);  // parked partial sums: the other tag
-#pragma unroll
-          for (int q = 0; q < 8; q += 2)
-            asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"(xs + q), "l"(tag_set(acc[q], tag)),
-                         "l"(tag_set(acc[q + 1], tag))
-                         : "memory");
-        }
-        keep ^= __double2hiint(acc[0]);
-      }
-      keep ^= code + slot;
+      };
+      if (z == 0u)
+        run(std::integral_constant<unsigned, 0u>());
+      else if (z == 1u)
+        run(std::integral_constant<unsigned, 1u>());
+      else if (K == 1u)
+        run(std::integral_constant<unsigned, 2u>());
+      else
+        run(std::integral_constant<unsigned, 3u>());
     }
+    // refill after everything read from the stage was used: the size depends on the digest without being
+    // changed by it (two reads of the same header word the compiler can not prove equal)
+    const unsigned y2     = *reinterpret_cast<const volatile unsigned *>(sg + 1);
+    const unsigned size16 = keep == 0x12345678u ? y2 : hd.y;
     __syncwarp();
-    if (lane == 0 && (hd.y + (keep == 0x12345678u ? 1u : 0u))) {  // refill after everything read from the stage was used
-      ws_mbar_expect_tx(bar0 + stage * 8u, hd.y * 16u);
-      ws_tma_g2s(ws_smem_addr(ring + stage * kStageBytes), src, hd.y * 16u, bar0 + stage * 8u, policy);
-      src += static_cast<std::size_t>(hd.y) * 16u;
+    if (lane == 0 && size16) {
+      ws_mbar_expect_tx(bar0 + stage * 8u, size16 * 16u);
+      ws_tma_g2s(ws_smem_addr(ring + stage * kStageBytes), src, size16 * 16u, bar0 + stage * 8u, policy);
+      src += static_cast<std::size_t>(size16) * 16u;
     }
-    if (lane == 0 && (flags & kSegLast) && hd.w > my_front + 3u) {
+    if (lane == 0 && hd.w > my_front + 3u) {
       my_front = hd.w;
       atomicMax(P.sync, static_cast<int>(hd.w));
     }
@@ -1260,36 +1321,46 @@ void launch_ws_V(Handle *h, const SweepPlan &plan, const WsParams &P) {
 }  // namespace
 
 namespace {
-template <bool UPPER, class VT>
-void launch_ws_mrhs_V(Handle *h, const SweepPlan &plan, const WsParams &P, unsigned nc) {
-  // the multi-rhs kernel keeps 8 accumulators and 2 x 8 gathered words per lane: 16 warps x 4 stages
-  constexpr int      kWarps = 16, kStages = 4;
+template <class VT, int G>
+void launch_ws_cols_G(Handle *h, const SweepPlan &plan, const WsParams &P) {
   constexpr unsigned kStageBytes = (kWsHdrWords + 64u + kWsU * 32u * (sizeof(VT) == 4 ? 2u : 3u)) * 4u;
-  constexpr unsigned smem        = kWarps * kStages * (8u + kStageBytes);
-  auto               kern        = wsweep_mrhs_kernel<UPPER, VT, kWarps, kStages>;
+  constexpr unsigned smem        = 24u * 2u * (8u + kStageBytes);
+  auto               kern        = wsweep_cols_kernel<VT, G>;
   static bool        configured[64] = {false};
-  if (h->device < 64 && !configured[h->device]) {
+  if (h->device >= 64 || !configured[h->device]) {
     HIF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    configured[h->device] = true;
+    if (h->device < 64) configured[h->device] = true;
   }
-  kern<<<plan.ws_grid, kWarps * 32, smem, h->stream>>>(P, nc);
+  kern<<<plan.ws_grid, 24 * 32, smem, h->stream>>>(P);
+}
+template <class VT>
+void launch_ws_cols_V(Handle *h, const SweepPlan &plan, const WsParams &P, unsigned nc) {
+  if (nc == 16u)
+    launch_ws_cols_G<VT, 8>(h, plan, P);
+  else if (nc == 32u)
+    launch_ws_cols_G<VT, 16>(h, plan, P);
+  else if (nc == 64u)
+    launch_ws_cols_G<VT, 32>(h, plan, P);
+  else
+    throw std::logic_error("multi-rhs sweep: 16, 32 or 64 columns per pass");
 }
 }  // namespace
 
-// multi-rhs sweep on a warp-stream plan built for 16 warps x 4 stages (build_ws_plan_mrhs)
-void launch_ws_sweep_mrhs(Handle *h, const SweepPlan &plan, const double *rhs_plain, const unsigned long long *rhs_tagged,
-                          const double *diag, unsigned long long *x, unsigned parity, int *sync, unsigned nc) {
+// multi-rhs LDU solve on the fused warp-stream plan of a level: nc in {16, 32, 64} columns, row-interleaved
+void launch_ws_sweep_cols(Handle *h, const SweepPlan &plan, const double *rhs_plain, const double *diag, unsigned long long *xL,
+                          unsigned long long *xU, unsigned parity, int *sync, unsigned nc) {
   if (!plan.nblocks) return;
-  if (plan.ws_warps != 16u || plan.ws_stages != 4u || (nc & 7u)) throw std::logic_error("multi-rhs warp-stream plan mismatch");
+  if (!plan.fused || plan.ws_warps != 24u || plan.ws_stages != 2u)
+    throw std::logic_error("multi-rhs sweep needs the fused 24 x 2 warp-stream plan");
   WsParams P;
   P.trace      = nullptr;
-  P.x2         = nullptr;
   P.wdesc      = plan.ws_wdesc.p;
   P.stream     = plan.ws_stream.p;
   P.rhs_plain  = rhs_plain;
-  P.rhs_tagged = rhs_tagged;
+  P.rhs_tagged = nullptr;
   P.diag       = diag;
-  P.x          = x;
+  P.x          = xL;
+  P.x2         = xU;
   P.sync       = sync;
   P.error_flag = h->error_flag.p;
   P.parity     = parity;
@@ -1298,11 +1369,10 @@ void launch_ws_sweep_mrhs(Handle *h, const SweepPlan &plan, const double *rhs_pl
   P.publish_st = 1;
   P.l1_first   = 0;
   P.spin_limit = static_cast<unsigned>(std::max(1000, ws_env("HIFIR_B200_WS_SPIN_LIMIT", 1 << 21)));
-  if (plan.upper) {
-    if (plan.f32) launch_ws_mrhs_V<true, float>(h, plan, P, nc); else launch_ws_mrhs_V<true, double>(h, plan, P, nc);
-  } else {
-    if (plan.f32) launch_ws_mrhs_V<false, float>(h, plan, P, nc); else launch_ws_mrhs_V<false, double>(h, plan, P, nc);
-  }
+  if (plan.f32)
+    launch_ws_cols_V<float>(h, plan, P, nc);
+  else
+    launch_ws_cols_V<double>(h, plan, P, nc);
   HIF_KERNEL_CHECK();
   ++h->launch_count;
 }

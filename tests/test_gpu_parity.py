@@ -169,9 +169,10 @@ def test_mrhs_is_column_loop_of_solves(golden):
         assert relerr(X3, ref[:, :3]) <= TOL_F64
 
 
-@pytest.mark.parametrize("nrhs", [8, 11, 16])
+@pytest.mark.parametrize("nrhs", [8, 11, 16, 20, 33, 64, 70])
 def test_mrhs_batched_widths(nrhs):
-    """Batched kernel (8 columns per pass): full, ragged and multiple chunks vs the C oracle."""
+    """Batched kernel (passes of 16 / 32 / 64 columns, lanes across the columns): full, ragged and several
+    passes vs the C oracle."""
     g = load_golden("stokes28_ml")
     B = P.seeded_rhs(g.n, 100, nrhs=nrhs)
     ref = O.OracleHif(g.levels).solve_mrhs(B)
@@ -181,6 +182,20 @@ def test_mrhs_batched_widths(nrhs):
             assert relerr(X[:, k], ref[:, k]) <= TOL_F64, k
         # the single-rhs path afterwards still works on the same handle (shared tickets / epochs)
         assert relerr(G.solve(np.ascontiguousarray(B[:, 0])), ref[:, 0]) <= TOL_F64
+
+
+def test_mrhs_width_changes_on_one_handle():
+    """The tagged multi-rhs work vectors are laid out for one pass width: a handle that is given blocks of
+    different widths (64 -> 16 -> 32 -> 64 columns per pass) must re-zero them (stale tags of an older layout)."""
+    g = load_golden("stokes28_ml")
+    Oh = O.OracleHif(g.levels)
+    with hb.GpuHif(g.levels) as G:
+        for rep, nrhs in enumerate([70, 5, 70, 24, 64, 3, 3, 64]):
+            B = P.seeded_rhs(g.n, 200 + rep, nrhs=nrhs)
+            X = G.solve_mrhs(B)
+            ref = Oh.solve_mrhs(B)
+            for k in range(nrhs):
+                assert relerr(X[:, k], ref[:, k]) <= TOL_F64, (rep, nrhs, k)
 
 
 def test_spmv_and_errors(golden):

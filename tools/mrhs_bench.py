@@ -19,9 +19,12 @@ def main():
     A, levels = cached_levels(workload, size)
     n = A[0]
     G = hb.GpuHif(levels)
-    G.set_stream(torch.cuda.current_stream().cuda_stream)
+    side = torch.cuda.Stream()
+    torch.cuda.set_stream(side)
+    G.set_stream(side.cuda_stream)
     st = G.stats()
-    for nrhs in (1, 8, 16, 64):
+    print("HIFIR_B200_MRHS_WIDE", os.environ.get("HIFIR_B200_MRHS_WIDE"), "HIFIR_B200_MRHS_RIF", os.environ.get("HIFIR_B200_MRHS_RIF"))
+    for nrhs in (1, 16, 32, 64):
         B = torch.from_numpy(P.seeded_rhs(n, 0, nrhs=nrhs)).cuda() if nrhs > 1 else torch.from_numpy(P.seeded_rhs(n, 0)).cuda()
         X = torch.empty_like(B)
         for _ in range(2):
@@ -39,15 +42,19 @@ def main():
         bytes_apply = st["bytes_factors"] + st["bytes_dense"] + nrhs * st["bytes_vec_per_rhs"]
         print(f"{workload} {size} nrhs={nrhs}: {ms:.3f} ms per block apply = {nrhs / ms * 1e3:.0f} column-applies/s; "
               f"algorithmic {bytes_apply / 1e9:.2f} GB -> {bytes_apply / ms / 1e6:.0f} GB/s")
-    # parity of one column against a single-rhs apply
-    B = torch.from_numpy(P.seeded_rhs(n, 0, nrhs=16)).cuda()
-    X = torch.empty_like(B)
-    G.solve_mrhs_dev(16, B.data_ptr(), X.data_ptr())
-    b5 = B[:, 5].contiguous()
-    x5 = torch.empty_like(b5)
-    G.solve_dev(b5.data_ptr(), x5.data_ptr())
-    G.synchronize()
-    print("column 5 vs single-rhs apply:", float((X[:, 5] - x5).norm() / x5.norm()))
+    # parity of some columns against single-rhs applies
+    for nrhs in (16, 64, 70):
+        B = torch.from_numpy(P.seeded_rhs(n, 0, nrhs=nrhs)).cuda()
+        X = torch.empty_like(B)
+        G.solve_mrhs_dev(nrhs, B.data_ptr(), X.data_ptr())
+        errs = []
+        for c in (0, 5, nrhs // 2 + 1, nrhs - 1):
+            bc = B[:, c].contiguous()
+            xc = torch.empty_like(bc)
+            G.solve_dev(bc.data_ptr(), xc.data_ptr())
+            G.synchronize()
+            errs.append(float((X[:, c] - xc).norm() / xc.norm()))
+        print(f"nrhs={nrhs}: columns vs single-rhs applies:", errs)
 
 
 if __name__ == "__main__":

@@ -15,6 +15,7 @@ def main():
     ap.add_argument("--workload", default="poisson")
     ap.add_argument("--size", type=int, default=128)
     ap.add_argument("--applies", type=int, default=3)
+    ap.add_argument("--nrhs", type=int, default=1)
     args = ap.parse_args()
     build.build()
     A = make_problem(args.workload, args.size)
@@ -30,6 +31,13 @@ def main():
     for _ in range(args.applies):
         G.solve_dev(b.data_ptr(), x.data_ptr())
     G.synchronize()
+    if args.nrhs > 1:
+        B = torch.from_numpy(P.seeded_rhs(n, 0, nrhs=args.nrhs)).cuda()
+        X = torch.empty_like(B)
+        for _ in range(args.applies):
+            G.solve_mrhs_dev(args.nrhs, B.data_ptr(), X.data_ptr())
+        G.synchronize()
+        print("mrhs column 0 vs single", float((X[:, 0] - x).norm() / x.norm()))
     xr = M.solve(bh)
     print("parity", float(np.linalg.norm(x.cpu().numpy() - xr) / np.linalg.norm(xr)))
 
