@@ -8,7 +8,7 @@
 //          xU   = U^{-1} (xL ./ d)                              (sptrsv_slab_kernel<UPPER>)
 //          r    = bhat[m:n] - E xU         -> b of level l+1    (spmv_resid_kernel)
 //   last:  ychild = P R^{-1} Q^T r                              (dense_qt_kernel, dense_trsv_kernel)
-//   up:    g    = bhat[0:m] - F ychild                          (spmv_resid_kernel)
+//   up:    g    = bhat[0:m] - F ychild  (in place, rows of F with entries: spmv_sub_rows_kernel)
 //          xL'  = L^{-1} g ; xU' = U^{-1} (xL' ./ d)
 //          y[i] = t[i] * [xU'; ychild][q_inv[i]]                (scatter_scale_kernel)
 // `bhat` is evaluated once per level (the reference evaluates s[p]*b[p] up to 3 times,
@@ -242,6 +242,19 @@ void launch_sweeps(Handle *h, DevLevel &D, const double *rhs, unsigned long long
   mark(h, tag + "U");
 }
 
+// g = bhat - F y in place: only the rows of F that have entries change (bhat[0:m] is not needed again in
+// this apply); one thread per such row (1.6 entries on average)
+__global__ void spmv_sub_rows_kernel(const unsigned nrows, const unsigned *__restrict__ rows, const unsigned *__restrict__ cptr,
+                                     const int *__restrict__ col, const double *__restrict__ val,
+                                     const double *__restrict__ x, double *__restrict__ inout) {
+  const unsigned k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= nrows) return;
+  double acc = 0.0;
+  for (unsigned e = cptr[k], end = cptr[k + 1]; e < end; ++e) acc = fma(val[e], x[col[e]], acc);
+  const unsigned r = rows[k];
+  inout[r]         = inout[r] - acc;
+}
+
 template <bool TAGGED>
 void launch_spmv_resid(Handle *h, const DevCsr &A, const int *col, const void *x, const double *base, double *out,
                        const std::string &tag) {
@@ -405,9 +418,12 @@ void apply_schedule(Handle *h, const double *d_b, double *d_x, std::size_t rank,
     DevLevel &    D      = h->levels[l];
     double *      y      = l == 0 ? d_x : h->levels[l - 1].ychild.p;
     const double *rhs    = D.bhat.p;
-    if (D.nm && D.F.nnz) {
-      launch_spmv_resid<false>(h, D.F, D.F.col.p, D.ychild.p, D.bhat.p, D.g.p, "lv" + std::to_string(l) + ".F");
-      rhs = D.g.p;
+    if (D.nm && D.F_rows.n) {
+      spmv_sub_rows_kernel<<<cdiv(D.F_rows.n, T), T, 0, h->stream>>>(static_cast<unsigned>(D.F_rows.n), D.F_rows.p, D.F_cptr.p,
+                                                                     D.F.col.p, D.F.val.p, D.ychild.p, D.bhat.p);
+      HIF_KERNEL_CHECK();
+      mark(h, "lv" + std::to_string(l) + ".F");
+      ++h->launch_count;
     }
     launch_sweeps(h, D, rhs, D.xL_up.p, D.xU_up.p, parity, h->tick(8 * l + 2), "lv" + std::to_string(l) + ".up.", 2);
     if (D.n) {

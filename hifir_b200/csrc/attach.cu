@@ -290,6 +290,14 @@ Handle *attach_levels(int device, std::size_t nlevels, const LhfdGpuLevel *lv, b
     }
     upload_csr(Er, D.E, tally);
     upload_csr(Fr, D.F, tally);
+    {
+      std::vector<unsigned> rows, cptr;
+      for (std::size_t i = 0; i < Fr.nrows; ++i)
+        if (Fr.ptr[i + 1] > Fr.ptr[i]) rows.push_back(static_cast<unsigned>(i)), cptr.push_back(Fr.ptr[i]);
+      cptr.push_back(Fr.nrows ? Fr.ptr[Fr.nrows] : 0u);
+      D.F_rows.upload(rows, tally);
+      D.F_cptr.upload(cptr, tally);
+    }
     D.hostE = std::move(Er);
     D.hostF = std::move(Fr);
     D.d.upload(P.d_B, P.m, tally);
@@ -304,7 +312,6 @@ Handle *attach_levels(int device, std::size_t nlevels, const LhfdGpuLevel *lv, b
     D.xU_dn.alloc(2 * P.m, tally);
     D.xL_up.alloc(2 * P.m, tally);
     D.xU_up.alloc(2 * P.m, tally);
-    D.g.alloc(P.m, tally);
     D.r.alloc(D.nm, tally);
     D.ychild.alloc(D.nm, tally);
 

@@ -171,6 +171,8 @@ struct DevLevel {
   // consumers of the sweeps' renumbered solution slots (wsweep.cu): built once at attach
   DevBuf<double> d_ls;     // d permuted to the slots of the L sweep (the U sweep divides its right-hand side)
   DevBuf<int>    E_xcol;   // E.col mapped to the slots of the U sweep
+  // rows of F that have entries (46 % at Poisson 128^3 level 0): g = bhat - F y is formed IN PLACE on those
+  DevBuf<unsigned> F_rows, F_cptr;  // row ids; F.ptr at those rows (+ end): entries are those of F.col / F.val
   DevBuf<int>    q_slot;   // q_inv mapped: < nslots(U) -> slot of the U sweep, else nslots + (q_inv - m)
   DevBuf<unsigned> L_slot, U_slot;  // slot of every original row (indirection for the off-path kernels)
   DevBuf<double> s, t;     // n
@@ -181,7 +183,6 @@ struct DevLevel {
   // per-apply work vectors (nrhs = 1 path); tagged = produced by a sync-free sweep
   DevBuf<double>             bhat;                      // n   s[p]*b[p]
   DevBuf<unsigned long long> xL_dn, xU_dn, xL_up, xU_up;  // m   tagged
-  DevBuf<double>             g;                         // m   bhat - F*y_child
   DevBuf<double>             r;                         // nm  Schur rhs = child's b
   DevBuf<double>             ychild;                    // nm  child's solution
   // multi-rhs (kMrhsWidth columns, row-interleaved): plans + work vectors, built on first use

@@ -55,6 +55,81 @@ __global__ void gather_scale_m_kernel(const unsigned n, const unsigned nc, const
   bhat[g]              = c < nvalid ? s[pi] * b[static_cast<std::size_t>(pi) * ldb + k0 + c] : 0.0;
 }
 
+// The glue of the column-parallel path: a thread owns FOUR columns of a row (32 bytes in flight per thread;
+// one element per thread left these kernels latency bound at 3 TB/s: p -> s, b is a chain of two round trips).
+// bhat[i][c] = s[p[i]] * b[p[i]][k0 + c], zero beyond nvalid columns; nc is a multiple of 4
+__global__ void gather_scale_w_kernel(const unsigned n, const unsigned nc, const int *__restrict__ p,
+                                      const double *__restrict__ s, const double *__restrict__ b, const unsigned ldb,
+                                      const unsigned k0, const unsigned nvalid, double *__restrict__ bhat) {
+  const std::size_t g = static_cast<std::size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const unsigned    q = nc >> 2;
+  if (g >= static_cast<std::size_t>(n) * q) return;
+  const std::size_t i = g / q;
+  const unsigned    c = static_cast<unsigned>(g % q) * 4u;
+  const int         pi = p[i];
+  const double      si = s[pi];
+  const double *    src = b + static_cast<std::size_t>(pi) * ldb + k0 + c;
+  double            v[4];
+#pragma unroll
+  for (unsigned j = 0; j < 4; ++j) v[j] = c + j < nvalid ? si * src[j] : 0.0;
+  double2 *dst = reinterpret_cast<double2 *>(bhat + i * nc + c);
+  dst[0]       = make_double2(v[0], v[1]);
+  dst[1]       = make_double2(v[2], v[3]);
+}
+
+// y[i][k0 + c] = t[i] * [xU; ychild][q_slot[i]][c] for the first nvalid columns
+__global__ void scatter_scale_w_kernel(const unsigned n, const unsigned nc, const int *__restrict__ q_slot,
+                                       const double *__restrict__ t, const unsigned long long *__restrict__ xU,
+                                       const double *__restrict__ ychild, double *__restrict__ y, const unsigned ldy,
+                                       const unsigned k0, const unsigned nvalid) {
+  const std::size_t g = static_cast<std::size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const unsigned    q = nc >> 2;
+  if (g >= static_cast<std::size_t>(n) * q) return;
+  const std::size_t i = g / q;
+  const unsigned    c = static_cast<unsigned>(g % q) * 4u;
+  if (c >= nvalid) return;
+  const int    j  = q_slot[i];
+  const double ti = t[i];
+  double       v[4];
+  if (j >= 0) {
+    const ulonglong2 *src = reinterpret_cast<const ulonglong2 *>(xU + static_cast<std::size_t>(j) * nc + c);
+    const ulonglong2  a = src[0], b2 = src[1];
+    v[0] = tag_value(a.x), v[1] = tag_value(a.y), v[2] = tag_value(b2.x), v[3] = tag_value(b2.y);
+  } else {
+    const double2 *src = reinterpret_cast<const double2 *>(ychild + static_cast<std::size_t>(-j - 1) * nc + c);
+    const double2  a = src[0], b2 = src[1];
+    v[0] = a.x, v[1] = a.y, v[2] = b2.x, v[3] = b2.y;
+  }
+  double *dst = y + i * ldy + k0 + c;
+#pragma unroll
+  for (unsigned k = 0; k < 4; ++k)
+    if (c + k < nvalid) dst[k] = ti * v[k];
+}
+
+// g = bhat - F y in place on the rows of F that have entries (apply.cu: spmv_sub_rows_kernel), two columns
+// per thread
+__global__ void spmv_sub_rows_m_kernel(const unsigned nrows, const unsigned nc, const unsigned *__restrict__ rows,
+                                       const unsigned *__restrict__ cptr, const int *__restrict__ col,
+                                       const double *__restrict__ val, const double *__restrict__ x,
+                                       double *__restrict__ inout) {
+  const std::size_t g = static_cast<std::size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const unsigned    q = nc >> 1;
+  if (g >= static_cast<std::size_t>(nrows) * q) return;
+  const std::size_t k = g / q;
+  const unsigned    c = static_cast<unsigned>(g % q) * 2u;
+  double            a0 = 0.0, a1 = 0.0;
+  for (unsigned e = cptr[k], end = cptr[k + 1]; e < end; ++e) {
+    const double2 xv = *reinterpret_cast<const double2 *>(x + static_cast<std::size_t>(col[e]) * nc + c);
+    const double  v  = val[e];
+    a0               = fma(v, xv.x, a0);
+    a1               = fma(v, xv.y, a1);
+  }
+  double2 *io = reinterpret_cast<double2 *>(inout + static_cast<std::size_t>(rows[k]) * nc + c);
+  double2  w  = *io;
+  w.x -= a0, w.y -= a1;
+  *io = w;
+}
+
 // out[i][c] = base[i][c] - sum_j A(i,j) x[j][c]; NR consecutive threads = the NR columns of one row
 template <bool TAGGED>
 __global__ void spmv_resid_m_kernel(const unsigned nrows, const unsigned nc, const unsigned *__restrict__ ptr,
@@ -87,22 +162,6 @@ __global__ void scatter_scale_m_kernel(const unsigned n, const unsigned nc, cons
   const double      w = j < m ? tag_value(xU[static_cast<std::size_t>(j) * nc + c])
                               : ychild[static_cast<std::size_t>(j - m) * nc + c];
   y[g]                = t[i] * w;
-}
-
-// the same with q_inv mapped to the solution slots of the U sweep (attach.cu: q_slot); y has row stride
-// ldy and receives the first nvalid columns of the pass at column k0
-__global__ void scatter_scale_ms_kernel(const unsigned n, const unsigned nc, const int *__restrict__ q_slot,
-                                        const double *__restrict__ t, const unsigned long long *__restrict__ xU,
-                                        const double *__restrict__ ychild, double *__restrict__ y, const unsigned ldy,
-                                        const unsigned k0, const unsigned nvalid) {
-  const std::size_t g = static_cast<std::size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (g >= static_cast<std::size_t>(n) * nc) return;
-  const std::size_t i = g / nc, c = g % nc;
-  if (c >= nvalid) return;
-  const int    j = q_slot[i];
-  const double w = j >= 0 ? tag_value(xU[static_cast<std::size_t>(j) * nc + c])
-                          : ychild[static_cast<std::size_t>(-j - 1) * nc + c];
-  y[i * ldy + k0 + c] = t[i] * w;
 }
 
 // dense level: cq[k][c] = Q(:,k)^T x[:, c] : one warp per column k of Q, NR accumulators
@@ -269,8 +328,8 @@ static void apply_cols(Handle *h, unsigned nc, const double *d_B, double *d_X, u
   for (std::size_t l = 0; l < nl; ++l) {
     DevLevel &D = h->levels[l];
     if (D.n) {
-      gather_scale_m_kernel<<<cdiv(D.n * nc, T), T, 0, h->stream>>>(static_cast<unsigned>(D.n), nc, D.p.p, D.s.p, b, ldb, kb,
-                                                                     nvb, D.m_bhat.p);
+      gather_scale_w_kernel<<<cdiv(D.n * (nc / 4), T), T, 0, h->stream>>>(static_cast<unsigned>(D.n), nc, D.p.p, D.s.p, b, ldb,
+                                                                           kb, nvb, D.m_bhat.p);
       HIF_KERNEL_CHECK();
       ++h->launch_count;
     }
@@ -300,17 +359,15 @@ static void apply_cols(Handle *h, unsigned nc, const double *d_B, double *d_X, u
   for (std::size_t l = nl; l-- > 0;) {
     DevLevel &    D   = h->levels[l];
     double *      y   = l == 0 ? d_X : h->levels[l - 1].m_ychild.p;
-    const double *rhs = D.m_bhat.p;
-    if (D.nm && D.F.nnz && D.m) {
-      spmv_resid_m_kernel<false><<<cdiv(D.m * nc, T), T, 0, h->stream>>>(
-          static_cast<unsigned>(D.m), nc, D.F.ptr.p, D.F.col.p, D.F.val.p, D.m_ychild.p, D.m_bhat.p, D.m_g.p);
+    if (D.nm && D.F_rows.n && D.m) {
+      spmv_sub_rows_m_kernel<<<cdiv(D.F_rows.n * (nc / 2), T), T, 0, h->stream>>>(
+          static_cast<unsigned>(D.F_rows.n), nc, D.F_rows.p, D.F_cptr.p, D.F.col.p, D.F.val.p, D.m_ychild.p, D.m_bhat.p);
       HIF_KERNEL_CHECK();
       ++h->launch_count;
-      rhs = D.m_g.p;
     }
-    if (D.m) launch_ws_sweep_cols(h, D.LU, rhs, D.d_ls.p, D.m_xL_up.p, D.m_xU_up.p, parity, h->tick(8 * l + 2), nc);
+    if (D.m) launch_ws_sweep_cols(h, D.LU, D.m_bhat.p, D.d_ls.p, D.m_xL_up.p, D.m_xU_up.p, parity, h->tick(8 * l + 2), nc);
     if (D.n) {
-      scatter_scale_ms_kernel<<<cdiv(D.n * nc, T), T, 0, h->stream>>>(
+      scatter_scale_w_kernel<<<cdiv(D.n * (nc / 4), T), T, 0, h->stream>>>(
           static_cast<unsigned>(D.n), nc, D.q_slot.p, D.t.p, D.m_xU_up.p, D.m_ychild.p, y, l == 0 ? nrhs : nc,
           l == 0 ? k0 : 0u, l == 0 ? nvalid : nc);
       HIF_KERNEL_CHECK();

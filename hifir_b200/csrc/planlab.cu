@@ -43,6 +43,25 @@ void plan_lab(const HostCsr &Tnat, bool upper, const int *user_key, const double
     depth  = std::max(depth, l + 1u);
   }
   auto rowlen = [&](unsigned i) { return S.ptr[i + 1] - S.ptr[i]; };
+  {  // fan-out of the solution slots: [10] most references to one row, [11] / [12] entries that reference rows
+     // with >= 32 / >= 256 references, [13] rows with >= 256 references, [14] entries at <= 1 / [15] <= 4 levels distance
+    std::vector<unsigned> refs(n, 0u);
+    for (int c : S.col) ++refs[c];
+    double mx = 0, e32 = 0, e256 = 0, r256 = 0, d1 = 0, d4 = 0;
+    for (unsigned i = 0; i < n; ++i) {
+      mx = std::max(mx, static_cast<double>(refs[i]));
+      if (refs[i] >= 256u) r256 += 1;
+    }
+    for (unsigned i = 0; i < n; ++i)
+      for (unsigned k = S.ptr[i]; k < S.ptr[i + 1]; ++k) {
+        const unsigned c = static_cast<unsigned>(S.col[k]);
+        if (refs[c] >= 32u) e32 += 1;
+        if (refs[c] >= 256u) e256 += 1;
+        if (lev[i] - lev[c] <= 1u) d1 += 1;
+        if (lev[i] - lev[c] <= 4u) d4 += 1;
+      }
+    out[10] = mx, out[11] = e32, out[12] = e256, out[13] = r256, out[14] = d1, out[15] = d4;
+  }
   auto orig   = [&](unsigned i) {
     const unsigned s = S.gid[i] & kCodeSlotMask;
     return s >= m ? s - m : s;

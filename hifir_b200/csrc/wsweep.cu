@@ -571,6 +571,7 @@ struct WsParams {
   int                       publish_st;
   int                       l1_first;    // first-try gathers through L1
   unsigned                  spin_limit;  // poll rounds after which a wait gives up (and every other wait with it)
+  unsigned                  poll_sleep;  // multi-rhs: nanoseconds between two poll rounds of a batch (0: none)
   unsigned long long *      trace;  // kTrace: 4 words per segment (decoded, admitted, gathered | rounds, published | level)
 };
 
@@ -909,12 +910,12 @@ __device__ __forceinline__ bool ws_ready2(unsigned long long a, unsigned long lo
   return !(((static_cast<unsigned>(a) ^ parity) | (static_cast<unsigned>(b) ^ parity)) & 1u);
 }
 
-template <class VT, int G>
+template <class VT, int G, unsigned B>
 __global__ void __launch_bounds__(24 * 32, 1) wsweep_cols_kernel(const WsParams P) {
   constexpr int      kWarps = 24, kStages = 2;
   constexpr unsigned NC = 2u * G, EPI = 32u / G;  // columns; rows (or row parts) per gather instruction
-  constexpr unsigned B = 4u;                      // entries of a row in flight per lane (a second row in flight
-                                                  // spills registers -- 85 per thread at 24 warps -- and measured slower)
+  // B = 4 or 8 entries of a row in flight per lane (a second ROW in flight spills the gathered words --
+  // 85 registers per thread at 24 warps -- and measured slower)
   constexpr unsigned kStageBytes = (kWsHdrWords + 64u + kWsU * 32u * (sizeof(VT) == 4 ? 2u : 3u)) * 4u;
   extern __shared__ __align__(128) unsigned char smem[];
   const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
@@ -1038,12 +1039,12 @@ __global__ void __launch_bounds__(24 * 32, 1) wsweep_cols_kernel(const WsParams 
       const unsigned *sc    = sg + kWsHdrWords + 64u;
       const VT *      sv    = reinterpret_cast<const VT *>(sc + width * 32u);
       const bool      first = (flags & kSegFirst) != 0u, last = (flags & kSegLast) != 0u;
-      // The entry slots of a row are walked in batches of B = 4, addressed by a running pointer and
-      // compile-time offsets.  Four layouts (word of entry u of lane l of the row: u * 32 + first lane + l):
-      //   CLS 0  one lane per row: slots u = 0 .. width-1, 32 words apart              (batch: +128 words)
-      //   CLS 1  two lanes per row: (u, l) = (0,0) (0,1) (1,0) (1,1) ...               (batch: +64 words)
-      //   CLS 2  4+ lanes per row, one lane group per row: consecutive lanes, then the next u
-      //   CLS 3  K lane groups share the row: every K-th lane (the partial sums are added below)
+      // The entry slots of a row are walked in batches of B, addressed by a running pointer and compile-time
+      // offsets (word of entry u of lane l of the row: u * 32 + first lane + l).  Layouts:
+      //   CLS 0..2  2^CLS < B lanes per row: a batch wraps over the lanes, (u, l) = (0,0) .. (0,2^z-1) (1,0) ...;
+      //             the row may end inside a batch (rem)
+      //   CLS 3     B or more lanes per row, one lane group per row: consecutive lanes, then the next u
+      //   CLS 4     K lane groups share the row: every K-th lane (the partial sums are added below)
       auto run = [&](auto cls_tag) {
         constexpr unsigned CLS = decltype(cls_tag)::value;
         for (unsigned r0 = 0; r0 < R; r0 += Rg) {
@@ -1061,27 +1062,34 @@ __global__ void __launch_bounds__(24 * 32, 1) wsweep_cols_kernel(const WsParams 
             // were parked in the row's own slot under the OTHER tag (nobody consumes them)
             ws_ld_poll2(xw + static_cast<std::size_t>(slot) * NC + cp, t0, t1);
           // gathered rows; a slot without entry keeps an older (finite) row and meets the value 0.0
-          unsigned long long g0[B] = {0ull, 0ull, 0ull, 0ull}, g1[B] = {0ull, 0ull, 0ull, 0ull};
-          bool               firstb = true;
-          auto batch = [&](const unsigned *pc, const VT *pv, unsigned rem) {  // rem: slots left (CLS 0, 1)
+          unsigned long long g0[B], g1[B];
+#pragma unroll
+          for (unsigned j = 0; j < B; ++j) g0[j] = g1[j] = 0ull;
+          bool firstb = true;
+          auto batch  = [&](const unsigned *pc, const VT *pv, unsigned rem) {  // rem: slots left (CLS 0..2)
             unsigned col[B];
 #pragma unroll
             for (unsigned j = 0; j < B; ++j) {
-              const unsigned off = CLS == 0u ? j * 32u : CLS == 1u ? (j >> 1) * 32u + (j & 1u) : CLS == 2u ? j : j * K;
+              const unsigned off = CLS <= 2u ? (j >> CLS) * 32u + (j & ((1u << CLS) - 1u)) : CLS == 3u ? j : j * K;
               col[j]             = kWsNone;
-              if ((CLS >= 2u || j < rem) && live) col[j] = pc[off];
+              if ((CLS >= 3u || j < rem) && live) col[j] = pc[off];
               if (col[j] != kWsNone) ws_ld_poll2(xw + static_cast<std::size_t>(col[j]) * NC + cp, g0[j], g1[j]);
             }
             unsigned bad = 0;
 #pragma unroll
             for (unsigned j = 0; j < B; ++j)
               bad |= col[j] != kWsNone ? (static_cast<unsigned>(g0[j]) ^ parity) | (static_cast<unsigned>(g1[j]) ^ parity) : 0u;
-            if (__any_sync(0xffffffffu, (bad & 1u) != 0u)) {  // rare: some row was not published yet
+            if (__any_sync(0xffffffffu, (bad & 1u) != 0u)) {
+              // Some row was not published yet (right behind the frontier this is the common case: ~3 poll
+              // rounds per batch were measured).  Every lane polls its own piece: letting only the first lane
+              // of a group poll (1 sector instead of the row) costs one more round trip at the end and
+              // measured 14 % slower -- the chain of dependent round trips is what bounds the sweep.
               unsigned pend = 0;
 #pragma unroll
               for (unsigned j = 0; j < B; ++j)
                 if (col[j] != kWsNone && !ws_ready2(g0[j], g1[j], parity)) pend |= 1u << j;
               for (unsigned rounds = 0; __any_sync(0xffffffffu, pend != 0u);) {
+                if (P.poll_sleep) __nanosleep(P.poll_sleep);
 #pragma unroll
                 for (unsigned j = 0; j < B; ++j)
                   if (pend & (1u << j)) {
@@ -1105,30 +1113,27 @@ __global__ void __launch_bounds__(24 * 32, 1) wsweep_cols_kernel(const WsParams 
             }
 #pragma unroll
             for (unsigned j = 0; j < B; ++j) {
-              const unsigned off = CLS == 0u ? j * 32u : CLS == 1u ? (j >> 1) * 32u + (j & 1u) : CLS == 2u ? j : j * K;
+              const unsigned off = CLS <= 2u ? (j >> CLS) * 32u + (j & ((1u << CLS) - 1u)) : CLS == 3u ? j : j * K;
               double         v   = 0.0;  // (beyond the row's slots the stage holds other data: never read)
-              if (CLS >= 2u || j < rem) v = static_cast<double>(pv[off]);
+              if (CLS >= 3u || j < rem) v = static_cast<double>(pv[off]);
               a0 = fma(-v, tag_value(g0[j]), a0);
               a1 = fma(-v, tag_value(g1[j]), a1);
             }
           };
-          if (CLS == 0u) {
+          if (CLS <= 2u) {
+            const unsigned  T  = width << CLS, adv = (B >> CLS) * 32u;
             const unsigned *pc = sc + ol;
             const VT *      pv = sv + ol;
-            for (unsigned t = 0; t < width; t += B, pc += 4u * 32u, pv += 4u * 32u) batch(pc, pv, width - t);
-          } else if (CLS == 1u) {
-            const unsigned *pc = sc + ol;
-            const VT *      pv = sv + ol;
-            for (unsigned t = 0; t < 2u * width; t += B, pc += 2u * 32u, pv += 2u * 32u) batch(pc, pv, 2u * width - t);
+            for (unsigned t = 0; t < T; t += B, pc += adv, pv += adv) batch(pc, pv, T - t);
           } else {
-            const unsigned step = CLS == 2u ? B : B * K, nb = lpr / step;  // batches per entry index u
+            const unsigned step = CLS == 3u ? B : B * K, nb = lpr / step;  // batches per entry index u
             for (unsigned u = 0; u < width; ++u) {
               const unsigned *pc = sc + u * 32u + ol + part;
               const VT *      pv = sv + u * 32u + ol + part;
               for (unsigned b = 0; b < nb; ++b, pc += step, pv += step) batch(pc, pv, B);
             }
           }
-          if (CLS == 3u) {  // the lane groups that shared a row add their partial sums
+          if (CLS == 4u) {  // the lane groups that shared a row add their partial sums
             for (unsigned o = Rg * G; o < 32u; o <<= 1) {
               a0 += __shfl_xor_sync(0xffffffffu, a0, o);
               a1 += __shfl_xor_sync(0xffffffffu, a1, o);
@@ -1141,14 +1146,18 @@ __global__ void __launch_bounds__(24 * 32, 1) wsweep_cols_kernel(const WsParams 
           keep ^= static_cast<unsigned>(__double2hiint(a0));
         }
       };
-      if (z == 0u)
-        run(std::integral_constant<unsigned, 0u>());
-      else if (z == 1u)
-        run(std::integral_constant<unsigned, 1u>());
-      else if (K == 1u)
-        run(std::integral_constant<unsigned, 2u>());
-      else
+      if (lpr < B) {
+        if (z == 0u)
+          run(std::integral_constant<unsigned, 0u>());
+        else if (z == 1u)
+          run(std::integral_constant<unsigned, 1u>());
+        else
+          run(std::integral_constant<unsigned, 2u>());
+      } else if (K == 1u) {
         run(std::integral_constant<unsigned, 3u>());
+      } else {
+        run(std::integral_constant<unsigned, 4u>());
+      }
     }
     // refill after everything read from the stage was used: the size depends on the digest without being
     // changed by it (two reads of the same header word the compiler can not prove equal)
@@ -1325,10 +1334,13 @@ template <class VT, int G>
 void launch_ws_cols_G(Handle *h, const SweepPlan &plan, const WsParams &P) {
   constexpr unsigned kStageBytes = (kWsHdrWords + 64u + kWsU * 32u * (sizeof(VT) == 4 ? 2u : 3u)) * 4u;
   constexpr unsigned smem        = 24u * 2u * (8u + kStageBytes);
-  auto               kern        = wsweep_cols_kernel<VT, G>;
+  static const int   bt          = ws_env("HIFIR_B200_MRHS_BATCH", 4);  // entries of a row in flight per lane
+  auto               kern        = bt >= 8 ? wsweep_cols_kernel<VT, G, 8u> : bt >= 4 ? wsweep_cols_kernel<VT, G, 4u> : wsweep_cols_kernel<VT, G, 2u>;
   static bool        configured[64] = {false};
   if (h->device >= 64 || !configured[h->device]) {
-    HIF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    HIF_CUDA(cudaFuncSetAttribute(wsweep_cols_kernel<VT, G, 8u>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    HIF_CUDA(cudaFuncSetAttribute(wsweep_cols_kernel<VT, G, 4u>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    HIF_CUDA(cudaFuncSetAttribute(wsweep_cols_kernel<VT, G, 2u>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     if (h->device < 64) configured[h->device] = true;
   }
   kern<<<plan.ws_grid, 24 * 32, smem, h->stream>>>(P);
@@ -1369,6 +1381,7 @@ void launch_ws_sweep_cols(Handle *h, const SweepPlan &plan, const double *rhs_pl
   P.publish_st = 1;
   P.l1_first   = 0;
   P.spin_limit = static_cast<unsigned>(std::max(1000, ws_env("HIFIR_B200_WS_SPIN_LIMIT", 1 << 21)));
+  P.poll_sleep = static_cast<unsigned>(std::max(0, ws_env("HIFIR_B200_MRHS_POLL_SLEEP", 0)));
   if (plan.f32)
     launch_ws_cols_V<float>(h, plan, P, nc);
   else
@@ -1398,6 +1411,7 @@ void launch_ws_sweep(Handle *h, const SweepPlan &plan, const double *rhs_plain, 
   P.publish_st = ws_env("HIFIR_B200_WS_PUBLISH_ST", 0);
   P.l1_first   = ws_env("HIFIR_B200_WS_L1", 0);
   P.spin_limit = static_cast<unsigned>(std::max(1000, ws_env("HIFIR_B200_WS_SPIN_LIMIT", 1 << 21)));
+  P.poll_sleep = 0;
   if (plan.fused) {
     if (!x2) throw std::logic_error("fused L-then-U sweep needs both solution buffers");
     if (plan.f32)

@@ -34,7 +34,7 @@ def lab(block, upper, key, opts):
     return out
 
 
-CONFIGS = [
+CONFIGS_ALL = [
     ("r1: (lev,len) orig slots", (0, 0, 0, 0)),
     ("(lev,cls,key) sweep-index key, lvl-major slots", (1, 1, 0, 0)),
     ("(lev,cls,key) user key p, lvl-major slots", (1, 1, 1, 0)),
@@ -45,6 +45,9 @@ CONFIGS = [
     ("barycenter x3 seeded sweep idx, lvl-major slots", (1, 1, 2, 3)),
     ("barycenter x3 seeded p, packed slots", (1, 2, 3, 3)),
 ]
+
+
+CONFIGS = CONFIGS_ALL if os.environ.get("PLAN_LAB_ALL") else CONFIGS_ALL[:2]
 
 
 def main():
@@ -69,6 +72,10 @@ def main():
                       f"sectors/entry {o[4] / ent:.3f} lines/entry {o[5] / ent:.3f} chunk-sectors/entry {o[6] / ent:.3f} "
                       f"pub sectors/row {o[8] / o[0]:.3f} rhs sectors/row {o[9] / o[0]:.3f}  ({time.time() - t0:.1f}s)",
                       flush=True)
+                if name.startswith("r1"):
+                    print(f"      fan-out: most references to one row {int(o[10])}; entries on rows referenced >= 32x "
+                          f"{o[11] / ent:.1%}, >= 256x {o[12] / ent:.1%} ({int(o[13])} such rows); entries at level "
+                          f"distance <= 1 {o[14] / ent:.1%}, <= 4 {o[15] / ent:.1%}", flush=True)
 
 
 if __name__ == "__main__":
