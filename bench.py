@@ -366,7 +366,9 @@ def run_mrhs(args, rank, world, local_rank):
         cpu = {"value": ncols / dt, "unit": "applies/s", "cores": 1, "kind": "reference",
                "sample": f"{ncols} of the {nrhs} columns, one hif::HIF::solve each on the same factorized object "
                          f"({dt:.1f} s; serial reference code, one object = one thread, builder.hpp:579)"}
-    chunks = -(-max(1, shard_range(nrhs, world, 0)[1]) // 8)
+    nloc0 = max(1, shard_range(nrhs, world, 0)[1])
+    width = 64 if nloc0 >= 64 else 32 if nloc0 > 16 else 16  # mrhs.cu: apply_mrhs_dev
+    chunks = -(-nloc0 // width)
     bytes_step = world * (st["bytes_factors"] + st["bytes_dense"]) + nrhs * st["bytes_vec_per_rhs"]
     line = {
         "metric": "M^-1 applies/sec", "value": nrhs * args.steps / (ms_total * 1e-3), "unit": "applies/s",
@@ -375,7 +377,7 @@ def run_mrhs(args, rank, world, local_rank):
         "config": {"workload": workload_name(args.workload, args.size, nrhs), "n": n, "levels": st["levels"],
                    "nnz_factors": st["nnz"], "params": "tau=1e-2 alpha=3 kappa=5 (reference PDE set)",
                    "l2_policy": "inputs larger than L2",
-                   "parallelism": f"replicas, {nrhs} columns sharded over {world} GPU(s), 8 columns per pass"},
+                   "parallelism": f"replicas, {nrhs} columns sharded over {world} GPU(s), {width} columns per pass"},
         "roofline": {"bound": "hbm", "kernel": "whole batched apply", "achieved": bytes_step / (ms_step * 1e-3) / 1e9,
                      "peak": peak * world, "unit": "GB/s", "frac": bytes_step / (ms_step * 1e-3) / 1e9 / (peak * world),
                      "traffic": None, "algorithmic_bytes_per_step": bytes_step, "peak_source": peak_src,

@@ -38,7 +38,7 @@ __device__ __forceinline__ unsigned long long tag_set(double v, unsigned parity)
   return (static_cast<unsigned long long>(__double_as_longlong(v)) & ~1ull) | parity;
 }
 __device__ __forceinline__ bool tag_ready(unsigned long long bits, unsigned parity) {
-  return (bits & 1ull) == parity;
+  return ((static_cast<unsigned>(bits) ^ parity) & 1u) == 0u;  // 32-bit: the 64-bit compare cost two more instructions per poll
 }
 __device__ __forceinline__ double tag_value(unsigned long long bits) {
   return __longlong_as_double(static_cast<long long>(bits));

@@ -384,7 +384,7 @@ void apply_mrhs_dev(Handle *h, std::size_t nrhs, const double *d_B, double *d_X,
   }
   static const int wide_max = [] {  // most columns per pass of the column-parallel path (0: passes of 8 on streaming plans)
     const char *e = std::getenv("HIFIR_B200_MRHS_WIDE");
-    const int   w = e ? std::atoi(e) : 32;
+    const int   w = e ? std::atoi(e) : 64;
     return w >= 64 ? 64 : w >= 32 ? 32 : w >= 16 ? 16 : 0;
   }();
   bool fused = wide_max > 0 && !h->levels.empty();

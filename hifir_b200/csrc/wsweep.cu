@@ -639,6 +639,8 @@ __global__ void __launch_bounds__(kWarps * 32, 1) wsweep_kernel(const WsParams P
   // never become ready.)
   unsigned           cc[kWsU];          // slot indices / gathered words of the current segment
   unsigned long long g[kWsU];
+#pragma unroll
+  for (unsigned u = 0; u < kWsU; ++u) g[u] = 0ull;
   bool               have_cur = false;  // kPipe: they were requested during the previous segment
   auto refill = [&](unsigned stage, unsigned size16) {
     __syncwarp();
@@ -823,10 +825,14 @@ __global__ void __launch_bounds__(kWarps * 32, 1) wsweep_kernel(const WsParams P
       for (unsigned u = 0; u < kWsU; ++u)
         if (pend & (1u << u)) g[u] = ld_poll(xw + cc[u]);
       if (UPPER && (pend & (1u << kWsU))) rhs_t = ld_poll(rht + (code & kCodeSlotMask));
+      // still pending: the low bit differs from the tag.  Computed for every position without a branch (a
+      // position that was not re-read is ready or holds no entry: its pend bit is clear already) -- this loop
+      // ran ~1.5 times per segment at 110 instructions per round (32 % of the kernel's instructions)
+      unsigned still = 0;
 #pragma unroll
-      for (unsigned u = 0; u < kWsU; ++u)
-        if ((pend & (1u << u)) && tag_ready(g[u], parity)) pend &= ~(1u << u);
-      if (UPPER && (pend & (1u << kWsU)) && tag_ready(rhs_t, parity)) pend &= ~(1u << kWsU);
+      for (unsigned u = 0; u < kWsU; ++u) still |= ((static_cast<unsigned>(g[u]) ^ parity) & 1u) << u;
+      if (UPPER) still |= ((static_cast<unsigned>(rhs_t) ^ parity) & 1u) << kWsU;
+      pend &= still;
       if (++rounds > P.spin_limit || ((rounds & 255u) == 255u && ws_aborted(P))) {
         // hang guard: a dependency never became ready (or another warp gave up) -- remember where, go on
         if (pend && !ws_aborted(P)) {
@@ -1382,11 +1388,16 @@ void launch_ws_sweep_cols(Handle *h, const SweepPlan &plan, const double *rhs_pl
   P.l1_first   = 0;
   P.spin_limit = static_cast<unsigned>(std::max(1000, ws_env("HIFIR_B200_WS_SPIN_LIMIT", 1 << 21)));
   P.poll_sleep = static_cast<unsigned>(std::max(0, ws_env("HIFIR_B200_MRHS_POLL_SLEEP", 0)));
-  if (plan.f32)
-    launch_ws_cols_V<float>(h, plan, P, nc);
-  else
-    launch_ws_cols_V<double>(h, plan, P, nc);
-  HIF_KERNEL_CHECK();
+  // developer experiment (HIFIR_B200_WS_REPEAT): launch the sweep again -- every slot carries the tag already,
+  // the second pass never waits: its duration is the pure throughput bound of the kernel on this factor
+  static const int repeat = ws_env("HIFIR_B200_WS_REPEAT", 0);
+  for (int r = 0; r <= repeat; ++r) {
+    if (plan.f32)
+      launch_ws_cols_V<float>(h, plan, P, nc);
+    else
+      launch_ws_cols_V<double>(h, plan, P, nc);
+    HIF_KERNEL_CHECK();
+  }
   ++h->launch_count;
 }
 
