@@ -639,8 +639,10 @@ __global__ void __launch_bounds__(kWarps * 32, 1) wsweep_kernel(const WsParams P
   // never become ready.)
   unsigned           cc[kWsU];          // slot indices / gathered words of the current segment
   unsigned long long g[kWsU];
+  // a position without entry keeps what an earlier segment gathered there -- a word that carries the tag
+  // (initially: "zero carrying the tag"): the combined tag test below needs no per-position mask
 #pragma unroll
-  for (unsigned u = 0; u < kWsU; ++u) g[u] = 0ull;
+  for (unsigned u = 0; u < kWsU; ++u) g[u] = static_cast<unsigned long long>(P.parity);
   bool               have_cur = false;  // kPipe: they were requested during the previous segment
   auto refill = [&](unsigned stage, unsigned size16) {
     __syncwarp();
@@ -765,6 +767,10 @@ __global__ void __launch_bounds__(kWarps * 32, 1) wsweep_kernel(const WsParams P
     bool               have_nxt = false;
     unsigned           ccn[kWsU];
     unsigned long long gn[kWsU];
+    if (kPipe) {
+#pragma unroll
+      for (unsigned u = 0; u < kWsU; ++u) gn[u] = static_cast<unsigned long long>(parity);
+    }
     if (kPipe && k + 1u < nseg) {
       const unsigned st1 = (k + 1u) % kStages, ph1 = ((k + 1u) / kStages) & 1u;
       if (__all_sync(0xffffffffu, ws_mbar_try_wait(bar0 + st1 * 8u, ph1))) {
@@ -805,8 +811,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) wsweep_kernel(const WsParams P
     {
       unsigned bad = 0;
 #pragma unroll
-      for (unsigned u = 0; u < kWsU; ++u)
-        if (cc[u] != kWsNone) bad |= static_cast<unsigned>(g[u]) ^ parity;
+      for (unsigned u = 0; u < kWsU; ++u) bad |= static_cast<unsigned>(g[u]) ^ parity;
       if (UPPER && want_r) bad |= static_cast<unsigned>(rhs_t) ^ parity;
       if (bad & 1u) {
 #pragma unroll
@@ -851,15 +856,12 @@ __global__ void __launch_bounds__(kWarps * 32, 1) wsweep_kernel(const WsParams P
       if (want_r) acc = UPPER ? tag_value(rhs_t) / dg : rhs_v;
     }
     // the factor values are read from the stage only now (no registers held across the gather wait);
-    // the multiply is unconditional for every entry position of the segment, so that each of these
-    // reads is consumed before the stage is refilled (a padded position holds 0.0)
+    // every value that is read is consumed by its multiply-add (same predicate): all reads of the stage
+    // have returned before it is refilled
     const VT *sv = reinterpret_cast<const VT *>(sg + kWsHdrWords + 64u + width * 32u);
 #pragma unroll
     for (unsigned u = 0; u < kWsU; ++u)
-      if (u < width) {
-        const double v = static_cast<double>(sv[u * 32u + lane]);
-        acc            = fma(-v, cc[u] != kWsNone ? tag_value(g[u]) : 0.0, acc);
-      }
+      if (cc[u] != kWsNone) acc = fma(-static_cast<double>(sv[u * 32u + lane]), tag_value(g[u]), acc);
     if (flags & kSegLast) {
       for (unsigned o = lpr >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
       if (own) ws_publish(xw + slot, tag_set(acc, parity), P.publish_st);
