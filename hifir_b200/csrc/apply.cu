@@ -24,13 +24,12 @@ namespace hifgpu {
 // ============================================================================
 
 // bhat[i] = s[p[i]] * b[p[i]]   (prec_solve.hpp:359, 368, 399)
-__global__ void gather_scale_kernel(const unsigned n, const int *__restrict__ p, const double *__restrict__ s,
+// (sp[i] = s[p[i]] is formed at attach: one scattered load per row, not two -- the kernel is bound by
+// scattered sector requests)
+__global__ void gather_scale_kernel(const unsigned n, const int *__restrict__ p, const double *__restrict__ sp,
                                     const double *__restrict__ b, double *__restrict__ bhat) {
   const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) {
-    const int pi = p[i];
-    bhat[i]      = s[pi] * b[pi];
-  }
+  if (i < n) bhat[i] = sp[i] * b[p[i]];
 }
 
 // out[i] = base[i] - sum_j A(i,j) x[j]  with x either tagged (result of a sweep) or plain
@@ -396,7 +395,7 @@ void apply_schedule(Handle *h, const double *d_b, double *d_x, std::size_t rank,
   for (std::size_t l = 0; l < nl; ++l) {
     DevLevel &D = h->levels[l];
     if (D.n) {
-      gather_scale_kernel<<<cdiv(D.n, T), T, 0, h->stream>>>(static_cast<unsigned>(D.n), D.p.p, D.s.p, b, D.bhat.p);
+      gather_scale_kernel<<<cdiv(D.n, T), T, 0, h->stream>>>(static_cast<unsigned>(D.n), D.p.p, D.sp.p, b, D.bhat.p);
       HIF_KERNEL_CHECK();
       mark(h, "lv" + std::to_string(l) + ".gather");
       ++h->launch_count;

@@ -302,6 +302,11 @@ Handle *attach_levels(int device, std::size_t nlevels, const LhfdGpuLevel *lv, b
     D.hostF = std::move(Fr);
     D.d.upload(P.d_B, P.m, tally);
     D.s.upload(P.s, P.n, tally);
+    {
+      std::vector<double> sp(P.n);
+      for (std::size_t i = 0; i < P.n; ++i) sp[i] = P.s[P.p[i]];
+      D.sp.upload(sp, tally);
+    }
     D.t.upload(P.t, P.n, tally);
     D.p.upload(reinterpret_cast<const int *>(P.p), P.n, tally);
     D.q_inv.upload(reinterpret_cast<const int *>(P.q_inv), P.n, tally);

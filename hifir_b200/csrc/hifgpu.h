@@ -176,6 +176,7 @@ struct DevLevel {
   DevBuf<int>    q_slot;   // q_inv mapped: < nslots(U) -> slot of the U sweep, else nslots + (q_inv - m)
   DevBuf<unsigned> L_slot, U_slot;  // slot of every original row (indirection for the off-path kernels)
   DevBuf<double> s, t;     // n
+  DevBuf<double> sp;       // n: s[p[i]] (the gather reads it coalesced: one scattered load per row instead of two)
   DevBuf<int>    p, q_inv; // n
   // triangular-sweep schedule
   int         rows_per_block = 1024;

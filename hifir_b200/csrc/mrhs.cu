@@ -67,7 +67,7 @@ __global__ void gather_scale_w_kernel(const unsigned n, const unsigned nc, const
   const std::size_t i = g / q;
   const unsigned    c = static_cast<unsigned>(g % q) * 4u;
   const int         pi = p[i];
-  const double      si = s[pi];
+  const double      si = s[i];  // s[p[i]], formed at attach
   const double *    src = b + static_cast<std::size_t>(pi) * ldb + k0 + c;
   double            v[4];
 #pragma unroll
@@ -328,7 +328,7 @@ static void apply_cols(Handle *h, unsigned nc, const double *d_B, double *d_X, u
   for (std::size_t l = 0; l < nl; ++l) {
     DevLevel &D = h->levels[l];
     if (D.n) {
-      gather_scale_w_kernel<<<cdiv(D.n * (nc / 4), T), T, 0, h->stream>>>(static_cast<unsigned>(D.n), nc, D.p.p, D.s.p, b, ldb,
+      gather_scale_w_kernel<<<cdiv(D.n * (nc / 4), T), T, 0, h->stream>>>(static_cast<unsigned>(D.n), nc, D.p.p, D.sp.p, b, ldb,
                                                                            kb, nvb, D.m_bhat.p);
       HIF_KERNEL_CHECK();
       ++h->launch_count;
