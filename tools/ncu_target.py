@@ -21,6 +21,7 @@ def main():
     A = make_problem(args.workload, args.size)
     M = factorize(A, threads=os.cpu_count() or 1)
     G = hb.GpuHif(M.levels())
+    print("sweep_bytes", G.stats()["sweep_bytes"], "sweep_entries", G.stats()["sweep_entries"])
     n = A[0]
     bh = P.seeded_rhs(n, 0)
     b = torch.from_numpy(bh).cuda()
