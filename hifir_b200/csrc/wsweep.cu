@@ -28,6 +28,7 @@
 //     lane by COPY segments.
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <numeric>
@@ -292,6 +293,20 @@ void pack_warp_streams(const HostCsr &S, WsHost &H, unsigned nwarps, unsigned wi
   // segment sizes for the ring: wdesc[4..7] = sizes (in 16-byte units) of the first 4 segments, header
   // word 1 of segment k = size of segment k + stages (set by finalize_ring)
   H.seg_off = std::move(seg_off);
+  if (ws_env("HIFIR_B200_WS_STATS", 0)) {  // developer: segments by entries per lane
+    std::size_t hist[kWsU + 1] = {0}, copies = 0;
+    for (unsigned w = 0; w < nwarps; ++w)
+      for (unsigned off : H.seg_off[w]) {
+        const unsigned hx = ws[w][off];
+        if ((hx >> 16) & kSegCopy)
+          ++copies;
+        else
+          ++hist[std::min(kWsU, hx & 0xffu)];
+      }
+    std::fprintf(stderr, "[ws stats] segments %zu copy %zu by width:", H.nsegs, copies);
+    for (unsigned u = 1; u <= kWsU; ++u) std::fprintf(stderr, " %u:%zu", u, hist[u]);
+    std::fprintf(stderr, "\n");
+  }
 }
 
 // header word 1 of segment k = size (16-byte units) of segment k + stages of the same warp; the
@@ -826,6 +841,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) wsweep_kernel(const WsParams P
     }
     for (unsigned rounds = 0; __any_sync(0xffffffffu, pend != 0u);) {
       if (kTrace) ++nrounds;
+      if (P.poll_sleep) __nanosleep(P.poll_sleep);  // developer knob: issue slots for the other warps instead of polls
 #pragma unroll
       for (unsigned u = 0; u < kWsU; ++u)
         if (pend & (1u << u)) g[u] = ld_poll(xw + cc[u]);
@@ -1424,7 +1440,7 @@ void launch_ws_sweep(Handle *h, const SweepPlan &plan, const double *rhs_plain, 
   P.publish_st = ws_env("HIFIR_B200_WS_PUBLISH_ST", 0);
   P.l1_first   = ws_env("HIFIR_B200_WS_L1", 0);
   P.spin_limit = static_cast<unsigned>(std::max(1000, ws_env("HIFIR_B200_WS_SPIN_LIMIT", 1 << 21)));
-  P.poll_sleep = 0;
+  P.poll_sleep = static_cast<unsigned>(std::max(0, ws_env("HIFIR_B200_WS_POLL_SLEEP", 0)));
   if (plan.fused) {
     if (!x2) throw std::logic_error("fused L-then-U sweep needs both solution buffers");
     if (plan.f32)
