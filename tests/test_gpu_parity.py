@@ -501,6 +501,33 @@ def test_degenerate_levels(shape):
             assert relerr(X[:, k], Oh.solve(np.ascontiguousarray(B[:, k]))) <= TOL_F64
 
 
+@pytest.mark.parametrize("merge", ["1", "0"], ids=["merged", "unmerged"])
+def test_rows_longer_than_one_segment(merge, monkeypatch):
+    """Rows of L_B / U_B with more than 256 entries span several segments of a warp stream (32 lanes x 8
+    entries each): the partial sums are carried from segment to segment (single-rhs sweep: in a register;
+    multi-rhs sweep: parked in the row's own slot under the other tag).  Dense-ish hand-made factors, rows up to
+    ~560 entries, checked against the C oracle for one right-hand side and for blocks of every pass width
+    (16 / 32 / 64 columns: 4, 2, 1 rows per gather instruction, long rows shared by 4, 2, 1 lane groups)."""
+    monkeypatch.setenv("HIFIR_B200_MERGE", merge)
+    n, m = 860, 800
+    rng = np.random.default_rng(4242)
+    lev = _tiny_level(rng, n, m, dense=True)
+    L = np.tril(rng.uniform(-1, 1, (m, m)) * (rng.uniform(size=(m, m)) < 0.7), -1) * (2.0 / m)
+    U = np.triu(rng.uniform(-1, 1, (m, m)) * (rng.uniform(size=(m, m)) < 0.7), 1) * (2.0 / m)
+    lev.update(L=_ccs(L), U=_ccs(U))
+    assert (np.count_nonzero(L, axis=1).max() > 256) and (np.count_nonzero(U, axis=1).max() > 256)
+    Oh = O.OracleHif([lev])
+    with hb.GpuHif([lev]) as G:
+        for k in range(2):
+            b = rng.uniform(-1, 1, n)
+            assert relerr(G.solve(b), Oh.solve(b)) <= TOL_F64
+        for nrhs in (5, 20, 70):
+            B = rng.uniform(-1, 1, (n, nrhs))
+            X = G.solve_mrhs(B)
+            for k in range(nrhs):
+                assert relerr(X[:, k], Oh.solve(np.ascontiguousarray(B[:, k]))) <= TOL_F64, (nrhs, k)
+
+
 def test_device_integer_arrays_are_bit_exact(golden):
     """north_star: index and permutation handling must be bit-exact.  The device-resident p, q_inv, jpvt
     and the CSR form of E and F (attach.cu: ccs_to_csr) are copied back and compared with the host
