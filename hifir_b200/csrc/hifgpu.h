@@ -283,6 +283,11 @@ struct Handle {
   DevBuf<double> ir_xk, ir_r, ir_t;
   DevBuf<double> kr_v, kr_w, kr_Q, kr_Z, kr_scal, kr_part;
   DevBuf<unsigned> kr_count;        // arrival counter of the fused Gram-Schmidt step (krylov.cu)
+  // persistent Gram-Schmidt kernel (krylov.cu): block partials of every step, grid barrier counter (only ever
+  // incremented: a launch with B barriers adds B * grid; the host keeps the value it starts from)
+  DevBuf<double>             kr_mpart;
+  DevBuf<unsigned long long> kr_bar;
+  unsigned long long         kr_bar_base = 0;
   double *       h_scal = nullptr;  // pinned
   int            kr_restart = 0;
   // multi-rhs column staging
