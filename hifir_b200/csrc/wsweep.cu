@@ -930,6 +930,13 @@ __device__ __forceinline__ void ws_ld_poll2(const unsigned long long *p, unsigne
 __device__ __forceinline__ void ws_st_publish2(unsigned long long *p, unsigned long long a, unsigned long long b) {
   asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(a), "l"(b) : "memory");
 }
+// the same through the L2 atomic unit (16-byte exchange): developer experiment, HIFIR_B200_MRHS_PUBLISH_ATOM=1
+__device__ __forceinline__ void ws_atom_publish2(unsigned long long *p, unsigned long long a, unsigned long long b) {
+  asm volatile(
+      "{\n\t.reg .b128 v, o;\n\tmov.b128 v, {%1, %2};\n\tatom.relaxed.gpu.global.exch.b128 o, [%0], v;\n\t}" ::"l"(p),
+      "l"(a), "l"(b)
+      : "memory");
+}
 __device__ __forceinline__ bool ws_ready2(unsigned long long a, unsigned long long b, unsigned parity) {
   return !(((static_cast<unsigned>(a) ^ parity) | (static_cast<unsigned>(b) ^ parity)) & 1u);
 }
@@ -1165,7 +1172,10 @@ __global__ void __launch_bounds__(24 * 32, 1) wsweep_cols_kernel(const WsParams 
           }
           if (head) {
             const unsigned tag = last ? parity : (parity ^ 1u);  // parked partial sums: the other tag
-            ws_st_publish2(xw + static_cast<std::size_t>(slot) * NC + cp, tag_set(a0, tag), tag_set(a1, tag));
+            if (P.publish_st)
+              ws_st_publish2(xw + static_cast<std::size_t>(slot) * NC + cp, tag_set(a0, tag), tag_set(a1, tag));
+            else
+              ws_atom_publish2(xw + static_cast<std::size_t>(slot) * NC + cp, tag_set(a0, tag), tag_set(a1, tag));
           }
           keep ^= static_cast<unsigned>(__double2hiint(a0));
         }
@@ -1402,7 +1412,7 @@ void launch_ws_sweep_cols(Handle *h, const SweepPlan &plan, const double *rhs_pl
   P.parity     = parity;
   P.window     = plan.ws_window;
   P.adm_sleep  = static_cast<unsigned>(std::max(0, ws_env("HIFIR_B200_WS_SLEEP", 200)));
-  P.publish_st = 1;
+  P.publish_st = ws_env("HIFIR_B200_MRHS_PUBLISH_ATOM", 0) ? 0 : 1;
   P.l1_first   = 0;
   P.spin_limit = static_cast<unsigned>(std::max(1000, ws_env("HIFIR_B200_WS_SPIN_LIMIT", 1 << 21)));
   P.poll_sleep = static_cast<unsigned>(std::max(0, ws_env("HIFIR_B200_MRHS_POLL_SLEEP", 0)));
