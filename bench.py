@@ -401,7 +401,17 @@ def pin_to_gpu_numa(local_rank):
         bus = out[-12:] if len(out) >= 12 else out  # 0000:xx:yy.z
         node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read())
         if node < 0:
-            return "numa node unknown"
+            # virtualised boxes do not expose the PCI device's node: ask NVML for the cores next to the GPU
+            import pynvml
+            pynvml.nvmlInit()
+            hdl = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+            words = pynvml.nvmlDeviceGetCpuAffinity(hdl, ((os.cpu_count() or 64) + 63) // 64)
+            cpus = [64 * w + b for w, word in enumerate(words) for b in range(64) if (word >> b) & 1]
+            allowed = sorted(set(cpus) & os.sched_getaffinity(0))
+            if allowed and len(allowed) < len(os.sched_getaffinity(0)):
+                os.sched_setaffinity(0, allowed)
+                return f"nvml cpu affinity, {len(allowed)} cores ({allowed[0]}-{allowed[-1]})"
+            return f"numa node unknown (nvml affinity = all {len(allowed)} allowed cores)"
         cpus = []
         for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
             lo, _, hi = part.partition("-")
