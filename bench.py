@@ -367,7 +367,7 @@ def run_mrhs(args, rank, world, local_rank):
                "sample": f"{ncols} of the {nrhs} columns, one hif::HIF::solve each on the same factorized object "
                          f"({dt:.1f} s; serial reference code, one object = one thread, builder.hpp:579)"}
     nloc0 = max(1, shard_range(nrhs, world, 0)[1])
-    width = 64 if nloc0 >= 64 else 32 if nloc0 > 16 else 16  # mrhs.cu: apply_mrhs_dev
+    width = 64 if nloc0 >= 64 else 32 if nloc0 > 16 else 16 if nloc0 > 8 else 8  # mrhs.cu: apply_mrhs_dev
     chunks = -(-nloc0 // width)
     bytes_step = world * (st["bytes_factors"] + st["bytes_dense"]) + nrhs * st["bytes_vec_per_rhs"]
     line = {

@@ -391,8 +391,8 @@ void apply_mrhs_dev(Handle *h, std::size_t nrhs, const double *d_B, double *d_X,
   for (const DevLevel &D : h->levels) fused = fused && (!D.m || (D.LU.nblocks && D.LU.ws_warps == 24u && D.LU.ws_stages == 2u));
   if (fused) {
     const std::size_t n = h->n0();
-    // one internal width per call: the widest pass that the block fills (narrow blocks: 16 columns)
-    const unsigned nc = nrhs >= 64u && wide_max >= 64 ? 64u : nrhs > 16u && wide_max >= 32 ? 32u : 16u;
+    // one internal width per call: the widest pass that the block fills (narrow blocks: 16 or 8 columns)
+    const unsigned nc = nrhs >= 64u && wide_max >= 64 ? 64u : nrhs > 16u && wide_max >= 32 ? 32u : nrhs > 8u ? 16u : 8u;
     if (static_cast<unsigned long long>(n) * std::max<std::size_t>(nc, nrhs) > 0xffffffffull) throw std::length_error("multi-rhs block too large");
     ensure_cols(h, nc);
     try {

@@ -909,7 +909,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) wsweep_kernel(const WsParams P
 // ---- multi-rhs: the same warp streams, lanes ACROSS the columns -------------------------------
 // Row-interleaved blocks X[slot * NC + c] (the Array<std::array<T,Nrhs>> layout of
 // hif::HIF::solve_mrhs, builder.hpp:433-445; per-column arithmetic = CCS::solve_as_strict_lower /
-// _upper_mrhs, CompressedStorage.hpp:2286-2301, 2376-2393).  NC = 2 G columns, G in {8, 16, 32}.
+// _upper_mrhs, CompressedStorage.hpp:2286-2301, 2376-2393).  NC = 2 G columns, G in {4, 8, 16, 32}.
 //
 // The single-rhs kernel gives every lane its own entries: 32 scattered 8-byte gathers per instruction,
 // one L1 wavefront each -- that is its throughput bound.  With NC columns the unit of dependency is a
@@ -1381,18 +1381,20 @@ void launch_ws_cols_G(Handle *h, const SweepPlan &plan, const WsParams &P) {
 }
 template <class VT>
 void launch_ws_cols_V(Handle *h, const SweepPlan &plan, const WsParams &P, unsigned nc) {
-  if (nc == 16u)
+  if (nc == 8u)
+    launch_ws_cols_G<VT, 4>(h, plan, P);
+  else if (nc == 16u)
     launch_ws_cols_G<VT, 8>(h, plan, P);
   else if (nc == 32u)
     launch_ws_cols_G<VT, 16>(h, plan, P);
   else if (nc == 64u)
     launch_ws_cols_G<VT, 32>(h, plan, P);
   else
-    throw std::logic_error("multi-rhs sweep: 16, 32 or 64 columns per pass");
+    throw std::logic_error("multi-rhs sweep: 8, 16, 32 or 64 columns per pass");
 }
 }  // namespace
 
-// multi-rhs LDU solve on the fused warp-stream plan of a level: nc in {16, 32, 64} columns, row-interleaved
+// multi-rhs LDU solve on the fused warp-stream plan of a level: nc in {8, 16, 32, 64} columns, row-interleaved
 void launch_ws_sweep_cols(Handle *h, const SweepPlan &plan, const double *rhs_plain, const double *diag, unsigned long long *xL,
                           unsigned long long *xU, unsigned parity, int *sync, unsigned nc) {
   if (!plan.nblocks) return;

@@ -24,7 +24,7 @@ def main():
     G.set_stream(side.cuda_stream)
     st = G.stats()
     print("HIFIR_B200_MRHS_WIDE", os.environ.get("HIFIR_B200_MRHS_WIDE"), "HIFIR_B200_MRHS_BATCH", os.environ.get("HIFIR_B200_MRHS_BATCH"))
-    for nrhs in (1, 16, 32, 64):
+    for nrhs in (1, 8, 16, 32, 64):
         B = torch.from_numpy(P.seeded_rhs(n, 0, nrhs=nrhs)).cuda() if nrhs > 1 else torch.from_numpy(P.seeded_rhs(n, 0)).cuda()
         X = torch.empty_like(B)
         for _ in range(2):
