@@ -288,6 +288,7 @@ struct Handle {
   DevBuf<double>             kr_mpart;
   DevBuf<unsigned long long> kr_bar;
   unsigned long long         kr_bar_base = 0;
+  bool                       kr_no_coop  = false;  // the cooperative launch was refused once: per-step kernels from then on
   double *       h_scal = nullptr;  // pinned
   int            kr_restart = 0;
   // multi-rhs column staging

@@ -440,7 +440,8 @@ void krylov_dev(Handle *h, bool flexible, const double *d_b, int restart, double
       const unsigned    pgrid  = static_cast<unsigned>(std::max(1, h->num_sms));
       const unsigned    pslice = cdiv(n, pgrid);
       const std::size_t psmem  = static_cast<std::size_t>(pslice) * sizeof(double);
-      const bool        persist = fused_mgs && persist_mgs && psmem <= 200u * 1024u;
+      const bool        persist = fused_mgs && persist_mgs && !h->kr_no_coop && psmem <= 200u * 1024u;
+      bool              launched = false;
       if (persist) {
         if (h->kr_mpart.n < static_cast<std::size_t>(restart + 2) * pgrid)
           h->kr_mpart.alloc(static_cast<std::size_t>(restart + 2) * pgrid, &h->device_bytes);
@@ -453,12 +454,28 @@ void krylov_dev(Handle *h, bool flexible, const double *d_b, int restart, double
           HIF_CUDA(cudaFuncSetAttribute(mgs_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
           if (h->device < 64) configured[h->device] = true;
         }
-        double *qout = j + 1 < restart ? Q + static_cast<std::size_t>(j + 1) * n : nullptr;
-        mgs_persistent_kernel<<<pgrid, kMT, psmem, h->stream>>>(un, static_cast<unsigned>(j), pslice, Q, v, qout, d_w2,
-                                                               d_w2 + restart, h->kr_mpart.p, h->kr_bar.p, h->kr_bar_base);
-        HIF_KERNEL_CHECK();
-        h->kr_bar_base += static_cast<unsigned long long>(j + 2) * pgrid;
-        ++h->launch_count;
+        // a COOPERATIVE launch: the runtime refuses it when the grid can not be resident at once (the barrier
+        // would never complete) -- then, and from then on, the per-step kernels do the work
+        double *           qout = j + 1 < restart ? Q + static_cast<std::size_t>(j + 1) * n : nullptr;
+        unsigned           a_n = un, a_j = static_cast<unsigned>(j), a_slice = pslice;
+        const double *     a_Q = Q, *a_v = v;
+        double *           a_coef = d_w2, *a_nrm = d_w2 + restart, *a_part = h->kr_mpart.p;
+        unsigned long long *a_bar = h->kr_bar.p, a_base = h->kr_bar_base;
+        void *args[] = {&a_n, &a_j, &a_slice, &a_Q, &a_v, &qout, &a_coef, &a_nrm, &a_part, &a_bar, &a_base};
+        const cudaError_t e = cudaLaunchCooperativeKernel(reinterpret_cast<const void *>(mgs_persistent_kernel), dim3(pgrid),
+                                                          dim3(kMT), args, psmem, h->stream);
+        if (e == cudaSuccess) {
+          h->kr_bar_base += static_cast<unsigned long long>(j + 2) * pgrid;
+          ++h->launch_count;
+          launched = true;
+        } else if (e == cudaErrorCooperativeLaunchTooLarge || e == cudaErrorNotSupported || e == cudaErrorInvalidConfiguration) {
+          cudaGetLastError();
+          h->kr_no_coop = true;
+        } else {
+          HIF_CUDA(e);
+        }
+      }
+      if (launched) {
       } else if (fused_mgs) {
         dot_to(h, n, v, Q, d_w2);
         for (int k = 0; k <= j; ++k) {
@@ -479,7 +496,7 @@ void krylov_dev(Handle *h, bool flexible, const double *d_b, int restart, double
         }
         dot_to(h, n, v, v, d_w2 + restart);
       }
-      if (!persist && j + 1 < restart) {
+      if (!launched && j + 1 < restart) {
         div_dev_kernel<<<kEW, kRT, 0, h->stream>>>(un, v, d_w2 + restart, true, Q + static_cast<std::size_t>(j + 1) * n);
         HIF_KERNEL_CHECK();
         ++h->launch_count;
