@@ -382,8 +382,6 @@ void launch_ws_sweep(Handle *h, const SweepPlan &plan, const double *rhs_plain, 
 void build_ws_ldu_plan(const HostCsr &SL, const HostCsr &SU, SweepPlan &plan, SweepPlan &L, SweepPlan &U, std::size_t *tally,
                        unsigned nsm);
 void ws_debug_graph(const HostCsr &S, unsigned nsm, std::vector<unsigned> &dep_ptr, std::vector<unsigned> &dep_idx);
-void build_ws_plan_for(const HostCsr &Tnat, bool upper, SweepPlan &plan, std::size_t *tally, unsigned nsm,
-                       const unsigned *rhs_index, unsigned warps, unsigned stages);  // merge + pack (sweep.cu)
 int  sweep_kind();  // HIFIR_B200_SWEEP = ws (default) | stream | slab  ->  2 | 1 | 0
 
 // ---- planlab.cu (developer tool, host only)

@@ -196,7 +196,6 @@ void ensure_cols(Handle *h, std::size_t nc) {
   if (h->wide_cap < nc) {
     for (DevLevel &D : h->levels) {
       D.m_bhat.alloc(D.n * nc, tally);
-      D.m_g.alloc(D.m * nc, tally);
       D.m_r.alloc(D.nm * nc, tally);
       D.m_ychild.alloc(D.nm * nc, tally);
       // m solution slots + m slots for the auxiliary unknowns of merge.cu, nc values each
@@ -235,6 +234,8 @@ void ensure_mrhs(Handle *h) {
     h->mrhs_ready = true;
   }
   ensure_cols(h, NR);
+  for (DevLevel &D : h->levels)  // only these passes keep g = bhat - F y in a buffer of its own
+    if (D.m_g.n < D.m * NR) D.m_g.alloc(D.m * NR, &h->device_bytes);
 }
 
 }  // namespace

@@ -35,20 +35,6 @@ void build_sweep_plan(const HostCsr &Tnat, bool upper, SweepPlan &plan, std::siz
   plan.merge = ms;
 }
 
-// merged factor -> warp-stream plan with an explicit kernel configuration (the multi-rhs kernel's)
-void build_ws_plan_for(const HostCsr &Tnat, bool upper, SweepPlan &plan, std::size_t *tally, unsigned nsm,
-                       const unsigned *rhs_index, unsigned warps, unsigned stages) {
-  plan.m       = static_cast<unsigned>(Tnat.nrows);
-  plan.upper   = upper;
-  plan.nblocks = 0;
-  plan.nr      = 1;
-  if (!plan.m) return;
-  const MergeParams mp = MergeParams::from_env();
-  HostCsr           T  = merged_sweep_form(Tnat, upper, mp, &plan.merge);
-  const MergeStats  ms = plan.merge;
-  build_ws_plan(T, upper, plan, tally, nsm, rhs_index, warps, stages);
-  plan.merge = ms;
-}
 
 // CPU emulation of a sweep on the packed data -- lets the host-side merging + packing be tested
 // without a GPU (tests/test_abi.py)
