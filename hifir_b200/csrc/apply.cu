@@ -278,14 +278,17 @@ void launch_spmv_resid(Handle *h, const DevCsr &A, const int *col, const void *x
 }  // namespace
 
 namespace {
-void apply_schedule(Handle *h, const double *d_b, double *d_x, std::size_t rank, unsigned parity);
+// parts of the schedule: the only kernel that reads the caller's b (level-0 gather), the only ones that write
+// the caller's x (level-0 scatter, null-space filter), and everything in between (handle-internal buffers only)
+constexpr unsigned kHead = 1u, kBody = 2u, kTail = 4u;
+void apply_schedule(Handle *h, const double *d_b, double *d_x, std::size_t rank, unsigned parity, unsigned parts);
 }
 void apply_dev_impl(Handle *h, const double *d_b, double *d_x, std::size_t rank);
 void reset_tagged_state(Handle *h);
 
-// The schedule of one apply is static: the second apply with the same (b, x, rank, tag parity, filter)
-// captures it into a CUDA graph, every later one is a single graph launch (the kernels of an apply
-// are short -- 8 to 160 us -- and there are a dozen and a half of them).
+// The schedule of one apply is static and only its first and last kernels touch the caller's vectors: the
+// kernels in between are captured into a CUDA graph per (rank, tag parity) and replayed for every b and x
+// (the kernels of an apply are short -- 8 to 270 us -- and there are 14 of them).
 void apply_dev(Handle *h, const double *d_b, double *d_x, std::size_t rank) {
   try {
     apply_dev_impl(h, d_b, d_x, rank);
@@ -303,45 +306,44 @@ void apply_dev_impl(Handle *h, const double *d_b, double *d_x, std::size_t rank)
     const char *e = std::getenv("HIFIR_B200_GRAPH");
     return !e || std::atoi(e) != 0;
   }();
+  const std::size_t launches0 = h->launch_count;
   if (!graphs_on || h->graphs_off || h->profiling || h->trace_level >= 0) {
-    apply_schedule(h, d_b, d_x, rank, parity);
+    apply_schedule(h, d_b, d_x, rank, parity, kHead | kBody | kTail);
+    h->kernels_per_apply = h->launch_count - launches0;
     return;
   }
+  // The graph holds the BODY of the schedule -- every kernel between the level-0 gather (the only reader of b)
+  // and the level-0 scatter / null-space filter (the only writers of x) -- so one graph per (rank, tag parity)
+  // serves every pair of vectors: the basis vectors of FGMRES, the staging slots of the pipelined host
+  // solves, a refinement loop.  Capturing and instantiating costs ~1.7 ms, a graph launch saves ~30 us: the
+  // body is captured on the third use of its key.
   ApplyGraph *g = nullptr;
   for (ApplyGraph &c : h->graphs)
-    if (c.b == d_b && c.x == d_x && c.rank == rank && c.parity == parity && c.nsp_on == h->nsp_on &&
-        c.nsp_start == h->nsp_start && c.nsp_end == h->nsp_end)
-      g = &c;
+    if (c.rank == rank && c.parity == parity) g = &c;
   if (!g) {
     if (h->graphs.size() >= 256) clear_apply_graphs(h);
-    h->graphs.push_back(ApplyGraph{d_b, d_x, rank, parity, h->nsp_on, h->nsp_start, h->nsp_end, 0, nullptr, 0, 0});
+    h->graphs.push_back(ApplyGraph{nullptr, nullptr, rank, parity, false, 0, 0, 0, nullptr, 0, 0});
     g = &h->graphs.back();
   }
-  // Capturing and instantiating costs ~1.7 ms (measured), a graph launch saves ~30 us: only a key that
-  // RECURS at short intervals -- the same vectors applied over and over, as in a solver's refinement
-  // loop or a stream of host-buffer solves through the two staging slots -- is captured, on its third
-  // use.  FGMRES, which walks through 2 x restart different basis vectors, keeps launching eagerly.
-  if (!g->exec) {
-    const bool recent = g->uses > 0 && h->epoch - g->last_epoch <= 16u;
-    g->uses           = recent ? g->uses + 1u : 1u;
-    g->last_epoch     = h->epoch;
-    if (g->uses < 3u) {
-      apply_schedule(h, d_b, d_x, rank, parity);
-      return;
-    }
+  if (!g->exec && ++g->uses < 3u) {
+    apply_schedule(h, d_b, d_x, rank, parity, kHead | kBody | kTail);
+    h->kernels_per_apply = h->launch_count - launches0;
+    return;
   }
+  apply_schedule(h, d_b, d_x, rank, parity, kHead);
   if (!g->exec) {
-    const std::size_t launches0 = h->launch_count;
+    const std::size_t body0 = h->launch_count;
     cudaGraph_t       graph = nullptr;
     if (cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
       // e.g. the legacy default stream can not be captured: this handle launches its kernels one by one
       cudaGetLastError();
       h->graphs_off = true;
-      apply_schedule(h, d_b, d_x, rank, parity);
+      apply_schedule(h, d_b, d_x, rank, parity, kBody | kTail);
+      h->kernels_per_apply = h->launch_count - launches0;
       return;
     }
     try {
-      apply_schedule(h, d_b, d_x, rank, parity);
+      apply_schedule(h, d_b, d_x, rank, parity, kBody);
     } catch (...) {
       cudaStreamEndCapture(h->stream, &graph);
       if (graph) cudaGraphDestroy(graph);
@@ -351,12 +353,13 @@ void apply_dev_impl(Handle *h, const double *d_b, double *d_x, std::size_t rank)
     const cudaError_t e = cudaGraphInstantiate(&g->exec, graph, 0);
     cudaGraphDestroy(graph);
     cuda_check(e, "cudaGraphInstantiate", __FILE__, __LINE__);
-    g->launches     = h->launch_count - launches0;
-    h->launch_count = launches0;
+    g->launches     = h->launch_count - body0;
+    h->launch_count = body0;
   }
   HIF_CUDA(cudaGraphLaunch(g->exec, h->stream));
   h->launch_count += g->launches;
-  h->kernels_per_apply = g->launches;
+  apply_schedule(h, d_b, d_x, rank, parity, kTail);
+  h->kernels_per_apply = h->launch_count - launches0;
 }
 
 // An apply that failed half way (launch error, exception) has bumped the epoch but rewritten only some
@@ -383,32 +386,34 @@ void clear_apply_graphs(Handle *h) {
 }
 
 namespace {
-void apply_schedule(Handle *h, const double *d_b, double *d_x, std::size_t rank, unsigned parity) {
-  const std::size_t nl = h->levels.size();
-  const std::size_t launches0 = h->launch_count;
-  HIF_CUDA(cudaMemsetAsync(h->tickets.p, 0, h->tickets.n * sizeof(int), h->stream));
+void apply_schedule(Handle *h, const double *d_b, double *d_x, std::size_t rank, unsigned parity, unsigned parts) {
+  const std::size_t nl   = h->levels.size();
+  const bool        body = (parts & kBody) != 0u;
+  if (body) HIF_CUDA(cudaMemsetAsync(h->tickets.p, 0, h->tickets.n * sizeof(int), h->stream));
   constexpr int T = 256;
-  mark(h, "begin");
+  if (parts & kHead) mark(h, "begin");
 
   // ---- down-sweep
   const double *b = d_b;
   for (std::size_t l = 0; l < nl; ++l) {
     DevLevel &D = h->levels[l];
-    if (D.n) {
+    if (D.n && (parts & (l == 0 ? kHead : kBody))) {
       gather_scale_kernel<<<cdiv(D.n, T), T, 0, h->stream>>>(static_cast<unsigned>(D.n), D.p.p, D.sp.p, b, D.bhat.p);
       HIF_KERNEL_CHECK();
       mark(h, "lv" + std::to_string(l) + ".gather");
       ++h->launch_count;
     }
     if (D.nm) {
-      launch_sweeps(h, D, D.bhat.p, D.xL_dn.p, D.xU_dn.p, parity, h->tick(8 * l), "lv" + std::to_string(l) + ".down.", 0);
-      launch_spmv_resid<true>(h, D.E, D.E_xcol.p, D.xU_dn.p, D.bhat.p + D.m, D.r.p, "lv" + std::to_string(l) + ".E");
+      if (body) {
+        launch_sweeps(h, D, D.bhat.p, D.xL_dn.p, D.xU_dn.p, parity, h->tick(8 * l), "lv" + std::to_string(l) + ".down.", 0);
+        launch_spmv_resid<true>(h, D.E, D.E_xcol.p, D.xU_dn.p, D.bhat.p + D.m, D.r.p, "lv" + std::to_string(l) + ".E");
+      }
       b = D.r.p;
     }
   }
   // ---- dense last level (QRCP.hpp:370-411); rank: 0 -> numerical, > nm -> nm
   DevLevel &last = h->levels[nl - 1];
-  if (last.nm) {
+  if (last.nm && body) {
     dense_solve_dev(h, last.r.p, last.ychild.p, rank);
     mark(h, "dense");
   }
@@ -417,15 +422,15 @@ void apply_schedule(Handle *h, const double *d_b, double *d_x, std::size_t rank,
     DevLevel &    D      = h->levels[l];
     double *      y      = l == 0 ? d_x : h->levels[l - 1].ychild.p;
     const double *rhs    = D.bhat.p;
-    if (D.nm && D.F_rows.n) {
+    if (D.nm && D.F_rows.n && body) {
       spmv_sub_rows_kernel<<<cdiv(D.F_rows.n, T), T, 0, h->stream>>>(static_cast<unsigned>(D.F_rows.n), D.F_rows.p, D.F_cptr.p,
                                                                      D.F.col.p, D.F.val.p, D.ychild.p, D.bhat.p);
       HIF_KERNEL_CHECK();
       mark(h, "lv" + std::to_string(l) + ".F");
       ++h->launch_count;
     }
-    launch_sweeps(h, D, rhs, D.xL_up.p, D.xU_up.p, parity, h->tick(8 * l + 2), "lv" + std::to_string(l) + ".up.", 2);
-    if (D.n) {
+    if (body) launch_sweeps(h, D, rhs, D.xL_up.p, D.xU_up.p, parity, h->tick(8 * l + 2), "lv" + std::to_string(l) + ".up.", 2);
+    if (D.n && (parts & (l == 0 ? kTail : kBody))) {
       scatter_scale_kernel<<<cdiv(D.n, T), T, 0, h->stream>>>(static_cast<unsigned>(D.n), D.q_slot.p, D.t.p,
                                                              D.xU_up.p, D.ychild.p, y);
       HIF_KERNEL_CHECK();
@@ -434,7 +439,7 @@ void apply_schedule(Handle *h, const double *d_b, double *d_x, std::size_t rank,
     }
   }
   // ---- null-space filter (builder.hpp:419-420)
-  if (h->nsp_on) {
+  if (h->nsp_on && (parts & kTail)) {
     const std::size_t n     = h->n0();
     std::size_t       start = h->nsp_start, end = h->nsp_end;
     if (end == static_cast<std::size_t>(-1) || end < start) end = n;
@@ -451,7 +456,6 @@ void apply_schedule(Handle *h, const double *d_b, double *d_x, std::size_t rank,
       h->launch_count += 2;
     }
   }
-  h->kernels_per_apply = h->launch_count - launches0;
 }
 }  // namespace
 
